@@ -1,0 +1,196 @@
+/*
+ * bittoss_b200.h — C ABI of the B200-native bittoss physics hot path.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no C++/torch types.
+ * A bittoss host keeps its own `ent` / `gamestate` / `catalog<T>` (ent.h,
+ * handlerRegistrar.h) and calls these entry points instead of the CPU tick
+ * functions.  Every entry point names the reference interface it replaces
+ * (file:line inside the sboerwinkle/bittoss tree).  INTEGRATION.md shows the
+ * host-side binding.
+ *
+ * All functions return 0 (BT_OK) or a negative BT_ERR_* code; CUDA failures
+ * return BT_ERR_CUDA and the text is available from bt_last_error().  There is
+ * no CPU fallback: without a usable CUDA device every compute entry point
+ * fails with BT_ERR_NO_DEVICE.
+ */
+#ifndef BITTOSS_B200_H
+#define BITTOSS_B200_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BT_OK 0
+#define BT_ERR_NO_DEVICE (-1)   /* no CUDA device / driver                        */
+#define BT_ERR_CUDA (-2)        /* a CUDA call failed, see bt_last_error()        */
+#define BT_ERR_ARG (-3)         /* bad argument (NULL, negative size, ...)        */
+#define BT_ERR_CAPACITY (-4)    /* world does not fit the capacities given        */
+#define BT_ERR_UNSUPPORTED (-5) /* handler id with no device-side implementation  */
+#define BT_ERR_OVERFLOW (-6)    /* a device work list overflowed its buffer       */
+
+/* Index of each handler slot inside bt_world_desc.handlers (10 bytes / entity).
+ * Values are the catalog IDs of handlerRegistrar.h:79-187, i.e. exactly what
+ * serialize.cpp:146-161 writes into a .sav file. */
+enum {
+	BT_H_WHOMOVES = 0, /* whoMovesHandlers  (handlerRegistrar.h:79-90)   */
+	BT_H_TICK,         /* tickHandlers      (:93-138) host-side only     */
+	BT_H_TICKHELD,     /* tickHandlers                                    */
+	BT_H_CRUSH,        /* crushHandlers     (:141-146)                    */
+	BT_H_PUSH,         /* pushHandlers      (:163-175)                    */
+	BT_H_PUSHED,       /* pushedHandlers    (:149-160)                    */
+	BT_H_ONFUMBLE,     /* entPairHandlers   (:178-187)                    */
+	BT_H_ONFUMBLED,
+	BT_H_ONPICKUP,
+	BT_H_ONPICKEDUP,
+	BT_H_NUM
+};
+
+/* bt_world_desc.misc bytes (4 / entity) */
+enum { BT_M_NEWDROP = 0, BT_M_DEADMAX0, BT_M_DEADMAX1, BT_M_FULLFLUSH, BT_M_NUM };
+
+/*
+ * Host-side structure-of-arrays image of one or more gamestates
+ * (`struct gamestate` ent.h:182-194, `struct ent_blueprint` ent.h:71-165).
+ *
+ * Entities are the LIVE ones, oldest first: index i is the entity's `.sav`
+ * index (serialize.cpp:79-94), i.e. its rank counted from the tail of
+ * gs->ents.  Every entity reference (holder, wires, ...) is such an index,
+ * -1 for NULL.  vec3 arrays are xyz-interleaved, length 3*n_ents.
+ * Several independent worlds may be concatenated (world_id non-NULL): all
+ * entities of one world are contiguous and references stay inside a world.
+ */
+typedef struct bt_world_desc {
+	int32_t n_ents;
+	int32_t n_sliders;   /* total, == slider_off[n_ents] */
+	int32_t n_wires;     /* total, == wire_off[n_ents]   */
+	int32_t n_worlds;    /* >= 1                          */
+
+	/* per world [n_worlds]  (gamestate scalars) */
+	int32_t *w_flip_flop; /* gs->flipFlop_death */
+	int32_t *w_gamerules; /* gs->gamerules (EFFECT_* bits, effects.h:8-17) */
+	int32_t *w_rand;      /* gs->rand (carried, not used on the path)     */
+
+	/* per entity [n_ents] unless noted */
+	int32_t *world_id;    /* may be NULL when n_worlds == 1 */
+	int32_t *uid;         /* caller-chosen stable id (unique inside a world); hashed */
+	int32_t *center, *vel, *old, *d_center, *d_vel, *radius; /* [3*n_ents] */
+	uint32_t *type_mask, *collide_mask, *new_type_mask, *new_collide_mask;
+	int32_t *friction;
+	int32_t *holder;      /* e->holder                                      */
+	int32_t *hold_flags;  /* e->holdFlags                                   */
+	int32_t *holdee_head; /* e->holdee (first of the holdee list)           */
+	int32_t *holdee_next; /* e->LL.n when held (next sibling), else -1      */
+	int32_t *root_order;  /* position in gs->rootEnts (0 = head) for roots, -1 when held */
+	int32_t *new_holder;  /* e->newHolder                                   */
+	int32_t *new_hold_flags;
+	uint8_t *handlers;    /* [BT_H_NUM*n_ents] catalog IDs                  */
+	uint8_t *btn;         /* [8*n_ents] ctrl.btns[0..3].v then [0..3].v2    */
+	uint8_t *misc;        /* [BT_M_NUM*n_ents] newDrop, dead_max[0..1], fullFlush */
+	int32_t *slider_off;  /* [n_ents+1] CSR offsets into slider_*           */
+	int32_t *slider_v, *slider_min, *slider_max; /* [n_sliders]            */
+	int32_t *wire_off;    /* [n_ents+1] CSR offsets into wire_to            */
+	int32_t *wire_to;     /* [n_wires] e->wires[k] in list order            */
+} bt_world_desc;
+
+/* Phases of one simulation step, in reference order (main.cpp:1072-1097). */
+#define BT_PHASE_CTRLS   1u  /* flushCtrls part of doUpdates   ent.cpp:817-824 (tick handlers stay on the host) */
+#define BT_PHASE_PREP    2u  /* prepPhysics = flush1           ent.cpp:834,794-804 */
+#define BT_PHASE_GRAVITY 4u  /* doGravity when EFFECT_GRAV     effects.cpp:35-41   */
+#define BT_PHASE_PHYSICS 8u  /* doPhysics                      ent.cpp:842-911     */
+#define BT_PHASE_FINISH 16u  /* finishStep = clearDeads        ent.cpp:913-915     */
+#define BT_PHASE_ALL    31u
+
+typedef struct bt_tick_stats {
+	int64_t ticks;
+	int64_t iterations;      /* doIteration rounds that found a collision (ent.cpp:866) */
+	int64_t candidate_pairs; /* broadphase pairs handed to the narrow phase              */
+	int64_t positives;       /* getAxisAndDir != 0 (ent.cpp:403-404)                     */
+	int64_t pushes;          /* push() calls (ent.cpp:881)                               */
+	int64_t serial_pushes;   /* of those, run in the serial tie/cycle lane               */
+	int64_t crushes;         /* crushEnt during resolution (ent.cpp:211)                 */
+	int64_t fumbles;         /* fumble() (ent.cpp:136)                                   */
+	int64_t kernel_launches; /* CUDA kernels launched by this library                    */
+	int64_t tree_builds;     /* full Morton sort + LBVH builds                           */
+	int64_t tree_refits;     /* bottom-up refits                                         */
+	int64_t live_ents;       /* live entities after the last tick                        */
+	int64_t entity_ticks;    /* sum over ticks of live entities after the tick           */
+} bt_tick_stats;
+
+/* Per-kernel-class device timing, filled only while profiling is enabled. */
+#define BT_PROF_MAX 24
+typedef struct bt_profile {
+	int32_t n;                      /* number of kernel classes */
+	const char *name[BT_PROF_MAX];
+	int64_t launches[BT_PROF_MAX];
+	double ms[BT_PROF_MAX];         /* summed CUDA-event time */
+} bt_profile;
+
+typedef struct bt_world bt_world; /* opaque, owns device memory + one stream */
+
+/* ---- library ---- */
+const char *bt_version(void);
+const char *bt_last_error(void);
+int bt_device_count(void); /* >=0, or BT_ERR_NO_DEVICE */
+
+/* ---- world lifecycle: replaces mkGamestate/resetGamestate/doCleanup (ent.h:216-218),
+ *      addEnt (ent.h:206) and velbox_init/getRoot/freeRoot (velbox/box.h:72-75) ---- */
+int bt_world_create(bt_world **out, int device, int32_t max_ents, int32_t max_sliders,
+                    int32_t max_wires, int32_t max_worlds);
+void bt_world_destroy(bt_world *w);
+/* Host AoS -> device SoA. Fails with BT_ERR_UNSUPPORTED if an entity names a
+ * collision-path handler ID that has no device implementation. */
+int bt_world_upload(bt_world *w, const bt_world_desc *desc);
+/* Sizes needed to download the current live state. */
+int bt_world_count(bt_world *w, int32_t *n_ents, int32_t *n_sliders, int32_t *n_wires);
+/* Device SoA -> host arrays (caller-allocated, sized from bt_world_count; the
+ * n_* fields are overwritten with what was written).  Dead entities are gone,
+ * order is oldest-first as in bt_world_desc. */
+int bt_world_download(bt_world *w, bt_world_desc *out);
+
+/* ---- the tick: replaces doUpdates(flushCtrls)/prepPhysics/doPhysics/finishStep
+ *      (ent.h:212-215, called from doWholeStep main.cpp:1072-1097) ---- */
+int bt_world_step(bt_world *w, uint32_t phases);
+/* n_ticks whole steps (BT_PHASE_ALL) with the world resident on the device.
+ * hashes: NULL, or [n_ticks*n_worlds] receiving the state hash after each tick. */
+int bt_world_tick(bt_world *w, int32_t n_ticks, uint64_t *hashes);
+/* Same as bt_world_tick but only enqueues on the world's stream (no host sync,
+ * no hash readback) so a caller can bracket it with its own CUDA events. */
+int bt_world_tick_async(bt_world *w, int32_t n_ticks);
+int bt_world_sync(bt_world *w);
+void *bt_world_stream(bt_world *w); /* the cudaStream_t every kernel of w runs on */
+
+/* Commutative 64-bit state hash per world over (uid, center, vel, typeMask,
+ * collideMask, holder uid, holdFlags) of every live entity, plus live count.
+ * out: [n_worlds]. */
+int bt_world_hash(bt_world *w, uint64_t *out);
+int bt_world_stats(bt_world *w, bt_tick_stats *out, int reset);
+int bt_world_profile_enable(bt_world *w, int on);
+int bt_world_profile_read(bt_world *w, bt_profile *out, int reset);
+/* Tuning knobs (integers): "rebuild_every" ticks between full LBVH rebuilds. */
+int bt_world_set_option(bt_world *w, const char *name, int64_t value);
+
+/* ---- raycast: replaces selectCast(gs, parent, look) (raycast.h:1, raycast.cpp:16-57),
+ *      batched.  origin_ent[i] = index of the casting entity (its hold tree is skipped),
+ *      look = 3 ints per ray (NOT modified, unlike the reference which sign-folds it
+ *      in place), winner[i] = entity index of the nearest hit or -1.  Indices refer to
+ *      the live, oldest-first order of bt_world_download. Host buffers. ---- */
+int bt_raycast_batch(bt_world *w, const int32_t *origin_ent, const int32_t *look, int32_t n_rays,
+                     int32_t *winner);
+/* Same with device-resident buffers, enqueued on the world's stream. */
+int bt_raycast_batch_device(bt_world *w, const int32_t *d_origin_ent, const int32_t *d_look,
+                            int32_t n_rays, int32_t *d_winner);
+int bt_raycast_build(bt_world *w); /* (re)build the all-entity tree used by raycasts */
+
+/* ---- synthetic worlds (BASELINE.json configs[2]): fills a caller-allocated desc.
+ *      bt_synth_boxstack_size gives the array sizes. ---- */
+int bt_synth_boxstack_size(int32_t n_cubes, int32_t height, int32_t *n_ents);
+int bt_synth_boxstack_fill(bt_world_desc *desc, int32_t n_cubes, int32_t height, uint32_t seed,
+                           int32_t push_every, int32_t push_max);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
