@@ -18,7 +18,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.dirname(HERE))
 from bittoss_b200.desc import BtWorldDesc, WorldArrays  # noqa: E402  (plain buffer plumbing)
 
-REF_SO = os.path.join(HERE, "_ref", "libbtref.so")
+REF_SO = os.environ.get("BTREF_SO", os.path.join(HERE, "_ref", "libbtref.so"))
 REF_DATA_PARENT = os.path.join(HERE, "_ref")
 ORACLE_SO = os.path.join(HERE, "libbtoracle.so")
 
