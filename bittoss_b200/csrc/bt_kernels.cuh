@@ -1,0 +1,252 @@
+/*
+ * bt_kernels.cuh — __global__ wrappers around the per-thread bodies of bt_phys.cuh,
+ * plus the hand-written LSD radix sort used by the LBVH build.  sm_100a only.
+ *
+ * Grid sizing: every kernel is one thread per entity / leaf / node, 128 threads per
+ * block (4 warps), so 1 M entities = 7 813 blocks = 52.8 blocks per SM on 148 SMs,
+ * i.e. > 3 full waves at 16 resident blocks/SM.  All of these kernels are bound by
+ * HBM/L2 latency, not math; nothing here is a dense contraction, so no tensor cores.
+ */
+#ifndef BT_KERNELS_CUH
+#define BT_KERNELS_CUH
+
+#include "bt_phys.cuh"
+
+#define BT_BLOCK 128
+
+static __device__ __forceinline__ u32 warp_sum(u32 v) {
+	return __reduce_add_sync(0xffffffffu, v);
+}
+
+/* add a per-thread count into a 64-bit stat with one atomic per warp */
+static __device__ __forceinline__ void stat_add(const DevWorld &W, int which, u32 v) {
+	u32 s = warp_sum(v);
+	if ((threadIdx.x & 31) == 0 && s) atomicAdd(((u64 *)&W.ctr[CT_STAT0]) + which, (u64)s);
+}
+static __device__ __forceinline__ void stats_flush(const DevWorld &W, const LocalStats &st) {
+	stat_add(W, SK_CAND, st.cand);
+	stat_add(W, SK_POS, st.pos);
+	stat_add(W, SK_PUSH, st.push);
+	stat_add(W, SK_CRUSH, st.crush);
+	stat_add(W, SK_FUMBLE, st.fumble);
+}
+
+#define TID ((i32)(blockIdx.x * blockDim.x + threadIdx.x))
+
+__global__ void __launch_bounds__(BT_BLOCK) k_pre(DevWorld W, u32 phases) { t_pre(W, TID, phases); }
+__global__ void __launch_bounds__(BT_BLOCK) k_flush_scan(DevWorld W) { t_flush_scan(W, TID); }
+__global__ void __launch_bounds__(BT_BLOCK) k_flush_serial(DevWorld W) {
+	LocalStats st = {0, 0, 0, 0, 0};
+	t_flush_serial(W, TID, st);
+	stats_flush(W, st);
+}
+__global__ void __launch_bounds__(BT_BLOCK) k_flush_misc(DevWorld W) { t_flush_misc(W, TID); }
+__global__ void __launch_bounds__(BT_BLOCK) k_gravity(DevWorld W) { t_gravity(W, TID); }
+__global__ void __launch_bounds__(BT_BLOCK) k_flush2_apply(DevWorld W) { t_flush2_apply(W, TID); }
+__global__ void __launch_bounds__(BT_BLOCK) k_zero_deltas(DevWorld W) { t_zero_deltas(W, TID); }
+__global__ void __launch_bounds__(BT_BLOCK) k_integrate(DevWorld W) { t_integrate(W, TID); }
+
+__global__ void __launch_bounds__(BT_BLOCK) k_begin_fused(DevWorld W, int gravity) { t_begin_fused(W, TID, gravity); }
+
+__global__ void __launch_bounds__(BT_BLOCK) k_bounds(DevWorld W) {
+	/* warp-reduce before the atomics: 6 atomics per warp instead of per thread */
+	i32 e = TID;
+	int valid = e < W.n && bt_is_leaf_ent(W, e);
+	int4 c = valid ? W.center[e] : make_int4(INT32_MAX, INT32_MAX, INT32_MAX, 0);
+	int4 d = valid ? c : make_int4(INT32_MIN, INT32_MIN, INT32_MIN, 0);
+	i32 mnx = __reduce_min_sync(0xffffffffu, c.x), mny = __reduce_min_sync(0xffffffffu, c.y),
+	    mnz = __reduce_min_sync(0xffffffffu, c.z);
+	i32 mxx = __reduce_max_sync(0xffffffffu, d.x), mxy = __reduce_max_sync(0xffffffffu, d.y),
+	    mxz = __reduce_max_sync(0xffffffffu, d.z);
+	u32 cnt = warp_sum((u32)valid);
+	if ((threadIdx.x & 31) == 0 && cnt) {
+		i32 *b = (i32 *)&W.ctr[CT_BOUNDS];
+		atomicMin(&b[0], mnx); atomicMin(&b[1], mny); atomicMin(&b[2], mnz);
+		atomicMax(&b[3], mxx); atomicMax(&b[4], mxy); atomicMax(&b[5], mxz);
+		atomicAdd(&W.ctr[CT_N_LEAVES], cnt);
+	}
+}
+__global__ void __launch_bounds__(BT_BLOCK) k_morton(DevWorld W) { t_morton(W, TID); }
+__global__ void __launch_bounds__(BT_BLOCK) k_lbvh(DevWorld W) { t_lbvh_node(W, TID); }
+__global__ void __launch_bounds__(BT_BLOCK) k_refit(DevWorld W) { t_refit(W, TID); }
+
+/* traversal stacks live in shared memory, interleaved so that lane i's slot k is at
+ * word k*128+i: the 32 lanes of a warp hit 32 different banks (no conflicts). */
+__global__ void __launch_bounds__(BT_BLOCK) k_collide(DevWorld W) {
+	__shared__ i32 stacks[BT_STACK * BT_BLOCK];
+	LocalStats st = {0, 0, 0, 0, 0};
+	u32 any = 0;
+	t_collide(W, TID, stacks + threadIdx.x, BT_BLOCK, st, any);
+	stats_flush(W, st);
+	if (__any_sync(0xffffffffu, any) && (threadIdx.x & 31) == 0) W.ctr[CT_ANY_PROPOSAL] = 1;
+}
+__global__ void __launch_bounds__(BT_BLOCK) k_decide(DevWorld W) {
+	if (TID == 0) W.ctr[CT_ANY_PROPOSAL] = 0; /* the host already fetched this iteration's value */
+	t_decide(W, TID);
+}
+__global__ void __launch_bounds__(BT_BLOCK) k_conflict(DevWorld W) { t_conflict(W, TID); }
+__global__ void __launch_bounds__(BT_BLOCK) k_push(DevWorld W) {
+	LocalStats st = {0, 0, 0, 0, 0};
+	t_push(W, TID, st);
+	stats_flush(W, st);
+}
+__global__ void k_push_serial(DevWorld W) {
+	if (threadIdx.x != 0 || blockIdx.x != 0) return;
+	if (W.ctr[CT_SERIAL_N] == 0) return;
+	LocalStats st = {0, 0, 0, 0, 0};
+	t_push_serial(W, st);
+	u64 *s = (u64 *)&W.ctr[CT_STAT0];
+	s[SK_PUSH] += st.push; s[SK_SERIAL] += st.push; s[SK_CRUSH] += st.crush; s[SK_FUMBLE] += st.fumble;
+}
+__global__ void __launch_bounds__(BT_BLOCK) k_post(DevWorld W) { t_post(W, TID); }
+
+/* host exchange: staging buffers hold [3*n_live] ints in live oldest-first order; while no
+ * entity has died, live rank == slot (the common case, checked by the host) */
+__global__ void __launch_bounds__(BT_BLOCK) k_add_deltas(DevWorld W, const i32 *dc, const i32 *dv, const i32 *slot2rank) {
+	i32 e = TID;
+	if (e >= W.n || !W.inList[e]) return;
+	i32 r = slot2rank ? slot2rank[e] : e;
+	int4 a = W.d_center[e], b = W.d_vel[e];
+	a.x += dc[3 * r]; a.y += dc[3 * r + 1]; a.z += dc[3 * r + 2];
+	b.x += dv[3 * r]; b.y += dv[3 * r + 1]; b.z += dv[3 * r + 2];
+	W.d_center[e] = a;
+	W.d_vel[e] = b;
+}
+__global__ void __launch_bounds__(BT_BLOCK) k_pack_state(DevWorld W, i32 *oc, i32 *ov, const i32 *slot2rank) {
+	i32 e = TID;
+	if (e >= W.n || !W.inList[e]) return;
+	i32 r = slot2rank ? slot2rank[e] : e;
+	int4 c = W.center[e], v = W.vel[e];
+	oc[3 * r] = c.x; oc[3 * r + 1] = c.y; oc[3 * r + 2] = c.z;
+	ov[3 * r] = v.x; ov[3 * r + 1] = v.y; ov[3 * r + 2] = v.z;
+}
+
+/* per-world commutative hash: warp-level pre-reduction when the whole warp is one world */
+__global__ void __launch_bounds__(BT_BLOCK) k_hash(DevWorld W, u64 *sum, u32 *cnt) {
+	i32 e = TID;
+	int live = e < W.n && W.inList[e];
+	u64 h = live ? bt_ent_hash(W, e) : 0;
+	i32 g = live ? W.world[e] : -1;
+	i32 g0 = __shfl_sync(0xffffffffu, g, 0);
+	int uniform = __all_sync(0xffffffffu, g == g0 || g < 0);
+	if (uniform) {
+		i32 gm = __reduce_max_sync(0xffffffffu, g);
+#pragma unroll
+		for (int off = 16; off > 0; off >>= 1) h += __shfl_down_sync(0xffffffffu, h, off);
+		u32 c = warp_sum((u32)live);
+		if ((threadIdx.x & 31) == 0 && gm >= 0) {
+			atomicAdd(&sum[gm], h);
+			atomicAdd(&cnt[gm], c);
+		}
+	} else if (live) {
+		atomicAdd(&sum[g], h);
+		atomicAdd(&cnt[g], 1u);
+	}
+}
+
+/* --------------------------------------------------------------------------
+ * LSD radix sort, 8 bits per pass, keys u64 + payload i32, stable.
+ * pass = histogram -> scan -> scatter.  Tile = 256 threads x 16 keys.
+ * -------------------------------------------------------------------------- */
+#define SORT_THREADS 256
+#define SORT_ITEMS 16
+#define SORT_TILE (SORT_THREADS * SORT_ITEMS)
+
+__global__ void __launch_bounds__(SORT_THREADS) k_sort_hist(const u64 *keys, i32 n, int shift, u32 *hist, int nb) {
+	__shared__ u32 h[256];
+	h[threadIdx.x] = 0;
+	__syncthreads();
+	i32 base = blockIdx.x * SORT_TILE;
+#pragma unroll 4
+	for (int k = 0; k < SORT_ITEMS; k++) {
+		i32 i = base + k * SORT_THREADS + threadIdx.x;
+		if (i < n) atomicAdd(&h[(keys[i] >> shift) & 0xff], 1u);
+	}
+	__syncthreads();
+	hist[threadIdx.x * nb + blockIdx.x] = h[threadIdx.x]; /* digit-major */
+}
+
+/* exclusive scan of `len` counters by one block of 1024 threads */
+__global__ void __launch_bounds__(1024) k_sort_scan(u32 *hist, int len) {
+	__shared__ u32 warpTot[32];
+	__shared__ u32 carry;
+	if (threadIdx.x == 0) carry = 0;
+	__syncthreads();
+	for (int base = 0; base < len; base += 1024) {
+		int i = base + threadIdx.x;
+		u32 v = i < len ? hist[i] : 0;
+		u32 x = v;
+#pragma unroll
+		for (int off = 1; off < 32; off <<= 1) {
+			u32 y = __shfl_up_sync(0xffffffffu, x, off);
+			if ((threadIdx.x & 31) >= off) x += y;
+		}
+		if ((threadIdx.x & 31) == 31) warpTot[threadIdx.x >> 5] = x;
+		__syncthreads();
+		if (threadIdx.x < 32) {
+			u32 w = warpTot[threadIdx.x];
+			u32 s = w;
+#pragma unroll
+			for (int off = 1; off < 32; off <<= 1) {
+				u32 y = __shfl_up_sync(0xffffffffu, s, off);
+				if (threadIdx.x >= off) s += y;
+			}
+			warpTot[threadIdx.x] = s - w; /* exclusive over warps */
+		}
+		__syncthreads();
+		u32 excl = carry + warpTot[threadIdx.x >> 5] + x - v;
+		if (i < len) hist[i] = excl;
+		__syncthreads();
+		if (threadIdx.x == 1023) carry = excl + v;
+		__syncthreads();
+	}
+}
+
+__global__ void __launch_bounds__(SORT_THREADS) k_sort_scatter(const u64 *keys, const i32 *vals, u64 *okeys, i32 *ovals,
+                                                             i32 n, int shift, const u32 *hist, int nb) {
+	__shared__ u32 warpOff[SORT_THREADS / 32][256];
+	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	for (int d = lane; d < 256; d += 32) warpOff[warp][d] = 0;
+	__syncwarp();
+	/* each warp owns a contiguous run of 32*SORT_ITEMS keys -> stability */
+	i32 wbase = blockIdx.x * SORT_TILE + warp * (32 * SORT_ITEMS);
+	u64 kreg[SORT_ITEMS];
+#pragma unroll
+	for (int k = 0; k < SORT_ITEMS; k++) {
+		i32 i = wbase + k * 32 + lane;
+		kreg[k] = i < n ? keys[i] : 0;
+		u32 d = i < n ? (u32)((kreg[k] >> shift) & 0xff) : 0xffffffffu;
+		u32 peers = __match_any_sync(0xffffffffu, d);
+		if (d != 0xffffffffu && (peers & ((1u << lane) - 1)) == 0) warpOff[warp][d] += __popc(peers);
+		__syncwarp();
+	}
+	__syncthreads();
+	{ /* thread d turns the per-warp counts into running offsets */
+		int d = threadIdx.x;
+		u32 run = hist[d * nb + blockIdx.x];
+#pragma unroll
+		for (int w = 0; w < SORT_THREADS / 32; w++) {
+			u32 c = warpOff[w][d];
+			warpOff[w][d] = run;
+			run += c;
+		}
+	}
+	__syncthreads();
+#pragma unroll
+	for (int k = 0; k < SORT_ITEMS; k++) {
+		i32 i = wbase + k * 32 + lane;
+		u32 d = i < n ? (u32)((kreg[k] >> shift) & 0xff) : 0xffffffffu;
+		u32 peers = __match_any_sync(0xffffffffu, d);
+		u32 rank = __popc(peers & ((1u << lane) - 1));
+		if (d != 0xffffffffu) {
+			u32 pos = warpOff[warp][d] + rank;
+			okeys[pos] = kreg[k];
+			ovals[pos] = vals[i];
+		}
+		__syncwarp();
+		if (d != 0xffffffffu && rank == 0) warpOff[warp][d] += __popc(peers);
+		__syncwarp();
+	}
+}
+
+#endif

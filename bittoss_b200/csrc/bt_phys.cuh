@@ -1,0 +1,984 @@
+/*
+ * bt_phys.cuh — per-thread bodies of the tick kernels.
+ *
+ * Each t_*() function is what ONE CUDA thread does; bt_world.cu wraps them in
+ * __global__ kernels (grid = ceil(n/128) x 128, sm_100a).  Citations are to the
+ * sboerwinkle/bittoss reference the behaviour is matched against.
+ *
+ * How the sequential reference loop maps onto parallel kernels:
+ *   doIteration (ent.cpp:437-462)  -> t_collide: one thread per active leaf walks the
+ *       LBVH; every narrow-phase hit PROPOSES a collision to the hold root it would
+ *       move, with a 64-bit CAS loop that keeps the maximum under collisionBetter +
+ *       canonical tie-break.  A maximum does not depend on arrival order, so the
+ *       result is deterministic although the order of atomics is not.
+ *   shouldResolveCollision (ent.cpp:631-672) -> t_decide: read-only walk of pend[].
+ *   push loop (ent.cpp:879-882)   -> t_push: one thread per ready root.  A ready root
+ *       owns its hold tree exclusively for the iteration (its buddy's tree is either
+ *       static this iteration or its mutual partner), except for tied cycles, which
+ *       t_conflict routes to the serial lane (t_push_serial, canonical order).
+ */
+#ifndef BT_PHYS_CUH
+#define BT_PHYS_CUH
+
+#include "bt_types.h"
+
+#if defined(BT_EMU)
+static inline u64 bt_cas64(u64 *p, u64 cmp, u64 val) { u64 o = *p; if (o == cmp) *p = val; return o; }
+static inline u32 bt_add32(u32 *p, u32 v) { u32 o = *p; *p += v; return o; }
+static inline void bt_add64(u64 *p, u64 v) { *p += v; }
+static inline void bt_min32(i32 *p, i32 v) { if (v < *p) *p = v; }
+static inline void bt_max32(i32 *p, i32 v) { if (v > *p) *p = v; }
+static inline void bt_or32(u32 *p, u32 v) { *p |= v; }
+static inline u64 bt_ld64(const u64 *p) { return *p; }
+static inline int4 bt_ldcg4(const int4 *p) { return *p; }
+static inline void bt_fence() {}
+static inline int bt_clz32(u32 x) { return x ? __builtin_clz(x) : 32; }
+static inline int bt_clz64(u64 x) { return x ? __builtin_clzll(x) : 64; }
+static inline int bt_abs(int x) { return x < 0 ? -x : x; }
+#else
+static BT_HD u64 bt_cas64(u64 *p, u64 cmp, u64 val) { return atomicCAS(p, cmp, val); }
+static BT_HD u32 bt_add32(u32 *p, u32 v) { return atomicAdd(p, v); }
+static BT_HD void bt_add64(u64 *p, u64 v) { atomicAdd(p, v); }
+static BT_HD void bt_min32(i32 *p, i32 v) { atomicMin(p, v); }
+static BT_HD void bt_max32(i32 *p, i32 v) { atomicMax(p, v); }
+static BT_HD void bt_or32(u32 *p, u32 v) { atomicOr(p, v); }
+static BT_HD u64 bt_ld64(const u64 *p) { return *(const volatile u64 *)p; }
+static BT_HD int4 bt_ldcg4(const int4 *p) { return __ldcg(p); } /* L2 load: another SM wrote it in this kernel */
+static BT_HD void bt_fence() { __threadfence(); }
+static BT_HD int bt_clz32(u32 x) { return __clz((int)x); }
+static BT_HD int bt_clz64(u64 x) { return __clzll((long long)x); }
+static BT_HD int bt_abs(int x) { return x < 0 ? -x : x; }
+#endif
+
+struct LocalStats {
+	u32 cand, pos, push, crush, fumble;
+};
+
+/* ------------------------------------------------------------------------- */
+/* helpers                                                                   */
+
+/* needsVelbox ent.cpp:75-77 */
+static BT_HD int bt_needs_box(u32 type, u32 collide) { return collide || (type & T_COLLIDABLE); }
+
+/* boundVec ent.cpp:20-30 (int64 multiply, truncating division) */
+static BT_HD void bt_bound_vec(i32 *v, i32 bound, int len) {
+	i32 mx = bound;
+	for (int i = 0; i < len; i++) {
+		i32 x = bt_abs(v[i]);
+		if (x > mx) mx = x;
+	}
+	if (mx == bound) return;
+	for (int i = 0; i < len; i++) v[i] = (i32)((long long)bound * v[i] / mx);
+}
+
+/* pre-order walk of the hold subtree of `r` without a stack (holdee / LL.n / holder links) */
+#define BT_FOR_SUBTREE(W, r, it, ...)                                    \
+	do {                                                                 \
+		i32 it = (r);                                                    \
+		while (1) {                                                      \
+			__VA_ARGS__;                                                     \
+			if ((W).holdee[it] >= 0) { it = (W).holdee[it]; continue; }  \
+			while (it != (r) && (W).LLn[it] < 0) it = (W).holder[it];    \
+			if (it == (r)) break;                                        \
+			it = (W).LLn[it];                                            \
+		}                                                                \
+	} while (0)
+
+/* uSlider entUpdaters.c:58-68 */
+static BT_HD void bt_uslider(const DevWorld &W, i32 e, int ix, i32 value) {
+	int ns = W.slider_off[e + 1] - W.slider_off[e];
+	if (ix < 0 || ix >= ns) return;
+	W.fullFlush[e] = 1;
+	int s = W.slider_off[e] + ix;
+	if (value > W.smax[s]) W.smax[s] = value;
+	if (value < W.smin[s]) W.smin[s] = value;
+}
+/* getSlider entGetters.c:42-48 */
+static BT_HD i32 bt_getslider(const DevWorld &W, i32 e, int ix) {
+	int ns = W.slider_off[e + 1] - W.slider_off[e];
+	if (ix < 0 || ix >= ns) return 0;
+	return W.sv[W.slider_off[e] + ix];
+}
+
+/* ------------------------------------------------------------------------- */
+/* handlers, selected by the catalog IDs of handlerRegistrar.h:79-187        */
+
+/* whoMoves_t: move_me common.c:48; explosion.cpp:8; player.c:84; stackem.c:9-22;
+ * material.c:5-24.  0 = unset -> MOVE_ME (ent.cpp:220-225), 3 aliases 1 (platform.c:56). */
+static BT_HD int bt_who_moves(int id, u32 ta, u32 tb, int axis, int dir) {
+	switch (id) {
+	case 2: return (tb & T_TERRAIN) ? MOVE_ME : MOVE_HIM;
+	case 4: return (tb & T_TERRAIN) ? MOVE_ME : MOVE_BOTH;
+	case 5: {
+		if (tb & T_TERRAIN) return MOVE_ME;
+		int goodTeam = (TEAM_MASK & tb & ta) != 0;
+		if (axis == 2) {
+			if (dir == -1 && ((tb & T_HEAVY) || goodTeam)) return MOVE_ME;
+			return MOVE_HIM;
+		}
+		return goodTeam ? MOVE_BOTH : MOVE_HIM;
+	}
+	case 6:
+		if (tb & T_TERRAIN) return MOVE_ME;
+		if (axis == 2) return dir == -1 ? MOVE_ME : MOVE_HIM;
+		return MOVE_BOTH;
+	case 7: return (tb & T_HEAVY) ? MOVE_ME : MOVE_HIM;
+	case 8:
+		if (dir == 1 && axis == 2 && !(tb & (T_TERRAIN | T_HEAVY))) return MOVE_BOTH;
+		return MOVE_ME;
+	default: return MOVE_ME;
+	}
+}
+
+/* which handler IDs have a device implementation (bt_world_upload checks these) */
+#define BT_SUPPORTED_WHOMOVES 0x1ffu /* 0..8 */
+#define BT_SUPPORTED_PUSH 0x005u     /* NIL, LOGIC */
+#define BT_SUPPORTED_PUSHED 0x02fu   /* NIL, PUDDLEJUMP, FRAGILE, FLAG, PLAYER */
+#define BT_SUPPORTED_PAIR 0x009u     /* NIL, FUMBLED_DECOR */
+#define BT_SUPPORTED_CRUSH 0x001u    /* NIL (others are host-side events) */
+
+/* push_t: 0 onPushDefault handlerRegistrar.cpp:16; 2 logic_push logic.c:44-49.
+ * Writing v2=1 is idempotent, so concurrent pushers of one logic block do not race. */
+static BT_HD int bt_push_handler(const DevWorld &W, i32 me, i32 him) {
+	int id = (W.hphys[me] >> 8) & 0xff;
+	if (id == 2) {
+		if (W.type[him] & (T_TERRAIN | T_OBSTACLE | T_DEBRIS)) bt_or32(&W.btn_v2[me], 1u); /* pushBtn(me,0) */
+	}
+	return 0;
+}
+
+/* pushed_t: 2 fragile_pushed common.c:56; 3 flag_pushed flag.c:13; 5 player_pushed
+ * player.c:88-106; 1 pj_pushed puddlejumper.cpp:44-65.  NULL slot (0) is skipped (ent.cpp:556). */
+static BT_HD int bt_pushed_handler(const DevWorld &W, i32 me, i32 him, int axis, int dir, i32 dv) {
+	int id = (W.hphys[me] >> 16) & 0xff;
+	switch (id) {
+	case 2: return 1;
+	case 3: return (W.type[him] & T_FLAG) ? 1 : 0;
+	case 1:
+	case 5: {
+		int s_vel = id == 5 ? 5 : 2, s_grounded = id == 5 ? 7 : 4;
+		int4 vm = W.vel[me], vh = W.vel[him];
+		i32 vel[3] = {vm.x - vh.x, vm.y - vh.y, vm.z - vh.z};
+		if (id == 1) bt_bound_vec(vel, 200, 2);
+		if (axis == 2) {
+			if (dir < 0) bt_uslider(W, me, s_grounded, 1);
+		} else {
+			i32 currentSlide = bt_getslider(W, me, s_vel + axis);
+			vel[axis] = currentSlide + dir * dv;
+			if (dir * vel[axis] > 0) vel[axis] = 0;
+		}
+		bt_uslider(W, me, s_vel, vel[0]);
+		bt_uslider(W, me, s_vel + 1, vel[1]);
+		return 0;
+	}
+	default: return 0;
+	}
+}
+
+/* entPair_t: 3 decor_fumbled common.c:61-67.  slot: 0 onFumble 1 onFumbled 2 onPickUp 3 onPickedUp */
+static BT_HD void bt_pair_handler(const DevWorld &W, int slot, i32 me) {
+	int id = (W.hpair[me] >> (8 * slot)) & 0xff;
+	if (id == 3) {
+		W.fullFlush[me] = 1;
+		W.ntype[me] = W.type[me] | T_DEBRIS;
+		W.ncollide[me] = W.collide[me] | T_TERRAIN | T_OBSTACLE | T_DEBRIS;
+		if (slot == 1) W.hpair[me] &= ~(0xffu << 8);
+	}
+}
+
+/* ------------------------------------------------------------------------- */
+/* tree edits (only ever called by the thread that owns the tree this iteration) */
+
+/* fumble ent.cpp:136-158; addRootEnt :60-66 has no list here (roots = holder < 0) */
+static BT_HD void bt_fumble(const DevWorld &W, i32 h, LocalStats &st) {
+	i32 a = W.holder[h];
+	if (a < 0) return;
+	st.fumble++;
+	W.needsCollision[h] = 1;
+	bt_pair_handler(W, 0, a);
+	bt_pair_handler(W, 1, h);
+	for (int i = 0; i < 3; i++) {
+		i32 x = h, y;
+		while ((y = W.holder[x]) >= 0 && bt_forced_get(W.forced[y], i) && bt_get3(W.forcedHoldees[y], i) == x) {
+			W.forced[y] = bt_forced_set(W.forced[y], i, 0);
+			x = y;
+		}
+	}
+	i32 n = W.LLn[h], p = W.LLp[h];
+	if (n >= 0) W.LLp[n] = p;
+	if (p >= 0) W.LLn[p] = n;
+	else W.holdee[a] = n;
+	W.holder[h] = -1;
+	W.LLn[h] = -1;
+	W.LLp[h] = -1;
+	BT_FOR_SUBTREE(W, h, it, W.holdRoot[it] = h); /* recursiveHoldRoot ent.cpp:39-45 */
+}
+
+/* killEntNoHandlers ent.cpp:190-208 + crushEnt :211-217.  The dead list replaces
+ * gs->deadTail; `key` orders it canonically (iteration, pusher) for the host. */
+static BT_HD void bt_crush(const DevWorld &W, i32 e, u32 key, LocalStats &st) {
+	if (W.dead[e]) return;
+	st.crush++;
+	while (W.holdee[e] >= 0) bt_fumble(W, W.holdee[e], st);
+	bt_fumble(W, e, st);
+	W.inList[e] = 0;
+	W.hasBox[e] = 0;
+	W.dead[e] = 1;
+	u32 slot = bt_add32(&W.ctr[CT_DEAD_N], 1u);
+	if ((i32)slot < W.dead_cap) W.deadList[slot] = ((u64)key << 32) | (u32)e;
+}
+
+/* moveRecursive ent.cpp:115-126 */
+static BT_HD void bt_move_recursive(const DevWorld &W, i32 who, const i32 *dc, const i32 *dv) {
+	BT_FOR_SUBTREE(W, who, it, {
+		int4 c = W.center[it], v = W.vel[it];
+		c.x += dc[0]; c.y += dc[1]; c.z += dc[2];
+		v.x += dv[0]; v.y += dv[1]; v.z += dv[2];
+		W.center[it] = c;
+		W.vel[it] = v;
+	});
+}
+
+/* ------------------------------------------------------------------------- */
+/* narrow phase                                                              */
+
+struct EntGeo {
+	int4 old, center, radius;
+};
+
+/* getAxisAndDir ent.cpp:238-313.  Returns +-(axis+1) or 0. */
+static BT_HD int bt_axis_and_dir(const EntGeo &a, const EntGeo &b) {
+	int d1[3], d2[3], wd[3];
+	const int ao[3] = {a.old.x, a.old.y, a.old.z}, bo[3] = {b.old.x, b.old.y, b.old.z};
+	const int ac[3] = {a.center.x, a.center.y, a.center.z}, bc[3] = {b.center.x, b.center.y, b.center.z};
+	const int ar[3] = {a.radius.x, a.radius.y, a.radius.z}, br[3] = {b.radius.x, b.radius.y, b.radius.z};
+#pragma unroll
+	for (int i = 0; i < 3; i++) {
+		d1[i] = bo[i] - ao[i];
+		d2[i] = bc[i] - ac[i];
+		wd[i] = ar[i] + br[i];
+		if (d1[i] > 0) {
+			if (d1[i] >= wd[i] && d2[i] >= wd[i]) return 0;
+		} else {
+			if (d1[i] <= -wd[i] && d2[i] <= -wd[i]) return 0;
+		}
+		d2[i] = d1[i] - d2[i];
+	}
+	int dir_by_axis[3];
+#pragma unroll
+	for (int i = 0; i < 3; i++) {
+		if (d2[i] >= 0) {
+			dir_by_axis[i] = -(i + 1);
+		} else {
+			dir_by_axis[i] = (i + 1);
+			d1[i] = -d1[i];
+			d2[i] = -d2[i];
+		}
+	}
+#pragma unroll
+	for (int i = 0; i < 3; i++) d1[i] -= wd[i];
+	int best;
+	{
+		long long cmp = ((long long)d1[0]) * d2[1] - ((long long)d1[1]) * d2[0];
+		if (cmp > 0) best = 0;
+		else if (cmp < 0) best = 1;
+		else best = (wd[0] > wd[1]) ? 1 : 0;
+	}
+	{
+		int A = best;
+		long long cmp = ((long long)d1[A]) * d2[2] - ((long long)d1[2]) * d2[A];
+		if (cmp > 0) best = A;
+		else if (cmp < 0) best = 2;
+		else best = (wd[A] > wd[2]) ? 2 : A;
+	}
+	if (d1[best] < 0) {
+		int depth = INT32_MAX;
+		int ret = 0;
+#pragma unroll
+		for (int i = 0; i < 3; i++) {
+			int d = d1[i] + wd[i];
+			int new_depth, new_ret;
+			if (d >= 0) {
+				new_depth = wd[i] - d;
+				new_ret = dir_by_axis[i];
+			} else {
+				new_depth = wd[i] + d;
+				new_ret = d2[i] ? 0 : -dir_by_axis[i];
+			}
+			if (new_depth < depth) {
+				depth = new_depth;
+				ret = new_ret;
+			}
+		}
+		return ret;
+	}
+#pragma unroll
+	for (int i = 0; i < 3; i++) {
+		int far_ = d1[i] + 2 * wd[i];
+		long long cmp = ((long long)d1[best]) * d2[i] - ((long long)far_) * d2[best];
+		if (cmp >= 0) return 0;
+	}
+	return dir_by_axis[best];
+}
+
+static BT_HD EntGeo bt_geo(const DevWorld &W, i32 e) {
+	EntGeo g;
+	g.old = W.old[e];
+	g.center = W.center[e];
+	g.radius = W.radius[e];
+	return g;
+}
+
+/* collisionBetter ent.cpp:317-382 as a three-way compare of two explicit records:
+ * +1 c0 strictly better, -1 strictly worse, 0 full tie.  32-bit products wrap
+ * exactly like the reference's `delta * speed` (ent.cpp:343). */
+static BT_HD int bt_collision_cmp(const DevWorld &W, const Coll &c0, const Coll &c1) {
+	EntGeo l0 = bt_geo(W, c0.leaf), f0 = bt_geo(W, c0.buddy);
+	EntGeo l1 = bt_geo(W, c1.leaf), f1 = bt_geo(W, c1.buddy);
+	int a0 = c0.axis, a1 = c1.axis;
+	i32 delta0 = (i32)((u32)(bt_get3(l0.old, a0) - bt_get3(f0.old, a0)) * (u32)c0.dir) - bt_get3(f0.radius, a0) -
+	             bt_get3(l0.radius, a0);
+	i32 delta1 = (i32)((u32)(bt_get3(l1.old, a1) - bt_get3(f1.old, a1)) * (u32)c1.dir) - bt_get3(f1.radius, a1) -
+	             bt_get3(l1.radius, a1);
+	/* speed of the OTHER record (ent.cpp:340) */
+	i32 speed1 = (i32)((u32)(bt_get3(f1.center, a1) - bt_get3(f1.old, a1) + bt_get3(l1.old, a1) -
+	                         bt_get3(l1.center, a1)) * (u32)c1.dir);
+	i32 speed0 = (i32)((u32)(bt_get3(f0.center, a0) - bt_get3(f0.old, a0) + bt_get3(l0.old, a0) -
+	                         bt_get3(l0.center, a0)) * (u32)c0.dir);
+	if (speed1 < 1) speed1 = 1;
+	if (speed0 < 1) speed0 = 1;
+	long long v0 = (i32)((u32)delta0 * (u32)speed1);
+	long long v1 = (i32)((u32)delta1 * (u32)speed0);
+	if (v0 != v1) return v0 < v1 ? 1 : -1;
+	int m0 = !c0.mutual, m1 = !c1.mutual;
+	if (m0 != m1) return m0 > m1 ? 1 : -1;
+	i32 k0, k1;
+	{
+		int x1 = (a0 + 1) % 3, x2 = (a0 + 2) % 3;
+		i32 p = bt_get3(f0.radius, x1) + bt_get3(l0.radius, x1) - bt_abs(bt_get3(f0.old, x1) - bt_get3(l0.old, x1));
+		i32 q = bt_get3(f0.radius, x2) + bt_get3(l0.radius, x2) - bt_abs(bt_get3(f0.old, x2) - bt_get3(l0.old, x2));
+		k0 = p < q ? p : q;
+	}
+	{
+		int x1 = (a1 + 1) % 3, x2 = (a1 + 2) % 3;
+		i32 p = bt_get3(f1.radius, x1) + bt_get3(l1.radius, x1) - bt_abs(bt_get3(f1.old, x1) - bt_get3(l1.old, x1));
+		i32 q = bt_get3(f1.radius, x2) + bt_get3(l1.radius, x2) - bt_abs(bt_get3(f1.old, x2) - bt_get3(l1.old, x2));
+		k1 = p < q ? p : q;
+	}
+	if (k0 != k1) return k0 > k1 ? 1 : -1;
+	k0 = bt_get3(f0.radius, a0) + bt_get3(l0.radius, a0) + (bt_get3(f0.center, a0) - bt_get3(l0.center, a0)) * c0.dir;
+	k1 = bt_get3(f1.radius, a1) + bt_get3(l1.radius, a1) + (bt_get3(f1.center, a1) - bt_get3(l1.center, a1)) * c1.dir;
+	if (k0 != k1) return k0 > k1 ? 1 : -1;
+	return 0;
+}
+
+/* tryCollide ent.cpp:384-396 as an order-independent atomic maximum on pend[root] */
+static BT_HD void bt_propose(const DevWorld &W, i32 leaf, i32 buddy, int axis, int dir, int mutual) {
+	i32 root = W.holdRoot[leaf];
+	Coll c;
+	c.leaf = leaf; c.buddy = buddy; c.axis = axis; c.dir = dir; c.mutual = mutual;
+	u64 mine = bt_pack_coll(c);
+	u64 cur = bt_ld64(&W.pend[root]);
+	while (1) {
+		if (cur != 0) {
+			Coll inc = bt_unpack_coll(cur);
+			int r = bt_collision_cmp(W, c, inc);
+			if (r < 0) return;
+			if (r == 0 && (mine >> 2) <= (cur >> 2)) return;
+		}
+		u64 prev = bt_cas64(&W.pend[root], cur, mine);
+		if (prev == cur) return;
+		cur = prev;
+	}
+}
+
+/* checkCollision ent.cpp:398-435 for scanning entity a (already loaded) against b */
+static BT_HD void bt_check_collision(const DevWorld &W, i32 a, const EntGeo &ga, u32 ta, u32 ca, i32 rootA, u32 ha,
+                                     i32 b, LocalStats &st, u32 &any) {
+	u32 tb = W.type[b], cb = W.collide[b];
+	int AonB = (tb & ca) != 0, BonA = (ta & cb) != 0;
+	if (!AonB && !BonA) return;
+	if (rootA == W.holdRoot[b]) return;
+	EntGeo gb = bt_geo(W, b);
+	int dir = bt_axis_and_dir(ga, gb);
+	if (dir == 0) return;
+	st.pos++;
+	int axis;
+	if (dir < 0) { axis = -dir - 1; dir = -1; }
+	else { axis = dir - 1; dir = 1; }
+	int hb = (int)(W.hphys[b] & 0xff);
+	int movee;
+	if (AonB) {
+		if (BonA) { /* arbitrateMovement ent.cpp:229-236 */
+			int A = bt_who_moves((int)(ha & 0xff), ta, tb, axis, dir);
+			int B = bt_who_moves(hb, tb, ta, axis, -dir);
+			if (B == MOVE_ME) B = MOVE_HIM;
+			else if (B == MOVE_HIM) B = MOVE_ME;
+			A = A & B;
+			movee = A ? A : MOVE_BOTH;
+		} else {
+			movee = bt_who_moves((int)(ha & 0xff), ta, tb, axis, dir);
+		}
+	} else {
+		movee = 3 ^ bt_who_moves(hb, tb, ta, axis, -dir);
+	}
+	if (movee & 8) return;
+	any = 1;
+	if (movee & 4) {
+		/* coordinator rule, DESIGN.md "Canonical order": a scans; it coordinates unless b
+		 * scans too and comes first in the reference's newest-first order */
+		int bScans = W.needsCollision[b] && W.hasBox[b] && W.inList[b];
+		int coordA = bScans ? (a > b) : 1;
+		bt_propose(W, a, b, axis, dir, coordA ? 1 : 2);
+		bt_propose(W, b, a, axis, -dir, coordA ? 2 : 1);
+		return;
+	}
+	if (movee == MOVE_ME) bt_propose(W, a, b, axis, dir, 0);
+	else bt_propose(W, b, a, axis, -dir, 0);
+}
+
+/* ------------------------------------------------------------------------- */
+/* broadphase: Morton keys, Karras LBVH, refit, traversal                    */
+
+static BT_HD void bt_swept_box(const int4 &o, const int4 &c, const int4 &r, i32 lo[3], i32 hi[3]) {
+	lo[0] = (o.x < c.x ? o.x : c.x) - r.x; hi[0] = (o.x > c.x ? o.x : c.x) + r.x;
+	lo[1] = (o.y < c.y ? o.y : c.y) - r.y; hi[1] = (o.y > c.y ? o.y : c.y) + r.y;
+	lo[2] = (o.z < c.z ? o.z : c.z) - r.z; hi[2] = (o.z > c.z ? o.z : c.z) + r.z;
+}
+
+static BT_HD int bt_is_leaf_ent(const DevWorld &W, i32 e) { return W.inList[e] && (W.ray_mode || W.hasBox[e]); }
+
+/* min/max of leaf centres -> ctr[CT_BOUNDS..+5] */
+static BT_HD void t_bounds(const DevWorld &W, i32 e) {
+	if (e >= W.n || !bt_is_leaf_ent(W, e)) return;
+	int4 c = W.center[e];
+	i32 *b = (i32 *)&W.ctr[CT_BOUNDS];
+	bt_min32(&b[0], c.x); bt_min32(&b[1], c.y); bt_min32(&b[2], c.z);
+	bt_max32(&b[3], c.x); bt_max32(&b[4], c.y); bt_max32(&b[5], c.z);
+}
+
+static BT_HD u32 bt_expand10(u32 v) { /* 10 bits -> every third bit */
+	v &= 0x3ff;
+	v = (v | (v << 16)) & 0x030000FF;
+	v = (v | (v << 8)) & 0x0300F00F;
+	v = (v | (v << 4)) & 0x030C30C3;
+	v = (v | (v << 2)) & 0x09249249;
+	return v;
+}
+
+/* key = world id << 30 | 30-bit Morton code of the centre; non-leaves get world id
+ * n_worlds and therefore sort last (radix passes cover 30 + bits(n_worlds) bits) */
+static BT_HD void t_morton(const DevWorld &W, i32 e) {
+	if (e >= W.n) return;
+	u64 key = (u64)(u32)W.n_worlds << 30;
+	if (bt_is_leaf_ent(W, e)) {
+		int4 c = W.center[e];
+		const i32 *b = (const i32 *)&W.ctr[CT_BOUNDS];
+		u32 qx = ((u32)(c.x - b[0])) >> W.key_shift[0];
+		u32 qy = ((u32)(c.y - b[1])) >> W.key_shift[1];
+		u32 qz = ((u32)(c.z - b[2])) >> W.key_shift[2];
+		u32 m = (bt_expand10(qx) << 2) | (bt_expand10(qy) << 1) | bt_expand10(qz);
+		key = ((u64)(u32)W.world[e] << 30) | m;
+	}
+	W.keys[e] = key;
+	W.leafEnt[e] = e;
+}
+
+static BT_HD int bt_delta(const DevWorld &W, int i, int j, int L) {
+	if (j < 0 || j >= L) return -1;
+	u64 a = W.keys[i], b = W.keys[j];
+	if (a == b) return 64 + bt_clz32((u32)i ^ (u32)j);
+	return bt_clz64(a ^ b);
+}
+
+/* Karras 2012 "Maximizing parallelism in the construction of BVHs": internal node i */
+static BT_HD void t_lbvh_node(const DevWorld &W, int i) {
+	int L = W.n_leaves;
+	if (i >= L - 1) return;
+	int d = (bt_delta(W, i, i + 1, L) - bt_delta(W, i, i - 1, L)) >= 0 ? 1 : -1;
+	int dmin = bt_delta(W, i, i - d, L);
+	int lmax = 2;
+	while (bt_delta(W, i, i + lmax * d, L) > dmin) lmax *= 2;
+	int l = 0;
+	for (int t = lmax / 2; t >= 1; t /= 2)
+		if (bt_delta(W, i, i + (l + t) * d, L) > dmin) l += t;
+	int j = i + l * d;
+	int dnode = bt_delta(W, i, j, L);
+	int s = 0;
+	int t = l;
+	do {
+		t = (t + 1) / 2;
+		if (bt_delta(W, i, i + (s + t) * d, L) > dnode) s += t;
+	} while (t > 1);
+	int gamma = i + s * d + (d < 0 ? -1 : 0);
+	int lo = i < j ? i : j, hi = i < j ? j : i;
+	BvhNode &N = W.nodes[i];
+	if (lo == gamma) { N.left = ~gamma; W.leafParent[gamma] = i; }
+	else { N.left = gamma; W.nodeParent[gamma] = i; }
+	if (hi == gamma + 1) { N.right = ~(gamma + 1); W.leafParent[gamma + 1] = i; }
+	else { N.right = gamma + 1; W.nodeParent[gamma + 1] = i; }
+	if (i == 0) W.nodeParent[0] = -1;
+}
+
+static BT_HD int bt_min(int a, int b) { return a < b ? a : b; }
+static BT_HD int bt_max(int a, int b) { return a > b ? a : b; }
+
+/* refit: leaf position t computes its swept box (what velbox_step / velbox_update keep in
+ * p1,p2,r: box.cpp:442-459, ent.cpp:892-904) and climbs; the second thread to reach a node
+ * (atomic counter) builds it from both children. */
+static BT_HD void t_refit(const DevWorld &W, int t) {
+	int L = W.n_leaves;
+	if (t >= L) return;
+	i32 e = W.leafEnt[t];
+	Box6 box;
+	if (bt_is_leaf_ent(W, e)) {
+		i32 lo[3], hi[3];
+		int4 cc = W.center[e];
+		bt_swept_box(W.ray_mode ? cc : W.old[e], cc, W.radius[e], lo, hi);
+		box.lo = make_int4(lo[0], lo[1], lo[2], W.world[e]);
+		box.hi = make_int4(hi[0], hi[1], hi[2], W.world[e]);
+	} else { /* died since the tree was built: empty box, never overlaps */
+		box.lo = make_int4(INT32_MAX, INT32_MAX, INT32_MAX, 0xffff);
+		box.hi = make_int4(INT32_MIN, INT32_MIN, INT32_MIN, 0);
+	}
+	W.leafBox[t] = box;
+	if (L < 2) return;
+	int node = W.leafParent[t];
+	while (node >= 0) {
+		bt_fence();
+		u32 prev = bt_add32(&W.nodeCount[node], 1u);
+		if (prev == 0) return; /* first arrival: the sibling subtree is not done yet */
+		bt_fence();
+		BvhNode &N = W.nodes[node];
+		i32 li = N.left, ri = N.right;
+		const Box6 *pa = li < 0 ? &W.leafBox[~li] : &W.nodeBox[li];
+		const Box6 *pb = ri < 0 ? &W.leafBox[~ri] : &W.nodeBox[ri];
+		int4 alo = bt_ldcg4(&pa->lo), ahi = bt_ldcg4(&pa->hi), blo = bt_ldcg4(&pb->lo), bhi = bt_ldcg4(&pb->hi);
+		N.llo[0] = alo.x; N.llo[1] = alo.y; N.llo[2] = alo.z;
+		N.lhi[0] = ahi.x; N.lhi[1] = ahi.y; N.lhi[2] = ahi.z;
+		N.rlo[0] = blo.x; N.rlo[1] = blo.y; N.rlo[2] = blo.z;
+		N.rhi[0] = bhi.x; N.rhi[1] = bhi.y; N.rhi[2] = bhi.z;
+		N.wl = (u32)alo.w | ((u32)ahi.w << 16);
+		N.wr = (u32)blo.w | ((u32)bhi.w << 16);
+		Box6 u;
+		u.lo = make_int4(bt_min(alo.x, blo.x), bt_min(alo.y, blo.y), bt_min(alo.z, blo.z), bt_min(alo.w, blo.w));
+		u.hi = make_int4(bt_max(ahi.x, bhi.x), bt_max(ahi.y, bhi.y), bt_max(ahi.z, bhi.z), bt_max(ahi.w, bhi.w));
+		W.nodeBox[node] = u;
+		node = W.nodeParent[node];
+	}
+}
+
+#define BT_STACK 64
+
+/* doIteration ent.cpp:437-462 for the entity at sorted leaf position t.
+ * `stack` is this thread's traversal stack (shared memory on the device). */
+static BT_HD void t_collide(const DevWorld &W, int t, i32 *stack, int stride, LocalStats &st, u32 &any) {
+	int L = W.n_leaves;
+	if (t >= L) return;
+	i32 a = W.leafEnt[t];
+	if (!(W.needsCollision[a] && bt_is_leaf_ent(W, a))) return;
+	if (L < 2) return;
+	EntGeo ga = bt_geo(W, a);
+	i32 qlo[3], qhi[3];
+	bt_swept_box(ga.old, ga.center, ga.radius, qlo, qhi);
+	u32 ta = W.type[a], ca = W.collide[a], ha = W.hphys[a], wa = (u32)W.world[a];
+	i32 rootA = W.holdRoot[a];
+	int sp = 0;
+	int node = 0;
+	while (1) {
+		const BvhNode &N = W.nodes[node];
+		i32 li = N.left, ri = N.right;
+		/* touching counts as a candidate, the narrow phase decides */
+		int ovL = qlo[0] <= N.lhi[0] && N.llo[0] <= qhi[0] && qlo[1] <= N.lhi[1] && N.llo[1] <= qhi[1] &&
+		          qlo[2] <= N.lhi[2] && N.llo[2] <= qhi[2] && (N.wl & 0xffff) <= wa && wa <= (N.wl >> 16);
+		int ovR = qlo[0] <= N.rhi[0] && N.rlo[0] <= qhi[0] && qlo[1] <= N.rhi[1] && N.rlo[1] <= qhi[1] &&
+		          qlo[2] <= N.rhi[2] && N.rlo[2] <= qhi[2] && (N.wr & 0xffff) <= wa && wa <= (N.wr >> 16);
+		if (ovL && li < 0) {
+			i32 b = W.leafEnt[~li];
+			if (b != a) { st.cand++; bt_check_collision(W, a, ga, ta, ca, rootA, ha, b, st, any); }
+		}
+		if (ovR && ri < 0) {
+			i32 b = W.leafEnt[~ri];
+			if (b != a) { st.cand++; bt_check_collision(W, a, ga, ta, ca, rootA, ha, b, st, any); }
+		}
+		int goL = ovL && li >= 0, goR = ovR && ri >= 0;
+		if (goL) {
+			node = li;
+			if (goR) {
+				if (sp < BT_STACK) stack[(sp++) * stride] = ri;
+				else W.ctr[CT_ERROR] = (u32)(-BT_ERR_OVERFLOW);
+			}
+		} else if (goR) {
+			node = ri;
+		} else {
+			if (sp == 0) break;
+			node = stack[(--sp) * stride];
+		}
+	}
+}
+
+/* ------------------------------------------------------------------------- */
+/* resolution                                                                */
+
+/* shouldResolveCollision ent.cpp:631-672.  Returns 0 no / 1 yes / 2 yes, decided by
+ * walking a cycle of pending collisions back to e. */
+static BT_HD int bt_should_resolve(const DevWorld &W, i32 e, u64 pe) {
+	Coll mine = bt_unpack_coll(pe);
+	if (mine.mutual == 2) return 0;
+	i32 otherRoot = W.holdRoot[mine.buddy];
+	u64 po = W.pend[otherRoot];
+	if (po == 0) return 1;
+	i32 loopDetector = otherRoot;
+	int flip = 0;
+	while (1) {
+		Coll other = bt_unpack_coll(po);
+		if (bt_collision_cmp(W, other, mine) > 0) return 0;
+		otherRoot = W.holdRoot[other.buddy];
+		if (otherRoot == e) return 2;
+		po = W.pend[otherRoot];
+		if (po == 0 || otherRoot == loopDetector) return 0;
+		if (flip) loopDetector = W.holdRoot[bt_unpack_coll(W.pend[loopDetector]).buddy];
+		flip = !flip;
+	}
+}
+
+/* every entity: doIteration clears needsCollision (ent.cpp:459); roots with a pending
+ * collision decide whether they resolve now (ent.cpp:870-878) */
+static BT_HD void t_decide(const DevWorld &W, i32 e) {
+	if (e >= W.n) return;
+	W.needsCollision[e] = 0;
+	u64 p = W.pend[e];
+	W.ready[e] = p ? (u8)bt_should_resolve(W, e, p) : 0;
+}
+
+/* A root that resolves by closing a cycle shares trees with the other members of that
+ * cycle.  If another member also resolves this iteration (a tie), both go to the serial
+ * lane so the outcome matches the reference's sequential loop in canonical order. */
+static BT_HD void t_conflict(const DevWorld &W, i32 e) {
+	if (e >= W.n || W.ready[e] != 2) return;
+	i32 r = W.holdRoot[bt_unpack_coll(W.pend[e]).buddy];
+	int conflict = 0, guard = 0;
+	while (r != e && guard++ < 1000000) {
+		if (W.ready[r]) conflict = 1;
+		r = W.holdRoot[bt_unpack_coll(W.pend[r]).buddy];
+	}
+	if (conflict) {
+		u32 slot = bt_add32(&W.ctr[CT_SERIAL_N], 1u);
+		if ((i32)slot < W.serial_cap) W.serialList[slot] = e;
+		else W.ctr[CT_ERROR] = (u32)(-BT_ERR_OVERFLOW);
+	} else {
+		W.ready[e] = 1;
+	}
+}
+
+/* pinch ent.cpp:483-507 */
+static BT_HD i32 bt_pinch(const DevWorld &W, i32 e, int axis, i32 o, u32 key, LocalStats &st) {
+	i32 leaf1 = e;
+	while (bt_get3(W.forcedHoldees[leaf1], axis) >= 0) leaf1 = bt_get3(W.forcedHoldees[leaf1], axis);
+	i32 leaf2;
+	if (o >= 0) {
+		leaf2 = o;
+		while (bt_get3(W.forcedHoldees[leaf2], axis) >= 0) leaf2 = bt_get3(W.forcedHoldees[leaf2], axis);
+	} else {
+		leaf2 = e;
+	}
+	if (leaf1 != e) {
+		bt_fumble(W, leaf1, st);
+		if (leaf2 != e) {
+			bt_fumble(W, leaf2, st);
+			return leaf2;
+		}
+		return e;
+	}
+	if (leaf2 != e) {
+		bt_fumble(W, leaf2, st);
+		return leaf2;
+	}
+	bt_crush(W, e, key, st);
+	return -1;
+}
+
+/* push_helper ent.cpp:509-525 */
+static BT_HD int bt_push_helper(const DevWorld &W, i32 e, i32 prev, int axis, int dir, u32 key, LocalStats &st) {
+	if (bt_forced_get(W.forced[e], axis) * dir < 0) {
+		i32 ret = bt_pinch(W, e, axis, prev, key, st);
+		if (ret < 0) return 1;
+		if (e != ret) return 0;
+	}
+	int f = bt_forced_get(W.forced[e], axis) + dir;
+	W.forced[e] = bt_forced_set(W.forced[e], axis, f);
+	if (f == dir * 15) { /* "Safety crush!" */
+		bt_crush(W, e, key, st);
+		return 1;
+	}
+	int4 fh = W.forcedHoldees[e];
+	bt_set3(fh, axis, prev);
+	W.forcedHoldees[e] = fh;
+	return 0;
+}
+
+/* getPushDv ent.cpp:527-540 */
+static BT_HD void bt_push_dv(const DevWorld &W, i32 dv[3], i32 e, i32 o, int axis, int dir, i32 accel) {
+	int4 ve = W.vel[e], vo = W.vel[o];
+	i32 d[3] = {vo.x - ve.x, vo.y - ve.y, vo.z - ve.z};
+	dv[0] = d[0]; dv[1] = d[1]; dv[2] = d[2];
+	dv[axis] = 0;
+	bt_bound_vec(dv, W.friction[e], 3);
+	dv[axis] = accel * dir;
+}
+
+/* doPushRegular ent.cpp:551-577 */
+static BT_HD void bt_push_regular(const DevWorld &W, i32 e, i32 o, int axis, int dir, i32 displacement,
+                                  const i32 dv[3], u32 key, LocalStats &st) {
+	i32 prev = -1;
+	while (1) {
+		if (bt_push_helper(W, e, prev, axis, dir, key, st)) break;
+		if ((W.hphys[e] >> 16) & 0xff) {
+			i32 accel = dv[axis] * dir;
+			if (bt_pushed_handler(W, e, o, axis, dir, accel)) {
+				bt_crush(W, e, key, st);
+				break;
+			}
+		}
+		prev = e;
+		e = W.holder[e];
+		if (e >= 0) {
+			i32 hf = W.holdFlags[prev];
+			if (hf == HOLD_PASS) continue;
+			if (hf == HOLD_DROP) bt_fumble(W, prev, st);
+		}
+		i32 dc[3] = {0, 0, 0};
+		dc[axis] = displacement * dir;
+		bt_move_recursive(W, prev, dc, dv);
+		break;
+	}
+}
+
+/* push ent.cpp:579-629.  None of the device push handlers asks for a pickup, so the
+ * doPushPickup branches (ent.cpp:598-609, 621-622) reduce to the regular ones. */
+static BT_HD void bt_push(const DevWorld &W, const Coll &c, u32 key, LocalStats &st) {
+	st.push++;
+	i32 e = c.leaf, o = c.buddy;
+	int axis = c.axis, dir = c.dir;
+	i32 displacement = (bt_get3(W.center[o], axis) - bt_get3(W.center[e], axis)) * dir + bt_get3(W.radius[e], axis) +
+	                   bt_get3(W.radius[o], axis);
+	i32 accel = (bt_get3(W.vel[o], axis) - bt_get3(W.vel[e], axis)) * dir;
+	if (accel < 0) accel = 0;
+	if (c.mutual) {
+		bt_push_handler(W, o, e);
+		bt_push_handler(W, e, o);
+		i32 dv1[3], dv2[3];
+		bt_push_dv(W, dv1, e, o, axis, dir, accel);
+		bt_push_dv(W, dv2, o, e, axis, -dir, accel);
+		bt_push_regular(W, e, o, axis, dir, displacement, dv1, key, st);
+		bt_push_regular(W, o, e, axis, -dir, displacement, dv2, key, st);
+	} else {
+		bt_push_handler(W, o, e);
+		i32 dv[3];
+		bt_push_dv(W, dv, e, o, axis, dir, accel);
+		bt_push_regular(W, e, o, axis, dir, displacement, dv, key, st);
+	}
+}
+
+/* event-order key of a push: iteration counter, then descending root index */
+static BT_HD u32 bt_push_key(const DevWorld &W, i32 root) {
+	return ((u32)W.iter_id << 20) ^ (u32)(0xfffff - (root & 0xfffff));
+}
+
+/* parallel lane: one thread per ready root (ent.cpp:879-882) */
+static BT_HD void t_push(const DevWorld &W, i32 e, LocalStats &st) {
+	if (e >= W.n || W.ready[e] != 1) return;
+	bt_push(W, bt_unpack_coll(W.pend[e]), bt_push_key(W, e), st);
+}
+
+/* serial lane: one thread, descending root index (DESIGN.md "Canonical order" B3) */
+static BT_HD void t_push_serial(const DevWorld &W, LocalStats &st) {
+	i32 n = (i32)W.ctr[CT_SERIAL_N];
+	if (n > W.serial_cap) n = W.serial_cap;
+	for (i32 i = 1; i < n; i++) { /* insertion sort, descending */
+		i32 v = W.serialList[i];
+		i32 j = i - 1;
+		while (j >= 0 && W.serialList[j] < v) { W.serialList[j + 1] = W.serialList[j]; j--; }
+		W.serialList[j + 1] = v;
+	}
+	for (i32 i = 0; i < n; i++) {
+		i32 e = W.serialList[i];
+		bt_push(W, bt_unpack_coll(W.pend[e]), bt_push_key(W, e), st);
+	}
+	W.ctr[CT_SERIAL_N] = 0;
+}
+
+/* ent.cpp:883-887: every root that had a pending collision forgets it and re-arms
+ * collision checks for its (post-push) tree */
+static BT_HD void t_post(const DevWorld &W, i32 e) {
+	if (e >= W.n || W.pend[e] == 0) return;
+	W.pend[e] = 0;
+	W.ready[e] = 0;
+	BT_FOR_SUBTREE(W, e, it, W.needsCollision[it] = 1); /* requireCollisionRecursive ent.cpp:128-134 */
+}
+
+/* ------------------------------------------------------------------------- */
+/* flushes, gravity, integration                                             */
+
+/* flushCtrls ent.cpp:32-37 + detection of work for the serial part of flush1 */
+static BT_HD void t_pre(const DevWorld &W, i32 e, u32 phases) {
+	if (e >= W.n || !W.inList[e]) return;
+	if (phases & BT_PHASE_CTRLS) {
+		W.btn_v[e] = W.btn_v2[e];
+		W.btn_v2[e] = 0;
+	}
+}
+
+/* marks worlds whose flush1 has deaths / drops / pickups to apply */
+static BT_HD void t_flush_scan(const DevWorld &W, i32 e) {
+	if (e >= W.n || !W.inList[e]) return;
+	if (W.dead_max0[e] | W.dead_max1[e] | W.newDrop[e] | (W.newHolder[e] >= 0)) {
+		W.wflush[W.world[e]] = 1;
+		W.ctr[CT_FLUSH_WORK] = 1;
+	}
+}
+
+/* flush1 ent.cpp:794-802, serial part, one thread per world: flushDeaths :747-761,
+ * flushDrops :765-773.  flushPickups (:775-792) is host-side in this version: a pending
+ * newHolder raises BT_ERR_UNSUPPORTED instead of being silently dropped. */
+static BT_HD void t_flush_serial(const DevWorld &W, i32 g, LocalStats &st) {
+	if (g >= W.n_worlds) return;
+	W.flip[g] ^= 1;
+	if (!W.wflush[g]) return;
+	W.wflush[g] = 0;
+	int slot = 1 ^ W.flip[g];
+	for (i32 i = W.wend[g] - 1; i >= W.wbegin[g]; i--) {
+		if (!W.inList[i]) continue;
+		u8 d = slot ? W.dead_max1[i] : W.dead_max0[i];
+		if (d) {
+			bt_crush(W, i, 0xffffffffu - (u32)i, st);
+			W.dead[i] = d;
+		}
+	}
+	for (i32 i = W.wend[g] - 1; i >= W.wbegin[g]; i--) {
+		if (!W.inList[i]) continue;
+		if (W.newDrop[i]) {
+			W.newDrop[i] = 0;
+			bt_fumble(W, i, st);
+		}
+		if (W.newHolder[i] >= 0) W.ctr[CT_ERROR] = (u32)(-BT_ERR_UNSUPPORTED);
+	}
+}
+
+/* flushMisc ent.cpp:674-714 */
+static BT_HD void t_flush_misc(const DevWorld &W, i32 e) {
+	if (e >= W.n || !W.inList[e]) return;
+	if (W.fullFlush[e]) {
+		W.fullFlush[e] = 0;
+		for (int s = W.slider_off[e]; s < W.slider_off[e + 1]; s++) {
+			if (W.smax[s] < W.smin[s]) continue;
+			W.sv[s] = (i32)(((long long)W.smax[s] + W.smin[s]) / 2);
+			W.smax[s] = INT32_MIN;
+			W.smin[s] = INT32_MAX;
+		}
+		if (W.ntype[e] != W.type[e] || W.collide[e] != W.ncollide[e]) {
+			W.type[e] = W.ntype[e];
+			W.collide[e] = W.ncollide[e];
+			u8 nb = (u8)bt_needs_box(W.type[e], W.collide[e]); /* fixHasVelbox ent.cpp:79-89 */
+			if (nb && !W.hasBox[e]) W.ctr[CT_NEED_REBUILD] = 1;
+			W.hasBox[e] = nb;
+		}
+	}
+	i32 base = W.wire_off[e];
+	i32 cnt = W.wire_cnt[e];
+	for (i32 i = 0; i < cnt; i++) {
+		i32 x = W.wire_to[base + i];
+		if (W.dead[x]) { /* quickRmAt: pull the last wire into this place (list.h) */
+			W.wire_to[base + i] = W.wire_to[base + (--cnt)];
+			i--;
+		}
+	}
+	W.wire_cnt[e] = cnt;
+}
+
+/* doGravity effects.cpp:35-41 */
+static BT_HD void t_gravity(const DevWorld &W, i32 e) {
+	if (e >= W.n || !W.inList[e] || W.holder[e] >= 0) return;
+	if (!(W.gamerules[W.world[e]] & EFFECT_GRAV)) return;
+	if (W.type[e] & T_WEIGHTLESS) return;
+	W.d_vel[e].z += 32;
+	W.ctr[CT_ANY_DELTA] = 1;
+}
+
+/* flush2 / flushPosVel ent.cpp:716-744, 806-811 as a gather: every entity sums the pending
+ * deltas of itself and its holders (they are only zeroed by the following kernel) */
+static BT_HD void t_flush2_apply(const DevWorld &W, i32 e) {
+	if (e >= W.n || !W.inList[e]) return;
+	i32 dc[3] = {0, 0, 0}, dv[3] = {0, 0, 0};
+	for (i32 x = e; x >= 0; x = W.holder[x]) {
+		int4 a = W.d_center[x], b = W.d_vel[x];
+		dc[0] += a.x; dc[1] += a.y; dc[2] += a.z;
+		dv[0] += b.x; dv[1] += b.y; dv[2] += b.z;
+	}
+	if ((dc[0] | dc[1] | dc[2]) != 0) {
+		int4 c = W.center[e], o = W.old[e];
+		c.x += dc[0]; c.y += dc[1]; c.z += dc[2];
+		o.x += dc[0]; o.y += dc[1]; o.z += dc[2];
+		W.center[e] = c;
+		W.old[e] = o;
+	}
+	if ((dv[0] | dv[1] | dv[2]) != 0) {
+		int4 v = W.vel[e];
+		v.x += dv[0]; v.y += dv[1]; v.z += dv[2];
+		W.vel[e] = v;
+	}
+}
+
+static BT_HD void t_zero_deltas(const DevWorld &W, i32 e) {
+	if (e >= W.n) return;
+	W.d_center[e] = make_int4(0, 0, 0, 0);
+	W.d_vel[e] = make_int4(0, 0, 0, 0);
+}
+
+/* integrate loop ent.cpp:845-858 (+ zeroing of the deltas flush2 just applied) */
+static BT_HD void t_integrate(const DevWorld &W, i32 e) {
+	if (e >= W.n) return;
+	W.d_center[e] = make_int4(0, 0, 0, 0);
+	W.d_vel[e] = make_int4(0, 0, 0, 0);
+	if (!W.inList[e]) return;
+	int4 c = W.center[e], v = W.vel[e];
+	W.old[e] = c;
+	c.x += v.x; c.y += v.y; c.z += v.z;
+	W.center[e] = c;
+	W.forced[e] = 0;
+	W.needsCollision[e] = 1;
+}
+
+/* Fast path of flush2 + doGravity + integrate when no delta is pending anywhere except the
+ * gravity this very kernel stands for: nothing is read from or written to d_center / d_vel.
+ * Gravity reaches every member of a tree whose root is not weightless, exactly what
+ * uVel(root) + flushPosVel do.  (ent.cpp:806-811, effects.cpp:35-41, ent.cpp:845-858) */
+static BT_HD void t_begin_fused(const DevWorld &W, i32 e, int gravity) {
+	if (e >= W.n || !W.inList[e]) return;
+	int4 c = W.center[e], v = W.vel[e];
+	if (gravity) {
+		i32 r = W.holdRoot[e];
+		if ((W.gamerules[W.world[e]] & EFFECT_GRAV) && !(W.type[r] & T_WEIGHTLESS)) {
+			v.z += 32;
+			W.vel[e] = v;
+		}
+	}
+	W.old[e] = c;
+	c.x += v.x; c.y += v.y; c.z += v.z;
+	W.center[e] = c;
+	W.forced[e] = 0;
+	W.needsCollision[e] = 1;
+}
+
+/* state hash (DESIGN.md "State hash"), summed per world with 64-bit atomics */
+static BT_HD u64 bt_ent_hash(const DevWorld &W, i32 e) {
+	int4 c = W.center[e], v = W.vel[e];
+	i32 hd = W.holder[e];
+	i32 wd[10] = {c.x, c.y, c.z, v.x, v.y, v.z, (i32)W.type[e], (i32)W.collide[e], hd >= 0 ? W.uid[hd] : -1,
+	              W.holdFlags[e]};
+	u64 h = bt_mix64((u64)(u32)W.uid[e] + 0x9E3779B97F4A7C15ULL);
+	for (int k = 0; k < 10; k++) h = bt_mix64(h + (u64)(u32)wd[k] + 0x9E3779B97F4A7C15ULL);
+	return h;
+}
+
+#endif

@@ -1,0 +1,177 @@
+/*
+ * bt_raycast.cuh — batched selectCast (raycast.cpp:16-57) over an LBVH of ALL live
+ * entities (the reference tests every ent, boxed or not, raycast.cpp:33).
+ *
+ * The reference is a brute-force scan in gs->ents order (newest first) that keeps a hit
+ * only if it is STRICTLY nearer than the best so far, so the winner is the hit with the
+ * smallest entry parameter `lower`, ties going to the entity met first, i.e. the larger
+ * index.  That is an order-independent reduction, which is what lets a tree traversal
+ * in arbitrary order return exactly the same entity.  All parameters are exact
+ * rationals n/d compared by 64-bit cross-multiplication like the reference's lt().
+ */
+#ifndef BT_RAYCAST_CUH
+#define BT_RAYCAST_CUH
+
+#include "bt_phys.cuh"
+
+struct Rat {
+	i32 n, d;
+};
+/* lt() raycast.cpp:14 */
+static BT_HD int rat_lt(const Rat &a, const Rat &b) { return (long long)a.n * b.d < (long long)b.n * a.d; }
+
+/* The reference's per-entity slab test (raycast.cpp:36-50) with `upper` starting at the
+ * largest rational instead of the running best; returns 1 and *out = lower on a hit. */
+static BT_HD int ray_hit_ent(const i32 pos[3], const i32 look[3], const i32 flip[3], const int4 &c, const int4 &r,
+                             Rat *out) {
+	const i32 cc[3] = {c.x, c.y, c.z}, rr[3] = {r.x, r.y, r.z};
+	Rat lower = {0, 1};
+	Rat upper = {INT32_MAX, 1};
+#pragma unroll
+	for (int d = 0; d < 3; d++) {
+		i32 x = flip[d] * (cc[d] - pos[d]);
+		Rat f1 = {x - rr[d], look[d]}, f2 = {x + rr[d], look[d]};
+		if (rat_lt(lower, f1)) lower = f1;
+		if (rat_lt(f2, upper)) upper = f2;
+		if (!rat_lt(lower, upper)) return 0;
+	}
+	if (!lower.n) return 0; /* only things a positive distance in front of us (raycast.cpp:51) */
+	*out = lower;
+	return 1;
+}
+
+/* conservative slab test of a node box against the ray, pruned by the best hit so far:
+ * a subtree is skipped only if every entity in it would enter strictly after `best`. */
+static BT_HD int ray_hit_box(const i32 pos[3], const i32 look[3], const i32 flip[3], const i32 lo[3], const i32 hi[3],
+                             const Rat &best) {
+	Rat lower = {0, 1};
+	Rat upper = {INT32_MAX, 1};
+#pragma unroll
+	for (int d = 0; d < 3; d++) {
+		/* in sign-folded coordinates the box spans [a, b] */
+		long long a64 = flip[d] > 0 ? (long long)lo[d] - pos[d] : (long long)pos[d] - hi[d];
+		long long b64 = flip[d] > 0 ? (long long)hi[d] - pos[d] : (long long)pos[d] - lo[d];
+		/* clamp to int32: boxes of huge entities may exceed it; clamping only widens */
+		i32 a = a64 < INT32_MIN ? INT32_MIN : (a64 > INT32_MAX ? INT32_MAX : (i32)a64);
+		i32 b = b64 < INT32_MIN ? INT32_MIN : (b64 > INT32_MAX ? INT32_MAX : (i32)b64);
+		Rat f1 = {a, look[d]}, f2 = {b, look[d]};
+		if (look[d] == 0) {
+			if (a > 0 || b < 0) return 0; /* origin outside the slab on an axis we do not move along */
+			continue;
+		}
+		if (rat_lt(lower, f1)) lower = f1;
+		if (rat_lt(f2, upper)) upper = f2;
+		if (rat_lt(upper, lower)) return 0; /* empty even when touching is allowed */
+	}
+	if (rat_lt(best, lower)) return 0; /* enters strictly after the best hit */
+	return 1;
+}
+
+/* one ray: origin entity `p` (its hold tree is skipped), direction look[3] */
+static BT_HD i32 t_raycast(const DevWorld &W, i32 p, const i32 look_in[3], i32 *stack, int stride) {
+	int L = W.n_leaves;
+	if (L < 1) return -1;
+	int4 pc = W.center[p];
+	const i32 pos[3] = {pc.x, pc.y, pc.z};
+	i32 look[3], flip[3];
+	for (int i = 0; i < 3; i++) { /* raycast.cpp:20-28 (on a private copy) */
+		if (look_in[i] >= 0) { flip[i] = 1; look[i] = look_in[i]; }
+		else { flip[i] = -1; look[i] = -look_in[i]; }
+	}
+	i32 root = W.holdRoot[p];
+	u32 wp = (u32)W.world[p];
+	Rat best = {INT32_MAX, 1};
+	i32 winner = -1;
+#define RAY_LEAF(t)                                                                              \
+	do {                                                                                         \
+		i32 e_ = W.leafEnt[t];                                                                   \
+		if (W.inList[e_] && W.holdRoot[e_] != root && (u32)W.world[e_] == wp) {                  \
+			Rat lw_;                                                                             \
+			if (ray_hit_ent(pos, look, flip, W.center[e_], W.radius[e_], &lw_)) {                \
+				if (rat_lt(lw_, best) || (winner >= 0 && !rat_lt(best, lw_) && e_ > winner)) { best = lw_; winner = e_; } \
+			}                                                                                    \
+		}                                                                                        \
+	} while (0)
+	if (L == 1) {
+		RAY_LEAF(0);
+		return winner;
+	}
+	int sp = 0, node = 0;
+	while (1) {
+		const BvhNode &N = W.nodes[node];
+		i32 li = N.left, ri = N.right;
+		int ovL = (N.wl & 0xffff) <= wp && wp <= (N.wl >> 16) && ray_hit_box(pos, look, flip, N.llo, N.lhi, best);
+		int ovR = (N.wr & 0xffff) <= wp && wp <= (N.wr >> 16) && ray_hit_box(pos, look, flip, N.rlo, N.rhi, best);
+		if (ovL && li < 0) RAY_LEAF(~li);
+		if (ovR && ri < 0) RAY_LEAF(~ri);
+		int goL = ovL && li >= 0, goR = ovR && ri >= 0;
+		if (goL) {
+			node = li;
+			if (goR) {
+				if (sp < BT_STACK) stack[(sp++) * stride] = ri;
+				else W.ctr[CT_ERROR] = (u32)(-BT_ERR_OVERFLOW);
+			}
+		} else if (goR) {
+			node = ri;
+		} else {
+			if (sp == 0) break;
+			node = stack[(--sp) * stride];
+		}
+	}
+#undef RAY_LEAF
+	return winner;
+}
+
+#ifndef BT_EMU
+/* origin/winner are LIVE RANKS (oldest-first order of bt_world_download); rank2slot /
+ * slot2rank translate to device slots. */
+__global__ void __launch_bounds__(128) k_raycast(DevWorld W, const i32 *origin, const i32 *look, i32 n_rays,
+                                                  i32 *winner, const i32 *rank2slot, const i32 *slot2rank) {
+	__shared__ i32 stacks[BT_STACK * 128];
+	i32 i = (i32)(blockIdx.x * blockDim.x + threadIdx.x);
+	if (i >= n_rays) return;
+	i32 lk[3] = {look[3 * i], look[3 * i + 1], look[3 * i + 2]};
+	i32 win = t_raycast(W, rank2slot[origin[i]], lk, stacks + threadIdx.x, 128);
+	winner[i] = win >= 0 ? slot2rank[win] : -1;
+}
+
+/* exclusive scan of inList -> live rank per slot (single block; raycast setup only) */
+__global__ void __launch_bounds__(1024) k_live_ranks(DevWorld W, i32 *rank2slot, i32 *slot2rank) {
+	__shared__ u32 warpTot[32];
+	__shared__ u32 carry;
+	if (threadIdx.x == 0) carry = 0;
+	__syncthreads();
+	for (int base = 0; base < W.n; base += 1024) {
+		int i = base + threadIdx.x;
+		u32 v = (i < W.n && W.inList[i]) ? 1u : 0u;
+		u32 x = v;
+#pragma unroll
+		for (int off = 1; off < 32; off <<= 1) {
+			u32 y = __shfl_up_sync(0xffffffffu, x, off);
+			if ((threadIdx.x & 31) >= off) x += y;
+		}
+		if ((threadIdx.x & 31) == 31) warpTot[threadIdx.x >> 5] = x;
+		__syncthreads();
+		if (threadIdx.x < 32) {
+			u32 t = warpTot[threadIdx.x], s = t;
+#pragma unroll
+			for (int off = 1; off < 32; off <<= 1) {
+				u32 y = __shfl_up_sync(0xffffffffu, s, off);
+				if (threadIdx.x >= off) s += y;
+			}
+			warpTot[threadIdx.x] = s - t;
+		}
+		__syncthreads();
+		u32 excl = carry + warpTot[threadIdx.x >> 5] + x - v;
+		if (i < W.n) {
+			slot2rank[i] = v ? (i32)excl : -1;
+			if (v) rank2slot[excl] = i;
+		}
+		__syncthreads();
+		if (threadIdx.x == 1023) carry = excl + v;
+		__syncthreads();
+	}
+}
+#endif
+
+#endif

@@ -1,0 +1,176 @@
+/*
+ * bt_types.h — device-side world layout (structure of arrays, int32) and small helpers
+ * shared by every kernel of the bittoss_b200 hot path.
+ *
+ * Layout in HBM (all arrays have `cap` slots; slot index = upload index, never reused):
+ *   int4  center/old/vel/radius/d_center/d_vel   xyz + pad  -> one 128-bit load per field
+ *   u32   type/collide/ntype/ncollide, i32 links (holder, holdee, LLn, LLp, holdRoot)
+ *   u64   pend            one pending collision per hold root, packed (see bt_pack_coll)
+ *   u8    flag arrays     needsCollision, hasBox, inList, dead, ...
+ *   BvhNode[L-1]          64-byte nodes: both children's boxes + world range + child ids
+ *
+ * The bodies in bt_phys.cuh are written per logical thread and compile both for
+ * sm_100a (the product) and, under BT_EMU, for the host so tests/emu can single-step
+ * the exact same logic on a machine without a GPU.  BT_EMU is test tooling only; the
+ * shipped library has no host execution path.
+ */
+#ifndef BT_TYPES_H
+#define BT_TYPES_H
+
+#include <stdint.h>
+
+#ifdef BT_EMU
+#define BT_HD
+#define BT_D
+struct int4 { int x, y, z, w; };
+static inline int4 make_int4(int x, int y, int z, int w) { int4 r = {x, y, z, w}; return r; }
+#else
+#include <cuda_runtime.h>
+#define BT_HD __device__ __forceinline__
+#define BT_D __device__ __forceinline__
+#endif
+
+#include "../../include/bittoss_b200.h"
+
+typedef unsigned long long u64;
+typedef uint32_t u32;
+typedef int32_t i32;
+typedef uint8_t u8;
+
+/* ent.h:243-284 */
+#define MOVE_ME 1
+#define MOVE_HIM 2
+#define MOVE_BOTH 7
+#define MOVE_NONE 15
+#define HOLD_PASS 0
+#define HOLD_DROP 1
+#define HOLD_MOVE 2
+#define HOLD_MASK 3
+#define HOLD_FREEZE 4
+#define T_HEAVY 1u
+#define T_TERRAIN 2u
+#define T_OBSTACLE 4u
+#define T_DEBRIS 8u
+#define T_WEIGHTLESS 16u
+#define T_FLAG 32u
+#define TEAM_BIT 256u
+#define TEAM_MASK (7u * TEAM_BIT)
+#define T_COLLIDABLE (T_HEAVY + T_TERRAIN + T_OBSTACLE + T_DEBRIS + T_FLAG)
+#define EFFECT_GRAV (1 << 3)
+
+/* 64-byte LBVH node: boxes of both children, so one node fetch decides two subtrees.
+ * wl/wr pack the world-id range of each child as lo | hi<<16 (batched worlds). */
+struct __attribute__((aligned(64))) BvhNode {
+	i32 llo[3], lhi[3];
+	i32 rlo[3], rhi[3];
+	i32 left, right; /* >= 0 internal node, < 0 leaf position ~x */
+	u32 wl, wr;
+};
+
+struct __attribute__((aligned(16))) Box6 { /* own box of a node or leaf, used only while refitting */
+	int4 lo; /* xyz min, w = lowest world id */
+	int4 hi; /* xyz max, w = highest world id */
+};
+
+/* device-side counters / flags block (one per bt_world) */
+enum {
+	CT_ANY_PROPOSAL = 0, /* doIteration's return value (ent.cpp:456,866) */
+	CT_SERIAL_N,         /* entries in serialList */
+	CT_DEAD_N,           /* entries in deadList */
+	CT_ERROR,            /* BT_ERR_* raised on device */
+	CT_NEED_REBUILD,     /* leaf set changed (an entity gained a box) */
+	CT_ANY_DELTA,        /* some d_center / d_vel is non-zero */
+	CT_FLUSH_WORK,       /* some world needs the serial part of flush1 */
+	CT_N_LEAVES,
+	CT_BOUNDS,           /* 6 ints: min xyz, max xyz of leaf centres */
+	CT_STAT0 = 16,       /* 64-bit stats start here (as pairs of u32 slots, 8-byte aligned) */
+	CT_WORDS = 64
+};
+enum { SK_ITERS = 0, SK_CAND, SK_POS, SK_PUSH, SK_SERIAL, SK_CRUSH, SK_FUMBLE, SK_NUM };
+
+struct DevWorld {
+	i32 n;        /* slots in use */
+	i32 n_worlds;
+	i32 n_leaves; /* leaves of the current tree (host copy) */
+	i32 key_shift[3];
+	i32 world_bits;
+	i32 serial_cap, dead_cap;
+	i32 iter_id; /* running doIteration counter, for event ordering keys */
+	i32 ray_mode; /* 1: tree over ALL live entities with static boxes (raycast), 0: collision tree */
+
+	i32 *wbegin, *wend, *flip, *gamerules, *rnd; /* per world */
+	u8 *wflush;                                  /* per world: serial flush1 work pending */
+
+	i32 *world, *uid;
+	int4 *center, *old, *vel, *radius, *d_center, *d_vel;
+	u32 *type, *collide, *ntype, *ncollide;
+	i32 *friction, *holder, *holdFlags, *holdRoot, *holdee, *LLn, *LLp, *newHolder, *newHoldFlags;
+	u32 *hphys; /* whoMoves | push<<8 | pushed<<16 | crush<<24  (catalog IDs) */
+	u32 *hpair; /* onFumble | onFumbled<<8 | onPickUp<<16 | onPickedUp<<24 */
+	u32 *htick; /* tick | tickHeld<<8 (carried for the host) */
+	u32 *btn_v, *btn_v2; /* 4 x u8 packed */
+	u8 *newDrop, *dead_max0, *dead_max1, *fullFlush, *dead, *inList, *needsCollision, *hasBox;
+	u8 *ready; /* 0 no, 1 push in parallel lane, 2 push in serial lane */
+	u32 *forced;        /* 3 x int8 packed: x | y<<8 | z<<16 */
+	int4 *forcedHoldees;
+	u64 *pend;
+	i32 *slider_off, *sv, *smin, *smax;
+	i32 *wire_off, *wire_cnt, *wire_to;
+
+	/* broadphase */
+	u64 *keys, *keys_alt;
+	i32 *leafEnt, *leafEnt_alt; /* sorted leaf position -> entity */
+	i32 *leafParent, *nodeParent;
+	u32 *nodeCount;
+	BvhNode *nodes;
+	Box6 *nodeBox, *leafBox;
+
+	i32 *serialList;
+	u64 *deadList; /* key<<32 | entity */
+	u64 *hash;     /* per world */
+	u32 *ctr;      /* CT_WORDS */
+};
+
+/* ---- packed pending collision (the 5 collision* fields of ent.h:79-85) ----
+ * bit 63 valid | buddy 29 | leaf 29 | axis 2 | dir 1 (1 = +1) | mutual 2
+ * The tie-break key of DESIGN.md "Canonical order" is the value without the
+ * mutual bits: larger (buddy, leaf, axis, dir) wins a full tie. */
+struct Coll {
+	i32 leaf, buddy;
+	int axis, dir, mutual;
+};
+#define BT_MAX_ENTS (1 << 29)
+
+static BT_HD u64 bt_pack_coll(const Coll &c) {
+	return (1ull << 63) | ((u64)(u32)c.buddy << 34) | ((u64)(u32)c.leaf << 5) | ((u64)c.axis << 3) |
+	       ((u64)(c.dir > 0 ? 1 : 0) << 2) | (u64)c.mutual;
+}
+static BT_HD Coll bt_unpack_coll(u64 p) {
+	Coll c;
+	c.buddy = (i32)((p >> 34) & 0x1fffffffu);
+	c.leaf = (i32)((p >> 5) & 0x1fffffffu);
+	c.axis = (int)((p >> 3) & 3);
+	c.dir = ((p >> 2) & 1) ? 1 : -1;
+	c.mutual = (int)(p & 3);
+	return c;
+}
+
+static BT_HD int bt_get3(const int4 &v, int k) { return k == 0 ? v.x : (k == 1 ? v.y : v.z); }
+static BT_HD void bt_set3(int4 &v, int k, int val) {
+	if (k == 0) v.x = val;
+	else if (k == 1) v.y = val;
+	else v.z = val;
+}
+static BT_HD int bt_forced_get(u32 f, int axis) { return (int)(int8_t)((f >> (8 * axis)) & 0xff); }
+static BT_HD u32 bt_forced_set(u32 f, int axis, int val) {
+	return (f & ~(0xffu << (8 * axis))) | (((u32)(uint8_t)(int8_t)val) << (8 * axis));
+}
+
+static BT_HD u64 bt_mix64(u64 x) {
+	x ^= x >> 30; x *= 0xbf58476d1ce4e5b9ULL;
+	x ^= x >> 27; x *= 0x94d049bb133111ebULL;
+	x ^= x >> 31;
+	return x;
+}
+
+#endif

@@ -1,0 +1,852 @@
+/*
+ * bt_world.cu — host side of the C ABI (include/bittoss_b200.h): device memory, the
+ * per-tick kernel schedule, upload/download between the caller's plain arrays and the
+ * device SoA.  One bt_world = one CUDA stream; every kernel of a world runs on it.
+ *
+ * Tick schedule (reference order main.cpp:1072-1097, ent.cpp:842-911):
+ *   k_pre                       flushCtrls
+ *   flush1: k_flush_scan, k_flush_serial, k_flush_misc
+ *   k_begin_fused               doGravity + flush2 + integrate (fast path, no pending deltas)
+ *     or k_gravity, k_flush2_apply, k_integrate
+ *   every `rebuild_every` ticks: k_bounds, k_morton, radix sort, k_lbvh   (LBVH build)
+ *   loop: k_refit, k_collide -> (host reads "any proposal") -> k_decide, k_conflict,
+ *         k_push, k_push_serial, k_post
+ *   flush1 again, (flush2 if deltas), k_hash on request
+ */
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <vector>
+#include <algorithm>
+
+#include "bt_kernels.cuh"
+#include "bt_raycast.cuh"
+
+static thread_local char g_err[512] = "";
+static void set_err(const char *fmt, const char *a, const char *b, int line) {
+	snprintf(g_err, sizeof g_err, fmt, a, b, line);
+}
+#define CK(call)                                                                      \
+	do {                                                                              \
+		cudaError_t _e = (call);                                                      \
+		if (_e != cudaSuccess) {                                                      \
+			set_err("%s failed: %s (bt_world.cu:%d)", #call, cudaGetErrorString(_e), __LINE__); \
+			return BT_ERR_CUDA;                                                       \
+		}                                                                             \
+	} while (0)
+
+enum {
+	PK_PRE = 0, PK_FLUSH, PK_BEGIN, PK_BUILD_KEYS, PK_SORT, PK_LBVH, PK_REFIT, PK_COLLIDE, PK_DECIDE, PK_PUSH,
+	PK_POST, PK_HASH, PK_RAY_BUILD, PK_RAYCAST, PK_EXCHANGE, PK_NUM
+};
+static const char *PK_NAMES[PK_NUM] = {"pre",    "flush1", "begin_integrate", "morton_keys", "radix_sort",
+                                       "lbvh_build", "refit", "collide",       "decide",      "push",
+                                       "post",   "hash",   "ray_tree_build",  "raycast", "host_exchange"};
+
+typedef long long i64;
+
+/* second LBVH (all live entities, static boxes) + live-rank maps for bt_raycast_* */
+struct RayTree {
+	u64 *keys, *keys_alt;
+	i32 *leafEnt, *leafEnt_alt, *leafParent, *nodeParent;
+	u32 *nodeCount;
+	BvhNode *nodes;
+	Box6 *nodeBox, *leafBox;
+	i32 *rank2slot, *slot2rank;
+	i32 n_leaves;
+	i32 key_shift[3];
+};
+
+struct bt_world {
+	int device;
+	cudaStream_t stream;
+	i32 cap_ents, cap_sliders, cap_wires, cap_worlds;
+	DevWorld W;
+	std::vector<void *> allocs;
+	u32 *h_flag; /* pinned, CT_WORDS words */
+	u64 *d_hsum; u32 *d_hcnt;
+	u32 *d_sorthist; int sorthist_len;
+	bool tree_valid, deltas_pending;
+	i32 ticks_since_build;
+	i64 rebuild_every;
+	i64 max_iterations;
+	bt_tick_stats stats;
+	bool profiling;
+	cudaEvent_t ev0, ev1;
+	i64 prof_launches[PK_NUM];
+	double prof_ms[PK_NUM];
+	std::vector<i32> up_root_order; /* per slot, from the last upload */
+	/* raycast tree (all live entities, static boxes) */
+	RayTree ray;
+	bool ray_valid;
+	i32 *d_stage_a, *d_stage_b; /* 3*cap ints each, staging for the per-tick host exchange */
+	bool ranks_valid;           /* ray.slot2rank reflects the current live set */
+};
+template <typename T> static int dalloc(bt_world *w, T **p, size_t count) {
+	void *q = NULL;
+	cudaError_t e = cudaMalloc(&q, sizeof(T) * (count ? count : 1));
+	if (e != cudaSuccess) {
+		set_err("%s failed: %s (bt_world.cu:%d)", "cudaMalloc", cudaGetErrorString(e), __LINE__);
+		return BT_ERR_CUDA;
+	}
+	cudaMemset(q, 0, sizeof(T) * (count ? count : 1));
+	w->allocs.push_back(q);
+	*p = (T *)q;
+	return 0;
+}
+
+/* launch helper: counts launches and, while profiling, brackets each one with events */
+#define LAUNCH(w, cls, kern, grid, block, ...)                                         \
+	do {                                                                               \
+		if ((grid) > 0) {                                                              \
+			if ((w)->profiling) cudaEventRecord((w)->ev0, (w)->stream);                \
+			kern<<<(grid), (block), 0, (w)->stream>>>(__VA_ARGS__);                    \
+			(w)->stats.kernel_launches++;                                              \
+			(w)->prof_launches[cls]++;                                                 \
+			if ((w)->profiling) {                                                      \
+				cudaEventRecord((w)->ev1, (w)->stream);                                \
+				cudaEventSynchronize((w)->ev1);                                        \
+				float ms = 0;                                                          \
+				cudaEventElapsedTime(&ms, (w)->ev0, (w)->ev1);                         \
+				(w)->prof_ms[cls] += ms;                                               \
+			}                                                                          \
+		}                                                                              \
+	} while (0)
+
+static inline int nblk(i64 n, int b = BT_BLOCK) { return (int)((n + b - 1) / b); }
+
+extern "C" {
+
+const char *bt_version(void) { return "bittoss_b200 0.1 (sm_100a)"; }
+const char *bt_last_error(void) { return g_err; }
+
+int bt_device_count(void) {
+	int n = 0;
+	cudaError_t e = cudaGetDeviceCount(&n);
+	if (e != cudaSuccess || n <= 0) {
+		set_err("%s: %s (bt_world.cu:%d)", "no usable CUDA device", cudaGetErrorString(e), __LINE__);
+		return BT_ERR_NO_DEVICE;
+	}
+	return n;
+}
+
+void bt_world_destroy(bt_world *w) {
+	if (!w) return;
+	cudaSetDevice(w->device);
+	for (void *p : w->allocs) cudaFree(p);
+	if (w->h_flag) cudaFreeHost(w->h_flag);
+	if (w->ev0) cudaEventDestroy(w->ev0);
+	if (w->ev1) cudaEventDestroy(w->ev1);
+	if (w->stream) cudaStreamDestroy(w->stream);
+	delete w;
+}
+
+int bt_world_create(bt_world **out, int device, int32_t max_ents, int32_t max_sliders, int32_t max_wires,
+                    int32_t max_worlds) {
+	if (!out || max_ents < 0 || max_sliders < 0 || max_wires < 0 || max_worlds < 1) return BT_ERR_ARG;
+	if (max_ents >= BT_MAX_ENTS || max_worlds > 65535) return BT_ERR_CAPACITY;
+	int nd = bt_device_count();
+	if (nd < 0) return nd;
+	if (device < 0 || device >= nd) return BT_ERR_ARG;
+	CK(cudaSetDevice(device));
+	bt_world *w = new bt_world();
+	memset(&w->W, 0, sizeof(w->W));
+	memset(&w->stats, 0, sizeof(w->stats));
+	memset(w->prof_launches, 0, sizeof(w->prof_launches));
+	memset(w->prof_ms, 0, sizeof(w->prof_ms));
+	memset(&w->ray, 0, sizeof(w->ray));
+	w->device = device;
+	w->cap_ents = max_ents; w->cap_sliders = max_sliders; w->cap_wires = max_wires; w->cap_worlds = max_worlds;
+	w->tree_valid = false; w->deltas_pending = true; w->ticks_since_build = 0;
+	w->rebuild_every = 8; w->max_iterations = 100000; w->profiling = false; w->ray_valid = false;
+	w->h_flag = NULL; w->ev0 = w->ev1 = NULL; w->stream = NULL;
+	*out = w;
+#define TRY(x) do { int _r = (x); if (_r) { bt_world_destroy(w); *out = NULL; return _r; } } while (0)
+#define TRYCU(x) do { cudaError_t _e = (x); if (_e != cudaSuccess) { set_err("%s failed: %s (bt_world.cu:%d)", #x, cudaGetErrorString(_e), __LINE__); bt_world_destroy(w); *out = NULL; return BT_ERR_CUDA; } } while (0)
+	TRYCU(cudaStreamCreateWithFlags(&w->stream, cudaStreamNonBlocking));
+	TRYCU(cudaEventCreate(&w->ev0));
+	TRYCU(cudaEventCreate(&w->ev1));
+	TRYCU(cudaHostAlloc((void **)&w->h_flag, sizeof(u32) * CT_WORDS, cudaHostAllocDefault));
+	DevWorld &W = w->W;
+	size_t n = (size_t)max_ents, nw = (size_t)max_worlds;
+	TRY(dalloc(w, &W.wbegin, nw)); TRY(dalloc(w, &W.wend, nw)); TRY(dalloc(w, &W.flip, nw));
+	TRY(dalloc(w, &W.gamerules, nw)); TRY(dalloc(w, &W.rnd, nw)); TRY(dalloc(w, &W.wflush, nw));
+	TRY(dalloc(w, &W.world, n)); TRY(dalloc(w, &W.uid, n));
+	TRY(dalloc(w, &W.center, n)); TRY(dalloc(w, &W.old, n)); TRY(dalloc(w, &W.vel, n));
+	TRY(dalloc(w, &W.radius, n)); TRY(dalloc(w, &W.d_center, n)); TRY(dalloc(w, &W.d_vel, n));
+	TRY(dalloc(w, &W.type, n)); TRY(dalloc(w, &W.collide, n)); TRY(dalloc(w, &W.ntype, n));
+	TRY(dalloc(w, &W.ncollide, n));
+	TRY(dalloc(w, &W.friction, n)); TRY(dalloc(w, &W.holder, n)); TRY(dalloc(w, &W.holdFlags, n));
+	TRY(dalloc(w, &W.holdRoot, n)); TRY(dalloc(w, &W.holdee, n)); TRY(dalloc(w, &W.LLn, n));
+	TRY(dalloc(w, &W.LLp, n)); TRY(dalloc(w, &W.newHolder, n)); TRY(dalloc(w, &W.newHoldFlags, n));
+	TRY(dalloc(w, &W.hphys, n)); TRY(dalloc(w, &W.hpair, n)); TRY(dalloc(w, &W.htick, n));
+	TRY(dalloc(w, &W.btn_v, n)); TRY(dalloc(w, &W.btn_v2, n));
+	TRY(dalloc(w, &W.newDrop, n)); TRY(dalloc(w, &W.dead_max0, n)); TRY(dalloc(w, &W.dead_max1, n));
+	TRY(dalloc(w, &W.fullFlush, n)); TRY(dalloc(w, &W.dead, n)); TRY(dalloc(w, &W.inList, n));
+	TRY(dalloc(w, &W.needsCollision, n)); TRY(dalloc(w, &W.hasBox, n)); TRY(dalloc(w, &W.ready, n));
+	TRY(dalloc(w, &W.forced, n)); TRY(dalloc(w, &W.forcedHoldees, n)); TRY(dalloc(w, &W.pend, n));
+	TRY(dalloc(w, &W.slider_off, n + 1)); TRY(dalloc(w, &W.sv, (size_t)max_sliders));
+	TRY(dalloc(w, &W.smin, (size_t)max_sliders)); TRY(dalloc(w, &W.smax, (size_t)max_sliders));
+	TRY(dalloc(w, &W.wire_off, n + 1)); TRY(dalloc(w, &W.wire_cnt, n)); TRY(dalloc(w, &W.wire_to, (size_t)max_wires));
+	TRY(dalloc(w, &W.keys, n)); TRY(dalloc(w, &W.keys_alt, n));
+	TRY(dalloc(w, &W.leafEnt, n)); TRY(dalloc(w, &W.leafEnt_alt, n));
+	TRY(dalloc(w, &W.leafParent, n)); TRY(dalloc(w, &W.nodeParent, n)); TRY(dalloc(w, &W.nodeCount, n));
+	TRY(dalloc(w, &W.nodes, n)); TRY(dalloc(w, &W.nodeBox, n)); TRY(dalloc(w, &W.leafBox, n));
+	W.serial_cap = 1 << 16; W.dead_cap = max_ents > 0 ? max_ents : 1;
+	TRY(dalloc(w, &W.serialList, (size_t)W.serial_cap)); TRY(dalloc(w, &W.deadList, (size_t)W.dead_cap));
+	TRY(dalloc(w, &W.hash, nw)); TRY(dalloc(w, &W.ctr, (size_t)CT_WORDS));
+	TRY(dalloc(w, &w->d_hsum, nw)); TRY(dalloc(w, &w->d_hcnt, nw));
+	w->sorthist_len = 256 * (int)((n + SORT_TILE - 1) / SORT_TILE + 1);
+	TRY(dalloc(w, &w->d_sorthist, (size_t)w->sorthist_len));
+	TRY(dalloc(w, &w->ray.keys, n)); TRY(dalloc(w, &w->ray.keys_alt, n));
+	TRY(dalloc(w, &w->ray.leafEnt, n)); TRY(dalloc(w, &w->ray.leafEnt_alt, n));
+	TRY(dalloc(w, &w->ray.leafParent, n)); TRY(dalloc(w, &w->ray.nodeParent, n)); TRY(dalloc(w, &w->ray.nodeCount, n));
+	TRY(dalloc(w, &w->ray.nodes, n)); TRY(dalloc(w, &w->ray.nodeBox, n)); TRY(dalloc(w, &w->ray.leafBox, n));
+	TRY(dalloc(w, &w->ray.rank2slot, n)); TRY(dalloc(w, &w->ray.slot2rank, n));
+	TRY(dalloc(w, &w->d_stage_a, 3 * n)); TRY(dalloc(w, &w->d_stage_b, 3 * n));
+	w->ranks_valid = false;
+#undef TRY
+#undef TRYCU
+	return BT_OK;
+}
+
+void *bt_world_stream(bt_world *w) { return w ? (void *)w->stream : NULL; }
+
+int bt_world_set_option(bt_world *w, const char *name, int64_t value) {
+	if (!w || !name) return BT_ERR_ARG;
+	if (!strcmp(name, "rebuild_every")) { w->rebuild_every = value < 1 ? 1 : value; return BT_OK; }
+	if (!strcmp(name, "max_iterations")) { w->max_iterations = value; return BT_OK; }
+	return BT_ERR_ARG;
+}
+
+/* ---------------------------------------------------------------- upload */
+
+} /* extern "C" */
+template <typename T> static int h2d(bt_world *w, T *dst, const std::vector<T> &src) {
+	if (src.empty()) return 0;
+	CK(cudaMemcpyAsync(dst, src.data(), sizeof(T) * src.size(), cudaMemcpyHostToDevice, w->stream));
+	return 0;
+}
+
+static bool supported(uint32_t mask, int id) { return id < 32 && ((mask >> id) & 1u); }
+extern "C" {
+
+int bt_world_upload(bt_world *w, const bt_world_desc *d) {
+	if (!w || !d || d->n_ents < 0 || d->n_worlds < 1) return BT_ERR_ARG;
+	if (d->n_ents > w->cap_ents || d->n_sliders > w->cap_sliders || d->n_wires > w->cap_wires ||
+	    d->n_worlds > w->cap_worlds)
+		return BT_ERR_CAPACITY;
+	CK(cudaSetDevice(w->device));
+	const int n = d->n_ents, nw = d->n_worlds;
+	/* handler IDs must have device implementations (no silent divergence) */
+	for (int i = 0; i < n; i++) {
+		const uint8_t *h = d->handlers + (size_t)BT_H_NUM * i;
+		const char *bad = NULL;
+		if (!supported(BT_SUPPORTED_WHOMOVES, h[BT_H_WHOMOVES])) bad = "whoMoves";
+		else if (!supported(BT_SUPPORTED_PUSH, h[BT_H_PUSH])) bad = "push";
+		else if (!supported(BT_SUPPORTED_PUSHED, h[BT_H_PUSHED])) bad = "pushed";
+		else if (!supported(BT_SUPPORTED_CRUSH, h[BT_H_CRUSH])) bad = "crush";
+		else
+			for (int k = BT_H_ONFUMBLE; k <= BT_H_ONPICKEDUP; k++)
+				if (!supported(BT_SUPPORTED_PAIR, h[k])) bad = "entPair";
+		if (bad) {
+			snprintf(g_err, sizeof g_err, "entity %d: %s handler id has no device-side implementation", i, bad);
+			return BT_ERR_UNSUPPORTED;
+		}
+	}
+	std::vector<i32> world(n), wbegin(nw, n), wend(nw, 0);
+	for (int i = 0; i < n; i++) {
+		int g = d->world_id ? d->world_id[i] : 0;
+		if (g < 0 || g >= nw) return BT_ERR_ARG;
+		world[i] = g;
+		wbegin[g] = std::min(wbegin[g], i);
+		wend[g] = std::max(wend[g], i + 1);
+	}
+	for (int g = 0; g < nw; g++)
+		if (wbegin[g] > wend[g]) wbegin[g] = wend[g] = 0;
+	auto v3 = [&](const int32_t *src) {
+		std::vector<int4> o(n);
+		for (int i = 0; i < n; i++) o[i] = make_int4(src[3 * i], src[3 * i + 1], src[3 * i + 2], 0);
+		return o;
+	};
+	bool deltas = false;
+	for (int i = 0; i < 3 * n && !deltas; i++) deltas = d->d_center[i] || d->d_vel[i];
+	std::vector<i32> holdRoot(n), LLn(n, -1), LLp(n, -1);
+	for (int i = 0; i < n; i++) {
+		i32 h = d->holder[i];
+		if (h < -1 || h >= n) return BT_ERR_ARG;
+		if (h >= 0) {
+			LLn[i] = d->holdee_next[i];
+			if (LLn[i] >= n) return BT_ERR_ARG;
+			if (LLn[i] >= 0) LLp[LLn[i]] = i;
+		}
+	}
+	for (int i = 0; i < n; i++) {
+		i32 r = i;
+		int guard = 0;
+		while (d->holder[r] >= 0 && guard++ < n) r = d->holder[r];
+		holdRoot[i] = r;
+	}
+	std::vector<u32> hphys(n), hpair(n), htick(n), bv(n), bv2(n), forced(n, 0);
+	std::vector<u8> newDrop(n), dm0(n), dm1(n), ff(n), dead(n, 0), inList(n, 1), needsC(n, 0), hasBox(n), ready(n, 0);
+	std::vector<int4> fh(n, make_int4(-1, -1, -1, 0));
+	std::vector<u64> pend(n, 0);
+	std::vector<i32> wire_cnt(n);
+	for (int i = 0; i < n; i++) {
+		const uint8_t *h = d->handlers + (size_t)BT_H_NUM * i;
+		hphys[i] = h[BT_H_WHOMOVES] | (h[BT_H_PUSH] << 8) | (h[BT_H_PUSHED] << 16) | ((u32)h[BT_H_CRUSH] << 24);
+		hpair[i] = h[BT_H_ONFUMBLE] | (h[BT_H_ONFUMBLED] << 8) | (h[BT_H_ONPICKUP] << 16) | ((u32)h[BT_H_ONPICKEDUP] << 24);
+		htick[i] = h[BT_H_TICK] | (h[BT_H_TICKHELD] << 8);
+		const uint8_t *b = d->btn + 8 * (size_t)i;
+		bv[i] = b[0] | (b[1] << 8) | (b[2] << 16) | ((u32)b[3] << 24);
+		bv2[i] = b[4] | (b[5] << 8) | (b[6] << 16) | ((u32)b[7] << 24);
+		const uint8_t *m = d->misc + (size_t)BT_M_NUM * i;
+		newDrop[i] = m[BT_M_NEWDROP]; dm0[i] = m[BT_M_DEADMAX0]; dm1[i] = m[BT_M_DEADMAX1]; ff[i] = m[BT_M_FULLFLUSH];
+		hasBox[i] = (u8)(d->collide_mask[i] || (d->type_mask[i] & T_COLLIDABLE));
+		wire_cnt[i] = d->wire_off[i + 1] - d->wire_off[i];
+	}
+	DevWorld &W = w->W;
+	W.n = n; W.n_worlds = nw; W.n_leaves = 0; W.iter_id = 0;
+#define UP(dst, vec) do { int _r = h2d(w, dst, vec); if (_r) return _r; } while (0)
+#define UPRAW(dst, src, cnt, T) do { if ((cnt) > 0) CK(cudaMemcpyAsync(dst, src, sizeof(T) * (size_t)(cnt), cudaMemcpyHostToDevice, w->stream)); } while (0)
+	UP(W.world, world); UP(W.wbegin, wbegin); UP(W.wend, wend);
+	UPRAW(W.flip, d->w_flip_flop, nw, i32); UPRAW(W.gamerules, d->w_gamerules, nw, i32); UPRAW(W.rnd, d->w_rand, nw, i32);
+	UPRAW(W.uid, d->uid, n, i32);
+	{
+		std::vector<int4> a = v3(d->center), b = v3(d->old), c = v3(d->vel), r = v3(d->radius), dc = v3(d->d_center),
+		                  dv = v3(d->d_vel);
+		UP(W.center, a); UP(W.old, b); UP(W.vel, c); UP(W.radius, r); UP(W.d_center, dc); UP(W.d_vel, dv);
+		CK(cudaStreamSynchronize(w->stream)); /* the staging vectors die here */
+	}
+	UPRAW(W.type, d->type_mask, n, u32); UPRAW(W.collide, d->collide_mask, n, u32);
+	UPRAW(W.ntype, d->new_type_mask, n, u32); UPRAW(W.ncollide, d->new_collide_mask, n, u32);
+	UPRAW(W.friction, d->friction, n, i32); UPRAW(W.holder, d->holder, n, i32);
+	UPRAW(W.holdFlags, d->hold_flags, n, i32); UPRAW(W.holdee, d->holdee_head, n, i32);
+	UPRAW(W.newHolder, d->new_holder, n, i32); UPRAW(W.newHoldFlags, d->new_hold_flags, n, i32);
+	UP(W.holdRoot, holdRoot); UP(W.LLn, LLn); UP(W.LLp, LLp);
+	UP(W.hphys, hphys); UP(W.hpair, hpair); UP(W.htick, htick); UP(W.btn_v, bv); UP(W.btn_v2, bv2);
+	UP(W.newDrop, newDrop); UP(W.dead_max0, dm0); UP(W.dead_max1, dm1); UP(W.fullFlush, ff); UP(W.dead, dead);
+	UP(W.inList, inList); UP(W.needsCollision, needsC); UP(W.hasBox, hasBox); UP(W.ready, ready);
+	UP(W.forced, forced); UP(W.forcedHoldees, fh); UP(W.pend, pend);
+	UPRAW(W.slider_off, d->slider_off, n + 1, i32); UPRAW(W.sv, d->slider_v, d->n_sliders, i32);
+	UPRAW(W.smin, d->slider_min, d->n_sliders, i32); UPRAW(W.smax, d->slider_max, d->n_sliders, i32);
+	UPRAW(W.wire_off, d->wire_off, n + 1, i32); UPRAW(W.wire_to, d->wire_to, d->n_wires, i32);
+	UP(W.wire_cnt, wire_cnt);
+	CK(cudaMemsetAsync(W.ctr, 0, sizeof(u32) * CT_WORDS, w->stream));
+	CK(cudaMemsetAsync(W.wflush, 0, (size_t)nw, w->stream));
+	CK(cudaStreamSynchronize(w->stream));
+#undef UP
+#undef UPRAW
+	w->up_root_order.assign(d->root_order, d->root_order + n);
+	w->tree_valid = false; w->ray_valid = false; w->ranks_valid = false;
+	w->deltas_pending = deltas;
+	w->ticks_since_build = 0;
+	w->stats.live_ents = n;
+	return BT_OK;
+}
+
+/* ---------------------------------------------------------------- tick */
+
+static int radix_sort(bt_world *w, int key_bits) {
+	DevWorld &W = w->W;
+	const i32 n = W.n;
+	const int nb = (n + SORT_TILE - 1) / SORT_TILE;
+	for (int shift = 0; shift < key_bits; shift += 8) {
+		LAUNCH(w, PK_SORT, k_sort_hist, nb, SORT_THREADS, W.keys, n, shift, w->d_sorthist, nb);
+		LAUNCH(w, PK_SORT, k_sort_scan, 1, 1024, w->d_sorthist, 256 * nb);
+		LAUNCH(w, PK_SORT, k_sort_scatter, nb, SORT_THREADS, W.keys, W.leafEnt, W.keys_alt, W.leafEnt_alt, n, shift,
+		       w->d_sorthist, nb);
+		std::swap(W.keys, W.keys_alt);
+		std::swap(W.leafEnt, W.leafEnt_alt);
+	}
+	return 0;
+}
+
+static int bits_for(u32 x) { int b = 0; while (x) { b++; x >>= 1; } return b; }
+
+/* Morton sort + Karras hierarchy over every live boxed entity */
+static int build_tree(bt_world *w) {
+	DevWorld &W = w->W;
+	const i32 n = W.n;
+	i32 init[8] = {0, INT32_MAX, INT32_MAX, INT32_MAX, INT32_MIN, INT32_MIN, INT32_MIN, 0};
+	CK(cudaMemcpyAsync(&W.ctr[CT_N_LEAVES], init, sizeof(i32) * 7, cudaMemcpyHostToDevice, w->stream));
+	LAUNCH(w, PK_BUILD_KEYS, k_bounds, nblk(n), BT_BLOCK, W);
+	CK(cudaMemcpyAsync(w->h_flag, W.ctr, sizeof(u32) * CT_WORDS, cudaMemcpyDeviceToHost, w->stream));
+	CK(cudaStreamSynchronize(w->stream));
+	W.n_leaves = (i32)w->h_flag[CT_N_LEAVES];
+	const i32 *b = (const i32 *)&w->h_flag[CT_BOUNDS];
+	for (int k = 0; k < 3; k++) {
+		u32 ext = W.n_leaves ? (u32)(b[3 + k] - b[k]) : 0;
+		int bits = bits_for(ext);
+		W.key_shift[k] = bits > 10 ? bits - 10 : 0;
+	}
+	W.world_bits = bits_for((u32)W.n_worlds); /* ids 0..n_worlds, the last one = "not a leaf" */
+	LAUNCH(w, PK_BUILD_KEYS, k_morton, nblk(n), BT_BLOCK, W);
+	int r = radix_sort(w, 30 + W.world_bits);
+	if (r) return r;
+	if (W.n_leaves >= 2) LAUNCH(w, PK_LBVH, k_lbvh, nblk(W.n_leaves - 1), BT_BLOCK, W);
+	w->tree_valid = true;
+	w->ticks_since_build = 0;
+	w->stats.tree_builds++;
+	return 0;
+}
+
+static int refit(bt_world *w) {
+	DevWorld &W = w->W;
+	if (W.n_leaves < 1) return 0;
+	CK(cudaMemsetAsync(W.nodeCount, 0, sizeof(u32) * (size_t)W.n_leaves, w->stream));
+	LAUNCH(w, PK_REFIT, k_refit, nblk(W.n_leaves), BT_BLOCK, W);
+	w->stats.tree_refits++;
+	return 0;
+}
+
+static int flush1(bt_world *w) {
+	DevWorld &W = w->W;
+	LAUNCH(w, PK_FLUSH, k_flush_scan, nblk(W.n), BT_BLOCK, W);
+	LAUNCH(w, PK_FLUSH, k_flush_serial, nblk(W.n_worlds), BT_BLOCK, W);
+	LAUNCH(w, PK_FLUSH, k_flush_misc, nblk(W.n), BT_BLOCK, W);
+	return 0;
+}
+
+static int fetch_ctr(bt_world *w) {
+	CK(cudaMemcpyAsync(w->h_flag, w->W.ctr, sizeof(u32) * CT_WORDS, cudaMemcpyDeviceToHost, w->stream));
+	CK(cudaStreamSynchronize(w->stream));
+	if (w->h_flag[CT_ERROR]) {
+		int code = -(int)w->h_flag[CT_ERROR];
+		snprintf(g_err, sizeof g_err, "device raised error %d (overflow of a work list or unsupported flush)", code);
+		return code;
+	}
+	return 0;
+}
+
+static int do_physics(bt_world *w, bool gravity) {
+	DevWorld &W = w->W;
+	const i32 n = W.n;
+	if (!w->deltas_pending) {
+		LAUNCH(w, PK_BEGIN, k_begin_fused, nblk(n), BT_BLOCK, W, gravity ? 1 : 0);
+	} else {
+		if (gravity) LAUNCH(w, PK_BEGIN, k_gravity, nblk(n), BT_BLOCK, W);
+		LAUNCH(w, PK_BEGIN, k_flush2_apply, nblk(n), BT_BLOCK, W);
+		LAUNCH(w, PK_BEGIN, k_integrate, nblk(n), BT_BLOCK, W);
+		w->deltas_pending = false;
+	}
+	/* leaf set changes (an entity gained a box) force a rebuild; deaths do not */
+	if (!w->tree_valid || w->ticks_since_build >= w->rebuild_every) {
+		int r = build_tree(w);
+		if (r) return r;
+	}
+	w->ticks_since_build++;
+	i64 it = 0;
+	while (1) {
+		int r = refit(w);
+		if (r) return r;
+		W.iter_id++;
+		LAUNCH(w, PK_COLLIDE, k_collide, nblk(W.n_leaves), BT_BLOCK, W);
+		r = fetch_ctr(w);
+		if (r) return r;
+		if (!w->h_flag[CT_ANY_PROPOSAL]) {
+			/* last doIteration found nothing; it still cleared needsCollision (ent.cpp:459) */
+			CK(cudaMemsetAsync(W.needsCollision, 0, (size_t)n, w->stream));
+			break;
+		}
+		w->stats.iterations++;
+		LAUNCH(w, PK_DECIDE, k_decide, nblk(n), BT_BLOCK, W);
+		LAUNCH(w, PK_DECIDE, k_conflict, nblk(n), BT_BLOCK, W);
+		LAUNCH(w, PK_PUSH, k_push, nblk(n), BT_BLOCK, W);
+		LAUNCH(w, PK_PUSH, k_push_serial, 1, 32, W);
+		LAUNCH(w, PK_POST, k_post, nblk(n), BT_BLOCK, W);
+		if (++it > w->max_iterations) {
+			snprintf(g_err, sizeof g_err, "doPhysics did not converge in %lld iterations", (long long)w->max_iterations);
+			return BT_ERR_OVERFLOW;
+		}
+	}
+	/* invokeOnCrush (ent.cpp:907): crush handlers are host-side events (dead list) */
+	int r = flush1(w);
+	if (r) return r;
+	/* flush2 (ent.cpp:910): none of the device-side handlers leaves a delta behind */
+	r = fetch_ctr(w);
+	if (r) return r;
+	if (w->h_flag[CT_NEED_REBUILD]) {
+		w->tree_valid = false;
+		CK(cudaMemsetAsync(&W.ctr[CT_NEED_REBUILD], 0, sizeof(u32), w->stream));
+	}
+	w->ray_valid = false;
+	return 0;
+}
+
+int bt_world_step(bt_world *w, uint32_t phases) {
+	if (!w) return BT_ERR_ARG;
+	CK(cudaSetDevice(w->device));
+	DevWorld &W = w->W;
+	const i32 n = W.n;
+	if (phases & BT_PHASE_CTRLS) LAUNCH(w, PK_PRE, k_pre, nblk(n), BT_BLOCK, W, phases);
+	if (phases & BT_PHASE_PREP) {
+		int r = flush1(w);
+		if (r) return r;
+	}
+	if ((phases & BT_PHASE_GRAVITY) && !(phases & BT_PHASE_PHYSICS)) {
+		LAUNCH(w, PK_BEGIN, k_gravity, nblk(n), BT_BLOCK, W);
+		w->deltas_pending = true;
+	}
+	if (phases & BT_PHASE_PHYSICS) {
+		int r = do_physics(w, (phases & BT_PHASE_GRAVITY) != 0);
+		if (r) return r;
+		w->stats.ticks++;
+	}
+	if (phases & BT_PHASE_FINISH) {
+		/* clearDeads (ent.cpp:471-481): slots of dead entities stay retired */
+		int r = fetch_ctr(w);
+		if (r) return r;
+		w->stats.live_ents -= (i64)w->h_flag[CT_DEAD_N];
+		if (w->h_flag[CT_DEAD_N]) w->ranks_valid = false;
+		CK(cudaMemsetAsync(&W.ctr[CT_DEAD_N], 0, sizeof(u32), w->stream));
+		w->stats.entity_ticks += w->stats.live_ents;
+	}
+	return BT_OK;
+}
+
+static int hash_into(bt_world *w, uint64_t *out) {
+	DevWorld &W = w->W;
+	CK(cudaMemsetAsync(w->d_hsum, 0, sizeof(u64) * (size_t)W.n_worlds, w->stream));
+	CK(cudaMemsetAsync(w->d_hcnt, 0, sizeof(u32) * (size_t)W.n_worlds, w->stream));
+	LAUNCH(w, PK_HASH, k_hash, nblk(W.n), BT_BLOCK, W, w->d_hsum, w->d_hcnt);
+	std::vector<u64> s(W.n_worlds);
+	std::vector<u32> c(W.n_worlds);
+	CK(cudaMemcpyAsync(s.data(), w->d_hsum, sizeof(u64) * s.size(), cudaMemcpyDeviceToHost, w->stream));
+	CK(cudaMemcpyAsync(c.data(), w->d_hcnt, sizeof(u32) * c.size(), cudaMemcpyDeviceToHost, w->stream));
+	CK(cudaStreamSynchronize(w->stream));
+	for (int g = 0; g < W.n_worlds; g++) {
+		u64 x = (u64)c[g];
+		x ^= x >> 30; x *= 0xbf58476d1ce4e5b9ULL; x ^= x >> 27; x *= 0x94d049bb133111ebULL; x ^= x >> 31;
+		out[g] = s[g] + x;
+	}
+	return 0;
+}
+
+int bt_world_hash(bt_world *w, uint64_t *out) {
+	if (!w || !out) return BT_ERR_ARG;
+	CK(cudaSetDevice(w->device));
+	return hash_into(w, out);
+}
+
+int bt_world_tick(bt_world *w, int32_t n_ticks, uint64_t *hashes) {
+	if (!w || n_ticks < 0) return BT_ERR_ARG;
+	for (int t = 0; t < n_ticks; t++) {
+		int r = bt_world_step(w, BT_PHASE_ALL);
+		if (r) return r;
+		if (hashes) {
+			r = hash_into(w, hashes + (size_t)t * w->W.n_worlds);
+			if (r) return r;
+		}
+	}
+	CK(cudaStreamSynchronize(w->stream));
+	return BT_OK;
+}
+
+int bt_world_tick_async(bt_world *w, int32_t n_ticks) { return bt_world_tick(w, n_ticks, NULL); }
+
+int bt_world_tick_timed(bt_world *w, int32_t n_ticks, float *ms) {
+	if (!w || n_ticks < 0 || !ms) return BT_ERR_ARG;
+	CK(cudaSetDevice(w->device));
+	cudaEvent_t a, b;
+	CK(cudaEventCreate(&a));
+	CK(cudaEventCreate(&b));
+	CK(cudaStreamSynchronize(w->stream));
+	CK(cudaEventRecord(a, w->stream));
+	int r = BT_OK;
+	for (int t = 0; t < n_ticks && r == BT_OK; t++) r = bt_world_step(w, BT_PHASE_ALL);
+	cudaEventRecord(b, w->stream);
+	cudaEventSynchronize(b);
+	cudaEventElapsedTime(ms, a, b);
+	cudaEventDestroy(a);
+	cudaEventDestroy(b);
+	return r;
+}
+
+/* live-rank maps (shared with the raycast path) */
+static int ensure_ranks(bt_world *w) {
+	if (w->ranks_valid) return 0;
+	LAUNCH(w, PK_EXCHANGE, k_live_ranks, 1, 1024, w->W, w->ray.rank2slot, w->ray.slot2rank);
+	w->ranks_valid = true;
+	return 0;
+}
+
+int bt_world_apply_host_deltas(bt_world *w, const int32_t *d_center, const int32_t *d_vel, int32_t n_ents) {
+	if (!w || !d_center || !d_vel || n_ents < 0) return BT_ERR_ARG;
+	CK(cudaSetDevice(w->device));
+	if ((i64)n_ents != w->stats.live_ents) return BT_ERR_ARG;
+	CK(cudaMemcpyAsync(w->d_stage_a, d_center, sizeof(i32) * 3 * (size_t)n_ents, cudaMemcpyHostToDevice, w->stream));
+	CK(cudaMemcpyAsync(w->d_stage_b, d_vel, sizeof(i32) * 3 * (size_t)n_ents, cudaMemcpyHostToDevice, w->stream));
+	bool dense = (i64)w->W.n == w->stats.live_ents;
+	if (!dense) { int r = ensure_ranks(w); if (r) return r; }
+	LAUNCH(w, PK_EXCHANGE, k_add_deltas, nblk(w->W.n), BT_BLOCK, w->W, w->d_stage_a, w->d_stage_b,
+	       dense ? (const i32 *)NULL : (const i32 *)w->ray.slot2rank);
+	w->deltas_pending = true;
+	return BT_OK;
+}
+
+int bt_world_read_state(bt_world *w, int32_t *center, int32_t *vel, int32_t n_ents) {
+	if (!w || !center || !vel || n_ents < 0) return BT_ERR_ARG;
+	CK(cudaSetDevice(w->device));
+	if ((i64)n_ents != w->stats.live_ents) return BT_ERR_ARG;
+	bool dense = (i64)w->W.n == w->stats.live_ents;
+	if (!dense) { int r = ensure_ranks(w); if (r) return r; }
+	LAUNCH(w, PK_EXCHANGE, k_pack_state, nblk(w->W.n), BT_BLOCK, w->W, w->d_stage_a, w->d_stage_b,
+	       dense ? (const i32 *)NULL : (const i32 *)w->ray.slot2rank);
+	CK(cudaMemcpyAsync(center, w->d_stage_a, sizeof(i32) * 3 * (size_t)n_ents, cudaMemcpyDeviceToHost, w->stream));
+	CK(cudaMemcpyAsync(vel, w->d_stage_b, sizeof(i32) * 3 * (size_t)n_ents, cudaMemcpyDeviceToHost, w->stream));
+	CK(cudaStreamSynchronize(w->stream));
+	return BT_OK;
+}
+
+int bt_world_sync(bt_world *w) {
+	if (!w) return BT_ERR_ARG;
+	CK(cudaSetDevice(w->device));
+	CK(cudaStreamSynchronize(w->stream));
+	return BT_OK;
+}
+
+int bt_world_stats(bt_world *w, bt_tick_stats *out, int reset) {
+	if (!w || !out) return BT_ERR_ARG;
+	CK(cudaSetDevice(w->device));
+	u64 s[SK_NUM];
+	CK(cudaMemcpyAsync(s, &w->W.ctr[CT_STAT0], sizeof(s), cudaMemcpyDeviceToHost, w->stream));
+	CK(cudaStreamSynchronize(w->stream));
+	w->stats.candidate_pairs = (i64)s[SK_CAND]; w->stats.positives = (i64)s[SK_POS];
+	w->stats.pushes = (i64)s[SK_PUSH]; w->stats.serial_pushes = (i64)s[SK_SERIAL];
+	w->stats.crushes = (i64)s[SK_CRUSH]; w->stats.fumbles = (i64)s[SK_FUMBLE];
+	*out = w->stats;
+	if (reset) {
+		i64 live = w->stats.live_ents;
+		memset(&w->stats, 0, sizeof(w->stats));
+		w->stats.live_ents = live;
+		CK(cudaMemsetAsync(&w->W.ctr[CT_STAT0], 0, sizeof(s), w->stream));
+	}
+	return BT_OK;
+}
+
+int bt_world_profile_enable(bt_world *w, int on) {
+	if (!w) return BT_ERR_ARG;
+	w->profiling = on != 0;
+	return BT_OK;
+}
+
+int bt_world_profile_read(bt_world *w, bt_profile *out, int reset) {
+	if (!w || !out) return BT_ERR_ARG;
+	out->n = PK_NUM;
+	for (int i = 0; i < PK_NUM; i++) {
+		out->name[i] = PK_NAMES[i];
+		out->launches[i] = w->prof_launches[i];
+		out->ms[i] = w->prof_ms[i];
+	}
+	if (reset) {
+		memset(w->prof_launches, 0, sizeof(w->prof_launches));
+		memset(w->prof_ms, 0, sizeof(w->prof_ms));
+	}
+	return BT_OK;
+}
+
+/* ---------------------------------------------------------------- download */
+
+int bt_world_count(bt_world *w, int32_t *n_ents, int32_t *n_sliders, int32_t *n_wires) {
+	if (!w) return BT_ERR_ARG;
+	CK(cudaSetDevice(w->device));
+	const int n = w->W.n;
+	std::vector<u8> inList(n);
+	std::vector<i32> so(n + 1), wc(n);
+	if (n) {
+		CK(cudaMemcpy(inList.data(), w->W.inList, n, cudaMemcpyDeviceToHost));
+		CK(cudaMemcpy(so.data(), w->W.slider_off, sizeof(i32) * (n + 1), cudaMemcpyDeviceToHost));
+		CK(cudaMemcpy(wc.data(), w->W.wire_cnt, sizeof(i32) * n, cudaMemcpyDeviceToHost));
+	}
+	i32 a = 0, b = 0, c = 0;
+	for (int i = 0; i < n; i++)
+		if (inList[i]) { a++; b += so[i + 1] - so[i]; c += wc[i]; }
+	if (n_ents) *n_ents = a;
+	if (n_sliders) *n_sliders = b;
+	if (n_wires) *n_wires = c;
+	return BT_OK;
+}
+
+} /* extern "C" */
+template <typename T> static int d2h(std::vector<T> &dst, const T *src, size_t cnt) {
+	dst.resize(cnt);
+	if (cnt) CK(cudaMemcpy(dst.data(), src, sizeof(T) * cnt, cudaMemcpyDeviceToHost));
+	return 0;
+}
+extern "C" {
+
+int bt_world_download(bt_world *w, bt_world_desc *d) {
+	if (!w || !d) return BT_ERR_ARG;
+	CK(cudaSetDevice(w->device));
+	CK(cudaStreamSynchronize(w->stream));
+	DevWorld &W = w->W;
+	const int n = W.n, nw = W.n_worlds;
+#define DN(vec, src, cnt) do { int _r = d2h(vec, src, (size_t)(cnt)); if (_r) return _r; } while (0)
+	std::vector<u8> inList, newDrop, dm0, dm1, ff;
+	std::vector<i32> world, uid, friction, holder, holdFlags, holdee, LLn, newHolder, newHoldFlags, so, sv, smin, smax, wo, wc, wt;
+	std::vector<int4> center, old, vel, radius, dc, dv;
+	std::vector<u32> type, collide, ntype, ncollide, hphys, hpair, htick, bv, bv2;
+	DN(inList, W.inList, n); DN(newDrop, W.newDrop, n); DN(dm0, W.dead_max0, n); DN(dm1, W.dead_max1, n);
+	DN(ff, W.fullFlush, n); DN(world, W.world, n); DN(uid, W.uid, n); DN(friction, W.friction, n);
+	DN(holder, W.holder, n); DN(holdFlags, W.holdFlags, n); DN(holdee, W.holdee, n); DN(LLn, W.LLn, n);
+	DN(newHolder, W.newHolder, n); DN(newHoldFlags, W.newHoldFlags, n);
+	DN(center, W.center, n); DN(old, W.old, n); DN(vel, W.vel, n); DN(radius, W.radius, n);
+	DN(dc, W.d_center, n); DN(dv, W.d_vel, n);
+	DN(type, W.type, n); DN(collide, W.collide, n); DN(ntype, W.ntype, n); DN(ncollide, W.ncollide, n);
+	DN(hphys, W.hphys, n); DN(hpair, W.hpair, n); DN(htick, W.htick, n); DN(bv, W.btn_v, n); DN(bv2, W.btn_v2, n);
+	DN(so, W.slider_off, n + 1); DN(wo, W.wire_off, n + 1); DN(wc, W.wire_cnt, n);
+	DN(sv, W.sv, so.empty() ? 0 : so[n]); DN(smin, W.smin, so.empty() ? 0 : so[n]); DN(smax, W.smax, so.empty() ? 0 : so[n]);
+	DN(wt, W.wire_to, wo.empty() ? 0 : wo[n]);
+#undef DN
+	std::vector<i32> map(n + 1, -1);
+	i32 k = 0;
+	for (int i = 0; i < n; i++)
+		if (inList[i]) map[i] = k++;
+	if (k > d->n_ents) return BT_ERR_CAPACITY;
+	auto ref = [&](i32 x) { return x >= 0 ? map[x] : -1; };
+	std::vector<i32> flip(nw), rules(nw), rnd(nw);
+	CK(cudaMemcpy(flip.data(), W.flip, sizeof(i32) * nw, cudaMemcpyDeviceToHost));
+	CK(cudaMemcpy(rules.data(), W.gamerules, sizeof(i32) * nw, cudaMemcpyDeviceToHost));
+	CK(cudaMemcpy(rnd.data(), W.rnd, sizeof(i32) * nw, cudaMemcpyDeviceToHost));
+	for (int g = 0; g < nw; g++) { d->w_flip_flop[g] = flip[g]; d->w_gamerules[g] = rules[g]; d->w_rand[g] = rnd[g]; }
+	/* rootEnts order: roots created on the device (fumbles) come first, newest index first,
+	 * then the surviving upload-time roots in their uploaded order */
+	{
+		std::vector<std::vector<std::pair<i64, i32>>> per(nw);
+		for (int i = 0; i < n; i++) {
+			if (!inList[i] || holder[i] >= 0) continue;
+			i32 ro = (i < (int)w->up_root_order.size()) ? w->up_root_order[i] : -1;
+			i64 key = ro >= 0 ? (i64)ro : (i64)-1 - (i64)i - ((i64)1 << 32);
+			if (ro < 0) key = -((i64)i) - 1; /* negative: ahead of every uploaded root, larger index first */
+			per[world[i]].push_back(std::make_pair(key, (i32)i));
+		}
+		for (int g = 0; g < nw; g++) {
+			std::sort(per[g].begin(), per[g].end());
+			for (size_t p = 0; p < per[g].size(); p++) d->root_order[map[per[g][p].second]] = (i32)p;
+		}
+	}
+	i32 sOut = 0, wOut = 0;
+	for (int i = 0; i < n; i++) {
+		if (!inList[i]) continue;
+		i32 o = map[i];
+		if (d->world_id) d->world_id[o] = world[i];
+		d->uid[o] = uid[i];
+		const int4 *src[6] = {&center[i], &vel[i], &old[i], &dc[i], &dv[i], &radius[i]};
+		int32_t *dst[6] = {d->center, d->vel, d->old, d->d_center, d->d_vel, d->radius};
+		for (int f = 0; f < 6; f++) { dst[f][3 * o] = src[f]->x; dst[f][3 * o + 1] = src[f]->y; dst[f][3 * o + 2] = src[f]->z; }
+		d->type_mask[o] = type[i]; d->collide_mask[o] = collide[i];
+		d->new_type_mask[o] = ntype[i]; d->new_collide_mask[o] = ncollide[i];
+		d->friction[o] = friction[i]; d->holder[o] = ref(holder[i]); d->hold_flags[o] = holdFlags[i];
+		d->holdee_head[o] = ref(holdee[i]); d->holdee_next[o] = holder[i] >= 0 ? ref(LLn[i]) : -1;
+		if (holder[i] >= 0) d->root_order[o] = -1;
+		d->new_holder[o] = ref(newHolder[i]); d->new_hold_flags[o] = newHoldFlags[i];
+		uint8_t *h = d->handlers + (size_t)BT_H_NUM * o;
+		h[BT_H_WHOMOVES] = hphys[i] & 0xff; h[BT_H_PUSH] = (hphys[i] >> 8) & 0xff;
+		h[BT_H_PUSHED] = (hphys[i] >> 16) & 0xff; h[BT_H_CRUSH] = (hphys[i] >> 24) & 0xff;
+		h[BT_H_ONFUMBLE] = hpair[i] & 0xff; h[BT_H_ONFUMBLED] = (hpair[i] >> 8) & 0xff;
+		h[BT_H_ONPICKUP] = (hpair[i] >> 16) & 0xff; h[BT_H_ONPICKEDUP] = (hpair[i] >> 24) & 0xff;
+		h[BT_H_TICK] = htick[i] & 0xff; h[BT_H_TICKHELD] = (htick[i] >> 8) & 0xff;
+		uint8_t *b = d->btn + 8 * (size_t)o;
+		for (int q = 0; q < 4; q++) { b[q] = (bv[i] >> (8 * q)) & 0xff; b[4 + q] = (bv2[i] >> (8 * q)) & 0xff; }
+		uint8_t *m = d->misc + (size_t)BT_M_NUM * o;
+		m[BT_M_NEWDROP] = newDrop[i]; m[BT_M_DEADMAX0] = dm0[i]; m[BT_M_DEADMAX1] = dm1[i]; m[BT_M_FULLFLUSH] = ff[i];
+		d->slider_off[o] = sOut;
+		for (int s = so[i]; s < so[i + 1]; s++, sOut++) {
+			if (sOut >= d->n_sliders) return BT_ERR_CAPACITY;
+			d->slider_v[sOut] = sv[s]; d->slider_min[sOut] = smin[s]; d->slider_max[sOut] = smax[s];
+		}
+		d->wire_off[o] = wOut;
+		for (int q = 0; q < wc[i]; q++, wOut++) {
+			if (wOut >= d->n_wires) return BT_ERR_CAPACITY;
+			d->wire_to[wOut] = ref(wt[wo[i] + q]);
+		}
+	}
+	d->slider_off[k] = sOut; d->wire_off[k] = wOut;
+	d->n_ents = k; d->n_sliders = sOut; d->n_wires = wOut; d->n_worlds = nw;
+	return BT_OK;
+}
+
+/* ---------------------------------------------------------------- raycast */
+} /* extern "C" */
+
+/* the ray tree reuses the collision-tree kernels on a DevWorld whose tree pointers are
+ * swapped for the RayTree arrays and whose ray_mode is set */
+static void ray_swap(bt_world *w) {
+	DevWorld &W = w->W;
+	RayTree &R = w->ray;
+	std::swap(W.keys, R.keys); std::swap(W.keys_alt, R.keys_alt);
+	std::swap(W.leafEnt, R.leafEnt); std::swap(W.leafEnt_alt, R.leafEnt_alt);
+	std::swap(W.leafParent, R.leafParent); std::swap(W.nodeParent, R.nodeParent);
+	std::swap(W.nodeCount, R.nodeCount); std::swap(W.nodes, R.nodes);
+	std::swap(W.nodeBox, R.nodeBox); std::swap(W.leafBox, R.leafBox);
+	std::swap(W.n_leaves, R.n_leaves);
+	for (int k = 0; k < 3; k++) std::swap(W.key_shift[k], R.key_shift[k]);
+	W.ray_mode ^= 1;
+}
+
+static int ray_build(bt_world *w) {
+	bool tv = w->tree_valid;
+	i32 tsb = w->ticks_since_build;
+	i64 builds = w->stats.tree_builds, refits = w->stats.tree_refits;
+	ray_swap(w);
+	int r = build_tree(w);
+	if (!r) r = refit(w);
+	if (!r) { LAUNCH(w, PK_RAY_BUILD, k_live_ranks, 1, 1024, w->W, w->ray.rank2slot, w->ray.slot2rank); w->ranks_valid = true; }
+	ray_swap(w);
+	w->tree_valid = tv; w->ticks_since_build = tsb;
+	w->stats.tree_builds = builds; w->stats.tree_refits = refits;
+	if (r) return r;
+	w->ray_valid = true;
+	return 0;
+}
+
+static int ray_cast(bt_world *w, const i32 *d_origin, const i32 *d_look, i32 n_rays, i32 *d_winner) {
+	ray_swap(w);
+	LAUNCH(w, PK_RAYCAST, k_raycast, nblk(n_rays, 128), 128, w->W, d_origin, d_look, n_rays, d_winner,
+	       w->ray.rank2slot, w->ray.slot2rank);
+	ray_swap(w);
+	return 0;
+}
+
+extern "C" {
+
+int bt_raycast_build(bt_world *w) {
+	if (!w) return BT_ERR_ARG;
+	CK(cudaSetDevice(w->device));
+	return ray_build(w);
+}
+
+int bt_raycast_batch_device(bt_world *w, const int32_t *d_origin, const int32_t *d_look, int32_t n_rays,
+                            int32_t *d_winner) {
+	if (!w || n_rays < 0) return BT_ERR_ARG;
+	CK(cudaSetDevice(w->device));
+	if (!w->ray_valid) {
+		int r = ray_build(w);
+		if (r) return r;
+	}
+	return ray_cast(w, d_origin, d_look, n_rays, d_winner);
+}
+
+int bt_raycast_batch(bt_world *w, const int32_t *origin, const int32_t *look, int32_t n_rays, int32_t *winner) {
+	if (!w || !origin || !look || !winner || n_rays < 0) return BT_ERR_ARG;
+	CK(cudaSetDevice(w->device));
+	i32 *d_o = NULL, *d_l = NULL, *d_w = NULL;
+	size_t nr = (size_t)(n_rays ? n_rays : 1);
+	CK(cudaMalloc(&d_o, sizeof(i32) * nr));
+	CK(cudaMalloc(&d_l, sizeof(i32) * 3 * nr));
+	CK(cudaMalloc(&d_w, sizeof(i32) * nr));
+	int r = BT_OK;
+	cudaError_t e = cudaMemcpyAsync(d_o, origin, sizeof(i32) * n_rays, cudaMemcpyHostToDevice, w->stream);
+	if (e == cudaSuccess) e = cudaMemcpyAsync(d_l, look, sizeof(i32) * 3 * n_rays, cudaMemcpyHostToDevice, w->stream);
+	if (e == cudaSuccess) r = bt_raycast_batch_device(w, d_o, d_l, n_rays, d_w);
+	if (e == cudaSuccess && r == BT_OK)
+		e = cudaMemcpyAsync(winner, d_w, sizeof(i32) * n_rays, cudaMemcpyDeviceToHost, w->stream);
+	if (e == cudaSuccess) e = cudaStreamSynchronize(w->stream);
+	cudaFree(d_o); cudaFree(d_l); cudaFree(d_w);
+	if (e != cudaSuccess) { set_err("%s failed: %s (bt_world.cu:%d)", "raycast copy", cudaGetErrorString(e), __LINE__); return BT_ERR_CUDA; }
+	return r;
+}
+
+} /* extern "C" */

@@ -160,6 +160,20 @@ int bt_world_tick(bt_world *w, int32_t n_ticks, uint64_t *hashes);
  * no hash readback) so a caller can bracket it with its own CUDA events. */
 int bt_world_tick_async(bt_world *w, int32_t n_ticks);
 int bt_world_sync(bt_world *w);
+/* n_ticks whole steps bracketed by CUDA events recorded on the world's own stream;
+ * *ms receives the device time between them (what bench.py reports). */
+int bt_world_tick_timed(bt_world *w, int32_t n_ticks, float *ms);
+
+/* ---- per-tick host exchange for a host that keeps running its tick handlers
+ *      (doUpdates, ent.cpp:823-832) on its own `ent` structs ----
+ * bt_world_apply_host_deltas: what uCenter / uVel (entUpdaters.c:6-18) accumulated on the
+ * host since the last tick, as [3*n] arrays in live oldest-first order; they are ADDED to
+ * the device-side d_center / d_vel and consumed by the next flush2 (ent.cpp:716-744).
+ * bt_world_read_state: centre and velocity of every live entity after the tick, same
+ * order, for the next round of handlers / rendering. Host buffers; copies are issued on
+ * the world's stream. */
+int bt_world_apply_host_deltas(bt_world *w, const int32_t *d_center, const int32_t *d_vel, int32_t n_ents);
+int bt_world_read_state(bt_world *w, int32_t *center, int32_t *vel, int32_t n_ents);
 void *bt_world_stream(bt_world *w); /* the cudaStream_t every kernel of w runs on */
 
 /* Commutative 64-bit state hash per world over (uid, center, vel, typeMask,

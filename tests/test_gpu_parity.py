@@ -1,0 +1,118 @@
+"""Parity of the CUDA path (through the C ABI) with the oracle and the reference's golden
+hash streams.  Run on the B200 box: python -m pytest tests -m gpu"""
+import numpy as np
+import pytest
+
+from util import SCENARIOS, load_scenario
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("name", list(SCENARIOS))
+def test_cuda_matches_oracle_and_reference_golden(bt, oracle_lib, name):
+    wa, ref = load_scenario(name)
+    ow = oracle_lib.create(wa)
+    w = bt.World(wa)
+    w.set_option("rebuild_every", 3)
+    assert w.hash() == ow.hash()
+    for t in range(len(ref)):
+        ow.step(31)
+        w.step(31)
+        h = w.hash()
+        assert h == ow.hash(), "%s: CUDA != oracle at tick %d" % (name, t)
+        assert h[0] == int(ref[t]), "%s: CUDA != reference golden at tick %d" % (name, t)
+    so, sg = ow.stats(), w.stats()
+    for k in ("iterations", "positives", "pushes", "crushes", "fumbles"):
+        assert so[k] == sg[k], k
+    a, b = ow.export().state_dict(), w.download().state_dict()
+    for k in a:
+        assert a[k].shape == b[k].shape and np.array_equal(a[k], b[k]), k
+    w.close()
+
+
+def test_cuda_tick_hash_stream_api(bt):
+    wa, ref = load_scenario("stack4k_pushall")
+    w = bt.World(wa)
+    hs = w.tick(len(ref), hashes=True)
+    assert [int(x) for x in hs[:, 0]] == [int(x) for x in ref]
+    w.close()
+
+
+def test_cuda_batched_worlds(bt, oracle_lib):
+    names = ["arena_kick", "diner_kick", "stack512", "arena_kick", "tower_kick"]
+    ws = [load_scenario(n)[0] for n in names]
+    refs = [load_scenario(n)[1] for n in names]
+    w = bt.World(bt.concat_worlds(ws))
+    for t in range(40):
+        w.step(31)
+        h = w.hash()
+        for g in range(len(names)):
+            assert h[g] == int(refs[g][t]), (names[g], t)
+    w.close()
+
+
+def test_cuda_100k_stack_vs_oracle(bt, oracle_lib):
+    wa = bt.synth_boxstack(100000, 4, 777, 64, 60)
+    ow = oracle_lib.create(wa)
+    w = bt.World(wa)
+    for t in range(12):
+        ow.step(31)
+        w.step(31)
+        assert w.hash() == ow.hash(), "tick %d" % t
+    w.close()
+
+
+def test_cuda_1m_stack_properties(bt):
+    """full BASELINE size: no oracle run (minutes on a CPU); size-independent properties:
+    determinism run-to-run, independence from the tree rebuild period, entity conservation"""
+    wa = bt.synth_boxstack(1000000, 4, 777, 64, 60)
+    hs = []
+    for period in (1, 8, 8):
+        w = bt.World(wa)
+        w.set_option("rebuild_every", period)
+        hs.append([int(x) for x in w.tick(12, hashes=True)[:, 0]])
+        st = w.stats()
+        assert st["live_ents"] + st["crushes"] == wa.n
+        w.close()
+    assert hs[0] == hs[1] == hs[2]
+    assert len(set(hs[0])) == len(hs[0])
+
+
+def test_cuda_raycast_matches_oracle(bt, oracle_lib):
+    for name in ("lobby_kick", "stack4k_pushall", "spider_static"):
+        wa, _ = load_scenario(name)
+        rng = np.random.RandomState(3)
+        origin = rng.randint(0, wa.n, size=2000).astype(np.int32)
+        look = rng.randint(-64, 65, size=(2000, 3)).astype(np.int32)
+        look[::5, 1] = 0
+        look[::9, 0] = 0
+        look[np.abs(look).sum(1) == 0] = (0, 0, 64)
+        want = oracle_lib.create(wa).selectcast(origin, look)
+        w = bt.World(wa)
+        got = w.raycast(origin, look)
+        w.close()
+        assert np.array_equal(want, got), name
+
+
+def test_cuda_raycast_after_ticks_skips_dead(bt, oracle_lib):
+    wa, _ = load_scenario("spider_static")
+    ow = oracle_lib.create(wa)
+    w = bt.World(wa)
+    for _ in range(20):
+        ow.step(31)
+        w.step(31)
+    n = w.count()[0]
+    assert n == ow.count()[0] and n < wa.n
+    rng = np.random.RandomState(9)
+    origin = rng.randint(0, n, size=1000).astype(np.int32)
+    look = rng.randint(-64, 65, size=(1000, 3)).astype(np.int32)
+    look[np.abs(look).sum(1) == 0] = (0, 0, 64)
+    assert np.array_equal(ow.selectcast(origin, look), w.raycast(origin, look))
+    w.close()
+
+
+def test_unsupported_handler_is_refused(bt):
+    wa, _ = load_scenario("arena_kick")
+    wa.a["handlers"][4] = 4  # PUSH_TEAMSELECT on entity 0: host-side effects, no device implementation
+    with pytest.raises(bt.BtError):
+        bt.World(wa)
