@@ -1,0 +1,19 @@
+"""Short, fixed workload for ncu: the bench world, a few whole ticks (same code path as
+bench.py's timed region, nothing else).  Usage: python tools/ncu_target.py [cubes] [ticks] [warm]"""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import bittoss_b200
+
+cubes = int(sys.argv[1]) if len(sys.argv) > 1 else 1000000
+ticks = int(sys.argv[2]) if len(sys.argv) > 2 else 2
+warm = int(sys.argv[3]) if len(sys.argv) > 3 else 3
+wa = bittoss_b200.synth_boxstack(cubes, 4, 777, 64, 60)
+w = bittoss_b200.World(wa)
+w.tick(warm)
+s0 = w.stats(reset=True)
+w.tick(ticks)
+s = w.stats()
+print("ticks", ticks, "launches", s["kernel_launches"], "iterations", s["iterations"], "hash", hex(w.hash()[0]))
+w.close()
