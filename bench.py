@@ -258,7 +258,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--entities", type=int, default=1000000)
-    ap.add_argument("--rebuild-every", type=int, default=8)
+    ap.add_argument("--rebuild-every", type=int, default=16)
     ap.add_argument("--cpu-ticks", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

@@ -80,6 +80,74 @@ __global__ void __launch_bounds__(BT_BLOCK) k_collide(DevWorld W) {
 	stats_flush(W, st);
 	if (__any_sync(0xffffffffu, any) && (threadIdx.x & 31) == 0) W.ctr[CT_ANY_PROPOSAL] = 1;
 }
+/* Pair emitter: hits are buffered per thread and written with ONE atomic per warp flush
+ * (warp-ballot/shuffle compaction) instead of one atomic per pair. */
+#define PAIR_BUF 8
+struct PairEmit {
+	u64 *pairs;
+	u32 *counter;
+	u32 cap;
+	i32 *buf; /* this thread's slots in shared memory, stride BT_BLOCK (bank-conflict free) */
+	i32 a;
+	int n;
+	__device__ __forceinline__ PairEmit(u64 *p, u32 *c, i32 cap_, i32 *sbuf)
+	    : pairs(p), counter(c), cap((u32)cap_), buf(sbuf), a(-1), n(0) {}
+	__device__ __forceinline__ void store(u32 pos, i32 b) {
+		if (pos < cap) pairs[pos] = (u64)(u32)a | ((u64)(u32)b << 32);
+	}
+	/* called from divergent code when this thread's buffer is full */
+	__device__ __forceinline__ void operator()(i32 a_, i32 b) {
+		a = a_;
+		buf[(n++) * BT_BLOCK] = b;
+		if (n == PAIR_BUF) {
+			u32 m = __activemask();
+			int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
+			u32 rank = __popc(m & ((1u << lane) - 1));
+			u32 base = 0;
+			if (lane == leader) base = atomicAdd(counter, (u32)(PAIR_BUF * __popc(m)));
+			base = __shfl_sync(m, base, leader) + rank * PAIR_BUF;
+#pragma unroll
+			for (int k = 0; k < PAIR_BUF; k++) store(base + k, buf[k * BT_BLOCK]);
+			n = 0;
+		}
+	}
+	/* called once by every thread of the warp, converged */
+	__device__ __forceinline__ void finish() {
+		int lane = threadIdx.x & 31;
+		u32 x = (u32)n;
+#pragma unroll
+		for (int off = 1; off < 32; off <<= 1) {
+			u32 y = __shfl_up_sync(0xffffffffu, x, off);
+			if (lane >= off) x += y;
+		}
+		u32 tot = __shfl_sync(0xffffffffu, x, 31);
+		u32 base = 0;
+		if (lane == 31 && tot) base = atomicAdd(counter, tot);
+		base = __shfl_sync(0xffffffffu, base, 31) + x - (u32)n;
+		for (int k = 0; k < n; k++) store(base + k, buf[k * BT_BLOCK]);
+	}
+};
+
+__global__ void __launch_bounds__(BT_BLOCK) k_pairs(DevWorld W) {
+	__shared__ i32 stacks[BT_STACK * BT_BLOCK];
+	__shared__ i32 pbuf[PAIR_BUF * BT_BLOCK];
+	PairEmit emit(W.pairs, &W.ctr[CT_PAIR_N], W.pair_cap, pbuf + threadIdx.x);
+	t_pairs(W, TID, stacks + threadIdx.x, BT_BLOCK, emit);
+	emit.finish();
+}
+
+/* one thread per cached pair, grid-stride so the launch does not need the pair count */
+__global__ void __launch_bounds__(256) k_narrow(DevWorld W) {
+	LocalStats st = {0, 0, 0, 0, 0};
+	u32 any = 0;
+	u32 np = W.ctr[CT_PAIR_N];
+	if (np > (u32)W.pair_cap) np = (u32)W.pair_cap;
+	for (u32 p = blockIdx.x * blockDim.x + threadIdx.x; p < np; p += gridDim.x * blockDim.x)
+		t_narrow(W, W.pairs[p], st, any);
+	stats_flush(W, st);
+	if (__any_sync(0xffffffffu, any) && (threadIdx.x & 31) == 0) W.ctr[CT_ANY_PROPOSAL] = 1;
+}
+
 __global__ void __launch_bounds__(BT_BLOCK) k_decide(DevWorld W) {
 	if (TID == 0) W.ctr[CT_ANY_PROPOSAL] = 0; /* the host already fetched this iteration's value */
 	t_decide(W, TID);

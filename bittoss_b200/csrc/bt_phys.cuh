@@ -228,6 +228,12 @@ static BT_HD void bt_crush(const DevWorld &W, i32 e, u32 key, LocalStats &st) {
 	if ((i32)slot < W.dead_cap) W.deadList[slot] = ((u64)key << 32) | (u32)e;
 }
 
+static BT_HD void bt_swept_box(const int4 &o, const int4 &c, const int4 &r, i32 lo[3], i32 hi[3]) {
+	lo[0] = (o.x < c.x ? o.x : c.x) - r.x; hi[0] = (o.x > c.x ? o.x : c.x) + r.x;
+	lo[1] = (o.y < c.y ? o.y : c.y) - r.y; hi[1] = (o.y > c.y ? o.y : c.y) + r.y;
+	lo[2] = (o.z < c.z ? o.z : c.z) - r.z; hi[2] = (o.z > c.z ? o.z : c.z) + r.z;
+}
+
 /* moveRecursive ent.cpp:115-126 */
 static BT_HD void bt_move_recursive(const DevWorld &W, i32 who, const i32 *dc, const i32 *dv) {
 	BT_FOR_SUBTREE(W, who, it, {
@@ -236,6 +242,15 @@ static BT_HD void bt_move_recursive(const DevWorld &W, i32 who, const i32 *dc, c
 		v.x += dv[0]; v.y += dv[1]; v.z += dv[2];
 		W.center[it] = c;
 		W.vel[it] = v;
+		if (W.hasBox[it]) { /* do the cached candidate pairs still cover this entity? */
+			int4 o = W.old[it], r = W.radius[it];
+			Box6 ib = W.ibox[it];
+			i32 lo[3], hi[3];
+			bt_swept_box(o, c, r, lo, hi);
+			if (lo[0] < ib.lo.x || lo[1] < ib.lo.y || lo[2] < ib.lo.z || hi[0] > ib.hi.x || hi[1] > ib.hi.y ||
+			    hi[2] > ib.hi.z)
+				W.ctr[CT_CACHE_INVALID] = 1;
+		}
 	});
 }
 
@@ -321,6 +336,25 @@ static BT_HD int bt_axis_and_dir(const EntGeo &a, const EntGeo &b) {
 	return dir_by_axis[best];
 }
 
+/* the three geometry arrays, passed by value into the non-inlined proposal code so that
+ * the whole DevWorld does not have to be spilled to the stack for the call */
+struct GeoView {
+	const int4 *old, *center, *radius;
+	u64 *pend;
+	const i32 *holdRoot;
+};
+static BT_HD GeoView bt_view(const DevWorld &W) {
+	GeoView v;
+	v.old = W.old; v.center = W.center; v.radius = W.radius; v.pend = W.pend; v.holdRoot = W.holdRoot;
+	return v;
+}
+static BT_HD EntGeo bt_geo(const GeoView &V, i32 e) {
+	EntGeo g;
+	g.old = V.old[e];
+	g.center = V.center[e];
+	g.radius = V.radius[e];
+	return g;
+}
 static BT_HD EntGeo bt_geo(const DevWorld &W, i32 e) {
 	EntGeo g;
 	g.old = W.old[e];
@@ -332,7 +366,7 @@ static BT_HD EntGeo bt_geo(const DevWorld &W, i32 e) {
 /* collisionBetter ent.cpp:317-382 as a three-way compare of two explicit records:
  * +1 c0 strictly better, -1 strictly worse, 0 full tie.  32-bit products wrap
  * exactly like the reference's `delta * speed` (ent.cpp:343). */
-static BT_HD int bt_collision_cmp(const DevWorld &W, const Coll &c0, const Coll &c1) {
+static BT_HD int bt_collision_cmp(const GeoView &W, const Coll &c0, const Coll &c1) {
 	EntGeo l0 = bt_geo(W, c0.leaf), f0 = bt_geo(W, c0.buddy);
 	EntGeo l1 = bt_geo(W, c1.leaf), f1 = bt_geo(W, c1.buddy);
 	int a0 = c0.axis, a1 = c1.axis;
@@ -373,13 +407,14 @@ static BT_HD int bt_collision_cmp(const DevWorld &W, const Coll &c0, const Coll 
 }
 
 /* tryCollide ent.cpp:384-396 as an order-independent atomic maximum on pend[root] */
-static BT_HD void bt_propose(const DevWorld &W, i32 leaf, i32 buddy, int axis, int dir, int mutual) {
+static BT_HD void bt_propose_v(const GeoView &W, i32 leaf, i32 buddy, int axis, int dir, int mutual) {
 	i32 root = W.holdRoot[leaf];
 	Coll c;
 	c.leaf = leaf; c.buddy = buddy; c.axis = axis; c.dir = dir; c.mutual = mutual;
 	u64 mine = bt_pack_coll(c);
 	u64 cur = bt_ld64(&W.pend[root]);
 	while (1) {
+		if (cur == mine) return; /* the same collision seen from the other end of the pair */
 		if (cur != 0) {
 			Coll inc = bt_unpack_coll(cur);
 			int r = bt_collision_cmp(W, c, inc);
@@ -392,21 +427,25 @@ static BT_HD void bt_propose(const DevWorld &W, i32 leaf, i32 buddy, int axis, i
 	}
 }
 
-/* checkCollision ent.cpp:398-435 for scanning entity a (already loaded) against b */
-static BT_HD void bt_check_collision(const DevWorld &W, i32 a, const EntGeo &ga, u32 ta, u32 ca, i32 rootA, u32 ha,
-                                     i32 b, LocalStats &st, u32 &any) {
-	u32 tb = W.type[b], cb = W.collide[b];
+static BT_HD void bt_propose(const DevWorld &W, i32 leaf, i32 buddy, int axis, int dir, int mutual) {
+	bt_propose_v(bt_view(W), leaf, buddy, axis, dir, mutual);
+}
+
+/* checkCollision ent.cpp:398-435 for scanning entity a against b, both already in registers.
+ * bScans = b is scanned itself in this doIteration (coordinator rule, DESIGN.md "Canonical order") */
+static BT_HD void bt_check_loaded(const DevWorld &W, i32 a, const EntGeo &ga, u32 ta, u32 ca, i32 rootA, u32 ha, i32 b,
+                                  const EntGeo &gb, u32 tb, u32 cb, i32 rootB, u32 hbp, int bScans, LocalStats &st,
+                                  u32 &any) {
 	int AonB = (tb & ca) != 0, BonA = (ta & cb) != 0;
 	if (!AonB && !BonA) return;
-	if (rootA == W.holdRoot[b]) return;
-	EntGeo gb = bt_geo(W, b);
+	if (rootA == rootB) return;
 	int dir = bt_axis_and_dir(ga, gb);
 	if (dir == 0) return;
 	st.pos++;
 	int axis;
 	if (dir < 0) { axis = -dir - 1; dir = -1; }
 	else { axis = dir - 1; dir = 1; }
-	int hb = (int)(W.hphys[b] & 0xff);
+	int hb = (int)(hbp & 0xff);
 	int movee;
 	if (AonB) {
 		if (BonA) { /* arbitrateMovement ent.cpp:229-236 */
@@ -424,27 +463,31 @@ static BT_HD void bt_check_collision(const DevWorld &W, i32 a, const EntGeo &ga,
 	}
 	if (movee & 8) return;
 	any = 1;
-	if (movee & 4) {
-		/* coordinator rule, DESIGN.md "Canonical order": a scans; it coordinates unless b
-		 * scans too and comes first in the reference's newest-first order */
-		int bScans = W.needsCollision[b] && W.hasBox[b] && W.inList[b];
-		int coordA = bScans ? (a > b) : 1;
-		bt_propose(W, a, b, axis, dir, coordA ? 1 : 2);
-		bt_propose(W, b, a, axis, -dir, coordA ? 2 : 1);
-		return;
+	/* one inlined copy of the proposal code, run once or (MOVE_BOTH) twice */
+	int both = (movee & 4) != 0;
+	/* a scans; it coordinates unless b scans too and comes first in the reference's newest-first order */
+	int coordA = bScans ? (a > b) : 1;
+	int first_is_a = both || movee == MOVE_ME;
+	GeoView V = bt_view(W);
+#pragma unroll 1
+	for (int k = 0; k < 1 + both; k++) {
+		int forA = k == 0 ? first_is_a : 0;
+		int mutual = both ? ((forA ? coordA : !coordA) ? 1 : 2) : 0;
+		if (forA) bt_propose_v(V, a, b, axis, dir, mutual);
+		else bt_propose_v(V, b, a, axis, -dir, mutual);
 	}
-	if (movee == MOVE_ME) bt_propose(W, a, b, axis, dir, 0);
-	else bt_propose(W, b, a, axis, -dir, 0);
+}
+
+static BT_HD void bt_check_collision(const DevWorld &W, i32 a, const EntGeo &ga, u32 ta, u32 ca, i32 rootA, u32 ha,
+                                     i32 b, LocalStats &st, u32 &any) {
+	u32 tb = W.type[b], cb = W.collide[b];
+	if (!((tb & ca) | (ta & cb))) return;
+	int bScans = W.needsCollision[b] && W.hasBox[b] && W.inList[b];
+	bt_check_loaded(W, a, ga, ta, ca, rootA, ha, b, bt_geo(W, b), tb, cb, W.holdRoot[b], W.hphys[b], bScans, st, any);
 }
 
 /* ------------------------------------------------------------------------- */
 /* broadphase: Morton keys, Karras LBVH, refit, traversal                    */
-
-static BT_HD void bt_swept_box(const int4 &o, const int4 &c, const int4 &r, i32 lo[3], i32 hi[3]) {
-	lo[0] = (o.x < c.x ? o.x : c.x) - r.x; hi[0] = (o.x > c.x ? o.x : c.x) + r.x;
-	lo[1] = (o.y < c.y ? o.y : c.y) - r.y; hi[1] = (o.y > c.y ? o.y : c.y) + r.y;
-	lo[2] = (o.z < c.z ? o.z : c.z) - r.z; hi[2] = (o.z > c.z ? o.z : c.z) + r.z;
-}
 
 static BT_HD int bt_is_leaf_ent(const DevWorld &W, i32 e) { return W.inList[e] && (W.ray_mode || W.hasBox[e]); }
 
@@ -466,19 +509,31 @@ static BT_HD u32 bt_expand10(u32 v) { /* 10 bits -> every third bit */
 	return v;
 }
 
-/* key = world id << 30 | 30-bit Morton code of the centre; non-leaves get world id
- * n_worlds and therefore sort last (radix passes cover 30 + bits(n_worlds) bits) */
+static BT_HD int bt_bits_for(u32 x) { return 32 - bt_clz32(x); }
+
+/* key = world id << 30 | size class << 27 | 27-bit Morton code of the centre (9 bits/axis).
+ * The size class (x4 radius steps, like velbox's SCALE=4 levels, velbox/box.h:24-30) sits
+ * ABOVE the Morton bits, so inside a world the Karras hierarchy first splits by class: huge
+ * boxes ("whales": ground tiles, walls) get their own tight subtree instead of bloating
+ * every ancestor of the small boxes around them, and because larger classes sort later, the
+ * "earlier leaf emits the pair" rule of t_pairs makes the many small boxes look up the few
+ * large ones and never the other way round.  Non-leaves get world id n_worlds and sort last
+ * (radix passes cover 30 + bits(n_worlds) bits). */
 static BT_HD void t_morton(const DevWorld &W, i32 e) {
 	if (e >= W.n) return;
 	u64 key = (u64)(u32)W.n_worlds << 30;
 	if (bt_is_leaf_ent(W, e)) {
-		int4 c = W.center[e];
+		int4 c = W.center[e], r = W.radius[e];
 		const i32 *b = (const i32 *)&W.ctr[CT_BOUNDS];
 		u32 qx = ((u32)(c.x - b[0])) >> W.key_shift[0];
 		u32 qy = ((u32)(c.y - b[1])) >> W.key_shift[1];
 		u32 qz = ((u32)(c.z - b[2])) >> W.key_shift[2];
 		u32 m = (bt_expand10(qx) << 2) | (bt_expand10(qy) << 1) | bt_expand10(qz);
-		key = ((u64)(u32)W.world[e] << 30) | m;
+		i32 rmax = r.x > r.y ? r.x : r.y;
+		if (r.z > rmax) rmax = r.z;
+		int cls = (bt_bits_for((u32)(rmax < 0 ? 0 : rmax)) - 7) >> 1;
+		cls = cls < 0 ? 0 : (cls > 7 ? 7 : cls);
+		key = ((u64)(u32)W.world[e] << 30) | ((u64)cls << 27) | (m & 0x7ffffffu);
 	}
 	W.keys[e] = key;
 	W.leafEnt[e] = e;
@@ -517,6 +572,7 @@ static BT_HD void t_lbvh_node(const DevWorld &W, int i) {
 	else { N.left = gamma; W.nodeParent[gamma] = i; }
 	if (hi == gamma + 1) { N.right = ~(gamma + 1); W.leafParent[gamma + 1] = i; }
 	else { N.right = gamma + 1; W.nodeParent[gamma + 1] = i; }
+	W.nodeHi[i] = hi;
 	if (i == 0) W.nodeParent[0] = -1;
 }
 
@@ -535,8 +591,10 @@ static BT_HD void t_refit(const DevWorld &W, int t) {
 		i32 lo[3], hi[3];
 		int4 cc = W.center[e];
 		bt_swept_box(W.ray_mode ? cc : W.old[e], cc, W.radius[e], lo, hi);
-		box.lo = make_int4(lo[0], lo[1], lo[2], W.world[e]);
-		box.hi = make_int4(hi[0], hi[1], hi[2], W.world[e]);
+		int m = W.ray_mode ? 0 : W.margin;
+		box.lo = make_int4(lo[0] - m, lo[1] - m, lo[2] - m, W.world[e]);
+		box.hi = make_int4(hi[0] + m, hi[1] + m, hi[2] + m, W.world[e]);
+		if (!W.ray_mode) W.ibox[e] = box;
 	} else { /* died since the tree was built: empty box, never overlaps */
 		box.lo = make_int4(INT32_MAX, INT32_MAX, INT32_MAX, 0xffff);
 		box.hi = make_int4(INT32_MIN, INT32_MIN, INT32_MIN, 0);
@@ -568,6 +626,28 @@ static BT_HD void t_refit(const DevWorld &W, int t) {
 	}
 }
 
+/* One LBVH node = exactly four 128-bit loads, issued together (no short-circuit chains of
+ * dependent scalar loads), then branch-free box tests on registers. */
+struct NodeRegs {
+	int4 a, b, c, d; /* a={llo.xyz,lhi.x} b={lhi.yz,rlo.xy} c={rlo.z,rhi.xyz} d={left,right,wl,wr} */
+};
+static BT_HD NodeRegs bt_load_node(const DevWorld &W, int node) {
+	const int4 *p = (const int4 *)&W.nodes[node];
+	NodeRegs r;
+	r.a = p[0]; r.b = p[1]; r.c = p[2]; r.d = p[3];
+	return r;
+}
+static BT_HD int bt_touch_left(const NodeRegs &n, const i32 *qlo, const i32 *qhi, u32 w) {
+	u32 wl = (u32)n.d.z;
+	return (qlo[0] <= n.a.w) & (n.a.x <= qhi[0]) & (qlo[1] <= n.b.x) & (n.a.y <= qhi[1]) & (qlo[2] <= n.b.y) &
+	       (n.a.z <= qhi[2]) & ((wl & 0xffff) <= w) & (w <= (wl >> 16));
+}
+static BT_HD int bt_touch_right(const NodeRegs &n, const i32 *qlo, const i32 *qhi, u32 w) {
+	u32 wr = (u32)n.d.w;
+	return (qlo[0] <= n.c.y) & (n.b.z <= qhi[0]) & (qlo[1] <= n.c.z) & (n.b.w <= qhi[1]) & (qlo[2] <= n.c.w) &
+	       (n.c.x <= qhi[2]) & ((wr & 0xffff) <= w) & (w <= (wr >> 16));
+}
+
 #define BT_STACK 64
 
 /* doIteration ent.cpp:437-462 for the entity at sorted leaf position t.
@@ -586,13 +666,11 @@ static BT_HD void t_collide(const DevWorld &W, int t, i32 *stack, int stride, Lo
 	int sp = 0;
 	int node = 0;
 	while (1) {
-		const BvhNode &N = W.nodes[node];
-		i32 li = N.left, ri = N.right;
+		const NodeRegs N = bt_load_node(W, node);
+		i32 li = N.d.x, ri = N.d.y;
 		/* touching counts as a candidate, the narrow phase decides */
-		int ovL = qlo[0] <= N.lhi[0] && N.llo[0] <= qhi[0] && qlo[1] <= N.lhi[1] && N.llo[1] <= qhi[1] &&
-		          qlo[2] <= N.lhi[2] && N.llo[2] <= qhi[2] && (N.wl & 0xffff) <= wa && wa <= (N.wl >> 16);
-		int ovR = qlo[0] <= N.rhi[0] && N.rlo[0] <= qhi[0] && qlo[1] <= N.rhi[1] && N.rlo[1] <= qhi[1] &&
-		          qlo[2] <= N.rhi[2] && N.rlo[2] <= qhi[2] && (N.wr & 0xffff) <= wa && wa <= (N.wr >> 16);
+		int ovL = bt_touch_left(N, qlo, qhi, wa);
+		int ovR = bt_touch_right(N, qlo, qhi, wa);
 		if (ovL && li < 0) {
 			i32 b = W.leafEnt[~li];
 			if (b != a) { st.cand++; bt_check_collision(W, a, ga, ta, ca, rootA, ha, b, st, any); }
@@ -617,6 +695,75 @@ static BT_HD void t_collide(const DevWorld &W, int t, i32 *stack, int stride, Lo
 	}
 }
 
+/* ---- cached candidate pairs --------------------------------------------------------
+ * k_pairs walks the tree once per tick (again only if an entity leaves its inflated box)
+ * and writes every unordered pair of leaves whose INFLATED boxes touch, once, from the
+ * leaf with the earlier position: subtrees that end at or before the query's own leaf
+ * position are skipped, which halves the traversal.  k_narrow then runs the narrow phase
+ * for a pair from both ends, like the reference does when both ends are scanned
+ * (ent.cpp:446-449).  This plays the role of velbox's cached `intersects` lists
+ * (velbox/box.cpp:95-136) within a tick. */
+template <class Emit> static BT_HD void t_pairs(const DevWorld &W, int t, i32 *stack, int stride, Emit &emit) {
+	int L = W.n_leaves;
+	if (t >= L || L < 2) return;
+	i32 a = W.leafEnt[t];
+	if (!bt_is_leaf_ent(W, a)) return;
+	Box6 q = W.leafBox[t];
+	u32 wa = (u32)q.lo.w;
+	const i32 qlo[3] = {q.lo.x, q.lo.y, q.lo.z}, qhi[3] = {q.hi.x, q.hi.y, q.hi.z};
+	int sp = 0, node = 0, cur_hi = L - 1;
+	while (1) {
+		const NodeRegs N = bt_load_node(W, node);
+		i32 li = N.d.x, ri = N.d.y;
+		int gamma = li < 0 ? ~li : li; /* Karras numbering: the split position is the left child's id */
+		int ovL = (gamma > t) & bt_touch_left(N, qlo, qhi, wa);
+		int ovR = (cur_hi > t) & bt_touch_right(N, qlo, qhi, wa);
+		if (ovL && li < 0) emit(a, W.leafEnt[~li]);
+		if (ovR && ri < 0 && ~ri > t) emit(a, W.leafEnt[~ri]);
+		int goL = ovL && li >= 0, goR = ovR && ri >= 0;
+		if (goL) {
+			node = li;
+			if (goR) {
+				if (sp < BT_STACK) stack[(sp++) * stride] = ri;
+				else W.ctr[CT_ERROR] = (u32)(-BT_ERR_OVERFLOW);
+			}
+			cur_hi = gamma;
+		} else if (goR) {
+			node = ri;
+		} else {
+			if (sp == 0) break;
+			node = stack[(--sp) * stride];
+			cur_hi = W.nodeHi[node];
+		}
+	}
+}
+
+/* checkCollision ent.cpp:398-435 for one cached pair, from whichever ends are scanning */
+static BT_HD void t_narrow(const DevWorld &W, u64 pr, LocalStats &st, u32 &any) {
+	i32 a = (i32)(u32)pr, b = (i32)(pr >> 32);
+	int na = W.needsCollision[a], nb = W.needsCollision[b];
+	if (!(na | nb)) return; /* the common case after the first iteration: two byte loads */
+	int alive = W.inList[a] & W.hasBox[a] & W.inList[b] & W.hasBox[b]; /* `o->dead` ent.cpp:455 */
+	if (!alive) return;
+	u32 ta = W.type[a], ca = W.collide[a], tb = W.type[b], cb = W.collide[b];
+	if (!((tb & ca) | (ta & cb))) { st.cand += (u32)(na + nb); return; }
+	i32 ra = W.holdRoot[a], rb = W.holdRoot[b];
+	u32 ha = W.hphys[a], hb = W.hphys[b];
+	EntGeo ga = bt_geo(W, a), gb = bt_geo(W, b);
+#pragma unroll 1
+	for (int k = 0; k < 2; k++) { /* one copy of the narrow phase, run from each scanning end */
+		if (na) {
+			st.cand++;
+			bt_check_loaded(W, a, ga, ta, ca, ra, ha, b, gb, tb, cb, rb, hb, nb, st, any);
+		}
+		{ i32 t_ = a; a = b; b = t_; }
+		{ EntGeo t_ = ga; ga = gb; gb = t_; }
+		{ u32 t_ = ta; ta = tb; tb = t_; t_ = ca; ca = cb; cb = t_; t_ = ha; ha = hb; hb = t_; }
+		{ i32 t_ = ra; ra = rb; rb = t_; }
+		{ int t_ = na; na = nb; nb = t_; }
+	}
+}
+
 /* ------------------------------------------------------------------------- */
 /* resolution                                                                */
 
@@ -632,7 +779,7 @@ static BT_HD int bt_should_resolve(const DevWorld &W, i32 e, u64 pe) {
 	int flip = 0;
 	while (1) {
 		Coll other = bt_unpack_coll(po);
-		if (bt_collision_cmp(W, other, mine) > 0) return 0;
+		if (bt_collision_cmp(bt_view(W), other, mine) > 0) return 0;
 		otherRoot = W.holdRoot[other.buddy];
 		if (otherRoot == e) return 2;
 		po = W.pend[otherRoot];

@@ -98,10 +98,13 @@ static BT_HD i32 t_raycast(const DevWorld &W, i32 p, const i32 look_in[3], i32 *
 	}
 	int sp = 0, node = 0;
 	while (1) {
-		const BvhNode &N = W.nodes[node];
-		i32 li = N.left, ri = N.right;
-		int ovL = (N.wl & 0xffff) <= wp && wp <= (N.wl >> 16) && ray_hit_box(pos, look, flip, N.llo, N.lhi, best);
-		int ovR = (N.wr & 0xffff) <= wp && wp <= (N.wr >> 16) && ray_hit_box(pos, look, flip, N.rlo, N.rhi, best);
+		const NodeRegs N = bt_load_node(W, node);
+		i32 li = N.d.x, ri = N.d.y;
+		u32 wl = (u32)N.d.z, wr = (u32)N.d.w;
+		const i32 llo[3] = {N.a.x, N.a.y, N.a.z}, lhi[3] = {N.a.w, N.b.x, N.b.y};
+		const i32 rlo[3] = {N.b.z, N.b.w, N.c.x}, rhi[3] = {N.c.y, N.c.z, N.c.w};
+		int ovL = (wl & 0xffff) <= wp && wp <= (wl >> 16) && ray_hit_box(pos, look, flip, llo, lhi, best);
+		int ovR = (wr & 0xffff) <= wp && wp <= (wr >> 16) && ray_hit_box(pos, look, flip, rlo, rhi, best);
 		if (ovL && li < 0) RAY_LEAF(~li);
 		if (ovR && ri < 0) RAY_LEAF(~ri);
 		int goL = ovL && li >= 0, goR = ovR && ri >= 0;

@@ -22,12 +22,14 @@
 #ifdef BT_EMU
 #define BT_HD
 #define BT_D
+#define BT_NOINLINE
 struct int4 { int x, y, z, w; };
 static inline int4 make_int4(int x, int y, int z, int w) { int4 r = {x, y, z, w}; return r; }
 #else
 #include <cuda_runtime.h>
 #define BT_HD __device__ __forceinline__
 #define BT_D __device__ __forceinline__
+#define BT_NOINLINE __device__ __noinline__
 #endif
 
 #include "../../include/bittoss_b200.h"
@@ -82,7 +84,10 @@ enum {
 	CT_ANY_DELTA,        /* some d_center / d_vel is non-zero */
 	CT_FLUSH_WORK,       /* some world needs the serial part of flush1 */
 	CT_N_LEAVES,
+	/* CT_BOUNDS occupies 6 words */
 	CT_BOUNDS,           /* 6 ints: min xyz, max xyz of leaf centres */
+	CT_PAIR_N = 14,      /* unordered candidate pairs emitted by k_pairs (may exceed pair_cap) */
+	CT_CACHE_INVALID,    /* an entity left the inflated box its cached pairs were found with */
 	CT_STAT0 = 16,       /* 64-bit stats start here (as pairs of u32 slots, 8-byte aligned) */
 	CT_WORDS = 64
 };
@@ -96,7 +101,9 @@ struct DevWorld {
 	i32 world_bits;
 	i32 serial_cap, dead_cap;
 	i32 iter_id; /* running doIteration counter, for event ordering keys */
-	i32 ray_mode; /* 1: tree over ALL live entities with static boxes (raycast), 0: collision tree */
+	i32 ray_mode;
+	i32 margin;   /* inflation of the boxes candidate pairs are cached with (collision tree only) */
+	i32 pair_cap; /* 1: tree over ALL live entities with static boxes (raycast), 0: collision tree */
 
 	i32 *wbegin, *wend, *flip, *gamerules, *rnd; /* per world */
 	u8 *wflush;                                  /* per world: serial flush1 work pending */
@@ -124,6 +131,9 @@ struct DevWorld {
 	u32 *nodeCount;
 	BvhNode *nodes;
 	Box6 *nodeBox, *leafBox;
+	i32 *nodeHi;     /* last leaf position below each internal node */
+	Box6 *ibox;      /* per entity: the inflated swept box of the last refit */
+	u64 *pairs;      /* a | b<<32, a = entity at the earlier leaf position */
 
 	i32 *serialList;
 	u64 *deadList; /* key<<32 | entity */

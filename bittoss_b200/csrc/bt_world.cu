@@ -37,11 +37,11 @@ static void set_err(const char *fmt, const char *a, const char *b, int line) {
 	} while (0)
 
 enum {
-	PK_PRE = 0, PK_FLUSH, PK_BEGIN, PK_BUILD_KEYS, PK_SORT, PK_LBVH, PK_REFIT, PK_COLLIDE, PK_DECIDE, PK_PUSH,
+	PK_PRE = 0, PK_FLUSH, PK_BEGIN, PK_BUILD_KEYS, PK_SORT, PK_LBVH, PK_REFIT, PK_PAIRS, PK_NARROW, PK_COLLIDE, PK_DECIDE, PK_PUSH,
 	PK_POST, PK_HASH, PK_RAY_BUILD, PK_RAYCAST, PK_EXCHANGE, PK_NUM
 };
 static const char *PK_NAMES[PK_NUM] = {"pre",    "flush1", "begin_integrate", "morton_keys", "radix_sort",
-                                       "lbvh_build", "refit", "collide",       "decide",      "push",
+                                       "lbvh_build", "refit", "pairs", "narrow", "collide",       "decide",      "push",
                                        "post",   "hash",   "ray_tree_build",  "raycast", "host_exchange"};
 
 typedef long long i64;
@@ -71,6 +71,8 @@ struct bt_world {
 	i32 ticks_since_build;
 	i64 rebuild_every;
 	i64 max_iterations;
+	i64 pair_cache; /* 1: cached candidate pairs (k_pairs + k_narrow); 0: traverse every iteration (k_collide) */
+	i64 pair_rebuilds, pair_overflows;
 	bt_tick_stats stats;
 	bool profiling;
 	cudaEvent_t ev0, ev1;
@@ -159,7 +161,7 @@ int bt_world_create(bt_world **out, int device, int32_t max_ents, int32_t max_sl
 	w->device = device;
 	w->cap_ents = max_ents; w->cap_sliders = max_sliders; w->cap_wires = max_wires; w->cap_worlds = max_worlds;
 	w->tree_valid = false; w->deltas_pending = true; w->ticks_since_build = 0;
-	w->rebuild_every = 8; w->max_iterations = 100000; w->profiling = false; w->ray_valid = false;
+	w->rebuild_every = 16; w->max_iterations = 100000; w->pair_cache = 1; w->pair_rebuilds = 0; w->pair_overflows = 0; w->profiling = false; w->ray_valid = false;
 	w->h_flag = NULL; w->ev0 = w->ev1 = NULL; w->stream = NULL;
 	*out = w;
 #define TRY(x) do { int _r = (x); if (_r) { bt_world_destroy(w); *out = NULL; return _r; } } while (0)
@@ -193,6 +195,10 @@ int bt_world_create(bt_world **out, int device, int32_t max_ents, int32_t max_sl
 	TRY(dalloc(w, &W.leafEnt, n)); TRY(dalloc(w, &W.leafEnt_alt, n));
 	TRY(dalloc(w, &W.leafParent, n)); TRY(dalloc(w, &W.nodeParent, n)); TRY(dalloc(w, &W.nodeCount, n));
 	TRY(dalloc(w, &W.nodes, n)); TRY(dalloc(w, &W.nodeBox, n)); TRY(dalloc(w, &W.leafBox, n));
+	TRY(dalloc(w, &W.nodeHi, n)); TRY(dalloc(w, &W.ibox, n));
+	W.pair_cap = (i32)std::min<size_t>((size_t)1 << 30, 12 * n + 4096);
+	W.margin = 32;
+	TRY(dalloc(w, &W.pairs, (size_t)W.pair_cap));
 	W.serial_cap = 1 << 16; W.dead_cap = max_ents > 0 ? max_ents : 1;
 	TRY(dalloc(w, &W.serialList, (size_t)W.serial_cap)); TRY(dalloc(w, &W.deadList, (size_t)W.dead_cap));
 	TRY(dalloc(w, &W.hash, nw)); TRY(dalloc(w, &W.ctr, (size_t)CT_WORDS));
@@ -217,6 +223,8 @@ int bt_world_set_option(bt_world *w, const char *name, int64_t value) {
 	if (!w || !name) return BT_ERR_ARG;
 	if (!strcmp(name, "rebuild_every")) { w->rebuild_every = value < 1 ? 1 : value; return BT_OK; }
 	if (!strcmp(name, "max_iterations")) { w->max_iterations = value; return BT_OK; }
+	if (!strcmp(name, "pair_cache")) { w->pair_cache = value != 0; return BT_OK; }
+	if (!strcmp(name, "cache_margin")) { w->W.margin = value < 0 ? 0 : (i32)value; return BT_OK; }
 	return BT_ERR_ARG;
 }
 
@@ -379,7 +387,7 @@ static int build_tree(bt_world *w) {
 	for (int k = 0; k < 3; k++) {
 		u32 ext = W.n_leaves ? (u32)(b[3 + k] - b[k]) : 0;
 		int bits = bits_for(ext);
-		W.key_shift[k] = bits > 10 ? bits - 10 : 0;
+		W.key_shift[k] = bits > 9 ? bits - 9 : 0; /* 9 bits per axis */
 	}
 	W.world_bits = bits_for((u32)W.n_worlds); /* ids 0..n_worlds, the last one = "not a leaf" */
 	LAUNCH(w, PK_BUILD_KEYS, k_morton, nblk(n), BT_BLOCK, W);
@@ -438,13 +446,36 @@ static int do_physics(bt_world *w, bool gravity) {
 	}
 	w->ticks_since_build++;
 	i64 it = 0;
+	bool use_cache = w->pair_cache != 0, pairs_valid = false;
 	while (1) {
-		int r = refit(w);
-		if (r) return r;
+		int r;
 		W.iter_id++;
-		LAUNCH(w, PK_COLLIDE, k_collide, nblk(W.n_leaves), BT_BLOCK, W);
+		if (use_cache) {
+			if (!pairs_valid) {
+				r = refit(w);
+				if (r) return r;
+				CK(cudaMemsetAsync(&W.ctr[CT_PAIR_N], 0, 2 * sizeof(u32), w->stream)); /* + CT_CACHE_INVALID */
+				LAUNCH(w, PK_PAIRS, k_pairs, nblk(W.n_leaves), BT_BLOCK, W);
+				pairs_valid = true;
+				w->pair_rebuilds++;
+			}
+			LAUNCH(w, PK_NARROW, k_narrow, 148 * 8, 256, W);
+		} else {
+			r = refit(w);
+			if (r) return r;
+			LAUNCH(w, PK_COLLIDE, k_collide, nblk(W.n_leaves), BT_BLOCK, W);
+		}
 		r = fetch_ctr(w);
 		if (r) return r;
+		if (use_cache && w->h_flag[CT_PAIR_N] > (u32)W.pair_cap) {
+			/* more touching pairs than the buffer holds: this tick falls back to per-iteration
+			 * traversal; the narrow pass above saw only part of the pairs, so redo the iteration */
+			use_cache = false;
+			w->pair_overflows++;
+			CK(cudaMemsetAsync(W.pend, 0, sizeof(u64) * (size_t)n, w->stream));
+			CK(cudaMemsetAsync(&W.ctr[CT_ANY_PROPOSAL], 0, sizeof(u32), w->stream));
+			continue;
+		}
 		if (!w->h_flag[CT_ANY_PROPOSAL]) {
 			/* last doIteration found nothing; it still cleared needsCollision (ent.cpp:459) */
 			CK(cudaMemsetAsync(W.needsCollision, 0, (size_t)n, w->stream));
@@ -456,6 +487,14 @@ static int do_physics(bt_world *w, bool gravity) {
 		LAUNCH(w, PK_PUSH, k_push, nblk(n), BT_BLOCK, W);
 		LAUNCH(w, PK_PUSH, k_push_serial, 1, 32, W);
 		LAUNCH(w, PK_POST, k_post, nblk(n), BT_BLOCK, W);
+		if (use_cache) {
+			/* did a push carry somebody out of the inflated box its pairs were found with? the
+			 * flag is read together with the next iteration's counters, one iteration late is
+			 * too late, so fetch it now (tiny D2H on the same stream) */
+			r = fetch_ctr(w);
+			if (r) return r;
+			if (w->h_flag[CT_CACHE_INVALID]) pairs_valid = false;
+		}
 		if (++it > w->max_iterations) {
 			snprintf(g_err, sizeof g_err, "doPhysics did not converge in %lld iterations", (long long)w->max_iterations);
 			return BT_ERR_OVERFLOW;

@@ -29,6 +29,8 @@ struct Emu {
 	int64_t iterations, ticks;
 	LocalStats st;
 	std::vector<i32> up_root_order;
+	int pair_cache;   /* 1: k_pairs + k_narrow, 0: k_collide every iteration */
+	int64_t pair_rebuilds;
 	int shuffle_seed; /* != 0: run the threads of order-sensitive kernels in a scrambled order */
 };
 
@@ -65,7 +67,7 @@ Emu *bte_create(const bt_world_desc *d, int rebuild_every, int shuffle_seed) {
 	memset(&E->W, 0, sizeof(E->W));
 	memset(&E->st, 0, sizeof(E->st));
 	E->tree_valid = false; E->ticks_since_build = 0; E->rebuild_every = rebuild_every > 0 ? rebuild_every : 1;
-	E->iterations = 0; E->ticks = 0; E->shuffle_seed = shuffle_seed;
+	E->iterations = 0; E->ticks = 0; E->shuffle_seed = shuffle_seed; E->pair_cache = 1; E->pair_rebuilds = 0;
 	DevWorld &W = E->W;
 	const int n = d->n_ents, nw = d->n_worlds;
 	W.n = n; W.n_worlds = nw;
@@ -82,7 +84,9 @@ Emu *bte_create(const bt_world_desc *d, int rebuild_every, int shuffle_seed) {
 	A(E, &W.wire_off, n + 1); A(E, &W.wire_cnt, n); A(E, &W.wire_to, d->n_wires);
 	A(E, &W.keys, n); A(E, &W.keys_alt, n); A(E, &W.leafEnt, n); A(E, &W.leafEnt_alt, n);
 	A(E, &W.leafParent, n); A(E, &W.nodeParent, n); A(E, &W.nodeCount, n); A(E, &W.nodes, n);
-	A(E, &W.nodeBox, n); A(E, &W.leafBox, n);
+	A(E, &W.nodeBox, n); A(E, &W.leafBox, n); A(E, &W.nodeHi, n); A(E, &W.ibox, n);
+	W.pair_cap = 12 * n + 4096; W.margin = 32;
+	A(E, &W.pairs, W.pair_cap);
 	W.serial_cap = 1 << 16; W.dead_cap = n ? n : 1;
 	A(E, &W.serialList, W.serial_cap); A(E, &W.deadList, W.dead_cap); A(E, &W.hash, nw); A(E, &W.ctr, CT_WORDS);
 	for (int g = 0; g < nw; g++) {
@@ -157,7 +161,7 @@ static void build_tree(Emu *E) {
 	for (int k = 0; k < 3; k++) {
 		u32 ext = L ? (u32)(b[3 + k] - b[k]) : 0;
 		int bits = bits_for(ext);
-		W.key_shift[k] = bits > 10 ? bits - 10 : 0;
+		W.key_shift[k] = bits > 9 ? bits - 9 : 0; /* 9 bits per axis */
 	}
 	for (i32 e = 0; e < W.n; e++) t_morton(W, e);
 	/* stand-in for the GPU radix sort: any stable sort by key gives the same result */
@@ -202,11 +206,32 @@ static int do_physics(Emu *E, bool gravity) {
 	E->ticks_since_build++;
 	std::vector<i32> stack(BT_STACK);
 	int guard = 0;
+	bool pairs_valid = false;
+	struct HostEmit {
+		const DevWorld &W;
+		void operator()(i32 a, i32 b) {
+			u32 pos = bt_add32(&W.ctr[CT_PAIR_N], 1u);
+			if ((i32)pos < W.pair_cap) W.pairs[pos] = (u64)(u32)a | ((u64)(u32)b << 32);
+		}
+	};
 	while (1) {
-		refit(E);
 		W.iter_id++;
 		u32 any = 0;
-		{
+		if (E->pair_cache) {
+			if (!pairs_valid) {
+				refit(E);
+				W.ctr[CT_PAIR_N] = 0; W.ctr[CT_CACHE_INVALID] = 0;
+				HostEmit emit = {W};
+				std::vector<i32> o = order(E, W.n_leaves);
+				for (i32 t : o) t_pairs(W, t, stack.data(), 1, emit);
+				if ((i32)W.ctr[CT_PAIR_N] > W.pair_cap) return BT_ERR_OVERFLOW;
+				pairs_valid = true;
+				E->pair_rebuilds++;
+			}
+			std::vector<i32> o = order(E, (i32)W.ctr[CT_PAIR_N]);
+			for (i32 p : o) t_narrow(W, W.pairs[p], E->st, any);
+		} else {
+			refit(E);
 			std::vector<i32> o = order(E, W.n_leaves);
 			for (i32 t : o) t_collide(W, t, stack.data(), 1, E->st, any);
 		}
@@ -224,6 +249,7 @@ static int do_physics(Emu *E, bool gravity) {
 		}
 		if (W.ctr[CT_SERIAL_N]) t_push_serial(W, E->st);
 		for (i32 e = 0; e < n; e++) t_post(W, e);
+		if (W.ctr[CT_CACHE_INVALID]) pairs_valid = false;
 		if (++guard > 100000) return BT_ERR_OVERFLOW;
 	}
 	flush1(E);
@@ -258,6 +284,12 @@ void bte_hash(Emu *E, uint64_t *out) {
 		if (W.inList[e]) { out[W.world[e]] += bt_ent_hash(W, e); cnt[W.world[e]]++; }
 	for (int g = 0; g < W.n_worlds; g++) out[g] += bt_mix64(cnt[g]);
 }
+
+void bte_set_option(Emu *E, const char *name, int64_t v) {
+	if (!strcmp(name, "pair_cache")) E->pair_cache = v != 0;
+	if (!strcmp(name, "cache_margin")) E->W.margin = (i32)v;
+}
+int64_t bte_pair_rebuilds(Emu *E) { return E->pair_rebuilds; }
 
 void bte_stats(Emu *E, int64_t *out) {
 	out[0] = E->ticks; out[1] = E->iterations; out[2] = E->st.cand; out[3] = E->st.pos; out[4] = E->st.push;

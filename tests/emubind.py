@@ -37,6 +37,9 @@ class EmuWorld:
         L.bte_hash.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
         L.bte_stats.argtypes = [C.c_void_p, C.POINTER(C.c_int64)]
         L.bte_peek.argtypes = [C.c_void_p, _i32p, _i32p, C.POINTER(C.c_uint8)]
+        L.bte_set_option.argtypes = [C.c_void_p, C.c_char_p, C.c_int64]
+        L.bte_pair_rebuilds.argtypes = [C.c_void_p]
+        L.bte_pair_rebuilds.restype = C.c_int64
         L.bte_raycast.argtypes = [C.c_void_p, _i32p, _i32p, C.c_int32, _i32p]
         self.L = L
         self.n_worlds = int(wa.desc.n_worlds)
@@ -52,6 +55,12 @@ class EmuWorld:
         rc = self.L.bte_step(self.h, phases)
         if rc != 0:
             raise RuntimeError("bte_step rc=%d" % rc)
+
+    def set_option(self, name, value):
+        self.L.bte_set_option(self.h, name.encode(), int(value))
+
+    def pair_rebuilds(self):
+        return int(self.L.bte_pair_rebuilds(self.h))
 
     def hash(self):
         out = (C.c_uint64 * self.n_worlds)()

@@ -63,3 +63,21 @@ def test_raycast_bodies_match_oracle(oracle_lib, emu):
         want = oracle_lib.create(wa).selectcast(origin, look)
         got = emu.EmuWorld(wa).raycast(origin, look)
         assert np.array_equal(want, got), name
+
+
+@pytest.mark.parametrize("name", ["stack4k_pushall", "spider_kick", "diner_kick"])
+def test_pair_cache_modes_agree(emu, name):
+    """cached candidate pairs (any margin, incl. 0 = constant invalidation) == traversal every iteration"""
+    wa, ref = load_scenario(name)
+    worlds = []
+    for cache, margin in ((0, 16), (1, 0), (1, 16), (1, 200)):
+        w = emu.EmuWorld(wa, rebuild_every=3, shuffle_seed=5)
+        w.set_option("pair_cache", cache)
+        w.set_option("cache_margin", margin)
+        worlds.append(w)
+    for t in range(len(ref)):
+        for w in worlds:
+            w.step(31)
+            assert w.hash()[0] == int(ref[t]), t
+    # a zero margin must have forced more pair rebuilds than a generous one
+    assert worlds[1].pair_rebuilds() >= worlds[3].pair_rebuilds()

@@ -116,3 +116,16 @@ def test_unsupported_handler_is_refused(bt):
     wa.a["handlers"][4] = 4  # PUSH_TEAMSELECT on entity 0: host-side effects, no device implementation
     with pytest.raises(bt.BtError):
         bt.World(wa)
+
+
+@pytest.mark.parametrize("name", ["stack4k_pushall", "spider_kick", "stack20k"])
+def test_cuda_pair_cache_modes_agree(bt, name):
+    """cached candidate pairs (k_pairs + k_narrow, any margin) == traversal every iteration (k_collide)"""
+    wa, ref = load_scenario(name)
+    for cache, margin in ((0, 16), (1, 0), (1, 32), (1, 300)):
+        w = bt.World(wa)
+        w.set_option("pair_cache", cache)
+        w.set_option("cache_margin", margin)
+        hs = w.tick(len(ref), hashes=True)
+        assert [int(x) for x in hs[:, 0]] == [int(x) for x in ref], (cache, margin)
+        w.close()
