@@ -82,12 +82,13 @@ def cpu_baseline(n_cubes, warm_ticks, ticks):
     from oracle import pybind
     cores = 1  # the reference tick is single-threaded and non-reentrant (ent.cpp:17, velbox/box.cpp:17-18)
     if pybind.have_ref():
-        R = pybind.RefLib()
-        R.new_world()
-        R.make_boxstack(n_cubes, 4, 777, 64, 60)
-        for _ in range(warm_ticks):
-            R.step(1)
-        secs, et = R.time_steps(ticks, 1)
+        with pybind.stdout_to_stderr():  # the reference chats on stdout ("Safety crush!" ...)
+            R = pybind.RefLib()
+            R.new_world()
+            R.make_boxstack(n_cubes, 4, 777, 64, 60)
+            for _ in range(warm_ticks):
+                R.step(1)
+            secs, et = R.time_steps(ticks, 1)
         kind = "reference"
     else:
         import bittoss_b200
@@ -158,17 +159,12 @@ def run_cuda(args):
     clocks = sampler.stop()
     st = w.stats()
     h_final = w.hash()[0]
-    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
-    et = torch.tensor([float(st["entity_ticks"])], dtype=torch.float64, device="cuda")
-    hashes = torch.tensor([h_final & 0x7FFFFFFFFFFFFFFF], dtype=torch.int64, device="cuda")
-    if dist is not None:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dist.all_reduce(et, op=dist.ReduceOp.SUM)
-        gathered = [torch.zeros_like(hashes) for _ in range(world_size)]
-        dist.all_gather(gathered, hashes)  # the only collective: final per-world state hashes
-        hashes = torch.cat(gathered)
-    ms_max = float(t.item())
-    value = float(et.item()) / (ms_max * 1e-3)
+    from bittoss_b200.parallel import gather_hashes, reduce_time_and_work, shard_range
+    assert shard_range(world_size, rank, world_size) == (rank, rank + 1)  # one whole world per rank
+    ms_max, et_sum = reduce_time_and_work(ms, float(st["entity_ticks"]), device="cuda")
+    # the only collective of the run: the final per-world state hashes
+    hashes = gather_hashes([h_final], world_size, device="cuda")
+    value = et_sum / (ms_max * 1e-3)
 
     # ---- (2) end to end through the C ABI with HOST buffers: `e2e` ----
     # per step: H2D of the host-side deltas (uCenter/uVel of the tick handlers, 24 B/entity),
@@ -194,35 +190,58 @@ def run_cuda(args):
         et_e2e += live
     barrier()
     e2e_s = time.perf_counter() - t0
-    te = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
-    ee = torch.tensor([float(et_e2e)], dtype=torch.float64, device="cuda")
-    if dist is not None:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-        dist.all_reduce(ee, op=dist.ReduceOp.SUM)
-    e2e_value = float(ee.item()) / float(te.item())
+    e2e_max, e2e_work = reduce_time_and_work(e2e_s, float(et_e2e), device="cuda")
+    e2e_value = e2e_work / e2e_max
 
-    # ---- (3) per-kernel device times (separate pass, events around every launch) ----
+    # ---- (3) per-kernel device times (separate pass, CUDA events around every launch) ----
     w.profile_enable(True)
     w.profile(reset=True)
-    s0 = w.stats()
-    prof_ticks = 4
+    w.stats(reset=True)
+    prof_ticks = 8
     w.tick(prof_ticks)
     prof = w.profile()
-    s1 = w.stats()
+    ps = w.stats()
     w.profile_enable(False)
     total_ms = sum(v[1] for v in prof.values()) or 1.0
-    top = max(prof.items(), key=lambda kv: kv[1][1])
     peak, peak_src = peaks()
-    name, (launches, kms) = top
     n_leaves = n  # every entity of this world is boxed
-    achieved = (COLLIDE_BYTES_PER_LEAF * n_leaves) / ((kms / max(1, launches)) * 1e-3) / 1e9 if name == "collide" else None
-    roofline = {"bound": "hbm", "kernel": name, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": (achieved / peak) if achieved else None, "traffic": None, "peak_source": peak_src,
-                "avg_launch_ms": kms / max(1, launches), "share_of_step": kms / total_ms,
+    P = ps["pairs_cached"] / max(1, ps["pair_builds"])            # cached pairs per k_pairs launch
+    # ALGORITHMIC bytes per launch of each kernel class (DESIGN.md "Kernels" states the per-unit figures)
+    alg = {
+        "narrow": lambda L: 8 * P + 64 * ps["candidate_pairs"] / max(1, L),
+        "pairs": lambda L: 32 * n_leaves + 8 * P,
+        "collide": lambda L: COLLIDE_BYTES_PER_LEAF * n_leaves,
+        "refit": lambda L: 212 * n_leaves,
+        "push": lambda L: 200 * ps["pushes"] / max(1, L),
+        "begin_integrate": lambda L: 94 * n,
+        "decide": lambda L: 10 * n,
+        "post": lambda L: 9 * n,
+        "flush1": lambda L: 5 * n,
+        "hash": lambda L: 61 * n,
+    }
+    per_kernel = {}
+    for k, (launches, kms) in prof.items():
+        if not launches:
+            continue
+        avg_ms = kms / launches
+        ach = alg[k](launches) / (avg_ms * 1e-3) / 1e9 if k in alg and avg_ms > 0 else None
+        per_kernel[k] = {"launches_per_tick": launches / prof_ticks, "avg_launch_ms": round(avg_ms, 5),
+                         "ms_per_tick": round(kms / prof_ticks, 5), "share_of_step": round(kms / total_ms, 4),
+                         "alg_gbs": round(ach, 2) if ach else None, "frac": round(ach / peak, 5) if ach else None}
+    name = max(per_kernel, key=lambda k: per_kernel[k]["ms_per_tick"])
+    top = per_kernel[name]
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "dominant_kernel_traffic.json")
+    if os.path.exists(tpath):
+        tj = json.load(open(tpath))
+        if tj.get("kernel") == name:
+            traffic = tj.get("dram_bytes_per_launch")
+    roofline = {"bound": "hbm", "kernel": "k_" + name, "achieved": top["alg_gbs"], "peak": peak, "unit": "GB/s",
+                "frac": top["frac"], "traffic": traffic, "peak_source": peak_src,
+                "avg_launch_ms": top["avg_launch_ms"], "share_of_step": top["share_of_step"],
                 "whole_tick_algorithmic_gbs": value * BYTES_PER_ENTITY_TICK / 1e9,
                 "whole_tick_frac": value * BYTES_PER_ENTITY_TICK / 1e9 / peak,
-                "per_kernel_ms_per_tick": {k: round(v[1] / prof_ticks, 4) for k, v in prof.items() if v[0]},
-                "per_kernel_launches_per_tick": {k: v[0] / prof_ticks for k, v in prof.items() if v[0]}}
+                "per_kernel": per_kernel}
 
     if rank == 0:
         cb = None
@@ -238,7 +257,9 @@ def run_cuda(args):
                            "l2": "state arrays (>=330 MB/world) exceed the 126 MB L2; no explicit flush",
                            "iterations_per_tick": st["iterations"] / max(1, st["ticks"]),
                            "pushes_per_tick": st["pushes"] / max(1, st["ticks"]),
-                           "final_state_hashes": [int(x) for x in hashes.tolist()]},
+                           "final_state_hashes": ["%016x" % int(x) for x in hashes],
+                           "pairs_cached_per_tick": st["pairs_cached"] / max(1, st["ticks"]),
+                           "pair_builds_per_tick": st["pair_builds"] / max(1, st["ticks"])},
                 "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 24 * live,
                         "d2h_bytes_per_step": 24 * live + 8, "steps": e2e_steps},

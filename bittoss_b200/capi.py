@@ -32,7 +32,8 @@ class BtError(RuntimeError):
 class BtTickStats(C.Structure):
     _fields_ = [(k, C.c_int64) for k in
                 ("ticks", "iterations", "candidate_pairs", "positives", "pushes", "serial_pushes", "crushes",
-                 "fumbles", "kernel_launches", "tree_builds", "tree_refits", "live_ents", "entity_ticks")]
+                 "fumbles", "kernel_launches", "tree_builds", "tree_refits", "live_ents", "entity_ticks",
+                 "pair_builds", "pairs_cached", "pair_overflows")]
 
 
 class BtProfile(C.Structure):

@@ -446,7 +446,7 @@ static int do_physics(bt_world *w, bool gravity) {
 	}
 	w->ticks_since_build++;
 	i64 it = 0;
-	bool use_cache = w->pair_cache != 0, pairs_valid = false;
+	bool use_cache = w->pair_cache != 0, pairs_valid = false, count_pairs = false;
 	while (1) {
 		int r;
 		W.iter_id++;
@@ -458,6 +458,8 @@ static int do_physics(bt_world *w, bool gravity) {
 				LAUNCH(w, PK_PAIRS, k_pairs, nblk(W.n_leaves), BT_BLOCK, W);
 				pairs_valid = true;
 				w->pair_rebuilds++;
+				w->stats.pair_builds++;
+				count_pairs = true;
 			}
 			LAUNCH(w, PK_NARROW, k_narrow, 148 * 8, 256, W);
 		} else {
@@ -467,11 +469,13 @@ static int do_physics(bt_world *w, bool gravity) {
 		}
 		r = fetch_ctr(w);
 		if (r) return r;
+		if (count_pairs) { w->stats.pairs_cached += (i64)w->h_flag[CT_PAIR_N]; count_pairs = false; }
 		if (use_cache && w->h_flag[CT_PAIR_N] > (u32)W.pair_cap) {
 			/* more touching pairs than the buffer holds: this tick falls back to per-iteration
 			 * traversal; the narrow pass above saw only part of the pairs, so redo the iteration */
 			use_cache = false;
 			w->pair_overflows++;
+			w->stats.pair_overflows++;
 			CK(cudaMemsetAsync(W.pend, 0, sizeof(u64) * (size_t)n, w->stream));
 			CK(cudaMemsetAsync(&W.ctr[CT_ANY_PROPOSAL], 0, sizeof(u32), w->stream));
 			continue;

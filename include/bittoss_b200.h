@@ -117,6 +117,9 @@ typedef struct bt_tick_stats {
 	int64_t tree_refits;     /* bottom-up refits                                         */
 	int64_t live_ents;       /* live entities after the last tick                        */
 	int64_t entity_ticks;    /* sum over ticks of live entities after the tick           */
+	int64_t pair_builds;     /* k_pairs launches (>= 1 per tick; more when the cache is invalidated) */
+	int64_t pairs_cached;    /* unordered candidate pairs written by those launches      */
+	int64_t pair_overflows;  /* ticks that fell back to per-iteration traversal          */
 } bt_tick_stats;
 
 /* Per-kernel-class device timing, filled only while profiling is enabled. */

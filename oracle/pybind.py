@@ -32,6 +32,29 @@ def build(ref: bool = True):
         subprocess.check_call(["make", "-s", "-C", HERE, "ref"])
 
 
+import contextlib
+
+
+@contextlib.contextmanager
+def stdout_to_stderr():
+    """The reference prints diagnostics with puts()/printf() (file.cpp:16, ent.cpp:519,582);
+    keep them away from a caller's machine-readable stdout."""
+    sys.stdout.flush()
+    saved = os.dup(1)
+    try:
+        os.dup2(2, 1)
+        yield
+    finally:
+        for name in (None, "libc.so.6"):
+            try:
+                C.CDLL(name).fflush(None)
+                break
+            except Exception:
+                continue
+        os.dup2(saved, 1)
+        os.close(saved)
+
+
 def have_ref():
     return os.path.exists(REF_SO) and os.path.isdir(os.path.join(REF_DATA_PARENT, "data"))
 
@@ -64,7 +87,9 @@ class RefLib:
         L.btref_selectcast_batch.argtypes = [_i32p, _i32p, C.c_int32, _i32p]
         L.btref_time_steps.argtypes = [C.c_int, C.c_int32, C.POINTER(C.c_int64)]
         L.btref_time_steps.restype = C.c_double
-        if L.btref_init(REF_DATA_PARENT.encode()) != 0:
+        with stdout_to_stderr():
+            rc = L.btref_init(REF_DATA_PARENT.encode())
+        if rc != 0:
             raise RuntimeError("btref_init failed")
         self.L = L
 

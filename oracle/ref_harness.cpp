@@ -100,6 +100,9 @@ extern "C" {
 
 int btref_init(const char *dir_with_data) {
 	if (inited) return 0;
+	/* the reference reports through puts()/printf(); line-buffer C stdout so a caller that
+	 * temporarily points fd 1 elsewhere (oracle/pybind.py stdout_to_stderr) really captures it */
+	setvbuf(stdout, NULL, _IOLBF, 0);
 	char prev[4096];
 	if (!getcwd(prev, sizeof prev)) return -1;
 	if (chdir(dir_with_data)) { perror("btref_init chdir"); return -1; }
@@ -121,6 +124,8 @@ int btref_init(const char *dir_with_data) {
 	inited = 1;
 	return 0;
 }
+
+void btref_flush(void) { fflush(stdout); fflush(stderr); }
 
 int btref_new_world(void) {
 	RefWorld *w = new RefWorld();

@@ -129,3 +129,44 @@ def test_cuda_pair_cache_modes_agree(bt, name):
         hs = w.tick(len(ref), hashes=True)
         assert [int(x) for x in hs[:, 0]] == [int(x) for x in ref], (cache, margin)
         w.close()
+
+
+def test_cuda_raycast_100k_world_vs_oracle(bt, oracle_lib):
+    """config-5 style: rays from random entities of a settled 100k-cube world, subsample vs brute force"""
+    wa = bt.synth_boxstack(100000, 4, 777, 64, 60)
+    w = bt.World(wa)
+    w.tick(30)
+    st = w.download()
+    rng = np.random.RandomState(11)
+    origin = rng.randint(0, st.n, size=2048).astype(np.int32)
+    look = rng.randint(-64, 65, size=(2048, 3)).astype(np.int32)
+    look[np.abs(look).sum(1) == 0] = (0, 0, 64)
+    got = w.raycast(origin, look)
+    want = oracle_lib.create(st).selectcast(origin, look)
+    assert np.array_equal(got, want)
+    assert (got >= 0).mean() > 0.3
+    w.close()
+
+
+def test_cuda_host_exchange_roundtrip(bt, oracle_lib):
+    """bt_world_apply_host_deltas == uVel/uCenter on the host side; bt_world_read_state == download"""
+    wa, _ = load_scenario("tower_kick")
+    rng = np.random.RandomState(2)
+    dc = rng.randint(-20, 21, size=(wa.n, 3)).astype(np.int32)
+    dv = rng.randint(-50, 51, size=(wa.n, 3)).astype(np.int32)
+    w = bt.World(wa)
+    w.apply_host_deltas(dc, dv)
+    wa.a["d_center"][: 3 * wa.n] += dc.reshape(-1)
+    wa.a["d_vel"][: 3 * wa.n] += dv.reshape(-1)
+    ow = oracle_lib.create(wa)
+    for t in range(20):
+        w.step(31)
+        ow.step(31)
+        assert w.hash() == ow.hash(), t
+    n = w.count()[0]
+    c = np.zeros((n, 3), dtype=np.int32)
+    v = np.zeros((n, 3), dtype=np.int32)
+    w.read_state(c, v)
+    st = w.download()
+    assert np.array_equal(c, st.vec("center")) and np.array_equal(v, st.vec("vel"))
+    w.close()
