@@ -119,7 +119,7 @@ def run_reference(args):
             "cpu_baseline": cb,
             "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def run_cuda(args):
@@ -266,13 +266,27 @@ def run_cuda(args):
                 "gpu_launches": st["kernel_launches"],
                 "roofline": roofline,
                 "cpu_baseline": cb}
-        print(json.dumps(line), flush=True)
+        emit(line)
     w.close()
     if dist is not None:
         dist.destroy_process_group()
 
 
+_REAL_STDOUT = None
+
+
+def emit(line):
+    """The one JSON line goes to the real stdout; everything else any library prints on
+    fd 1 (NCCL's version banner, the reference's puts()) was pointed at stderr in main()."""
+    data = (json.dumps(line) + "\n").encode()
+    os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, data)
+
+
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=50)
