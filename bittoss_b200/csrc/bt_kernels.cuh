@@ -46,7 +46,8 @@ __global__ void __launch_bounds__(BT_BLOCK) k_flush2_apply(DevWorld W) { t_flush
 __global__ void __launch_bounds__(BT_BLOCK) k_zero_deltas(DevWorld W) { t_zero_deltas(W, TID); }
 __global__ void __launch_bounds__(BT_BLOCK) k_integrate(DevWorld W) { t_integrate(W, TID); }
 
-__global__ void __launch_bounds__(BT_BLOCK) k_begin_fused(DevWorld W, int gravity) { t_begin_fused(W, TID, gravity); }
+__global__ void __launch_bounds__(BT_BLOCK) k_begin_fused(DevWorld W, int gravity, int ctrls) { t_begin_fused(W, TID, gravity, ctrls); }
+__global__ void __launch_bounds__(BT_BLOCK) k_flip_only(DevWorld W) { t_flip_only(W, TID); }
 
 __global__ void __launch_bounds__(BT_BLOCK) k_bounds(DevWorld W) {
 	/* warp-reduce before the atomics: 6 atomics per warp instead of per thread */
@@ -152,7 +153,6 @@ __global__ void __launch_bounds__(BT_BLOCK) k_decide(DevWorld W) {
 	if (TID == 0) W.ctr[CT_ANY_PROPOSAL] = 0; /* the host already fetched this iteration's value */
 	t_decide(W, TID);
 }
-__global__ void __launch_bounds__(BT_BLOCK) k_conflict(DevWorld W) { t_conflict(W, TID); }
 __global__ void __launch_bounds__(BT_BLOCK) k_push(DevWorld W) {
 	LocalStats st = {0, 0, 0, 0, 0};
 	t_push(W, TID, st);

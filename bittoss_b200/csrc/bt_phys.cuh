@@ -89,6 +89,7 @@ static BT_HD void bt_uslider(const DevWorld &W, i32 e, int ix, i32 value) {
 	int ns = W.slider_off[e + 1] - W.slider_off[e];
 	if (ix < 0 || ix >= ns) return;
 	W.fullFlush[e] = 1;
+	W.ctr[CT_FLUSH_HINT] = 1;
 	int s = W.slider_off[e] + ix;
 	if (value > W.smax[s]) W.smax[s] = value;
 	if (value < W.smin[s]) W.smin[s] = value;
@@ -180,6 +181,7 @@ static BT_HD void bt_pair_handler(const DevWorld &W, int slot, i32 me) {
 	int id = (W.hpair[me] >> (8 * slot)) & 0xff;
 	if (id == 3) {
 		W.fullFlush[me] = 1;
+		W.ctr[CT_FLUSH_HINT] = 1;
 		W.ntype[me] = W.type[me] | T_DEBRIS;
 		W.ncollide[me] = W.collide[me] | T_TERRAIN | T_OBSTACLE | T_DEBRIS;
 		if (slot == 1) W.hpair[me] &= ~(0xffu << 8);
@@ -224,6 +226,7 @@ static BT_HD void bt_crush(const DevWorld &W, i32 e, u32 key, LocalStats &st) {
 	W.inList[e] = 0;
 	W.hasBox[e] = 0;
 	W.dead[e] = 1;
+	W.ctr[CT_FLUSH_HINT] = 1; /* wires that point at it must go (flushMisc ent.cpp:706-712) */
 	u32 slot = bt_add32(&W.ctr[CT_DEAD_N], 1u);
 	if ((i32)slot < W.dead_cap) W.deadList[slot] = ((u64)key << 32) | (u32)e;
 }
@@ -648,7 +651,7 @@ static BT_HD int bt_touch_right(const NodeRegs &n, const i32 *qlo, const i32 *qh
 	       (n.c.x <= qhi[2]) & ((wr & 0xffff) <= w) & (w <= (wr >> 16));
 }
 
-#define BT_STACK 64
+#define BT_STACK 32 /* deferred right children; observed <= 6 on the benchmark worlds; overflow raises BT_ERR_OVERFLOW */
 
 /* doIteration ent.cpp:437-462 for the entity at sorted leaf position t.
  * `stack` is this thread's traversal stack (shared memory on the device). */
@@ -798,26 +801,6 @@ static BT_HD void t_decide(const DevWorld &W, i32 e) {
 	W.ready[e] = p ? (u8)bt_should_resolve(W, e, p) : 0;
 }
 
-/* A root that resolves by closing a cycle shares trees with the other members of that
- * cycle.  If another member also resolves this iteration (a tie), both go to the serial
- * lane so the outcome matches the reference's sequential loop in canonical order. */
-static BT_HD void t_conflict(const DevWorld &W, i32 e) {
-	if (e >= W.n || W.ready[e] != 2) return;
-	i32 r = W.holdRoot[bt_unpack_coll(W.pend[e]).buddy];
-	int conflict = 0, guard = 0;
-	while (r != e && guard++ < 1000000) {
-		if (W.ready[r]) conflict = 1;
-		r = W.holdRoot[bt_unpack_coll(W.pend[r]).buddy];
-	}
-	if (conflict) {
-		u32 slot = bt_add32(&W.ctr[CT_SERIAL_N], 1u);
-		if ((i32)slot < W.serial_cap) W.serialList[slot] = e;
-		else W.ctr[CT_ERROR] = (u32)(-BT_ERR_OVERFLOW);
-	} else {
-		W.ready[e] = 1;
-	}
-}
-
 /* pinch ent.cpp:483-507 */
 static BT_HD i32 bt_pinch(const DevWorld &W, i32 e, int axis, i32 o, u32 key, LocalStats &st) {
 	i32 leaf1 = e;
@@ -932,9 +915,29 @@ static BT_HD u32 bt_push_key(const DevWorld &W, i32 root) {
 	return ((u32)W.iter_id << 20) ^ (u32)(0xfffff - (root & 0xfffff));
 }
 
-/* parallel lane: one thread per ready root (ent.cpp:879-882) */
+/* parallel lane: one thread per ready root (ent.cpp:879-882).  A root that resolves by
+ * closing a cycle (ready == 2) first checks the other members of its cycle: if one of them
+ * resolves too (a tie) both go to the serial lane.  ready[] of other roots is only ever
+ * rewritten 2 -> 1 by their own thread here, and the test is "non-zero", so the concurrent
+ * reads are safe. */
 static BT_HD void t_push(const DevWorld &W, i32 e, LocalStats &st) {
-	if (e >= W.n || W.ready[e] != 1) return;
+	if (e >= W.n) return;
+	u8 rd = W.ready[e];
+	if (!rd) return;
+	if (rd == 2) {
+		i32 r = W.holdRoot[bt_unpack_coll(W.pend[e]).buddy];
+		int conflict = 0, guard = 0;
+		while (r != e && guard++ < 1000000) {
+			if (W.ready[r]) conflict = 1;
+			r = W.holdRoot[bt_unpack_coll(W.pend[r]).buddy];
+		}
+		if (conflict) {
+			u32 slot = bt_add32(&W.ctr[CT_SERIAL_N], 1u);
+			if ((i32)slot < W.serial_cap) W.serialList[slot] = e;
+			else W.ctr[CT_ERROR] = (u32)(-BT_ERR_OVERFLOW);
+			return;
+		}
+	}
 	bt_push(W, bt_unpack_coll(W.pend[e]), bt_push_key(W, e), st);
 }
 
@@ -1010,6 +1013,11 @@ static BT_HD void t_flush_serial(const DevWorld &W, i32 g, LocalStats &st) {
 		}
 		if (W.newHolder[i] >= 0) W.ctr[CT_ERROR] = (u32)(-BT_ERR_UNSUPPORTED);
 	}
+}
+
+/* flush1 with nothing to do still toggles the death flip-flop (ent.cpp:795) */
+static BT_HD void t_flip_only(const DevWorld &W, i32 g) {
+	if (g < W.n_worlds) W.flip[g] ^= 1;
 }
 
 /* flushMisc ent.cpp:674-714 */
@@ -1100,8 +1108,12 @@ static BT_HD void t_integrate(const DevWorld &W, i32 e) {
  * gravity this very kernel stands for: nothing is read from or written to d_center / d_vel.
  * Gravity reaches every member of a tree whose root is not weightless, exactly what
  * uVel(root) + flushPosVel do.  (ent.cpp:806-811, effects.cpp:35-41, ent.cpp:845-858) */
-static BT_HD void t_begin_fused(const DevWorld &W, i32 e, int gravity) {
+static BT_HD void t_begin_fused(const DevWorld &W, i32 e, int gravity, int ctrls) {
 	if (e >= W.n || !W.inList[e]) return;
+	if (ctrls) { /* flushCtrls ent.cpp:32-37; nothing on the device reads buttons before this point */
+		u32 v2 = W.btn_v2[e];
+		if (W.btn_v[e] | v2) { W.btn_v[e] = v2; W.btn_v2[e] = 0; }
+	}
 	int4 c = W.center[e], v = W.vel[e];
 	if (gravity) {
 		i32 r = W.holdRoot[e];

@@ -87,8 +87,9 @@ enum {
 	/* CT_BOUNDS occupies 6 words */
 	CT_BOUNDS,           /* 6 ints: min xyz, max xyz of leaf centres */
 	CT_PAIR_N = 14,      /* unordered candidate pairs emitted by k_pairs (may exceed pair_cap) */
-	CT_CACHE_INVALID,    /* an entity left the inflated box its cached pairs were found with */
+	CT_CACHE_INVALID = 15, /* an entity left the inflated box its cached pairs were found with */
 	CT_STAT0 = 16,       /* 64-bit stats start here (as pairs of u32 slots, 8-byte aligned) */
+	CT_FLUSH_HINT = 32,  /* something happened that flush1 has to act on (slider/mask request, a death) */
 	CT_WORDS = 64
 };
 enum { SK_ITERS = 0, SK_CAND, SK_POS, SK_PUSH, SK_SERIAL, SK_CRUSH, SK_FUMBLE, SK_NUM };

@@ -9,8 +9,8 @@
  *   k_begin_fused               doGravity + flush2 + integrate (fast path, no pending deltas)
  *     or k_gravity, k_flush2_apply, k_integrate
  *   every `rebuild_every` ticks: k_bounds, k_morton, radix sort, k_lbvh   (LBVH build)
- *   loop: k_refit, k_collide -> (host reads "any proposal") -> k_decide, k_conflict,
- *         k_push, k_push_serial, k_post
+ *   loop: [k_refit, k_pairs when the pair cache is stale] k_narrow -> (host reads "any proposal")
+ *         -> k_decide, k_push (+ tie-cycle detection), k_push_serial, k_post
  *   flush1 again, (flush2 if deltas), k_hash on request
  */
 #include <cuda_runtime.h>
@@ -68,6 +68,8 @@ struct bt_world {
 	u64 *d_hsum; u32 *d_hcnt;
 	u32 *d_sorthist; int sorthist_len;
 	bool tree_valid, deltas_pending;
+	int full_flush_left; /* flush1 calls that must run in full (after an upload); afterwards CT_FLUSH_HINT decides */
+	bool ctrls_fused;    /* flushCtrls of this step rides in k_begin_fused */
 	i32 ticks_since_build;
 	i64 rebuild_every;
 	i64 max_iterations;
@@ -160,7 +162,7 @@ int bt_world_create(bt_world **out, int device, int32_t max_ents, int32_t max_sl
 	memset(&w->ray, 0, sizeof(w->ray));
 	w->device = device;
 	w->cap_ents = max_ents; w->cap_sliders = max_sliders; w->cap_wires = max_wires; w->cap_worlds = max_worlds;
-	w->tree_valid = false; w->deltas_pending = true; w->ticks_since_build = 0;
+	w->tree_valid = false; w->deltas_pending = true; w->ticks_since_build = 0; w->full_flush_left = 2; w->ctrls_fused = false;
 	w->rebuild_every = 16; w->max_iterations = 100000; w->pair_cache = 1; w->pair_rebuilds = 0; w->pair_overflows = 0; w->profiling = false; w->ray_valid = false;
 	w->h_flag = NULL; w->ev0 = w->ev1 = NULL; w->stream = NULL;
 	*out = w;
@@ -349,6 +351,7 @@ int bt_world_upload(bt_world *w, const bt_world_desc *d) {
 	w->up_root_order.assign(d->root_order, d->root_order + n);
 	w->tree_valid = false; w->ray_valid = false; w->ranks_valid = false;
 	w->deltas_pending = deltas;
+	w->full_flush_left = 2; /* both dead_max slots of the upload get looked at */
 	w->ticks_since_build = 0;
 	w->stats.live_ents = n;
 	return BT_OK;
@@ -409,8 +412,17 @@ static int refit(bt_world *w) {
 	return 0;
 }
 
-static int flush1(bt_world *w) {
+/* flush1 (ent.cpp:794-804).  `hint` = the host's latest copy of CT_FLUSH_HINT: when
+ * nothing asked for a flush (no slider/mask request, no death, nothing uploaded) the three
+ * full passes would find nothing, so only the death flip-flop is toggled. */
+static int flush1(bt_world *w, bool hint) {
 	DevWorld &W = w->W;
+	if (w->full_flush_left <= 0 && !hint) {
+		LAUNCH(w, PK_FLUSH, k_flip_only, nblk(W.n_worlds), BT_BLOCK, W);
+		return 0;
+	}
+	if (w->full_flush_left > 0) w->full_flush_left--;
+	CK(cudaMemsetAsync(&W.ctr[CT_FLUSH_HINT], 0, sizeof(u32), w->stream));
 	LAUNCH(w, PK_FLUSH, k_flush_scan, nblk(W.n), BT_BLOCK, W);
 	LAUNCH(w, PK_FLUSH, k_flush_serial, nblk(W.n_worlds), BT_BLOCK, W);
 	LAUNCH(w, PK_FLUSH, k_flush_misc, nblk(W.n), BT_BLOCK, W);
@@ -432,7 +444,7 @@ static int do_physics(bt_world *w, bool gravity) {
 	DevWorld &W = w->W;
 	const i32 n = W.n;
 	if (!w->deltas_pending) {
-		LAUNCH(w, PK_BEGIN, k_begin_fused, nblk(n), BT_BLOCK, W, gravity ? 1 : 0);
+		LAUNCH(w, PK_BEGIN, k_begin_fused, nblk(n), BT_BLOCK, W, gravity ? 1 : 0, w->ctrls_fused ? 1 : 0);
 	} else {
 		if (gravity) LAUNCH(w, PK_BEGIN, k_gravity, nblk(n), BT_BLOCK, W);
 		LAUNCH(w, PK_BEGIN, k_flush2_apply, nblk(n), BT_BLOCK, W);
@@ -487,7 +499,6 @@ static int do_physics(bt_world *w, bool gravity) {
 		}
 		w->stats.iterations++;
 		LAUNCH(w, PK_DECIDE, k_decide, nblk(n), BT_BLOCK, W);
-		LAUNCH(w, PK_DECIDE, k_conflict, nblk(n), BT_BLOCK, W);
 		LAUNCH(w, PK_PUSH, k_push, nblk(n), BT_BLOCK, W);
 		LAUNCH(w, PK_PUSH, k_push_serial, 1, 32, W);
 		LAUNCH(w, PK_POST, k_post, nblk(n), BT_BLOCK, W);
@@ -505,11 +516,15 @@ static int do_physics(bt_world *w, bool gravity) {
 		}
 	}
 	/* invokeOnCrush (ent.cpp:907): crush handlers are host-side events (dead list) */
-	int r = flush1(w);
+	/* h_flag holds the counters fetched after the last k_narrow, i.e. after every push */
+	int r = flush1(w, w->h_flag[CT_FLUSH_HINT] != 0);
 	if (r) return r;
+	/* a flush1 that runs k_flush_serial can itself kill (dead_max) and so leave wires to clean
+	 * up: keep the next flush1 full in that case */
 	/* flush2 (ent.cpp:910): none of the device-side handlers leaves a delta behind */
 	r = fetch_ctr(w);
 	if (r) return r;
+	if (w->h_flag[CT_FLUSH_HINT] && w->full_flush_left < 1) w->full_flush_left = 1;
 	if (w->h_flag[CT_NEED_REBUILD]) {
 		w->tree_valid = false;
 		CK(cudaMemsetAsync(&W.ctr[CT_NEED_REBUILD], 0, sizeof(u32), w->stream));
@@ -523,9 +538,11 @@ int bt_world_step(bt_world *w, uint32_t phases) {
 	CK(cudaSetDevice(w->device));
 	DevWorld &W = w->W;
 	const i32 n = W.n;
-	if (phases & BT_PHASE_CTRLS) LAUNCH(w, PK_PRE, k_pre, nblk(n), BT_BLOCK, W, phases);
+	/* flushCtrls rides in k_begin_fused when this step also integrates on the fast path */
+	w->ctrls_fused = (phases & BT_PHASE_CTRLS) && (phases & BT_PHASE_PHYSICS) && !w->deltas_pending;
+	if ((phases & BT_PHASE_CTRLS) && !w->ctrls_fused) LAUNCH(w, PK_PRE, k_pre, nblk(n), BT_BLOCK, W, phases);
 	if (phases & BT_PHASE_PREP) {
-		int r = flush1(w);
+		int r = flush1(w, false);
 		if (r) return r;
 	}
 	if ((phases & BT_PHASE_GRAVITY) && !(phases & BT_PHASE_PHYSICS)) {

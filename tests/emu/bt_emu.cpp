@@ -24,7 +24,8 @@
 struct Emu {
 	DevWorld W;
 	std::vector<void *> allocs;
-	bool tree_valid, deltas_pending;
+	bool tree_valid, deltas_pending, ctrls_fused;
+	int full_flush_left;
 	int ticks_since_build, rebuild_every;
 	int64_t iterations, ticks;
 	LocalStats st;
@@ -66,7 +67,7 @@ Emu *bte_create(const bt_world_desc *d, int rebuild_every, int shuffle_seed) {
 	Emu *E = new Emu();
 	memset(&E->W, 0, sizeof(E->W));
 	memset(&E->st, 0, sizeof(E->st));
-	E->tree_valid = false; E->ticks_since_build = 0; E->rebuild_every = rebuild_every > 0 ? rebuild_every : 1;
+	E->tree_valid = false; E->ticks_since_build = 0; E->ctrls_fused = false; E->full_flush_left = 2; E->rebuild_every = rebuild_every > 0 ? rebuild_every : 1;
 	E->iterations = 0; E->ticks = 0; E->shuffle_seed = shuffle_seed; E->pair_cache = 1; E->pair_rebuilds = 0;
 	DevWorld &W = E->W;
 	const int n = d->n_ents, nw = d->n_worlds;
@@ -184,8 +185,14 @@ static void refit(Emu *E) {
 	for (i32 t : o) t_refit(W, t);
 }
 
-static void flush1(Emu *E) {
+static void flush1(Emu *E, bool hint) {
 	DevWorld &W = E->W;
+	if (E->full_flush_left <= 0 && !hint) {
+		for (i32 g = 0; g < W.n_worlds; g++) t_flip_only(W, g);
+		return;
+	}
+	if (E->full_flush_left > 0) E->full_flush_left--;
+	W.ctr[CT_FLUSH_HINT] = 0;
 	for (i32 e = 0; e < W.n; e++) t_flush_scan(W, e);
 	for (i32 g = 0; g < W.n_worlds; g++) t_flush_serial(W, g, E->st);
 	for (i32 e = 0; e < W.n; e++) t_flush_misc(W, e);
@@ -195,7 +202,7 @@ static int do_physics(Emu *E, bool gravity) {
 	DevWorld &W = E->W;
 	const i32 n = W.n;
 	if (!E->deltas_pending) {
-		for (i32 e = 0; e < n; e++) t_begin_fused(W, e, gravity ? 1 : 0);
+		for (i32 e = 0; e < n; e++) t_begin_fused(W, e, gravity ? 1 : 0, E->ctrls_fused ? 1 : 0);
 	} else {
 		if (gravity) for (i32 e = 0; e < n; e++) t_gravity(W, e);
 		for (i32 e = 0; e < n; e++) t_flush2_apply(W, e);
@@ -242,7 +249,6 @@ static int do_physics(Emu *E, bool gravity) {
 		}
 		E->iterations++;
 		for (i32 e = 0; e < n; e++) t_decide(W, e);
-		for (i32 e = 0; e < n; e++) t_conflict(W, e);
 		{
 			std::vector<i32> o = order(E, n);
 			for (i32 e : o) t_push(W, e, E->st);
@@ -252,7 +258,8 @@ static int do_physics(Emu *E, bool gravity) {
 		if (W.ctr[CT_CACHE_INVALID]) pairs_valid = false;
 		if (++guard > 100000) return BT_ERR_OVERFLOW;
 	}
-	flush1(E);
+	flush1(E, W.ctr[CT_FLUSH_HINT] != 0);
+	if (W.ctr[CT_FLUSH_HINT] && E->full_flush_left < 1) E->full_flush_left = 1;
 	if (W.ctr[CT_ERROR]) return -(int)W.ctr[CT_ERROR];
 	if (W.ctr[CT_NEED_REBUILD]) { E->tree_valid = false; W.ctr[CT_NEED_REBUILD] = 0; }
 	return 0;
@@ -260,8 +267,9 @@ static int do_physics(Emu *E, bool gravity) {
 
 int bte_step(Emu *E, uint32_t phases) {
 	DevWorld &W = E->W;
-	if (phases & BT_PHASE_CTRLS) for (i32 e = 0; e < W.n; e++) t_pre(W, e, phases);
-	if (phases & BT_PHASE_PREP) flush1(E);
+	E->ctrls_fused = (phases & BT_PHASE_CTRLS) && (phases & BT_PHASE_PHYSICS) && !E->deltas_pending;
+	if ((phases & BT_PHASE_CTRLS) && !E->ctrls_fused) for (i32 e = 0; e < W.n; e++) t_pre(W, e, phases);
+	if (phases & BT_PHASE_PREP) flush1(E, false);
 	if ((phases & BT_PHASE_GRAVITY) && !(phases & BT_PHASE_PHYSICS)) {
 		for (i32 e = 0; e < W.n; e++) t_gravity(W, e);
 		E->deltas_pending = true;
