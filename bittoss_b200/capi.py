@@ -33,7 +33,7 @@ class BtTickStats(C.Structure):
     _fields_ = [(k, C.c_int64) for k in
                 ("ticks", "iterations", "candidate_pairs", "positives", "pushes", "serial_pushes", "crushes",
                  "fumbles", "kernel_launches", "tree_builds", "tree_refits", "live_ents", "entity_ticks",
-                 "pair_builds", "pairs_cached", "pair_overflows")]
+                 "pair_builds", "pairs_cached", "pair_overflows", "unsupported_events")]
 
 
 class BtProfile(C.Structure):
@@ -82,6 +82,7 @@ def lib():
     L.bt_world_stream.restype = C.c_void_p
     L.bt_world_hash.argtypes = [C.c_void_p, _u64p]
     L.bt_world_stats.argtypes = [C.c_void_p, C.POINTER(BtTickStats), C.c_int]
+    L.bt_world_unsupported.argtypes = [C.c_void_p, C.POINTER(C.c_uint32)]
     L.bt_world_profile_enable.argtypes = [C.c_void_p, C.c_int]
     L.bt_world_profile_read.argtypes = [C.c_void_p, C.POINTER(BtProfile), C.c_int]
     L.bt_world_set_option.argtypes = [C.c_void_p, C.c_char_p, C.c_int64]
@@ -229,6 +230,11 @@ class World:
         s = BtTickStats()
         _ck(self.L.bt_world_stats(self.h, C.byref(s), int(reset)), "bt_world_stats")
         return {k: int(getattr(s, k)) for k, _ in BtTickStats._fields_}
+
+    def unsupported_per_world(self):
+        out = np.zeros(self.n_worlds, dtype=np.uint32)
+        _ck(self.L.bt_world_unsupported(self.h, out.ctypes.data_as(C.POINTER(C.c_uint32))), "bt_world_unsupported")
+        return out
 
     def profile_enable(self, on=True):
         _ck(self.L.bt_world_profile_enable(self.h, int(on)), "bt_world_profile_enable")

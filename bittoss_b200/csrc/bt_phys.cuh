@@ -60,6 +60,12 @@ struct LocalStats {
 /* needsVelbox ent.cpp:75-77 */
 static BT_HD int bt_needs_box(u32 type, u32 collide) { return collide || (type & T_COLLIDABLE); }
 
+/* a handler with no device implementation would have run for entity e (lenient uploads only) */
+static BT_HD void bt_unsup(const DevWorld &W, i32 e) {
+	bt_add32(&W.ctr[CT_UNSUPPORTED], 1u);
+	bt_add32(&W.wunsup[W.world[e]], 1u);
+}
+
 /* boundVec ent.cpp:20-30 (int64 multiply, truncating division) */
 static BT_HD void bt_bound_vec(i32 *v, i32 bound, int len) {
 	i32 mx = bound;
@@ -144,6 +150,8 @@ static BT_HD int bt_push_handler(const DevWorld &W, i32 me, i32 him) {
 	int id = (W.hphys[me] >> 8) & 0xff;
 	if (id == 2) {
 		if (W.type[him] & (T_TERRAIN | T_OBSTACLE | T_DEBRIS)) bt_or32(&W.btn_v2[me], 1u); /* pushBtn(me,0) */
+	} else if (id != 0) {
+		bt_unsup(W, me); /* only reachable after a lenient upload */
 	}
 	return 0;
 }
@@ -172,7 +180,9 @@ static BT_HD int bt_pushed_handler(const DevWorld &W, i32 me, i32 him, int axis,
 		bt_uslider(W, me, s_vel + 1, vel[1]);
 		return 0;
 	}
-	default: return 0;
+	default:
+		bt_unsup(W, me);
+		return 0;
 	}
 }
 
@@ -185,6 +195,8 @@ static BT_HD void bt_pair_handler(const DevWorld &W, int slot, i32 me) {
 		W.ntype[me] = W.type[me] | T_DEBRIS;
 		W.ncollide[me] = W.collide[me] | T_TERRAIN | T_OBSTACLE | T_DEBRIS;
 		if (slot == 1) W.hpair[me] &= ~(0xffu << 8);
+	} else if (id != 0) {
+		bt_unsup(W, me);
 	}
 }
 
@@ -227,6 +239,7 @@ static BT_HD void bt_crush(const DevWorld &W, i32 e, u32 key, LocalStats &st) {
 	W.hasBox[e] = 0;
 	W.dead[e] = 1;
 	W.ctr[CT_FLUSH_HINT] = 1; /* wires that point at it must go (flushMisc ent.cpp:706-712) */
+	if ((W.hphys[e] >> 24) & 0xff) bt_unsup(W, e); /* invokeOnCrush ent.cpp:464-469 is host-side */
 	u32 slot = bt_add32(&W.ctr[CT_DEAD_N], 1u);
 	if ((i32)slot < W.dead_cap) W.deadList[slot] = ((u64)key << 32) | (u32)e;
 }
@@ -1011,7 +1024,10 @@ static BT_HD void t_flush_serial(const DevWorld &W, i32 g, LocalStats &st) {
 			W.newDrop[i] = 0;
 			bt_fumble(W, i, st);
 		}
-		if (W.newHolder[i] >= 0) W.ctr[CT_ERROR] = (u32)(-BT_ERR_UNSUPPORTED);
+		if (W.newHolder[i] >= 0) {
+			if (W.lenient) { bt_unsup(W, i); W.newHolder[i] = -1; }
+			else W.ctr[CT_ERROR] = (u32)(-BT_ERR_UNSUPPORTED);
+		}
 	}
 }
 

@@ -90,6 +90,7 @@ enum {
 	CT_CACHE_INVALID = 15, /* an entity left the inflated box its cached pairs were found with */
 	CT_STAT0 = 16,       /* 64-bit stats start here (as pairs of u32 slots, 8-byte aligned) */
 	CT_FLUSH_HINT = 32,  /* something happened that flush1 has to act on (slider/mask request, a death) */
+	CT_UNSUPPORTED = 33, /* times a handler without a device implementation would have run (lenient uploads only) */
 	CT_WORDS = 64
 };
 enum { SK_ITERS = 0, SK_CAND, SK_POS, SK_PUSH, SK_SERIAL, SK_CRUSH, SK_FUMBLE, SK_NUM };
@@ -102,11 +103,13 @@ struct DevWorld {
 	i32 world_bits;
 	i32 serial_cap, dead_cap;
 	i32 iter_id; /* running doIteration counter, for event ordering keys */
+	i32 lenient;  /* uploads with unknown handler IDs were accepted: count would-be invocations instead */
 	i32 ray_mode;
 	i32 margin;   /* inflation of the boxes candidate pairs are cached with (collision tree only) */
 	i32 pair_cap; /* 1: tree over ALL live entities with static boxes (raycast), 0: collision tree */
 
 	i32 *wbegin, *wend, *flip, *gamerules, *rnd; /* per world */
+	u32 *wunsup;                                 /* per world: would-be invocations of unimplemented handlers */
 	u8 *wflush;                                  /* per world: serial flush1 work pending */
 
 	i32 *world, *uid;

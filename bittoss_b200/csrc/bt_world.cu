@@ -175,7 +175,7 @@ int bt_world_create(bt_world **out, int device, int32_t max_ents, int32_t max_sl
 	DevWorld &W = w->W;
 	size_t n = (size_t)max_ents, nw = (size_t)max_worlds;
 	TRY(dalloc(w, &W.wbegin, nw)); TRY(dalloc(w, &W.wend, nw)); TRY(dalloc(w, &W.flip, nw));
-	TRY(dalloc(w, &W.gamerules, nw)); TRY(dalloc(w, &W.rnd, nw)); TRY(dalloc(w, &W.wflush, nw));
+	TRY(dalloc(w, &W.gamerules, nw)); TRY(dalloc(w, &W.rnd, nw)); TRY(dalloc(w, &W.wflush, nw)); TRY(dalloc(w, &W.wunsup, nw));
 	TRY(dalloc(w, &W.world, n)); TRY(dalloc(w, &W.uid, n));
 	TRY(dalloc(w, &W.center, n)); TRY(dalloc(w, &W.old, n)); TRY(dalloc(w, &W.vel, n));
 	TRY(dalloc(w, &W.radius, n)); TRY(dalloc(w, &W.d_center, n)); TRY(dalloc(w, &W.d_vel, n));
@@ -225,6 +225,7 @@ int bt_world_set_option(bt_world *w, const char *name, int64_t value) {
 	if (!w || !name) return BT_ERR_ARG;
 	if (!strcmp(name, "rebuild_every")) { w->rebuild_every = value < 1 ? 1 : value; return BT_OK; }
 	if (!strcmp(name, "max_iterations")) { w->max_iterations = value; return BT_OK; }
+	if (!strcmp(name, "allow_unsupported")) { w->W.lenient = value != 0; return BT_OK; }
 	if (!strcmp(name, "pair_cache")) { w->pair_cache = value != 0; return BT_OK; }
 	if (!strcmp(name, "cache_margin")) { w->W.margin = value < 0 ? 0 : (i32)value; return BT_OK; }
 	return BT_ERR_ARG;
@@ -260,7 +261,7 @@ int bt_world_upload(bt_world *w, const bt_world_desc *d) {
 		else
 			for (int k = BT_H_ONFUMBLE; k <= BT_H_ONPICKEDUP; k++)
 				if (!supported(BT_SUPPORTED_PAIR, h[k])) bad = "entPair";
-		if (bad) {
+		if (bad && !w->W.lenient) {
 			snprintf(g_err, sizeof g_err, "entity %d: %s handler id has no device-side implementation", i, bad);
 			return BT_ERR_UNSUPPORTED;
 		}
@@ -676,13 +677,28 @@ int bt_world_stats(bt_world *w, bt_tick_stats *out, int reset) {
 	w->stats.candidate_pairs = (i64)s[SK_CAND]; w->stats.positives = (i64)s[SK_POS];
 	w->stats.pushes = (i64)s[SK_PUSH]; w->stats.serial_pushes = (i64)s[SK_SERIAL];
 	w->stats.crushes = (i64)s[SK_CRUSH]; w->stats.fumbles = (i64)s[SK_FUMBLE];
+	{
+		u32 un = 0;
+		CK(cudaMemcpy(&un, &w->W.ctr[CT_UNSUPPORTED], sizeof(u32), cudaMemcpyDeviceToHost));
+		w->stats.unsupported_events = (i64)un;
+	}
 	*out = w->stats;
 	if (reset) {
 		i64 live = w->stats.live_ents;
 		memset(&w->stats, 0, sizeof(w->stats));
 		w->stats.live_ents = live;
 		CK(cudaMemsetAsync(&w->W.ctr[CT_STAT0], 0, sizeof(s), w->stream));
+		CK(cudaMemsetAsync(&w->W.ctr[CT_UNSUPPORTED], 0, sizeof(u32), w->stream));
+		CK(cudaMemsetAsync(w->W.wunsup, 0, sizeof(u32) * (size_t)w->cap_worlds, w->stream));
 	}
+	return BT_OK;
+}
+
+int bt_world_unsupported(bt_world *w, uint32_t *per_world) {
+	if (!w || !per_world) return BT_ERR_ARG;
+	CK(cudaSetDevice(w->device));
+	CK(cudaStreamSynchronize(w->stream));
+	CK(cudaMemcpy(per_world, w->W.wunsup, sizeof(u32) * (size_t)w->W.n_worlds, cudaMemcpyDeviceToHost));
 	return BT_OK;
 }
 

@@ -120,6 +120,8 @@ typedef struct bt_tick_stats {
 	int64_t pair_builds;     /* k_pairs launches (>= 1 per tick; more when the cache is invalidated) */
 	int64_t pairs_cached;    /* unordered candidate pairs written by those launches      */
 	int64_t pair_overflows;  /* ticks that fell back to per-iteration traversal          */
+	int64_t unsupported_events; /* lenient uploads only ("allow_unsupported"): times a handler with no device
+	                           * implementation would have been invoked; != 0 means the state diverged */
 } bt_tick_stats;
 
 /* Per-kernel-class device timing, filled only while profiling is enabled. */
@@ -184,9 +186,14 @@ void *bt_world_stream(bt_world *w); /* the cudaStream_t every kernel of w runs o
  * out: [n_worlds]. */
 int bt_world_hash(bt_world *w, uint64_t *out);
 int bt_world_stats(bt_world *w, bt_tick_stats *out, int reset);
+/* per world [n_worlds]: unsupported_events since the last bt_world_stats(reset) */
+int bt_world_unsupported(bt_world *w, uint32_t *per_world);
 int bt_world_profile_enable(bt_world *w, int on);
 int bt_world_profile_read(bt_world *w, bt_profile *out, int reset);
-/* Tuning knobs (integers): "rebuild_every" ticks between full LBVH rebuilds. */
+/* Knobs (integers): "rebuild_every" ticks between full LBVH rebuilds; "pair_cache" 0/1;
+ * "cache_margin"; "allow_unsupported" 1 = bt_world_upload accepts handler IDs without a device
+ * implementation, treats them as NIL and counts every would-be invocation in
+ * bt_tick_stats.unsupported_events (used to measure handler coverage on real levels). */
 int bt_world_set_option(bt_world *w, const char *name, int64_t value);
 
 /* ---- raycast: replaces selectCast(gs, parent, look) (raycast.h:1, raycast.cpp:16-57),

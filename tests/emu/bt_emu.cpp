@@ -72,7 +72,7 @@ Emu *bte_create(const bt_world_desc *d, int rebuild_every, int shuffle_seed) {
 	DevWorld &W = E->W;
 	const int n = d->n_ents, nw = d->n_worlds;
 	W.n = n; W.n_worlds = nw;
-	A(E, &W.wbegin, nw); A(E, &W.wend, nw); A(E, &W.flip, nw); A(E, &W.gamerules, nw); A(E, &W.rnd, nw); A(E, &W.wflush, nw);
+	A(E, &W.wbegin, nw); A(E, &W.wend, nw); A(E, &W.flip, nw); A(E, &W.gamerules, nw); A(E, &W.rnd, nw); A(E, &W.wflush, nw); A(E, &W.wunsup, nw);
 	A(E, &W.world, n); A(E, &W.uid, n); A(E, &W.center, n); A(E, &W.old, n); A(E, &W.vel, n); A(E, &W.radius, n);
 	A(E, &W.d_center, n); A(E, &W.d_vel, n); A(E, &W.type, n); A(E, &W.collide, n); A(E, &W.ntype, n); A(E, &W.ncollide, n);
 	A(E, &W.friction, n); A(E, &W.holder, n); A(E, &W.holdFlags, n); A(E, &W.holdRoot, n); A(E, &W.holdee, n);
@@ -295,9 +295,11 @@ void bte_hash(Emu *E, uint64_t *out) {
 
 void bte_set_option(Emu *E, const char *name, int64_t v) {
 	if (!strcmp(name, "pair_cache")) E->pair_cache = v != 0;
+	if (!strcmp(name, "allow_unsupported")) E->W.lenient = v != 0;
 	if (!strcmp(name, "cache_margin")) E->W.margin = (i32)v;
 }
 int64_t bte_pair_rebuilds(Emu *E) { return E->pair_rebuilds; }
+int64_t bte_unsupported(Emu *E) { return (int64_t)E->W.ctr[CT_UNSUPPORTED]; }
 
 void bte_stats(Emu *E, int64_t *out) {
 	out[0] = E->ticks; out[1] = E->iterations; out[2] = E->st.cand; out[3] = E->st.pos; out[4] = E->st.push;

@@ -27,7 +27,7 @@ def build_emu(force=False):
 
 
 class EmuWorld:
-    def __init__(self, wa: WorldArrays, rebuild_every=4, shuffle_seed=0):
+    def __init__(self, wa: WorldArrays, rebuild_every=4, shuffle_seed=0, lenient=False):
         build_emu()
         L = C.CDLL(EMU_SO)
         L.bte_create.restype = C.c_void_p
@@ -40,11 +40,15 @@ class EmuWorld:
         L.bte_set_option.argtypes = [C.c_void_p, C.c_char_p, C.c_int64]
         L.bte_pair_rebuilds.argtypes = [C.c_void_p]
         L.bte_pair_rebuilds.restype = C.c_int64
+        L.bte_unsupported.argtypes = [C.c_void_p]
+        L.bte_unsupported.restype = C.c_int64
         L.bte_raycast.argtypes = [C.c_void_p, _i32p, _i32p, C.c_int32, _i32p]
         self.L = L
         self.n_worlds = int(wa.desc.n_worlds)
         self.n = wa.n
         self.h = L.bte_create(wa.ref(), rebuild_every, shuffle_seed)
+        if lenient:
+            self.set_option("allow_unsupported", 1)
 
     def __del__(self):
         if getattr(self, "h", None):
@@ -58,6 +62,9 @@ class EmuWorld:
 
     def set_option(self, name, value):
         self.L.bte_set_option(self.h, name.encode(), int(value))
+
+    def unsupported(self):
+        return int(self.L.bte_unsupported(self.h))
 
     def pair_rebuilds(self):
         return int(self.L.bte_pair_rebuilds(self.h))

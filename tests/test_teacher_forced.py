@@ -1,0 +1,126 @@
+"""BASELINE.json configs[0], [1], [3] with the FULL game running: players with seeded random
+inputs, every tick handler, spawners, world rules — all on the host, in the unmodified
+reference (oracle/_ref).  Each tick the reference's state right before doPhysics is exported,
+the device path runs doPhysics + finishStep on it, and the result must hash-equal what the
+reference's own doPhysics produced ("teacher forcing": errors cannot hide behind drift, and
+nothing needs the reference's pointer structures rebuilt from device state).
+
+Handlers without a device implementation are accepted by a lenient upload and
+every would-be invocation is counted; a tick in which one fired is reported as skipped, not
+as passed.  The assertion is: zero mismatches, and a bounded skip rate."""
+import numpy as np
+import pytest
+
+CASES = {
+    # name: (level, players' data, spacetrash spawner on, ticks, max skipped fraction)
+    "lobby_4players": ("lobby", (0, 0, 0, 0), 0, 1000, 0.05),
+    "spacetrash_spawner": ("spacetrash", (), 1, 4000, 0.0),
+    "arena_2players": ("arena", (1, 2), 0, 1000, 0.02),
+}
+PHYSICS_FINISH = 8 | 16
+
+
+def _run(ref, make_world, name, ticks=None):
+    level, players, st_on, n_ticks, max_skip = CASES[name]
+    n_ticks = ticks or n_ticks
+    R = ref
+    wid = R.new_world()
+    R.load_sav(level + ".sav", players=players)
+    R.set_options(st_on, 0)
+    ok = skipped = 0
+    stepper = None
+    for t in range(n_ticks):
+        R.pre_physics(0)           # main.cpp:1030-1090: rules, inputs, doUpdates, mkHeroes, prepPhysics, doGravity
+        wa = R.export()
+        R.do_physics()             # doPhysics, cleanupDeadHeroes, finishStep
+        want = R.hash()
+        stepper, got, unsupported = make_world(stepper, wa)
+        if unsupported:
+            skipped += 1
+            continue
+        assert got == want, "%s: device physics != reference at tick %d" % (name, t)
+        ok += 1
+    final_ents = R.count()[0]
+    R.free_world(wid)
+    assert skipped <= max_skip * n_ticks, "%d of %d ticks needed an unimplemented handler" % (skipped, n_ticks)
+    return ok, skipped, final_ents
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_kernel_bodies_teacher_forced(ref_lib, emu, name):
+    def step(_, wa):
+        ew = emu.EmuWorld(wa, 1, 0, lenient=True)
+        ew.step(PHYSICS_FINISH)
+        return None, ew.hash()[0], ew.unsupported()
+    ok, skipped, ents = _run(ref_lib, step, name, ticks=300 if name != "spacetrash_spawner" else 800)
+    assert ok > 250
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", list(CASES))
+def test_cuda_teacher_forced(ref_lib, bt, name):
+    def step(w, wa):
+        if w is None:
+            w = bt.World(None, max_ents=8192, max_sliders=16384, max_wires=8192, max_worlds=1)
+            w.set_option("allow_unsupported", 1)
+        w.stats(reset=True)
+        w.upload(wa)
+        w.step(PHYSICS_FINISH)
+        return w, w.hash()[0], w.stats()["unsupported_events"]
+    ok, skipped, ents = _run(ref_lib, step, name)
+    print("%s: %d ticks bit-exact, %d skipped, %d entities at the end" % (name, ok, skipped, ents))
+    assert ok >= 0.9 * CASES[name][3]
+
+
+@pytest.mark.gpu
+def test_cuda_batched_arena_worlds_teacher_forced(ref_lib, bt):
+    """configs[3] shape: many independent arena.sav worlds (own RNG seed and input stream each)
+    in ONE device world, all their physics in the same kernels."""
+    import ctypes as C
+    from bittoss_b200.desc import WorldArrays
+    R = ref_lib
+    n_worlds, ticks = 192, 120
+    ids = []
+    for g in range(n_worlds):
+        ids.append(R.new_world())
+        R.load_sav("arena.sav", players=(1, 2), rand_seed=12345 + g)
+        R.set_options(0, 0x9e3779b9 * (g + 1) & 0xffffffff)
+    w = bt.World(None, max_ents=n_worlds * 256, max_sliders=n_worlds * 1024, max_wires=n_worlds * 256,
+                 max_worlds=n_worlds)
+    w.set_option("allow_unsupported", 1)
+    ok = skipped = 0
+    for t in range(ticks):
+        counts = []
+        for g in ids:
+            R.select(g)
+            R.pre_physics(0)
+            counts.append(R.count())
+        batch = WorldArrays(sum(c[0] for c in counts), sum(c[1] for c in counts), sum(c[2] for c in counts), n_worlds)
+        eb = sb = wb = 0
+        for k, g in enumerate(ids):
+            R.select(g)
+            n = R.L.btref_export_at(batch.ref(), eb, sb, wb, k)
+            assert n == counts[k][0]
+            eb, sb, wb = eb + counts[k][0], sb + counts[k][1], wb + counts[k][2]
+        batch.desc.n_ents, batch.desc.n_sliders, batch.desc.n_wires, batch.desc.n_worlds = eb, sb, wb, n_worlds
+        want = []
+        for g in ids:
+            R.select(g)
+            R.do_physics()
+            want.append(R.hash())
+        w.stats(reset=True)
+        w.upload(batch)
+        w.step(PHYSICS_FINISH)
+        fired = w.unsupported_per_world() != 0
+        got = w.hash()
+        for k in range(n_worlds):
+            if fired[k]:
+                skipped += 1
+                continue
+            assert got[k] == want[k], "world %d tick %d" % (k, t)
+            ok += 1
+    for g in ids:
+        R.free_world(g)
+    w.close()
+    print("batched arena: %d world-ticks bit-exact, %d skipped" % (ok, skipped))
+    assert ok >= 0.97 * ticks * n_worlds
