@@ -61,7 +61,8 @@ struct LocalStats {
 static BT_HD int bt_needs_box(u32 type, u32 collide) { return collide || (type & T_COLLIDABLE); }
 
 /* a handler with no device implementation would have run for entity e (lenient uploads only) */
-static BT_HD void bt_unsup(const DevWorld &W, i32 e) {
+static BT_HD void bt_unsup(const DevWorld &W, i32 e, int kind, int id) {
+	W.ctr[CT_UNSUP_LAST] = (u32)(kind << 8 | id);
 	bt_add32(&W.ctr[CT_UNSUPPORTED], 1u);
 	bt_add32(&W.wunsup[W.world[e]], 1u);
 }
@@ -139,19 +140,51 @@ static BT_HD int bt_who_moves(int id, u32 ta, u32 tb, int axis, int dir) {
 
 /* which handler IDs have a device implementation (bt_world_upload checks these) */
 #define BT_SUPPORTED_WHOMOVES 0x1ffu /* 0..8 */
-#define BT_SUPPORTED_PUSH 0x005u     /* NIL, LOGIC */
+#define BT_SUPPORTED_PUSH 0x007u     /* NIL, PLAYER, LOGIC */
 #define BT_SUPPORTED_PUSHED 0x02fu   /* NIL, PUDDLEJUMP, FRAGILE, FLAG, PLAYER */
-#define BT_SUPPORTED_PAIR 0x009u     /* NIL, FUMBLED_DECOR */
+#define BT_SUPPORTED_PAIR 0x029u     /* NIL, FUMBLED_DECOR, PICKUP_PLAYER */
 #define BT_SUPPORTED_CRUSH 0x001u    /* NIL (others are host-side events) */
 
-/* push_t: 0 onPushDefault handlerRegistrar.cpp:16; 2 logic_push logic.c:44-49.
+/* player_push player.c:108-165 (sliders s_equip_processed=10, s_editmode=11).  Returns 1 =
+ * "I pick him up".  Only ever runs in the serial lane (see t_push): it reads and edits the
+ * player's own holdee list and flags. */
+static BT_HD int bt_player_push(const DevWorld &W, i32 me, i32 him) {
+	u32 th = W.type[him];
+	if (!(th & EQUIP_MASK)) return 0;
+	if ((W.btn_v[me] >> 8) & 0xff) return 0; /* getButton(me, 1): shift inhibits pickups */
+	if (bt_getslider(W, me, 10) & 1) return 0;
+	if (bt_getslider(W, me, 11)) return 0;
+	if (W.holder[him] >= 0 || W.holder[me] >= 0) return 0;
+	u32 tEquip = th & T_EQUIP, tEquipSm = th & T_EQUIP_SM;
+	i32 existing = -1;
+	for (i32 h = W.holdee[me]; h >= 0; h = W.LLn[h]) {
+		u32 heldEquip = W.type[h] & T_EQUIP, heldEquipSm = W.type[h] & T_EQUIP_SM;
+		if (heldEquip) {
+			if (heldEquipSm || tEquip || existing >= 0) return 0;
+			existing = h;
+		} else if (heldEquipSm) {
+			if (existing >= 0) return 0;
+			if (tEquip && tEquipSm) return 0;
+			existing = h;
+		}
+	}
+	if (!(tEquip && tEquipSm)) {
+		int hand = existing >= 0 && !bt_getslider(W, existing, 0);
+		bt_uslider(W, him, 0, hand);
+	}
+	W.sv[W.slider_off[me] + 10] |= 1; /* direct write, player.c:157 */
+	return 1;
+}
+
+/* push_t: 0 onPushDefault handlerRegistrar.cpp:16; 1 player_push; 2 logic_push logic.c:44-49.
  * Writing v2=1 is idempotent, so concurrent pushers of one logic block do not race. */
 static BT_HD int bt_push_handler(const DevWorld &W, i32 me, i32 him) {
 	int id = (W.hphys[me] >> 8) & 0xff;
+	if (id == 1) return bt_player_push(W, me, him);
 	if (id == 2) {
 		if (W.type[him] & (T_TERRAIN | T_OBSTACLE | T_DEBRIS)) bt_or32(&W.btn_v2[me], 1u); /* pushBtn(me,0) */
 	} else if (id != 0) {
-		bt_unsup(W, me); /* only reachable after a lenient upload */
+		bt_unsup(W, me, 0, id); /* only reachable after a lenient upload */
 	}
 	return 0;
 }
@@ -181,14 +214,30 @@ static BT_HD int bt_pushed_handler(const DevWorld &W, i32 me, i32 him, int axis,
 		return 0;
 	}
 	default:
-		bt_unsup(W, me);
+		bt_unsup(W, me, 1, id);
 		return 0;
 	}
 }
 
 /* entPair_t: 3 decor_fumbled common.c:61-67.  slot: 0 onFumble 1 onFumbled 2 onPickUp 3 onPickedUp */
-static BT_HD void bt_pair_handler(const DevWorld &W, int slot, i32 me) {
+static BT_HD void bt_pair_handler(const DevWorld &W, int slot, i32 me, i32 him) {
 	int id = (W.hpair[me] >> (8 * slot)) & 0xff;
+	if (id == 5) { /* player_pickup player.c:167-178 -> updateTrajectory entUpdaters.c:102-114 */
+		if (W.type[him] & EQUIP_MASK) {
+			int4 mo = W.old[me], mc = W.center[me], mv = W.vel[me];
+			int4 ho = W.old[him], hc = W.center[him], hv = W.vel[him];
+			BT_FOR_SUBTREE(W, him, it, {
+				int4 o = W.old[it], c = W.center[it], v = W.vel[it];
+				o.x += mo.x - ho.x; o.y += mo.y - ho.y; o.z += mo.z - ho.z;
+				c.x += mc.x - hc.x; c.y += mc.y - hc.y; c.z += mc.z - hc.z;
+				v.x += mv.x - hv.x; v.y += mv.y - hv.y; v.z += mv.z - hv.z;
+				W.old[it] = o; W.center[it] = c; W.vel[it] = v;
+			});
+			W.ctr[CT_CACHE_INVALID] = 1; /* it jumped: the cached pairs no longer cover it */
+			W.holdFlags[him] |= HOLD_DROP;
+		}
+		return;
+	}
 	if (id == 3) {
 		W.fullFlush[me] = 1;
 		W.ctr[CT_FLUSH_HINT] = 1;
@@ -196,7 +245,7 @@ static BT_HD void bt_pair_handler(const DevWorld &W, int slot, i32 me) {
 		W.ncollide[me] = W.collide[me] | T_TERRAIN | T_OBSTACLE | T_DEBRIS;
 		if (slot == 1) W.hpair[me] &= ~(0xffu << 8);
 	} else if (id != 0) {
-		bt_unsup(W, me);
+		bt_unsup(W, me, 2, id);
 	}
 }
 
@@ -209,8 +258,8 @@ static BT_HD void bt_fumble(const DevWorld &W, i32 h, LocalStats &st) {
 	if (a < 0) return;
 	st.fumble++;
 	W.needsCollision[h] = 1;
-	bt_pair_handler(W, 0, a);
-	bt_pair_handler(W, 1, h);
+	bt_pair_handler(W, 0, a, h);
+	bt_pair_handler(W, 1, h, a);
 	for (int i = 0; i < 3; i++) {
 		i32 x = h, y;
 		while ((y = W.holder[x]) >= 0 && bt_forced_get(W.forced[y], i) && bt_get3(W.forcedHoldees[y], i) == x) {
@@ -239,7 +288,7 @@ static BT_HD void bt_crush(const DevWorld &W, i32 e, u32 key, LocalStats &st) {
 	W.hasBox[e] = 0;
 	W.dead[e] = 1;
 	W.ctr[CT_FLUSH_HINT] = 1; /* wires that point at it must go (flushMisc ent.cpp:706-712) */
-	if ((W.hphys[e] >> 24) & 0xff) bt_unsup(W, e); /* invokeOnCrush ent.cpp:464-469 is host-side */
+	if ((W.hphys[e] >> 24) & 0xff) bt_unsup(W, e, 3, (int)((W.hphys[e] >> 24) & 0xff)); /* invokeOnCrush ent.cpp:464-469 is host-side */
 	u32 slot = bt_add32(&W.ctr[CT_DEAD_N], 1u);
 	if ((i32)slot < W.dead_cap) W.deadList[slot] = ((u64)key << 32) | (u32)e;
 }
@@ -897,8 +946,35 @@ static BT_HD void bt_push_regular(const DevWorld &W, i32 e, i32 o, int axis, int
 	}
 }
 
-/* push ent.cpp:579-629.  None of the device push handlers asks for a pickup, so the
- * doPushPickup branches (ent.cpp:598-609, 621-622) reduce to the regular ones. */
+/* pickupNoHandlers ent.cpp:166-182 + pickup :184-188 (the root list has no counterpart here) */
+static BT_HD void bt_pickup(const DevWorld &W, i32 x, i32 y, i32 holdFlags) {
+	i32 first = W.holdee[x];
+	W.LLn[y] = first;
+	W.LLp[y] = -1;
+	if (first >= 0) W.LLp[first] = y;
+	W.holdee[x] = y;
+	W.holder[y] = x;
+	i32 r = W.holdRoot[x];
+	BT_FOR_SUBTREE(W, y, it, W.holdRoot[it] = r);
+	W.holdFlags[y] = HOLD_MASK & holdFlags;
+	if (holdFlags & HOLD_FREEZE) {
+		int4 vx = W.vel[x], vy = W.vel[y];
+		W.d_vel[y] = make_int4(vx.x - vy.x, vx.y - vy.y, vx.z - vy.z, 0);
+	}
+	bt_pair_handler(W, 2, x, y);
+	bt_pair_handler(W, 3, y, x);
+}
+
+/* doPushPickup ent.cpp:542-549 */
+static BT_HD void bt_push_pickup(const DevWorld &W, i32 e, i32 holder, u32 key, LocalStats &st) {
+	if (W.holder[e] >= 0 || W.holdRoot[holder] == e) {
+		bt_crush(W, e, key, st);
+		return;
+	}
+	bt_pickup(W, holder, e, 0);
+}
+
+/* push ent.cpp:579-629 */
 static BT_HD void bt_push(const DevWorld &W, const Coll &c, u32 key, LocalStats &st) {
 	st.push++;
 	i32 e = c.leaf, o = c.buddy;
@@ -908,18 +984,31 @@ static BT_HD void bt_push(const DevWorld &W, const Coll &c, u32 key, LocalStats 
 	i32 accel = (bt_get3(W.vel[o], axis) - bt_get3(W.vel[e], axis)) * dir;
 	if (accel < 0) accel = 0;
 	if (c.mutual) {
-		bt_push_handler(W, o, e);
-		bt_push_handler(W, e, o);
-		i32 dv1[3], dv2[3];
-		bt_push_dv(W, dv1, e, o, axis, dir, accel);
-		bt_push_dv(W, dv2, o, e, axis, -dir, accel);
-		bt_push_regular(W, e, o, axis, dir, displacement, dv1, key, st);
-		bt_push_regular(W, o, e, axis, -dir, displacement, dv2, key, st);
+		int p1 = bt_push_handler(W, o, e);
+		int p2 = bt_push_handler(W, e, o);
+		if (p1 != p2) {
+			if (p1) { i32 t_ = e; e = o; o = t_; } /* the branchless swap of ent.cpp:601-603 */
+			dir *= (p2 - p1);
+			i32 dv[3];
+			bt_push_dv(W, dv, e, o, axis, dir, accel);
+			bt_push_regular(W, e, o, axis, dir, displacement, dv, key, st);
+			bt_push_pickup(W, o, e, key, st);
+		} else {
+			i32 dv1[3], dv2[3];
+			bt_push_dv(W, dv1, e, o, axis, dir, accel);
+			bt_push_dv(W, dv2, o, e, axis, -dir, accel);
+			bt_push_regular(W, e, o, axis, dir, displacement, dv1, key, st);
+			bt_push_regular(W, o, e, axis, -dir, displacement, dv2, key, st);
+		}
 	} else {
-		bt_push_handler(W, o, e);
-		i32 dv[3];
-		bt_push_dv(W, dv, e, o, axis, dir, accel);
-		bt_push_regular(W, e, o, axis, dir, displacement, dv, key, st);
+		int p1 = bt_push_handler(W, o, e);
+		if (p1) {
+			bt_push_pickup(W, e, o, key, st);
+		} else {
+			i32 dv[3];
+			bt_push_dv(W, dv, e, o, axis, dir, accel);
+			bt_push_regular(W, e, o, axis, dir, displacement, dv, key, st);
+		}
 	}
 }
 
@@ -937,6 +1026,16 @@ static BT_HD void t_push(const DevWorld &W, i32 e, LocalStats &st) {
 	if (e >= W.n) return;
 	u8 rd = W.ready[e];
 	if (!rd) return;
+	Coll pc = bt_unpack_coll(W.pend[e]);
+	/* push handlers that edit somebody else's tree (player_push: pickup into the player's
+	 * holdee list, first come first served) run in the serial lane, canonical order */
+	int serial_handler = ((W.hphys[pc.buddy] >> 8) & 0xff) == 1 || (pc.mutual && ((W.hphys[pc.leaf] >> 8) & 0xff) == 1);
+	if (serial_handler) {
+		u32 slot = bt_add32(&W.ctr[CT_SERIAL_N], 1u);
+		if ((i32)slot < W.serial_cap) W.serialList[slot] = e;
+		else W.ctr[CT_ERROR] = (u32)(-BT_ERR_OVERFLOW);
+		return;
+	}
 	if (rd == 2) {
 		i32 r = W.holdRoot[bt_unpack_coll(W.pend[e]).buddy];
 		int conflict = 0, guard = 0;
@@ -1025,7 +1124,7 @@ static BT_HD void t_flush_serial(const DevWorld &W, i32 g, LocalStats &st) {
 			bt_fumble(W, i, st);
 		}
 		if (W.newHolder[i] >= 0) {
-			if (W.lenient) { bt_unsup(W, i); W.newHolder[i] = -1; }
+			if (W.lenient) { bt_unsup(W, i, 4, 0); W.newHolder[i] = -1; }
 			else W.ctr[CT_ERROR] = (u32)(-BT_ERR_UNSUPPORTED);
 		}
 	}

@@ -58,6 +58,9 @@ typedef uint8_t u8;
 #define TEAM_BIT 256u
 #define TEAM_MASK (7u * TEAM_BIT)
 #define T_COLLIDABLE (T_HEAVY + T_TERRAIN + T_OBSTACLE + T_DEBRIS + T_FLAG)
+#define T_EQUIP (1u << 12)
+#define T_EQUIP_SM (1u << 13)
+#define EQUIP_MASK (T_EQUIP + T_EQUIP_SM)
 #define EFFECT_GRAV (1 << 3)
 
 /* 64-byte LBVH node: boxes of both children, so one node fetch decides two subtrees.
@@ -91,6 +94,7 @@ enum {
 	CT_STAT0 = 16,       /* 64-bit stats start here (as pairs of u32 slots, 8-byte aligned) */
 	CT_FLUSH_HINT = 32,  /* something happened that flush1 has to act on (slider/mask request, a death) */
 	CT_UNSUPPORTED = 33, /* times a handler without a device implementation would have run (lenient uploads only) */
+	CT_UNSUP_LAST = 34,  /* kind<<8 | catalog id of the last such handler (0 push, 1 pushed, 2 entPair, 3 crush, 4 pickup flush) */
 	CT_WORDS = 64
 };
 enum { SK_ITERS = 0, SK_CAND, SK_POS, SK_PUSH, SK_SERIAL, SK_CRUSH, SK_FUMBLE, SK_NUM };

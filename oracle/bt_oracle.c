@@ -58,6 +58,9 @@
 #define TEAM_BIT 256
 #define TEAM_MASK (7 * TEAM_BIT)
 #define T_COLLIDABLE (T_HEAVY + T_TERRAIN + T_OBSTACLE + T_DEBRIS + T_FLAG)
+#define T_EQUIP (1 << 12)
+#define T_EQUIP_SM (1 << 13)
+#define EQUIP_MASK (T_EQUIP + T_EQUIP_SM)
 #define EFFECT_GRAV (1 << 3)
 
 typedef int32_t i32;
@@ -198,10 +201,38 @@ static int whoMovesH(const World *w, i32 a, i32 b, int axis, int dir) {
 	}
 }
 
-/* push_t handlers: 0 onPushDefault handlerRegistrar.cpp:16; 2 logic_push modules/logic.c:44-49 */
+/* player_push modules/player.c:108-165 (sliders s_equip_processed=10, s_editmode=11) */
+static int player_push(World *w, i32 me, i32 him) {
+	uint32_t th = w->type[him];
+	if (!((th & EQUIP_MASK) && !w->btn[me][1] && !(1 & getSlider(w, me, 10)) && !getSlider(w, me, 11) &&
+	      w->holder[him] < 0 && w->holder[me] < 0))
+		return 0;
+	uint32_t tEquip = th & T_EQUIP, tEquipSm = th & T_EQUIP_SM;
+	i32 existing = -1;
+	for (i32 h = w->holdee[me]; h >= 0; h = w->LLn[h]) {
+		uint32_t heldEquip = w->type[h] & T_EQUIP, heldEquipSm = w->type[h] & T_EQUIP_SM;
+		if (heldEquip) {
+			if (heldEquipSm || tEquip || existing >= 0) return 0;
+			existing = h;
+		} else if (heldEquipSm) {
+			if (existing >= 0) return 0;
+			if (tEquip && tEquipSm) return 0;
+			existing = h;
+		}
+	}
+	if (!(tEquip && tEquipSm)) {
+		int hand = existing >= 0 && !getSlider(w, existing, 0);
+		uSlider(w, him, 0, hand);
+	}
+	w->sv[w->slider_off[me] + 10] |= 1; /* direct write, player.c:157 */
+	return 1;
+}
+
+/* push_t handlers: 0 onPushDefault handlerRegistrar.cpp:16; 1 player_push; 2 logic_push modules/logic.c:44-49 */
 static int pushH(World *w, i32 me, i32 him, int axis, int dir, i32 displacement, i32 dv) {
 	(void)axis; (void)dir; (void)displacement; (void)dv;
 	switch (w->h[me][BT_H_PUSH]) {
+	case 1: return player_push(w, me, him);
 	case 2:
 		if (w->type[him] & (T_TERRAIN | T_OBSTACLE | T_DEBRIS)) w->btn[me][4 + 0] = 1; /* pushBtn(me,0) */
 		return 0;
@@ -240,9 +271,32 @@ static int pushedH(World *w, i32 me, i32 him, int axis, int dir, i32 dx, i32 dv)
 	}
 }
 
-/* entPair_t handlers: 3 decor_fumbled common.c:61-67 */
+/* updateTrajectory entUpdaters.c:102-114 */
+static void updateTrajectory(World *w, i32 who, const i32 *o, const i32 *c, const i32 *v) {
+	w->needsPhysUpdate[who] = 1;
+	for (int i = 0; i < 3; i++) {
+		w->old[who][i] += o[i];
+		w->center[who][i] += c[i];
+		w->vel[who][i] += v[i];
+	}
+	for (i32 e = w->holdee[who]; e >= 0; e = w->LLn[e]) updateTrajectory(w, e, o, c, v);
+}
+
+/* entPair_t handlers: 3 decor_fumbled common.c:61-67; 5 player_pickup player.c:167-178 */
 static void entPairH(World *w, int slot, i32 me, i32 him) {
-	(void)him;
+	if (w->h[me][slot] == 5) {
+		if (w->type[him] & EQUIP_MASK) {
+			i32 o[3], c[3], v[3];
+			for (int i = 0; i < 3; i++) {
+				o[i] = w->old[me][i] - w->old[him][i];
+				c[i] = w->center[me][i] - w->center[him][i];
+				v[i] = w->vel[me][i] - w->vel[him][i];
+			}
+			updateTrajectory(w, him, o, c, v);
+			w->holdFlags[him] |= HOLD_DROP;
+		}
+		return;
+	}
 	if (w->h[me][slot] == 3) {
 		w->fullFlush[me] = 1;
 		w->ntype[me] = w->type[me] | T_DEBRIS; /* uMyTypeMask */

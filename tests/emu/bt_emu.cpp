@@ -300,6 +300,7 @@ void bte_set_option(Emu *E, const char *name, int64_t v) {
 }
 int64_t bte_pair_rebuilds(Emu *E) { return E->pair_rebuilds; }
 int64_t bte_unsupported(Emu *E) { return (int64_t)E->W.ctr[CT_UNSUPPORTED]; }
+int64_t bte_unsupported_last(Emu *E) { return (int64_t)E->W.ctr[CT_UNSUP_LAST]; }
 
 void bte_stats(Emu *E, int64_t *out) {
 	out[0] = E->ticks; out[1] = E->iterations; out[2] = E->st.cand; out[3] = E->st.pos; out[4] = E->st.push;

@@ -13,9 +13,9 @@ import pytest
 
 CASES = {
     # name: (level, players' data, spacetrash spawner on, ticks, max skipped fraction)
-    "lobby_4players": ("lobby", (0, 0, 0, 0), 0, 1000, 0.05),
+    "lobby_4players": ("lobby", (0, 0, 0, 0), 0, 1000, 0.005),   # PUSH_TEAMSELECT / PUSH_LOADBLOCK are host-side
     "spacetrash_spawner": ("spacetrash", (), 1, 4000, 0.0),
-    "arena_2players": ("arena", (1, 2), 0, 1000, 0.02),
+    "arena_2players": ("arena", (1, 2), 0, 1000, 0.0),
 }
 PHYSICS_FINISH = 8 | 16
 
@@ -69,7 +69,7 @@ def test_cuda_teacher_forced(ref_lib, bt, name):
         return w, w.hash()[0], w.stats()["unsupported_events"]
     ok, skipped, ents = _run(ref_lib, step, name)
     print("%s: %d ticks bit-exact, %d skipped, %d entities at the end" % (name, ok, skipped, ents))
-    assert ok >= 0.9 * CASES[name][3]
+    assert ok >= 0.99 * CASES[name][3]
 
 
 @pytest.mark.gpu
@@ -123,4 +123,4 @@ def test_cuda_batched_arena_worlds_teacher_forced(ref_lib, bt):
         R.free_world(g)
     w.close()
     print("batched arena: %d world-ticks bit-exact, %d skipped" % (ok, skipped))
-    assert ok >= 0.97 * ticks * n_worlds
+    assert skipped <= 0.005 * ticks * n_worlds and ok + skipped == ticks * n_worlds
