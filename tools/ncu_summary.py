@@ -1,0 +1,62 @@
+"""Summarise ncu outputs into profiles/: launch list CSV -> per-kernel totals/shares;
+`--set full` raw CSV -> per-launch table of the metrics that matter for an HBM-bound path.
+    python tools/ncu_summary.py launches <launches.csv>
+    python tools/ncu_summary.py full <report.ncu-rep>            (needs ncu on PATH)"""
+import collections
+import csv
+import json
+import subprocess
+import sys
+
+
+def launches(path):
+    rows = [r for r in csv.reader(open(path)) if len(r) > 10]
+    hdr = rows[0]
+    ki, vi = hdr.index("Kernel Name"), hdr.index("Metric Value")
+    agg = collections.OrderedDict()
+    for r in rows[1:]:
+        k = r[ki].split("(")[0]
+        a = agg.setdefault(k, [0, 0.0])
+        a[0] += 1
+        a[1] += float(r[vi].replace(",", ""))
+    tot = sum(a[1] for a in agg.values())
+    print("| kernel | launches | total us | avg us | share |\n|---|---|---|---|---|")
+    for k, a in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+        print("| %s | %d | %.1f | %.1f | %.1f%% |" % (k, a[0], a[1] / 1e3, a[1] / a[0] / 1e3, 100 * a[1] / tot))
+    print("\ntotal %.1f us over %d launches (cold-cache, serialised by ncu: compare shares, not absolutes)" %
+          (tot / 1e3, sum(a[0] for a in agg.values())))
+
+
+WANT = [("gpu__time_duration.sum", "us"), ("dram__bytes_read.sum", "dram rd"), ("dram__bytes_write.sum", "dram wr"),
+        ("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "dram %"),
+        ("lts__t_bytes.sum", "L2 bytes"), ("l1tex__t_sector_hit_rate.pct", "L1 hit %"),
+        ("lts__t_sector_hit_rate.pct", "L2 hit %"), ("sm__warps_active.avg.pct_of_peak_sustained_active", "occupancy %"),
+        ("smsp__thread_inst_executed_per_inst_executed.ratio", "active thr/inst"),
+        ("smsp__inst_executed.sum", "warp inst"), ("launch__registers_per_thread", "regs")]
+
+
+def full(rep):
+    out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(out.splitlines()))
+    hdr, units = rows[0], rows[1]
+    idx = [(hdr.index(m), lab) for m, lab in WANT if m in hdr]
+    ki = hdr.index("Kernel Name")
+    print("| kernel | " + " | ".join("%s" % lab for _, lab in idx) + " |")
+    print("|---|" + "---|" * len(idx))
+    per = collections.defaultdict(list)
+    for r in rows[2:]:
+        name = r[ki].split("(")[0]
+        print("| %s | " % name + " | ".join("%s %s" % (r[i][:12], units[i] if lab in ("dram rd", "dram wr", "L2 bytes") else "")
+                                            for i, lab in idx) + " |")
+        def val(m):
+            i = hdr.index(m)
+            v = float(r[i].replace(",", ""))
+            u = units[i].lower()
+            return v * {"byte": 1, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9}.get(u, 1)
+        per[name].append(val("dram__bytes_read.sum") + val("dram__bytes_write.sum"))
+    print()
+    print(json.dumps({k: {"launches": len(v), "dram_bytes_per_launch": sum(v) / len(v)} for k, v in per.items()}))
+
+
+if __name__ == "__main__":
+    {"launches": launches, "full": full}[sys.argv[1]](sys.argv[2])
