@@ -77,7 +77,7 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def cpu_baseline(n_cubes, warm_ticks, ticks):
+def cpu_baseline(n_cubes, warm_ticks, ticks, settle=0):
     """The UNMODIFIED reference's CPU tick (oracle/_ref) when it was compiled, else the C port."""
     from oracle import pybind
     cores = 1  # the reference tick is single-threaded and non-reentrant (ent.cpp:17, velbox/box.cpp:17-18)
@@ -86,7 +86,7 @@ def cpu_baseline(n_cubes, warm_ticks, ticks):
             R = pybind.RefLib()
             R.new_world()
             R.make_boxstack(n_cubes, 4, 777, 64, 60)
-            for _ in range(warm_ticks):
+            for _ in range(settle + warm_ticks):
                 R.step(1)
             secs, et = R.time_steps(ticks, 1)
         kind = "reference"
@@ -94,28 +94,28 @@ def cpu_baseline(n_cubes, warm_ticks, ticks):
         import bittoss_b200
         wa = bittoss_b200.synth_boxstack(n_cubes, 4, 777, 64, 60)
         ow = pybind.OracleLib().create(wa)
-        for _ in range(warm_ticks):
+        for _ in range(settle + warm_ticks):
             ow.step(31)
         secs, et = ow.time_steps(ticks)
         kind = "port"
     return {"value": et / secs, "unit": UNIT, "cores": cores, "kind": kind, "seconds": round(secs, 3),
-            "sample": "%d whole ticks of the %d-cube box-stack world after %d warm-up ticks, 1 thread"
-                      % (ticks, n_cubes, warm_ticks)}
+            "sample": "%d whole ticks of the %d-cube box-stack world after %d settle + %d warm-up ticks, 1 thread"
+                      % (ticks, n_cubes, settle, warm_ticks)}
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    ticks = args.steps + args.warmup
-    # bounded sample: keep the whole run within ~2 minutes at ~5.5 us per entity-tick on one core
-    n_cubes = int(min(args.entities, max(20000, 110.0 / (ticks * 5.5e-6))))
-    cb = cpu_baseline(n_cubes, args.warmup, args.steps)
+    ticks = args.steps + args.warmup + args.settle
+    # bounded sample: keep the whole run within ~2.5 minutes at ~4 us per entity-tick on one core
+    n_cubes = int(min(args.entities, max(20000, 150.0 / (ticks * 4e-6))))
+    cb = cpu_baseline(n_cubes, args.warmup, args.steps, args.settle)
     line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * cb["seconds"] / max(1, args.steps),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
             "config": {"workload": "synthetic box-stack world, gravity + pushes (BASELINE.json configs[2])",
-                       "entities": n_cubes, "height": 4, "sample": cb["sample"]},
+                       "entities": n_cubes, "height": 4, "settle_ticks": args.settle, "sample": cb["sample"]},
             "cpu_baseline": cb,
             "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -148,6 +148,10 @@ def run_cuda(args):
     w = bittoss_b200.World(wa, device=local_rank)
     w.set_option("rebuild_every", args.rebuild_every)
 
+    # ---- (0) settle phase ("run 100 ticks after a 50-tick settle; report
+    #      both phases"): the cubes start 100-164 units apart and drop onto each other ----
+    settle_ms = w.tick_timed(args.settle) if args.settle > 0 else 0.0
+    settle_stats = w.stats(reset=True)
     # ---- (1) device-resident throughput: `value` ----
     w.tick(args.warmup)
     w.stats(reset=True)
@@ -246,7 +250,8 @@ def run_cuda(args):
     if rank == 0:
         cb = None
         if world_size == 1 and not args.no_cpu_baseline:
-            cb = cpu_baseline(args.entities, 1, args.cpu_ticks)
+            # bounded sample of the same workload (same recipe, settle included), sized for ~30 s
+            cb = cpu_baseline(min(args.entities, 100000), 1, args.cpu_ticks, args.settle)
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world_size, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
@@ -254,6 +259,11 @@ def run_cuda(args):
                                        "(BASELINE.json configs[2]), one independent world per GPU",
                            "entities_per_gpu": n, "cubes": args.entities, "height": 4, "push_every": 64,
                            "push_max": 60, "rebuild_every": args.rebuild_every,
+                           "settle_ticks": args.settle,
+                           "settle_phase": {"ms_per_step": settle_ms / max(1, args.settle),
+                                            "value": settle_stats["entity_ticks"] / max(1e-9, settle_ms * 1e-3),
+                                            "iterations_per_tick": settle_stats["iterations"] / max(1, args.settle),
+                                            "pair_builds_per_tick": settle_stats["pair_builds"] / max(1, args.settle)},
                            "l2": "state arrays (>=330 MB/world) exceed the 126 MB L2; no explicit flush",
                            "iterations_per_tick": st["iterations"] / max(1, st["ticks"]),
                            "pushes_per_tick": st["pushes"] / max(1, st["ticks"]),
@@ -294,7 +304,8 @@ def main():
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--entities", type=int, default=1000000)
     ap.add_argument("--rebuild-every", type=int, default=16)
-    ap.add_argument("--cpu-ticks", type=int, default=3)
+    ap.add_argument("--cpu-ticks", type=int, default=10)
+    ap.add_argument("--settle", type=int, default=50)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "cuda":

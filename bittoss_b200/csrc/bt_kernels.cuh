@@ -69,7 +69,7 @@ __global__ void __launch_bounds__(BT_BLOCK) k_bounds(DevWorld W) {
 }
 __global__ void __launch_bounds__(BT_BLOCK) k_morton(DevWorld W) { t_morton(W, TID); }
 __global__ void __launch_bounds__(BT_BLOCK) k_lbvh(DevWorld W) { t_lbvh_node(W, TID); }
-__global__ void __launch_bounds__(BT_BLOCK) k_refit(DevWorld W) { t_refit(W, TID); }
+__global__ void __launch_bounds__(BT_BLOCK) k_refit(DevWorld W, int cond) { t_refit(W, TID, cond); }
 
 /* traversal stacks live in shared memory, interleaved so that lane i's slot k is at
  * word k*128+i: the 32 lanes of a warp hit 32 different banks (no conflicts). */
@@ -143,6 +143,8 @@ __global__ void __launch_bounds__(256) k_narrow(DevWorld W) {
 	u32 any = 0;
 	u32 np = W.ctr[CT_PAIR_N];
 	if (np > (u32)W.pair_cap) np = (u32)W.pair_cap;
+	/* k_refit / k_pairs of this iteration have consumed the flag; pushes may raise it again */
+	if (blockIdx.x == 0 && threadIdx.x == 0) W.ctr[CT_CACHE_INVALID] = 0;
 	for (u32 p = blockIdx.x * blockDim.x + threadIdx.x; p < np; p += gridDim.x * blockDim.x)
 		t_narrow(W, W.pairs[p], st, any);
 	stats_flush(W, st);

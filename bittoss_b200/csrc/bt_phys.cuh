@@ -299,6 +299,16 @@ static BT_HD void bt_swept_box(const int4 &o, const int4 &c, const int4 &r, i32 
 	lo[2] = (o.z < c.z ? o.z : c.z) - r.z; hi[2] = (o.z > c.z ? o.z : c.z) + r.z;
 }
 
+/* does the entity still lie inside the inflated box its cached pairs were found with? */
+static BT_HD void bt_check_cover(const DevWorld &W, i32 e, const int4 &o, const int4 &c) {
+	int4 r = W.radius[e];
+	Box6 ib = W.ibox[e];
+	i32 lo[3], hi[3];
+	bt_swept_box(o, c, r, lo, hi);
+	if (lo[0] < ib.lo.x || lo[1] < ib.lo.y || lo[2] < ib.lo.z || hi[0] > ib.hi.x || hi[1] > ib.hi.y || hi[2] > ib.hi.z)
+		W.ctr[CT_CACHE_INVALID] = 1;
+}
+
 /* moveRecursive ent.cpp:115-126 */
 static BT_HD void bt_move_recursive(const DevWorld &W, i32 who, const i32 *dc, const i32 *dv) {
 	BT_FOR_SUBTREE(W, who, it, {
@@ -307,15 +317,7 @@ static BT_HD void bt_move_recursive(const DevWorld &W, i32 who, const i32 *dc, c
 		v.x += dv[0]; v.y += dv[1]; v.z += dv[2];
 		W.center[it] = c;
 		W.vel[it] = v;
-		if (W.hasBox[it]) { /* do the cached candidate pairs still cover this entity? */
-			int4 o = W.old[it], r = W.radius[it];
-			Box6 ib = W.ibox[it];
-			i32 lo[3], hi[3];
-			bt_swept_box(o, c, r, lo, hi);
-			if (lo[0] < ib.lo.x || lo[1] < ib.lo.y || lo[2] < ib.lo.z || hi[0] > ib.hi.x || hi[1] > ib.hi.y ||
-			    hi[2] > ib.hi.z)
-				W.ctr[CT_CACHE_INVALID] = 1;
-		}
+		if (W.hasBox[it]) bt_check_cover(W, it, W.old[it], c);
 	});
 }
 
@@ -647,9 +649,11 @@ static BT_HD int bt_max(int a, int b) { return a > b ? a : b; }
 /* refit: leaf position t computes its swept box (what velbox_step / velbox_update keep in
  * p1,p2,r: box.cpp:442-459, ent.cpp:892-904) and climbs; the second thread to reach a node
  * (atomic counter) builds it from both children. */
-static BT_HD void t_refit(const DevWorld &W, int t) {
+static BT_HD void t_refit(const DevWorld &W, int t, int cond) {
 	int L = W.n_leaves;
 	if (t >= L) return;
+	if (cond && !W.ctr[CT_CACHE_INVALID]) return; /* the cached pairs still cover everybody: nothing to do */
+	if (cond && t == 0) { W.ctr[CT_PAIR_N] = 0; bt_add32(&W.ctr[CT_PAIR_BUILDS], 1u); }
 	i32 e = W.leafEnt[t];
 	Box6 box;
 	if (bt_is_leaf_ent(W, e)) {
@@ -669,8 +673,10 @@ static BT_HD void t_refit(const DevWorld &W, int t) {
 	int node = W.leafParent[t];
 	while (node >= 0) {
 		bt_fence();
+		/* two arrivals per node and refit, so the counter's parity tells first from second
+		 * and never needs resetting */
 		u32 prev = bt_add32(&W.nodeCount[node], 1u);
-		if (prev == 0) return; /* first arrival: the sibling subtree is not done yet */
+		if (!(prev & 1u)) return; /* first arrival: the sibling subtree is not done yet */
 		bt_fence();
 		BvhNode &N = W.nodes[node];
 		i32 li = N.left, ri = N.right;
@@ -771,6 +777,7 @@ static BT_HD void t_collide(const DevWorld &W, int t, i32 *stack, int stride, Lo
 template <class Emit> static BT_HD void t_pairs(const DevWorld &W, int t, i32 *stack, int stride, Emit &emit) {
 	int L = W.n_leaves;
 	if (t >= L || L < 2) return;
+	if (!W.ctr[CT_CACHE_INVALID]) return; /* pairs of an earlier iteration / tick are still a superset */
 	i32 a = W.leafEnt[t];
 	if (!bt_is_leaf_ent(W, a)) return;
 	Box6 q = W.leafBox[t];
@@ -1213,10 +1220,12 @@ static BT_HD void t_integrate(const DevWorld &W, i32 e) {
 	if (!W.inList[e]) return;
 	int4 c = W.center[e], v = W.vel[e];
 	W.old[e] = c;
+	int4 o = c;
 	c.x += v.x; c.y += v.y; c.z += v.z;
 	W.center[e] = c;
 	W.forced[e] = 0;
 	W.needsCollision[e] = 1;
+	if (W.hasBox[e]) bt_check_cover(W, e, o, c);
 }
 
 /* Fast path of flush2 + doGravity + integrate when no delta is pending anywhere except the
@@ -1238,10 +1247,13 @@ static BT_HD void t_begin_fused(const DevWorld &W, i32 e, int gravity, int ctrls
 		}
 	}
 	W.old[e] = c;
+	int4 o = c;
 	c.x += v.x; c.y += v.y; c.z += v.z;
 	W.center[e] = c;
 	W.forced[e] = 0;
 	W.needsCollision[e] = 1;
+	/* pairs cached in an earlier tick stay valid while nobody leaves its inflated box */
+	if (W.hasBox[e]) bt_check_cover(W, e, o, c);
 }
 
 /* state hash (DESIGN.md "State hash"), summed per world with 64-bit atomics */

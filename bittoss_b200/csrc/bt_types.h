@@ -95,6 +95,7 @@ enum {
 	CT_FLUSH_HINT = 32,  /* something happened that flush1 has to act on (slider/mask request, a death) */
 	CT_UNSUPPORTED = 33, /* times a handler without a device implementation would have run (lenient uploads only) */
 	CT_UNSUP_LAST = 34,  /* kind<<8 | catalog id of the last such handler (0 push, 1 pushed, 2 entPair, 3 crush, 4 pickup flush) */
+	CT_PAIR_BUILDS = 35, /* k_pairs runs that actually rebuilt the pair list */
 	CT_WORDS = 64
 };
 enum { SK_ITERS = 0, SK_CAND, SK_POS, SK_PUSH, SK_SERIAL, SK_CRUSH, SK_FUMBLE, SK_NUM };

@@ -75,6 +75,7 @@ struct bt_world {
 	i64 max_iterations;
 	i64 pair_cache; /* 1: cached candidate pairs (k_pairs + k_narrow); 0: traverse every iteration (k_collide) */
 	i64 pair_rebuilds, pair_overflows;
+	u32 seen_pair_builds, pair_builds_at_tree;
 	bt_tick_stats stats;
 	bool profiling;
 	cudaEvent_t ev0, ev1;
@@ -163,7 +164,7 @@ int bt_world_create(bt_world **out, int device, int32_t max_ents, int32_t max_sl
 	w->device = device;
 	w->cap_ents = max_ents; w->cap_sliders = max_sliders; w->cap_wires = max_wires; w->cap_worlds = max_worlds;
 	w->tree_valid = false; w->deltas_pending = true; w->ticks_since_build = 0; w->full_flush_left = 2; w->ctrls_fused = false;
-	w->rebuild_every = 16; w->max_iterations = 100000; w->pair_cache = 1; w->pair_rebuilds = 0; w->pair_overflows = 0; w->profiling = false; w->ray_valid = false;
+	w->rebuild_every = 16; w->max_iterations = 100000; w->pair_cache = 1; w->pair_rebuilds = 0; w->pair_overflows = 0; w->seen_pair_builds = 0; w->pair_builds_at_tree = 0; w->profiling = false; w->ray_valid = false;
 	w->h_flag = NULL; w->ev0 = w->ev1 = NULL; w->stream = NULL;
 	*out = w;
 #define TRY(x) do { int _r = (x); if (_r) { bt_world_destroy(w); *out = NULL; return _r; } } while (0)
@@ -345,6 +346,12 @@ int bt_world_upload(bt_world *w, const bt_world_desc *d) {
 	UPRAW(W.wire_off, d->wire_off, n + 1, i32); UPRAW(W.wire_to, d->wire_to, d->n_wires, i32);
 	UP(W.wire_cnt, wire_cnt);
 	CK(cudaMemsetAsync(W.ctr, 0, sizeof(u32) * CT_WORDS, w->stream));
+	{
+		u32 one = 1;
+		CK(cudaMemcpyAsync(&W.ctr[CT_CACHE_INVALID], &one, sizeof(u32), cudaMemcpyHostToDevice, w->stream));
+	}
+	w->seen_pair_builds = 0; w->pair_builds_at_tree = 0;
+	CK(cudaMemsetAsync(W.nodeCount, 0, sizeof(u32) * (size_t)w->cap_ents, w->stream));
 	CK(cudaMemsetAsync(W.wflush, 0, (size_t)nw, w->stream));
 	CK(cudaStreamSynchronize(w->stream));
 #undef UP
@@ -377,6 +384,8 @@ static int radix_sort(bt_world *w, int key_bits) {
 
 static int bits_for(u32 x) { int b = 0; while (x) { b++; x >>= 1; } return b; }
 
+static int raise_cache_invalid(bt_world *w);
+
 /* Morton sort + Karras hierarchy over every live boxed entity */
 static int build_tree(bt_world *w) {
 	DevWorld &W = w->W;
@@ -398,18 +407,28 @@ static int build_tree(bt_world *w) {
 	int r = radix_sort(w, 30 + W.world_bits);
 	if (r) return r;
 	if (W.n_leaves >= 2) LAUNCH(w, PK_LBVH, k_lbvh, nblk(W.n_leaves - 1), BT_BLOCK, W);
+	/* new topology: node boxes are stale until the next refit, counters restart even */
+	CK(cudaMemsetAsync(W.nodeCount, 0, sizeof(u32) * (size_t)n, w->stream));
+	if (!W.ray_mode) { int rr = raise_cache_invalid(w); if (rr) return rr; }
 	w->tree_valid = true;
 	w->ticks_since_build = 0;
+	w->pair_builds_at_tree = w->seen_pair_builds + 1; /* + the pair search this build itself forces */
 	w->stats.tree_builds++;
 	return 0;
 }
 
-static int refit(bt_world *w) {
+/* cond: only if CT_CACHE_INVALID is raised (decided on the device, no host round trip) */
+static int refit(bt_world *w, bool cond) {
 	DevWorld &W = w->W;
 	if (W.n_leaves < 1) return 0;
-	CK(cudaMemsetAsync(W.nodeCount, 0, sizeof(u32) * (size_t)W.n_leaves, w->stream));
-	LAUNCH(w, PK_REFIT, k_refit, nblk(W.n_leaves), BT_BLOCK, W);
+	LAUNCH(w, PK_REFIT, k_refit, nblk(W.n_leaves), BT_BLOCK, W, cond ? 1 : 0);
 	w->stats.tree_refits++;
+	return 0;
+}
+
+static int raise_cache_invalid(bt_world *w) {
+	static const u32 one = 1;
+	CK(cudaMemcpyAsync(&w->W.ctr[CT_CACHE_INVALID], &one, sizeof(u32), cudaMemcpyHostToDevice, w->stream));
 	return 0;
 }
 
@@ -453,36 +472,38 @@ static int do_physics(bt_world *w, bool gravity) {
 		w->deltas_pending = false;
 	}
 	/* leaf set changes (an entity gained a box) force a rebuild; deaths do not */
-	if (!w->tree_valid || w->ticks_since_build >= w->rebuild_every) {
+	/* ... and an old tree is only rebuilt if pair lists are being rebuilt at all (a world at
+	 * rest keeps its cached pairs for as long as nobody leaves its inflated box) */
+	if (!w->tree_valid || (w->ticks_since_build >= w->rebuild_every &&
+	                       (!w->pair_cache || w->seen_pair_builds > w->pair_builds_at_tree))) {
 		int r = build_tree(w);
 		if (r) return r;
 	}
 	w->ticks_since_build++;
 	i64 it = 0;
-	bool use_cache = w->pair_cache != 0, pairs_valid = false, count_pairs = false;
+	bool use_cache = w->pair_cache != 0;
 	while (1) {
 		int r;
 		W.iter_id++;
 		if (use_cache) {
-			if (!pairs_valid) {
-				r = refit(w);
-				if (r) return r;
-				CK(cudaMemsetAsync(&W.ctr[CT_PAIR_N], 0, 2 * sizeof(u32), w->stream)); /* + CT_CACHE_INVALID */
-				LAUNCH(w, PK_PAIRS, k_pairs, nblk(W.n_leaves), BT_BLOCK, W);
-				pairs_valid = true;
-				w->pair_rebuilds++;
-				w->stats.pair_builds++;
-				count_pairs = true;
-			}
+			/* refit + pair search run only if CT_CACHE_INVALID is up (upload, rebuilt tree, or an
+			 * entity left the inflated box its pairs were found with); they test it on the device */
+			r = refit(w, true);
+			if (r) return r;
+			LAUNCH(w, PK_PAIRS, k_pairs, nblk(W.n_leaves), BT_BLOCK, W);
 			LAUNCH(w, PK_NARROW, k_narrow, 148 * 8, 256, W);
 		} else {
-			r = refit(w);
+			r = refit(w, false);
 			if (r) return r;
 			LAUNCH(w, PK_COLLIDE, k_collide, nblk(W.n_leaves), BT_BLOCK, W);
 		}
 		r = fetch_ctr(w);
 		if (r) return r;
-		if (count_pairs) { w->stats.pairs_cached += (i64)w->h_flag[CT_PAIR_N]; count_pairs = false; }
+		if (use_cache && w->h_flag[CT_PAIR_BUILDS] != w->seen_pair_builds) {
+			w->stats.pair_builds += (i64)(w->h_flag[CT_PAIR_BUILDS] - w->seen_pair_builds);
+			w->stats.pairs_cached += (i64)w->h_flag[CT_PAIR_N];
+			w->seen_pair_builds = w->h_flag[CT_PAIR_BUILDS];
+		}
 		if (use_cache && w->h_flag[CT_PAIR_N] > (u32)W.pair_cap) {
 			/* more touching pairs than the buffer holds: this tick falls back to per-iteration
 			 * traversal; the narrow pass above saw only part of the pairs, so redo the iteration */
@@ -503,18 +524,14 @@ static int do_physics(bt_world *w, bool gravity) {
 		LAUNCH(w, PK_PUSH, k_push, nblk(n), BT_BLOCK, W);
 		LAUNCH(w, PK_PUSH, k_push_serial, 1, 32, W);
 		LAUNCH(w, PK_POST, k_post, nblk(n), BT_BLOCK, W);
-		if (use_cache) {
-			/* did a push carry somebody out of the inflated box its pairs were found with? the
-			 * flag is read together with the next iteration's counters, one iteration late is
-			 * too late, so fetch it now (tiny D2H on the same stream) */
-			r = fetch_ctr(w);
-			if (r) return r;
-			if (w->h_flag[CT_CACHE_INVALID]) pairs_valid = false;
-		}
 		if (++it > w->max_iterations) {
 			snprintf(g_err, sizeof g_err, "doPhysics did not converge in %lld iterations", (long long)w->max_iterations);
 			return BT_ERR_OVERFLOW;
 		}
+	}
+	if (w->pair_cache && !use_cache) { /* overflowed: the partial pair list must not be reused */
+		int rr = raise_cache_invalid(w);
+		if (rr) return rr;
 	}
 	/* invokeOnCrush (ent.cpp:907): crush handlers are host-side events (dead list) */
 	/* h_flag holds the counters fetched after the last k_narrow, i.e. after every push */
@@ -527,7 +544,7 @@ static int do_physics(bt_world *w, bool gravity) {
 	if (r) return r;
 	if (w->h_flag[CT_FLUSH_HINT] && w->full_flush_left < 1) w->full_flush_left = 1;
 	if (w->h_flag[CT_NEED_REBUILD]) {
-		w->tree_valid = false;
+		w->tree_valid = false; /* build_tree raises CT_CACHE_INVALID */
 		CK(cudaMemsetAsync(&W.ctr[CT_NEED_REBUILD], 0, sizeof(u32), w->stream));
 	}
 	w->ray_valid = false;
@@ -868,7 +885,7 @@ static int ray_build(bt_world *w) {
 	i64 builds = w->stats.tree_builds, refits = w->stats.tree_refits;
 	ray_swap(w);
 	int r = build_tree(w);
-	if (!r) r = refit(w);
+	if (!r) r = refit(w, false);
 	if (!r) { LAUNCH(w, PK_RAY_BUILD, k_live_ranks, 1, 1024, w->W, w->ray.rank2slot, w->ray.slot2rank); w->ranks_valid = true; }
 	ray_swap(w);
 	w->tree_valid = tv; w->ticks_since_build = tsb;

@@ -31,6 +31,7 @@ struct Emu {
 	LocalStats st;
 	std::vector<i32> up_root_order;
 	int pair_cache;   /* 1: k_pairs + k_narrow, 0: k_collide every iteration */
+	u32 pair_builds_at_tree;
 	int64_t pair_rebuilds;
 	int shuffle_seed; /* != 0: run the threads of order-sensitive kernels in a scrambled order */
 };
@@ -142,6 +143,8 @@ Emu *bte_create(const bt_world_desc *d, int rebuild_every, int shuffle_seed) {
 	}
 	for (int g = 0; g < nw; g++)
 		if (W.wbegin[g] > W.wend[g]) W.wbegin[g] = W.wend[g] = 0;
+	W.ctr[CT_CACHE_INVALID] = 1;
+	E->pair_builds_at_tree = 0;
 	E->deltas_pending = deltas;
 	E->up_root_order.assign(d->root_order, d->root_order + n);
 	return E;
@@ -174,15 +177,19 @@ static void build_tree(Emu *E) {
 	for (i32 i = 0; i < W.n; i++) { k2[i] = W.keys[idx[i]]; v2[i] = W.leafEnt[idx[i]]; }
 	for (i32 i = 0; i < W.n; i++) { W.keys[i] = k2[i]; W.leafEnt[i] = v2[i]; }
 	for (i32 i = 0; i < L - 1; i++) t_lbvh_node(W, i);
+	for (i32 i = 0; i < W.n; i++) W.nodeCount[i] = 0;
+	if (!W.ray_mode) W.ctr[CT_CACHE_INVALID] = 1;
 	E->tree_valid = true;
 	E->ticks_since_build = 0;
+	E->pair_builds_at_tree = W.ctr[CT_PAIR_BUILDS] + 1; /* + the pair search this build itself forces */
 }
 
-static void refit(Emu *E) {
+static void refit(Emu *E, int cond) {
 	DevWorld &W = E->W;
-	for (i32 i = 0; i < W.n_leaves; i++) W.nodeCount[i] = 0;
+	/* thread 0 may reset counters: run it first like any other thread would see it (the flag is
+	 * only read, never written, by this kernel) */
 	std::vector<i32> o = order(E, W.n_leaves);
-	for (i32 t : o) t_refit(W, t);
+	for (i32 t : o) t_refit(W, t, cond);
 }
 
 static void flush1(Emu *E, bool hint) {
@@ -209,11 +216,12 @@ static int do_physics(Emu *E, bool gravity) {
 		for (i32 e = 0; e < n; e++) t_integrate(W, e);
 		E->deltas_pending = false;
 	}
-	if (!E->tree_valid || E->ticks_since_build >= E->rebuild_every) build_tree(E);
+	if (!E->tree_valid || (E->ticks_since_build >= E->rebuild_every &&
+	                       (!E->pair_cache || W.ctr[CT_PAIR_BUILDS] > E->pair_builds_at_tree)))
+		build_tree(E);
 	E->ticks_since_build++;
 	std::vector<i32> stack(BT_STACK);
 	int guard = 0;
-	bool pairs_valid = false;
 	struct HostEmit {
 		const DevWorld &W;
 		void operator()(i32 a, i32 b) {
@@ -225,20 +233,20 @@ static int do_physics(Emu *E, bool gravity) {
 		W.iter_id++;
 		u32 any = 0;
 		if (E->pair_cache) {
-			if (!pairs_valid) {
-				refit(E);
-				W.ctr[CT_PAIR_N] = 0; W.ctr[CT_CACHE_INVALID] = 0;
+			u32 before = W.ctr[CT_PAIR_BUILDS];
+			refit(E, 1);
+			{
 				HostEmit emit = {W};
 				std::vector<i32> o = order(E, W.n_leaves);
 				for (i32 t : o) t_pairs(W, t, stack.data(), 1, emit);
-				if ((i32)W.ctr[CT_PAIR_N] > W.pair_cap) return BT_ERR_OVERFLOW;
-				pairs_valid = true;
-				E->pair_rebuilds++;
 			}
+			if ((i32)W.ctr[CT_PAIR_N] > W.pair_cap) return BT_ERR_OVERFLOW;
+			if (W.ctr[CT_PAIR_BUILDS] != before) E->pair_rebuilds++;
+			W.ctr[CT_CACHE_INVALID] = 0; /* k_narrow, block 0 thread 0 */
 			std::vector<i32> o = order(E, (i32)W.ctr[CT_PAIR_N]);
 			for (i32 p : o) t_narrow(W, W.pairs[p], E->st, any);
 		} else {
-			refit(E);
+			refit(E, 0);
 			std::vector<i32> o = order(E, W.n_leaves);
 			for (i32 t : o) t_collide(W, t, stack.data(), 1, E->st, any);
 		}
@@ -255,7 +263,6 @@ static int do_physics(Emu *E, bool gravity) {
 		}
 		if (W.ctr[CT_SERIAL_N]) t_push_serial(W, E->st);
 		for (i32 e = 0; e < n; e++) t_post(W, e);
-		if (W.ctr[CT_CACHE_INVALID]) pairs_valid = false;
 		if (++guard > 100000) return BT_ERR_OVERFLOW;
 	}
 	flush1(E, W.ctr[CT_FLUSH_HINT] != 0);
@@ -333,7 +340,7 @@ int bte_raycast(Emu *E, const int32_t *origin, const int32_t *look, int32_t n_ra
 	Emu tmp = *E;
 	tmp.W = W; tmp.shuffle_seed = 0;
 	build_tree(&tmp);
-	refit(&tmp);
+	refit(&tmp, 0);
 	W = tmp.W;
 	std::vector<i32> rank2slot, slot2rank(W.n, -1);
 	for (i32 e = 0; e < W.n; e++)
