@@ -124,3 +124,40 @@ def test_cuda_batched_arena_worlds_teacher_forced(ref_lib, bt):
     w.close()
     print("batched arena: %d world-ticks bit-exact, %d skipped" % (ok, skipped))
     assert skipped <= 0.005 * ticks * n_worlds and ok + skipped == ticks * n_worlds
+
+
+# ---- the same check from committed fixtures (no reference needed on the machine) ----
+TF_GOLDEN = ["tf_arena_2players", "tf_lobby_4players", "tf_spacetrash_spawner"]
+
+
+@pytest.mark.parametrize("name", TF_GOLDEN)
+def test_kernel_bodies_teacher_forced_golden(emu, name):
+    from util import load_teacher_forced
+    ok = 0
+    for wa, want in load_teacher_forced(name):
+        ew = emu.EmuWorld(wa, 1, 0, lenient=True)
+        ew.step(PHYSICS_FINISH)
+        if ew.unsupported():
+            continue
+        assert ew.hash()[0] == want
+        ok += 1
+    assert ok >= 55
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", TF_GOLDEN)
+def test_cuda_teacher_forced_golden(bt, name):
+    from util import load_teacher_forced
+    w = bt.World(None, max_ents=4096, max_sliders=8192, max_wires=4096, max_worlds=1)
+    w.set_option("allow_unsupported", 1)
+    ok = 0
+    for wa, want in load_teacher_forced(name):
+        w.stats(reset=True)
+        w.upload(wa)
+        w.step(PHYSICS_FINISH)
+        if w.stats()["unsupported_events"]:
+            continue
+        assert w.hash()[0] == want
+        ok += 1
+    w.close()
+    assert ok >= 55

@@ -64,3 +64,18 @@ def load_scenario(name):
     """-> (WorldArrays initial state, reference per-tick hashes uint64[ticks])."""
     wa, extra = load_world(golden_path(name))
     return wa, extra["ref_hashes"]
+
+
+def load_teacher_forced(name):
+    """-> list of (WorldArrays state before doPhysics, reference hash after it), one per tick."""
+    z = np.load(golden_path(name))
+    sizes, hashes = z["sizes"], z["ref_hashes"]
+    out = []
+    for t in range(len(sizes)):
+        n, ns, nw = [int(x) for x in sizes[t]]
+        wa = WorldArrays(n, ns, nw, 1)
+        for k in wa.a:
+            off = z["o_" + k]
+            wa.a[k][:] = z["f_" + k][off[t]: off[t + 1]][: len(wa.a[k])]
+        out.append((wa, int(hashes[t])))
+    return out
