@@ -213,9 +213,11 @@ def run_cuda(args):
     # ALGORITHMIC bytes per launch of each kernel class (DESIGN.md "Kernels" states the per-unit figures)
     alg = {
         "narrow": lambda L: 8 * P + 64 * ps["candidate_pairs"] / max(1, L),
-        "pairs": lambda L: 32 * n_leaves + 8 * P,
+        # k_refit / k_pairs return at once unless the pair cache was invalidated: only the launches
+        # that did the work (pair_builds of them) move bytes
+        "pairs": lambda L: (32 * n_leaves + 8 * P) * ps["pair_builds"] / max(1, L),
         "collide": lambda L: COLLIDE_BYTES_PER_LEAF * n_leaves,
-        "refit": lambda L: 212 * n_leaves,
+        "refit": lambda L: 212 * n_leaves * ps["pair_builds"] / max(1, L),
         "push": lambda L: 200 * ps["pushes"] / max(1, L),
         "begin_integrate": lambda L: 94 * n,
         "decide": lambda L: 10 * n,
@@ -229,6 +231,8 @@ def run_cuda(args):
             continue
         avg_ms = kms / launches
         ach = alg[k](launches) / (avg_ms * 1e-3) / 1e9 if k in alg and avg_ms > 0 else None
+        if ach is not None and ach <= 0:
+            ach = None
         per_kernel[k] = {"launches_per_tick": launches / prof_ticks, "avg_launch_ms": round(avg_ms, 5),
                          "ms_per_tick": round(kms / prof_ticks, 5), "share_of_step": round(kms / total_ms, 4),
                          "alg_gbs": round(ach, 2) if ach else None, "frac": round(ach / peak, 5) if ach else None}
