@@ -32,6 +32,12 @@ static __device__ __forceinline__ void stats_flush(const DevWorld &W, const Loca
 }
 
 #define TID ((i32)(blockIdx.x * blockDim.x + threadIdx.x))
+/* grid-stride loop for the two kernels that usually return at once (k_refit, k_pairs are
+ * conditional on CT_CACHE_INVALID): a one-wave grid makes the no-op launch ~3 us instead of
+ * ~10 us at 1 M entities.  Measured: the always-busy per-iteration kernels (decide, push,
+ * post) gain nothing from it and keep one thread per entity. */
+#define GS_FOR(i, n) for (i32 i = TID; i < (n); i += (i32)(gridDim.x * blockDim.x))
+#define GS_BLOCK 256
 
 __global__ void __launch_bounds__(BT_BLOCK) k_pre(DevWorld W, u32 phases) { t_pre(W, TID, phases); }
 __global__ void __launch_bounds__(BT_BLOCK) k_flush_scan(DevWorld W) { t_flush_scan(W, TID); }
@@ -69,7 +75,10 @@ __global__ void __launch_bounds__(BT_BLOCK) k_bounds(DevWorld W) {
 }
 __global__ void __launch_bounds__(BT_BLOCK) k_morton(DevWorld W) { t_morton(W, TID); }
 __global__ void __launch_bounds__(BT_BLOCK) k_lbvh(DevWorld W) { t_lbvh_node(W, TID); }
-__global__ void __launch_bounds__(BT_BLOCK) k_refit(DevWorld W, int cond) { t_refit(W, TID, cond); }
+__global__ void __launch_bounds__(GS_BLOCK) k_refit(DevWorld W, int cond) {
+	if (cond && !W.ctr[CT_CACHE_INVALID]) return;
+	GS_FOR(t, W.n_leaves) t_refit(W, t, cond);
+}
 
 /* traversal stacks live in shared memory, interleaved so that lane i's slot k is at
  * word k*128+i: the 32 lanes of a warp hit 32 different banks (no conflicts). */
@@ -88,18 +97,16 @@ struct PairEmit {
 	u64 *pairs;
 	u32 *counter;
 	u32 cap;
-	i32 *buf; /* this thread's slots in shared memory, stride BT_BLOCK (bank-conflict free) */
-	i32 a;
+	u64 *buf; /* this thread's slots in shared memory, stride BT_BLOCK */
 	int n;
-	__device__ __forceinline__ PairEmit(u64 *p, u32 *c, i32 cap_, i32 *sbuf)
-	    : pairs(p), counter(c), cap((u32)cap_), buf(sbuf), a(-1), n(0) {}
-	__device__ __forceinline__ void store(u32 pos, i32 b) {
-		if (pos < cap) pairs[pos] = (u64)(u32)a | ((u64)(u32)b << 32);
+	__device__ __forceinline__ PairEmit(u64 *p, u32 *c, i32 cap_, u64 *sbuf)
+	    : pairs(p), counter(c), cap((u32)cap_), buf(sbuf), n(0) {}
+	__device__ __forceinline__ void store(u32 pos, u64 pr) {
+		if (pos < cap) pairs[pos] = pr;
 	}
 	/* called from divergent code when this thread's buffer is full */
-	__device__ __forceinline__ void operator()(i32 a_, i32 b) {
-		a = a_;
-		buf[(n++) * BT_BLOCK] = b;
+	__device__ __forceinline__ void operator()(i32 a, i32 b) {
+		buf[(n++) * BT_BLOCK] = (u64)(u32)a | ((u64)(u32)b << 32);
 		if (n == PAIR_BUF) {
 			u32 m = __activemask();
 			int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
@@ -131,9 +138,14 @@ struct PairEmit {
 
 __global__ void __launch_bounds__(BT_BLOCK) k_pairs(DevWorld W) {
 	__shared__ i32 stacks[BT_STACK * BT_BLOCK];
-	__shared__ i32 pbuf[PAIR_BUF * BT_BLOCK];
+	__shared__ u64 pbuf[PAIR_BUF * BT_BLOCK];
+	if (!W.ctr[CT_CACHE_INVALID]) return; /* uniform: the cached pairs are still a superset */
 	PairEmit emit(W.pairs, &W.ctr[CT_PAIR_N], W.pair_cap, pbuf + threadIdx.x);
-	t_pairs(W, TID, stacks + threadIdx.x, BT_BLOCK, emit);
+	/* blocked distribution: each block walks one contiguous run of leaves, so the pair list
+	 * stays in Morton order (k_narrow's gathers depend on that locality) */
+	i32 chunk = (W.n_leaves + (i32)gridDim.x - 1) / (i32)gridDim.x;
+	i32 t0 = (i32)blockIdx.x * chunk, t1 = t0 + chunk < W.n_leaves ? t0 + chunk : W.n_leaves;
+	for (i32 t = t0 + (i32)threadIdx.x; t < t1; t += BT_BLOCK) t_pairs(W, t, stacks + threadIdx.x, BT_BLOCK, emit);
 	emit.finish();
 }
 

@@ -120,6 +120,20 @@ template <typename T> static int dalloc(bt_world *w, T **p, size_t count) {
 	} while (0)
 
 static inline int nblk(i64 n, int b = BT_BLOCK) { return (int)((n + b - 1) / b); }
+/* fixed one-wave grid for the grid-stride kernels: 148 SMs x 8 blocks of 256 threads */
+static inline int gsblk(i64 n) { return (int)std::min<i64>((n + GS_BLOCK - 1) / GS_BLOCK, 148 * 8); }
+/* one full wave of k_pairs: SM count x resident blocks per SM (occupancy API, cached) */
+static int pairs_wave() {
+	static int wave = 0;
+	if (!wave) {
+		int dev = 0, sms = 148, per = 8;
+		cudaGetDevice(&dev);
+		cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+		if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, k_pairs, BT_BLOCK, 0) != cudaSuccess || per < 1) per = 8;
+		wave = sms * per;
+	}
+	return wave;
+}
 
 extern "C" {
 
@@ -421,7 +435,7 @@ static int build_tree(bt_world *w) {
 static int refit(bt_world *w, bool cond) {
 	DevWorld &W = w->W;
 	if (W.n_leaves < 1) return 0;
-	LAUNCH(w, PK_REFIT, k_refit, nblk(W.n_leaves), BT_BLOCK, W, cond ? 1 : 0);
+	LAUNCH(w, PK_REFIT, k_refit, gsblk(W.n_leaves), GS_BLOCK, W, cond ? 1 : 0);
 	w->stats.tree_refits++;
 	return 0;
 }
@@ -490,7 +504,7 @@ static int do_physics(bt_world *w, bool gravity) {
 			 * entity left the inflated box its pairs were found with); they test it on the device */
 			r = refit(w, true);
 			if (r) return r;
-			LAUNCH(w, PK_PAIRS, k_pairs, nblk(W.n_leaves), BT_BLOCK, W);
+			LAUNCH(w, PK_PAIRS, k_pairs, std::min(nblk(W.n_leaves), pairs_wave()), BT_BLOCK, W);
 			LAUNCH(w, PK_NARROW, k_narrow, 148 * 8, 256, W);
 		} else {
 			r = refit(w, false);
