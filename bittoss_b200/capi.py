@@ -47,7 +47,8 @@ def build(force=False, verbose=False):
     deps.append(os.path.join(INCLUDE, "bittoss_b200.h"))
     if not force and os.path.exists(LIB_SO) and all(os.path.getmtime(LIB_SO) >= os.path.getmtime(d) for d in deps):
         return LIB_SO
-    cmd = ["nvcc"] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_SO] + srcs
+    extra = os.environ.get("BT_NVCC_EXTRA", "").split()
+    cmd = ["nvcc"] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_SO] + srcs
     subprocess.check_call(cmd)
     return LIB_SO
 
