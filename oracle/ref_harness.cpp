@@ -241,6 +241,15 @@ int btref_make_boxstack(int32_t n_cubes, int32_t H, uint32_t seed, int32_t push_
 	return w->next_uid;
 }
 
+/* one entity through the reference's own initEnt (entFuncs.c:88-111); whoMoves by catalog id */
+int btref_add_ent(const int32_t *c, const int32_t *v, const int32_t *r, uint32_t typeMask, uint32_t collideMask,
+                  int whoMovesId) {
+	ent *e = initEnt(cur->gs, NULL, c, v, r, 0, (int32_t)typeMask, (int32_t)collideMask);
+	e->whoMoves = whoMovesHandlers.get(whoMovesId);
+	assign_new_uids(cur);
+	return cur->next_uid - 1;
+}
+
 /* Replace collision-path handlers that have no device-side implementation by
  * the catalog's NIL entry, and (mode&2) drop every tick handler, so that a
  * shipped level becomes a pure physics fixture.  This edits the INPUT world,

@@ -14,7 +14,7 @@ import pytest
 CASES = {
     # name: (level, players' data, spacetrash spawner on, ticks, max skipped fraction)
     "lobby_4players": ("lobby", (0, 0, 0, 0), 0, 1000, 0.005),   # PUSH_TEAMSELECT / PUSH_LOADBLOCK are host-side
-    "spacetrash_spawner": ("spacetrash", (), 1, 4000, 0.0),
+    "spacetrash_spawner": ("spacetrash", (), 1, 10000, 0.0),
     "arena_2players": ("arena", (1, 2), 0, 1000, 0.0),
 }
 PHYSICS_FINISH = 8 | 16
