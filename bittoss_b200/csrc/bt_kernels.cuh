@@ -88,7 +88,7 @@ __global__ void __launch_bounds__(BT_BLOCK) k_collide(DevWorld W) {
 	u32 any = 0;
 	t_collide(W, TID, stacks + threadIdx.x, BT_BLOCK, st, any);
 	stats_flush(W, st);
-	if (__any_sync(0xffffffffu, any) && (threadIdx.x & 31) == 0) W.ctr[CT_ANY_PROPOSAL] = 1;
+	if (__any_sync(0xffffffffu, any) && (threadIdx.x & 31) == 0) W.ctr[CT_ANY_PROPOSAL] = (u32)W.iter_id;
 }
 /* Pair emitter: hits are buffered per thread and written with ONE atomic per warp flush
  * (warp-ballot/shuffle compaction) instead of one atomic per pair. */
@@ -170,17 +170,24 @@ __global__ void __launch_bounds__(256) k_narrow(DevWorld W) {
 	LocalStats st = {0, 0, 0, 0, 0};
 	u32 any = 0;
 	u32 np = W.ctr[CT_PAIR_N];
-	if (np > (u32)W.pair_cap) np = (u32)W.pair_cap;
+	if (np > (u32)W.pair_cap) { /* incomplete pair list: nobody may act on it */
+		if (blockIdx.x == 0 && threadIdx.x == 0) W.ctr[CT_PAIR_OVERFLOW] = 1;
+		return;
+	}
 	/* k_refit / k_pairs of this iteration have consumed the flag; pushes may raise it again */
 	if (blockIdx.x == 0 && threadIdx.x == 0) W.ctr[CT_CACHE_INVALID] = 0;
 	for (u32 p = blockIdx.x * blockDim.x + threadIdx.x; p < np; p += gridDim.x * blockDim.x)
 		t_narrow(W, W.pairs[p], st, any);
 	stats_flush(W, st);
-	if (__any_sync(0xffffffffu, any) && (threadIdx.x & 31) == 0) W.ctr[CT_ANY_PROPOSAL] = 1;
+	if (__any_sync(0xffffffffu, any) && (threadIdx.x & 31) == 0) W.ctr[CT_ANY_PROPOSAL] = (u32)W.iter_id;
 }
 
+/* The resolve kernels of an iteration are enqueued right behind its narrow phase, before the
+ * host knows whether anything was proposed (one host sync per iteration instead of two).  With
+ * no proposal they are no-ops by construction; if the pair buffer overflowed they stand down
+ * (CT_PAIR_OVERFLOW) and the host redoes the iteration through k_collide. */
 __global__ void __launch_bounds__(BT_BLOCK) k_decide(DevWorld W) {
-	if (TID == 0) W.ctr[CT_ANY_PROPOSAL] = 0; /* the host already fetched this iteration's value */
+	if (W.ctr[CT_PAIR_OVERFLOW]) return;
 	t_decide(W, TID);
 }
 /* ready roots (typically 1 entity in 4) are re-packed into full warps before the push */
@@ -188,6 +195,7 @@ __global__ void __launch_bounds__(BT_BLOCK) k_push(DevWorld W) {
 	__shared__ u32 queue[BT_BLOCK];
 	__shared__ u32 qn;
 	LocalStats st = {0, 0, 0, 0, 0};
+	if (W.ctr[CT_PAIR_OVERFLOW]) return;
 	if (threadIdx.x == 0) qn = 0;
 	__syncthreads();
 	i32 e = TID;
@@ -198,13 +206,16 @@ __global__ void __launch_bounds__(BT_BLOCK) k_push(DevWorld W) {
 }
 __global__ void k_push_serial(DevWorld W) {
 	if (threadIdx.x != 0 || blockIdx.x != 0) return;
-	if (W.ctr[CT_SERIAL_N] == 0) return;
+	if (W.ctr[CT_SERIAL_N] == 0 || W.ctr[CT_PAIR_OVERFLOW]) return;
 	LocalStats st = {0, 0, 0, 0, 0};
 	t_push_serial(W, st);
 	u64 *s = (u64 *)&W.ctr[CT_STAT0];
 	s[SK_PUSH] += st.push; s[SK_SERIAL] += st.push; s[SK_CRUSH] += st.crush; s[SK_FUMBLE] += st.fumble;
 }
-__global__ void __launch_bounds__(BT_BLOCK) k_post(DevWorld W) { t_post(W, TID); }
+__global__ void __launch_bounds__(BT_BLOCK) k_post(DevWorld W) {
+	if (W.ctr[CT_PAIR_OVERFLOW]) return;
+	t_post(W, TID);
+}
 
 /* host exchange: staging buffers hold [3*n_live] ints in live oldest-first order; while no
  * entity has died, live rank == slot (the common case, checked by the host) */

@@ -810,50 +810,6 @@ template <class Emit> static BT_HD void t_pairs(const DevWorld &W, int t, i32 *s
 	}
 }
 
-/* The narrow phase of a cached pair in two steps, so that the kernel can re-pack the few
- * survivors of the cheap step into full warps before the expensive one (most pairs of a
- * resting world are rejected by the flags or by the per-axis separation test).
- *
- * Step 1: which ends scan (ent.cpp:443-455), mask test and same-tree test (ent.cpp:399-402)
- * and the early-out of getAxisAndDir (ent.cpp:241-250).  Returns bit 0: a scans b survives,
- * bit 1: b scans a survives. */
-static BT_HD int bt_separated(const EntGeo &a, const EntGeo &b) {
-	i32 d1, d2, wd;
-	d1 = b.old.x - a.old.x; d2 = b.center.x - a.center.x; wd = a.radius.x + b.radius.x;
-	if (d1 > 0 ? (d1 >= wd && d2 >= wd) : (d1 <= -wd && d2 <= -wd)) return 1;
-	d1 = b.old.y - a.old.y; d2 = b.center.y - a.center.y; wd = a.radius.y + b.radius.y;
-	if (d1 > 0 ? (d1 >= wd && d2 >= wd) : (d1 <= -wd && d2 <= -wd)) return 1;
-	d1 = b.old.z - a.old.z; d2 = b.center.z - a.center.z; wd = a.radius.z + b.radius.z;
-	if (d1 > 0 ? (d1 >= wd && d2 >= wd) : (d1 <= -wd && d2 <= -wd)) return 1;
-	return 0;
-}
-
-static BT_HD int t_narrow_filter(const DevWorld &W, u64 pr, LocalStats &st) {
-	i32 a = (i32)(u32)pr, b = (i32)(pr >> 32);
-	int na = W.needsCollision[a], nb = W.needsCollision[b];
-	if (!(na | nb)) return 0; /* the common case after the first iteration: two byte loads */
-	int alive = W.inList[a] & W.hasBox[a] & W.inList[b] & W.hasBox[b]; /* `o->dead` ent.cpp:455 */
-	if (!alive) return 0;
-	st.cand += (u32)(na + nb);
-	u32 ta = W.type[a], ca = W.collide[a], tb = W.type[b], cb = W.collide[b];
-	if (!((tb & ca) | (ta & cb))) return 0;
-	if (W.holdRoot[a] == W.holdRoot[b]) return 0;
-	EntGeo ga = bt_geo(W, a), gb = bt_geo(W, b);
-	int m = 0;
-	if (na && !bt_separated(ga, gb)) m |= 1;
-	if (nb && !bt_separated(gb, ga)) m |= 2;
-	return m;
-}
-
-/* Step 2: the full checkCollision (ent.cpp:398-435) for one surviving direction. */
-static BT_HD void t_narrow_item(const DevWorld &W, u64 pr, int second, LocalStats &st, u32 &any) {
-	i32 a = (i32)(u32)pr, b = (i32)(pr >> 32);
-	if (second) { i32 t_ = a; a = b; b = t_; }
-	int bScans = W.needsCollision[b]; /* b is alive and boxed: checked by the filter */
-	bt_check_loaded(W, a, bt_geo(W, a), W.type[a], W.collide[a], W.holdRoot[a], W.hphys[a], b, bt_geo(W, b), W.type[b],
-	                W.collide[b], W.holdRoot[b], W.hphys[b], bScans, st, any);
-}
-
 /* checkCollision ent.cpp:398-435 for one cached pair, from whichever ends are scanning: all
  * loads of both ends first (they are independent), then one copy of the narrow phase run from
  * each scanning end */

@@ -79,7 +79,7 @@ struct __attribute__((aligned(16))) Box6 { /* own box of a node or leaf, used on
 
 /* device-side counters / flags block (one per bt_world) */
 enum {
-	CT_ANY_PROPOSAL = 0, /* doIteration's return value (ent.cpp:456,866) */
+	CT_ANY_PROPOSAL = 0, /* doIteration's return value (ent.cpp:456,866): == iter_id of the iteration that proposed */
 	CT_SERIAL_N,         /* entries in serialList */
 	CT_DEAD_N,           /* entries in deadList */
 	CT_ERROR,            /* BT_ERR_* raised on device */
@@ -96,6 +96,7 @@ enum {
 	CT_UNSUPPORTED = 33, /* times a handler without a device implementation would have run (lenient uploads only) */
 	CT_UNSUP_LAST = 34,  /* kind<<8 | catalog id of the last such handler (0 push, 1 pushed, 2 entPair, 3 crush, 4 pickup flush) */
 	CT_PAIR_BUILDS = 35, /* k_pairs runs that actually rebuilt the pair list */
+	CT_PAIR_OVERFLOW = 36, /* k_pairs produced more pairs than pair_cap: the iteration's kernels stood down */
 	CT_WORDS = 64
 };
 enum { SK_ITERS = 0, SK_CAND, SK_POS, SK_PUSH, SK_SERIAL, SK_CRUSH, SK_FUMBLE, SK_NUM };

@@ -496,21 +496,38 @@ static int do_physics(bt_world *w, bool gravity) {
 	w->ticks_since_build++;
 	i64 it = 0;
 	bool use_cache = w->pair_cache != 0;
+	/* 0: the host does not know whether the cache is valid (first iteration: integrate may have
+	 * invalidated it) -> conditional kernels decide on the device; 1: known stale; 2: known good */
+	int cache_state = 0;
+	auto pair_build = [&](int cond) -> int {
+		int r = refit(w, cond != 0);
+		if (r) return r;
+		LAUNCH(w, PK_PAIRS, k_pairs, std::min(nblk(W.n_leaves), pairs_wave()), BT_BLOCK, W);
+		return 0;
+	};
 	while (1) {
 		int r;
 		W.iter_id++;
 		if (use_cache) {
-			/* refit + pair search run only if CT_CACHE_INVALID is up (upload, rebuilt tree, or an
-			 * entity left the inflated box its pairs were found with); they test it on the device */
-			r = refit(w, true);
-			if (r) return r;
-			LAUNCH(w, PK_PAIRS, k_pairs, std::min(nblk(W.n_leaves), pairs_wave()), BT_BLOCK, W);
+			/* refit + pair search + neighbour lists run only if CT_CACHE_INVALID is up (upload, rebuilt
+			 * tree, or an entity left the inflated box its pairs were found with) */
+			/* state 1: the flag is up (the host has just read it), the same conditional kernels run */
+			if (cache_state != 2) { r = pair_build(1); if (r) return r; }
+			/* pair-parallel in every iteration.  (Measured alternative: walking per-entity neighbour
+			 * lists for the re-armed entities only -- 2.6x slower per launch at 1 M entities: one
+			 * thread per scanner serialises its 2-5 neighbours' gather chains, one thread per pair
+			 * keeps them all in flight.) */
 			LAUNCH(w, PK_NARROW, k_narrow, 148 * 8, 256, W);
 		} else {
 			r = refit(w, false);
 			if (r) return r;
 			LAUNCH(w, PK_COLLIDE, k_collide, nblk(W.n_leaves), BT_BLOCK, W);
 		}
+		/* resolve, speculatively (see k_decide) */
+		LAUNCH(w, PK_DECIDE, k_decide, nblk(n), BT_BLOCK, W);
+		LAUNCH(w, PK_PUSH, k_push, nblk(n), BT_BLOCK, W);
+		LAUNCH(w, PK_PUSH, k_push_serial, 1, 32, W);
+		LAUNCH(w, PK_POST, k_post, nblk(n), BT_BLOCK, W);
 		r = fetch_ctr(w);
 		if (r) return r;
 		if (use_cache && w->h_flag[CT_PAIR_BUILDS] != w->seen_pair_builds) {
@@ -518,26 +535,18 @@ static int do_physics(bt_world *w, bool gravity) {
 			w->stats.pairs_cached += (i64)w->h_flag[CT_PAIR_N];
 			w->seen_pair_builds = w->h_flag[CT_PAIR_BUILDS];
 		}
-		if (use_cache && w->h_flag[CT_PAIR_N] > (u32)W.pair_cap) {
-			/* more touching pairs than the buffer holds: this tick falls back to per-iteration
-			 * traversal; the narrow pass above saw only part of the pairs, so redo the iteration */
+		if (use_cache && w->h_flag[CT_PAIR_OVERFLOW]) {
+			/* more touching pairs than the buffer holds: every kernel of this iteration stood down;
+			 * redo it, and the rest of the tick, with per-iteration traversal */
 			use_cache = false;
 			w->pair_overflows++;
 			w->stats.pair_overflows++;
-			CK(cudaMemsetAsync(W.pend, 0, sizeof(u64) * (size_t)n, w->stream));
-			CK(cudaMemsetAsync(&W.ctr[CT_ANY_PROPOSAL], 0, sizeof(u32), w->stream));
+			CK(cudaMemsetAsync(&W.ctr[CT_PAIR_OVERFLOW], 0, sizeof(u32), w->stream));
 			continue;
 		}
-		if (!w->h_flag[CT_ANY_PROPOSAL]) {
-			/* last doIteration found nothing; it still cleared needsCollision (ent.cpp:459) */
-			CK(cudaMemsetAsync(W.needsCollision, 0, (size_t)n, w->stream));
-			break;
-		}
+		if (w->h_flag[CT_ANY_PROPOSAL] != (u32)W.iter_id) break; /* nothing proposed: doIteration returned 0 */
 		w->stats.iterations++;
-		LAUNCH(w, PK_DECIDE, k_decide, nblk(n), BT_BLOCK, W);
-		LAUNCH(w, PK_PUSH, k_push, nblk(n), BT_BLOCK, W);
-		LAUNCH(w, PK_PUSH, k_push_serial, 1, 32, W);
-		LAUNCH(w, PK_POST, k_post, nblk(n), BT_BLOCK, W);
+		cache_state = w->h_flag[CT_CACHE_INVALID] ? 1 : 2;
 		if (++it > w->max_iterations) {
 			snprintf(g_err, sizeof g_err, "doPhysics did not converge in %lld iterations", (long long)w->max_iterations);
 			return BT_ERR_OVERFLOW;

@@ -229,33 +229,34 @@ static int do_physics(Emu *E, bool gravity) {
 			if ((i32)pos < W.pair_cap) W.pairs[pos] = (u64)(u32)a | ((u64)(u32)b << 32);
 		}
 	};
+	int cache_state = 0, it = 0;
 	while (1) {
 		W.iter_id++;
 		u32 any = 0;
 		if (E->pair_cache) {
-			u32 before = W.ctr[CT_PAIR_BUILDS];
-			refit(E, 1);
-			{
-				HostEmit emit = {W};
-				std::vector<i32> o = order(E, W.n_leaves);
-				for (i32 t : o) t_pairs(W, t, stack.data(), 1, emit);
+			if (cache_state != 2) {
+				u32 before = W.ctr[CT_PAIR_BUILDS];
+				refit(E, 1);
+				{
+					HostEmit emit = {W};
+					std::vector<i32> o = order(E, W.n_leaves);
+					for (i32 t : o) t_pairs(W, t, stack.data(), 1, emit);
+				}
+				if ((i32)W.ctr[CT_PAIR_N] > W.pair_cap) return BT_ERR_OVERFLOW;
+				if (W.ctr[CT_PAIR_BUILDS] != before) E->pair_rebuilds++;
 			}
-			if ((i32)W.ctr[CT_PAIR_N] > W.pair_cap) return BT_ERR_OVERFLOW;
-			if (W.ctr[CT_PAIR_BUILDS] != before) E->pair_rebuilds++;
-			W.ctr[CT_CACHE_INVALID] = 0; /* k_narrow, block 0 thread 0 */
-			std::vector<i32> o = order(E, (i32)W.ctr[CT_PAIR_N]);
-			for (i32 p : o) t_narrow(W, W.pairs[p], E->st, any);
+			W.ctr[CT_CACHE_INVALID] = 0; /* narrow kernels, block 0 thread 0 */
+			{
+				std::vector<i32> o = order(E, (i32)W.ctr[CT_PAIR_N]);
+				for (i32 p : o) t_narrow(W, W.pairs[p], E->st, any);
+			}
 		} else {
 			refit(E, 0);
 			std::vector<i32> o = order(E, W.n_leaves);
 			for (i32 t : o) t_collide(W, t, stack.data(), 1, E->st, any);
 		}
 		if (W.ctr[CT_ERROR]) return -(int)W.ctr[CT_ERROR];
-		if (!any) {
-			for (i32 e = 0; e < n; e++) W.needsCollision[e] = 0;
-			break;
-		}
-		E->iterations++;
+		/* the resolve kernels run speculatively behind the narrow phase (no-ops without proposals) */
 		for (i32 e = 0; e < n; e++) t_decide(W, e);
 		{
 			std::vector<i32> o = order(E, n);
@@ -263,6 +264,10 @@ static int do_physics(Emu *E, bool gravity) {
 		}
 		if (W.ctr[CT_SERIAL_N]) t_push_serial(W, E->st);
 		for (i32 e = 0; e < n; e++) t_post(W, e);
+		if (!any) break;
+		E->iterations++;
+		cache_state = W.ctr[CT_CACHE_INVALID] ? 1 : 2;
+		it++;
 		if (++guard > 100000) return BT_ERR_OVERFLOW;
 	}
 	flush1(E, W.ctr[CT_FLUSH_HINT] != 0);
