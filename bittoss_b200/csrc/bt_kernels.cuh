@@ -32,6 +32,8 @@ static __device__ __forceinline__ void stats_flush(const DevWorld &W, const Loca
 }
 
 #define TID ((i32)(blockIdx.x * blockDim.x + threadIdx.x))
+/* the proposal stamp of iteration `id` lives in one of two slots, by parity */
+#define ANY_SLOT(id) (((id) & 1) ? CT_ANY_ODD : CT_ANY_PROPOSAL)
 /* grid-stride loop for the two kernels that usually return at once (k_refit, k_pairs are
  * conditional on CT_CACHE_INVALID): a one-wave grid makes the no-op launch ~3 us instead of
  * ~10 us at 1 M entities.  Measured: the always-busy per-iteration kernels (decide, push,
@@ -88,7 +90,7 @@ __global__ void __launch_bounds__(BT_BLOCK) k_collide(DevWorld W) {
 	u32 any = 0;
 	t_collide(W, TID, stacks + threadIdx.x, BT_BLOCK, st, any);
 	stats_flush(W, st);
-	if (__any_sync(0xffffffffu, any) && (threadIdx.x & 31) == 0) W.ctr[CT_ANY_PROPOSAL] = (u32)W.iter_id;
+	if (__any_sync(0xffffffffu, any) && (threadIdx.x & 31) == 0) W.ctr[ANY_SLOT(W.iter_id)] = (u32)W.iter_id;
 }
 /* Pair emitter: hits are buffered per thread and written with ONE atomic per warp flush
  * (warp-ballot/shuffle compaction) instead of one atomic per pair. */
@@ -166,20 +168,34 @@ static __device__ __forceinline__ void queue_push(u32 *q, u32 *count, int pred, 
  * (A two-step variant that re-packs the survivors of the cheap tests into full warps was
  * measured 20 % slower here: the step is bound by the latency of its gathers, which the
  * re-packing doubles, not by divergent ALU work.  k_push below does gain from re-packing.) */
-__global__ void __launch_bounds__(256) k_narrow(DevWorld W) {
+/* spec = 1: an iteration enqueued ahead of the host's knowledge (run-ahead).  It proceeds only
+ * if the previous iteration proposed something and no push has invalidated the pair cache;
+ * otherwise it records its id in CT_STOP and it and everything enqueued behind it stand down. */
+__global__ void __launch_bounds__(256) k_narrow(DevWorld W, int spec) {
 	LocalStats st = {0, 0, 0, 0, 0};
 	u32 any = 0;
+	if (spec) {
+		/* none of these words is written by this kernel while `go` holds (the stamp of THIS
+		 * iteration goes to the other parity slot), so early and late blocks agree */
+		int go = W.ctr[CT_STOP] == 0 && W.ctr[ANY_SLOT(W.iter_id - 1)] == (u32)(W.iter_id - 1) && !W.ctr[CT_CACHE_INVALID] &&
+		         !W.ctr[CT_PAIR_OVERFLOW];
+		if (!go) {
+			if (blockIdx.x == 0 && threadIdx.x == 0 && W.ctr[CT_STOP] == 0) W.ctr[CT_STOP] = (u32)W.iter_id;
+			return;
+		}
+	}
 	u32 np = W.ctr[CT_PAIR_N];
 	if (np > (u32)W.pair_cap) { /* incomplete pair list: nobody may act on it */
 		if (blockIdx.x == 0 && threadIdx.x == 0) W.ctr[CT_PAIR_OVERFLOW] = 1;
 		return;
 	}
-	/* k_refit / k_pairs of this iteration have consumed the flag; pushes may raise it again */
-	if (blockIdx.x == 0 && threadIdx.x == 0) W.ctr[CT_CACHE_INVALID] = 0;
+	/* k_refit / k_pairs of this iteration have consumed the flag; pushes may raise it again
+	 * (a run-ahead iteration only gets here with the flag down, and other blocks are reading it) */
+	if (!spec && blockIdx.x == 0 && threadIdx.x == 0) W.ctr[CT_CACHE_INVALID] = 0;
 	for (u32 p = blockIdx.x * blockDim.x + threadIdx.x; p < np; p += gridDim.x * blockDim.x)
 		t_narrow(W, W.pairs[p], st, any);
 	stats_flush(W, st);
-	if (__any_sync(0xffffffffu, any) && (threadIdx.x & 31) == 0) W.ctr[CT_ANY_PROPOSAL] = (u32)W.iter_id;
+	if (__any_sync(0xffffffffu, any) && (threadIdx.x & 31) == 0) W.ctr[ANY_SLOT(W.iter_id)] = (u32)W.iter_id;
 }
 
 /* The resolve kernels of an iteration are enqueued right behind its narrow phase, before the
@@ -187,7 +203,7 @@ __global__ void __launch_bounds__(256) k_narrow(DevWorld W) {
  * no proposal they are no-ops by construction; if the pair buffer overflowed they stand down
  * (CT_PAIR_OVERFLOW) and the host redoes the iteration through k_collide. */
 __global__ void __launch_bounds__(BT_BLOCK) k_decide(DevWorld W) {
-	if (W.ctr[CT_PAIR_OVERFLOW]) return;
+	if (W.ctr[CT_PAIR_OVERFLOW] | W.ctr[CT_STOP]) return;
 	t_decide(W, TID);
 }
 /* ready roots (typically 1 entity in 4) are re-packed into full warps before the push */
@@ -195,7 +211,7 @@ __global__ void __launch_bounds__(BT_BLOCK) k_push(DevWorld W) {
 	__shared__ u32 queue[BT_BLOCK];
 	__shared__ u32 qn;
 	LocalStats st = {0, 0, 0, 0, 0};
-	if (W.ctr[CT_PAIR_OVERFLOW]) return;
+	if (W.ctr[CT_PAIR_OVERFLOW] | W.ctr[CT_STOP]) return;
 	if (threadIdx.x == 0) qn = 0;
 	__syncthreads();
 	i32 e = TID;
@@ -206,14 +222,14 @@ __global__ void __launch_bounds__(BT_BLOCK) k_push(DevWorld W) {
 }
 __global__ void k_push_serial(DevWorld W) {
 	if (threadIdx.x != 0 || blockIdx.x != 0) return;
-	if (W.ctr[CT_SERIAL_N] == 0 || W.ctr[CT_PAIR_OVERFLOW]) return;
+	if (W.ctr[CT_SERIAL_N] == 0 || W.ctr[CT_PAIR_OVERFLOW] || W.ctr[CT_STOP]) return;
 	LocalStats st = {0, 0, 0, 0, 0};
 	t_push_serial(W, st);
 	u64 *s = (u64 *)&W.ctr[CT_STAT0];
 	s[SK_PUSH] += st.push; s[SK_SERIAL] += st.push; s[SK_CRUSH] += st.crush; s[SK_FUMBLE] += st.fumble;
 }
 __global__ void __launch_bounds__(BT_BLOCK) k_post(DevWorld W) {
-	if (W.ctr[CT_PAIR_OVERFLOW]) return;
+	if (W.ctr[CT_PAIR_OVERFLOW] | W.ctr[CT_STOP]) return;
 	t_post(W, TID);
 }
 

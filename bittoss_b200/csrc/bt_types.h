@@ -97,6 +97,9 @@ enum {
 	CT_UNSUP_LAST = 34,  /* kind<<8 | catalog id of the last such handler (0 push, 1 pushed, 2 entPair, 3 crush, 4 pickup flush) */
 	CT_PAIR_BUILDS = 35, /* k_pairs runs that actually rebuilt the pair list */
 	CT_PAIR_OVERFLOW = 36, /* k_pairs produced more pairs than pair_cap: the iteration's kernels stood down */
+	CT_STOP = 37,        /* run-ahead: iter_id of the first speculatively enqueued iteration that stood down */
+	CT_ANY_ODD = 38,     /* CT_ANY_PROPOSAL of odd iteration ids (even ones use slot 0): an iteration never
+	                      * reads the slot it is itself stamping */
 	CT_WORDS = 64
 };
 enum { SK_ITERS = 0, SK_CAND, SK_POS, SK_PUSH, SK_SERIAL, SK_CRUSH, SK_FUMBLE, SK_NUM };

@@ -76,6 +76,8 @@ struct bt_world {
 	i64 pair_cache; /* 1: cached candidate pairs (k_pairs + k_narrow); 0: traverse every iteration (k_collide) */
 	i64 pair_rebuilds, pair_overflows;
 	u32 seen_pair_builds, pair_builds_at_tree;
+	int predicted_iters; /* iterations (incl. the final empty one) the last tick needed: run-ahead depth */
+	i64 run_ahead;       /* option: 1 = enqueue the predicted iterations without waiting for the host */
 	bt_tick_stats stats;
 	bool profiling;
 	cudaEvent_t ev0, ev1;
@@ -242,6 +244,7 @@ int bt_world_set_option(bt_world *w, const char *name, int64_t value) {
 	if (!strcmp(name, "max_iterations")) { w->max_iterations = value; return BT_OK; }
 	if (!strcmp(name, "allow_unsupported")) { w->W.lenient = value != 0; return BT_OK; }
 	if (!strcmp(name, "pair_cache")) { w->pair_cache = value != 0; return BT_OK; }
+	if (!strcmp(name, "run_ahead")) { w->run_ahead = value != 0; return BT_OK; }
 	if (!strcmp(name, "cache_margin")) { w->W.margin = value < 0 ? 0 : (i32)value; return BT_OK; }
 	return BT_ERR_ARG;
 }
@@ -499,35 +502,55 @@ static int do_physics(bt_world *w, bool gravity) {
 	/* 0: the host does not know whether the cache is valid (first iteration: integrate may have
 	 * invalidated it) -> conditional kernels decide on the device; 1: known stale; 2: known good */
 	int cache_state = 0;
+	int iters_this_tick = 0;
+	CK(cudaMemsetAsync(&W.ctr[CT_STOP], 0, sizeof(u32), w->stream));
 	auto pair_build = [&](int cond) -> int {
 		int r = refit(w, cond != 0);
 		if (r) return r;
 		LAUNCH(w, PK_PAIRS, k_pairs, std::min(nblk(W.n_leaves), pairs_wave()), BT_BLOCK, W);
 		return 0;
 	};
+	auto resolve = [&]() {
+		/* speculative behind the narrow phase (see k_decide) */
+		LAUNCH(w, PK_DECIDE, k_decide, nblk(n), BT_BLOCK, W);
+		LAUNCH(w, PK_PUSH, k_push, nblk(n), BT_BLOCK, W);
+		LAUNCH(w, PK_PUSH, k_push_serial, 1, 32, W);
+		LAUNCH(w, PK_POST, k_post, nblk(n), BT_BLOCK, W);
+	};
 	while (1) {
 		int r;
 		W.iter_id++;
+		const i32 first_id = W.iter_id;
+		int enq = 1; /* iterations enqueued in this batch */
 		if (use_cache) {
-			/* refit + pair search + neighbour lists run only if CT_CACHE_INVALID is up (upload, rebuilt
-			 * tree, or an entity left the inflated box its pairs were found with) */
-			/* state 1: the flag is up (the host has just read it), the same conditional kernels run */
+			/* refit + pair search run only if CT_CACHE_INVALID is up (upload, rebuilt tree, or an
+			 * entity left the inflated box its pairs were found with); state 1: the flag is up (the
+			 * host has just read it), the same conditional kernels run */
 			if (cache_state != 2) { r = pair_build(1); if (r) return r; }
 			/* pair-parallel in every iteration.  (Measured alternative: walking per-entity neighbour
 			 * lists for the re-armed entities only -- 2.6x slower per launch at 1 M entities: one
 			 * thread per scanner serialises its 2-5 neighbours' gather chains, one thread per pair
 			 * keeps them all in flight.) */
-			LAUNCH(w, PK_NARROW, k_narrow, 148 * 8, 256, W);
+			LAUNCH(w, PK_NARROW, k_narrow, 148 * 8, 256, W, 0);
+			resolve();
+			if (w->run_ahead) {
+				/* run-ahead: as many further iterations as the previous tick needed, each of which
+				 * checks on the device that its predecessor proposed something and that the pair
+				 * cache is still good, and otherwise stands down together with everything behind it */
+				int more = (iters_this_tick == 0 ? w->predicted_iters - 1 : 2);
+				for (int k = 0; k < more; k++) {
+					W.iter_id++;
+					LAUNCH(w, PK_NARROW, k_narrow, 148 * 8, 256, W, 1);
+					resolve();
+					enq++;
+				}
+			}
 		} else {
 			r = refit(w, false);
 			if (r) return r;
 			LAUNCH(w, PK_COLLIDE, k_collide, nblk(W.n_leaves), BT_BLOCK, W);
+			resolve();
 		}
-		/* resolve, speculatively (see k_decide) */
-		LAUNCH(w, PK_DECIDE, k_decide, nblk(n), BT_BLOCK, W);
-		LAUNCH(w, PK_PUSH, k_push, nblk(n), BT_BLOCK, W);
-		LAUNCH(w, PK_PUSH, k_push_serial, 1, 32, W);
-		LAUNCH(w, PK_POST, k_post, nblk(n), BT_BLOCK, W);
 		r = fetch_ctr(w);
 		if (r) return r;
 		if (use_cache && w->h_flag[CT_PAIR_BUILDS] != w->seen_pair_builds) {
@@ -536,22 +559,31 @@ static int do_physics(bt_world *w, bool gravity) {
 			w->seen_pair_builds = w->h_flag[CT_PAIR_BUILDS];
 		}
 		if (use_cache && w->h_flag[CT_PAIR_OVERFLOW]) {
-			/* more touching pairs than the buffer holds: every kernel of this iteration stood down;
+			/* more touching pairs than the buffer holds: every kernel of this batch stood down;
 			 * redo it, and the rest of the tick, with per-iteration traversal */
 			use_cache = false;
 			w->pair_overflows++;
 			w->stats.pair_overflows++;
-			CK(cudaMemsetAsync(&W.ctr[CT_PAIR_OVERFLOW], 0, sizeof(u32), w->stream));
+			CK(cudaMemsetAsync(&W.ctr[CT_PAIR_OVERFLOW], 0, 2 * sizeof(u32), w->stream)); /* + CT_STOP */
 			continue;
 		}
-		if (w->h_flag[CT_ANY_PROPOSAL] != (u32)W.iter_id) break; /* nothing proposed: doIteration returned 0 */
-		w->stats.iterations++;
+		/* which of the enqueued iterations actually ran */
+		const u32 stop = w->h_flag[CT_STOP];
+		const i32 last_run = stop ? (i32)stop - 1 : first_id + enq - 1;
+		const bool last_proposed = w->h_flag[ANY_SLOT(last_run)] == (u32)last_run;
+		const int ran = last_run - first_id + 1;
+		w->stats.iterations += ran - (last_proposed ? 0 : 1);
+		iters_this_tick += ran;
+		it += ran;
+		if (!last_proposed) break; /* doIteration returned 0 (ent.cpp:866) */
+		if (stop) CK(cudaMemsetAsync(&W.ctr[CT_STOP], 0, sizeof(u32), w->stream));
 		cache_state = w->h_flag[CT_CACHE_INVALID] ? 1 : 2;
-		if (++it > w->max_iterations) {
+		if (it > w->max_iterations) {
 			snprintf(g_err, sizeof g_err, "doPhysics did not converge in %lld iterations", (long long)w->max_iterations);
 			return BT_ERR_OVERFLOW;
 		}
 	}
+	w->predicted_iters = iters_this_tick > 0 ? iters_this_tick : 1;
 	if (w->pair_cache && !use_cache) { /* overflowed: the partial pair list must not be reused */
 		int rr = raise_cache_invalid(w);
 		if (rr) return rr;

@@ -170,3 +170,22 @@ def test_cuda_host_exchange_roundtrip(bt, oracle_lib):
     st = w.download()
     assert np.array_equal(c, st.vec("center")) and np.array_equal(v, st.vec("vel"))
     w.close()
+
+
+def test_cuda_schedule_variants_agree_at_scale(bt, oracle_lib):
+    """200k cubes, 90 ticks: run-ahead on/off x pair cache on/off x rebuild period must give one
+    hash stream (grids larger than one wave, many blocks, stand-downs), and it must be the oracle's"""
+    wa = bt.synth_boxstack(200000, 4, 777, 64, 60)
+    streams = []
+    for run_ahead, cache, period in ((1, 1, 16), (0, 1, 16), (1, 1, 3), (0, 0, 5)):
+        w = bt.World(wa)
+        w.set_option("run_ahead", run_ahead)
+        w.set_option("pair_cache", cache)
+        w.set_option("rebuild_every", period)
+        streams.append([int(x) for x in w.tick(90, hashes=True)[:, 0]])
+        w.close()
+    assert streams[0] == streams[1] == streams[2] == streams[3]
+    ow = oracle_lib.create(wa)
+    for t in range(10):
+        ow.step(31)
+        assert ow.hash()[0] == streams[0][t], t
