@@ -129,12 +129,14 @@ static BT_HD i32 t_raycast(const DevWorld &W, i32 p, const i32 look_in[3], i32 *
 /* origin/winner are LIVE RANKS (oldest-first order of bt_world_download); rank2slot /
  * slot2rank translate to device slots. */
 __global__ void __launch_bounds__(128) k_raycast(DevWorld W, const i32 *origin, const i32 *look, i32 n_rays,
-                                                  i32 *winner, const i32 *rank2slot, const i32 *slot2rank) {
+                                                  i32 *winner, const i32 *rank2slot, const i32 *slot2rank, i32 n_live) {
 	__shared__ i32 stacks[BT_STACK * 128];
 	i32 i = (i32)(blockIdx.x * blockDim.x + threadIdx.x);
 	if (i >= n_rays) return;
 	i32 lk[3] = {look[3 * i], look[3 * i + 1], look[3 * i + 2]};
-	i32 win = t_raycast(W, rank2slot[origin[i]], lk, stacks + threadIdx.x, 128);
+	i32 og = origin[i];
+	if (og < 0 || og >= n_live) { winner[i] = -1; return; } /* not a live entity: no caster, no hit */
+	i32 win = t_raycast(W, rank2slot[og], lk, stacks + threadIdx.x, 128);
 	winner[i] = win >= 0 ? slot2rank[win] : -1;
 }
 

@@ -953,7 +953,7 @@ static int ray_build(bt_world *w) {
 static int ray_cast(bt_world *w, const i32 *d_origin, const i32 *d_look, i32 n_rays, i32 *d_winner) {
 	ray_swap(w);
 	LAUNCH(w, PK_RAYCAST, k_raycast, nblk(n_rays, 128), 128, w->W, d_origin, d_look, n_rays, d_winner,
-	       w->ray.rank2slot, w->ray.slot2rank);
+	       w->ray.rank2slot, w->ray.slot2rank, (i32)w->stats.live_ents);
 	ray_swap(w);
 	return 0;
 }

@@ -353,6 +353,7 @@ int bte_raycast(Emu *E, const int32_t *origin, const int32_t *look, int32_t n_ra
 	std::vector<i32> stack(BT_STACK);
 	for (i32 i = 0; i < n_rays; i++) {
 		i32 lk[3] = {look[3 * i], look[3 * i + 1], look[3 * i + 2]};
+		if (origin[i] < 0 || origin[i] >= (i32)rank2slot.size()) { winner[i] = -1; continue; }
 		i32 win = t_raycast(W, rank2slot[origin[i]], lk, stack.data(), 1);
 		winner[i] = win >= 0 ? slot2rank[win] : -1;
 	}
