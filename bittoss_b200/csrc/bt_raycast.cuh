@@ -43,7 +43,7 @@ static BT_HD int ray_hit_ent(const i32 pos[3], const i32 look[3], const i32 flip
 /* conservative slab test of a node box against the ray, pruned by the best hit so far:
  * a subtree is skipped only if every entity in it would enter strictly after `best`. */
 static BT_HD int ray_hit_box(const i32 pos[3], const i32 look[3], const i32 flip[3], const i32 lo[3], const i32 hi[3],
-                             const Rat &best) {
+                             const Rat &best, Rat *entry) {
 	Rat lower = {0, 1};
 	Rat upper = {INT32_MAX, 1};
 #pragma unroll
@@ -64,6 +64,7 @@ static BT_HD int ray_hit_box(const i32 pos[3], const i32 look[3], const i32 flip
 		if (rat_lt(upper, lower)) return 0; /* empty even when touching is allowed */
 	}
 	if (rat_lt(best, lower)) return 0; /* enters strictly after the best hit */
+	*entry = lower; /* where the ray enters the box: orders the two children front to back */
 	return 1;
 }
 
@@ -103,17 +104,21 @@ static BT_HD i32 t_raycast(const DevWorld &W, i32 p, const i32 look_in[3], i32 *
 		u32 wl = (u32)N.d.z, wr = (u32)N.d.w;
 		const i32 llo[3] = {N.a.x, N.a.y, N.a.z}, lhi[3] = {N.a.w, N.b.x, N.b.y};
 		const i32 rlo[3] = {N.b.z, N.b.w, N.c.x}, rhi[3] = {N.c.y, N.c.z, N.c.w};
-		int ovL = (wl & 0xffff) <= wp && wp <= (wl >> 16) && ray_hit_box(pos, look, flip, llo, lhi, best);
-		int ovR = (wr & 0xffff) <= wp && wp <= (wr >> 16) && ray_hit_box(pos, look, flip, rlo, rhi, best);
+		Rat eL = {0, 1}, eR = {0, 1};
+		int ovL = (wl & 0xffff) <= wp && wp <= (wl >> 16) && ray_hit_box(pos, look, flip, llo, lhi, best, &eL);
+		int ovR = (wr & 0xffff) <= wp && wp <= (wr >> 16) && ray_hit_box(pos, look, flip, rlo, rhi, best, &eR);
 		if (ovL && li < 0) RAY_LEAF(~li);
 		if (ovR && ri < 0) RAY_LEAF(~ri);
 		int goL = ovL && li >= 0, goR = ovR && ri >= 0;
-		if (goL) {
+		if (goL && goR) {
+			/* nearer child first: its hits shrink `best` and prune the farther one when it is
+			 * popped (its children are tested against the new best).  Order only affects speed. */
+			int rightFirst = rat_lt(eR, eL);
+			node = rightFirst ? ri : li;
+			if (sp < BT_STACK) stack[(sp++) * stride] = rightFirst ? li : ri;
+			else W.ctr[CT_ERROR] = (u32)(-BT_ERR_OVERFLOW);
+		} else if (goL) {
 			node = li;
-			if (goR) {
-				if (sp < BT_STACK) stack[(sp++) * stride] = ri;
-				else W.ctr[CT_ERROR] = (u32)(-BT_ERR_OVERFLOW);
-			}
 		} else if (goR) {
 			node = ri;
 		} else {
