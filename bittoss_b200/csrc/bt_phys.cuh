@@ -817,13 +817,15 @@ static BT_HD void t_narrow(const DevWorld &W, u64 pr, LocalStats &st, u32 &any) 
 	i32 a = (i32)(u32)pr, b = (i32)(pr >> 32);
 	int na = W.needsCollision[a], nb = W.needsCollision[b];
 	if (!(na | nb)) return; /* the common case after the first iteration: two byte loads */
-	int alive = W.inList[a] & W.hasBox[a] & W.inList[b] & W.hasBox[b]; /* `o->dead` ent.cpp:455 */
-	if (!alive) return;
+	/* everything else in ONE batch of independent loads (no branch in between, or the compiler
+	 * must wait for each test before it may issue the next gather) */
+	int ia = W.inList[a], ba = W.hasBox[a], ib = W.inList[b], bb = W.hasBox[b];
 	u32 ta = W.type[a], ca = W.collide[a], tb = W.type[b], cb = W.collide[b];
-	if (!((tb & ca) | (ta & cb))) { st.cand += (u32)(na + nb); return; }
 	i32 ra = W.holdRoot[a], rb = W.holdRoot[b];
 	u32 ha = W.hphys[a], hb = W.hphys[b];
 	EntGeo ga = bt_geo(W, a), gb = bt_geo(W, b);
+	if (!(ia & ba & ib & bb)) return; /* `o->dead` ent.cpp:455 */
+	if (!((tb & ca) | (ta & cb))) { st.cand += (u32)(na + nb); return; }
 #pragma unroll 1
 	for (int k = 0; k < 2; k++) {
 		if (na) {
