@@ -35,6 +35,7 @@ static inline void bt_fence() {}
 static inline int bt_clz32(u32 x) { return x ? __builtin_clz(x) : 32; }
 static inline int bt_clz64(u64 x) { return x ? __builtin_clzll(x) : 64; }
 static inline int bt_abs(int x) { return x < 0 ? -x : x; }
+static inline void bt_prefetch(const void *) {}
 #else
 static BT_HD u64 bt_cas64(u64 *p, u64 cmp, u64 val) { return atomicCAS(p, cmp, val); }
 static BT_HD u32 bt_add32(u32 *p, u32 v) { return atomicAdd(p, v); }
@@ -48,6 +49,8 @@ static BT_HD void bt_fence() { __threadfence(); }
 static BT_HD int bt_clz32(u32 x) { return __clz((int)x); }
 static BT_HD int bt_clz64(u64 x) { return __clzll((long long)x); }
 static BT_HD int bt_abs(int x) { return x < 0 ? -x : x; }
+/* start a line on its way to L1 without waiting for it */
+static BT_HD void bt_prefetch(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 #endif
 
 struct LocalStats {
@@ -990,6 +993,11 @@ static BT_HD void bt_push(const DevWorld &W, const Coll &c, u32 key, LocalStats 
 	st.push++;
 	i32 e = c.leaf, o = c.buddy;
 	int axis = c.axis, dir = c.dir;
+	/* the push is a chain of dependent gathers through handler code the compiler cannot
+	 * reorder; start everything it is going to touch on its way to L1 now */
+	bt_prefetch(&W.forced[e]); bt_prefetch(&W.friction[e]); bt_prefetch(&W.holder[e]); bt_prefetch(&W.hphys[e]);
+	bt_prefetch(&W.hphys[o]); bt_prefetch(&W.type[o]); bt_prefetch(&W.ibox[e]); bt_prefetch(&W.old[e]);
+	bt_prefetch(&W.forcedHoldees[e]); bt_prefetch(&W.holdee[e]); bt_prefetch(&W.hasBox[e]); bt_prefetch(&W.LLn[e]);
 	i32 displacement = (bt_get3(W.center[o], axis) - bt_get3(W.center[e], axis)) * dir + bt_get3(W.radius[e], axis) +
 	                   bt_get3(W.radius[o], axis);
 	i32 accel = (bt_get3(W.vel[o], axis) - bt_get3(W.vel[e], axis)) * dir;
