@@ -69,6 +69,8 @@ def lib():
     L.bt_last_error.restype = C.c_char_p
     L.bt_world_create.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_int32, C.c_int32, C.c_int32, C.c_int32]
     L.bt_world_destroy.argtypes = [C.c_void_p]
+    L.bt_world_dup.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
+    L.bt_world_assign.argtypes = [C.c_void_p, C.c_void_p]
     L.bt_world_upload.argtypes = [C.c_void_p, C.POINTER(BtWorldDesc)]
     L.bt_world_count.argtypes = [C.c_void_p, _i32p, _i32p, _i32p]
     L.bt_world_download.argtypes = [C.c_void_p, C.POINTER(BtWorldDesc)]
@@ -173,6 +175,18 @@ class World:
 
     def __del__(self):
         self.close()
+
+    def dup(self):
+        """dup(gs) (ent.cpp:1135-1200): an independent copy of this world, device to device."""
+        other = World.__new__(World)
+        other.L, other.h, other.n_worlds = self.L, C.c_void_p(), self.n_worlds
+        _ck(self.L.bt_world_dup(self.h, C.byref(other.h)), "bt_world_dup")
+        return other
+
+    def assign(self, src):
+        """self := src (same capacities), the rollback restore."""
+        _ck(self.L.bt_world_assign(self.h, src.h), "bt_world_assign")
+        self.n_worlds = src.n_worlds
 
     def upload(self, wa: WorldArrays):
         _ck(self.L.bt_world_upload(self.h, wa.ref()), "bt_world_upload")

@@ -64,6 +64,7 @@ struct bt_world {
 	i32 cap_ents, cap_sliders, cap_wires, cap_worlds;
 	DevWorld W;
 	std::vector<void *> allocs;
+	std::vector<size_t> alloc_bytes;
 	u32 *h_flag; /* pinned, CT_WORDS words */
 	u64 *d_hsum; u32 *d_hcnt;
 	u32 *d_sorthist; int sorthist_len;
@@ -99,6 +100,7 @@ template <typename T> static int dalloc(bt_world *w, T **p, size_t count) {
 	}
 	cudaMemset(q, 0, sizeof(T) * (count ? count : 1));
 	w->allocs.push_back(q);
+	w->alloc_bytes.push_back(sizeof(T) * (count ? count : 1));
 	*p = (T *)q;
 	return 0;
 }
@@ -772,6 +774,57 @@ int bt_world_unsupported(bt_world *w, uint32_t *per_world) {
 	CK(cudaStreamSynchronize(w->stream));
 	CK(cudaMemcpy(per_world, w->W.wunsup, sizeof(u32) * (size_t)w->W.n_worlds, cudaMemcpyDeviceToHost));
 	return BT_OK;
+}
+
+/* ---------------------------------------------------------------- dup (ent.cpp:1135-1200) */
+} /* extern "C" */
+
+/* every device pointer inside a POD block is re-based from src's allocation to dst's */
+static void rebase(void *block, size_t bytes, const bt_world *src, const bt_world *dst) {
+	uintptr_t *wd = (uintptr_t *)block;
+	for (size_t i = 0; i + sizeof(uintptr_t) <= bytes; i += sizeof(uintptr_t), wd++)
+		for (size_t a = 0; a < src->allocs.size(); a++)
+			if (*wd == (uintptr_t)src->allocs[a]) { *wd = (uintptr_t)dst->allocs[a]; break; }
+}
+
+extern "C" {
+
+/* dst := src.  Both worlds must have been created with the same capacities on the same
+ * device (then their allocation lists line up); the copy is device-to-device on dst's stream. */
+int bt_world_assign(bt_world *dst, bt_world *src) {
+	if (!dst || !src || dst == src) return BT_ERR_ARG;
+	if (dst->device != src->device || dst->cap_ents != src->cap_ents || dst->cap_sliders != src->cap_sliders ||
+	    dst->cap_wires != src->cap_wires || dst->cap_worlds != src->cap_worlds || dst->allocs.size() != src->allocs.size())
+		return BT_ERR_CAPACITY;
+	CK(cudaSetDevice(src->device));
+	CK(cudaStreamSynchronize(src->stream));
+	for (size_t a = 0; a < src->allocs.size(); a++)
+		CK(cudaMemcpyAsync(dst->allocs[a], src->allocs[a], src->alloc_bytes[a], cudaMemcpyDeviceToDevice, dst->stream));
+	dst->W = src->W;
+	rebase(&dst->W, sizeof(dst->W), src, dst);
+	dst->ray = src->ray;
+	rebase(&dst->ray, sizeof(dst->ray), src, dst);
+	dst->tree_valid = src->tree_valid; dst->deltas_pending = src->deltas_pending;
+	dst->full_flush_left = src->full_flush_left; dst->ctrls_fused = src->ctrls_fused;
+	dst->ticks_since_build = src->ticks_since_build; dst->rebuild_every = src->rebuild_every;
+	dst->max_iterations = src->max_iterations; dst->pair_cache = src->pair_cache;
+	dst->seen_pair_builds = src->seen_pair_builds; dst->pair_builds_at_tree = src->pair_builds_at_tree;
+	dst->predicted_iters = src->predicted_iters; dst->run_ahead = src->run_ahead;
+	dst->stats = src->stats; dst->up_root_order = src->up_root_order;
+	dst->ray_valid = src->ray_valid; dst->ranks_valid = src->ranks_valid;
+	CK(cudaStreamSynchronize(dst->stream));
+	return BT_OK;
+}
+
+/* dup(gs) ent.cpp:1135-1200: a second, independent world in the same state (cached pairs and
+ * tree included, like the reference clones velbox's cached intersects). */
+int bt_world_dup(bt_world *src, bt_world **out) {
+	if (!src || !out) return BT_ERR_ARG;
+	int r = bt_world_create(out, src->device, src->cap_ents, src->cap_sliders, src->cap_wires, src->cap_worlds);
+	if (r) return r;
+	r = bt_world_assign(*out, src);
+	if (r) { bt_world_destroy(*out); *out = NULL; }
+	return r;
 }
 
 int bt_world_profile_enable(bt_world *w, int on) {

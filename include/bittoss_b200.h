@@ -145,6 +145,11 @@ int bt_device_count(void); /* >=0, or BT_ERR_NO_DEVICE */
 int bt_world_create(bt_world **out, int device, int32_t max_ents, int32_t max_sliders,
                     int32_t max_wires, int32_t max_worlds);
 void bt_world_destroy(bt_world *w);
+/* dup(gs) (ent.h:222, ent.cpp:1135-1200; the rollback loop main.cpp:1265 clones rootState into
+ * phantomState every frame): a second world in the same state, device-to-device.
+ * bt_world_assign overwrites an existing world of identical capacities (no allocation). */
+int bt_world_dup(bt_world *src, bt_world **out);
+int bt_world_assign(bt_world *dst, bt_world *src);
 /* Host AoS -> device SoA. Fails with BT_ERR_UNSUPPORTED if an entity names a
  * collision-path handler ID that has no device implementation. */
 int bt_world_upload(bt_world *w, const bt_world_desc *desc);

@@ -189,3 +189,26 @@ def test_cuda_schedule_variants_agree_at_scale(bt, oracle_lib):
     for t in range(10):
         ow.step(31)
         assert ow.hash()[0] == streams[0][t], t
+
+
+def test_cuda_dup_and_rollback(bt):
+    """bt_world_dup / bt_world_assign = dup() (ent.cpp:1135-1200): the copy evolves identically,
+    and restoring a snapshot replays the same hashes (the client's rollback loop, main.cpp:1265-1280)"""
+    wa, ref = load_scenario("spider_kick")
+    w = bt.World(wa)
+    w.tick(7)
+    snap = w.dup()
+    a = [int(x) for x in w.tick(15, hashes=True)[:, 0]]
+    b = [int(x) for x in snap.tick(15, hashes=True)[:, 0]]
+    assert a == b == [int(x) for x in ref[7:22]]
+    snap2 = w.dup()          # state at tick 22
+    w.tick(5)
+    w.assign(snap2)          # roll back to tick 22
+    c = [int(x) for x in w.tick(10, hashes=True)[:, 0]]
+    assert c == [int(x) for x in ref[22:32]]
+    big = bt.World(bt.synth_boxstack(50000))
+    big.tick(20)
+    twin = big.dup()
+    assert [int(x) for x in big.tick(10, hashes=True)[:, 0]] == [int(x) for x in twin.tick(10, hashes=True)[:, 0]]
+    for x in (w, snap, snap2, big, twin):
+        x.close()
