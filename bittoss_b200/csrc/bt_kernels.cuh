@@ -50,6 +50,7 @@ __global__ void __launch_bounds__(BT_BLOCK) k_flush_serial(DevWorld W) {
 }
 __global__ void __launch_bounds__(BT_BLOCK) k_flush_misc(DevWorld W) { t_flush_misc(W, TID); }
 __global__ void __launch_bounds__(BT_BLOCK) k_gravity(DevWorld W) { t_gravity(W, TID); }
+__global__ void __launch_bounds__(BT_BLOCK) k_world_rules(DevWorld W) { t_world_rules(W, TID); }
 __global__ void __launch_bounds__(BT_BLOCK) k_flush2_apply(DevWorld W) { t_flush2_apply(W, TID); }
 __global__ void __launch_bounds__(BT_BLOCK) k_zero_deltas(DevWorld W) { t_zero_deltas(W, TID); }
 __global__ void __launch_bounds__(BT_BLOCK) k_integrate(DevWorld W) { t_integrate(W, TID); }

@@ -1185,6 +1185,42 @@ static BT_HD void t_flush_misc(const DevWorld &W, i32 e) {
 	W.wire_cnt[e] = cnt;
 }
 
+/* world rules that are per-entity scans: crush() effects.cpp:48-60 (doCrushtainer 64000,
+ * doBigCrushtainer 2560000), doLava :43-46, bounce() :71-92.  uDead = dead_max[flip] |= 1
+ * (entUpdaters.c:21-23), picked up by the next flush1. */
+#define EFFECT_CRUSH 1
+#define EFFECT_CRUSH_BIG 2
+#define EFFECT_LAVA 16
+#define EFFECT_BOUNCE 32
+static BT_HD int bt_outside(const int4 &c, i32 r) { return bt_abs(c.x) > r * 2 || bt_abs(c.y) > r || bt_abs(c.z) > r; }
+static BT_HD void t_world_rules(const DevWorld &W, i32 e) {
+	if (e >= W.n || !W.inList[e]) return;
+	int g = W.world[e];
+	i32 rules = W.gamerules[g];
+	if (!(rules & (EFFECT_CRUSH | EFFECT_CRUSH_BIG | EFFECT_LAVA | EFFECT_BOUNCE))) return;
+	int4 c = W.center[e];
+	int die = 0;
+	if ((rules & EFFECT_CRUSH) && bt_outside(c, 64000)) die = 1;
+	if ((rules & EFFECT_CRUSH_BIG) && bt_outside(c, 2560000)) die = 1;
+	if ((rules & EFFECT_LAVA) && c.z > 64000) die = 1;
+	if ((rules & EFFECT_BOUNCE) && bt_outside(c, 64000)) {
+		if (W.type[e] & T_TERRAIN) {
+			int4 v = W.vel[e];
+			if ((c.x > 128000 && v.x > 0) || (c.x < -128000 && v.x < 0)) v.x = -v.x;
+			if ((c.y > 64000 && v.y > 0) || (c.y < -64000 && v.y < 0)) v.y = -v.y;
+			if ((c.z > 64000 && v.z > 0) || (c.z < -64000 && v.z < 0)) v.z = -v.z;
+			W.vel[e] = v;
+		} else {
+			die = 1;
+		}
+	}
+	if (die) {
+		if (W.flip[g]) W.dead_max1[e] |= 1;
+		else W.dead_max0[e] |= 1;
+		W.ctr[CT_FLUSH_HINT] = 1;
+	}
+}
+
 /* doGravity effects.cpp:35-41 */
 static BT_HD void t_gravity(const DevWorld &W, i32 e) {
 	if (e >= W.n || !W.inList[e] || W.holder[e] >= 0) return;

@@ -68,6 +68,7 @@ struct bt_world {
 	u32 *h_flag; /* pinned, CT_WORDS words */
 	u64 *d_hsum; u32 *d_hcnt;
 	u32 *d_sorthist; int sorthist_len;
+	bool any_rules; /* some world's gamerules contain a scan rule (crush / lava / bounce) */
 	bool tree_valid, deltas_pending;
 	int full_flush_left; /* flush1 calls that must run in full (after an upload); afterwards CT_FLUSH_HINT decides */
 	bool ctrls_fused;    /* flushCtrls of this step rides in k_begin_fused */
@@ -377,6 +378,8 @@ int bt_world_upload(bt_world *w, const bt_world_desc *d) {
 #undef UPRAW
 	w->up_root_order.assign(d->root_order, d->root_order + n);
 	w->tree_valid = false; w->ray_valid = false; w->ranks_valid = false;
+	w->any_rules = false;
+	for (int g = 0; g < nw; g++) w->any_rules = w->any_rules || (d->w_gamerules[g] & (1 | 2 | 16 | 32));
 	w->deltas_pending = deltas;
 	w->full_flush_left = 2; /* both dead_max slots of the upload get looked at */
 	w->ticks_since_build = 0;
@@ -613,6 +616,11 @@ int bt_world_step(bt_world *w, uint32_t phases) {
 	CK(cudaSetDevice(w->device));
 	DevWorld &W = w->W;
 	const i32 n = W.n;
+	if (phases & BT_PHASE_WORLD_RULES) {
+		LAUNCH(w, PK_PRE, k_world_rules, nblk(n), BT_BLOCK, W);
+		/* a death requested here is flushed by this step's prepPhysics: make sure it looks */
+		if (w->full_flush_left < 1) w->full_flush_left = 1;
+	}
 	/* flushCtrls rides in k_begin_fused when this step also integrates on the fast path */
 	w->ctrls_fused = (phases & BT_PHASE_CTRLS) && (phases & BT_PHASE_PHYSICS) && !w->deltas_pending;
 	if ((phases & BT_PHASE_CTRLS) && !w->ctrls_fused) LAUNCH(w, PK_PRE, k_pre, nblk(n), BT_BLOCK, W, phases);
@@ -668,7 +676,7 @@ int bt_world_hash(bt_world *w, uint64_t *out) {
 int bt_world_tick(bt_world *w, int32_t n_ticks, uint64_t *hashes) {
 	if (!w || n_ticks < 0) return BT_ERR_ARG;
 	for (int t = 0; t < n_ticks; t++) {
-		int r = bt_world_step(w, BT_PHASE_ALL);
+		int r = bt_world_step(w, BT_PHASE_ALL | (w->any_rules ? BT_PHASE_WORLD_RULES : 0u));
 		if (r) return r;
 		if (hashes) {
 			r = hash_into(w, hashes + (size_t)t * w->W.n_worlds);
@@ -690,7 +698,8 @@ int bt_world_tick_timed(bt_world *w, int32_t n_ticks, float *ms) {
 	CK(cudaStreamSynchronize(w->stream));
 	CK(cudaEventRecord(a, w->stream));
 	int r = BT_OK;
-	for (int t = 0; t < n_ticks && r == BT_OK; t++) r = bt_world_step(w, BT_PHASE_ALL);
+	for (int t = 0; t < n_ticks && r == BT_OK; t++)
+		r = bt_world_step(w, BT_PHASE_ALL | (w->any_rules ? BT_PHASE_WORLD_RULES : 0u));
 	cudaEventRecord(b, w->stream);
 	cudaEventSynchronize(b);
 	cudaEventElapsedTime(ms, a, b);
@@ -804,7 +813,7 @@ int bt_world_assign(bt_world *dst, bt_world *src) {
 	rebase(&dst->W, sizeof(dst->W), src, dst);
 	dst->ray = src->ray;
 	rebase(&dst->ray, sizeof(dst->ray), src, dst);
-	dst->tree_valid = src->tree_valid; dst->deltas_pending = src->deltas_pending;
+	dst->tree_valid = src->tree_valid; dst->deltas_pending = src->deltas_pending; dst->any_rules = src->any_rules;
 	dst->full_flush_left = src->full_flush_left; dst->ctrls_fused = src->ctrls_fused;
 	dst->ticks_since_build = src->ticks_since_build; dst->rebuild_every = src->rebuild_every;
 	dst->max_iterations = src->max_iterations; dst->pair_cache = src->pair_cache;

@@ -102,6 +102,12 @@ typedef struct bt_world_desc {
 #define BT_PHASE_PHYSICS 8u  /* doPhysics                      ent.cpp:842-911     */
 #define BT_PHASE_FINISH 16u  /* finishStep = clearDeads        ent.cpp:913-915     */
 #define BT_PHASE_ALL    31u
+/* world rules of doWholeStep main.cpp:1030-1034 that are plain scans: doCrushtainer /
+ * doBigCrushtainer / doLava / doBouncetainer (effects.cpp:43-96).  Runs before everything else.
+ * Not part of BT_PHASE_ALL (a host that runs its own rules must not get them twice);
+ * bt_world_tick adds it when a world's gamerules ask for one of them.  createDebris
+ * (EFFECT_BLOCKS) creates entities and stays on the host. */
+#define BT_PHASE_WORLD_RULES 32u
 
 typedef struct bt_tick_stats {
 	int64_t ticks;

@@ -1201,9 +1201,34 @@ void bto_destroy(World *w) {
 	free(w);
 }
 
+/* world rules that are plain scans (main.cpp:1030-1034): crush() effects.cpp:48-60, doLava
+ * :43-46, bounce() :71-92; uDead entUpdaters.c:21-23 */
+static int outside(const i32 *c, i32 r) { return abs(c[0]) > r * 2 || abs(c[1]) > r || abs(c[2]) > r; }
+static void worldRules(World *w, int g) {
+	i32 rules = w->gamerules[g];
+	for (i32 e = w->wend[g] - 1; e >= w->wbegin[g]; e--) {
+		if (!w->inList[e]) continue;
+		if ((rules & 1) && outside(w->center[e], 64000)) w->dead_max[e][w->flip[g]] |= 1;
+		if ((rules & 2) && outside(w->center[e], 2560000)) w->dead_max[e][w->flip[g]] |= 1;
+		if ((rules & 16) && w->center[e][2] > 64000) w->dead_max[e][w->flip[g]] |= 1;
+		if ((rules & 32) && outside(w->center[e], 64000)) {
+			if (w->type[e] & T_TERRAIN) {
+				for (int i = 0; i < 3; i++) {
+					i32 bound = i ? 64000 : 128000;
+					if ((w->center[e][i] > bound && w->vel[e][i] > 0) || (w->center[e][i] < -bound && w->vel[e][i] < 0))
+						w->vel[e][i] *= -1;
+				}
+			} else {
+				w->dead_max[e][w->flip[g]] |= 1;
+			}
+		}
+	}
+}
+
 /* one step of the phases given, in doWholeStep order (main.cpp:1072-1097) */
 int bto_step(World *w, uint32_t phases) {
 	for (int g = 0; g < w->n_worlds; g++) {
+		if (phases & BT_PHASE_WORLD_RULES) worldRules(w, g);
 		if (phases & BT_PHASE_CTRLS) /* flushCtrls ent.cpp:32-37, 817-821 */
 			for (i32 i = w->wbegin[g]; i < w->wend[g]; i++)
 				if (w->inList[i])

@@ -376,6 +376,12 @@ void btref_pre_physics(int mode) {
 			}
 		}
 	} else {
+		if (mode == 2) { /* physics-only plus the scan rules of main.cpp:1030-1034 */
+			if (gs->gamerules & EFFECT_CRUSH) doCrushtainer(gs);
+			if (gs->gamerules & EFFECT_CRUSH_BIG) doBigCrushtainer(gs);
+			if (gs->gamerules & EFFECT_LAVA) doLava(gs);
+			if (gs->gamerules & EFFECT_BOUNCE) doBouncetainer(gs);
+		}
 		for (ent *e = gs->ents; e; e = e->ll.n) flushCtrls(e);
 	}
 	prepPhysics(gs);

@@ -279,6 +279,10 @@ static int do_physics(Emu *E, bool gravity) {
 
 int bte_step(Emu *E, uint32_t phases) {
 	DevWorld &W = E->W;
+	if (phases & BT_PHASE_WORLD_RULES) {
+		for (i32 e = 0; e < W.n; e++) t_world_rules(W, e);
+		if (E->full_flush_left < 1) E->full_flush_left = 1;
+	}
 	E->ctrls_fused = (phases & BT_PHASE_CTRLS) && (phases & BT_PHASE_PHYSICS) && !E->deltas_pending;
 	if ((phases & BT_PHASE_CTRLS) && !E->ctrls_fused) for (i32 e = 0; e < W.n; e++) t_pre(W, e, phases);
 	if (phases & BT_PHASE_PREP) flush1(E, false);

@@ -102,3 +102,62 @@ def test_edge_world_cuda_vs_oracle(bt, oracle_lib, name):
         if n_live:
             assert np.array_equal(w.raycast(origin, look), ow.selectcast(origin, look))
     w.close()
+
+
+def falling_world(rules):
+    """30 cubes and 10 terrain slabs with no ground under them: everything drops out of the world"""
+    import ctypes as C
+    wa = tiny_world(40, spacing=3000)
+    wa.a["w_gamerules"][0] = 8 | rules
+    for i in range(40):
+        wa.a["center"][3 * i + 2] = 60000 + 40 * i
+        wa.a["old"][3 * i + 2] = 60000 + 40 * i
+        wa.a["center"][3 * i] = -58000 + 3000 * i
+        wa.a["old"][3 * i] = -58000 + 3000 * i
+        wa.a["vel"][3 * i] = 900 * (1 if i % 2 else -1)
+        wa.a["old"][3 * i] -= 900 * (1 if i % 2 else -1)
+        if i % 4 == 0:
+            wa.a["type_mask"][i] = wa.a["new_type_mask"][i] = 2 | 16   # TERRAIN | WEIGHTLESS: bounces, does not die
+            wa.a["collide_mask"][i] = wa.a["new_collide_mask"][i] = 0
+    return wa
+
+
+@pytest.mark.parametrize("rules", [16, 1, 2, 32, 1 | 16 | 32])
+def test_world_rules_kernel_bodies_oracle_and_reference(ref_lib, oracle_lib, emu, rules):
+    """BT_PHASE_WORLD_RULES: lava / crushtainers / bouncetainer, against the reference's effects.cpp"""
+    import ctypes as C
+    wa = falling_world(rules)
+    R = ref_lib
+    wid = R.new_world()
+    R.L.btref_add_ent.argtypes = [C.POINTER(C.c_int32)] * 3 + [C.c_uint32, C.c_uint32, C.c_int]
+    for i in range(wa.n):
+        c = (C.c_int32 * 3)(*[int(x) for x in wa.a["center"][3 * i: 3 * i + 3]])
+        v = (C.c_int32 * 3)(*[int(x) for x in wa.a["vel"][3 * i: 3 * i + 3]])
+        r = (C.c_int32 * 3)(*[int(x) for x in wa.a["radius"][3 * i: 3 * i + 3]])
+        R.L.btref_add_ent(c, v, r, int(wa.a["type_mask"][i]), int(wa.a["collide_mask"][i]), 6)
+    R.set_gamerules(8 | rules)
+    start = R.export()
+    ow = oracle_lib.create(start)
+    ew = emu.EmuWorld(start, rebuild_every=2, shuffle_seed=1)
+    for t in range(120):
+        R.step(2)
+        ow.step(31 | 32)
+        ew.step(31 | 32)
+        assert ow.hash()[0] == R.hash(), "oracle != reference, tick %d" % t
+        assert ew.hash() == ow.hash(), "kernel bodies != oracle, tick %d" % t
+    assert R.count()[0] < wa.n   # something did fall out and die
+    R.free_world(wid)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("rules", [16, 1 | 16 | 32])
+def test_world_rules_cuda(bt, oracle_lib, rules):
+    wa = falling_world(rules)
+    ow = oracle_lib.create(wa)
+    w = bt.World(wa)
+    hs = w.tick(120, hashes=True)   # bt_world_tick adds the rules phase by itself
+    for t in range(120):
+        ow.step(31 | 32)
+        assert int(hs[t, 0]) == ow.hash()[0], t
+    assert w.count()[0] == ow.count()[0] < wa.n
+    w.close()
