@@ -36,6 +36,10 @@ class BtTickStats(C.Structure):
                  "pair_builds", "pairs_cached", "pair_overflows", "unsupported_events")]
 
 
+class BtEvent(C.Structure):
+    _fields_ = [(k, C.c_int32) for k in ("kind", "handler", "world", "me_uid", "him_uid", "arg")]
+
+
 class BtProfile(C.Structure):
     _fields_ = [("n", C.c_int32), ("name", C.c_char_p * 24), ("launches", C.c_int64 * 24), ("ms", C.c_double * 24)]
 
@@ -85,6 +89,7 @@ def lib():
     L.bt_world_stream.restype = C.c_void_p
     L.bt_world_hash.argtypes = [C.c_void_p, _u64p]
     L.bt_world_stats.argtypes = [C.c_void_p, C.POINTER(BtTickStats), C.c_int]
+    L.bt_world_drain_events.argtypes = [C.c_void_p, C.POINTER(BtEvent), C.c_int32, C.POINTER(C.c_int32)]
     L.bt_world_unsupported.argtypes = [C.c_void_p, C.POINTER(C.c_uint32)]
     L.bt_world_profile_enable.argtypes = [C.c_void_p, C.c_int]
     L.bt_world_profile_read.argtypes = [C.c_void_p, C.POINTER(BtProfile), C.c_int]
@@ -245,6 +250,13 @@ class World:
         s = BtTickStats()
         _ck(self.L.bt_world_stats(self.h, C.byref(s), int(reset)), "bt_world_stats")
         return {k: int(getattr(s, k)) for k, _ in BtTickStats._fields_}
+
+    def drain_events(self, max_events=4096):
+        """host-side handler events (PUSH_TEAMSELECT / PUSH_LOADBLOCK) since the last drain"""
+        buf = (BtEvent * max_events)()
+        n = C.c_int32()
+        _ck(self.L.bt_world_drain_events(self.h, buf, max_events, C.byref(n)), "bt_world_drain_events")
+        return [{k: int(getattr(buf[i], k)) for k, _ in BtEvent._fields_} for i in range(n.value)]
 
     def unsupported_per_world(self):
         out = np.zeros(self.n_worlds, dtype=np.uint32)

@@ -143,7 +143,9 @@ static BT_HD int bt_who_moves(int id, u32 ta, u32 tb, int axis, int dir) {
 
 /* which handler IDs have a device implementation (bt_world_upload checks these) */
 #define BT_SUPPORTED_WHOMOVES 0x1ffu /* 0..8 */
-#define BT_SUPPORTED_PUSH 0x007u     /* NIL, PLAYER, LOGIC */
+#define BT_SUPPORTED_PUSH 0x0b7u     /* NIL, PLAYER, LOGIC, TEAMSELECT (event), SCOREBOARD, LOADBLOCK (event) */
+#define BT_SERIAL_PUSH 0x0b2u        /* of those, the ones that run in the serial lane: PLAYER, TEAMSELECT, SCOREBOARD, LOADBLOCK */
+#define TICK_PLAYER 7                /* handlerRegistrar.h:93-101 */
 #define BT_SUPPORTED_PUSHED 0x02fu   /* NIL, PUDDLEJUMP, FRAGILE, FLAG, PLAYER */
 #define BT_SUPPORTED_PAIR 0x029u     /* NIL, FUMBLED_DECOR, PICKUP_PLAYER */
 #define BT_SUPPORTED_CRUSH 0x001u    /* NIL (others are host-side events) */
@@ -184,6 +186,25 @@ static BT_HD int bt_player_push(const DevWorld &W, i32 me, i32 him) {
 static BT_HD int bt_push_handler(const DevWorld &W, i32 me, i32 him) {
 	int id = (W.hphys[me] >> 8) & 0xff;
 	if (id == 1) return bt_player_push(W, me, him);
+	if (id == 4 || id == 7) {
+		/* teamselect_push teamselect.cpp:36-45 / loadblock_push loadblock.cpp:17-31: both act on
+		 * gs->players, i.e. on the host; "him is some player's entity" is "him runs TICK_PLAYER" */
+		if (id == 7 && bt_getslider(W, me, 1) > 0) return 0;
+		if ((W.htick[him] & 0xff) != TICK_PLAYER) return 0;
+		u32 slot = bt_add32(&W.ctr[CT_EVENT_N], 1u);
+		if ((i32)slot < W.event_cap) W.events[slot] = make_int4(id, me, him, id == 7 ? bt_getslider(W, me, 0) : 0);
+		if (id == 7 && W.slider_off[me + 1] - W.slider_off[me] > 1) W.sv[W.slider_off[me] + 1] = 15; /* direct write */
+		return 0;
+	}
+	if (id == 5) { /* scoreboard_push scoreboard.cpp:19-36 */
+		if ((W.htick[me] & 0xff) != (W.htick[him] & 0xff)) return 0;
+		bt_uslider(W, me, 0, 0);
+		bt_uslider(W, me, 1, 0);
+		bt_uslider(W, me, 2, bt_getslider(W, him, 2));
+		bt_uslider(W, me, 3, bt_getslider(W, him, 3));
+		for (i32 k = 0; k < W.wire_cnt[me]; k++) bt_or32(&W.btn_v2[W.wire_to[W.wire_off[me] + k]], 1u);
+		return 0;
+	}
 	if (id == 2) {
 		if (W.type[him] & (T_TERRAIN | T_OBSTACLE | T_DEBRIS)) bt_or32(&W.btn_v2[me], 1u); /* pushBtn(me,0) */
 	} else if (id != 0) {
@@ -1048,7 +1069,8 @@ static BT_HD void t_push(const DevWorld &W, i32 e, LocalStats &st) {
 	Coll pc = bt_unpack_coll(W.pend[e]);
 	/* push handlers that edit somebody else's tree (player_push: pickup into the player's
 	 * holdee list, first come first served) run in the serial lane, canonical order */
-	int serial_handler = ((W.hphys[pc.buddy] >> 8) & 0xff) == 1 || (pc.mutual && ((W.hphys[pc.leaf] >> 8) & 0xff) == 1);
+	int serial_handler = ((BT_SERIAL_PUSH >> ((W.hphys[pc.buddy] >> 8) & 0x1f)) & 1) ||
+	                     (pc.mutual && ((BT_SERIAL_PUSH >> ((W.hphys[pc.leaf] >> 8) & 0x1f)) & 1));
 	if (serial_handler) {
 		u32 slot = bt_add32(&W.ctr[CT_SERIAL_N], 1u);
 		if ((i32)slot < W.serial_cap) W.serialList[slot] = e;

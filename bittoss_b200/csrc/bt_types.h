@@ -100,6 +100,7 @@ enum {
 	CT_STOP = 37,        /* run-ahead: iter_id of the first speculatively enqueued iteration that stood down */
 	CT_ANY_ODD = 38,     /* CT_ANY_PROPOSAL of odd iteration ids (even ones use slot 0): an iteration never
 	                      * reads the slot it is itself stamping */
+	CT_EVENT_N = 40,     /* entries in events[] */
 	CT_WORDS = 64
 };
 enum { SK_ITERS = 0, SK_CAND, SK_POS, SK_PUSH, SK_SERIAL, SK_CRUSH, SK_FUMBLE, SK_NUM };
@@ -148,6 +149,8 @@ struct DevWorld {
 	Box6 *ibox;      /* per entity: the inflated swept box of the last refit */
 	u64 *pairs;      /* a | b<<32, a = entity at the earlier leaf position */
 
+	int4 *events;    /* {kind<<8 | handler, me slot, him slot, arg}; only the serial lane appends */
+	i32 event_cap;
 	i32 *serialList;
 	u64 *deadList; /* key<<32 | entity */
 	u64 *hash;     /* per world */

@@ -221,7 +221,8 @@ int bt_world_create(bt_world **out, int device, int32_t max_ents, int32_t max_sl
 	W.pair_cap = (i32)std::min<size_t>((size_t)1 << 30, 12 * n + 4096);
 	W.margin = 32;
 	TRY(dalloc(w, &W.pairs, (size_t)W.pair_cap));
-	W.serial_cap = 1 << 16; W.dead_cap = max_ents > 0 ? max_ents : 1;
+	W.serial_cap = 1 << 16; W.dead_cap = max_ents > 0 ? max_ents : 1; W.event_cap = 1 << 16;
+	TRY(dalloc(w, &W.events, (size_t)W.event_cap));
 	TRY(dalloc(w, &W.serialList, (size_t)W.serial_cap)); TRY(dalloc(w, &W.deadList, (size_t)W.dead_cap));
 	TRY(dalloc(w, &W.hash, nw)); TRY(dalloc(w, &W.ctr, (size_t)CT_WORDS));
 	TRY(dalloc(w, &w->d_hsum, nw)); TRY(dalloc(w, &w->d_hcnt, nw));
@@ -775,6 +776,31 @@ int bt_world_stats(bt_world *w, bt_tick_stats *out, int reset) {
 		CK(cudaMemsetAsync(w->W.wunsup, 0, sizeof(u32) * (size_t)w->cap_worlds, w->stream));
 	}
 	return BT_OK;
+}
+
+int bt_world_drain_events(bt_world *w, bt_event *out, int32_t max, int32_t *n) {
+	if (!w || !n || max < 0 || (max > 0 && !out)) return BT_ERR_ARG;
+	CK(cudaSetDevice(w->device));
+	CK(cudaStreamSynchronize(w->stream));
+	u32 cnt = 0;
+	CK(cudaMemcpy(&cnt, &w->W.ctr[CT_EVENT_N], sizeof(u32), cudaMemcpyDeviceToHost));
+	bool overflow = cnt > (u32)w->W.event_cap;
+	if (overflow) cnt = (u32)w->W.event_cap;
+	u32 take = cnt < (u32)max ? cnt : (u32)max;
+	std::vector<int4> ev(take);
+	std::vector<i32> uid(w->W.n), world(w->W.n);
+	if (take) {
+		CK(cudaMemcpy(ev.data(), w->W.events, sizeof(int4) * take, cudaMemcpyDeviceToHost));
+		CK(cudaMemcpy(uid.data(), w->W.uid, sizeof(i32) * (size_t)w->W.n, cudaMemcpyDeviceToHost));
+		CK(cudaMemcpy(world.data(), w->W.world, sizeof(i32) * (size_t)w->W.n, cudaMemcpyDeviceToHost));
+	}
+	for (u32 i = 0; i < take; i++) {
+		out[i].kind = 0; out[i].handler = ev[i].x; out[i].world = world[ev[i].y];
+		out[i].me_uid = uid[ev[i].y]; out[i].him_uid = uid[ev[i].z]; out[i].arg = ev[i].w;
+	}
+	*n = (int32_t)take;
+	CK(cudaMemsetAsync(&w->W.ctr[CT_EVENT_N], 0, sizeof(u32), w->stream));
+	return overflow ? BT_ERR_OVERFLOW : BT_OK;
 }
 
 int bt_world_unsupported(bt_world *w, uint32_t *per_world) {

@@ -139,6 +139,19 @@ typedef struct bt_profile {
 	double ms[BT_PROF_MAX];         /* summed CUDA-event time */
 } bt_profile;
 
+/* A collision-path handler whose effect lives on the HOST side of the game (gs->players,
+ * requestLoad, ...) is reported instead of executed: PUSH_TEAMSELECT (teamselect.cpp:36-45),
+ * PUSH_LOADBLOCK (loadblock.cpp:17-31; its slider write is done on the device).  Events of a
+ * step are delivered in the canonical push order. */
+typedef struct bt_event {
+	int32_t kind;     /* 0 = push handler */
+	int32_t handler;  /* catalog id (PUSH_TEAMSELECT = 4, PUSH_LOADBLOCK = 7) */
+	int32_t world;
+	int32_t me_uid;   /* the entity owning the handler */
+	int32_t him_uid;  /* the entity that pushed it */
+	int32_t arg;      /* LOADBLOCK: getSlider(me, 0), the game-string index to load */
+} bt_event;
+
 typedef struct bt_world bt_world; /* opaque, owns device memory + one stream */
 
 /* ---- library ---- */
@@ -197,6 +210,9 @@ void *bt_world_stream(bt_world *w); /* the cudaStream_t every kernel of w runs o
  * out: [n_worlds]. */
 int bt_world_hash(bt_world *w, uint64_t *out);
 int bt_world_stats(bt_world *w, bt_tick_stats *out, int reset);
+/* Copies out (and clears) the events queued since the last drain; *n = how many were written,
+ * at most max.  Returns BT_ERR_OVERFLOW if the device queue (65536 entries) had overflowed. */
+int bt_world_drain_events(bt_world *w, bt_event *out, int32_t max, int32_t *n);
 /* per world [n_worlds]: unsupported_events since the last bt_world_stats(reset) */
 int bt_world_unsupported(bt_world *w, uint32_t *per_world);
 int bt_world_profile_enable(bt_world *w, int on);

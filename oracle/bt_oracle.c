@@ -107,6 +107,7 @@ typedef struct {
 	i32 *stamp;
 	i32 stampCtr;
 	int64_t stats[8];
+	int64_t n_events; /* host-side handler invocations reported instead of executed */
 } World;
 
 enum { ST_TICKS, ST_ITERS, ST_CAND, ST_POS, ST_PUSH, ST_SERIAL, ST_CRUSH, ST_FUMBLE };
@@ -233,6 +234,23 @@ static int pushH(World *w, i32 me, i32 him, int axis, int dir, i32 displacement,
 	(void)axis; (void)dir; (void)displacement; (void)dv;
 	switch (w->h[me][BT_H_PUSH]) {
 	case 1: return player_push(w, me, him);
+	case 4: /* teamselect_push teamselect.cpp:36-45: acts on gs->players (host); reported as an event */
+	case 7: { /* loadblock_push loadblock.cpp:17-31 */
+		int id = w->h[me][BT_H_PUSH];
+		if (id == 7 && getSlider(w, me, 1) > 0) return 0;
+		if (w->h[him][BT_H_TICK] != 7) return 0; /* "him is a player's entity" = runs TICK_PLAYER */
+		w->n_events++;
+		if (id == 7 && w->slider_off[me + 1] - w->slider_off[me] > 1) w->sv[w->slider_off[me] + 1] = 15;
+		return 0;
+	}
+	case 5: /* scoreboard_push scoreboard.cpp:19-36 */
+		if (w->h[me][BT_H_TICK] != w->h[him][BT_H_TICK]) return 0;
+		uSlider(w, me, 0, 0);
+		uSlider(w, me, 1, 0);
+		uSlider(w, me, 2, getSlider(w, him, 2));
+		uSlider(w, me, 3, getSlider(w, him, 3));
+		for (int k = 0; k < w->wires[me].num; k++) w->btn[w->wires[me].items[k]][4 + 0] = 1;
+		return 0;
 	case 2:
 		if (w->type[him] & (T_TERRAIN | T_OBSTACLE | T_DEBRIS)) w->btn[me][4 + 0] = 1; /* pushBtn(me,0) */
 		return 0;

@@ -89,7 +89,8 @@ Emu *bte_create(const bt_world_desc *d, int rebuild_every, int shuffle_seed) {
 	A(E, &W.nodeBox, n); A(E, &W.leafBox, n); A(E, &W.nodeHi, n); A(E, &W.ibox, n);
 	W.pair_cap = 12 * n + 4096; W.margin = 32;
 	A(E, &W.pairs, W.pair_cap);
-	W.serial_cap = 1 << 16; W.dead_cap = n ? n : 1;
+	W.serial_cap = 1 << 16; W.dead_cap = n ? n : 1; W.event_cap = 1 << 16;
+	A(E, &W.events, W.event_cap);
 	A(E, &W.serialList, W.serial_cap); A(E, &W.deadList, W.dead_cap); A(E, &W.hash, nw); A(E, &W.ctr, CT_WORDS);
 	for (int g = 0; g < nw; g++) {
 		W.wbegin[g] = n; W.wend[g] = 0;
@@ -315,6 +316,7 @@ void bte_set_option(Emu *E, const char *name, int64_t v) {
 	if (!strcmp(name, "cache_margin")) E->W.margin = (i32)v;
 }
 int64_t bte_pair_rebuilds(Emu *E) { return E->pair_rebuilds; }
+int64_t bte_events(Emu *E) { return (int64_t)E->W.ctr[CT_EVENT_N]; }
 int64_t bte_unsupported(Emu *E) { return (int64_t)E->W.ctr[CT_UNSUPPORTED]; }
 int64_t bte_unsupported_last(Emu *E) { return (int64_t)E->W.ctr[CT_UNSUP_LAST]; }
 

@@ -40,6 +40,8 @@ class EmuWorld:
         L.bte_set_option.argtypes = [C.c_void_p, C.c_char_p, C.c_int64]
         L.bte_pair_rebuilds.argtypes = [C.c_void_p]
         L.bte_pair_rebuilds.restype = C.c_int64
+        L.bte_events.argtypes = [C.c_void_p]
+        L.bte_events.restype = C.c_int64
         L.bte_unsupported.argtypes = [C.c_void_p]
         L.bte_unsupported.restype = C.c_int64
         L.bte_raycast.argtypes = [C.c_void_p, _i32p, _i32p, C.c_int32, _i32p]
@@ -62,6 +64,9 @@ class EmuWorld:
 
     def set_option(self, name, value):
         self.L.bte_set_option(self.h, name.encode(), int(value))
+
+    def events(self):
+        return int(self.L.bte_events(self.h))
 
     def unsupported(self):
         return int(self.L.bte_unsupported(self.h))

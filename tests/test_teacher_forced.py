@@ -13,7 +13,7 @@ import pytest
 
 CASES = {
     # name: (level, players' data, spacetrash spawner on, ticks, max skipped fraction)
-    "lobby_4players": ("lobby", (0, 0, 0, 0), 0, 1000, 0.005),   # PUSH_TEAMSELECT / PUSH_LOADBLOCK are host-side
+    "lobby_4players": ("lobby", (0, 0, 0, 0), 0, 1000, 0.0),   # PUSH_TEAMSELECT / PUSH_LOADBLOCK arrive as events
     "spacetrash_spawner": ("spacetrash", (), 1, 10000, 0.0),
     "arena_2players": ("arena", (1, 2), 0, 1000, 0.0),
 }
@@ -66,9 +66,14 @@ def test_cuda_teacher_forced(ref_lib, bt, name):
         w.stats(reset=True)
         w.upload(wa)
         w.step(PHYSICS_FINISH)
+        events.extend(w.drain_events())
         return w, w.hash()[0], w.stats()["unsupported_events"]
+    events = []
     ok, skipped, ents = _run(ref_lib, step, name)
-    print("%s: %d ticks bit-exact, %d skipped, %d entities at the end" % (name, ok, skipped, ents))
+    print("%s: %d ticks bit-exact, %d skipped, %d entities at the end, %d host-side handler events %s" % (
+        name, ok, skipped, ents, len(events), sorted(set(e["handler"] for e in events))))
+    if name == "lobby_4players":
+        assert events and set(e["handler"] for e in events) <= {4, 7}   # PUSH_TEAMSELECT, PUSH_LOADBLOCK
     assert ok >= 0.99 * CASES[name][3]
 
 
