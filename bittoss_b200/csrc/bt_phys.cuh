@@ -57,6 +57,8 @@ struct LocalStats {
 	u32 cand, pos, push, crush, fumble;
 };
 
+static BT_HD void bt_check_cover(const DevWorld &W, i32 e, const int4 &o, const int4 &c);
+
 /* ------------------------------------------------------------------------- */
 /* helpers                                                                   */
 
@@ -146,7 +148,7 @@ static BT_HD int bt_who_moves(int id, u32 ta, u32 tb, int axis, int dir) {
 #define BT_SUPPORTED_PUSH 0x0b7u     /* NIL, PLAYER, LOGIC, TEAMSELECT (event), SCOREBOARD, LOADBLOCK (event) */
 #define BT_SERIAL_PUSH 0x0b2u        /* of those, the ones that run in the serial lane: PLAYER, TEAMSELECT, SCOREBOARD, LOADBLOCK */
 #define TICK_PLAYER 7                /* handlerRegistrar.h:93-101 */
-#define BT_SUPPORTED_PUSHED 0x02fu   /* NIL, PUDDLEJUMP, FRAGILE, FLAG, PLAYER */
+#define BT_SUPPORTED_PUSHED 0x12fu   /* NIL, PUDDLEJUMP, FRAGILE, FLAG, PLAYER, BULLET */
 #define BT_SUPPORTED_PAIR 0x029u     /* NIL, FUMBLED_DECOR, PICKUP_PLAYER */
 #define BT_SUPPORTED_CRUSH 0x001u    /* NIL (others are host-side events) */
 
@@ -213,13 +215,47 @@ static BT_HD int bt_push_handler(const DevWorld &W, i32 me, i32 him) {
 	return 0;
 }
 
+/* uPickup entUpdaters.c:29-52: a request, applied by the next flushPickups */
+static BT_HD void bt_upickup(const DevWorld &W, i32 p, i32 e, i32 holdFlags) {
+	if (W.holder[e] >= 0) return;
+	if (W.dead[e] || W.dead[p]) return;
+	i32 nh = W.newHolder[e];
+	if (nh >= 0) {
+		if (nh != p || W.newHoldFlags[e] != holdFlags) W.newHolder[e] = e;
+		return;
+	}
+	W.newHolder[e] = p;
+	W.newHoldFlags[e] = holdFlags;
+	W.ctr[CT_FLUSH_HINT] = 1;
+}
+
 /* pushed_t: 2 fragile_pushed common.c:56; 3 flag_pushed flag.c:13; 5 player_pushed
  * player.c:88-106; 1 pj_pushed puddlejumper.cpp:44-65.  NULL slot (0) is skipped (ent.cpp:556). */
-static BT_HD int bt_pushed_handler(const DevWorld &W, i32 me, i32 him, int axis, int dir, i32 dv) {
+static BT_HD int bt_pushed_handler(const DevWorld &W, i32 me, i32 him, int axis, int dir, i32 dx, i32 dv) {
 	int id = (W.hphys[me] >> 16) & 0xff;
 	switch (id) {
 	case 2: return 1;
 	case 3: return (W.type[him] & T_FLAG) ? 1 : 0;
+	case 8: { /* bullet_pushed gun.c:90-114: stick to whatever was hit */
+		if (bt_getslider(W, me, 0) == 0) return 0;
+		bt_upickup(W, him, me, HOLD_DROP | HOLD_FREEZE);
+		W.sv[W.slider_off[me]] = 0; /* immediate slider write */
+		if (dv) {
+			i32 scale = 7000;
+			i32 ratio = dx * scale / dv;
+			int4 c = W.center[me], vm = W.vel[me], vh = W.vel[him];
+			const i32 rel[3] = {vm.x - vh.x, vm.y - vh.y, vm.z - vh.z};
+			for (int i = 0; i < 2; i++) {
+				int dim = (axis + 1 + i) % 3;
+				bt_set3(c, dim, bt_get3(c, dim) - rel[dim] * ratio / scale);
+			}
+			W.center[me] = c;
+			if (W.hasBox[me]) bt_check_cover(W, me, W.old[me], c);
+		}
+		W.type[me] = 0; /* immediate, without touching new*Mask or the box */
+		W.collide[me] = 0;
+		return 0;
+	}
 	case 1:
 	case 5: {
 		int s_vel = id == 5 ? 5 : 2, s_grounded = id == 5 ? 7 : 4;
@@ -962,7 +998,7 @@ static BT_HD void bt_push_regular(const DevWorld &W, i32 e, i32 o, int axis, int
 		if (bt_push_helper(W, e, prev, axis, dir, key, st)) break;
 		if ((W.hphys[e] >> 16) & 0xff) {
 			i32 accel = dv[axis] * dir;
-			if (bt_pushed_handler(W, e, o, axis, dir, accel)) {
+			if (bt_pushed_handler(W, e, o, axis, dir, displacement, accel)) {
 				bt_crush(W, e, key, st);
 				break;
 			}
@@ -995,6 +1031,7 @@ static BT_HD void bt_pickup(const DevWorld &W, i32 x, i32 y, i32 holdFlags) {
 	if (holdFlags & HOLD_FREEZE) {
 		int4 vx = W.vel[x], vy = W.vel[y];
 		W.d_vel[y] = make_int4(vx.x - vy.x, vx.y - vy.y, vx.z - vy.z, 0);
+		W.ctr[CT_ANY_DELTA] = 1; /* the flush2 that follows has something to apply */
 	}
 	bt_pair_handler(W, 2, x, y);
 	bt_pair_handler(W, 3, y, x);
@@ -1164,10 +1201,16 @@ static BT_HD void t_flush_serial(const DevWorld &W, i32 g, LocalStats &st) {
 			W.newDrop[i] = 0;
 			bt_fumble(W, i, st);
 		}
-		if (W.newHolder[i] >= 0) {
-			if (W.lenient) { bt_unsup(W, i, 4, 0); W.newHolder[i] = -1; }
-			else W.ctr[CT_ERROR] = (u32)(-BT_ERR_UNSUPPORTED);
-		}
+	}
+	/* flushPickups ent.cpp:775-792.  The reference walks gs->rootEnts (newest root first); there
+	 * is no such list here, the walk is newest entity first, which is the same order unless a
+	 * fumble re-rooted an older entity this tick (only observable for mutual pickup requests) */
+	for (i32 i = W.wend[g] - 1; i >= W.wbegin[g]; i--) {
+		if (!W.inList[i] || W.holder[i] >= 0) continue;
+		i32 x = W.newHolder[i];
+		if (x < 0) continue;
+		if (W.holdRoot[x] != i && !W.dead[x]) bt_pickup(W, x, i, W.newHoldFlags[i]);
+		W.newHolder[i] = -1;
 	}
 }
 
@@ -1248,8 +1291,7 @@ static BT_HD void t_gravity(const DevWorld &W, i32 e) {
 	if (e >= W.n || !W.inList[e] || W.holder[e] >= 0) return;
 	if (!(W.gamerules[W.world[e]] & EFFECT_GRAV)) return;
 	if (W.type[e] & T_WEIGHTLESS) return;
-	W.d_vel[e].z += 32;
-	W.ctr[CT_ANY_DELTA] = 1;
+	W.d_vel[e].z += 32; /* consumed by the flush2 at the start of doPhysics (host-tracked) */
 }
 
 /* flush2 / flushPosVel ent.cpp:716-744, 806-811 as a gather: every entity sums the pending

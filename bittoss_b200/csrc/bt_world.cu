@@ -600,10 +600,15 @@ static int do_physics(bt_world *w, bool gravity) {
 	if (r) return r;
 	/* a flush1 that runs k_flush_serial can itself kill (dead_max) and so leave wires to clean
 	 * up: keep the next flush1 full in that case */
-	/* flush2 (ent.cpp:910): none of the device-side handlers leaves a delta behind */
 	r = fetch_ctr(w);
 	if (r) return r;
 	if (w->h_flag[CT_FLUSH_HINT] && w->full_flush_left < 1) w->full_flush_left = 1;
+	if (w->h_flag[CT_ANY_DELTA]) {
+		/* flush2 (ent.cpp:910): a pickup with HOLD_FREEZE left a d_vel behind (ent.cpp:176-181) */
+		LAUNCH(w, PK_FLUSH, k_flush2_apply, nblk(n), BT_BLOCK, W);
+		LAUNCH(w, PK_FLUSH, k_zero_deltas, nblk(n), BT_BLOCK, W);
+		CK(cudaMemsetAsync(&W.ctr[CT_ANY_DELTA], 0, sizeof(u32), w->stream));
+	}
 	if (w->h_flag[CT_NEED_REBUILD]) {
 		w->tree_valid = false; /* build_tree raises CT_CACHE_INVALID */
 		CK(cudaMemsetAsync(&W.ctr[CT_NEED_REBUILD], 0, sizeof(u32), w->stream));

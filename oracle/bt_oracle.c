@@ -261,13 +261,40 @@ static int pushH(World *w, i32 me, i32 him, int axis, int dir, i32 displacement,
 /* pushed_t handlers: 2 fragile_pushed common.c:56; 3 flag_pushed flag.c:13;
  * 5 player_pushed player.c:88-106; 1 pj_pushed puddlejumper.cpp:44-65.
  * returns -1 when the slot is NULL (ent.cpp:556) */
+/* uPickup entUpdaters.c:29-52 */
+static void uPickup(World *w, i32 p, i32 e, i32 holdFlags) {
+	if (w->holder[e] >= 0) return;
+	if (w->dead[e] || w->dead[p]) return;
+	if (w->newHolder[e] >= 0) {
+		if (w->newHolder[e] != p || w->newHoldFlags[e] != holdFlags) w->newHolder[e] = e;
+		return;
+	}
+	w->newHolder[e] = p;
+	w->newHoldFlags[e] = holdFlags;
+}
+
 static int pushedH(World *w, i32 me, i32 him, int axis, int dir, i32 dx, i32 dv) {
-	(void)dx;
 	int id = w->h[me][BT_H_PUSHED];
 	switch (id) {
 	case 0: return -1;
 	case 2: return 1;
 	case 3: return (w->type[him] & T_FLAG) ? 1 : 0;
+	case 8: { /* bullet_pushed gun.c:90-114 */
+		if (getSlider(w, me, 0) == 0) return 0;
+		uPickup(w, him, me, HOLD_DROP | HOLD_FREEZE);
+		w->sv[w->slider_off[me]] = 0;
+		if (dv) {
+			i32 scale = 7000;
+			i32 ratio = dx * scale / dv;
+			for (int i = 0; i < 2; i++) {
+				int dim = (axis + 1 + i) % 3;
+				w->center[me][dim] -= (w->vel[me][dim] - w->vel[him][dim]) * ratio / scale;
+			}
+		}
+		w->type[me] = 0;
+		w->collide[me] = 0;
+		return 0;
+	}
 	case 1:
 	case 5: {
 		int s_vel = id == 5 ? 5 : 2, s_grounded = id == 5 ? 7 : 4;

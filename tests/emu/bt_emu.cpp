@@ -273,6 +273,11 @@ static int do_physics(Emu *E, bool gravity) {
 	}
 	flush1(E, W.ctr[CT_FLUSH_HINT] != 0);
 	if (W.ctr[CT_FLUSH_HINT] && E->full_flush_left < 1) E->full_flush_left = 1;
+	if (W.ctr[CT_ANY_DELTA]) { /* flush2 ent.cpp:910 */
+		for (i32 e = 0; e < n; e++) t_flush2_apply(W, e);
+		for (i32 e = 0; e < n; e++) t_zero_deltas(W, e);
+		W.ctr[CT_ANY_DELTA] = 0;
+	}
 	if (W.ctr[CT_ERROR]) return -(int)W.ctr[CT_ERROR];
 	if (W.ctr[CT_NEED_REBUILD]) { E->tree_valid = false; W.ctr[CT_NEED_REBUILD] = 0; }
 	return 0;
