@@ -113,7 +113,7 @@ def test_cuda_raycast_after_ticks_skips_dead(bt, oracle_lib):
 
 def test_unsupported_handler_is_refused(bt):
     wa, _ = load_scenario("arena_kick")
-    wa.a["handlers"][4] = 4  # PUSH_TEAMSELECT on entity 0: host-side effects, no device implementation
+    wa.a["handlers"][4] = 3  # PUSH_SEAT on entity 0: no device implementation (needs wire edits)
     with pytest.raises(bt.BtError):
         bt.World(wa)
 
