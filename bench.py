@@ -147,6 +147,9 @@ def run_cuda(args):
     n = wa.n
     w = bittoss_b200.World(wa, device=local_rank)
     w.set_option("rebuild_every", args.rebuild_every)
+    for kv in args.opt:  # experiments only: any bt_world_set_option knob; none of them changes results
+        k, v = kv.split("=")
+        w.set_option(k, int(v))
 
     # ---- (0) settle phase ("run 100 ticks after a 50-tick settle; report
     #      both phases"): the cubes start 100-164 units apart and drop onto each other ----
@@ -311,6 +314,7 @@ def main():
     ap.add_argument("--cpu-ticks", type=int, default=10)
     ap.add_argument("--settle", type=int, default=50)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--opt", action="append", default=[], help="name=value for bt_world_set_option (tuning experiments)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "cuda":
         args.warmup = 3

@@ -33,7 +33,7 @@ class BtTickStats(C.Structure):
     _fields_ = [(k, C.c_int64) for k in
                 ("ticks", "iterations", "candidate_pairs", "positives", "pushes", "serial_pushes", "crushes",
                  "fumbles", "kernel_launches", "tree_builds", "tree_refits", "live_ents", "entity_ticks",
-                 "pair_builds", "pairs_cached", "pair_overflows", "unsupported_events")]
+                 "pair_builds", "pairs_cached", "pair_overflows", "unsupported_events", "pair_patches")]
 
 
 class BtEvent(C.Structure):

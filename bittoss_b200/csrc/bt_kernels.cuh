@@ -80,6 +80,10 @@ __global__ void __launch_bounds__(BT_BLOCK) k_morton(DevWorld W) { t_morton(W, T
 __global__ void __launch_bounds__(BT_BLOCK) k_lbvh(DevWorld W) { t_lbvh_node(W, TID); }
 __global__ void __launch_bounds__(GS_BLOCK) k_refit(DevWorld W, int cond) {
 	if (cond && !W.ctr[CT_CACHE_INVALID]) return;
+	if (cond && bt_patch_mode(W)) {
+		GS_FOR(t, (i32)W.ctr[CT_DIRTY_N]) t_refit_patch(W, t);
+		return;
+	}
 	GS_FOR(t, W.n_leaves) t_refit(W, t, cond);
 }
 
@@ -144,6 +148,11 @@ __global__ void __launch_bounds__(BT_BLOCK) k_pairs(DevWorld W) {
 	__shared__ u64 pbuf[PAIR_BUF * BT_BLOCK];
 	if (!W.ctr[CT_CACHE_INVALID]) return; /* uniform: the cached pairs are still a superset */
 	PairEmit emit(W.pairs, &W.ctr[CT_PAIR_N], W.pair_cap, pbuf + threadIdx.x);
+	if (bt_patch_mode(W)) { /* a few moved entities: spread them over the whole grid */
+		GS_FOR(t, (i32)W.ctr[CT_DIRTY_N]) t_pairs_patch(W, t, stacks + threadIdx.x, BT_BLOCK, emit);
+		emit.finish();
+		return;
+	}
 	/* blocked distribution: each block walks one contiguous run of leaves, so the pair list
 	 * stays in Morton order (k_narrow's gathers depend on that locality) */
 	i32 chunk = (W.n_leaves + (i32)gridDim.x - 1) / (i32)gridDim.x;
@@ -192,7 +201,7 @@ __global__ void __launch_bounds__(256) k_narrow(DevWorld W, int spec) {
 	}
 	/* k_refit / k_pairs of this iteration have consumed the flag; pushes may raise it again
 	 * (a run-ahead iteration only gets here with the flag down, and other blocks are reading it) */
-	if (!spec && blockIdx.x == 0 && threadIdx.x == 0) W.ctr[CT_CACHE_INVALID] = 0;
+	if (!spec && blockIdx.x == 0 && threadIdx.x == 0) bt_consume_cache_flags(W, np);
 	for (u32 p = blockIdx.x * blockDim.x + threadIdx.x; p < np; p += gridDim.x * blockDim.x)
 		t_narrow(W, W.pairs[p], st, any);
 	stats_flush(W, st);

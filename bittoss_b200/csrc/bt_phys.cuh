@@ -29,6 +29,8 @@ static inline void bt_add64(u64 *p, u64 v) { *p += v; }
 static inline void bt_min32(i32 *p, i32 v) { if (v < *p) *p = v; }
 static inline void bt_max32(i32 *p, i32 v) { if (v > *p) *p = v; }
 static inline void bt_or32(u32 *p, u32 v) { *p |= v; }
+static inline u32 bt_xchg32(u32 *p, u32 v) { u32 o = *p; *p = v; return o; }
+static inline i32 bt_ldv32(const i32 *p) { return *p; }
 static inline u64 bt_ld64(const u64 *p) { return *p; }
 static inline int4 bt_ldcg4(const int4 *p) { return *p; }
 static inline void bt_fence() {}
@@ -43,6 +45,8 @@ static BT_HD void bt_add64(u64 *p, u64 v) { atomicAdd(p, v); }
 static BT_HD void bt_min32(i32 *p, i32 v) { atomicMin(p, v); }
 static BT_HD void bt_max32(i32 *p, i32 v) { atomicMax(p, v); }
 static BT_HD void bt_or32(u32 *p, u32 v) { atomicOr(p, v); }
+static BT_HD u32 bt_xchg32(u32 *p, u32 v) { return atomicExch(p, v); }
+static BT_HD i32 bt_ldv32(const i32 *p) { return *(const volatile i32 *)p; }
 static BT_HD u64 bt_ld64(const u64 *p) { return *(const volatile u64 *)p; }
 static BT_HD int4 bt_ldcg4(const int4 *p) { return __ldcg(p); } /* L2 load: another SM wrote it in this kernel */
 static BT_HD void bt_fence() { __threadfence(); }
@@ -293,7 +297,8 @@ static BT_HD void bt_pair_handler(const DevWorld &W, int slot, i32 me, i32 him) 
 				v.x += mv.x - hv.x; v.y += mv.y - hv.y; v.z += mv.z - hv.z;
 				W.old[it] = o; W.center[it] = c; W.vel[it] = v;
 			});
-			W.ctr[CT_CACHE_INVALID] = 1; /* it jumped: the cached pairs no longer cover it */
+			W.ctr[CT_CACHE_FULL] = 1; /* it jumped: the cached pairs no longer cover it */
+			W.ctr[CT_CACHE_INVALID] = 1;
 			W.holdFlags[him] |= HOLD_DROP;
 		}
 		return;
@@ -365,8 +370,12 @@ static BT_HD void bt_check_cover(const DevWorld &W, i32 e, const int4 &o, const 
 	Box6 ib = W.ibox[e];
 	i32 lo[3], hi[3];
 	bt_swept_box(o, c, r, lo, hi);
-	if (lo[0] < ib.lo.x || lo[1] < ib.lo.y || lo[2] < ib.lo.z || hi[0] > ib.hi.x || hi[1] > ib.hi.y || hi[2] > ib.hi.z)
+	if (lo[0] < ib.lo.x || lo[1] < ib.lo.y || lo[2] < ib.lo.z || hi[0] > ib.hi.x || hi[1] > ib.hi.y || hi[2] > ib.hi.z) {
+		/* once per entity and epoch onto the list the next patch works from */
+		u32 stamp = W.ctr[CT_PATCH_EPOCH] + 1u;
+		if (bt_xchg32(&W.dirtyStamp[e], stamp) != stamp) W.dirtyList[bt_add32(&W.ctr[CT_DIRTY_N], 1u)] = e;
 		W.ctr[CT_CACHE_INVALID] = 1;
+	}
 }
 
 /* moveRecursive ent.cpp:115-126 */
@@ -709,21 +718,116 @@ static BT_HD int bt_max(int a, int b) { return a > b ? a : b; }
 /* refit: leaf position t computes its swept box (what velbox_step / velbox_update keep in
  * p1,p2,r: box.cpp:442-459, ent.cpp:892-904) and climbs; the second thread to reach a node
  * (atomic counter) builds it from both children. */
+/* Patch or full build?  Uniform over a launch and the same for k_refit, k_pairs and the
+ * k_narrow that consumes the flags: none of the three writes a word this reads before the
+ * last of them has read it. */
+static BT_HD int bt_patch_mode(const DevWorld &W) {
+	return W.patch && !W.ray_mode && !W.ctr[CT_CACHE_FULL] && ((u64)W.ctr[CT_DIRTY_N] << W.patch_shift) <= (u64)(u32)W.n_leaves;
+}
+
+static BT_HD Box6 bt_inflated_box(const DevWorld &W, i32 e) {
+	i32 lo[3], hi[3];
+	int4 cc = W.center[e];
+	bt_swept_box(W.ray_mode ? cc : W.old[e], cc, W.radius[e], lo, hi);
+	int m = W.ray_mode ? 0 : W.margin;
+	if (!W.ray_mode && W.horizon > 0) {
+		/* where it will be for the next `horizon` ticks if nothing hits it; gravity adds 32 per
+		 * tick to +z (effects.cpp:36).  A heuristic only: bt_check_cover stays exact. */
+		int4 v = W.vel[e];
+		i32 H = W.horizon;
+		long long ex = (long long)v.x * H, ey = (long long)v.y * H, ez = (long long)v.z * H + 16 * H * (H + 1);
+		const long long cap = 1 << 20; /* no stretching by absurd speeds */
+		ex = ex < -cap ? -cap : (ex > cap ? cap : ex); ey = ey < -cap ? -cap : (ey > cap ? cap : ey);
+		ez = ez < -cap ? -cap : (ez > cap ? cap : ez);
+		if (ex < 0) lo[0] += (i32)ex; else hi[0] += (i32)ex;
+		if (ey < 0) lo[1] += (i32)ey; else hi[1] += (i32)ey;
+		if (ez < 0) lo[2] += (i32)ez; else hi[2] += (i32)ez;
+	}
+	Box6 box;
+	box.lo = make_int4(lo[0] - m, lo[1] - m, lo[2] - m, W.world[e]);
+	box.hi = make_int4(hi[0] + m, hi[1] + m, hi[2] + m, W.world[e]);
+	return box;
+}
+
+/* grow p[k] to include [lo,hi]; returns whether anything changed */
+static BT_HD int bt_grow3(i32 *plo, i32 *phi, const int4 &lo, const int4 &hi) {
+	int ch = 0;
+	if (lo.x < bt_ldv32(&plo[0])) { bt_min32(&plo[0], lo.x); ch = 1; }
+	if (lo.y < bt_ldv32(&plo[1])) { bt_min32(&plo[1], lo.y); ch = 1; }
+	if (lo.z < bt_ldv32(&plo[2])) { bt_min32(&plo[2], lo.z); ch = 1; }
+	if (hi.x > bt_ldv32(&phi[0])) { bt_max32(&phi[0], hi.x); ch = 1; }
+	if (hi.y > bt_ldv32(&phi[1])) { bt_max32(&phi[1], hi.y); ch = 1; }
+	if (hi.z > bt_ldv32(&phi[2])) { bt_max32(&phi[2], hi.z); ch = 1; }
+	return ch;
+}
+
+/* Incremental refit, thread t = t-th entry of dirtyList: what velbox_update does for one box
+ * that outran its validity (velbox/box.cpp:442-459, ent.cpp:892-904).  The entity gets a
+ * fresh inflated box; its parent takes it as is, and every higher ancestor only GROWS to
+ * contain it (atomic min/max), so the tree stays a superset until the next full refit. */
+static BT_HD void t_refit_patch(const DevWorld &W, int t) {
+	if ((u32)t >= W.ctr[CT_DIRTY_N]) return;
+	if (t == 0) bt_add32(&W.ctr[CT_PAIR_PATCHES], 1u);
+	i32 e = W.dirtyList[t];
+	W.iboxOld[e] = W.ibox[e];
+	if (!bt_is_leaf_ent(W, e)) return; /* died meanwhile: its cached pairs are filtered by the narrow phase */
+	Box6 box = bt_inflated_box(W, e);
+	W.ibox[e] = box;
+	int pos = W.leafOf[e];
+	W.leafBox[pos] = box;
+	if (W.n_leaves < 2) return;
+	int node = W.leafParent[pos];
+	{
+		BvhNode &N = W.nodes[node];
+		if (N.left == ~pos) {
+			N.llo[0] = box.lo.x; N.llo[1] = box.lo.y; N.llo[2] = box.lo.z;
+			N.lhi[0] = box.hi.x; N.lhi[1] = box.hi.y; N.lhi[2] = box.hi.z;
+		} else {
+			N.rlo[0] = box.lo.x; N.rlo[1] = box.lo.y; N.rlo[2] = box.lo.z;
+			N.rhi[0] = box.hi.x; N.rhi[1] = box.hi.y; N.rhi[2] = box.hi.z;
+		}
+	}
+	int child = node;
+	node = W.nodeParent[node];
+	while (node >= 0) {
+		BvhNode &N = W.nodes[node];
+		int ch = N.left == child ? bt_grow3(N.llo, N.lhi, box.lo, box.hi) : bt_grow3(N.rlo, N.rhi, box.lo, box.hi);
+		/* already inside: every higher ancestor contains this node's box, or will by the end of
+		 * the launch (whoever grew it is still climbing with a box whose union covers ours) */
+		if (!ch) break;
+		child = node;
+		node = W.nodeParent[node];
+	}
+}
+
+/* Bookkeeping of the non-speculative k_narrow (block 0, thread 0) once k_refit / k_pairs have
+ * consumed the invalidation: np = CT_PAIR_N as this narrow phase sees it. */
+static BT_HD void bt_consume_cache_flags(const DevWorld &W, u32 np) {
+	if (!W.ctr[CT_CACHE_INVALID]) return;
+	if (!bt_patch_mode(W)) {
+		W.ctr[CT_PAIR_N_FULL] = np;
+		W.ctr[CT_CACHE_FULL] = 0;
+	} else {
+		/* patches only append: once the list has grown by half, the next build is a full one */
+		u32 f = W.ctr[CT_PAIR_N_FULL];
+		if (np > f + f / 2 + 4096u) W.ctr[CT_CACHE_FULL] = 1;
+	}
+	W.ctr[CT_DIRTY_N] = 0;
+	W.ctr[CT_PATCH_EPOCH]++;
+	W.ctr[CT_CACHE_INVALID] = 0;
+}
+
 static BT_HD void t_refit(const DevWorld &W, int t, int cond) {
 	int L = W.n_leaves;
 	if (t >= L) return;
 	if (cond && !W.ctr[CT_CACHE_INVALID]) return; /* the cached pairs still cover everybody: nothing to do */
+	if (cond && bt_patch_mode(W)) { t_refit_patch(W, t); return; }
 	if (cond && t == 0) { W.ctr[CT_PAIR_N] = 0; bt_add32(&W.ctr[CT_PAIR_BUILDS], 1u); }
 	i32 e = W.leafEnt[t];
 	Box6 box;
 	if (bt_is_leaf_ent(W, e)) {
-		i32 lo[3], hi[3];
-		int4 cc = W.center[e];
-		bt_swept_box(W.ray_mode ? cc : W.old[e], cc, W.radius[e], lo, hi);
-		int m = W.ray_mode ? 0 : W.margin;
-		box.lo = make_int4(lo[0] - m, lo[1] - m, lo[2] - m, W.world[e]);
-		box.hi = make_int4(hi[0] + m, hi[1] + m, hi[2] + m, W.world[e]);
-		if (!W.ray_mode) W.ibox[e] = box;
+		box = bt_inflated_box(W, e);
+		if (!W.ray_mode) { W.ibox[e] = box; W.leafOf[e] = t; }
 	} else { /* died since the tree was built: empty box, never overlaps */
 		box.lo = make_int4(INT32_MAX, INT32_MAX, INT32_MAX, 0xffff);
 		box.hi = make_int4(INT32_MIN, INT32_MIN, INT32_MIN, 0);
@@ -834,6 +938,58 @@ static BT_HD void t_collide(const DevWorld &W, int t, i32 *stack, int stride, Lo
  * for a pair from both ends, like the reference does when both ends are scanned
  * (ent.cpp:446-449).  This plays the role of velbox's cached `intersects` lists
  * (velbox/box.cpp:95-136) within a tick. */
+static BT_HD int bt_box_touch(const Box6 &a, const Box6 &b) {
+	return (a.lo.x <= b.hi.x) & (b.lo.x <= a.hi.x) & (a.lo.y <= b.hi.y) & (b.lo.y <= a.hi.y) & (a.lo.z <= b.hi.z) &
+	       (b.lo.z <= a.hi.z);
+}
+
+/* Patch of the pair list, thread t = t-th entry of dirtyList (velbox_single_refresh,
+ * velbox/box.cpp:95-136, for the boxes that moved): the entity's new box is checked against the
+ * whole tree and every neighbour it did not already touch with its OLD box is appended.
+ * Invariant kept: the list holds every pair whose current inflated boxes touch.  Pairs that
+ * stopped touching stay until the next full build (the narrow phase rejects them). */
+template <class Emit> static BT_HD void t_pairs_patch(const DevWorld &W, int t, i32 *stack, int stride, Emit &emit) {
+	if ((u32)t >= W.ctr[CT_DIRTY_N] || W.n_leaves < 2) return;
+	i32 a = W.dirtyList[t];
+	if (!bt_is_leaf_ent(W, a)) return;
+	const u32 stamp = W.ctr[CT_PATCH_EPOCH] + 1u;
+	const Box6 q = W.ibox[a], qo = W.iboxOld[a];
+	const u32 wa = (u32)q.lo.w;
+	const i32 qlo[3] = {q.lo.x, q.lo.y, q.lo.z}, qhi[3] = {q.hi.x, q.hi.y, q.hi.z};
+	int sp = 0, node = 0;
+	while (1) {
+		const NodeRegs N = bt_load_node(W, node);
+		i32 li = N.d.x, ri = N.d.y;
+		int ovL = bt_touch_left(N, qlo, qhi, wa);
+		int ovR = bt_touch_right(N, qlo, qhi, wa);
+#pragma unroll 1
+		for (int side = 0; side < 2; side++) {
+			i32 ci = side ? ri : li;
+			if (!(side ? ovR : ovL) || ci >= 0) continue;
+			i32 b = W.leafEnt[~ci];
+			if (b == a) continue;
+			int bdirty = W.dirtyStamp[b] == stamp;
+			const Box6 bo = bdirty ? W.iboxOld[b] : W.ibox[b];
+			if (bt_box_touch(qo, bo)) continue; /* they touched before this patch: already cached */
+			if (bdirty && b < a) continue;       /* both moved: the lower index emits */
+			emit(a, b);
+		}
+		int goL = ovL && li >= 0, goR = ovR && ri >= 0;
+		if (goL) {
+			node = li;
+			if (goR) {
+				if (sp < BT_STACK) stack[(sp++) * stride] = ri;
+				else W.ctr[CT_ERROR] = (u32)(-BT_ERR_OVERFLOW);
+			}
+		} else if (goR) {
+			node = ri;
+		} else {
+			if (sp == 0) break;
+			node = stack[(--sp) * stride];
+		}
+	}
+}
+
 template <class Emit> static BT_HD void t_pairs(const DevWorld &W, int t, i32 *stack, int stride, Emit &emit) {
 	int L = W.n_leaves;
 	if (t >= L || L < 2) return;

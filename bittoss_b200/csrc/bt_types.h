@@ -101,6 +101,11 @@ enum {
 	CT_ANY_ODD = 38,     /* CT_ANY_PROPOSAL of odd iteration ids (even ones use slot 0): an iteration never
 	                      * reads the slot it is itself stamping */
 	CT_EVENT_N = 40,     /* entries in events[] */
+	CT_CACHE_FULL = 41,  /* the next pair build must be a full one (upload, new tree, a jump, list grown stale) */
+	CT_DIRTY_N = 42,     /* entries in dirtyList: entities that left their inflated box since the last build / patch */
+	CT_PATCH_EPOCH = 43, /* counts consumed builds / patches; dirtyStamp[e] == epoch + 1 <=> e is in dirtyList */
+	CT_PAIR_N_FULL = 44, /* CT_PAIR_N right after the last full build */
+	CT_PAIR_PATCHES = 45, /* incremental pair-list patches (k_refit / k_pairs in patch mode) */
 	CT_WORDS = 64
 };
 enum { SK_ITERS = 0, SK_CAND, SK_POS, SK_PUSH, SK_SERIAL, SK_CRUSH, SK_FUMBLE, SK_NUM };
@@ -117,6 +122,10 @@ struct DevWorld {
 	i32 ray_mode;
 	i32 margin;   /* inflation of the boxes candidate pairs are cached with (collision tree only) */
 	i32 pair_cap; /* 1: tree over ALL live entities with static boxes (raycast), 0: collision tree */
+	i32 horizon;  /* ticks of undisturbed motion (velocity + gravity) the cached box is stretched ahead by:
+	               * velbox's validity idea (velbox/box.h:32-34), a box in free flight stays covered */
+	i32 patch;    /* incremental pair-list patches allowed (option pair_patch) */
+	i32 patch_shift; /* patch while dirty entities << patch_shift <= leaves, full build beyond */
 
 	i32 *wbegin, *wend, *flip, *gamerules, *rnd; /* per world */
 	u32 *wunsup;                                 /* per world: would-be invocations of unimplemented handlers */
@@ -147,6 +156,10 @@ struct DevWorld {
 	Box6 *nodeBox, *leafBox;
 	i32 *nodeHi;     /* last leaf position below each internal node */
 	Box6 *ibox;      /* per entity: the inflated swept box of the last refit */
+	Box6 *iboxOld;   /* per entity: the box it had before the patch of the current epoch (dirty entities only) */
+	i32 *leafOf;     /* entity -> sorted leaf position (inverse of leafEnt) */
+	i32 *dirtyList;
+	u32 *dirtyStamp;
 	u64 *pairs;      /* a | b<<32, a = entity at the earlier leaf position */
 
 	int4 *events;    /* {kind<<8 | handler, me slot, him slot, arg}; only the serial lane appends */

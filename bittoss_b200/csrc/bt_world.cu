@@ -77,7 +77,7 @@ struct bt_world {
 	i64 max_iterations;
 	i64 pair_cache; /* 1: cached candidate pairs (k_pairs + k_narrow); 0: traverse every iteration (k_collide) */
 	i64 pair_rebuilds, pair_overflows;
-	u32 seen_pair_builds, pair_builds_at_tree;
+	u32 seen_pair_builds, seen_pair_patches, pair_builds_at_tree; /* the last one counts builds + patches */
 	int predicted_iters; /* iterations (incl. the final empty one) the last tick needed: run-ahead depth */
 	i64 run_ahead;       /* option: 1 = enqueue the predicted iterations without waiting for the host */
 	bt_tick_stats stats;
@@ -183,7 +183,7 @@ int bt_world_create(bt_world **out, int device, int32_t max_ents, int32_t max_sl
 	w->device = device;
 	w->cap_ents = max_ents; w->cap_sliders = max_sliders; w->cap_wires = max_wires; w->cap_worlds = max_worlds;
 	w->tree_valid = false; w->deltas_pending = true; w->ticks_since_build = 0; w->full_flush_left = 2; w->ctrls_fused = false;
-	w->rebuild_every = 16; w->max_iterations = 100000; w->pair_cache = 1; w->pair_rebuilds = 0; w->pair_overflows = 0; w->seen_pair_builds = 0; w->pair_builds_at_tree = 0; w->profiling = false; w->ray_valid = false;
+	w->rebuild_every = 16; w->max_iterations = 100000; w->pair_cache = 1; w->pair_rebuilds = 0; w->pair_overflows = 0; w->seen_pair_builds = 0; w->seen_pair_patches = 0; w->pair_builds_at_tree = 0; w->profiling = false; w->ray_valid = false;
 	w->h_flag = NULL; w->ev0 = w->ev1 = NULL; w->stream = NULL;
 	*out = w;
 #define TRY(x) do { int _r = (x); if (_r) { bt_world_destroy(w); *out = NULL; return _r; } } while (0)
@@ -218,6 +218,8 @@ int bt_world_create(bt_world **out, int device, int32_t max_ents, int32_t max_sl
 	TRY(dalloc(w, &W.leafParent, n)); TRY(dalloc(w, &W.nodeParent, n)); TRY(dalloc(w, &W.nodeCount, n));
 	TRY(dalloc(w, &W.nodes, n)); TRY(dalloc(w, &W.nodeBox, n)); TRY(dalloc(w, &W.leafBox, n));
 	TRY(dalloc(w, &W.nodeHi, n)); TRY(dalloc(w, &W.ibox, n));
+	TRY(dalloc(w, &W.iboxOld, n)); TRY(dalloc(w, &W.leafOf, n)); TRY(dalloc(w, &W.dirtyList, n)); TRY(dalloc(w, &W.dirtyStamp, n));
+	W.patch = 1; W.patch_shift = 4;
 	W.pair_cap = (i32)std::min<size_t>((size_t)1 << 30, 12 * n + 4096);
 	W.margin = 32;
 	TRY(dalloc(w, &W.pairs, (size_t)W.pair_cap));
@@ -248,6 +250,9 @@ int bt_world_set_option(bt_world *w, const char *name, int64_t value) {
 	if (!strcmp(name, "max_iterations")) { w->max_iterations = value; return BT_OK; }
 	if (!strcmp(name, "allow_unsupported")) { w->W.lenient = value != 0; return BT_OK; }
 	if (!strcmp(name, "pair_cache")) { w->pair_cache = value != 0; return BT_OK; }
+	if (!strcmp(name, "cache_horizon")) { w->W.horizon = value < 0 ? 0 : (value > 64 ? 64 : (i32)value); return BT_OK; }
+	if (!strcmp(name, "pair_patch")) { w->W.patch = value != 0; return BT_OK; }
+	if (!strcmp(name, "patch_shift")) { w->W.patch_shift = value < 0 ? 0 : (value > 20 ? 20 : (i32)value); return BT_OK; }
 	if (!strcmp(name, "run_ahead")) { w->run_ahead = value != 0; return BT_OK; }
 	if (!strcmp(name, "cache_margin")) { w->W.margin = value < 0 ? 0 : (i32)value; return BT_OK; }
 	return BT_ERR_ARG;
@@ -265,6 +270,7 @@ template <typename T> static int h2d(bt_world *w, T *dst, const std::vector<T> &
 static bool supported(uint32_t mask, int id) { return id < 32 && ((mask >> id) & 1u); }
 extern "C" {
 
+static int raise_cache_invalid(bt_world *w);
 int bt_world_upload(bt_world *w, const bt_world_desc *d) {
 	if (!w || !d || d->n_ents < 0 || d->n_worlds < 1) return BT_ERR_ARG;
 	if (d->n_ents > w->cap_ents || d->n_sliders > w->cap_sliders || d->n_wires > w->cap_wires ||
@@ -367,11 +373,9 @@ int bt_world_upload(bt_world *w, const bt_world_desc *d) {
 	UPRAW(W.wire_off, d->wire_off, n + 1, i32); UPRAW(W.wire_to, d->wire_to, d->n_wires, i32);
 	UP(W.wire_cnt, wire_cnt);
 	CK(cudaMemsetAsync(W.ctr, 0, sizeof(u32) * CT_WORDS, w->stream));
-	{
-		u32 one = 1;
-		CK(cudaMemcpyAsync(&W.ctr[CT_CACHE_INVALID], &one, sizeof(u32), cudaMemcpyHostToDevice, w->stream));
-	}
-	w->seen_pair_builds = 0; w->pair_builds_at_tree = 0;
+	{ int rr = raise_cache_invalid(w); if (rr) return rr; }
+	CK(cudaMemsetAsync(W.dirtyStamp, 0, sizeof(u32) * (size_t)w->cap_ents, w->stream));
+	w->seen_pair_builds = 0; w->seen_pair_patches = 0; w->pair_builds_at_tree = 0;
 	CK(cudaMemsetAsync(W.nodeCount, 0, sizeof(u32) * (size_t)w->cap_ents, w->stream));
 	CK(cudaMemsetAsync(W.wflush, 0, (size_t)nw, w->stream));
 	CK(cudaStreamSynchronize(w->stream));
@@ -407,7 +411,6 @@ static int radix_sort(bt_world *w, int key_bits) {
 
 static int bits_for(u32 x) { int b = 0; while (x) { b++; x >>= 1; } return b; }
 
-static int raise_cache_invalid(bt_world *w);
 
 /* Morton sort + Karras hierarchy over every live boxed entity */
 static int build_tree(bt_world *w) {
@@ -435,7 +438,7 @@ static int build_tree(bt_world *w) {
 	if (!W.ray_mode) { int rr = raise_cache_invalid(w); if (rr) return rr; }
 	w->tree_valid = true;
 	w->ticks_since_build = 0;
-	w->pair_builds_at_tree = w->seen_pair_builds + 1; /* + the pair search this build itself forces */
+	w->pair_builds_at_tree = w->seen_pair_builds + w->seen_pair_patches + 1; /* + the pair search this build itself forces */
 	w->stats.tree_builds++;
 	return 0;
 }
@@ -449,8 +452,10 @@ static int refit(bt_world *w, bool cond) {
 	return 0;
 }
 
+/* the next pair build must be a full one */
 static int raise_cache_invalid(bt_world *w) {
 	static const u32 one = 1;
+	CK(cudaMemcpyAsync(&w->W.ctr[CT_CACHE_FULL], &one, sizeof(u32), cudaMemcpyHostToDevice, w->stream));
 	CK(cudaMemcpyAsync(&w->W.ctr[CT_CACHE_INVALID], &one, sizeof(u32), cudaMemcpyHostToDevice, w->stream));
 	return 0;
 }
@@ -498,7 +503,7 @@ static int do_physics(bt_world *w, bool gravity) {
 	/* ... and an old tree is only rebuilt if pair lists are being rebuilt at all (a world at
 	 * rest keeps its cached pairs for as long as nobody leaves its inflated box) */
 	if (!w->tree_valid || (w->ticks_since_build >= w->rebuild_every &&
-	                       (!w->pair_cache || w->seen_pair_builds > w->pair_builds_at_tree))) {
+	                       (!w->pair_cache || w->seen_pair_builds + w->seen_pair_patches > w->pair_builds_at_tree))) {
 		int r = build_tree(w);
 		if (r) return r;
 	}
@@ -563,6 +568,10 @@ static int do_physics(bt_world *w, bool gravity) {
 			w->stats.pair_builds += (i64)(w->h_flag[CT_PAIR_BUILDS] - w->seen_pair_builds);
 			w->stats.pairs_cached += (i64)w->h_flag[CT_PAIR_N];
 			w->seen_pair_builds = w->h_flag[CT_PAIR_BUILDS];
+		}
+		if (use_cache && w->h_flag[CT_PAIR_PATCHES] != w->seen_pair_patches) {
+			w->stats.pair_patches += (i64)(w->h_flag[CT_PAIR_PATCHES] - w->seen_pair_patches);
+			w->seen_pair_patches = w->h_flag[CT_PAIR_PATCHES];
 		}
 		if (use_cache && w->h_flag[CT_PAIR_OVERFLOW]) {
 			/* more touching pairs than the buffer holds: every kernel of this batch stood down;
@@ -848,7 +857,7 @@ int bt_world_assign(bt_world *dst, bt_world *src) {
 	dst->full_flush_left = src->full_flush_left; dst->ctrls_fused = src->ctrls_fused;
 	dst->ticks_since_build = src->ticks_since_build; dst->rebuild_every = src->rebuild_every;
 	dst->max_iterations = src->max_iterations; dst->pair_cache = src->pair_cache;
-	dst->seen_pair_builds = src->seen_pair_builds; dst->pair_builds_at_tree = src->pair_builds_at_tree;
+	dst->seen_pair_builds = src->seen_pair_builds; dst->seen_pair_patches = src->seen_pair_patches; dst->pair_builds_at_tree = src->pair_builds_at_tree;
 	dst->predicted_iters = src->predicted_iters; dst->run_ahead = src->run_ahead;
 	dst->stats = src->stats; dst->up_root_order = src->up_root_order;
 	dst->ray_valid = src->ray_valid; dst->ranks_valid = src->ranks_valid;

@@ -123,11 +123,12 @@ typedef struct bt_tick_stats {
 	int64_t tree_refits;     /* bottom-up refits                                         */
 	int64_t live_ents;       /* live entities after the last tick                        */
 	int64_t entity_ticks;    /* sum over ticks of live entities after the tick           */
-	int64_t pair_builds;     /* k_pairs launches (>= 1 per tick; more when the cache is invalidated) */
+	int64_t pair_builds;     /* full rebuilds of the cached pair list (tree refit + pair search) */
 	int64_t pairs_cached;    /* unordered candidate pairs written by those launches      */
 	int64_t pair_overflows;  /* ticks that fell back to per-iteration traversal          */
 	int64_t unsupported_events; /* lenient uploads only ("allow_unsupported"): times a handler with no device
 	                           * implementation would have been invoked; != 0 means the state diverged */
+	int64_t pair_patches;    /* incremental updates of the cached pair list (moved entities only)  */
 } bt_tick_stats;
 
 /* Per-kernel-class device timing, filled only while profiling is enabled. */

@@ -32,7 +32,7 @@ struct Emu {
 	std::vector<i32> up_root_order;
 	int pair_cache;   /* 1: k_pairs + k_narrow, 0: k_collide every iteration */
 	u32 pair_builds_at_tree;
-	int64_t pair_rebuilds;
+	int64_t pair_rebuilds, pair_patches;
 	int shuffle_seed; /* != 0: run the threads of order-sensitive kernels in a scrambled order */
 };
 
@@ -69,7 +69,7 @@ Emu *bte_create(const bt_world_desc *d, int rebuild_every, int shuffle_seed) {
 	memset(&E->W, 0, sizeof(E->W));
 	memset(&E->st, 0, sizeof(E->st));
 	E->tree_valid = false; E->ticks_since_build = 0; E->ctrls_fused = false; E->full_flush_left = 2; E->rebuild_every = rebuild_every > 0 ? rebuild_every : 1;
-	E->iterations = 0; E->ticks = 0; E->shuffle_seed = shuffle_seed; E->pair_cache = 1; E->pair_rebuilds = 0;
+	E->iterations = 0; E->ticks = 0; E->shuffle_seed = shuffle_seed; E->pair_cache = 1; E->pair_rebuilds = 0; E->pair_patches = 0;
 	DevWorld &W = E->W;
 	const int n = d->n_ents, nw = d->n_worlds;
 	W.n = n; W.n_worlds = nw;
@@ -87,6 +87,8 @@ Emu *bte_create(const bt_world_desc *d, int rebuild_every, int shuffle_seed) {
 	A(E, &W.keys, n); A(E, &W.keys_alt, n); A(E, &W.leafEnt, n); A(E, &W.leafEnt_alt, n);
 	A(E, &W.leafParent, n); A(E, &W.nodeParent, n); A(E, &W.nodeCount, n); A(E, &W.nodes, n);
 	A(E, &W.nodeBox, n); A(E, &W.leafBox, n); A(E, &W.nodeHi, n); A(E, &W.ibox, n);
+	A(E, &W.iboxOld, n); A(E, &W.leafOf, n); A(E, &W.dirtyList, n); A(E, &W.dirtyStamp, n);
+	W.patch = 1; W.patch_shift = 4;
 	W.pair_cap = 12 * n + 4096; W.margin = 32;
 	A(E, &W.pairs, W.pair_cap);
 	W.serial_cap = 1 << 16; W.dead_cap = n ? n : 1; W.event_cap = 1 << 16;
@@ -144,7 +146,7 @@ Emu *bte_create(const bt_world_desc *d, int rebuild_every, int shuffle_seed) {
 	}
 	for (int g = 0; g < nw; g++)
 		if (W.wbegin[g] > W.wend[g]) W.wbegin[g] = W.wend[g] = 0;
-	W.ctr[CT_CACHE_INVALID] = 1;
+	W.ctr[CT_CACHE_INVALID] = 1; W.ctr[CT_CACHE_FULL] = 1;
 	E->pair_builds_at_tree = 0;
 	E->deltas_pending = deltas;
 	E->up_root_order.assign(d->root_order, d->root_order + n);
@@ -179,10 +181,10 @@ static void build_tree(Emu *E) {
 	for (i32 i = 0; i < W.n; i++) { W.keys[i] = k2[i]; W.leafEnt[i] = v2[i]; }
 	for (i32 i = 0; i < L - 1; i++) t_lbvh_node(W, i);
 	for (i32 i = 0; i < W.n; i++) W.nodeCount[i] = 0;
-	if (!W.ray_mode) W.ctr[CT_CACHE_INVALID] = 1;
+	if (!W.ray_mode) { W.ctr[CT_CACHE_INVALID] = 1; W.ctr[CT_CACHE_FULL] = 1; }
 	E->tree_valid = true;
 	E->ticks_since_build = 0;
-	E->pair_builds_at_tree = W.ctr[CT_PAIR_BUILDS] + 1; /* + the pair search this build itself forces */
+	E->pair_builds_at_tree = W.ctr[CT_PAIR_BUILDS] + W.ctr[CT_PAIR_PATCHES] + 1; /* + the pair search this build itself forces */
 }
 
 static void refit(Emu *E, int cond) {
@@ -218,7 +220,7 @@ static int do_physics(Emu *E, bool gravity) {
 		E->deltas_pending = false;
 	}
 	if (!E->tree_valid || (E->ticks_since_build >= E->rebuild_every &&
-	                       (!E->pair_cache || W.ctr[CT_PAIR_BUILDS] > E->pair_builds_at_tree)))
+	                       (!E->pair_cache || W.ctr[CT_PAIR_BUILDS] + W.ctr[CT_PAIR_PATCHES] > E->pair_builds_at_tree)))
 		build_tree(E);
 	E->ticks_since_build++;
 	std::vector<i32> stack(BT_STACK);
@@ -236,17 +238,23 @@ static int do_physics(Emu *E, bool gravity) {
 		u32 any = 0;
 		if (E->pair_cache) {
 			if (cache_state != 2) {
-				u32 before = W.ctr[CT_PAIR_BUILDS];
+				u32 before = W.ctr[CT_PAIR_BUILDS], pbefore = W.ctr[CT_PAIR_PATCHES];
 				refit(E, 1);
 				{
 					HostEmit emit = {W};
-					std::vector<i32> o = order(E, W.n_leaves);
-					for (i32 t : o) t_pairs(W, t, stack.data(), 1, emit);
+					if (W.ctr[CT_CACHE_INVALID] && bt_patch_mode(W)) {
+						std::vector<i32> o = order(E, (i32)W.ctr[CT_DIRTY_N]);
+						for (i32 t : o) t_pairs_patch(W, t, stack.data(), 1, emit);
+					} else {
+						std::vector<i32> o = order(E, W.n_leaves);
+						for (i32 t : o) t_pairs(W, t, stack.data(), 1, emit);
+					}
 				}
+				if (W.ctr[CT_PAIR_PATCHES] != pbefore) E->pair_patches++;
 				if ((i32)W.ctr[CT_PAIR_N] > W.pair_cap) return BT_ERR_OVERFLOW;
 				if (W.ctr[CT_PAIR_BUILDS] != before) E->pair_rebuilds++;
 			}
-			W.ctr[CT_CACHE_INVALID] = 0; /* narrow kernels, block 0 thread 0 */
+			bt_consume_cache_flags(W, W.ctr[CT_PAIR_N]); /* narrow kernels, block 0 thread 0 */
 			{
 				std::vector<i32> o = order(E, (i32)W.ctr[CT_PAIR_N]);
 				for (i32 p : o) t_narrow(W, W.pairs[p], E->st, any);
@@ -319,8 +327,12 @@ void bte_set_option(Emu *E, const char *name, int64_t v) {
 	if (!strcmp(name, "pair_cache")) E->pair_cache = v != 0;
 	if (!strcmp(name, "allow_unsupported")) E->W.lenient = v != 0;
 	if (!strcmp(name, "cache_margin")) E->W.margin = (i32)v;
+	if (!strcmp(name, "cache_horizon")) E->W.horizon = (i32)v;
+	if (!strcmp(name, "pair_patch")) E->W.patch = v != 0;
+	if (!strcmp(name, "patch_shift")) E->W.patch_shift = (i32)v;
 }
 int64_t bte_pair_rebuilds(Emu *E) { return E->pair_rebuilds; }
+int64_t bte_pair_patches(Emu *E) { return E->pair_patches; }
 int64_t bte_events(Emu *E) { return (int64_t)E->W.ctr[CT_EVENT_N]; }
 int64_t bte_unsupported(Emu *E) { return (int64_t)E->W.ctr[CT_UNSUPPORTED]; }
 int64_t bte_unsupported_last(Emu *E) { return (int64_t)E->W.ctr[CT_UNSUP_LAST]; }

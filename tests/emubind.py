@@ -40,6 +40,8 @@ class EmuWorld:
         L.bte_set_option.argtypes = [C.c_void_p, C.c_char_p, C.c_int64]
         L.bte_pair_rebuilds.argtypes = [C.c_void_p]
         L.bte_pair_rebuilds.restype = C.c_int64
+        L.bte_pair_patches.argtypes = [C.c_void_p]
+        L.bte_pair_patches.restype = C.c_int64
         L.bte_events.argtypes = [C.c_void_p]
         L.bte_events.restype = C.c_int64
         L.bte_unsupported.argtypes = [C.c_void_p]
@@ -73,6 +75,9 @@ class EmuWorld:
 
     def pair_rebuilds(self):
         return int(self.L.bte_pair_rebuilds(self.h))
+
+    def pair_patches(self):
+        return int(self.L.bte_pair_patches(self.h))
 
     def hash(self):
         out = (C.c_uint64 * self.n_worlds)()

@@ -80,4 +80,27 @@ def test_pair_cache_modes_agree(emu, name):
             w.step(31)
             assert w.hash()[0] == int(ref[t]), t
     # a zero margin must have forced more pair rebuilds than a generous one
-    assert worlds[1].pair_rebuilds() >= worlds[3].pair_rebuilds()
+    assert worlds[1].pair_rebuilds() + worlds[1].pair_patches() >= worlds[3].pair_rebuilds() + worlds[3].pair_patches()
+
+
+@pytest.mark.parametrize("name", ["stack4k_pushall", "stack2k_8high", "spider_kick", "diner_kick", "lobby_kick", "arena_kick"])
+@pytest.mark.parametrize("rebuild_every", [2, 1000])
+def test_incremental_pair_patches_agree(emu, name, rebuild_every):
+    """patching the cached pair list for the entities that moved == rebuilding it from scratch"""
+    if name not in SCENARIOS:
+        pytest.skip("no such fixture")
+    wa, ref = load_scenario(name)
+    worlds = []
+    for patch, margin, horizon in ((0, 8, 0), (1, 8, 0), (1, 0, 0), (1, 64, 0), (1, 8, 5), (0, 0, 3)):
+        w = emu.EmuWorld(wa, rebuild_every=rebuild_every, shuffle_seed=11)
+        w.set_option("pair_patch", patch)
+        w.set_option("cache_margin", margin)
+        w.set_option("cache_horizon", horizon)
+        worlds.append(w)
+    for t in range(len(ref)):
+        for w in worlds:
+            w.step(31)
+            assert w.hash()[0] == int(ref[t]), t
+    assert worlds[0].pair_patches() == 0
+    if wa.n >= 1000:
+        assert worlds[1].pair_patches() > 0

@@ -122,12 +122,15 @@ def test_unsupported_handler_is_refused(bt):
 def test_cuda_pair_cache_modes_agree(bt, name):
     """cached candidate pairs (k_pairs + k_narrow, any margin) == traversal every iteration (k_collide)"""
     wa, ref = load_scenario(name)
-    for cache, margin in ((0, 16), (1, 0), (1, 32), (1, 300)):
+    for cache, margin, patch in ((0, 16, 1), (1, 0, 1), (1, 32, 1), (1, 300, 1), (1, 0, 0), (1, 32, 0)):
         w = bt.World(wa)
         w.set_option("pair_cache", cache)
         w.set_option("cache_margin", margin)
+        w.set_option("pair_patch", patch)
         hs = w.tick(len(ref), hashes=True)
-        assert [int(x) for x in hs[:, 0]] == [int(x) for x in ref], (cache, margin)
+        assert [int(x) for x in hs[:, 0]] == [int(x) for x in ref], (cache, margin, patch)
+        if not patch:
+            assert w.stats()["pair_patches"] == 0
         w.close()
 
 
@@ -177,14 +180,19 @@ def test_cuda_schedule_variants_agree_at_scale(bt, oracle_lib):
     hash stream (grids larger than one wave, many blocks, stand-downs), and it must be the oracle's"""
     wa = bt.synth_boxstack(200000, 4, 777, 64, 60)
     streams = []
-    for run_ahead, cache, period in ((1, 1, 16), (0, 1, 16), (1, 1, 3), (0, 0, 5)):
+    patches = []
+    for run_ahead, cache, period, patch in ((1, 1, 16, 1), (0, 1, 16, 1), (1, 1, 3, 1), (0, 0, 5, 1), (1, 1, 16, 0),
+                                            (1, 1, 1000, 1)):
         w = bt.World(wa)
         w.set_option("run_ahead", run_ahead)
         w.set_option("pair_cache", cache)
         w.set_option("rebuild_every", period)
+        w.set_option("pair_patch", patch)
         streams.append([int(x) for x in w.tick(90, hashes=True)[:, 0]])
+        patches.append(w.stats()["pair_patches"])
         w.close()
-    assert streams[0] == streams[1] == streams[2] == streams[3]
+    assert all(s == streams[0] for s in streams[1:])
+    assert patches[0] > 0 and patches[4] == 0  # the incremental path was really exercised
     ow = oracle_lib.create(wa)
     for t in range(10):
         ow.step(31)

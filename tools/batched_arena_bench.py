@@ -31,6 +31,10 @@ def main():
     ap.add_argument("--kick-max", type=int, default=150)
     ap.add_argument("--level", default=os.path.join(ROOT, "oracle", "_ref", "data", "arena.sav"))
     ap.add_argument("--check", type=int, default=4)
+    ap.add_argument("--patch-shift", type=int, default=-1)
+    ap.add_argument("--horizon", type=int, default=-1)
+    ap.add_argument("--patch", type=int, default=1)
+    ap.add_argument("--margin", type=int, default=-1)
     ap.add_argument("--profile", action="store_true", help="extra pass with CUDA events around every launch")
     args = ap.parse_args()
     import torch
@@ -58,6 +62,13 @@ def main():
         w = bittoss_b200.World(None, device=lr, max_ents=batch.n, max_sliders=int(batch.desc.n_sliders),
                                max_wires=max(1, int(batch.desc.n_wires)), max_worlds=len(world_ids))
         w.set_option("allow_unsupported", 1)
+        if args.horizon >= 0:
+            w.set_option("cache_horizon", args.horizon)
+        if args.patch_shift >= 0:
+            w.set_option("patch_shift", args.patch_shift)
+        w.set_option("pair_patch", args.patch)
+        if args.margin >= 0:
+            w.set_option("cache_margin", args.margin)
         w.upload(batch)
         return w
 
@@ -92,7 +103,7 @@ def main():
             "entity_ticks_per_sec": et / (ms_max * 1e-3), "n_gpus": ws, "worlds": args.worlds, "ticks": args.ticks,
             "entities_per_world": n1, "ms_per_tick": ms_max / args.ticks, "level": os.path.basename(args.level),
             "iterations_per_tick": st["iterations"] / max(1, st["ticks"]), "crushes": st["crushes"],
-            "unsupported_events": st["unsupported_events"], "distinct_hashes": len(set(all_hashes)),
+            "unsupported_events": st["unsupported_events"], "pair_builds": st["pair_builds"], "pair_patches": st["pair_patches"], "tree_builds": st["tree_builds"], "distinct_hashes": len(set(all_hashes)),
             "alone_equals_batched": ok, "checked_worlds": args.check}))
     if dist is not None:
         dist.destroy_process_group()
