@@ -40,6 +40,16 @@ class BtEvent(C.Structure):
     _fields_ = [(k, C.c_int32) for k in ("kind", "handler", "world", "me_uid", "him_uid", "arg")]
 
 
+class BtRequest(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("world", C.c_int32), ("me_uid", C.c_int32), ("other_uid", C.c_int32),
+                ("a", C.c_int32 * 3)]
+
+
+# request kinds (include/bittoss_b200.h BT_REQ_*)
+REQ_DROP, REQ_DEAD, REQ_PICKUP, REQ_BUTTON, REQ_VEL, REQ_CENTER, REQ_SLIDER, REQ_ERASE, REQ_TYPEMASK, \
+    REQ_COLLIDEMASK = range(10)
+
+
 class BtProfile(C.Structure):
     _fields_ = [("n", C.c_int32), ("name", C.c_char_p * 24), ("launches", C.c_int64 * 24), ("ms", C.c_double * 24)]
 
@@ -89,6 +99,7 @@ def lib():
     L.bt_world_stream.restype = C.c_void_p
     L.bt_world_hash.argtypes = [C.c_void_p, _u64p]
     L.bt_world_stats.argtypes = [C.c_void_p, C.POINTER(BtTickStats), C.c_int]
+    L.bt_world_apply_requests.argtypes = [C.c_void_p, C.POINTER(BtRequest), C.c_int32]
     L.bt_world_drain_events.argtypes = [C.c_void_p, C.POINTER(BtEvent), C.c_int32, C.POINTER(C.c_int32)]
     L.bt_world_unsupported.argtypes = [C.c_void_p, C.POINTER(C.c_uint32)]
     L.bt_world_profile_enable.argtypes = [C.c_void_p, C.c_int]
@@ -219,6 +230,15 @@ class World:
         _ck(self.L.bt_world_apply_host_deltas(self.h, C.cast(d_center.ctypes.data, _i32p),
                                               C.cast(d_vel.ctypes.data, _i32p), n), "bt_world_apply_host_deltas")
 
+    def apply_requests(self, reqs):
+        """deferred updater calls made by host-side handlers: [(kind, world, me_uid, other_uid, (a0, a1, a2)), ...]"""
+        buf = (BtRequest * max(1, len(reqs)))()
+        for i, (kind, world, me, other, a) in enumerate(reqs):
+            buf[i].kind, buf[i].world, buf[i].me_uid, buf[i].other_uid = int(kind), int(world), int(me), int(other)
+            for k in range(3):
+                buf[i].a[k] = int(a[k]) if k < len(a) else 0
+        _ck(self.L.bt_world_apply_requests(self.h, buf, len(reqs)), "bt_world_apply_requests")
+
     def read_state(self, center, vel):
         n = center.size // 3
         _ck(self.L.bt_world_read_state(self.h, C.cast(center.ctypes.data, _i32p), C.cast(vel.ctypes.data, _i32p), n),
@@ -252,7 +272,7 @@ class World:
         return {k: int(getattr(s, k)) for k, _ in BtTickStats._fields_}
 
     def drain_events(self, max_events=4096):
-        """host-side handler events (PUSH_TEAMSELECT / PUSH_LOADBLOCK) since the last drain"""
+        """host-side handler events (PUSH_TEAMSELECT / PUSH_LOADBLOCK, crush handlers) since the last drain"""
         buf = (BtEvent * max_events)()
         n = C.c_int32()
         _ck(self.L.bt_world_drain_events(self.h, buf, max_events, C.byref(n)), "bt_world_drain_events")

@@ -49,6 +49,10 @@ __global__ void __launch_bounds__(BT_BLOCK) k_flush_serial(DevWorld W) {
 	stats_flush(W, st);
 }
 __global__ void __launch_bounds__(BT_BLOCK) k_flush_misc(DevWorld W) { t_flush_misc(W, TID); }
+__global__ void k_requests(DevWorld W, const BtReq *q, i32 n) {
+	if (threadIdx.x != 0 || blockIdx.x != 0) return;
+	for (i32 i = 0; i < n; i++) t_request(W, q[i]);
+}
 __global__ void __launch_bounds__(BT_BLOCK) k_gravity(DevWorld W) { t_gravity(W, TID); }
 __global__ void __launch_bounds__(BT_BLOCK) k_world_rules(DevWorld W) { t_world_rules(W, TID); }
 __global__ void __launch_bounds__(BT_BLOCK) k_flush2_apply(DevWorld W) { t_flush2_apply(W, TID); }

@@ -62,6 +62,7 @@ struct LocalStats {
 };
 
 static BT_HD void bt_check_cover(const DevWorld &W, i32 e, const int4 &o, const int4 &c);
+static BT_HD void bt_upickup(const DevWorld &W, i32 p, i32 e, i32 holdFlags);
 
 /* ------------------------------------------------------------------------- */
 /* helpers                                                                   */
@@ -149,12 +150,13 @@ static BT_HD int bt_who_moves(int id, u32 ta, u32 tb, int axis, int dir) {
 
 /* which handler IDs have a device implementation (bt_world_upload checks these) */
 #define BT_SUPPORTED_WHOMOVES 0x1ffu /* 0..8 */
-#define BT_SUPPORTED_PUSH 0x0b7u     /* NIL, PLAYER, LOGIC, TEAMSELECT (event), SCOREBOARD, LOADBLOCK (event) */
-#define BT_SERIAL_PUSH 0x0b2u        /* of those, the ones that run in the serial lane: PLAYER, TEAMSELECT, SCOREBOARD, LOADBLOCK */
+#define BT_SUPPORTED_PUSH 0x3ffu     /* the whole catalog (handlerRegistrar.h:163-175); TEAMSELECT / LOADBLOCK as events */
+#define BT_SERIAL_PUSH 0x3f2u        /* the ones that run in the serial lane (order-sensitive side effects): all but NIL, LOGIC, SEAT */
+#define TICK_BOTTLE 37
 #define TICK_PLAYER 7                /* handlerRegistrar.h:93-101 */
 #define BT_SUPPORTED_PUSHED 0x12fu   /* NIL, PUDDLEJUMP, FRAGILE, FLAG, PLAYER, BULLET */
-#define BT_SUPPORTED_PAIR 0x029u     /* NIL, FUMBLED_DECOR, PICKUP_PLAYER */
-#define BT_SUPPORTED_CRUSH 0x001u    /* NIL (others are host-side events) */
+#define BT_SUPPORTED_PAIR 0x03fu     /* NIL, PICKUP_SEAT, FUMBLE_SEAT_OLD, FUMBLED_DECOR, FUMBLE_SEAT, PICKUP_PLAYER */
+#define BT_SUPPORTED_CRUSH 0x007u    /* NIL; FLAG and PLATFORM create entities (explode): delivered as host events */
 
 /* player_push player.c:108-165 (sliders s_equip_processed=10, s_editmode=11).  Returns 1 =
  * "I pick him up".  Only ever runs in the serial lane (see t_push): it reads and edits the
@@ -187,6 +189,85 @@ static BT_HD int bt_player_push(const DevWorld &W, i32 me, i32 him) {
 	return 1;
 }
 
+/* uWire / uUnwire entUpdaters.c:66-73: one pending request of each kind per entity and flush
+ * (a seat wires / unwires its single rider); a second, different one cannot be represented */
+static BT_HD void bt_uwire(const DevWorld &W, i32 e, i32 w) {
+	W.fullFlush[e] = 1;
+	W.ctr[CT_FLUSH_HINT] = 1;
+	if (W.wireAdd[e] >= 0 && W.wireAdd[e] != w) bt_unsup(W, e, 5, 0);
+	W.wireAdd[e] = w;
+}
+static BT_HD void bt_uunwire(const DevWorld &W, i32 e, i32 w) {
+	W.ctr[CT_FLUSH_HINT] = 1;
+	if (W.wireRm[e] >= 0 && W.wireRm[e] != w) bt_unsup(W, e, 5, 1);
+	W.wireRm[e] = w;
+}
+
+/* teleport_push teleport.c:12-37.  Serial lane only.  It reads the pad's and the destination's
+ * position while other pushes of the same iteration may move them; the reference interleaves
+ * those pushes in root order, the serial lane runs after them, so that case is refused. */
+static BT_HD int bt_teleport_push(const DevWorld &W, i32 me, i32 him) {
+	if (W.type[him] & (T_TERRAIN | T_OBSTACLE | T_DEBRIS)) bt_or32(&W.btn_v2[me], 1u);
+	i32 dest = -1;
+	for (i32 k = 0; k < W.wire_cnt[me]; k++) {
+		i32 w = W.wire_to[W.wire_off[me] + k];
+		if ((W.btn_v[w] >> 16) & 0xffu) {
+			if (dest >= 0) return 0; /* "Behavior with multiple teleport destinations active is undefined!" */
+			dest = w;
+		}
+	}
+	if (dest < 0) return 0;
+	if (W.ready[W.holdRoot[dest]] || W.ready[W.holdRoot[me]]) bt_unsup(W, me, 0, 6);
+	i32 r = W.holdRoot[him];
+	int4 dc = W.center[dest], mc = W.center[me], dv = W.vel[dest], mv = W.vel[me];
+	int4 a = W.d_center[r], b = W.d_vel[r];
+	a.x += dc.x - mc.x; a.y += dc.y - mc.y; a.z += dc.z - mc.z; /* uCenter(him->holdRoot, ...) */
+	b.x += dv.x - mv.x; b.y += dv.y - mv.y; b.z += dv.z - mv.z; /* uVel */
+	W.d_center[r] = a; W.d_vel[r] = b;
+	W.ctr[CT_ANY_DELTA] = 1;
+	return 0;
+}
+
+/* bottle_push bottle.cpp:92-116 (id 9) and pj_push puddlejumper.cpp:67-78 (id 8): both pour a
+ * bottle (`him->tick == bottle_tick`) into `me` with direct slider writes, then bottleUpdate
+ * (bottle.cpp:118-130).  Serial lane only.  Sliders: bottle hand 0 type 1 amt 2 max 3; puddlejumper
+ * fuel 0 fuel_max 1. */
+static BT_HD int bt_bottle_push(const DevWorld &W, int id, i32 me, i32 him) {
+	if ((W.htick[him] & 0xffu) != TICK_BOTTLE) return 0;
+	i32 *ms = &W.sv[W.slider_off[me]], *hs = &W.sv[W.slider_off[him]];
+	int mn = W.slider_off[me + 1] - W.slider_off[me], hn = W.slider_off[him + 1] - W.slider_off[him];
+	if (hn < 3 || mn < (id == 9 ? 4 : 2)) { bt_unsup(W, me, 0, id); return 0; } /* the reference would read out of bounds */
+	int poured = 0;
+	if (id == 8) {
+		if (hs[1] != 1) return 0; /* BOTTLE_FUEL */
+		i32 capacity = ms[1] - ms[0], avail = hs[2];
+		if (avail < capacity) capacity = avail;
+		hs[2] -= capacity;
+		ms[0] += capacity;
+		poured = 1;
+	} else {
+		i32 myType = ms[1], hisType = hs[1];
+		if (myType == -1 || myType == hisType) {
+			i32 capacity = ms[3] - ms[2], hisAmt = hs[2];
+			if (hisAmt < capacity) capacity = hisAmt;
+			if (capacity <= 0) return 0;
+			hs[2] -= capacity;
+			ms[2] += capacity;
+			poured = 1;
+		}
+		if (myType == -1) ms[1] = hisType;
+	}
+	if (poured && hs[2] == 0) { /* bottleUpdate(him) */
+		if (((W.hphys[him] >> 8) & 0xffu) == 9) hs[1] = -1;
+		else { /* uDead entUpdaters.c:20-22 */
+			int g = W.world[him];
+			if (W.flip[g]) W.dead_max1[him] |= 1; else W.dead_max0[him] |= 1;
+			W.ctr[CT_FLUSH_HINT] = 1;
+		}
+	}
+	return 0;
+}
+
 /* push_t: 0 onPushDefault handlerRegistrar.cpp:16; 1 player_push; 2 logic_push logic.c:44-49.
  * Writing v2=1 is idempotent, so concurrent pushers of one logic block do not race. */
 static BT_HD int bt_push_handler(const DevWorld &W, i32 me, i32 him) {
@@ -211,6 +292,13 @@ static BT_HD int bt_push_handler(const DevWorld &W, i32 me, i32 him) {
 		for (i32 k = 0; k < W.wire_cnt[me]; k++) bt_or32(&W.btn_v2[W.wire_to[W.wire_off[me] + k]], 1u);
 		return 0;
 	}
+	if (id == 3) { /* seat_push seat.cpp:10-16 */
+		if (W.wire_cnt[me]) return 0;
+		if ((W.type[him] & T_INPUTS) && !(W.btn_v[him] & 0xffu)) bt_upickup(W, me, him, HOLD_DROP + HOLD_FREEZE + HOLD_SINGLE);
+		return 0;
+	}
+	if (id == 6) return bt_teleport_push(W, me, him);
+	if (id == 8 || id == 9) return bt_bottle_push(W, id, me, him);
 	if (id == 2) {
 		if (W.type[him] & (T_TERRAIN | T_OBSTACLE | T_DEBRIS)) bt_or32(&W.btn_v2[me], 1u); /* pushBtn(me,0) */
 	} else if (id != 0) {
@@ -303,6 +391,20 @@ static BT_HD void bt_pair_handler(const DevWorld &W, int slot, i32 me, i32 him) 
 		}
 		return;
 	}
+	if (id == 1) { /* seat_pickUp seat.cpp:32-36 */
+		if (!W.wire_cnt[me] && (W.type[him] & T_INPUTS)) bt_uwire(W, me, him);
+		return;
+	}
+	if (id == 2 || id == 4) { /* seat_fumble_old / seat_fumble seat.cpp:18-30 */
+		bt_uunwire(W, me, him);
+		if (id == 4) {
+			int ns = W.slider_off[me + 1] - W.slider_off[me];
+			for (int i = 0; i < 5; i++) {
+				if (i < ns) bt_uslider(W, me, i, 0);
+			}
+		}
+		return;
+	}
 	if (id == 3) {
 		W.fullFlush[me] = 1;
 		W.ctr[CT_FLUSH_HINT] = 1;
@@ -344,7 +446,7 @@ static BT_HD void bt_fumble(const DevWorld &W, i32 h, LocalStats &st) {
 
 /* killEntNoHandlers ent.cpp:190-208 + crushEnt :211-217.  The dead list replaces
  * gs->deadTail; `key` orders it canonically (iteration, pusher) for the host. */
-static BT_HD void bt_crush(const DevWorld &W, i32 e, u32 key, LocalStats &st) {
+static BT_HD void bt_crush(const DevWorld &W, i32 e, u32 key, LocalStats &st, int d = 1) {
 	if (W.dead[e]) return;
 	st.crush++;
 	while (W.holdee[e] >= 0) bt_fumble(W, W.holdee[e], st);
@@ -353,7 +455,14 @@ static BT_HD void bt_crush(const DevWorld &W, i32 e, u32 key, LocalStats &st) {
 	W.hasBox[e] = 0;
 	W.dead[e] = 1;
 	W.ctr[CT_FLUSH_HINT] = 1; /* wires that point at it must go (flushMisc ent.cpp:706-712) */
-	if ((W.hphys[e] >> 24) & 0xff) bt_unsup(W, e, 3, (int)((W.hphys[e] >> 24) & 0xff)); /* invokeOnCrush ent.cpp:464-469 is host-side */
+	int cid = (int)((W.hphys[e] >> 24) & 0xff);
+	if (cid > 2) bt_unsup(W, e, 3, cid);
+	else if (cid && d == 1 && !W.flush_stage) {
+		/* invokeOnCrush ent.cpp:464-469 runs flag_crush / platform crush on the host (they create
+		 * entities): one event per death that the reference would call the handler for */
+		u32 ev = bt_add32(&W.ctr[CT_EVENT_N], 1u);
+		if ((i32)ev < W.event_cap) W.events[ev] = make_int4(0x300 | cid, e, e, (i32)key);
+	}
 	u32 slot = bt_add32(&W.ctr[CT_DEAD_N], 1u);
 	if ((i32)slot < W.dead_cap) W.deadList[slot] = ((u64)key << 32) | (u32)e;
 }
@@ -1247,7 +1356,7 @@ static BT_HD void bt_push(const DevWorld &W, const Coll &c, u32 key, LocalStats 
 
 /* event-order key of a push: iteration counter, then descending root index */
 static BT_HD u32 bt_push_key(const DevWorld &W, i32 root) {
-	return ((u32)W.iter_id << 20) ^ (u32)(0xfffff - (root & 0xfffff));
+	return ((u32)(W.iter_id - W.iter_base) << 20) ^ (u32)(0xfffff - (root & 0xfffff));
 }
 
 /* parallel lane: one thread per ready root (ent.cpp:879-882).  A root that resolves by
@@ -1313,6 +1422,31 @@ static BT_HD void t_post(const DevWorld &W, i32 e) {
 	BT_FOR_SUBTREE(W, e, it, W.needsCollision[it] = 1); /* requireCollisionRecursive ent.cpp:128-134 */
 }
 
+/* The deferred updaters of entUpdaters.c called by HOST-side code (tick handlers, doInputs,
+ * edit commands) between two steps.  Applied by one thread in the order given, like the host
+ * would have called them. */
+static BT_HD void t_request(const DevWorld &W, const BtReq &q) {
+	i32 e = q.me;
+	if (e < 0 || e >= W.n || !W.inList[e]) return;
+	int g = W.world[e];
+	switch (q.kind) {
+	case BT_REQ_DROP: W.newDrop[e] = 1; break;                                  /* uDrop :28 */
+	case BT_REQ_DEAD: if (W.flip[g]) W.dead_max1[e] |= 1; else W.dead_max0[e] |= 1; break; /* uDead :20 */
+	case BT_REQ_ERASE: if (W.flip[g]) W.dead_max1[e] = 3; else W.dead_max0[e] = 3; break;  /* uErase :24 */
+	case BT_REQ_PICKUP:                                                         /* uPickup :32 */
+		if (q.other >= 0 && q.other < W.n && W.inList[q.other]) bt_upickup(W, e, q.other, q.a0);
+		break;
+	case BT_REQ_BUTTON: if (q.a0 >= 0 && q.a0 < 4) W.btn_v2[e] |= 1u << (8 * q.a0); break; /* pushBtn :6 */
+	case BT_REQ_VEL: { int4 v = W.d_vel[e]; v.x += q.a0; v.y += q.a1; v.z += q.a2; W.d_vel[e] = v; W.ctr[CT_ANY_DELTA] = 1; break; }       /* uVel :14 */
+	case BT_REQ_CENTER: { int4 v = W.d_center[e]; v.x += q.a0; v.y += q.a1; v.z += q.a2; W.d_center[e] = v; W.ctr[CT_ANY_DELTA] = 1; break; } /* uCenter :8 */
+	case BT_REQ_SLIDER: bt_uslider(W, e, q.a0, q.a1); break;                    /* uSlider :54 */
+	case BT_REQ_TYPEMASK: W.fullFlush[e] = 1; W.ntype[e] = (u32)q.a0; break;    /* uMyTypeMask :75 */
+	case BT_REQ_COLLIDEMASK: W.fullFlush[e] = 1; W.ncollide[e] = (u32)q.a0; break; /* uMyCollideMask :80 */
+	default: W.ctr[CT_ERROR] = (u32)(-BT_ERR_ARG); break;
+	}
+	W.ctr[CT_FLUSH_HINT] = 1;
+}
+
 /* ------------------------------------------------------------------------- */
 /* flushes, gravity, integration                                             */
 
@@ -1347,7 +1481,7 @@ static BT_HD void t_flush_serial(const DevWorld &W, i32 g, LocalStats &st) {
 		if (!W.inList[i]) continue;
 		u8 d = slot ? W.dead_max1[i] : W.dead_max0[i];
 		if (d) {
-			bt_crush(W, i, 0xffffffffu - (u32)i, st);
+			bt_crush(W, i, 0xfffffu - ((u32)i & 0xfffffu), st, d); /* before every push of the tick, newest first */
 			W.dead[i] = d;
 		}
 	}
@@ -1393,12 +1527,25 @@ static BT_HD void t_flush_misc(const DevWorld &W, i32 e) {
 			if (nb && !W.hasBox[e]) W.ctr[CT_NEED_REBUILD] = 1;
 			W.hasBox[e] = nb;
 		}
+		i32 add = W.wireAdd[e];
+		if (add >= 0) { /* wiresAdd ent.cpp:694-698 */
+			W.wireAdd[e] = -1;
+			i32 b0 = W.wire_off[e], c0 = W.wire_cnt[e];
+			int has = 0;
+			for (i32 i = 0; i < c0; i++) has |= W.wire_to[b0 + i] == add;
+			if (!has) {
+				if (b0 + c0 < W.wire_off[e + 1]) { W.wire_to[b0 + c0] = add; W.wire_cnt[e] = c0 + 1; }
+				else W.ctr[CT_ERROR] = (u32)(-BT_ERR_CAPACITY);
+			}
+		}
 	}
 	i32 base = W.wire_off[e];
 	i32 cnt = W.wire_cnt[e];
+	i32 rm = W.wireRm[e];
+	W.wireRm[e] = -1;
 	for (i32 i = 0; i < cnt; i++) {
 		i32 x = W.wire_to[base + i];
-		if (W.dead[x]) { /* quickRmAt: pull the last wire into this place (list.h) */
+		if (W.dead[x] || x == rm) { /* quickRmAt: pull the last wire into this place (list.h) */
 			W.wire_to[base + i] = W.wire_to[base + (--cnt)];
 			i--;
 		}

@@ -49,12 +49,14 @@ typedef uint8_t u8;
 #define HOLD_MOVE 2
 #define HOLD_MASK 3
 #define HOLD_FREEZE 4
+#define HOLD_SINGLE 8
 #define T_HEAVY 1u
 #define T_TERRAIN 2u
 #define T_OBSTACLE 4u
 #define T_DEBRIS 8u
 #define T_WEIGHTLESS 16u
 #define T_FLAG 32u
+#define T_INPUTS (1u << 11)
 #define TEAM_BIT 256u
 #define TEAM_MASK (7u * TEAM_BIT)
 #define T_COLLIDABLE (T_HEAVY + T_TERRAIN + T_OBSTACLE + T_DEBRIS + T_FLAG)
@@ -118,6 +120,8 @@ struct DevWorld {
 	i32 world_bits;
 	i32 serial_cap, dead_cap;
 	i32 iter_id; /* running doIteration counter, for event ordering keys */
+	i32 iter_base; /* iter_id when the current tick's doPhysics began */
+	i32 flush_stage; /* 0: a death now still gets its crush handler (ent.cpp:907); 1: the flush1 after invokeOnCrush */
 	i32 lenient;  /* uploads with unknown handler IDs were accepted: count would-be invocations instead */
 	i32 ray_mode;
 	i32 margin;   /* inflation of the boxes candidate pairs are cached with (collision tree only) */
@@ -145,7 +149,8 @@ struct DevWorld {
 	int4 *forcedHoldees;
 	u64 *pend;
 	i32 *slider_off, *sv, *smin, *smax;
-	i32 *wire_off, *wire_cnt, *wire_to;
+	i32 *wire_off, *wire_cnt, *wire_to; /* wire_off leaves one spare slot behind every seat (PICKUP_SEAT wires its rider) */
+	i32 *wireAdd, *wireRm;              /* pending uWire / uUnwire target, -1 = none */
 
 	/* broadphase */
 	u64 *keys, *keys_alt;
@@ -168,6 +173,11 @@ struct DevWorld {
 	u64 *deadList; /* key<<32 | entity */
 	u64 *hash;     /* per world */
 	u32 *ctr;      /* CT_WORDS */
+};
+
+/* one deferred updater call made by host-side code (bt_world_apply_requests) */
+struct BtReq {
+	i32 kind, me, other, a0, a1, a2; /* me / other are entity slots here */
 };
 
 /* ---- packed pending collision (the 5 collision* fields of ent.h:79-85) ----

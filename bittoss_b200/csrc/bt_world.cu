@@ -18,6 +18,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <vector>
+#include <unordered_map>
 #include <algorithm>
 
 #include "bt_kernels.cuh"
@@ -70,6 +71,9 @@ struct bt_world {
 	u32 *d_sorthist; int sorthist_len;
 	bool any_rules; /* some world's gamerules contain a scan rule (crush / lava / bounce) */
 	bool tree_valid, deltas_pending;
+	std::unordered_map<u64, i32> uid_map; /* (world << 32 | uid) -> slot, built on the first bt_world_apply_requests */
+	bool uid_map_valid;
+	BtReq *d_reqs; i32 reqs_cap;
 	int full_flush_left; /* flush1 calls that must run in full (after an upload); afterwards CT_FLUSH_HINT decides */
 	bool ctrls_fused;    /* flushCtrls of this step rides in k_begin_fused */
 	i32 ticks_since_build;
@@ -160,6 +164,7 @@ void bt_world_destroy(bt_world *w) {
 	cudaSetDevice(w->device);
 	for (void *p : w->allocs) cudaFree(p);
 	if (w->h_flag) cudaFreeHost(w->h_flag);
+	if (w->d_reqs) cudaFree(w->d_reqs);
 	if (w->ev0) cudaEventDestroy(w->ev0);
 	if (w->ev1) cudaEventDestroy(w->ev1);
 	if (w->stream) cudaStreamDestroy(w->stream);
@@ -183,7 +188,7 @@ int bt_world_create(bt_world **out, int device, int32_t max_ents, int32_t max_sl
 	w->device = device;
 	w->cap_ents = max_ents; w->cap_sliders = max_sliders; w->cap_wires = max_wires; w->cap_worlds = max_worlds;
 	w->tree_valid = false; w->deltas_pending = true; w->ticks_since_build = 0; w->full_flush_left = 2; w->ctrls_fused = false;
-	w->rebuild_every = 16; w->max_iterations = 100000; w->pair_cache = 1; w->pair_rebuilds = 0; w->pair_overflows = 0; w->seen_pair_builds = 0; w->seen_pair_patches = 0; w->pair_builds_at_tree = 0; w->profiling = false; w->ray_valid = false;
+	w->rebuild_every = 16; w->max_iterations = 100000; w->pair_cache = 1; w->pair_rebuilds = 0; w->pair_overflows = 0; w->seen_pair_builds = 0; w->seen_pair_patches = 0; w->pair_builds_at_tree = 0; w->profiling = false; w->ray_valid = false; w->uid_map_valid = false; w->d_reqs = NULL; w->reqs_cap = 0;
 	w->h_flag = NULL; w->ev0 = w->ev1 = NULL; w->stream = NULL;
 	*out = w;
 #define TRY(x) do { int _r = (x); if (_r) { bt_world_destroy(w); *out = NULL; return _r; } } while (0)
@@ -212,7 +217,8 @@ int bt_world_create(bt_world **out, int device, int32_t max_ents, int32_t max_sl
 	TRY(dalloc(w, &W.forced, n)); TRY(dalloc(w, &W.forcedHoldees, n)); TRY(dalloc(w, &W.pend, n));
 	TRY(dalloc(w, &W.slider_off, n + 1)); TRY(dalloc(w, &W.sv, (size_t)max_sliders));
 	TRY(dalloc(w, &W.smin, (size_t)max_sliders)); TRY(dalloc(w, &W.smax, (size_t)max_sliders));
-	TRY(dalloc(w, &W.wire_off, n + 1)); TRY(dalloc(w, &W.wire_cnt, n)); TRY(dalloc(w, &W.wire_to, (size_t)max_wires));
+	TRY(dalloc(w, &W.wire_off, n + 1)); TRY(dalloc(w, &W.wire_cnt, n)); TRY(dalloc(w, &W.wire_to, (size_t)max_wires + n)); /* + one spare slot per (seat) entity at worst */
+	TRY(dalloc(w, &W.wireAdd, n)); TRY(dalloc(w, &W.wireRm, n));
 	TRY(dalloc(w, &W.keys, n)); TRY(dalloc(w, &W.keys_alt, n));
 	TRY(dalloc(w, &W.leafEnt, n)); TRY(dalloc(w, &W.leafEnt_alt, n));
 	TRY(dalloc(w, &W.leafParent, n)); TRY(dalloc(w, &W.nodeParent, n)); TRY(dalloc(w, &W.nodeCount, n));
@@ -345,6 +351,24 @@ int bt_world_upload(bt_world *w, const bt_world_desc *d) {
 		hasBox[i] = (u8)(d->collide_mask[i] || (d->type_mask[i] & T_COLLIDABLE));
 		wire_cnt[i] = d->wire_off[i + 1] - d->wire_off[i];
 	}
+	/* device wire CSR: the caller's lists plus one spare slot behind every seat */
+	std::vector<i32> wire_off(n + 1), wire_to;
+	{
+		i32 o = 0;
+		for (int i = 0; i < n; i++) {
+			wire_off[i] = o;
+			o += wire_cnt[i] + (d->handlers[(size_t)BT_H_NUM * i + BT_H_ONPICKUP] == 1 ? 1 : 0);
+		}
+		wire_off[n] = o;
+		if (o > w->cap_wires + w->cap_ents) {
+			snprintf(g_err, sizeof g_err, "world needs %d wire slots (incl. one spare per seat), capacity %d", o, w->cap_wires);
+			return BT_ERR_CAPACITY;
+		}
+		wire_to.assign((size_t)o, -1);
+		for (int i = 0; i < n; i++)
+			for (i32 k = 0; k < wire_cnt[i]; k++) wire_to[wire_off[i] + k] = d->wire_to[d->wire_off[i] + k];
+	}
+	std::vector<i32> minus1(n, -1);
 	DevWorld &W = w->W;
 	W.n = n; W.n_worlds = nw; W.n_leaves = 0; W.iter_id = 0;
 #define UP(dst, vec) do { int _r = h2d(w, dst, vec); if (_r) return _r; } while (0)
@@ -370,8 +394,8 @@ int bt_world_upload(bt_world *w, const bt_world_desc *d) {
 	UP(W.forced, forced); UP(W.forcedHoldees, fh); UP(W.pend, pend);
 	UPRAW(W.slider_off, d->slider_off, n + 1, i32); UPRAW(W.sv, d->slider_v, d->n_sliders, i32);
 	UPRAW(W.smin, d->slider_min, d->n_sliders, i32); UPRAW(W.smax, d->slider_max, d->n_sliders, i32);
-	UPRAW(W.wire_off, d->wire_off, n + 1, i32); UPRAW(W.wire_to, d->wire_to, d->n_wires, i32);
-	UP(W.wire_cnt, wire_cnt);
+	UP(W.wire_off, wire_off); UP(W.wire_to, wire_to);
+	UP(W.wire_cnt, wire_cnt); UP(W.wireAdd, minus1); UP(W.wireRm, minus1);
 	CK(cudaMemsetAsync(W.ctr, 0, sizeof(u32) * CT_WORDS, w->stream));
 	{ int rr = raise_cache_invalid(w); if (rr) return rr; }
 	CK(cudaMemsetAsync(W.dirtyStamp, 0, sizeof(u32) * (size_t)w->cap_ents, w->stream));
@@ -387,6 +411,7 @@ int bt_world_upload(bt_world *w, const bt_world_desc *d) {
 	for (int g = 0; g < nw; g++) w->any_rules = w->any_rules || (d->w_gamerules[g] & (1 | 2 | 16 | 32));
 	w->deltas_pending = deltas;
 	w->full_flush_left = 2; /* both dead_max slots of the upload get looked at */
+	w->uid_map_valid = false;
 	w->ticks_since_build = 0;
 	w->stats.live_ents = n;
 	return BT_OK;
@@ -508,6 +533,7 @@ static int do_physics(bt_world *w, bool gravity) {
 		if (r) return r;
 	}
 	w->ticks_since_build++;
+	W.iter_base = W.iter_id;
 	i64 it = 0;
 	bool use_cache = w->pair_cache != 0;
 	/* 0: the host does not know whether the cache is valid (first iteration: integrate may have
@@ -605,7 +631,9 @@ static int do_physics(bt_world *w, bool gravity) {
 	}
 	/* invokeOnCrush (ent.cpp:907): crush handlers are host-side events (dead list) */
 	/* h_flag holds the counters fetched after the last k_narrow, i.e. after every push */
+	W.flush_stage = 1; /* deaths flushed from here on are past invokeOnCrush (ent.cpp:907-909) */
 	int r = flush1(w, w->h_flag[CT_FLUSH_HINT] != 0);
+	W.flush_stage = 0;
 	if (r) return r;
 	/* a flush1 that runs k_flush_serial can itself kill (dead_max) and so leave wires to clean
 	 * up: keep the next flush1 full in that case */
@@ -745,6 +773,53 @@ int bt_world_apply_host_deltas(bt_world *w, const int32_t *d_center, const int32
 	return BT_OK;
 }
 
+int bt_world_apply_requests(bt_world *w, const bt_request *reqs, int32_t n) {
+	if (!w || n < 0 || (n > 0 && !reqs)) return BT_ERR_ARG;
+	if (n == 0) return BT_OK;
+	CK(cudaSetDevice(w->device));
+	DevWorld &W = w->W;
+	if (!w->uid_map_valid) {
+		std::vector<i32> uid(W.n), world(W.n);
+		CK(cudaStreamSynchronize(w->stream));
+		if (W.n) {
+			CK(cudaMemcpy(uid.data(), W.uid, sizeof(i32) * (size_t)W.n, cudaMemcpyDeviceToHost));
+			CK(cudaMemcpy(world.data(), W.world, sizeof(i32) * (size_t)W.n, cudaMemcpyDeviceToHost));
+		}
+		w->uid_map.clear();
+		w->uid_map.reserve((size_t)W.n * 2);
+		for (i32 i = 0; i < W.n; i++) w->uid_map[((u64)(u32)world[i] << 32) | (u32)uid[i]] = i;
+		w->uid_map_valid = true;
+	}
+	std::vector<BtReq> q((size_t)n);
+	bool deltas = false;
+	for (i32 i = 0; i < n; i++) {
+		const bt_request &r = reqs[i];
+		if (r.kind < 0 || r.kind >= BT_REQ_NUM) { snprintf(g_err, sizeof g_err, "request %d: unknown kind %d", i, r.kind); return BT_ERR_ARG; }
+		auto it = w->uid_map.find(((u64)(u32)r.world << 32) | (u32)r.me_uid);
+		if (it == w->uid_map.end()) { snprintf(g_err, sizeof g_err, "request %d: no entity uid %d in world %d", i, r.me_uid, r.world); return BT_ERR_ARG; }
+		q[i].kind = r.kind; q[i].me = it->second; q[i].other = -1;
+		if (r.kind == BT_REQ_PICKUP) {
+			auto jt = w->uid_map.find(((u64)(u32)r.world << 32) | (u32)r.other_uid);
+			if (jt == w->uid_map.end()) { snprintf(g_err, sizeof g_err, "request %d: no entity uid %d in world %d", i, r.other_uid, r.world); return BT_ERR_ARG; }
+			q[i].other = jt->second;
+		}
+		q[i].a0 = r.a[0]; q[i].a1 = r.a[1]; q[i].a2 = r.a[2];
+		deltas |= r.kind == BT_REQ_VEL || r.kind == BT_REQ_CENTER;
+	}
+	if (n > w->reqs_cap) {
+		if (w->d_reqs) cudaFree(w->d_reqs);
+		w->d_reqs = NULL; w->reqs_cap = 0;
+		CK(cudaMalloc(&w->d_reqs, sizeof(BtReq) * (size_t)n));
+		w->reqs_cap = n;
+	}
+	CK(cudaMemcpyAsync(w->d_reqs, q.data(), sizeof(BtReq) * (size_t)n, cudaMemcpyHostToDevice, w->stream));
+	LAUNCH(w, PK_EXCHANGE, k_requests, 1, 32, W, (const BtReq *)w->d_reqs, n);
+	CK(cudaStreamSynchronize(w->stream)); /* q goes out of scope */
+	if (deltas) w->deltas_pending = true;
+	if (w->full_flush_left < 1) w->full_flush_left = 1; /* the next flush1 has requests to look at */
+	return BT_OK;
+}
+
 int bt_world_read_state(bt_world *w, int32_t *center, int32_t *vel, int32_t n_ents) {
 	if (!w || !center || !vel || n_ents < 0) return BT_ERR_ARG;
 	CK(cudaSetDevice(w->device));
@@ -808,8 +883,15 @@ int bt_world_drain_events(bt_world *w, bt_event *out, int32_t max, int32_t *n) {
 		CK(cudaMemcpy(uid.data(), w->W.uid, sizeof(i32) * (size_t)w->W.n, cudaMemcpyDeviceToHost));
 		CK(cudaMemcpy(world.data(), w->W.world, sizeof(i32) * (size_t)w->W.n, cudaMemcpyDeviceToHost));
 	}
+	/* push events keep their (canonical) order; crush events follow them, most recent death first,
+	 * the order invokeOnCrush walks gs->deadTail in (ent.cpp:464-469) */
+	std::stable_sort(ev.begin(), ev.end(), [](const int4 &a, const int4 &b) {
+		int ka = a.x >> 8, kb = b.x >> 8;
+		if (ka != kb) return ka < kb;
+		return ka == 3 && (u32)a.w > (u32)b.w;
+	});
 	for (u32 i = 0; i < take; i++) {
-		out[i].kind = 0; out[i].handler = ev[i].x; out[i].world = world[ev[i].y];
+		out[i].kind = ev[i].x >> 8; out[i].handler = ev[i].x & 0xff; out[i].world = world[ev[i].y];
 		out[i].me_uid = uid[ev[i].y]; out[i].him_uid = uid[ev[i].z]; out[i].arg = ev[i].w;
 	}
 	*n = (int32_t)take;
@@ -855,6 +937,7 @@ int bt_world_assign(bt_world *dst, bt_world *src) {
 	rebase(&dst->ray, sizeof(dst->ray), src, dst);
 	dst->tree_valid = src->tree_valid; dst->deltas_pending = src->deltas_pending; dst->any_rules = src->any_rules;
 	dst->full_flush_left = src->full_flush_left; dst->ctrls_fused = src->ctrls_fused;
+	dst->uid_map_valid = false;
 	dst->ticks_since_build = src->ticks_since_build; dst->rebuild_every = src->rebuild_every;
 	dst->max_iterations = src->max_iterations; dst->pair_cache = src->pair_cache;
 	dst->seen_pair_builds = src->seen_pair_builds; dst->seen_pair_patches = src->seen_pair_patches; dst->pair_builds_at_tree = src->pair_builds_at_tree;

@@ -141,17 +141,39 @@ typedef struct bt_profile {
 } bt_profile;
 
 /* A collision-path handler whose effect lives on the HOST side of the game (gs->players,
- * requestLoad, ...) is reported instead of executed: PUSH_TEAMSELECT (teamselect.cpp:36-45),
- * PUSH_LOADBLOCK (loadblock.cpp:17-31; its slider write is done on the device).  Events of a
- * step are delivered in the canonical push order. */
+ * requestLoad, entity creation) is reported instead of executed: PUSH_TEAMSELECT
+ * (teamselect.cpp:36-45), PUSH_LOADBLOCK (loadblock.cpp:17-31; its slider write is done on the
+ * device) and the crush handlers CRUSH_FLAG / CRUSH_PLATFORM (flag.c:17-19: explode()).  Drain
+ * after every step: push events come in the canonical push order, then the crush events in the
+ * order invokeOnCrush (ent.cpp:464-469) calls the handlers, most recent death first. */
 typedef struct bt_event {
-	int32_t kind;     /* 0 = push handler */
-	int32_t handler;  /* catalog id (PUSH_TEAMSELECT = 4, PUSH_LOADBLOCK = 7) */
+	int32_t kind;     /* 0 = push handler, 3 = crush handler */
+	int32_t handler;  /* catalog id (PUSH_TEAMSELECT = 4, PUSH_LOADBLOCK = 7; CRUSH_FLAG = 1, CRUSH_PLATFORM = 2) */
 	int32_t world;
 	int32_t me_uid;   /* the entity owning the handler */
-	int32_t him_uid;  /* the entity that pushed it */
-	int32_t arg;      /* LOADBLOCK: getSlider(me, 0), the game-string index to load */
+	int32_t him_uid;  /* push: the entity that pushed it; crush: me_uid again */
+	int32_t arg;      /* LOADBLOCK: getSlider(me, 0), the game-string index to load; crush: ordering key */
 } bt_event;
+
+/* One deferred updater call of entUpdaters.c made by code that stays on the host (tick
+ * handlers, doInputs, edit commands).  Entities are named by (world, uid). */
+enum {
+	BT_REQ_DROP = 0,    /* uDrop(me)                               entUpdaters.c:28 */
+	BT_REQ_DEAD,        /* uDead(me)                               :20 */
+	BT_REQ_PICKUP,      /* uPickup(me, other, holdFlags = a[0])    :32 */
+	BT_REQ_BUTTON,      /* pushBtn(me, ix = a[0])                  :6  */
+	BT_REQ_VEL,         /* uVel(me, a)                             :14 */
+	BT_REQ_CENTER,      /* uCenter(me, a)                          :8  */
+	BT_REQ_SLIDER,      /* uSlider(me, ix = a[0], value = a[1])    :54 */
+	BT_REQ_ERASE,       /* uErase(me)                              :24 */
+	BT_REQ_TYPEMASK,    /* uMyTypeMask(me, a[0])                   :75 */
+	BT_REQ_COLLIDEMASK, /* uMyCollideMask(me, a[0])                :80 */
+	BT_REQ_NUM
+};
+typedef struct bt_request {
+	int32_t kind, world, me_uid, other_uid;
+	int32_t a[3];
+} bt_request;
 
 typedef struct bt_world bt_world; /* opaque, owns device memory + one stream */
 
@@ -203,6 +225,9 @@ int bt_world_tick_timed(bt_world *w, int32_t n_ticks, float *ms);
  * order, for the next round of handlers / rendering. Host buffers; copies are issued on
  * the world's stream. */
 int bt_world_apply_host_deltas(bt_world *w, const int32_t *d_center, const int32_t *d_vel, int32_t n_ents);
+/* Sparse counterpart of bt_world_apply_host_deltas: the deferred updater calls host-side handlers
+ * made this tick, applied in the order given before the next step.  Unknown (world, uid): BT_ERR_ARG. */
+int bt_world_apply_requests(bt_world *w, const bt_request *reqs, int32_t n);
 int bt_world_read_state(bt_world *w, int32_t *center, int32_t *vel, int32_t n_ents);
 void *bt_world_stream(bt_world *w); /* the cudaStream_t every kernel of w runs on */
 

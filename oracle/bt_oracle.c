@@ -62,6 +62,9 @@
 #define T_EQUIP_SM (1 << 13)
 #define EQUIP_MASK (T_EQUIP + T_EQUIP_SM)
 #define EFFECT_GRAV (1 << 3)
+#define T_INPUTS (1 << 11)
+#define HOLD_SINGLE 8
+#define TICK_BOTTLE 37
 
 typedef int32_t i32;
 typedef int32_t v3[3];
@@ -108,6 +111,7 @@ typedef struct {
 	i32 stampCtr;
 	int64_t stats[8];
 	int64_t n_events; /* host-side handler invocations reported instead of executed */
+	ilist crush_log;  /* uids whose crush handler invokeOnCrush would have run, in call order */
 } World;
 
 enum { ST_TICKS, ST_ITERS, ST_CAND, ST_POS, ST_PUSH, ST_SERIAL, ST_CRUSH, ST_FUMBLE };
@@ -229,6 +233,7 @@ static int player_push(World *w, i32 me, i32 him) {
 	return 1;
 }
 
+static void uPickup(World *w, i32 p, i32 e, i32 holdFlags);
 /* push_t handlers: 0 onPushDefault handlerRegistrar.cpp:16; 1 player_push; 2 logic_push modules/logic.c:44-49 */
 static int pushH(World *w, i32 me, i32 him, int axis, int dir, i32 displacement, i32 dv) {
 	(void)axis; (void)dir; (void)displacement; (void)dv;
@@ -254,6 +259,59 @@ static int pushH(World *w, i32 me, i32 him, int axis, int dir, i32 displacement,
 	case 2:
 		if (w->type[him] & (T_TERRAIN | T_OBSTACLE | T_DEBRIS)) w->btn[me][4 + 0] = 1; /* pushBtn(me,0) */
 		return 0;
+	case 3: /* seat_push seat.cpp:10-16 */
+		if (w->wires[me].num) return 0;
+		if ((w->type[him] & T_INPUTS) && !w->btn[him][0]) uPickup(w, me, him, HOLD_DROP + HOLD_FREEZE + HOLD_SINGLE);
+		return 0;
+	case 6: { /* teleport_push teleport.c:12-37 */
+		if (w->type[him] & (T_TERRAIN | T_OBSTACLE | T_DEBRIS)) w->btn[me][4 + 0] = 1;
+		i32 dest = -1;
+		for (int k = 0; k < w->wires[me].num; k++) {
+			i32 x = w->wires[me].items[k];
+			if (w->btn[x][2]) {
+				if (dest >= 0) return 0; /* several lit destinations: undefined, nothing happens */
+				dest = x;
+			}
+		}
+		if (dest < 0) return 0;
+		i32 r = w->holdRoot[him];
+		for (int i = 0; i < 3; i++) {
+			w->d_center[r][i] += w->center[dest][i] - w->center[me][i]; /* uCenter(him->holdRoot) */
+			w->d_vel[r][i] += w->vel[dest][i] - w->vel[me][i];          /* uVel */
+		}
+		return 0;
+	}
+	case 8:   /* pj_push puddlejumper.cpp:67-78: sliders fuel 0, fuel_max 1 */
+	case 9: { /* bottle_push bottle.cpp:92-116: sliders hand 0, type 1, amt 2, max 3 */
+		int id = w->h[me][BT_H_PUSH];
+		if (w->h[him][BT_H_TICK] != TICK_BOTTLE) return 0;
+		i32 *ms = &w->sv[w->slider_off[me]], *hs = &w->sv[w->slider_off[him]];
+		int poured = 0;
+		if (id == 8) {
+			if (hs[1] != 1) return 0; /* BOTTLE_FUEL */
+			i32 capacity = ms[1] - ms[0], avail = hs[2];
+			if (avail < capacity) capacity = avail;
+			hs[2] -= capacity;
+			ms[0] += capacity;
+			poured = 1;
+		} else {
+			i32 myType = ms[1], hisType = hs[1];
+			if (myType == -1 || myType == hisType) {
+				i32 capacity = ms[3] - ms[2], hisAmt = hs[2];
+				if (hisAmt < capacity) capacity = hisAmt;
+				if (capacity <= 0) return 0;
+				hs[2] -= capacity;
+				ms[2] += capacity;
+				poured = 1;
+			}
+			if (myType == -1) ms[1] = hisType;
+		}
+		if (poured && hs[2] == 0) { /* bottleUpdate bottle.cpp:118-130 */
+			if (w->h[him][BT_H_PUSH] == 9) hs[1] = -1;
+			else w->dead_max[him][w->flip[w->world[him]]] |= 1; /* uDead */
+		}
+		return 0;
+	}
 	default: return 0;
 	}
 }
@@ -340,6 +398,16 @@ static void entPairH(World *w, int slot, i32 me, i32 him) {
 			updateTrajectory(w, him, o, c, v);
 			w->holdFlags[him] |= HOLD_DROP;
 		}
+		return;
+	}
+	if (w->h[me][slot] == 1) { /* seat_pickUp seat.cpp:32-36 */
+		if (!w->wires[me].num && (w->type[him] & T_INPUTS)) { w->fullFlush[me] = 1; il_add(&w->wiresAdd[me], him); } /* uWire */
+		return;
+	}
+	if (w->h[me][slot] == 2 || w->h[me][slot] == 4) { /* seat_fumble_old / seat_fumble seat.cpp:18-30 */
+		il_add(&w->wiresRm[me], him); /* uUnwire */
+		if (w->h[me][slot] == 4)
+			for (int i = 0; i < 5; i++) uSlider(w, me, i, 0);
 		return;
 	}
 	if (w->h[me][slot] == 3) {
@@ -1098,8 +1166,10 @@ static void doPhysics(World *w, int g) {
 		for (i32 i = b0; i < b1; i++)
 			if (w->inList[i]) w->needsPhysUpdate[i] = 0;
 	}
-	/* invokeOnCrush ent.cpp:464-469: crush handlers are tier-C (host side effects);
-	 * none of the IDs this restatement accepts has one, so nothing to run */
+	/* invokeOnCrush ent.cpp:464-469: the crush handlers themselves create entities (explode) and
+	 * stay on the host; what is restated is WHICH entities they run for and in what order */
+	for (i32 e = w->deadTail[g]; e >= 0; e = w->deadLink[e])
+		if (w->h[e][BT_H_CRUSH] && w->dead[e] == 1) il_add(&w->crush_log, w->uid[e]);
 	flush1(w, g);
 	flush2(w, g);
 }
@@ -1242,7 +1312,7 @@ void bto_destroy(World *w) {
 	free(w->dead); free(w->inList); free(w->needsCollision); free(w->needsPhysUpdate); free(w->hasBox); free(w->needs0);
 	free(w->forced); free(w->forcedHoldees); free(w->cLeaf); free(w->cBuddy); free(w->cAxis); free(w->cDir);
 	free(w->cMutual); free(w->slider_off); free(w->sv); free(w->smin); free(w->smax); free(w->wires);
-	free(w->wiresAdd); free(w->wiresRm); free(w->stamp); free(w->entList.items);
+	free(w->wiresAdd); free(w->wiresRm); free(w->stamp); free(w->entList.items); free(w->crush_log.items);
 	free(w);
 }
 
@@ -1419,6 +1489,40 @@ int bto_selectcast_batch(const World *w, const i32 *origin, const i32 *look_in, 
 		winner[r] = win >= 0 ? rank[win] : -1;
 	}
 	free(live); free(rank);
+	return 0;
+}
+
+/* uids the crush handlers would have run for since the last call, in invokeOnCrush order */
+int bto_crush_log(World *w, i32 *out, int max) {
+	int n = w->crush_log.num;
+	for (int i = 0; i < n && i < max; i++) out[i] = w->crush_log.items[i];
+	w->crush_log.num = 0;
+	return n;
+}
+
+/* the deferred updaters of entUpdaters.c as called by host-side code; kinds = BT_REQ_* */
+int bto_request(World *w, int kind, i32 me_uid, i32 other_uid, i32 a0, i32 a1, i32 a2) {
+	i32 e = -1, o = -1;
+	for (i32 i = 0; i < w->n; i++) {
+		if (!w->inList[i]) continue;
+		if (w->uid[i] == me_uid) e = i;
+		if (w->uid[i] == other_uid) o = i;
+	}
+	if (e < 0) return -3;
+	int g = w->world[e];
+	switch (kind) {
+	case BT_REQ_DROP: w->newDrop[e] = 1; break;
+	case BT_REQ_DEAD: w->dead_max[e][w->flip[g]] |= 1; break;
+	case BT_REQ_ERASE: w->dead_max[e][w->flip[g]] = 3; break;
+	case BT_REQ_PICKUP: if (o < 0) return -3; uPickup(w, e, o, a0); break;
+	case BT_REQ_BUTTON: if (a0 >= 0 && a0 < 4) w->btn[e][4 + a0] = 1; break;
+	case BT_REQ_VEL: w->d_vel[e][0] += a0; w->d_vel[e][1] += a1; w->d_vel[e][2] += a2; break;
+	case BT_REQ_CENTER: w->d_center[e][0] += a0; w->d_center[e][1] += a1; w->d_center[e][2] += a2; break;
+	case BT_REQ_SLIDER: uSlider(w, e, a0, a1); break;
+	case BT_REQ_TYPEMASK: w->fullFlush[e] = 1; w->ntype[e] = (uint32_t)a0; break;
+	case BT_REQ_COLLIDEMASK: w->fullFlush[e] = 1; w->ncollide[e] = (uint32_t)a0; break;
+	default: return -3;
+	}
 	return 0;
 }
 

@@ -87,6 +87,13 @@ class RefLib:
         L.btref_selectcast_batch.argtypes = [_i32p, _i32p, C.c_int32, _i32p]
         L.btref_time_steps.argtypes = [C.c_int, C.c_int32, C.POINTER(C.c_int64)]
         L.btref_time_steps.restype = C.c_double
+        L.btref_add_ent.argtypes = [_i32p, _i32p, _i32p, C.c_uint32, C.c_uint32, C.c_int]
+        L.btref_lab_set_handlers.argtypes = [C.c_int32, C.c_int, C.c_int, C.c_int, _i32p, C.c_int, C.c_int]
+        L.btref_lab_set_sliders.argtypes = [C.c_int32, C.c_int, _i32p]
+        L.btref_lab_add_wire.argtypes = [C.c_int32, C.c_int32]
+        L.btref_lab_set_button.argtypes = [C.c_int32, C.c_int, C.c_int]
+        L.btref_lab_request.argtypes = [C.c_int32, C.c_int, C.c_int32, C.c_int32]
+        L.btref_lab_crush_log.argtypes = [_i32p, C.c_int]
         with stdout_to_stderr():
             rc = L.btref_init(REF_DATA_PARENT.encode())
         if rc != 0:
@@ -117,6 +124,34 @@ class RefLib:
 
     def kick(self, seed, max_v, every=1):
         self.L.btref_kick(seed, max_v, every)
+
+    # -- handler lab (small hand-built worlds, see tests/golden/make_handler_labs.py) --
+    def add_ent(self, center, vel, radius, type_mask, collide_mask, who_moves):
+        a = lambda v: (C.c_int32 * 3)(*[int(x) for x in v])
+        return int(self.L.btref_add_ent(a(center), a(vel), a(radius), type_mask, collide_mask, who_moves))
+
+    def lab_set_handlers(self, uid, push=-1, pushed=-1, crush=-1, pair=(-1, -1, -1, -1), tick=-1, tick_held=-1):
+        p = (C.c_int32 * 4)(*pair)
+        assert self.L.btref_lab_set_handlers(uid, push, pushed, crush, p, tick, tick_held) == 0
+
+    def lab_set_sliders(self, uid, values):
+        v = (C.c_int32 * max(1, len(values)))(*[int(x) for x in values])
+        assert self.L.btref_lab_set_sliders(uid, len(values), v) == 0
+
+    def lab_add_wire(self, a, b):
+        assert self.L.btref_lab_add_wire(a, b) == 0
+
+    def lab_set_button(self, uid, ix, v=1):
+        assert self.L.btref_lab_set_button(uid, ix, v) == 0
+
+    def lab_request(self, uid, what, other=-1, arg=0):
+        """what: 0 uDrop, 1 uDead, 2 uPickup(uid picks up other, arg = hold flags)"""
+        assert self.L.btref_lab_request(uid, what, other, arg) == 0
+
+    def lab_crush_log(self):
+        buf = (C.c_int32 * 4096)()
+        n = self.L.btref_lab_crush_log(buf, 4096)
+        return [int(buf[i]) for i in range(min(n, 4096))]
 
     def set_options(self, spacetrash_on=0, input_key=0):
         self.L.btref_set_options(spacetrash_on, input_key)
@@ -183,6 +218,8 @@ class OracleLib:
         L.bto_stats.argtypes = [C.c_void_p, C.POINTER(C.c_int64)]
         L.bto_time_steps.argtypes = [C.c_void_p, C.c_int32, C.POINTER(C.c_int64)]
         L.bto_time_steps.restype = C.c_double
+        L.bto_crush_log.argtypes = [C.c_void_p, _i32p, C.c_int]
+        L.bto_request.argtypes = [C.c_void_p, C.c_int] + [C.c_int32] * 5
         self.L = L
 
     def create(self, wa: WorldArrays):
@@ -210,6 +247,16 @@ class OracleWorld:
         out = (C.c_uint64 * self.n_worlds)()
         self.L.bto_hash(self.h, out)
         return [int(x) for x in out]
+
+    def request(self, kind, me_uid, other_uid=-1, a=(0, 0, 0)):
+        a = list(a) + [0] * (3 - len(a))
+        if self.L.bto_request(self.h, kind, me_uid, other_uid, a[0], a[1], a[2]) != 0:
+            raise RuntimeError("bto_request failed")
+
+    def crush_log(self):
+        buf = (C.c_int32 * 4096)()
+        n = self.L.bto_crush_log(self.h, buf, 4096)
+        return [int(buf[i]) for i in range(min(n, 4096))]
 
     def count(self):
         a, b, c = C.c_int32(), C.c_int32(), C.c_int32()

@@ -250,6 +250,88 @@ int btref_add_ent(const int32_t *c, const int32_t *v, const int32_t *r, uint32_t
 	return cur->next_uid - 1;
 }
 
+/* ---- "handler lab" setters: build small worlds that exercise one collision-path handler.
+ * They only edit the INPUT world through the reference's own catalogs and updaters. ---- */
+static ent *by_uid(int32_t uid) {
+	for (auto &kv : cur->uid)
+		if (kv.second == uid) return kv.first;
+	return NULL;
+}
+
+/* crush handlers create entities on the host (explode, flag.c:17-19); the lab replaces them by a
+ * recorder so that the ORDER of invokeOnCrush (ent.cpp:464-469) can be compared.  An entity whose
+ * crush pointer is the recorder exports as catalog id `lab_crush_id[e]`. */
+static std::vector<int32_t> lab_crush_log;
+static std::unordered_map<ent *, int> lab_crush_id;
+static void lab_crush_recorder(gamestate *gs, ent *me) {
+	(void)gs;
+	lab_crush_log.push_back(cur->uid.count(me) ? cur->uid[me] : -1);
+}
+
+/* ids < 0 leave the slot alone.  pair = {onFumble, onFumbled, onPickUp, onPickedUp} */
+int btref_lab_set_handlers(int32_t uid, int push, int pushed, int crush, const int32_t *pair, int tick, int tickHeld) {
+	ent *e = by_uid(uid);
+	if (!e) return -1;
+	if (push >= 0) e->push = pushHandlers.get(push);
+	if (pushed >= 0) e->pushed = pushed ? pushedHandlers.get(pushed) : NULL;
+	if (crush >= 0) {
+		if (crush) { e->crush = lab_crush_recorder; lab_crush_id[e] = crush; }
+		else e->crush = NULL;
+	}
+	if (pair) {
+		entPair_t *slots[4] = {&e->onFumble, &e->onFumbled, &e->onPickUp, &e->onPickedUp};
+		for (int k = 0; k < 4; k++)
+			if (pair[k] >= 0) *slots[k] = entPairHandlers.get(pair[k]);
+	}
+	if (tick >= 0) e->tick = tick ? tickHandlers.get(tick) : NULL;
+	if (tickHeld >= 0) e->tickHeld = tickHeld ? tickHandlers.get(tickHeld) : NULL;
+	return 0;
+}
+
+/* (re)allocate the slider block like initEnt does (entFuncs.c:88-111) and set the values */
+int btref_lab_set_sliders(int32_t uid, int n, const int32_t *v) {
+	ent *e = by_uid(uid);
+	if (!e) return -1;
+	e->sliders = (slider *)realloc(e->sliders, sizeof(slider) * (n > 0 ? n : 1));
+	e->numSliders = n;
+	for (int i = 0; i < n; i++) { e->sliders[i].v = v[i]; e->sliders[i].min = INT32_MAX; e->sliders[i].max = INT32_MIN; }
+	return 0;
+}
+
+int btref_lab_add_wire(int32_t from, int32_t to) {
+	ent *a = by_uid(from), *b = by_uid(to);
+	if (!a || !b) return -1;
+	a->wires.add(b);
+	return 0;
+}
+
+/* ctrl.btns[ix].v, what getButton reads (entGetters.c:23); physics-only stepping never flushes it */
+int btref_lab_set_button(int32_t uid, int ix, int v) {
+	ent *e = by_uid(uid);
+	if (!e || ix < 0 || ix > 3) return -1;
+	e->ctrl.btns[ix].v = (char)v;
+	return 0;
+}
+
+/* deferred requests through the reference's own updaters (entUpdaters.c) */
+int btref_lab_request(int32_t uid, int what, int32_t other, int32_t arg) {
+	ent *e = by_uid(uid);
+	if (!e) return -1;
+	if (what == 0) uDrop(cur->gs, e);
+	else if (what == 1) uDead(cur->gs, e);
+	else if (what == 2) { ent *o = by_uid(other); if (!o) return -1; uPickup(cur->gs, e, o, arg); }
+	else if (what == 3) pushBtn(e, arg);
+	else return -1;
+	return 0;
+}
+
+int btref_lab_crush_log(int32_t *out, int max) {
+	int n = (int)lab_crush_log.size();
+	for (int i = 0; i < n && i < max; i++) out[i] = lab_crush_log[i];
+	lab_crush_log.clear();
+	return n;
+}
+
 /* Replace collision-path handlers that have no device-side implementation by
  * the catalog's NIL entry, and (mode&2) drop every tick handler, so that a
  * shipped level becomes a pure physics fixture.  This edits the INPUT world,
@@ -265,7 +347,7 @@ void btref_strip_handlers(int drop_ticks, uint32_t keep_push, uint32_t keep_push
 			if (!(keep_pushed >> id & 1)) e->pushed = NULL;
 		}
 		if (e->crush) {
-			id = crushHandlers.reverseLookup(e->crush);
+			id = e->crush == lab_crush_recorder ? lab_crush_id[e] : crushHandlers.reverseLookup(e->crush);
 			if (!(keep_crush >> id & 1)) e->crush = NULL;
 		}
 		entPair_t *pairs[4] = {&e->onFumble, &e->onFumbled, &e->onPickUp, &e->onPickedUp};
@@ -480,7 +562,7 @@ int btref_export_at(bt_world_desc *d, int32_t ent_base, int32_t slider_base, int
 		h[BT_H_WHOMOVES] = (uint8_t)whoMovesHandlers.reverseLookup(e->whoMoves);
 		h[BT_H_TICK] = (uint8_t)(e->tick ? tickHandlers.reverseLookup(e->tick) : 0);
 		h[BT_H_TICKHELD] = (uint8_t)(e->tickHeld ? tickHandlers.reverseLookup(e->tickHeld) : 0);
-		h[BT_H_CRUSH] = (uint8_t)(e->crush ? crushHandlers.reverseLookup(e->crush) : 0);
+		h[BT_H_CRUSH] = (uint8_t)(e->crush ? (e->crush == lab_crush_recorder ? lab_crush_id[e] : crushHandlers.reverseLookup(e->crush)) : 0);
 		h[BT_H_PUSH] = (uint8_t)pushHandlers.reverseLookup(e->push);
 		h[BT_H_PUSHED] = (uint8_t)(e->pushed ? pushedHandlers.reverseLookup(e->pushed) : 0);
 		h[BT_H_ONFUMBLE] = (uint8_t)entPairHandlers.reverseLookup(e->onFumble);

@@ -83,7 +83,8 @@ Emu *bte_create(const bt_world_desc *d, int rebuild_every, int shuffle_seed) {
 	A(E, &W.inList, n); A(E, &W.needsCollision, n); A(E, &W.hasBox, n); A(E, &W.ready, n);
 	A(E, &W.forced, n); A(E, &W.forcedHoldees, n); A(E, &W.pend, n);
 	A(E, &W.slider_off, n + 1); A(E, &W.sv, d->n_sliders); A(E, &W.smin, d->n_sliders); A(E, &W.smax, d->n_sliders);
-	A(E, &W.wire_off, n + 1); A(E, &W.wire_cnt, n); A(E, &W.wire_to, d->n_wires);
+	A(E, &W.wire_off, n + 1); A(E, &W.wire_cnt, n); A(E, &W.wire_to, d->n_wires + n);
+	A(E, &W.wireAdd, n); A(E, &W.wireRm, n);
 	A(E, &W.keys, n); A(E, &W.keys_alt, n); A(E, &W.leafEnt, n); A(E, &W.leafEnt_alt, n);
 	A(E, &W.leafParent, n); A(E, &W.nodeParent, n); A(E, &W.nodeCount, n); A(E, &W.nodes, n);
 	A(E, &W.nodeBox, n); A(E, &W.leafBox, n); A(E, &W.nodeHi, n); A(E, &W.ibox, n);
@@ -127,13 +128,22 @@ Emu *bte_create(const bt_world_desc *d, int rebuild_every, int shuffle_seed) {
 		W.hasBox[i] = (u8)bt_needs_box(W.type[i], W.collide[i]);
 		W.forcedHoldees[i] = make_int4(-1, -1, -1, 0);
 		W.slider_off[i] = d->slider_off[i];
-		W.wire_off[i] = d->wire_off[i];
 		W.wire_cnt[i] = d->wire_off[i + 1] - d->wire_off[i];
+		W.wireAdd[i] = -1; W.wireRm[i] = -1;
 		W.LLn[i] = -1; W.LLp[i] = -1;
 	}
-	W.slider_off[n] = d->slider_off[n]; W.wire_off[n] = d->wire_off[n];
+	W.slider_off[n] = d->slider_off[n];
+	{ /* one spare wire slot behind every seat, like bt_world_upload */
+		i32 o = 0;
+		for (int i = 0; i < n; i++) {
+			W.wire_off[i] = o;
+			o += W.wire_cnt[i] + (d->handlers[(size_t)BT_H_NUM * i + BT_H_ONPICKUP] == 1 ? 1 : 0);
+		}
+		W.wire_off[n] = o;
+	}
 	for (int s = 0; s < d->n_sliders; s++) { W.sv[s] = d->slider_v[s]; W.smin[s] = d->slider_min[s]; W.smax[s] = d->slider_max[s]; }
-	for (int s = 0; s < d->n_wires; s++) W.wire_to[s] = d->wire_to[s];
+	for (int i = 0; i < n; i++)
+		for (i32 k = 0; k < W.wire_cnt[i]; k++) W.wire_to[W.wire_off[i] + k] = d->wire_to[d->wire_off[i] + k];
 	for (int i = 0; i < n; i++)
 		if (W.holder[i] >= 0) {
 			W.LLn[i] = d->holdee_next[i];
@@ -223,6 +233,7 @@ static int do_physics(Emu *E, bool gravity) {
 	                       (!E->pair_cache || W.ctr[CT_PAIR_BUILDS] + W.ctr[CT_PAIR_PATCHES] > E->pair_builds_at_tree)))
 		build_tree(E);
 	E->ticks_since_build++;
+	W.iter_base = W.iter_id;
 	std::vector<i32> stack(BT_STACK);
 	int guard = 0;
 	struct HostEmit {
@@ -279,7 +290,9 @@ static int do_physics(Emu *E, bool gravity) {
 		it++;
 		if (++guard > 100000) return BT_ERR_OVERFLOW;
 	}
+	W.flush_stage = 1;
 	flush1(E, W.ctr[CT_FLUSH_HINT] != 0);
+	W.flush_stage = 0;
 	if (W.ctr[CT_FLUSH_HINT] && E->full_flush_left < 1) E->full_flush_left = 1;
 	if (W.ctr[CT_ANY_DELTA]) { /* flush2 ent.cpp:910 */
 		for (i32 e = 0; e < n; e++) t_flush2_apply(W, e);
@@ -334,6 +347,59 @@ void bte_set_option(Emu *E, const char *name, int64_t v) {
 int64_t bte_pair_rebuilds(Emu *E) { return E->pair_rebuilds; }
 int64_t bte_pair_patches(Emu *E) { return E->pair_patches; }
 int64_t bte_events(Emu *E) { return (int64_t)E->W.ctr[CT_EVENT_N]; }
+
+/* events since the last call as {kind, handler, me uid, him uid, arg} rows, ordered like
+ * bt_world_drain_events orders them */
+int bte_drain_events(Emu *E, int32_t *out, int max) {
+	DevWorld &W = E->W;
+	int n = (int)W.ctr[CT_EVENT_N];
+	std::vector<int4> ev(W.events, W.events + n);
+	std::stable_sort(ev.begin(), ev.end(), [](const int4 &a, const int4 &b) {
+		int ka = a.x >> 8, kb = b.x >> 8;
+		if (ka != kb) return ka < kb;
+		return ka == 3 && (u32)a.w > (u32)b.w;
+	});
+	for (int i = 0; i < n && i < max; i++) {
+		out[5 * i] = ev[i].x >> 8; out[5 * i + 1] = ev[i].x & 0xff; out[5 * i + 2] = W.uid[ev[i].y];
+		out[5 * i + 3] = W.uid[ev[i].z]; out[5 * i + 4] = ev[i].w;
+	}
+	W.ctr[CT_EVENT_N] = 0;
+	return n;
+}
+
+/* bt_world_apply_requests for the emulator; me / other are uids (single world) */
+int bte_request(Emu *E, int kind, int32_t me_uid, int32_t other_uid, int32_t a0, int32_t a1, int32_t a2) {
+	DevWorld &W = E->W;
+	BtReq q = {kind, -1, -1, a0, a1, a2};
+	for (i32 e = 0; e < W.n; e++) {
+		if (W.uid[e] == me_uid) q.me = e;
+		if (W.uid[e] == other_uid) q.other = e;
+	}
+	if (q.me < 0) return BT_ERR_ARG;
+	t_request(W, q);
+	if (kind == BT_REQ_VEL || kind == BT_REQ_CENTER) E->deltas_pending = true;
+	if (E->full_flush_left < 1) E->full_flush_left = 1;
+	return W.ctr[CT_ERROR] ? -(int)W.ctr[CT_ERROR] : 0;
+}
+
+/* sliders, wires, holders of every LIVE entity in slot order (compact CSR), for full-state diffs */
+int bte_export_misc(Emu *E, int32_t *uid, int32_t *holder_uid, int32_t *n_sliders, int32_t *sliders, int32_t *n_wires,
+                    int32_t *wires_uid, int max_ents, int max_items) {
+	DevWorld &W = E->W;
+	int k = 0, so = 0, wo = 0;
+	for (i32 e = 0; e < W.n; e++) {
+		if (!W.inList[e]) continue;
+		if (k >= max_ents) return -1;
+		uid[k] = W.uid[e];
+		holder_uid[k] = W.holder[e] >= 0 ? W.uid[W.holder[e]] : -1;
+		n_sliders[k] = W.slider_off[e + 1] - W.slider_off[e];
+		for (i32 s = W.slider_off[e]; s < W.slider_off[e + 1]; s++) { if (so >= max_items) return -1; sliders[so++] = W.sv[s]; }
+		n_wires[k] = W.wire_cnt[e];
+		for (i32 q = 0; q < W.wire_cnt[e]; q++) { if (wo >= max_items) return -1; wires_uid[wo++] = W.uid[W.wire_to[W.wire_off[e] + q]]; }
+		k++;
+	}
+	return k;
+}
 int64_t bte_unsupported(Emu *E) { return (int64_t)E->W.ctr[CT_UNSUPPORTED]; }
 int64_t bte_unsupported_last(Emu *E) { return (int64_t)E->W.ctr[CT_UNSUP_LAST]; }
 

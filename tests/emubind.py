@@ -47,6 +47,9 @@ class EmuWorld:
         L.bte_unsupported.argtypes = [C.c_void_p]
         L.bte_unsupported.restype = C.c_int64
         L.bte_raycast.argtypes = [C.c_void_p, _i32p, _i32p, C.c_int32, _i32p]
+        L.bte_drain_events.argtypes = [C.c_void_p, _i32p, C.c_int]
+        L.bte_request.argtypes = [C.c_void_p, C.c_int] + [C.c_int32] * 5
+        L.bte_export_misc.argtypes = [C.c_void_p] + [_i32p] * 6 + [C.c_int, C.c_int]
         self.L = L
         self.n_worlds = int(wa.desc.n_worlds)
         self.n = wa.n
@@ -69,6 +72,32 @@ class EmuWorld:
 
     def events(self):
         return int(self.L.bte_events(self.h))
+
+    def drain_events(self):
+        buf = (C.c_int32 * (5 * 4096))()
+        n = self.L.bte_drain_events(self.h, buf, 4096)
+        return [dict(kind=buf[5 * i], handler=buf[5 * i + 1], me_uid=buf[5 * i + 2], him_uid=buf[5 * i + 3],
+                     arg=buf[5 * i + 4]) for i in range(min(n, 4096))]
+
+    def request(self, kind, me_uid, other_uid=-1, a=(0, 0, 0)):
+        a = list(a) + [0] * (3 - len(a))
+        rc = self.L.bte_request(self.h, kind, me_uid, other_uid, a[0], a[1], a[2])
+        if rc != 0:
+            raise RuntimeError("bte_request rc=%d" % rc)
+
+    def export_misc(self):
+        """-> {uid: (holder uid, [sliders], [wire target uids])} of live entities"""
+        me, mi = self.n + 1, 1 << 16
+        uid, hol, ns, nw = [(C.c_int32 * me)() for _ in range(4)]
+        sl, wr = (C.c_int32 * mi)(), (C.c_int32 * mi)()
+        k = self.L.bte_export_misc(self.h, uid, hol, ns, sl, nw, wr, me, mi)
+        assert k >= 0
+        out, so, wo = {}, 0, 0
+        for i in range(k):
+            out[int(uid[i])] = (int(hol[i]), [int(sl[so + j]) for j in range(ns[i])], [int(wr[wo + j]) for j in range(nw[i])])
+            so += ns[i]
+            wo += nw[i]
+        return out
 
     def unsupported(self):
         return int(self.L.bte_unsupported(self.h))

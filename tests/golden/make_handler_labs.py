@@ -1,0 +1,181 @@
+"""Hand-built "handler lab" worlds: each exercises collision-path handlers that no kicked shipped
+level triggers without players (PUSH_TELEPORT / SEAT / PUDDLEJUMP / BOTTLE, PICKUP_SEAT,
+FUMBLE_SEAT(_OLD), crush handlers).  Built through the UNMODIFIED reference (initEnt, its handler
+catalogs and deferred updaters) via oracle/_ref, stepped physics-only (prepPhysics, doGravity,
+doPhysics, finishStep: main.cpp:1076-1096) and saved as fixtures:
+initial world + per-tick state hashes + final full state (+ the order crush handlers ran in).
+
+    python tests/golden/make_handler_labs.py          # needs /root/reference (oracle/_ref built)
+"""
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+sys.path.insert(0, os.path.dirname(HERE))
+
+T_HEAVY, T_TERRAIN, T_OBSTACLE, T_DEBRIS, T_WEIGHTLESS, T_FLAG = 1, 2, 4, 8, 16, 32
+T_INPUTS, T_EQUIP, T_EQUIP_SM = 1 << 11, 1 << 12, 1 << 13
+HOLD_DROP, HOLD_MOVE, HOLD_FREEZE, HOLD_SINGLE = 1, 2, 4, 8
+WM_ME, WM_WOOD = 1, 6
+PUSH_SEAT, PUSH_TELEPORT, PUSH_PUDDLEJUMP, PUSH_BOTTLE = 3, 6, 8, 9
+PICKUP_SEAT, FUMBLE_SEAT_OLD, FUMBLE_SEAT = 1, 2, 4
+TICK_BOTTLE = 37
+EFFECT_GRAV = 8
+
+GROUND = T_TERRAIN | T_HEAVY | T_WEIGHTLESS
+CUBE = T_OBSTACLE | T_HEAVY
+CUBE_COLLIDE = T_TERRAIN | T_OBSTACLE
+
+
+def pad(R, x, y, r=(1500, 1500, 300), z=400):
+    """immovable slab whose top face is at z-300 (+z is down)"""
+    return R.add_ent((x, y, z), (0, 0, 0), r, GROUND, 0, WM_ME)
+
+
+def cube(R, x, y, z, v=(0, 0, 0), r=400, extra_type=0):
+    return R.add_ent((x, y, z), v, (r, r, r), CUBE | extra_type, CUBE_COLLIDE, WM_WOOD)
+
+
+def lab_teleport(R):
+    """two pads wired to destination markers; one destination is lit (button 2), cubes rain on both"""
+    ev = []
+    a = pad(R, 0, 0)
+    b = pad(R, 6000, 0)
+    c = pad(R, 12000, 0)          # two lit destinations: undefined -> no teleport (teleport.c:19-23)
+    da = R.add_ent((40000, 5000, -3000), (7, -3, 0), (10, 10, 10), T_WEIGHTLESS, 0, WM_ME)
+    db = R.add_ent((-40000, 0, -1000), (0, 0, 0), (10, 10, 10), T_WEIGHTLESS, 0, WM_ME)
+    for p, dests in ((a, (da,)), (b, (db,)), (c, (da, db))):
+        R.lab_set_handlers(p, push=PUSH_TELEPORT)
+        for d in dests:
+            R.lab_add_wire(p, d)
+    floor = pad(R, 40000, 5000, r=(4000, 4000, 300), z=2000)   # something to land on after the jump
+    for i, (x, y) in enumerate(((-300, 200), (500, -400), (6100, 100), (12100, -50))):
+        cube(R, x, y, -600 - 50 * i, v=(3 * i, -2 * i, 20))
+    # a held pair: the holder's root is what moves (uCenter(him->holdRoot), teleport.c:31)
+    h = cube(R, 100, 900, -2500, v=(0, 0, 10))
+    k = cube(R, 100, 900, -3400, r=300)
+    R.lab_request(h, 2, k, HOLD_MOVE)
+    # destination `da` is lit on every tick but 20..24 (pushBtn(da, 2) like a logic gate does, logic.c:76)
+    # and `db` is lit on ticks 3..8: pad b teleports, pad c sees two lit destinations and does nothing
+    return 60, ([(t, 3, da, -1, 2) for t in range(60) if not 20 <= t < 25] + [(t, 3, db, -1, 2) for t in range(3, 9)])
+
+
+def lab_bottles(R):
+    """bottle2 blocks (PUSH_BOTTLE) and a puddlejumper (PUSH_PUDDLEJUMP) filled by falling bottles"""
+    b2 = pad(R, 0, 0)
+    R.lab_set_handlers(b2, push=PUSH_BOTTLE)
+    R.lab_set_sliders(b2, [0, -1, 0, 100])            # hand, type (unknown), amount, max
+    b3 = pad(R, 6000, 0)
+    R.lab_set_handlers(b3, push=PUSH_BOTTLE)
+    R.lab_set_sliders(b3, [0, 1, 95, 100])            # holds fuel already, nearly full
+    pj = pad(R, 12000, 0)
+    R.lab_set_handlers(pj, push=PUSH_PUDDLEJUMP)
+    R.lab_set_sliders(pj, [10, 60, 0, 0, 0, 0])       # fuel, fuel_max, vel, vel1, grounded, power
+    specs = [
+        (-500, -300, [0, 0, 30]), (600, 500, [0, 0, 90]), (100, 100, [0, 1, 10]),     # juice, juice, fuel
+        (5800, 200, [0, 1, 20]), (6400, -300, [0, 0, 20]),                            # fuel, juice (wrong type)
+        (11800, 0, [0, 1, 30]), (12500, 300, [0, 1, 40]), (12000, -600, [0, 0, 40]),  # fuel, fuel, juice
+    ]
+    for i, (x, y, sl) in enumerate(specs):
+        e = cube(R, x, y, -500 - 900 * (i % 3), v=(0, 0, 5 * i), r=250, extra_type=T_EQUIP_SM)
+        R.lab_set_handlers(e, tick=TICK_BOTTLE)       # identifies a bottle (bottle.cpp:95); never run (physics-only)
+        R.lab_set_sliders(e, sl)
+    return 70
+
+
+def lab_seats(R):
+    """seats pick up T_INPUTS cubes that land on them (PUSH_SEAT -> uPickup -> PICKUP_SEAT wires them);
+    later the rider is dropped / the seat is killed (FUMBLE_SEAT unwires and zeroes sliders)"""
+    seats = []
+    for i, fum in enumerate((FUMBLE_SEAT, FUMBLE_SEAT_OLD, FUMBLE_SEAT)):
+        s = pad(R, 6000 * i, 0)
+        R.lab_set_handlers(s, push=PUSH_SEAT, pair=(fum, -1, PICKUP_SEAT, -1))
+        R.lab_set_sliders(s, [5, 6, 7, 8, 9, 10])
+        seats.append(s)
+    riders = [cube(R, 6000 * i + 100, -50, -700 - 100 * i, v=(0, 0, 30), extra_type=T_INPUTS) for i in range(3)]
+    cube(R, 300, 900, -700)                            # no T_INPUTS: just rests on the seat
+    script = [(t, 3, riders[2], -1, 0) for t in range(40)]   # holds "get off": seat_push leaves it alone (seat.cpp:12)
+    # tick 18: rider 0 asks to be dropped (uDrop -> fumble -> FUMBLE_SEAT on the seat);
+    # tick 24: seat 1 dies (its rider is fumbled by killEntNoHandlers, FUMBLE_SEAT_OLD only unwires)
+    script += [(18, 0, riders[0], -1, 0), (24, 1, seats[1], -1, 0)]
+    return 40, script
+
+
+def lab_crush(R):
+    """entities with crush handlers squeezed between a floor and a ceiling that a falling weight drives"""
+    floor = pad(R, 0, 0, r=(6000, 6000, 300), z=400)
+    out = []
+    for i in range(4):
+        e = cube(R, -3000 + 2000 * i, 0, -300, r=400)
+        R.lab_set_handlers(e, crush=1 + (i & 1))
+        out.append(e)
+    lid = R.add_ent((0, 0, -1300), (0, 0, 200), (5000, 5000, 200), GROUND, 0, WM_ME)   # an unstoppable slab
+    return 12
+
+
+# builders return ticks, or (ticks, script) with script = [(tick, what, uid, other, arg)] applied before
+# that tick's step: what 0 uDrop, 1 uDead, 2 uPickup(uid, other, arg), 3 pushBtn(uid, arg)
+LABS = {
+    "lab_teleport": lab_teleport,
+    "lab_bottles": lab_bottles,
+    "lab_seats": lab_seats,
+    "lab_crush": lab_crush,
+}
+
+
+def make(name, verbose=False):
+    from oracle.pybind import RefLib
+    from util import golden_path, save_world
+    R = RefLib()
+    w = R.new_world()
+    R.set_gamerules(EFFECT_GRAV)
+    res = LABS[name](R)
+    script = []
+    if isinstance(res, tuple):
+        ticks, script = res
+    else:
+        ticks = res
+    R.lab_crush_log()
+    wa = R.export()
+    hashes = np.zeros(ticks, dtype=np.uint64)
+    crush_order = []
+    for t in range(ticks):
+        for (tt, what, uid, other, arg) in script:
+            if tt == t:
+                R.lab_request(uid, what, other, arg)
+        R.step(1)
+        hashes[t] = R.hash()
+        for u in R.lab_crush_log():
+            crush_order.append((t, u))
+    final = R.export()
+    n_final = R.count()[0]
+    R.free_world(w)
+    extra = {"ref_hashes": hashes, "n_final": np.array([n_final]),
+             "script": np.array(script, dtype=np.int64).reshape(-1, 5),
+             "crush_order": np.array(crush_order, dtype=np.int64).reshape(-1, 2)}
+    for k, v in final.a.items():
+        extra["final_" + k] = v
+    extra["final_n"] = np.array([final.n, int(final.desc.n_sliders), int(final.desc.n_wires)])
+    save_world(golden_path(name), wa, **extra)
+    print("%-14s ents %3d -> %3d  ticks %3d  last hash %016x  crush handlers run: %s" %
+          (name, wa.n, n_final, ticks, int(hashes[-1]), crush_order))
+    if verbose:
+        a = final.a
+        n = final.n
+        print("  uid      ", a["uid"][:n].tolist())
+        print("  center   ", a["center"].reshape(-1, 3)[:n].tolist())
+        print("  holder   ", a["holder"][:n].tolist())
+        so = a["slider_off"]
+        print("  sliders  ", [a["slider_v"][so[i]:so[i + 1]].tolist() for i in range(n)])
+        wo = a["wire_off"]
+        print("  wires    ", [a["wire_to"][wo[i]:wo[i + 1]].tolist() for i in range(n)])
+        print("  distinct hashes", len(set(hashes.tolist())))
+
+
+if __name__ == "__main__":
+    args = [a for a in sys.argv[1:] if not a.startswith("-")]
+    for nm in (args or list(LABS)):
+        make(nm, verbose="-v" in sys.argv)

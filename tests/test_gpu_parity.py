@@ -113,7 +113,11 @@ def test_cuda_raycast_after_ticks_skips_dead(bt, oracle_lib):
 
 def test_unsupported_handler_is_refused(bt):
     wa, _ = load_scenario("arena_kick")
-    wa.a["handlers"][4] = 3  # PUSH_SEAT on entity 0: no device implementation (needs wire edits)
+    wa.a["handlers"][4] = 10  # push id PUSH_NUM on entity 0: not in the catalog (handlerRegistrar.h:163-175)
+    with pytest.raises(bt.BtError):
+        bt.World(wa)
+    wa.a["handlers"][4] = 0
+    wa.a["handlers"][6] = 6  # onFumble = ENTPAIR_reuse1: no registered handler
     with pytest.raises(bt.BtError):
         bt.World(wa)
 

@@ -1,0 +1,104 @@
+"""Collision-path handlers no kicked shipped level triggers without players: PUSH_SEAT / TELEPORT /
+PUDDLEJUMP / BOTTLE, PICKUP_SEAT, FUMBLE_SEAT(_OLD), crush handlers as host events, and the sparse
+host-request channel (bt_world_apply_requests).  Fixtures = small hand-built worlds stepped by the
+unmodified reference (tests/golden/make_handler_labs.py): per-tick hashes, the order the crush
+handlers ran in, and the final sliders / wires / hold tree."""
+import numpy as np
+import pytest
+
+from util import golden_path, load_world
+
+LABS = ["lab_teleport", "lab_bottles", "lab_seats", "lab_crush"]
+
+
+def _final_misc(extra):
+    n, ns, nw = [int(x) for x in extra["final_n"]]
+    uid = extra["final_uid"][:n]
+    so, wo = extra["final_slider_off"], extra["final_wire_off"]
+    out = {}
+    for i in range(n):
+        h = int(extra["final_holder"][i])
+        out[int(uid[i])] = (int(uid[h]) if h >= 0 else -1,
+                            [int(x) for x in extra["final_slider_v"][so[i]:so[i + 1]]],
+                            [int(uid[x]) for x in extra["final_wire_to"][wo[i]:wo[i + 1]]])
+    return out
+
+
+def _run(name, make, request, step_hash, drain, misc):
+    wa, extra = load_world(golden_path(name))
+    script, ref = extra["script"], extra["ref_hashes"]
+    w = make(wa)
+    crush = []
+    for t in range(len(ref)):
+        for (_, what, uid, other, arg) in script[script[:, 0] == t]:
+            request(w, int(what), int(uid), int(other), int(arg))
+        assert step_hash(w) == int(ref[t]), (name, t)
+        crush += [(t, ev["me_uid"]) for ev in drain(w) if ev["kind"] == 3]
+    assert crush == [tuple(int(x) for x in r) for r in extra["crush_order"]], name
+    assert misc(w) == _final_misc(extra), name
+    return w
+
+
+@pytest.mark.parametrize("name", LABS)
+@pytest.mark.parametrize("shuffle", [0, 7])
+def test_emu_handler_labs(emu, name, shuffle):
+    def step_hash(w):
+        w.step(31)
+        return w.hash()[0]
+
+    w = _run(name, lambda wa: emu.EmuWorld(wa, rebuild_every=3, shuffle_seed=shuffle),
+             lambda w, what, uid, other, arg: w.request(what, uid, other, (arg, 0, 0)),
+             step_hash, lambda w: w.drain_events(), lambda w: w.export_misc())
+    assert w.unsupported() == 0
+
+
+def _desc_misc(st):
+    a, n = st.a, st.n
+    out = {}
+    for i in range(n):
+        h = int(a["holder"][i])
+        out[int(a["uid"][i])] = (int(a["uid"][h]) if h >= 0 else -1,
+                                 [int(x) for x in a["slider_v"][a["slider_off"][i]:a["slider_off"][i + 1]]],
+                                 [int(a["uid"][x]) for x in a["wire_to"][a["wire_off"][i]:a["wire_off"][i + 1]]])
+    return out
+
+
+def _cuda_misc(w):
+    return _desc_misc(w.download())
+
+
+@pytest.mark.parametrize("name", LABS)
+def test_oracle_handler_labs(oracle_lib, name):
+    """the plain-C restatement against the same reference fixtures"""
+    def step_hash(w):
+        w.step(31)
+        return w.hash()[0]
+
+    _run(name, lambda wa: oracle_lib.create(wa),
+         lambda w, what, uid, other, arg: w.request(what, uid, other, (arg, 0, 0)),
+         step_hash, lambda w: [dict(kind=3, me_uid=u) for u in w.crush_log()], lambda w: _desc_misc(w.export()))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", LABS)
+def test_cuda_handler_labs(bt, name):
+    """strict upload (every handler id of the catalog has a device implementation or is an event)"""
+    def step_hash(w):
+        return int(w.tick(1, hashes=True)[0, 0])
+
+    w = _run(name, lambda wa: bt.World(wa),
+             lambda w, what, uid, other, arg: w.apply_requests([(what, 0, uid, other, (arg, 0, 0))]),
+             step_hash, lambda w: w.drain_events(), _cuda_misc)
+    assert w.stats()["unsupported_events"] == 0
+    w.close()
+
+
+@pytest.mark.gpu
+def test_cuda_requests_reject_unknown_entity(bt):
+    wa, _ = load_world(golden_path("lab_seats"))
+    w = bt.World(wa)
+    with pytest.raises(bt.BtError):
+        w.apply_requests([(0, 0, 12345, -1, (0, 0, 0))])
+    with pytest.raises(bt.BtError):
+        w.apply_requests([(99, 0, 0, -1, (0, 0, 0))])
+    w.close()

@@ -49,7 +49,7 @@ def _run(ref, make_world, name, ticks=None):
 @pytest.mark.parametrize("name", list(CASES))
 def test_kernel_bodies_teacher_forced(ref_lib, emu, name):
     def step(_, wa):
-        ew = emu.EmuWorld(wa, 1, 0, lenient=True)
+        ew = emu.EmuWorld(wa, 1, 0)  # strict: every collision-path handler id of the level has a device body
         ew.step(PHYSICS_FINISH)
         return None, ew.hash()[0], ew.unsupported()
     ok, skipped, ents = _run(ref_lib, step, name, ticks=300 if name != "spacetrash_spawner" else 800)
@@ -61,8 +61,7 @@ def test_kernel_bodies_teacher_forced(ref_lib, emu, name):
 def test_cuda_teacher_forced(ref_lib, bt, name):
     def step(w, wa):
         if w is None:
-            w = bt.World(None, max_ents=8192, max_sliders=16384, max_wires=8192, max_worlds=1)
-            w.set_option("allow_unsupported", 1)
+            w = bt.World(None, max_ents=8192, max_sliders=16384, max_wires=8192, max_worlds=1)  # strict uploads
         w.stats(reset=True)
         w.upload(wa)
         w.step(PHYSICS_FINISH)
@@ -73,7 +72,8 @@ def test_cuda_teacher_forced(ref_lib, bt, name):
     print("%s: %d ticks bit-exact, %d skipped, %d entities at the end, %d host-side handler events %s" % (
         name, ok, skipped, ents, len(events), sorted(set(e["handler"] for e in events))))
     if name == "lobby_4players":
-        assert events and set(e["handler"] for e in events) <= {4, 7}   # PUSH_TEAMSELECT, PUSH_LOADBLOCK
+        push_events = [e for e in events if e["kind"] == 0]
+        assert push_events and set(e["handler"] for e in push_events) <= {4, 7}   # PUSH_TEAMSELECT, PUSH_LOADBLOCK
     assert ok >= 0.99 * CASES[name][3]
 
 
@@ -92,7 +92,6 @@ def test_cuda_batched_arena_worlds_teacher_forced(ref_lib, bt):
         R.set_options(0, 0x9e3779b9 * (g + 1) & 0xffffffff)
     w = bt.World(None, max_ents=n_worlds * 256, max_sliders=n_worlds * 1024, max_wires=n_worlds * 256,
                  max_worlds=n_worlds)
-    w.set_option("allow_unsupported", 1)
     ok = skipped = 0
     for t in range(ticks):
         counts = []
@@ -140,7 +139,7 @@ def test_kernel_bodies_teacher_forced_golden(emu, name):
     from util import load_teacher_forced
     ok = 0
     for wa, want in load_teacher_forced(name):
-        ew = emu.EmuWorld(wa, 1, 0, lenient=True)
+        ew = emu.EmuWorld(wa, 1, 0)
         ew.step(PHYSICS_FINISH)
         if ew.unsupported():
             continue
@@ -154,7 +153,6 @@ def test_kernel_bodies_teacher_forced_golden(emu, name):
 def test_cuda_teacher_forced_golden(bt, name):
     from util import load_teacher_forced
     w = bt.World(None, max_ents=4096, max_sliders=8192, max_wires=4096, max_worlds=1)
-    w.set_option("allow_unsupported", 1)
     ok = 0
     for wa, want in load_teacher_forced(name):
         w.stats(reset=True)
