@@ -148,6 +148,9 @@ class RefLib:
         """what: 0 uDrop, 1 uDead, 2 uPickup(uid picks up other, arg = hold flags)"""
         assert self.L.btref_lab_request(uid, what, other, arg) == 0
 
+    def lab_record_all_crushes(self):
+        return int(self.L.btref_lab_record_all_crushes())
+
     def lab_crush_log(self):
         buf = (C.c_int32 * 4096)()
         n = self.L.btref_lab_crush_log(buf, 4096)

@@ -325,6 +325,18 @@ int btref_lab_request(int32_t uid, int what, int32_t other, int32_t arg) {
 	return 0;
 }
 
+/* every entity that has a crush handler gets the recorder instead (same catalog id on export) */
+int btref_lab_record_all_crushes(void) {
+	int k = 0;
+	for (ent *e = cur->gs->ents; e; e = e->ll.n)
+		if (e->crush && e->crush != lab_crush_recorder) {
+			lab_crush_id[e] = crushHandlers.reverseLookup(e->crush);
+			e->crush = lab_crush_recorder;
+			k++;
+		}
+	return k;
+}
+
 int btref_lab_crush_log(int32_t *out, int max) {
 	int n = (int)lab_crush_log.size();
 	for (int i = 0; i < n && i < max; i++) out[i] = lab_crush_log[i];

@@ -102,3 +102,53 @@ def test_cuda_requests_reject_unknown_entity(bt):
     with pytest.raises(bt.BtError):
         w.apply_requests([(99, 0, 0, -1, (0, 0, 0))])
     w.close()
+
+
+# ---- every shipped level with its FULL set of collision-path handlers (only tick handlers dropped) ----
+ALL_LEVELS = ["arena", "blank", "ctf", "diner", "forest", "forts", "leggs", "lobby", "run", "ship", "soccer",
+              "spacetrash", "speed", "spider", "tower", "w1-1"]   # lights: the reference itself is order-sensitive
+                                                                   # under a kick, see test_oracle
+
+
+def _full_catalog_level(R, level, seed, maxv):
+    wid = R.new_world()
+    R.load_sav(level if level == "w1-1" else level + ".sav")
+    R.strip_handlers(True, keep_push=0xffffffff, keep_pushed=0xffffffff, keep_pair=0xffffffff, keep_crush=0xffffffff)
+    R.lab_record_all_crushes()   # explode() would create entities on the host: record the calls instead
+    R.lab_crush_log()
+    R.kick(seed, maxv, 1)
+    return wid
+
+
+def _run_level_live(R, level, make, step_hash, drain, ticks=40):
+    import os
+    if not os.path.exists(os.path.join(os.path.dirname(R.L._name), "data", level if level == "w1-1" else level + ".sav")):
+        pytest.skip("level not shipped")
+    wid = _full_catalog_level(R, level, 77, 250)
+    w = make(R.export())
+    for t in range(ticks):
+        R.step(1)
+        assert step_hash(w) == R.hash(), (level, t)
+        assert [ev["me_uid"] for ev in drain(w) if ev["kind"] == 3] == R.lab_crush_log(), (level, t)
+    R.free_world(wid)
+    return w
+
+
+@pytest.mark.parametrize("level", ALL_LEVELS)
+def test_emu_every_shipped_level_full_catalog(ref_lib, emu, level):
+    def step_hash(w):
+        w.step(31)
+        return w.hash()[0]
+    w = _run_level_live(ref_lib, level, lambda wa: emu.EmuWorld(wa, rebuild_every=4, shuffle_seed=3), step_hash,
+                        lambda w: w.drain_events(), ticks=25)
+    assert w.unsupported() == 0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("level", ALL_LEVELS)
+def test_cuda_every_shipped_level_full_catalog(ref_lib, bt, level):
+    """strict upload: no handler id of any shipped level is refused, and 40 kicked ticks match the reference"""
+    w = _run_level_live(ref_lib, level, lambda wa: bt.World(wa), lambda w: int(w.tick(1, hashes=True)[0, 0]),
+                        lambda w: w.drain_events())
+    assert w.stats()["unsupported_events"] == 0
+    w.close()
