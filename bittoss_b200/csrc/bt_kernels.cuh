@@ -49,6 +49,8 @@ __global__ void __launch_bounds__(BT_BLOCK) k_flush_serial(DevWorld W) {
 	stats_flush(W, st);
 }
 __global__ void __launch_bounds__(BT_BLOCK) k_flush_misc(DevWorld W) { t_flush_misc(W, TID); }
+__global__ void __launch_bounds__(BT_BLOCK) k_tick(DevWorld W) { t_tick(W, TID); }
+__global__ void __launch_bounds__(BT_BLOCK) k_tick_serial(DevWorld W) { t_tick_serial(W, TID); }
 __global__ void k_requests(DevWorld W, const BtReq *q, i32 n) {
 	if (threadIdx.x != 0 || blockIdx.x != 0) return;
 	for (i32 i = 0; i < n; i++) t_request(W, q[i]);

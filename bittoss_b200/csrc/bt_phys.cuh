@@ -21,6 +21,7 @@
 #define BT_PHYS_CUH
 
 #include "bt_types.h"
+#include <math.h>
 
 #if defined(BT_EMU)
 static inline u64 bt_cas64(u64 *p, u64 cmp, u64 val) { u64 o = *p; if (o == cmp) *p = val; return o; }
@@ -1420,6 +1421,177 @@ static BT_HD void t_post(const DevWorld &W, i32 e) {
 	W.pend[e] = 0;
 	W.ready[e] = 0;
 	BT_FOR_SUBTREE(W, e, it, W.needsCollision[it] = 1); /* requireCollisionRecursive ent.cpp:128-134 */
+}
+
+/* ------------------------------------------------------------------------- */
+/* tick handlers (doUpdates ent.cpp:826-832), SURVEY.md §8(f)-1: the ones that only read flushed
+ * state (buttons .v, sliders .v, centres) and write commutative requests (pushBtn = OR, uSlider =
+ * min/max, uVel = add, uDead = OR, uDrop), so every entity can run its handler at the same time.
+ * TICK_RAND draws from gs->rand and therefore runs per world, in list order (t_tick_serial). */
+enum {
+	TICK_RAND = 6, TICK_LOGIC = 11, TICK_LOGIC_DEBUG = 12, TICK_DOOR = 13, TICK_CURSED = 14, TICK_RESPAWN = 15,
+	TICK_SEAT_OLD = 17, TICK_ADJUST = 19, TICK_SEAT = 23, TICK_TIMER = 28, TICK_DEMOLISH = 29, TICK_SIGN = 34
+};
+/* NIL + the ids above */
+#define BT_SUPPORTED_TICK ((1ull << 0) | (1ull << TICK_RAND) | (1ull << TICK_LOGIC) | (1ull << TICK_LOGIC_DEBUG) | \
+	(1ull << TICK_DOOR) | (1ull << TICK_CURSED) | (1ull << TICK_RESPAWN) | (1ull << TICK_SEAT_OLD) |                  \
+	(1ull << TICK_ADJUST) | (1ull << TICK_SEAT) | (1ull << TICK_TIMER) | (1ull << TICK_DEMOLISH) | (1ull << TICK_SIGN))
+
+static BT_HD int bt_button(const DevWorld &W, i32 e, int i) { return (int)(int8_t)((W.btn_v[e] >> (8 * i)) & 0xffu); }
+static BT_HD void bt_push_btn(const DevWorld &W, i32 e, int i) { bt_or32(&W.btn_v2[e], 1u << (8 * i)); }
+/* uSlider on an entity other threads may be writing too */
+static BT_HD void bt_uslider_shared(const DevWorld &W, i32 e, int ix, i32 value) {
+	int ns = W.slider_off[e + 1] - W.slider_off[e];
+	if (ix < 0 || ix >= ns) return;
+	W.fullFlush[e] = 1;
+	W.ctr[CT_FLUSH_HINT] = 1;
+	int s = W.slider_off[e] + ix;
+	bt_max32(&W.smax[s], value);
+	bt_min32(&W.smin[s], value);
+}
+static BT_HD void bt_udead(const DevWorld &W, i32 e) {
+	if (W.flip[W.world[e]]) W.dead_max1[e] |= 1; else W.dead_max0[e] |= 1;
+	W.ctr[CT_FLUSH_HINT] = 1;
+}
+/* logic_common_input logic.c:51-61 / logic_common_output :63-80 */
+static BT_HD int bt_logic_input(const DevWorld &W, i32 me, i32 mode) {
+	int a = bt_button(W, me, 0), b = bt_button(W, me, 1);
+	if ((mode | 1) == 1) return (a ^ b ^ mode) != 0;
+	return a && b;
+}
+static BT_HD void bt_logic_output(const DevWorld &W, i32 me, int sl) {
+	i32 outputs = bt_getslider(W, me, sl);
+	for (i32 k = 0; k < W.wire_cnt[me]; k++) {
+		i32 w = W.wire_to[W.wire_off[me] + k];
+		if (outputs & 1) bt_push_btn(W, w, 0);
+		if (outputs & 2) bt_push_btn(W, w, 1);
+	}
+	bt_push_btn(W, me, 2);
+}
+/* getApproachSpeed / getStoppingDist modules/common.c:6-37 */
+static BT_HD i32 bt_approach_speed(const DevWorld &W, i32 e, i32 d, i32 a) {
+	if (a <= 0 || d <= 0) return 0;
+	i32 q = d / a;
+	if (q >= (1 << 28)) { bt_unsup(W, e, 6, TICK_DOOR); return 0; } /* 1 + 8q overflows: sqrt of a negative in the reference */
+	i32 n = ((i32)sqrt((double)(1 + 8 * q)) - 1) / 2;
+	i32 r = (d - n * (n + 1) / 2 * a) / (n + 1);
+	return n * a + r;
+}
+static BT_HD i32 bt_stopping_dist(i32 s, i32 a) {
+	if (s <= 0 || a <= 0) return 0;
+	i32 n = s / a, r = s % a;
+	return n * (n + 1) / 2 * a + r * (n + 1);
+}
+
+/* door_tick door.c:14-62 */
+static BT_HD void bt_door_tick(const DevWorld &W, i32 me) {
+	i32 nw = W.wire_cnt[me];
+	if (!nw) return;
+	i32 pos[3] = {0, 0, 0}, vel[3] = {0, 0, 0};
+	int4 mc = W.center[me], mv = W.vel[me];
+	int numActive = 0;
+	for (i32 k = 0; k < nw; k++) {
+		i32 w = W.wire_to[W.wire_off[me] + k];
+		int4 wc = W.center[w], wv = W.vel[w];
+		if (bt_button(W, w, 2)) {
+			if (!numActive) vel[0] = vel[1] = vel[2] = 0;
+			numActive++;
+			pos[0] += wc.x - mc.x; pos[1] += wc.y - mc.y; pos[2] += wc.z - mc.z;
+			vel[0] += wv.x - mv.x; vel[1] += wv.y - mv.y; vel[2] += wv.z - mv.z;
+		} else if (!numActive) {
+			vel[0] += wv.x - mv.x; vel[1] += wv.y - mv.y; vel[2] += wv.z - mv.z;
+		}
+	}
+	if (!numActive) numActive = nw;
+	for (int i = 0; i < 3; i++) { pos[i] /= numActive; vel[i] /= numActive; }
+	i32 speed = bt_getslider(W, me, 0), accel = bt_getslider(W, me, 1);
+	i32 dist = 0;
+	for (int i = 0; i < 3; i++) { i32 x = bt_abs(pos[i]); if (x > dist) dist = x; }
+	if (dist && bt_stopping_dist(speed, accel) > dist) speed = bt_approach_speed(W, me, dist, accel);
+	bt_bound_vec(pos, speed, 3);
+	for (int i = 0; i < 3; i++) vel[i] = pos[i] + vel[i];
+	bt_bound_vec(vel, accel, 3);
+	int4 dv = W.d_vel[me]; /* uVel(me, vel) */
+	dv.x += vel[0]; dv.y += vel[1]; dv.z += vel[2];
+	W.d_vel[me] = dv;
+	W.ctr[CT_ANY_DELTA] = 1;
+}
+
+/* one entity's tick / tickHeld handler.  Returns without effect for TICK_RAND (serial pass). */
+static BT_HD void t_tick(const DevWorld &W, i32 me) {
+	if (me >= W.n || !W.inList[me]) return;
+	u32 ht = W.htick[me];
+	int id = (int)(W.holder[me] >= 0 ? (ht >> 8) & 0xffu : ht & 0xffu);
+	switch (id) {
+	case 0: case TICK_SIGN: case TICK_RAND: return;
+	case TICK_LOGIC: case TICK_LOGIC_DEBUG: /* logic_tick logic.c:131-149 (the debug colour is not simulation state) */
+		if (bt_logic_input(W, me, bt_getslider(W, me, 0))) bt_logic_output(W, me, 1);
+		return;
+	case TICK_TIMER: { /* timer_tick logic.c:82-99 */
+		if (bt_button(W, me, 0) ^ bt_button(W, me, 1)) { bt_uslider_shared(W, me, 2, bt_getslider(W, me, 0)); return; }
+		i32 timer = bt_getslider(W, me, 2);
+		if (timer) { bt_uslider_shared(W, me, 2, timer - 1); return; }
+		bt_logic_output(W, me, 1);
+		return;
+	}
+	case TICK_ADJUST: /* adjust_tick logic.c:101-109 */
+		if (bt_button(W, me, 0) ^ bt_button(W, me, 1)) {
+			i32 sl = bt_getslider(W, me, 0), value = bt_getslider(W, me, 1);
+			for (i32 k = 0; k < W.wire_cnt[me]; k++) bt_uslider_shared(W, W.wire_to[W.wire_off[me] + k], sl, value);
+		}
+		return;
+	case TICK_DEMOLISH: if (bt_button(W, me, 0)) bt_udead(W, me); return; /* logic.c:170-172 */
+	case TICK_CURSED: bt_udead(W, me); return;                             /* common.c:52-54 */
+	case TICK_DOOR: bt_door_tick(W, me); return;
+	case TICK_RESPAWN: { /* respawn_tick respawn.cpp:24-66; a device world has no player table, so
+	                      * nobody is ever waiting to be revived (gs->players.num == 0) */
+		i32 cooldown = bt_getslider(W, me, 4);
+		if (cooldown > 0) bt_uslider_shared(W, me, 4, cooldown - 1);
+		return;
+	}
+	case TICK_SEAT_OLD: case TICK_SEAT: /* seat_tick(_old) seat.cpp:38-60 */
+		for (i32 k = 0; k < W.wire_cnt[me]; k++) {
+			i32 w = W.wire_to[W.wire_off[me] + k];
+			if (bt_button(W, w, 0)) { W.newDrop[w] = 1; W.ctr[CT_FLUSH_HINT] = 1; continue; } /* uDrop */
+			if (id == TICK_SEAT_OLD) continue;
+			for (int i = 0; i < 5; i++) bt_uslider_shared(W, me, i, bt_getslider(W, w, i));
+			for (int i = 0; i < 4; i++)
+				if (bt_button(W, w, i)) bt_push_btn(W, me, i);
+		}
+		return;
+	default: bt_unsup(W, me, 6, id); return;
+	}
+}
+
+/* stepRand random.cpp:7-9 */
+static BT_HD i32 bt_random(const DevWorld &W, int g) {
+	i32 x = (i32)(((long long)W.rnd[g] * 48271) % 2147483647);
+	W.rnd[g] = x;
+	return x;
+}
+/* randomazzo_tick logic.c:151-168 for every TICK_RAND entity of world g, newest first (gs->ents order) */
+static BT_HD void t_tick_serial(const DevWorld &W, int g) {
+	if (g >= W.n_worlds) return;
+	for (i32 me = W.wend[g] - 1; me >= W.wbegin[g]; me--) {
+		if (!W.inList[me]) continue;
+		u32 ht = W.htick[me];
+		if ((W.holder[me] >= 0 ? (ht >> 8) & 0xffu : ht & 0xffu) != TICK_RAND) continue;
+		if (!bt_logic_input(W, me, bt_getslider(W, me, 0))) continue;
+		int options = 0;
+		for (i32 k = 0; k < W.wire_cnt[me]; k++) options += !bt_button(W, W.wire_to[W.wire_off[me] + k], 0);
+		if (!options) continue;
+		int roll = bt_random(W, g) % options;
+		for (i32 k = 0; k < W.wire_cnt[me]; k++) {
+			i32 w = W.wire_to[W.wire_off[me] + k];
+			if (bt_button(W, w, 0)) continue;
+			if (roll--) continue;
+			i32 outputs = bt_getslider(W, me, 1);
+			if (outputs & 1) bt_push_btn(W, w, 0);
+			if (outputs & 2) bt_push_btn(W, w, 1);
+			bt_push_btn(W, me, 2);
+			break;
+		}
+	}
 }
 
 /* The deferred updaters of entUpdaters.c called by HOST-side code (tick handlers, doInputs,

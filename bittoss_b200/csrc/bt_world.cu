@@ -39,11 +39,11 @@ static void set_err(const char *fmt, const char *a, const char *b, int line) {
 
 enum {
 	PK_PRE = 0, PK_FLUSH, PK_BEGIN, PK_BUILD_KEYS, PK_SORT, PK_LBVH, PK_REFIT, PK_PAIRS, PK_NARROW, PK_COLLIDE, PK_DECIDE, PK_PUSH,
-	PK_POST, PK_HASH, PK_RAY_BUILD, PK_RAYCAST, PK_EXCHANGE, PK_NUM
+	PK_POST, PK_HASH, PK_RAY_BUILD, PK_RAYCAST, PK_EXCHANGE, PK_TICK, PK_NUM
 };
 static const char *PK_NAMES[PK_NUM] = {"pre",    "flush1", "begin_integrate", "morton_keys", "radix_sort",
                                        "lbvh_build", "refit", "pairs", "narrow", "collide",       "decide",      "push",
-                                       "post",   "hash",   "ray_tree_build",  "raycast", "host_exchange"};
+                                       "post",   "hash",   "ray_tree_build",  "raycast", "host_exchange", "tick_handlers"};
 
 typedef long long i64;
 
@@ -73,6 +73,9 @@ struct bt_world {
 	bool tree_valid, deltas_pending;
 	std::unordered_map<u64, i32> uid_map; /* (world << 32 | uid) -> slot, built on the first bt_world_apply_requests */
 	bool uid_map_valid;
+	bool any_ticks, any_rand; /* some entity has a tick handler / a TICK_RAND */
+	int bad_tick;             /* first tick handler id without a device implementation, 0 = none */
+	int device_ticks;         /* option: bt_world_tick runs the tick handlers itself when it can */
 	BtReq *d_reqs; i32 reqs_cap;
 	int full_flush_left; /* flush1 calls that must run in full (after an upload); afterwards CT_FLUSH_HINT decides */
 	bool ctrls_fused;    /* flushCtrls of this step rides in k_begin_fused */
@@ -188,7 +191,7 @@ int bt_world_create(bt_world **out, int device, int32_t max_ents, int32_t max_sl
 	w->device = device;
 	w->cap_ents = max_ents; w->cap_sliders = max_sliders; w->cap_wires = max_wires; w->cap_worlds = max_worlds;
 	w->tree_valid = false; w->deltas_pending = true; w->ticks_since_build = 0; w->full_flush_left = 2; w->ctrls_fused = false;
-	w->rebuild_every = 16; w->max_iterations = 100000; w->pair_cache = 1; w->pair_rebuilds = 0; w->pair_overflows = 0; w->seen_pair_builds = 0; w->seen_pair_patches = 0; w->pair_builds_at_tree = 0; w->profiling = false; w->ray_valid = false; w->uid_map_valid = false; w->d_reqs = NULL; w->reqs_cap = 0;
+	w->rebuild_every = 16; w->max_iterations = 100000; w->pair_cache = 1; w->pair_rebuilds = 0; w->pair_overflows = 0; w->seen_pair_builds = 0; w->seen_pair_patches = 0; w->pair_builds_at_tree = 0; w->profiling = false; w->ray_valid = false; w->uid_map_valid = false; w->d_reqs = NULL; w->reqs_cap = 0; w->any_ticks = w->any_rand = false; w->bad_tick = 0; w->device_ticks = 1;
 	w->h_flag = NULL; w->ev0 = w->ev1 = NULL; w->stream = NULL;
 	*out = w;
 #define TRY(x) do { int _r = (x); if (_r) { bt_world_destroy(w); *out = NULL; return _r; } } while (0)
@@ -257,6 +260,7 @@ int bt_world_set_option(bt_world *w, const char *name, int64_t value) {
 	if (!strcmp(name, "allow_unsupported")) { w->W.lenient = value != 0; return BT_OK; }
 	if (!strcmp(name, "pair_cache")) { w->pair_cache = value != 0; return BT_OK; }
 	if (!strcmp(name, "cache_horizon")) { w->W.horizon = value < 0 ? 0 : (value > 64 ? 64 : (i32)value); return BT_OK; }
+	if (!strcmp(name, "device_ticks")) { w->device_ticks = value != 0; return BT_OK; }
 	if (!strcmp(name, "pair_patch")) { w->W.patch = value != 0; return BT_OK; }
 	if (!strcmp(name, "patch_shift")) { w->W.patch_shift = value < 0 ? 0 : (value > 20 ? 20 : (i32)value); return BT_OK; }
 	if (!strcmp(name, "run_ahead")) { w->run_ahead = value != 0; return BT_OK; }
@@ -338,11 +342,19 @@ int bt_world_upload(bt_world *w, const bt_world_desc *d) {
 	std::vector<int4> fh(n, make_int4(-1, -1, -1, 0));
 	std::vector<u64> pend(n, 0);
 	std::vector<i32> wire_cnt(n);
+	bool any_ticks = false, any_rand = false;
+	int bad_tick = 0;
 	for (int i = 0; i < n; i++) {
 		const uint8_t *h = d->handlers + (size_t)BT_H_NUM * i;
 		hphys[i] = h[BT_H_WHOMOVES] | (h[BT_H_PUSH] << 8) | (h[BT_H_PUSHED] << 16) | ((u32)h[BT_H_CRUSH] << 24);
 		hpair[i] = h[BT_H_ONFUMBLE] | (h[BT_H_ONFUMBLED] << 8) | (h[BT_H_ONPICKUP] << 16) | ((u32)h[BT_H_ONPICKEDUP] << 24);
 		htick[i] = h[BT_H_TICK] | (h[BT_H_TICKHELD] << 8);
+		for (int k = 0; k < 2; k++) {
+			int id = h[k ? BT_H_TICKHELD : BT_H_TICK];
+			if (id) any_ticks = true;
+			if (id >= 64 || !((BT_SUPPORTED_TICK >> id) & 1ull)) { if (!bad_tick) bad_tick = id; }
+			if (id == TICK_RAND) any_rand = true;
+		}
 		const uint8_t *b = d->btn + 8 * (size_t)i;
 		bv[i] = b[0] | (b[1] << 8) | (b[2] << 16) | ((u32)b[3] << 24);
 		bv2[i] = b[4] | (b[5] << 8) | (b[6] << 16) | ((u32)b[7] << 24);
@@ -412,6 +424,7 @@ int bt_world_upload(bt_world *w, const bt_world_desc *d) {
 	w->deltas_pending = deltas;
 	w->full_flush_left = 2; /* both dead_max slots of the upload get looked at */
 	w->uid_map_valid = false;
+	w->any_ticks = any_ticks; w->any_rand = any_rand; w->bad_tick = bad_tick;
 	w->ticks_since_build = 0;
 	w->stats.live_ents = n;
 	return BT_OK;
@@ -665,8 +678,18 @@ int bt_world_step(bt_world *w, uint32_t phases) {
 		if (w->full_flush_left < 1) w->full_flush_left = 1;
 	}
 	/* flushCtrls rides in k_begin_fused when this step also integrates on the fast path */
-	w->ctrls_fused = (phases & BT_PHASE_CTRLS) && (phases & BT_PHASE_PHYSICS) && !w->deltas_pending;
+	if ((phases & BT_PHASE_TICKS) && w->bad_tick && !W.lenient) {
+		snprintf(g_err, sizeof g_err, "BT_PHASE_TICKS: tick handler id %d has no device implementation", w->bad_tick);
+		return BT_ERR_UNSUPPORTED;
+	}
+	w->ctrls_fused = (phases & BT_PHASE_CTRLS) && (phases & BT_PHASE_PHYSICS) && !w->deltas_pending && !(phases & BT_PHASE_TICKS);
 	if ((phases & BT_PHASE_CTRLS) && !w->ctrls_fused) LAUNCH(w, PK_PRE, k_pre, nblk(n), BT_BLOCK, W, phases);
+	if ((phases & BT_PHASE_TICKS) && w->any_ticks) {
+		LAUNCH(w, PK_TICK, k_tick, nblk(n), BT_BLOCK, W);
+		if (w->any_rand) LAUNCH(w, PK_TICK, k_tick_serial, nblk(W.n_worlds), BT_BLOCK, W);
+		w->deltas_pending = true;                           /* door_tick's uVel */
+		if (w->full_flush_left < 1) w->full_flush_left = 1; /* sliders, deaths, drops the handlers asked for */
+	}
 	if (phases & BT_PHASE_PREP) {
 		int r = flush1(w, false);
 		if (r) return r;
@@ -690,6 +713,12 @@ int bt_world_step(bt_world *w, uint32_t phases) {
 		w->stats.entity_ticks += w->stats.live_ents;
 	}
 	return BT_OK;
+}
+
+/* one doWholeStep (main.cpp:1019-1097) as far as the device can run it */
+static uint32_t tick_phases(const bt_world *w) {
+	return BT_PHASE_ALL | (w->any_rules ? BT_PHASE_WORLD_RULES : 0u) |
+	       (w->device_ticks && w->any_ticks && !w->bad_tick ? BT_PHASE_TICKS : 0u);
 }
 
 static int hash_into(bt_world *w, uint64_t *out) {
@@ -719,7 +748,7 @@ int bt_world_hash(bt_world *w, uint64_t *out) {
 int bt_world_tick(bt_world *w, int32_t n_ticks, uint64_t *hashes) {
 	if (!w || n_ticks < 0) return BT_ERR_ARG;
 	for (int t = 0; t < n_ticks; t++) {
-		int r = bt_world_step(w, BT_PHASE_ALL | (w->any_rules ? BT_PHASE_WORLD_RULES : 0u));
+		int r = bt_world_step(w, tick_phases(w));
 		if (r) return r;
 		if (hashes) {
 			r = hash_into(w, hashes + (size_t)t * w->W.n_worlds);
@@ -742,7 +771,7 @@ int bt_world_tick_timed(bt_world *w, int32_t n_ticks, float *ms) {
 	CK(cudaEventRecord(a, w->stream));
 	int r = BT_OK;
 	for (int t = 0; t < n_ticks && r == BT_OK; t++)
-		r = bt_world_step(w, BT_PHASE_ALL | (w->any_rules ? BT_PHASE_WORLD_RULES : 0u));
+		r = bt_world_step(w, tick_phases(w));
 	cudaEventRecord(b, w->stream);
 	cudaEventSynchronize(b);
 	cudaEventElapsedTime(ms, a, b);
@@ -938,6 +967,7 @@ int bt_world_assign(bt_world *dst, bt_world *src) {
 	dst->tree_valid = src->tree_valid; dst->deltas_pending = src->deltas_pending; dst->any_rules = src->any_rules;
 	dst->full_flush_left = src->full_flush_left; dst->ctrls_fused = src->ctrls_fused;
 	dst->uid_map_valid = false;
+	dst->any_ticks = src->any_ticks; dst->any_rand = src->any_rand; dst->bad_tick = src->bad_tick; dst->device_ticks = src->device_ticks;
 	dst->ticks_since_build = src->ticks_since_build; dst->rebuild_every = src->rebuild_every;
 	dst->max_iterations = src->max_iterations; dst->pair_cache = src->pair_cache;
 	dst->seen_pair_builds = src->seen_pair_builds; dst->seen_pair_patches = src->seen_pair_patches; dst->pair_builds_at_tree = src->pair_builds_at_tree;

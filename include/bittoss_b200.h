@@ -108,6 +108,15 @@ typedef struct bt_world_desc {
  * bt_world_tick adds it when a world's gamerules ask for one of them.  createDebris
  * (EFFECT_BLOCKS) creates entities and stays on the host. */
 #define BT_PHASE_WORLD_RULES 32u
+/* The tick handlers of doUpdates (ent.cpp:826-832) that have a device implementation: the logic
+ * family (logic.c: LOGIC, LOGIC_DEBUG, TIMER, ADJUST, DEMOLISH, RAND), DOOR (door.c), CURSED,
+ * SEAT / SEAT_OLD (seat.cpp), SIGN, and RESPAWN for a world without players.  Runs right after
+ * BT_PHASE_CTRLS.  Not part of BT_PHASE_ALL: a host that runs its own tick handlers must not get
+ * them twice.  Fails with BT_ERR_UNSUPPORTED if the world holds any other tick handler (unless
+ * the upload was lenient, then those count as unsupported events).  bt_world_tick adds the phase
+ * by itself when every tick handler of the world is in that set (option "device_ticks", default
+ * 1; 0 = never). */
+#define BT_PHASE_TICKS 64u
 
 typedef struct bt_tick_stats {
 	int64_t ticks;

@@ -34,6 +34,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
+#include <math.h>
 #include <string.h>
 #include <time.h>
 
@@ -1341,6 +1342,128 @@ static void worldRules(World *w, int g) {
 }
 
 /* one step of the phases given, in doWholeStep order (main.cpp:1072-1097) */
+/* ---- tick handlers, doUpdates ent.cpp:823-832: the logic family of
+ * modules/logic.c, door.c, seat.cpp, cursed (common.c:52), respawn.cpp without players, sign.c.
+ * Run one entity after the other in gs->ents order (newest first), like the reference. ---- */
+enum {
+	TICK_RAND = 6, TICK_LOGIC = 11, TICK_LOGIC_DEBUG = 12, TICK_DOOR = 13, TICK_CURSED = 14, TICK_RESPAWN = 15,
+	TICK_SEAT_OLD = 17, TICK_ADJUST = 19, TICK_SEAT = 23, TICK_TIMER = 28, TICK_DEMOLISH = 29, TICK_SIGN = 34
+};
+static int getButton(const World *w, i32 e, int i) { return (int)(signed char)w->btn[e][i]; }
+static void pushBtn(World *w, i32 e, int i) { w->btn[e][4 + i] = 1; }
+static void uDead(World *w, i32 e) { w->dead_max[e][w->flip[w->world[e]]] |= 1; }
+
+static int logic_common_input(const World *w, i32 me, i32 mode) { /* logic.c:51-61 */
+	int a = getButton(w, me, 0), b = getButton(w, me, 1);
+	if ((mode | 1) == 1) return (a ^ b ^ mode) != 0;
+	return a && b;
+}
+static void logic_common_output(World *w, i32 me, int sl) { /* logic.c:63-80 */
+	i32 outputs = getSlider(w, me, sl);
+	if (outputs & 1)
+		for (int k = 0; k < w->wires[me].num; k++) pushBtn(w, w->wires[me].items[k], 0);
+	if (outputs & 2)
+		for (int k = 0; k < w->wires[me].num; k++) pushBtn(w, w->wires[me].items[k], 1);
+	pushBtn(w, me, 2);
+}
+static i32 getApproachSpeed(i32 d, i32 a) { /* modules/common.c:6-29 */
+	if (a <= 0 || d <= 0) return 0;
+	i32 q = d / a;
+	i32 n = (((i32)sqrt((double)(1 + 8 * q))) - 1) / 2;
+	i32 r = (d - n * (n + 1) / 2 * a) / (n + 1);
+	return n * a + r;
+}
+static i32 getStoppingDist(i32 s, i32 a) { /* modules/common.c:31-37 */
+	if (s <= 0 || a <= 0) return 0;
+	i32 n = s / a, r = s % a;
+	return n * (n + 1) / 2 * a + r * (n + 1);
+}
+static void door_tick(World *w, i32 me) { /* door.c:14-62 */
+	int nw = w->wires[me].num;
+	if (!nw) return;
+	i32 pos[3] = {0, 0, 0}, vel[3] = {0, 0, 0};
+	int numActive = 0;
+	for (int k = 0; k < nw; k++) {
+		i32 x = w->wires[me].items[k];
+		if (getButton(w, x, 2)) {
+			if (!numActive) vel[0] = vel[1] = vel[2] = 0;
+			numActive++;
+			for (int i = 0; i < 3; i++) { pos[i] += w->center[x][i] - w->center[me][i]; vel[i] += w->vel[x][i] - w->vel[me][i]; }
+		} else if (!numActive) {
+			for (int i = 0; i < 3; i++) vel[i] += w->vel[x][i] - w->vel[me][i];
+		}
+	}
+	if (!numActive) numActive = nw;
+	for (int i = 0; i < 3; i++) { pos[i] /= numActive; vel[i] /= numActive; }
+	i32 speed = getSlider(w, me, 0), accel = getSlider(w, me, 1);
+	i32 dist = 0;
+	for (int i = 0; i < 3; i++) if (abs(pos[i]) > dist) dist = abs(pos[i]);
+	if (dist && getStoppingDist(speed, accel) > dist) speed = getApproachSpeed(dist, accel);
+	boundVec(pos, speed, 3);
+	for (int i = 0; i < 3; i++) vel[i] = pos[i] + vel[i];
+	boundVec(vel, accel, 3);
+	for (int i = 0; i < 3; i++) w->d_vel[me][i] += vel[i]; /* uVel */
+}
+static void tickOne(World *w, int g, i32 me) {
+	int id = w->h[me][w->holder[me] >= 0 ? BT_H_TICKHELD : BT_H_TICK];
+	switch (id) {
+	case TICK_LOGIC: case TICK_LOGIC_DEBUG: /* logic.c:131-149 */
+		if (logic_common_input(w, me, getSlider(w, me, 0))) logic_common_output(w, me, 1);
+		break;
+	case TICK_TIMER: { /* logic.c:82-99 */
+		if (getButton(w, me, 0) ^ getButton(w, me, 1)) { uSlider(w, me, 2, getSlider(w, me, 0)); break; }
+		i32 timer = getSlider(w, me, 2);
+		if (timer) { uSlider(w, me, 2, timer - 1); break; }
+		logic_common_output(w, me, 1);
+		break;
+	}
+	case TICK_ADJUST: /* logic.c:101-109 */
+		if (getButton(w, me, 0) ^ getButton(w, me, 1)) {
+			i32 sl = getSlider(w, me, 0), value = getSlider(w, me, 1);
+			for (int k = 0; k < w->wires[me].num; k++) uSlider(w, w->wires[me].items[k], sl, value);
+		}
+		break;
+	case TICK_RAND: { /* randomazzo_tick logic.c:151-168 */
+		if (!logic_common_input(w, me, getSlider(w, me, 0))) break;
+		int options = 0;
+		for (int k = 0; k < w->wires[me].num; k++) options += !getButton(w, w->wires[me].items[k], 0);
+		if (!options) break;
+		w->rnd[g] = (i32)(((int64_t)w->rnd[g] * 48271) % 2147483647); /* stepRand random.cpp:7-9 */
+		int roll = w->rnd[g] % options;
+		for (int k = 0; k < w->wires[me].num; k++) {
+			i32 x = w->wires[me].items[k];
+			if (getButton(w, x, 0)) continue;
+			if (roll--) continue;
+			i32 outputs = getSlider(w, me, 1);
+			if (outputs & 1) pushBtn(w, x, 0);
+			if (outputs & 2) pushBtn(w, x, 1);
+			pushBtn(w, me, 2);
+			break;
+		}
+		break;
+	}
+	case TICK_DEMOLISH: if (getButton(w, me, 0)) uDead(w, me); break; /* logic.c:170-172 */
+	case TICK_CURSED: uDead(w, me); break;
+	case TICK_DOOR: door_tick(w, me); break;
+	case TICK_RESPAWN: { /* respawn.cpp:24-66 with gs->players.num == 0 */
+		i32 cooldown = getSlider(w, me, 4);
+		if (cooldown > 0) uSlider(w, me, 4, cooldown - 1);
+		break;
+	}
+	case TICK_SEAT_OLD: case TICK_SEAT: /* seat.cpp:38-60 */
+		for (int k = 0; k < w->wires[me].num; k++) {
+			i32 x = w->wires[me].items[k];
+			if (getButton(w, x, 0)) { w->newDrop[x] = 1; continue; }
+			if (id == TICK_SEAT_OLD) continue;
+			for (int i = 0; i < 5; i++) uSlider(w, me, i, getSlider(w, x, i));
+			for (int i = 0; i < 4; i++)
+				if (getButton(w, x, i)) pushBtn(w, me, i);
+		}
+		break;
+	default: break; /* NIL, SIGN; other ids belong to the host */
+	}
+}
+
 int bto_step(World *w, uint32_t phases) {
 	for (int g = 0; g < w->n_worlds; g++) {
 		if (phases & BT_PHASE_WORLD_RULES) worldRules(w, g);
@@ -1351,6 +1474,9 @@ int bto_step(World *w, uint32_t phases) {
 						w->btn[i][k] = w->btn[i][4 + k];
 						w->btn[i][4 + k] = 0;
 					}
+		if (phases & BT_PHASE_TICKS)
+			for (i32 i = w->wend[g] - 1; i >= w->wbegin[g]; i--)
+				if (w->inList[i]) tickOne(w, g, i);
 		if (phases & BT_PHASE_PREP) flush1(w, g);
 		if ((phases & BT_PHASE_GRAVITY) && (w->gamerules[g] & EFFECT_GRAV)) doGravity(w, g);
 		if (phases & BT_PHASE_PHYSICS) doPhysics(w, g);

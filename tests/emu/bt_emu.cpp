@@ -310,8 +310,15 @@ int bte_step(Emu *E, uint32_t phases) {
 		for (i32 e = 0; e < W.n; e++) t_world_rules(W, e);
 		if (E->full_flush_left < 1) E->full_flush_left = 1;
 	}
-	E->ctrls_fused = (phases & BT_PHASE_CTRLS) && (phases & BT_PHASE_PHYSICS) && !E->deltas_pending;
+	E->ctrls_fused = (phases & BT_PHASE_CTRLS) && (phases & BT_PHASE_PHYSICS) && !E->deltas_pending && !(phases & BT_PHASE_TICKS);
 	if ((phases & BT_PHASE_CTRLS) && !E->ctrls_fused) for (i32 e = 0; e < W.n; e++) t_pre(W, e, phases);
+	if (phases & BT_PHASE_TICKS) {
+		std::vector<i32> o = order(E, W.n);
+		for (i32 e : o) t_tick(W, e);
+		for (i32 g = 0; g < W.n_worlds; g++) t_tick_serial(W, g);
+		E->deltas_pending = true;
+		if (E->full_flush_left < 1) E->full_flush_left = 1;
+	}
 	if (phases & BT_PHASE_PREP) flush1(E, false);
 	if ((phases & BT_PHASE_GRAVITY) && !(phases & BT_PHASE_PHYSICS)) {
 		for (i32 e = 0; e < W.n; e++) t_gravity(W, e);
@@ -384,7 +391,7 @@ int bte_request(Emu *E, int kind, int32_t me_uid, int32_t other_uid, int32_t a0,
 
 /* sliders, wires, holders of every LIVE entity in slot order (compact CSR), for full-state diffs */
 int bte_export_misc(Emu *E, int32_t *uid, int32_t *holder_uid, int32_t *n_sliders, int32_t *sliders, int32_t *n_wires,
-                    int32_t *wires_uid, int max_ents, int max_items) {
+                    int32_t *wires_uid, uint32_t *btn, int max_ents, int max_items) {
 	DevWorld &W = E->W;
 	int k = 0, so = 0, wo = 0;
 	for (i32 e = 0; e < W.n; e++) {
@@ -395,6 +402,7 @@ int bte_export_misc(Emu *E, int32_t *uid, int32_t *holder_uid, int32_t *n_slider
 		n_sliders[k] = W.slider_off[e + 1] - W.slider_off[e];
 		for (i32 s = W.slider_off[e]; s < W.slider_off[e + 1]; s++) { if (so >= max_items) return -1; sliders[so++] = W.sv[s]; }
 		n_wires[k] = W.wire_cnt[e];
+		btn[2 * k] = W.btn_v[e]; btn[2 * k + 1] = W.btn_v2[e];
 		for (i32 q = 0; q < W.wire_cnt[e]; q++) { if (wo >= max_items) return -1; wires_uid[wo++] = W.uid[W.wire_to[W.wire_off[e] + q]]; }
 		k++;
 	}

@@ -49,7 +49,7 @@ class EmuWorld:
         L.bte_raycast.argtypes = [C.c_void_p, _i32p, _i32p, C.c_int32, _i32p]
         L.bte_drain_events.argtypes = [C.c_void_p, _i32p, C.c_int]
         L.bte_request.argtypes = [C.c_void_p, C.c_int] + [C.c_int32] * 5
-        L.bte_export_misc.argtypes = [C.c_void_p] + [_i32p] * 6 + [C.c_int, C.c_int]
+        L.bte_export_misc.argtypes = [C.c_void_p] + [_i32p] * 6 + [C.POINTER(C.c_uint32), C.c_int, C.c_int]
         self.L = L
         self.n_worlds = int(wa.desc.n_worlds)
         self.n = wa.n
@@ -90,11 +90,13 @@ class EmuWorld:
         me, mi = self.n + 1, 1 << 16
         uid, hol, ns, nw = [(C.c_int32 * me)() for _ in range(4)]
         sl, wr = (C.c_int32 * mi)(), (C.c_int32 * mi)()
-        k = self.L.bte_export_misc(self.h, uid, hol, ns, sl, nw, wr, me, mi)
+        bt = (C.c_uint32 * (2 * me))()
+        k = self.L.bte_export_misc(self.h, uid, hol, ns, sl, nw, wr, bt, me, mi)
         assert k >= 0
         out, so, wo = {}, 0, 0
         for i in range(k):
-            out[int(uid[i])] = (int(hol[i]), [int(sl[so + j]) for j in range(ns[i])], [int(wr[wo + j]) for j in range(nw[i])])
+            btn = [(int(bt[2 * i + q]) >> (8 * b)) & 0xff for q in range(2) for b in range(4)]
+            out[int(uid[i])] = (int(hol[i]), [int(sl[so + j]) for j in range(ns[i])], [int(wr[wo + j]) for j in range(nw[i])], btn)
             so += ns[i]
             wo += nw[i]
         return out

@@ -116,6 +116,84 @@ def lab_crush(R):
     return 12
 
 
+TICK_RAND, TICK_LOGIC, TICK_LOGIC_DEBUG, TICK_DOOR, TICK_CURSED, TICK_RESPAWN = 6, 11, 12, 13, 14, 15
+TICK_ADJUST, TICK_SEAT, TICK_TIMER, TICK_DEMOLISH, TICK_SIGN = 19, 23, 28, 29, 34
+
+
+def gate(R, x, y, z, tick, sliders, held_too=True):
+    """a small weightless block running a logic-family tick handler"""
+    e = R.add_ent((x, y, z), (0, 0, 0), (50, 50, 50), T_WEIGHTLESS, 0, WM_ME)
+    R.lab_set_handlers(e, tick=tick, tick_held=tick if held_too else -1)
+    R.lab_set_sliders(e, sliders)
+    return e
+
+
+def lab_logic(R):
+    """FULL ticks (doUpdates + physics, btref step mode 0): an oscillating timer drives gates, a door
+    platform carrying cubes shuttles between two markers, an adjuster retunes it, demolish / cursed
+    blocks die, a randomiser picks outputs from gs->rand, a respawner counts down, a seat mirrors its
+    rider, and one gate runs as tickHeld.  Scripted pushBtn calls play the part of player input."""
+    script = []
+    # self-inhibiting timer: outputs, then sees its own pulse on button 0 and waits `delay` ticks
+    tm = gate(R, -5000, 0, -3000, TICK_TIMER, [3, 1, 0])
+    g_xor = gate(R, -5000, 500, -3000, TICK_LOGIC, [0, 1])        # XOR: fires while the timer pulse is in
+    g_xnor = gate(R, -5000, 1000, -3000, TICK_LOGIC_DEBUG, [1, 3])  # XNOR: fires when both or neither
+    g_and = gate(R, -5000, 1500, -3000, TICK_LOGIC, [2, 3])       # AND of timer and xnor
+    R.lab_add_wire(tm, tm); R.lab_add_wire(tm, g_xor); R.lab_add_wire(tm, g_and)
+    R.lab_add_wire(g_xor, g_xnor); R.lab_add_wire(g_xnor, g_and); R.lab_add_wire(g_and, g_xor)
+    # door platform with two markers; marker gates are lit by script in turns
+    m1 = gate(R, 0, 0, -200, TICK_LOGIC, [0, 0])
+    m2 = gate(R, 6000, 2000, -1200, TICK_LOGIC, [0, 0])
+    door = R.add_ent((0, 0, 400), (0, 0, 0), (1500, 1500, 300), GROUND, 0, WM_ME)
+    R.lab_set_handlers(door, tick=TICK_DOOR)
+    R.lab_set_sliders(door, [60, 6])                               # speed, accel
+    R.lab_add_wire(door, m1); R.lab_add_wire(door, m2)
+    for i, (x, y) in enumerate(((-600, -300), (500, 400), (100, -900))):
+        cube(R, x, y, -400 - 30 * i)
+    script += [(t, 3, m1, -1, 0) for t in range(0, 25)] + [(t, 3, m2, -1, 0) for t in range(25, 70)]
+    script += [(t, 3, m1, -1, 0) for t in range(85, 100)]          # 70..84: nobody lit -> coast to a halt
+    # adjuster: while its input is on, retunes the door's speed slider (and a bogus slider index on m2)
+    adj = gate(R, -5000, 2000, -3000, TICK_ADJUST, [0, 25])
+    R.lab_add_wire(adj, door); R.lab_add_wire(adj, m2)
+    script += [(t, 3, adj, -1, 1) for t in range(40, 44)]
+    # demolish blocks wired from the AND gate, a cursed block, a sign
+    for i in range(2):
+        d = cube(R, -9000, 1200 * i, -400, r=300)
+        R.lab_set_handlers(d, tick=TICK_DEMOLISH)
+        if i == 0:
+            R.lab_add_wire(g_and, d)
+    floor = pad(R, -9000, 600, r=(2000, 2000, 300), z=400)
+    cz = cube(R, -9000, 600, -1500, r=200)
+    R.lab_set_handlers(cz, tick=TICK_CURSED)
+    sg = gate(R, -5000, 2500, -3000, TICK_SIGN, [1, 6000, 0], held_too=False)
+    # randomiser over three gates, two of which are sometimes busy
+    rnd = gate(R, -5000, 3000, -3000, TICK_RAND, [1, 3])
+    outs = [gate(R, -5000 + 300 * k, 3500, -3000, TICK_LOGIC, [0, 1]) for k in range(3)]
+    for o in outs:
+        R.lab_add_wire(rnd, o)
+    R.lab_add_wire(outs[0], adj)
+    script += [(t, 3, outs[1], -1, 0) for t in range(10, 30, 3)] + [(t, 3, rnd, -1, 0) for t in range(50, 55)]
+    # respawner with nobody to revive: only its cooldown runs (slider 4)
+    rs = gate(R, -5000, 4000, -3000, TICK_RESPAWN, [0, 0, 0, 10, 7, 0, 0])
+    script += [(t, 3, rs, -1, 0) for t in range(3, 5)]
+    # a seat with a wired rider: mirrors sliders 0-4 and buttons, drops the rider on button 0
+    seat = pad(R, 12000, 0)
+    R.lab_set_handlers(seat, push=PUSH_SEAT, pair=(FUMBLE_SEAT, -1, PICKUP_SEAT, -1), tick=TICK_SEAT, tick_held=TICK_SEAT)
+    R.lab_set_sliders(seat, [0, 0, 0, 0, 0, 0, 0])
+    rider = cube(R, 12100, -50, -700, v=(0, 0, 30), extra_type=T_INPUTS)
+    R.lab_set_sliders(rider, [11, -12, 13, 14, 15, 16])
+    script += [(t, 3, rider, -1, 1 + (t % 3)) for t in range(20, 50)] + [(60, 3, rider, -1, 0)]
+    # a gate that is HELD by a cube runs its tickHeld slot
+    carrier = cube(R, 18000, 0, -800)
+    pad(R, 18000, 0)
+    hg = gate(R, 18000, 0, -1400, TICK_LOGIC, [1, 1])
+    R.lab_set_handlers(hg, tick=0)                                 # only tickHeld is set: silent until picked up
+    lamp = gate(R, 18000, 600, -3000, TICK_DEMOLISH, [])
+    R.lab_add_wire(hg, lamp)
+    script += [(30, 2, carrier, hg, HOLD_MOVE)]
+    return 100, script, 0
+
+
 # builders return ticks, or (ticks, script) with script = [(tick, what, uid, other, arg)] applied before
 # that tick's step: what 0 uDrop, 1 uDead, 2 uPickup(uid, other, arg), 3 pushBtn(uid, arg)
 LABS = {
@@ -123,6 +201,7 @@ LABS = {
     "lab_bottles": lab_bottles,
     "lab_seats": lab_seats,
     "lab_crush": lab_crush,
+    "lab_logic": lab_logic,
 }
 
 
@@ -134,8 +213,11 @@ def make(name, verbose=False):
     R.set_gamerules(EFFECT_GRAV)
     res = LABS[name](R)
     script = []
+    mode = 1   # btref step mode: 1 = physics only (tick handlers never run), 0 = the full doWholeStep
     if isinstance(res, tuple):
-        ticks, script = res
+        ticks, script = res[0], res[1]
+        if len(res) > 2:
+            mode = res[2]
     else:
         ticks = res
     R.lab_crush_log()
@@ -146,7 +228,7 @@ def make(name, verbose=False):
         for (tt, what, uid, other, arg) in script:
             if tt == t:
                 R.lab_request(uid, what, other, arg)
-        R.step(1)
+        R.step(mode)
         hashes[t] = R.hash()
         for u in R.lab_crush_log():
             crush_order.append((t, u))
@@ -154,7 +236,7 @@ def make(name, verbose=False):
     n_final = R.count()[0]
     R.free_world(w)
     extra = {"ref_hashes": hashes, "n_final": np.array([n_final]),
-             "script": np.array(script, dtype=np.int64).reshape(-1, 5),
+             "script": np.array(script, dtype=np.int64).reshape(-1, 5), "mode": np.array([mode]),
              "crush_order": np.array(crush_order, dtype=np.int64).reshape(-1, 2)}
     for k, v in final.a.items():
         extra["final_" + k] = v
@@ -172,6 +254,7 @@ def make(name, verbose=False):
         print("  sliders  ", [a["slider_v"][so[i]:so[i + 1]].tolist() for i in range(n)])
         wo = a["wire_off"]
         print("  wires    ", [a["wire_to"][wo[i]:wo[i + 1]].tolist() for i in range(n)])
+        print("  btn      ", a["btn"].reshape(-1, 8)[:n].tolist())
         print("  distinct hashes", len(set(hashes.tolist())))
 
 

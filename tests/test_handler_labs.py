@@ -8,7 +8,8 @@ import pytest
 
 from util import golden_path, load_world
 
-LABS = ["lab_teleport", "lab_bottles", "lab_seats", "lab_crush"]
+LABS = ["lab_teleport", "lab_bottles", "lab_seats", "lab_crush", "lab_logic"]
+TICKS = 64  # BT_PHASE_TICKS
 
 
 def _final_misc(extra):
@@ -20,19 +21,22 @@ def _final_misc(extra):
         h = int(extra["final_holder"][i])
         out[int(uid[i])] = (int(uid[h]) if h >= 0 else -1,
                             [int(x) for x in extra["final_slider_v"][so[i]:so[i + 1]]],
-                            [int(uid[x]) for x in extra["final_wire_to"][wo[i]:wo[i + 1]]])
+                            [int(uid[x]) for x in extra["final_wire_to"][wo[i]:wo[i + 1]]],
+                            [int(x) for x in extra["final_btn"][8 * i:8 * i + 8]])
     return out
 
 
 def _run(name, make, request, step_hash, drain, misc):
     wa, extra = load_world(golden_path(name))
     script, ref = extra["script"], extra["ref_hashes"]
+    # fixtures stepped with btref mode 0 ran the tick handlers too (doUpdates, ent.cpp:826-832)
+    phases = 31 | (TICKS if int(extra["mode"][0]) == 0 else 0)
     w = make(wa)
     crush = []
     for t in range(len(ref)):
         for (_, what, uid, other, arg) in script[script[:, 0] == t]:
             request(w, int(what), int(uid), int(other), int(arg))
-        assert step_hash(w) == int(ref[t]), (name, t)
+        assert step_hash(w, phases) == int(ref[t]), (name, t)
         crush += [(t, ev["me_uid"]) for ev in drain(w) if ev["kind"] == 3]
     assert crush == [tuple(int(x) for x in r) for r in extra["crush_order"]], name
     assert misc(w) == _final_misc(extra), name
@@ -42,8 +46,8 @@ def _run(name, make, request, step_hash, drain, misc):
 @pytest.mark.parametrize("name", LABS)
 @pytest.mark.parametrize("shuffle", [0, 7])
 def test_emu_handler_labs(emu, name, shuffle):
-    def step_hash(w):
-        w.step(31)
+    def step_hash(w, phases):
+        w.step(phases)
         return w.hash()[0]
 
     w = _run(name, lambda wa: emu.EmuWorld(wa, rebuild_every=3, shuffle_seed=shuffle),
@@ -59,7 +63,8 @@ def _desc_misc(st):
         h = int(a["holder"][i])
         out[int(a["uid"][i])] = (int(a["uid"][h]) if h >= 0 else -1,
                                  [int(x) for x in a["slider_v"][a["slider_off"][i]:a["slider_off"][i + 1]]],
-                                 [int(a["uid"][x]) for x in a["wire_to"][a["wire_off"][i]:a["wire_off"][i + 1]]])
+                                 [int(a["uid"][x]) for x in a["wire_to"][a["wire_off"][i]:a["wire_off"][i + 1]]],
+                                 [int(x) for x in a["btn"][8 * i:8 * i + 8]])
     return out
 
 
@@ -70,8 +75,8 @@ def _cuda_misc(w):
 @pytest.mark.parametrize("name", LABS)
 def test_oracle_handler_labs(oracle_lib, name):
     """the plain-C restatement against the same reference fixtures"""
-    def step_hash(w):
-        w.step(31)
+    def step_hash(w, phases):
+        w.step(phases)
         return w.hash()[0]
 
     _run(name, lambda wa: oracle_lib.create(wa),
@@ -83,8 +88,11 @@ def test_oracle_handler_labs(oracle_lib, name):
 @pytest.mark.parametrize("name", LABS)
 def test_cuda_handler_labs(bt, name):
     """strict upload (every handler id of the catalog has a device implementation or is an event)"""
-    def step_hash(w):
-        return int(w.tick(1, hashes=True)[0, 0])
+    def step_hash(w, phases):
+        if phases & TICKS:   # bt_world_tick adds the tick phase by itself when every handler has a device body
+            return int(w.tick(1, hashes=True)[0, 0])
+        w.step(phases)
+        return int(w.hash()[0])
 
     w = _run(name, lambda wa: bt.World(wa),
              lambda w, what, uid, other, arg: w.apply_requests([(what, 0, uid, other, (arg, 0, 0))]),
@@ -153,4 +161,56 @@ def test_cuda_every_shipped_level_full_catalog(ref_lib, bt, level):
         return int(w.hash()[0])
     w = _run_level_live(ref_lib, level, lambda wa: bt.World(wa), step_hash, lambda w: w.drain_events())
     assert w.stats()["unsupported_events"] == 0
+    w.close()
+
+
+# ---- shipped levels whose tick handlers all have device bodies: the FULL game tick on the device ----
+TICK_LEVELS = ["tower", "forest", "speed", "blank", "lights"]
+EFFECT_BLOCKS = 4   # createDebris (effects.cpp:99-150) spawns platforms from gs->rand: host side, switched off here
+
+
+def _device_tick_level(R, level, seed, maxv):
+    wid = R.new_world()
+    R.load_sav(level + ".sav")                     # all handlers stay, tick handlers included; no players
+    R.set_gamerules(R.get_gamerules() & ~EFFECT_BLOCKS)
+    R.lab_record_all_crushes()
+    R.lab_crush_log()
+    R.kick(seed, maxv, 1)
+    return wid
+
+
+def _run_tick_level(R, level, make, step_hash, maxv, ticks):
+    wid = _device_tick_level(R, level, 5, maxv)
+    w = make(R.export())
+    n0 = R.count()[0]
+    for t in range(ticks):
+        R.step(0)                                  # the reference's whole doWholeStep (main.cpp:1019-1097)
+        assert step_hash(w) == R.hash(), (level, t)
+    n1 = R.count()[0]
+    R.free_world(wid)
+    return w, n0, n1
+
+
+# lights + a kick: the reference's own result depends on its list order there, no canonical answer
+TICK_CASES = [(lv, v) for lv in TICK_LEVELS for v in (0, 120) if (lv, v) != ("lights", 120)]
+
+
+@pytest.mark.parametrize("level,maxv", TICK_CASES)
+def test_emu_levels_with_device_tick_handlers(ref_lib, emu, level, maxv):
+    def step_hash(w):
+        w.step(31 | TICKS | 32)
+        return w.hash()[0]
+    w, n0, n1 = _run_tick_level(ref_lib, level, lambda wa: emu.EmuWorld(wa, rebuild_every=4, shuffle_seed=9),
+                                step_hash, maxv, 60)
+    assert w.unsupported() == 0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("level,maxv", TICK_CASES)
+def test_cuda_levels_with_device_tick_handlers(ref_lib, bt, level, maxv):
+    """bt_world_tick alone = doWholeStep of the unmodified reference, tick handlers and world rules included"""
+    w, n0, n1 = _run_tick_level(ref_lib, level, lambda wa: bt.World(wa), lambda w: int(w.tick(1, hashes=True)[0, 0]),
+                                maxv, 150)
+    st = w.stats()
+    assert st["unsupported_events"] == 0 and st["live_ents"] == n1
     w.close()
