@@ -18,6 +18,7 @@ LIB_SO = os.path.join(HERE, "libbittoss_b200.so")
 INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 
 PHASE_CTRLS, PHASE_PREP, PHASE_GRAVITY, PHASE_PHYSICS, PHASE_FINISH, PHASE_ALL = 1, 2, 4, 8, 16, 31
+PHASE_WORLD_RULES, PHASE_TICKS = 32, 64
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
               "-shared"]
 
