@@ -820,6 +820,23 @@ static BT_HD void t_lbvh_node(const DevWorld &W, int i) {
 	else { N.right = gamma + 1; W.nodeParent[gamma + 1] = i; }
 	W.nodeHi[i] = hi;
 	if (i == 0) W.nodeParent[0] = -1;
+	/* World roots.  Keys carry the world id in their top bits, so every world is one subtree;
+	 * the nodes above (they span several worlds, whose boxes all overlap) would only cost every
+	 * query and every refit ~log2(worlds) extra levels.  A child of a multi-world node that is
+	 * all one world IS that world (a Karras node holds every key with its prefix): cut it loose. */
+	u32 wlo = (u32)(W.keys[lo] >> 30), whi = (u32)(W.keys[hi] >> 30);
+	if (wlo != whi) {
+		if ((u32)(W.keys[gamma] >> 30) == wlo) {
+			if (lo == gamma) { W.leafParent[gamma] = -1; W.wroot[wlo] = ~gamma; }
+			else { W.nodeParent[gamma] = -1; W.wroot[wlo] = gamma; }
+		}
+		if ((u32)(W.keys[gamma + 1] >> 30) == whi) {
+			if (hi == gamma + 1) { W.leafParent[gamma + 1] = -1; W.wroot[whi] = ~(gamma + 1); }
+			else { W.nodeParent[gamma + 1] = -1; W.wroot[whi] = gamma + 1; }
+		}
+	} else if (i == 0) {
+		W.wroot[wlo] = 0;
+	}
 }
 
 static BT_HD int bt_min(int a, int b) { return a < b ? a : b; }
@@ -1009,7 +1026,8 @@ static BT_HD void t_collide(const DevWorld &W, int t, i32 *stack, int stride, Lo
 	u32 ta = W.type[a], ca = W.collide[a], ha = W.hphys[a], wa = (u32)W.world[a];
 	i32 rootA = W.holdRoot[a];
 	int sp = 0;
-	int node = 0;
+	int node = W.wroot[wa]; /* this world's subtree */
+	if (node < 0) return;   /* it is the world's only leaf */
 	while (1) {
 		const NodeRegs N = bt_load_node(W, node);
 		i32 li = N.d.x, ri = N.d.y;
@@ -1066,7 +1084,8 @@ template <class Emit> static BT_HD void t_pairs_patch(const DevWorld &W, int t, 
 	const Box6 q = W.ibox[a], qo = W.iboxOld[a];
 	const u32 wa = (u32)q.lo.w;
 	const i32 qlo[3] = {q.lo.x, q.lo.y, q.lo.z}, qhi[3] = {q.hi.x, q.hi.y, q.hi.z};
-	int sp = 0, node = 0;
+	int sp = 0, node = W.wroot[wa];
+	if (node < 0) return;
 	while (1) {
 		const NodeRegs N = bt_load_node(W, node);
 		i32 li = N.d.x, ri = N.d.y;
@@ -1109,7 +1128,9 @@ template <class Emit> static BT_HD void t_pairs(const DevWorld &W, int t, i32 *s
 	Box6 q = W.leafBox[t];
 	u32 wa = (u32)q.lo.w;
 	const i32 qlo[3] = {q.lo.x, q.lo.y, q.lo.z}, qhi[3] = {q.hi.x, q.hi.y, q.hi.z};
-	int sp = 0, node = 0, cur_hi = L - 1;
+	int sp = 0, node = W.wroot[wa];
+	if (node < 0) return;
+	int cur_hi = W.nodeHi[node];
 	while (1) {
 		const NodeRegs N = bt_load_node(W, node);
 		i32 li = N.d.x, ri = N.d.y;

@@ -97,7 +97,11 @@ static BT_HD i32 t_raycast(const DevWorld &W, i32 p, const i32 look_in[3], i32 *
 		RAY_LEAF(0);
 		return winner;
 	}
-	int sp = 0, node = 0;
+	int sp = 0, node = W.wroot[wp];
+	if (node < 0) { /* a single leaf (~node), or none */
+		if (~node < L) RAY_LEAF(~node);
+		return winner;
+	}
 	while (1) {
 		const NodeRegs N = bt_load_node(W, node);
 		i32 li = N.d.x, ri = N.d.y;

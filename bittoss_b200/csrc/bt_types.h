@@ -160,6 +160,7 @@ struct DevWorld {
 	BvhNode *nodes;
 	Box6 *nodeBox, *leafBox;
 	i32 *nodeHi;     /* last leaf position below each internal node */
+	i32 *wroot;      /* per world: root of its subtree (node id, ~leaf for a single leaf, INT32_MIN none) */
 	Box6 *ibox;      /* per entity: the inflated swept box of the last refit */
 	Box6 *iboxOld;   /* per entity: the box it had before the patch of the current epoch (dirty entities only) */
 	i32 *leafOf;     /* entity -> sorted leaf position (inverse of leafEnt) */

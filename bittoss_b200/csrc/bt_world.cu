@@ -55,6 +55,7 @@ struct RayTree {
 	BvhNode *nodes;
 	Box6 *nodeBox, *leafBox;
 	i32 *rank2slot, *slot2rank;
+	i32 *wroot;
 	i32 n_leaves;
 	i32 key_shift[3];
 };
@@ -226,7 +227,7 @@ int bt_world_create(bt_world **out, int device, int32_t max_ents, int32_t max_sl
 	TRY(dalloc(w, &W.leafEnt, n)); TRY(dalloc(w, &W.leafEnt_alt, n));
 	TRY(dalloc(w, &W.leafParent, n)); TRY(dalloc(w, &W.nodeParent, n)); TRY(dalloc(w, &W.nodeCount, n));
 	TRY(dalloc(w, &W.nodes, n)); TRY(dalloc(w, &W.nodeBox, n)); TRY(dalloc(w, &W.leafBox, n));
-	TRY(dalloc(w, &W.nodeHi, n)); TRY(dalloc(w, &W.ibox, n));
+	TRY(dalloc(w, &W.nodeHi, n)); TRY(dalloc(w, &W.ibox, n)); TRY(dalloc(w, &W.wroot, nw + 1)); TRY(dalloc(w, &w->ray.wroot, nw + 1));
 	TRY(dalloc(w, &W.iboxOld, n)); TRY(dalloc(w, &W.leafOf, n)); TRY(dalloc(w, &W.dirtyList, n)); TRY(dalloc(w, &W.dirtyStamp, n));
 	W.patch = 1; W.patch_shift = 4;
 	W.pair_cap = (i32)std::min<size_t>((size_t)1 << 30, 12 * n + 4096);
@@ -470,6 +471,7 @@ static int build_tree(bt_world *w) {
 	LAUNCH(w, PK_BUILD_KEYS, k_morton, nblk(n), BT_BLOCK, W);
 	int r = radix_sort(w, 30 + W.world_bits);
 	if (r) return r;
+	CK(cudaMemsetAsync(W.wroot, 0x80, sizeof(i32) * (size_t)(w->cap_worlds + 1), w->stream)); /* "no subtree" */
 	if (W.n_leaves >= 2) LAUNCH(w, PK_LBVH, k_lbvh, nblk(W.n_leaves - 1), BT_BLOCK, W);
 	/* new topology: node boxes are stale until the next refit, counters restart even */
 	CK(cudaMemsetAsync(W.nodeCount, 0, sizeof(u32) * (size_t)n, w->stream));
@@ -1141,7 +1143,7 @@ static void ray_swap(bt_world *w) {
 	RayTree &R = w->ray;
 	std::swap(W.keys, R.keys); std::swap(W.keys_alt, R.keys_alt);
 	std::swap(W.leafEnt, R.leafEnt); std::swap(W.leafEnt_alt, R.leafEnt_alt);
-	std::swap(W.leafParent, R.leafParent); std::swap(W.nodeParent, R.nodeParent);
+	std::swap(W.leafParent, R.leafParent); std::swap(W.nodeParent, R.nodeParent); std::swap(W.wroot, R.wroot);
 	std::swap(W.nodeCount, R.nodeCount); std::swap(W.nodes, R.nodes);
 	std::swap(W.nodeBox, R.nodeBox); std::swap(W.leafBox, R.leafBox);
 	std::swap(W.n_leaves, R.n_leaves);

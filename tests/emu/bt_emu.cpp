@@ -88,6 +88,7 @@ Emu *bte_create(const bt_world_desc *d, int rebuild_every, int shuffle_seed) {
 	A(E, &W.keys, n); A(E, &W.keys_alt, n); A(E, &W.leafEnt, n); A(E, &W.leafEnt_alt, n);
 	A(E, &W.leafParent, n); A(E, &W.nodeParent, n); A(E, &W.nodeCount, n); A(E, &W.nodes, n);
 	A(E, &W.nodeBox, n); A(E, &W.leafBox, n); A(E, &W.nodeHi, n); A(E, &W.ibox, n);
+	A(E, &W.wroot, nw + 1);
 	A(E, &W.iboxOld, n); A(E, &W.leafOf, n); A(E, &W.dirtyList, n); A(E, &W.dirtyStamp, n);
 	W.patch = 1; W.patch_shift = 4;
 	W.pair_cap = 12 * n + 4096; W.margin = 32;
@@ -189,6 +190,7 @@ static void build_tree(Emu *E) {
 	std::vector<i32> v2(W.n);
 	for (i32 i = 0; i < W.n; i++) { k2[i] = W.keys[idx[i]]; v2[i] = W.leafEnt[idx[i]]; }
 	for (i32 i = 0; i < W.n; i++) { W.keys[i] = k2[i]; W.leafEnt[i] = v2[i]; }
+	for (i32 g = 0; g <= W.n_worlds; g++) W.wroot[g] = INT32_MIN;
 	for (i32 i = 0; i < L - 1; i++) t_lbvh_node(W, i);
 	for (i32 i = 0; i < W.n; i++) W.nodeCount[i] = 0;
 	if (!W.ray_mode) { W.ctr[CT_CACHE_INVALID] = 1; W.ctr[CT_CACHE_FULL] = 1; }
@@ -432,13 +434,14 @@ int bte_raycast(Emu *E, const int32_t *origin, const int32_t *look, int32_t n_ra
 	std::vector<u64> keys(W.n);
 	std::vector<i32> leafEnt(W.n), leafParent(W.n), nodeParent(W.n);
 	std::vector<u32> nodeCount(W.n);
+	std::vector<i32> wroot(W.n_worlds + 1);
 	std::vector<BvhNode> nodes(W.n ? W.n : 1);
 	std::vector<Box6> nodeBox(W.n ? W.n : 1), leafBox(W.n ? W.n : 1);
 	u32 ctr[CT_WORDS];
 	memset(ctr, 0, sizeof ctr);
 	W.keys = keys.data(); W.leafEnt = leafEnt.data(); W.leafParent = leafParent.data(); W.nodeParent = nodeParent.data();
 	W.nodeCount = nodeCount.data(); W.nodes = nodes.data(); W.nodeBox = nodeBox.data(); W.leafBox = leafBox.data();
-	W.ctr = ctr; W.ray_mode = 1;
+	W.ctr = ctr; W.ray_mode = 1; W.wroot = wroot.data();
 	Emu tmp = *E;
 	tmp.W = W; tmp.shuffle_seed = 0;
 	build_tree(&tmp);

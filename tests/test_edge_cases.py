@@ -161,3 +161,49 @@ def test_world_rules_cuda(bt, oracle_lib, rules):
         assert int(hs[t, 0]) == ow.hash()[0], t
     assert w.count()[0] == ow.count()[0] < wa.n
     w.close()
+
+
+def _ragged_batch():
+    """worlds of very different sizes in one device world: the LBVH gives each its own subtree
+    (a single-leaf world is just that leaf, a world without boxes has none)"""
+    import bittoss_b200
+    order = ["single", "pile_of_40_same_place", "empty", "no_boxes_at_all", "two_overlapping", "single",
+             "one_tree_of_25", "row_touching"]
+    return order, bittoss_b200.concat_worlds([CASES[k]() for k in order])
+
+
+def test_ragged_batch_kernel_bodies_vs_oracle(oracle_lib, emu):
+    order, batch = _ragged_batch()
+    ow = oracle_lib.create(batch)
+    ew = emu.EmuWorld(batch, rebuild_every=3, shuffle_seed=5)
+    alone = [oracle_lib.create(CASES[k]()) for k in order]
+    for t in range(30):
+        ow.step(31)
+        ew.step(31)
+        for a in alone:
+            a.step(31)
+        assert ew.hash() == ow.hash() == [a.hash()[0] for a in alone], t
+    rng = np.random.RandomState(1)
+    n = ow.count()[0]
+    origin = rng.randint(0, n, size=400).astype(np.int32)
+    look = rng.randint(-64, 65, size=(400, 3)).astype(np.int32)
+    look[np.abs(look).sum(1) == 0] = (0, 0, 64)
+    assert np.array_equal(ow.selectcast(origin, look), ew.raycast(origin, look))
+
+
+@pytest.mark.gpu
+def test_ragged_batch_cuda_vs_oracle(bt, oracle_lib):
+    order, batch = _ragged_batch()
+    ow = oracle_lib.create(batch)
+    w = bt.World(batch)
+    for t in range(30):
+        ow.step(31)
+        w.step(31)
+        assert [int(x) for x in w.hash()] == ow.hash(), t
+    rng = np.random.RandomState(1)
+    n = ow.count()[0]
+    origin = rng.randint(0, n, size=400).astype(np.int32)
+    look = rng.randint(-64, 65, size=(400, 3)).astype(np.int32)
+    look[np.abs(look).sum(1) == 0] = (0, 0, 64)
+    assert np.array_equal(ow.selectcast(origin, look), w.raycast(origin, look))
+    w.close()
