@@ -14,13 +14,15 @@ ROOT = os.path.dirname(HERE)
 sys.path.insert(0, ROOT)
 from bittoss_b200.desc import BtWorldDesc, WorldArrays  # noqa: E402
 
-EMU_SO = os.path.join(HERE, "emu", "libbtemu.so")
+EMU_SO = os.environ.get("BT_EMU_SO", os.path.join(HERE, "emu", "libbtemu.so"))  # override: a sanitizer build
 _i32p = C.POINTER(C.c_int32)
 
 
 def build_emu(force=False):
     src = os.path.join(HERE, "emu", "bt_emu.cpp")
     deps = [src] + [os.path.join(ROOT, "bittoss_b200", "csrc", f) for f in ("bt_phys.cuh", "bt_types.h", "bt_raycast.cuh")]
+    if "BT_EMU_SO" in os.environ:
+        return
     if not force and os.path.exists(EMU_SO) and all(os.path.getmtime(EMU_SO) >= os.path.getmtime(d) for d in deps):
         return
     subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-Wno-unknown-pragmas", "-o", EMU_SO, src])
