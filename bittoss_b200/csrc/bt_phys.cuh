@@ -1330,6 +1330,12 @@ static BT_HD void bt_push_pickup(const DevWorld &W, i32 e, i32 holder, u32 key, 
 		bt_crush(W, e, key, st);
 		return;
 	}
+	/* The reference runs every push it decided on (ent.cpp:879-882) even if an earlier push of
+	 * the same iteration killed the would-be holder: e->holder then dangles once clearDeads frees
+	 * it (use-after-free in the reference; observed with 2048 arena worlds, one case in ~10^5
+	 * world-ticks).  Done the same way here, the entity ends up attached to a retired slot,
+	 * and counted, because from this point on the reference's own behaviour is undefined. */
+	if (W.dead[holder]) bt_unsup(W, e, 7, 0);
 	bt_pickup(W, holder, e, 0);
 }
 
@@ -1868,8 +1874,12 @@ static BT_HD void t_begin_fused(const DevWorld &W, i32 e, int gravity, int ctrls
 static BT_HD u64 bt_ent_hash(const DevWorld &W, i32 e) {
 	int4 c = W.center[e], v = W.vel[e];
 	i32 hd = W.holder[e];
-	i32 wd[10] = {c.x, c.y, c.z, v.x, v.y, v.z, (i32)W.type[e], (i32)W.collide[e], hd >= 0 ? W.uid[hd] : -1,
-	              W.holdFlags[e]};
+	/* A holder that died this tick after its holdees were fumbled can still pick something up in a
+	 * later push of the same iteration (the reference runs every decided push, ent.cpp:879-882, and
+	 * leaves a dangling e->holder behind once clearDeads frees it): hashed as "no holder", which is
+	 * also what an export / download reports. */
+	i32 wd[10] = {c.x, c.y, c.z, v.x, v.y, v.z, (i32)W.type[e], (i32)W.collide[e],
+	              hd >= 0 && W.inList[hd] ? W.uid[hd] : -1, W.holdFlags[e]};
 	u64 h = bt_mix64((u64)(u32)W.uid[e] + 0x9E3779B97F4A7C15ULL);
 	for (int k = 0; k < 10; k++) h = bt_mix64(h + (u64)(u32)wd[k] + 0x9E3779B97F4A7C15ULL);
 	return h;

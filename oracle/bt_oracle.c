@@ -1501,7 +1501,8 @@ void bto_hash(const World *w, uint64_t *out) {
 			if (!w->inList[e]) continue;
 			i32 wd[10] = {w->center[e][0], w->center[e][1], w->center[e][2], w->vel[e][0], w->vel[e][1],
 			              w->vel[e][2], (i32)w->type[e], (i32)w->collide[e],
-			              w->holder[e] >= 0 ? w->uid[w->holder[e]] : -1, w->holdFlags[e]};
+			              w->holder[e] >= 0 && w->inList[w->holder[e]] ? w->uid[w->holder[e]] : -1, /* a dead holder = none */
+			              w->holdFlags[e]};
 			uint64_t h = mix64((uint64_t)(uint32_t)w->uid[e] + 0x9E3779B97F4A7C15ULL);
 			for (int k = 0; k < 10; k++) h = mix64(h + (uint64_t)(uint32_t)wd[k] + 0x9E3779B97F4A7C15ULL);
 			sum += h;
