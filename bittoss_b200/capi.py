@@ -34,7 +34,7 @@ class BtTickStats(C.Structure):
     _fields_ = [(k, C.c_int64) for k in
                 ("ticks", "iterations", "candidate_pairs", "positives", "pushes", "serial_pushes", "crushes",
                  "fumbles", "kernel_launches", "tree_builds", "tree_refits", "live_ents", "entity_ticks",
-                 "pair_builds", "pairs_cached", "pair_overflows", "unsupported_events", "pair_patches")]
+                 "pair_builds", "pairs_cached", "pair_overflows", "unsupported_events", "pair_patches", "order_ties")]
 
 
 class BtEvent(C.Structure):
@@ -100,6 +100,7 @@ def lib():
     L.bt_world_stream.restype = C.c_void_p
     L.bt_world_hash.argtypes = [C.c_void_p, _u64p]
     L.bt_world_stats.argtypes = [C.c_void_p, C.POINTER(BtTickStats), C.c_int]
+    L.bt_world_order_ties.argtypes = [C.c_void_p, C.POINTER(C.c_uint32)]
     L.bt_world_apply_requests.argtypes = [C.c_void_p, C.POINTER(BtRequest), C.c_int32]
     L.bt_world_drain_events.argtypes = [C.c_void_p, C.POINTER(BtEvent), C.c_int32, C.POINTER(C.c_int32)]
     L.bt_world_unsupported.argtypes = [C.c_void_p, C.POINTER(C.c_uint32)]
@@ -278,6 +279,11 @@ class World:
         n = C.c_int32()
         _ck(self.L.bt_world_drain_events(self.h, buf, max_events, C.byref(n)), "bt_world_drain_events")
         return [{k: int(getattr(buf[i], k)) for k, _ in BtEvent._fields_} for i in range(n.value)]
+
+    def order_ties_per_world(self):
+        out = np.zeros(self.n_worlds, dtype=np.uint32)
+        _ck(self.L.bt_world_order_ties(self.h, out.ctypes.data_as(C.POINTER(C.c_uint32))), "bt_world_order_ties")
+        return out
 
     def unsupported_per_world(self):
         out = np.zeros(self.n_worlds, dtype=np.uint32)

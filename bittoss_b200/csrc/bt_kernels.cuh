@@ -51,9 +51,11 @@ __global__ void __launch_bounds__(BT_BLOCK) k_flush_serial(DevWorld W) {
 __global__ void __launch_bounds__(BT_BLOCK) k_flush_misc(DevWorld W) { t_flush_misc(W, TID); }
 __global__ void __launch_bounds__(BT_BLOCK) k_tick(DevWorld W) { t_tick(W, TID); }
 __global__ void __launch_bounds__(BT_BLOCK) k_tick_serial(DevWorld W) { t_tick_serial(W, TID); }
-__global__ void k_requests(DevWorld W, const BtReq *q, i32 n) {
-	if (threadIdx.x != 0 || blockIdx.x != 0) return;
-	for (i32 i = 0; i < n; i++) t_request(W, q[i]);
+/* requests arrive grouped by world (stable), one thread per world applies its run in order */
+__global__ void __launch_bounds__(BT_BLOCK) k_requests(DevWorld W, const BtReq *q, const i32 *starts, i32 n_groups) {
+	i32 g = TID;
+	if (g >= n_groups) return;
+	for (i32 i = starts[g]; i < starts[g + 1]; i++) t_request(W, q[i]);
 }
 __global__ void __launch_bounds__(BT_BLOCK) k_gravity(DevWorld W) { t_gravity(W, TID); }
 __global__ void __launch_bounds__(BT_BLOCK) k_world_rules(DevWorld W) { t_world_rules(W, TID); }

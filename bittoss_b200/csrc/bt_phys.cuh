@@ -588,10 +588,13 @@ struct GeoView {
 	const int4 *old, *center, *radius;
 	u64 *pend;
 	const i32 *holdRoot;
+	const i32 *world;
+	u32 *wties, *ctr;
 };
 static BT_HD GeoView bt_view(const DevWorld &W) {
 	GeoView v;
 	v.old = W.old; v.center = W.center; v.radius = W.radius; v.pend = W.pend; v.holdRoot = W.holdRoot;
+	v.world = W.world; v.wties = W.wties; v.ctr = W.ctr;
 	return v;
 }
 static BT_HD EntGeo bt_geo(const GeoView &V, i32 e) {
@@ -665,7 +668,15 @@ static BT_HD void bt_propose_v(const GeoView &W, i32 leaf, i32 buddy, int axis, 
 			Coll inc = bt_unpack_coll(cur);
 			int r = bt_collision_cmp(W, c, inc);
 			if (r < 0) return;
-			if (r == 0 && (mine >> 2) <= (cur >> 2)) return;
+			if (r == 0) {
+				/* A full tie between two different collisions: the reference keeps whichever its list
+				 * order met first (tryCollide only replaces on "better", ent.cpp:367-396), here the
+				 * larger key wins.  Almost always the same outcome; counted, because when it is
+				 * not (two equal supporters, one of which is hit in the same tick) the reference's
+				 * answer depends on its visiting order. */
+				if ((mine >> 2) != (cur >> 2)) { bt_add32(&W.wties[W.world[root]], 1u); bt_add32(&W.ctr[CT_ORDER_TIES], 1u); }
+				if ((mine >> 2) <= (cur >> 2)) return;
+			}
 		}
 		u64 prev = bt_cas64(&W.pend[root], cur, mine);
 		if (prev == cur) return;

@@ -108,6 +108,7 @@ enum {
 	CT_PATCH_EPOCH = 43, /* counts consumed builds / patches; dirtyStamp[e] == epoch + 1 <=> e is in dirtyList */
 	CT_PAIR_N_FULL = 44, /* CT_PAIR_N right after the last full build */
 	CT_PAIR_PATCHES = 45, /* incremental pair-list patches (k_refit / k_pairs in patch mode) */
+	CT_ORDER_TIES = 46,  /* full collisionBetter ties between different collisions (resolved by the canonical key) */
 	CT_WORDS = 64
 };
 enum { SK_ITERS = 0, SK_CAND, SK_POS, SK_PUSH, SK_SERIAL, SK_CRUSH, SK_FUMBLE, SK_NUM };
@@ -133,6 +134,7 @@ struct DevWorld {
 
 	i32 *wbegin, *wend, *flip, *gamerules, *rnd; /* per world */
 	u32 *wunsup;                                 /* per world: would-be invocations of unimplemented handlers */
+	u32 *wties;                                  /* per world: CT_ORDER_TIES */
 	u8 *wflush;                                  /* per world: serial flush1 work pending */
 
 	i32 *world, *uid;

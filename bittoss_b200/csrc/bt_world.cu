@@ -77,7 +77,7 @@ struct bt_world {
 	bool any_ticks, any_rand; /* some entity has a tick handler / a TICK_RAND */
 	int bad_tick;             /* first tick handler id without a device implementation, 0 = none */
 	int device_ticks;         /* option: bt_world_tick runs the tick handlers itself when it can */
-	BtReq *d_reqs; i32 reqs_cap;
+	BtReq *d_reqs; i32 *d_req_starts; i32 reqs_cap;
 	int full_flush_left; /* flush1 calls that must run in full (after an upload); afterwards CT_FLUSH_HINT decides */
 	bool ctrls_fused;    /* flushCtrls of this step rides in k_begin_fused */
 	i32 ticks_since_build;
@@ -169,6 +169,7 @@ void bt_world_destroy(bt_world *w) {
 	for (void *p : w->allocs) cudaFree(p);
 	if (w->h_flag) cudaFreeHost(w->h_flag);
 	if (w->d_reqs) cudaFree(w->d_reqs);
+	if (w->d_req_starts) cudaFree(w->d_req_starts);
 	if (w->ev0) cudaEventDestroy(w->ev0);
 	if (w->ev1) cudaEventDestroy(w->ev1);
 	if (w->stream) cudaStreamDestroy(w->stream);
@@ -192,7 +193,7 @@ int bt_world_create(bt_world **out, int device, int32_t max_ents, int32_t max_sl
 	w->device = device;
 	w->cap_ents = max_ents; w->cap_sliders = max_sliders; w->cap_wires = max_wires; w->cap_worlds = max_worlds;
 	w->tree_valid = false; w->deltas_pending = true; w->ticks_since_build = 0; w->full_flush_left = 2; w->ctrls_fused = false;
-	w->rebuild_every = 16; w->max_iterations = 100000; w->pair_cache = 1; w->pair_rebuilds = 0; w->pair_overflows = 0; w->seen_pair_builds = 0; w->seen_pair_patches = 0; w->pair_builds_at_tree = 0; w->profiling = false; w->ray_valid = false; w->uid_map_valid = false; w->d_reqs = NULL; w->reqs_cap = 0; w->any_ticks = w->any_rand = false; w->bad_tick = 0; w->device_ticks = 1;
+	w->rebuild_every = 16; w->max_iterations = 100000; w->pair_cache = 1; w->pair_rebuilds = 0; w->pair_overflows = 0; w->seen_pair_builds = 0; w->seen_pair_patches = 0; w->pair_builds_at_tree = 0; w->profiling = false; w->ray_valid = false; w->uid_map_valid = false; w->d_reqs = NULL; w->d_req_starts = NULL; w->reqs_cap = 0; w->any_ticks = w->any_rand = false; w->bad_tick = 0; w->device_ticks = 1;
 	w->h_flag = NULL; w->ev0 = w->ev1 = NULL; w->stream = NULL;
 	*out = w;
 #define TRY(x) do { int _r = (x); if (_r) { bt_world_destroy(w); *out = NULL; return _r; } } while (0)
@@ -204,7 +205,7 @@ int bt_world_create(bt_world **out, int device, int32_t max_ents, int32_t max_sl
 	DevWorld &W = w->W;
 	size_t n = (size_t)max_ents, nw = (size_t)max_worlds;
 	TRY(dalloc(w, &W.wbegin, nw)); TRY(dalloc(w, &W.wend, nw)); TRY(dalloc(w, &W.flip, nw));
-	TRY(dalloc(w, &W.gamerules, nw)); TRY(dalloc(w, &W.rnd, nw)); TRY(dalloc(w, &W.wflush, nw)); TRY(dalloc(w, &W.wunsup, nw));
+	TRY(dalloc(w, &W.gamerules, nw)); TRY(dalloc(w, &W.rnd, nw)); TRY(dalloc(w, &W.wflush, nw)); TRY(dalloc(w, &W.wunsup, nw)); TRY(dalloc(w, &W.wties, nw));
 	TRY(dalloc(w, &W.world, n)); TRY(dalloc(w, &W.uid, n));
 	TRY(dalloc(w, &W.center, n)); TRY(dalloc(w, &W.old, n)); TRY(dalloc(w, &W.vel, n));
 	TRY(dalloc(w, &W.radius, n)); TRY(dalloc(w, &W.d_center, n)); TRY(dalloc(w, &W.d_vel, n));
@@ -821,30 +822,42 @@ int bt_world_apply_requests(bt_world *w, const bt_request *reqs, int32_t n) {
 		for (i32 i = 0; i < W.n; i++) w->uid_map[((u64)(u32)world[i] << 32) | (u32)uid[i]] = i;
 		w->uid_map_valid = true;
 	}
+	/* group by world, keeping the caller's order inside a world (the updaters of one gamestate are
+	 * order-sensitive, e.g. uPickup is first come first served; different worlds are independent) */
+	std::vector<i32> order((size_t)n);
+	for (i32 i = 0; i < n; i++) order[i] = i;
+	std::stable_sort(order.begin(), order.end(), [&](i32 a, i32 b) { return reqs[a].world < reqs[b].world; });
+	std::vector<i32> starts;
 	std::vector<BtReq> q((size_t)n);
 	bool deltas = false;
 	for (i32 i = 0; i < n; i++) {
-		const bt_request &r = reqs[i];
-		if (r.kind < 0 || r.kind >= BT_REQ_NUM) { snprintf(g_err, sizeof g_err, "request %d: unknown kind %d", i, r.kind); return BT_ERR_ARG; }
+		const bt_request &r = reqs[order[i]];
+		if (i == 0 || r.world != reqs[order[i - 1]].world) starts.push_back(i);
+		if (r.kind < 0 || r.kind >= BT_REQ_NUM) { snprintf(g_err, sizeof g_err, "request %d: unknown kind %d", order[i], r.kind); return BT_ERR_ARG; }
 		auto it = w->uid_map.find(((u64)(u32)r.world << 32) | (u32)r.me_uid);
-		if (it == w->uid_map.end()) { snprintf(g_err, sizeof g_err, "request %d: no entity uid %d in world %d", i, r.me_uid, r.world); return BT_ERR_ARG; }
+		if (it == w->uid_map.end()) { snprintf(g_err, sizeof g_err, "request %d: no entity uid %d in world %d", order[i], r.me_uid, r.world); return BT_ERR_ARG; }
 		q[i].kind = r.kind; q[i].me = it->second; q[i].other = -1;
 		if (r.kind == BT_REQ_PICKUP) {
 			auto jt = w->uid_map.find(((u64)(u32)r.world << 32) | (u32)r.other_uid);
-			if (jt == w->uid_map.end()) { snprintf(g_err, sizeof g_err, "request %d: no entity uid %d in world %d", i, r.other_uid, r.world); return BT_ERR_ARG; }
+			if (jt == w->uid_map.end()) { snprintf(g_err, sizeof g_err, "request %d: no entity uid %d in world %d", order[i], r.other_uid, r.world); return BT_ERR_ARG; }
 			q[i].other = jt->second;
 		}
 		q[i].a0 = r.a[0]; q[i].a1 = r.a[1]; q[i].a2 = r.a[2];
 		deltas |= r.kind == BT_REQ_VEL || r.kind == BT_REQ_CENTER;
 	}
+	starts.push_back(n);
+	const i32 n_groups = (i32)starts.size() - 1;
 	if (n > w->reqs_cap) {
 		if (w->d_reqs) cudaFree(w->d_reqs);
-		w->d_reqs = NULL; w->reqs_cap = 0;
+		if (w->d_req_starts) cudaFree(w->d_req_starts);
+		w->d_reqs = NULL; w->d_req_starts = NULL; w->reqs_cap = 0;
 		CK(cudaMalloc(&w->d_reqs, sizeof(BtReq) * (size_t)n));
+		CK(cudaMalloc(&w->d_req_starts, sizeof(i32) * ((size_t)n + 1)));
 		w->reqs_cap = n;
 	}
 	CK(cudaMemcpyAsync(w->d_reqs, q.data(), sizeof(BtReq) * (size_t)n, cudaMemcpyHostToDevice, w->stream));
-	LAUNCH(w, PK_EXCHANGE, k_requests, 1, 32, W, (const BtReq *)w->d_reqs, n);
+	CK(cudaMemcpyAsync(w->d_req_starts, starts.data(), sizeof(i32) * starts.size(), cudaMemcpyHostToDevice, w->stream));
+	LAUNCH(w, PK_EXCHANGE, k_requests, nblk(n_groups), BT_BLOCK, W, (const BtReq *)w->d_reqs, (const i32 *)w->d_req_starts, n_groups);
 	CK(cudaStreamSynchronize(w->stream)); /* q goes out of scope */
 	if (deltas) w->deltas_pending = true;
 	if (w->full_flush_left < 1) w->full_flush_left = 1; /* the next flush1 has requests to look at */
@@ -885,6 +898,8 @@ int bt_world_stats(bt_world *w, bt_tick_stats *out, int reset) {
 		u32 un = 0;
 		CK(cudaMemcpy(&un, &w->W.ctr[CT_UNSUPPORTED], sizeof(u32), cudaMemcpyDeviceToHost));
 		w->stats.unsupported_events = (i64)un;
+		CK(cudaMemcpy(&un, &w->W.ctr[CT_ORDER_TIES], sizeof(u32), cudaMemcpyDeviceToHost));
+		w->stats.order_ties = (i64)un;
 	}
 	*out = w->stats;
 	if (reset) {
@@ -894,6 +909,8 @@ int bt_world_stats(bt_world *w, bt_tick_stats *out, int reset) {
 		CK(cudaMemsetAsync(&w->W.ctr[CT_STAT0], 0, sizeof(s), w->stream));
 		CK(cudaMemsetAsync(&w->W.ctr[CT_UNSUPPORTED], 0, sizeof(u32), w->stream));
 		CK(cudaMemsetAsync(w->W.wunsup, 0, sizeof(u32) * (size_t)w->cap_worlds, w->stream));
+		CK(cudaMemsetAsync(&w->W.ctr[CT_ORDER_TIES], 0, sizeof(u32), w->stream));
+		CK(cudaMemsetAsync(w->W.wties, 0, sizeof(u32) * (size_t)w->cap_worlds, w->stream));
 	}
 	return BT_OK;
 }
@@ -935,6 +952,14 @@ int bt_world_unsupported(bt_world *w, uint32_t *per_world) {
 	CK(cudaSetDevice(w->device));
 	CK(cudaStreamSynchronize(w->stream));
 	CK(cudaMemcpy(per_world, w->W.wunsup, sizeof(u32) * (size_t)w->W.n_worlds, cudaMemcpyDeviceToHost));
+	return BT_OK;
+}
+
+int bt_world_order_ties(bt_world *w, uint32_t *per_world) {
+	if (!w || !per_world) return BT_ERR_ARG;
+	CK(cudaSetDevice(w->device));
+	CK(cudaStreamSynchronize(w->stream));
+	CK(cudaMemcpy(per_world, w->W.wties, sizeof(u32) * (size_t)w->W.n_worlds, cudaMemcpyDeviceToHost));
 	return BT_OK;
 }
 

@@ -138,6 +138,8 @@ typedef struct bt_tick_stats {
 	int64_t unsupported_events; /* lenient uploads only ("allow_unsupported"): times a handler with no device
 	                           * implementation would have been invoked; != 0 means the state diverged */
 	int64_t pair_patches;    /* incremental updates of the cached pair list (moved entities only)  */
+	int64_t order_ties;      /* full collisionBetter ties between different collisions: the reference keeps the
+	                          * one its list order met first, the device the larger key */
 } bt_tick_stats;
 
 /* Per-kernel-class device timing, filled only while profiling is enabled. */
@@ -247,6 +249,8 @@ int bt_world_hash(bt_world *w, uint64_t *out);
 int bt_world_stats(bt_world *w, bt_tick_stats *out, int reset);
 /* Copies out (and clears) the events queued since the last drain; *n = how many were written,
  * at most max.  Returns BT_ERR_OVERFLOW if the device queue (65536 entries) had overflowed. */
+/* per world: full ties since the last stats reset (see bt_tick_stats.order_ties) */
+int bt_world_order_ties(bt_world *w, uint32_t *per_world);
 int bt_world_drain_events(bt_world *w, bt_event *out, int32_t max, int32_t *n);
 /* per world [n_worlds]: unsupported_events since the last bt_world_stats(reset) */
 int bt_world_unsupported(bt_world *w, uint32_t *per_world);

@@ -112,6 +112,7 @@ typedef struct {
 	i32 stampCtr;
 	int64_t stats[8];
 	int64_t n_events; /* host-side handler invocations reported instead of executed */
+	int64_t order_ties; /* full ties resolved by the canonical key */
 	ilist crush_log;  /* uids whose crush handler invokeOnCrush would have run, in call order */
 } World;
 
@@ -650,6 +651,7 @@ static int tryCollide(World *w, i32 leaf, i32 buddy, int axis, int dir, int mutu
 			int64_t ki[4] = {inc.buddy, inc.leaf, inc.axis, inc.dir};
 			int k = 0;
 			while (k < 4 && kc[k] == ki[k]) k++;
+			if (k < 4) w->order_ties++; /* two different collisions, equal under collisionBetter: the reference keeps the first it met */
 			if (k == 4 || kc[k] < ki[k]) return 0;
 		}
 	} else {
@@ -1652,6 +1654,8 @@ int bto_request(World *w, int kind, i32 me_uid, i32 other_uid, i32 a0, i32 a1, i
 	}
 	return 0;
 }
+
+int64_t bto_order_ties(const World *w) { return w->order_ties; }
 
 void bto_stats(const World *w, int64_t *out) { memcpy(out, w->stats, sizeof(w->stats)); }
 

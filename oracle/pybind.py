@@ -222,6 +222,8 @@ class OracleLib:
         L.bto_time_steps.argtypes = [C.c_void_p, C.c_int32, C.POINTER(C.c_int64)]
         L.bto_time_steps.restype = C.c_double
         L.bto_crush_log.argtypes = [C.c_void_p, _i32p, C.c_int]
+        L.bto_order_ties.argtypes = [C.c_void_p]
+        L.bto_order_ties.restype = C.c_int64
         L.bto_request.argtypes = [C.c_void_p, C.c_int] + [C.c_int32] * 5
         self.L = L
 
@@ -255,6 +257,9 @@ class OracleWorld:
         a = list(a) + [0] * (3 - len(a))
         if self.L.bto_request(self.h, kind, me_uid, other_uid, a[0], a[1], a[2]) != 0:
             raise RuntimeError("bto_request failed")
+
+    def order_ties(self):
+        return int(self.L.bto_order_ties(self.h))
 
     def crush_log(self):
         buf = (C.c_int32 * 4096)()

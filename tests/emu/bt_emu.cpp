@@ -73,7 +73,7 @@ Emu *bte_create(const bt_world_desc *d, int rebuild_every, int shuffle_seed) {
 	DevWorld &W = E->W;
 	const int n = d->n_ents, nw = d->n_worlds;
 	W.n = n; W.n_worlds = nw;
-	A(E, &W.wbegin, nw); A(E, &W.wend, nw); A(E, &W.flip, nw); A(E, &W.gamerules, nw); A(E, &W.rnd, nw); A(E, &W.wflush, nw); A(E, &W.wunsup, nw);
+	A(E, &W.wbegin, nw); A(E, &W.wend, nw); A(E, &W.flip, nw); A(E, &W.gamerules, nw); A(E, &W.rnd, nw); A(E, &W.wflush, nw); A(E, &W.wunsup, nw); A(E, &W.wties, nw);
 	A(E, &W.world, n); A(E, &W.uid, n); A(E, &W.center, n); A(E, &W.old, n); A(E, &W.vel, n); A(E, &W.radius, n);
 	A(E, &W.d_center, n); A(E, &W.d_vel, n); A(E, &W.type, n); A(E, &W.collide, n); A(E, &W.ntype, n); A(E, &W.ncollide, n);
 	A(E, &W.friction, n); A(E, &W.holder, n); A(E, &W.holdFlags, n); A(E, &W.holdRoot, n); A(E, &W.holdee, n);
@@ -411,6 +411,7 @@ int bte_export_misc(Emu *E, int32_t *uid, int32_t *holder_uid, int32_t *n_slider
 	return k;
 }
 int64_t bte_unsupported(Emu *E) { return (int64_t)E->W.ctr[CT_UNSUPPORTED]; }
+int64_t bte_order_ties(Emu *E) { return (int64_t)E->W.ctr[CT_ORDER_TIES]; }
 int64_t bte_unsupported_last(Emu *E) { return (int64_t)E->W.ctr[CT_UNSUP_LAST]; }
 
 void bte_stats(Emu *E, int64_t *out) {

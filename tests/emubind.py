@@ -48,6 +48,8 @@ class EmuWorld:
         L.bte_events.restype = C.c_int64
         L.bte_unsupported.argtypes = [C.c_void_p]
         L.bte_unsupported.restype = C.c_int64
+        L.bte_order_ties.argtypes = [C.c_void_p]
+        L.bte_order_ties.restype = C.c_int64
         L.bte_raycast.argtypes = [C.c_void_p, _i32p, _i32p, C.c_int32, _i32p]
         L.bte_drain_events.argtypes = [C.c_void_p, _i32p, C.c_int]
         L.bte_request.argtypes = [C.c_void_p, C.c_int] + [C.c_int32] * 5
@@ -105,6 +107,9 @@ class EmuWorld:
 
     def unsupported(self):
         return int(self.L.bte_unsupported(self.h))
+
+    def order_ties(self):
+        return int(self.L.bte_order_ties(self.h))
 
     def pair_rebuilds(self):
         return int(self.L.bte_pair_rebuilds(self.h))

@@ -214,3 +214,29 @@ def test_cuda_levels_with_device_tick_handlers(ref_lib, bt, level, maxv):
     st = w.stats()
     assert st["unsupported_events"] == 0 and st["live_ents"] == n1
     w.close()
+
+
+@pytest.mark.gpu
+def test_cuda_requests_across_batched_worlds(bt):
+    """three labs as three worlds of ONE device world, each driven by its own script through one
+    bt_world_apply_requests call per tick (requests interleaved across worlds): every world must
+    follow its own fixture"""
+    names = ["lab_seats", "lab_logic", "lab_seats"]
+    loaded = [load_world(golden_path(n)) for n in names]
+    w = bt.World(bt.concat_worlds([wa for wa, _ in loaded]))
+    ticks = min(len(ex["ref_hashes"]) for _, ex in loaded)
+    for t in range(ticks):
+        per_world = []
+        for g, (_, ex) in enumerate(loaded):
+            sc = ex["script"]
+            per_world.append([(int(what), g, int(uid), int(other), (int(arg), 0, 0))
+                              for (_, what, uid, other, arg) in sc[sc[:, 0] == t]])
+        reqs = []                              # round-robin merge: worlds interleaved, per-world order kept
+        for i in range(max(len(p) for p in per_world)):
+            reqs += [p[i] for p in per_world if i < len(p)]
+        if reqs:
+            w.apply_requests(reqs)
+        hs = w.tick(1, hashes=True)[0]         # lab_logic needs the tick phase: bt_world_tick adds it (all worlds)
+        for g, (_, ex) in enumerate(loaded):
+            assert int(hs[g]) == int(ex["ref_hashes"][t]), (names[g], t)
+    w.close()
