@@ -13,7 +13,14 @@ wa = bittoss_b200.synth_boxstack(cubes, 4, 777, 64, 60)
 w = bittoss_b200.World(wa)
 w.tick(warm)
 s0 = w.stats(reset=True)
+w.sync()
+# under `ncu --profile-from-start off` only the measured ticks are captured
+import ctypes
+_cu = ctypes.CDLL("libcuda.so.1")
+_cu.cuProfilerStart()
 w.tick(ticks)
+w.sync()
+_cu.cuProfilerStop()
 s = w.stats()
 print("ticks", ticks, "launches", s["kernel_launches"], "iterations", s["iterations"], "hash", hex(w.hash()[0]))
 w.close()
