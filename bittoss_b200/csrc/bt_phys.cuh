@@ -71,7 +71,11 @@ static BT_HD void bt_upickup(const DevWorld &W, i32 p, i32 e, i32 holdFlags);
 /* needsVelbox ent.cpp:75-77 */
 static BT_HD int bt_needs_box(u32 type, u32 collide) { return collide || (type & T_COLLIDABLE); }
 
-/* a handler with no device implementation would have run for entity e (lenient uploads only) */
+/* Something the device cannot answer like the reference happened for entity e: a handler without
+ * a device implementation would have run (lenient uploads only; kinds 0 push, 1 pushed, 2 entPair,
+ * 3 crush, 5 wire request overflow, 6 tick), or the reference itself leaves defined behaviour
+ * (kind 0 id 6: teleport while pad / destination are being pushed; kind 7: pickup by a dead entity).
+ * Counted, never silent. */
 static BT_HD void bt_unsup(const DevWorld &W, i32 e, int kind, int id) {
 	W.ctr[CT_UNSUP_LAST] = (u32)(kind << 8 | id);
 	bt_add32(&W.ctr[CT_UNSUPPORTED], 1u);
@@ -1679,8 +1683,7 @@ static BT_HD void t_flush_scan(const DevWorld &W, i32 e) {
 }
 
 /* flush1 ent.cpp:794-802, serial part, one thread per world: flushDeaths :747-761,
- * flushDrops :765-773.  flushPickups (:775-792) is host-side in this version: a pending
- * newHolder raises BT_ERR_UNSUPPORTED instead of being silently dropped. */
+ * flushDrops :765-773, flushPickups :775-792.  Worlds with nothing pending (wflush) return at once. */
 static BT_HD void t_flush_serial(const DevWorld &W, i32 g, LocalStats &st) {
 	if (g >= W.n_worlds) return;
 	W.flip[g] ^= 1;
