@@ -142,6 +142,10 @@ def run_cuda(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    # a throw-away small world first: pays CUDA's lazy module loading outside every measured phase
+    _warm = bittoss_b200.World(bittoss_b200.synth_boxstack(4096, 4, 1, 64, 60), device=local_rank)
+    _warm.tick(3)
+    _warm.close()
     # one independent world per GPU (a single world does not shard)
     wa = bittoss_b200.synth_boxstack(args.entities, 4, 777 + rank, 64, 60)
     n = wa.n
