@@ -90,12 +90,15 @@ def test_cuda_batched_arena_worlds_teacher_forced(ref_lib, bt):
     R = ref_lib
     # BT_TF_WORLDS / BT_TF_TICKS: one-off larger runs (profiles/README.md), the suite keeps it short
     n_worlds, ticks = int(os.environ.get("BT_TF_WORLDS", 192)), int(os.environ.get("BT_TF_TICKS", 120))
+    level = os.environ.get("BT_TF_LEVEL", "arena")   # one-off runs on other levels: BT_TF_LEVEL=lobby BT_TF_PLAYERS=0,0,0,0
+    players = tuple(int(x) for x in os.environ.get("BT_TF_PLAYERS", "1,2").split(",") if x != "")
     ids = []
     for g in range(n_worlds):
         ids.append(R.new_world())
-        R.load_sav("arena.sav", players=(1, 2), rand_seed=12345 + g)
-        R.set_options(0, 0x9e3779b9 * (g + 1) & 0xffffffff)
-    w = bt.World(None, max_ents=n_worlds * 256, max_sliders=n_worlds * 1024, max_wires=n_worlds * 256,
+        R.load_sav(level + ".sav", players=players, rand_seed=12345 + g)
+        R.set_options(1 if level == "spacetrash" else 0, 0x9e3779b9 * (g + 1) & 0xffffffff)
+    per = 256 if level == "arena" else 1024   # entity slots per world (players, bullets, debris appear)
+    w = bt.World(None, max_ents=n_worlds * per, max_sliders=n_worlds * per * 4, max_wires=n_worlds * per,
                  max_worlds=n_worlds)
     ok = skipped = 0
     tie_mismatch, tie_ticks = [], 0
@@ -144,9 +147,9 @@ def test_cuda_batched_arena_worlds_teacher_forced(ref_lib, bt):
         if k not in undefined:   # their heap is no longer trustworthy: leak them rather than walk it
             R.free_world(g)
     w.close()
-    print("batched arena: %d worlds x %d ticks: %d world-ticks bit-exact, %d worlds left the defined behaviour of "
+    print("batched %s: %d worlds x %d ticks: %d world-ticks bit-exact, %d worlds left the defined behaviour of "
           "the reference (pickup by an entity that died in the same iteration) and were dropped from there on: %s"
-          % (n_worlds, ticks, ok, len(undefined), sorted(undefined)))
+          % (level, n_worlds, ticks, ok, len(undefined), sorted(undefined)))
     print("  full collisionBetter ties were resolved in %d world-ticks; in %d of them the reference's list order picked "
           "the other candidate AND it mattered: %s" % (tie_ticks, len(tie_mismatch), tie_mismatch))
     if n_worlds <= 192:
