@@ -74,6 +74,7 @@ struct bt_world {
 	bool tree_valid, deltas_pending;
 	std::unordered_map<u64, i32> uid_map; /* (world << 32 | uid) -> slot, built on the first bt_world_apply_requests */
 	bool uid_map_valid;
+	bool ctr_fresh; /* h_flag mirrors the device counters (nothing that can change CT_DEAD_N ran since the last fetch) */
 	bool any_ticks, any_rand; /* some entity has a tick handler / a TICK_RAND */
 	int bad_tick;             /* first tick handler id without a device implementation, 0 = none */
 	int device_ticks;         /* option: bt_world_tick runs the tick handlers itself when it can */
@@ -193,7 +194,7 @@ int bt_world_create(bt_world **out, int device, int32_t max_ents, int32_t max_sl
 	w->device = device;
 	w->cap_ents = max_ents; w->cap_sliders = max_sliders; w->cap_wires = max_wires; w->cap_worlds = max_worlds;
 	w->tree_valid = false; w->deltas_pending = true; w->ticks_since_build = 0; w->full_flush_left = 2; w->ctrls_fused = false;
-	w->rebuild_every = 16; w->max_iterations = 100000; w->pair_cache = 1; w->pair_rebuilds = 0; w->pair_overflows = 0; w->seen_pair_builds = 0; w->seen_pair_patches = 0; w->pair_builds_at_tree = 0; w->profiling = false; w->ray_valid = false; w->uid_map_valid = false; w->d_reqs = NULL; w->d_req_starts = NULL; w->reqs_cap = 0; w->any_ticks = w->any_rand = false; w->bad_tick = 0; w->device_ticks = 1;
+	w->rebuild_every = 16; w->max_iterations = 100000; w->pair_cache = 1; w->pair_rebuilds = 0; w->pair_overflows = 0; w->seen_pair_builds = 0; w->seen_pair_patches = 0; w->pair_builds_at_tree = 0; w->profiling = false; w->ray_valid = false; w->uid_map_valid = false; w->ctr_fresh = false; w->d_reqs = NULL; w->d_req_starts = NULL; w->reqs_cap = 0; w->any_ticks = w->any_rand = false; w->bad_tick = 0; w->device_ticks = 1;
 	w->h_flag = NULL; w->ev0 = w->ev1 = NULL; w->stream = NULL;
 	*out = w;
 #define TRY(x) do { int _r = (x); if (_r) { bt_world_destroy(w); *out = NULL; return _r; } } while (0)
@@ -425,7 +426,7 @@ int bt_world_upload(bt_world *w, const bt_world_desc *d) {
 	for (int g = 0; g < nw; g++) w->any_rules = w->any_rules || (d->w_gamerules[g] & (1 | 2 | 16 | 32));
 	w->deltas_pending = deltas;
 	w->full_flush_left = 2; /* both dead_max slots of the upload get looked at */
-	w->uid_map_valid = false;
+	w->uid_map_valid = false; w->ctr_fresh = false;
 	w->any_ticks = any_ticks; w->any_rand = any_rand; w->bad_tick = bad_tick;
 	w->ticks_since_build = 0;
 	w->stats.live_ents = n;
@@ -511,6 +512,7 @@ static int flush1(bt_world *w, bool hint) {
 		return 0;
 	}
 	if (w->full_flush_left > 0) w->full_flush_left--;
+	w->ctr_fresh = false;
 	CK(cudaMemsetAsync(&W.ctr[CT_FLUSH_HINT], 0, sizeof(u32), w->stream));
 	LAUNCH(w, PK_FLUSH, k_flush_scan, nblk(W.n), BT_BLOCK, W);
 	LAUNCH(w, PK_FLUSH, k_flush_serial, nblk(W.n_worlds), BT_BLOCK, W);
@@ -648,13 +650,18 @@ static int do_physics(bt_world *w, bool gravity) {
 	/* invokeOnCrush (ent.cpp:907): crush handlers are host-side events (dead list) */
 	/* h_flag holds the counters fetched after the last k_narrow, i.e. after every push */
 	W.flush_stage = 1; /* deaths flushed from here on are past invokeOnCrush (ent.cpp:907-909) */
+	const bool full_flush = w->full_flush_left > 0 || w->h_flag[CT_FLUSH_HINT] != 0;
 	int r = flush1(w, w->h_flag[CT_FLUSH_HINT] != 0);
 	W.flush_stage = 0;
 	if (r) return r;
 	/* a flush1 that runs k_flush_serial can itself kill (dead_max) and so leave wires to clean
-	 * up: keep the next flush1 full in that case */
-	r = fetch_ctr(w);
-	if (r) return r;
+	 * up: keep the next flush1 full in that case.  A flush1 that only toggled the flip-flop
+	 * changed no counter: the copy fetched after the last iteration is still exact, and the host
+	 * round trip (the GPU idles through it) is skipped -- the steady state of a world at rest. */
+	if (full_flush) {
+		r = fetch_ctr(w);
+		if (r) return r;
+	}
 	if (w->h_flag[CT_FLUSH_HINT] && w->full_flush_left < 1) w->full_flush_left = 1;
 	if (w->h_flag[CT_ANY_DELTA]) {
 		/* flush2 (ent.cpp:910): a pickup with HOLD_FREEZE left a d_vel behind (ent.cpp:176-181) */
@@ -667,6 +674,7 @@ static int do_physics(bt_world *w, bool gravity) {
 		CK(cudaMemsetAsync(&W.ctr[CT_NEED_REBUILD], 0, sizeof(u32), w->stream));
 	}
 	w->ray_valid = false;
+	w->ctr_fresh = true;
 	return 0;
 }
 
@@ -681,6 +689,7 @@ int bt_world_step(bt_world *w, uint32_t phases) {
 		if (w->full_flush_left < 1) w->full_flush_left = 1;
 	}
 	/* flushCtrls rides in k_begin_fused when this step also integrates on the fast path */
+	if (phases & ~BT_PHASE_FINISH) w->ctr_fresh = false; /* until doPhysics refreshes it */
 	if ((phases & BT_PHASE_TICKS) && w->bad_tick && !W.lenient) {
 		snprintf(g_err, sizeof g_err, "BT_PHASE_TICKS: tick handler id %d has no device implementation", w->bad_tick);
 		return BT_ERR_UNSUPPORTED;
@@ -708,11 +717,16 @@ int bt_world_step(bt_world *w, uint32_t phases) {
 	}
 	if (phases & BT_PHASE_FINISH) {
 		/* clearDeads (ent.cpp:471-481): slots of dead entities stay retired */
-		int r = fetch_ctr(w);
-		if (r) return r;
+		if (!w->ctr_fresh) { /* doPhysics of this same step leaves an exact host copy behind: no second round trip */
+			int r = fetch_ctr(w);
+			if (r) return r;
+		}
 		w->stats.live_ents -= (i64)w->h_flag[CT_DEAD_N];
-		if (w->h_flag[CT_DEAD_N]) w->ranks_valid = false;
-		CK(cudaMemsetAsync(&W.ctr[CT_DEAD_N], 0, sizeof(u32), w->stream));
+		if (w->h_flag[CT_DEAD_N]) {
+			w->ranks_valid = false;
+			CK(cudaMemsetAsync(&W.ctr[CT_DEAD_N], 0, sizeof(u32), w->stream));
+			w->h_flag[CT_DEAD_N] = 0;
+		}
 		w->stats.entity_ticks += w->stats.live_ents;
 	}
 	return BT_OK;
@@ -993,7 +1007,7 @@ int bt_world_assign(bt_world *dst, bt_world *src) {
 	rebase(&dst->ray, sizeof(dst->ray), src, dst);
 	dst->tree_valid = src->tree_valid; dst->deltas_pending = src->deltas_pending; dst->any_rules = src->any_rules;
 	dst->full_flush_left = src->full_flush_left; dst->ctrls_fused = src->ctrls_fused;
-	dst->uid_map_valid = false;
+	dst->uid_map_valid = false; dst->ctr_fresh = false;
 	dst->any_ticks = src->any_ticks; dst->any_rand = src->any_rand; dst->bad_tick = src->bad_tick; dst->device_ticks = src->device_ticks;
 	dst->ticks_since_build = src->ticks_since_build; dst->rebuild_every = src->rebuild_every;
 	dst->max_iterations = src->max_iterations; dst->pair_cache = src->pair_cache;
