@@ -31,6 +31,15 @@ static __device__ __forceinline__ void stats_flush(const DevWorld &W, const Loca
 	stat_add(W, SK_FUMBLE, st.fumble);
 }
 
+/* Programmatic dependent launch: every kernel of the tick is launched with
+ * cudaLaunchAttributeProgrammaticStreamSerialization.  First thing, a kernel lets ITS successor be
+ * scheduled (its blocks fill SMs as ours drain, hiding launch latency and part of the tail), then
+ * waits until its own predecessor has completed and its memory is visible.  Without the launch
+ * attribute both instructions are no-ops. */
+#define PDL_ENTRY() asm volatile("griddepcontrol.launch_dependents;\ngriddepcontrol.wait;" ::: "memory")
+/* the two long multi-wave kernels (k_narrow, k_push) only wait: their successor is released when they
+ * complete, so that no waiting block holds registers while their last waves run */
+#define PDL_WAIT() asm volatile("griddepcontrol.wait;" ::: "memory")
 #define TID ((i32)(blockIdx.x * blockDim.x + threadIdx.x))
 /* the proposal stamp of iteration `id` lives in one of two slots, by parity */
 #define ANY_SLOT(id) (((id) & 1) ? CT_ANY_ODD : CT_ANY_PROPOSAL)
@@ -41,32 +50,32 @@ static __device__ __forceinline__ void stats_flush(const DevWorld &W, const Loca
 #define GS_FOR(i, n) for (i32 i = TID; i < (n); i += (i32)(gridDim.x * blockDim.x))
 #define GS_BLOCK 256
 
-__global__ void __launch_bounds__(BT_BLOCK) k_pre(DevWorld W, u32 phases) { t_pre(W, TID, phases); }
-__global__ void __launch_bounds__(BT_BLOCK) k_flush_scan(DevWorld W) { t_flush_scan(W, TID); }
-__global__ void __launch_bounds__(BT_BLOCK) k_flush_serial(DevWorld W) {
+__global__ void __launch_bounds__(BT_BLOCK) k_pre(DevWorld W, u32 phases) { PDL_ENTRY(); t_pre(W, TID, phases); }
+__global__ void __launch_bounds__(BT_BLOCK) k_flush_scan(DevWorld W) { PDL_ENTRY(); t_flush_scan(W, TID); }
+__global__ void __launch_bounds__(BT_BLOCK) k_flush_serial(DevWorld W) { PDL_ENTRY();
 	LocalStats st = {0, 0, 0, 0, 0};
 	t_flush_serial(W, TID, st);
 	stats_flush(W, st);
 }
-__global__ void __launch_bounds__(BT_BLOCK) k_flush_misc(DevWorld W) { t_flush_misc(W, TID); }
-__global__ void __launch_bounds__(BT_BLOCK) k_tick(DevWorld W) { t_tick(W, TID); }
-__global__ void __launch_bounds__(BT_BLOCK) k_tick_serial(DevWorld W) { t_tick_serial(W, TID); }
+__global__ void __launch_bounds__(BT_BLOCK) k_flush_misc(DevWorld W) { PDL_ENTRY(); t_flush_misc(W, TID); }
+__global__ void __launch_bounds__(BT_BLOCK) k_tick(DevWorld W) { PDL_ENTRY(); t_tick(W, TID); }
+__global__ void __launch_bounds__(BT_BLOCK) k_tick_serial(DevWorld W) { PDL_ENTRY(); t_tick_serial(W, TID); }
 /* requests arrive grouped by world (stable), one thread per world applies its run in order */
-__global__ void __launch_bounds__(BT_BLOCK) k_requests(DevWorld W, const BtReq *q, const i32 *starts, i32 n_groups) {
+__global__ void __launch_bounds__(BT_BLOCK) k_requests(DevWorld W, const BtReq *q, const i32 *starts, i32 n_groups) { PDL_ENTRY();
 	i32 g = TID;
 	if (g >= n_groups) return;
 	for (i32 i = starts[g]; i < starts[g + 1]; i++) t_request(W, q[i]);
 }
-__global__ void __launch_bounds__(BT_BLOCK) k_gravity(DevWorld W) { t_gravity(W, TID); }
-__global__ void __launch_bounds__(BT_BLOCK) k_world_rules(DevWorld W) { t_world_rules(W, TID); }
-__global__ void __launch_bounds__(BT_BLOCK) k_flush2_apply(DevWorld W) { t_flush2_apply(W, TID); }
-__global__ void __launch_bounds__(BT_BLOCK) k_zero_deltas(DevWorld W) { t_zero_deltas(W, TID); }
-__global__ void __launch_bounds__(BT_BLOCK) k_integrate(DevWorld W) { t_integrate(W, TID); }
+__global__ void __launch_bounds__(BT_BLOCK) k_gravity(DevWorld W) { PDL_ENTRY(); t_gravity(W, TID); }
+__global__ void __launch_bounds__(BT_BLOCK) k_world_rules(DevWorld W) { PDL_ENTRY(); t_world_rules(W, TID); }
+__global__ void __launch_bounds__(BT_BLOCK) k_flush2_apply(DevWorld W) { PDL_ENTRY(); t_flush2_apply(W, TID); }
+__global__ void __launch_bounds__(BT_BLOCK) k_zero_deltas(DevWorld W) { PDL_ENTRY(); t_zero_deltas(W, TID); }
+__global__ void __launch_bounds__(BT_BLOCK) k_integrate(DevWorld W) { PDL_ENTRY(); t_integrate(W, TID); }
 
-__global__ void __launch_bounds__(BT_BLOCK) k_begin_fused(DevWorld W, int gravity, int ctrls) { t_begin_fused(W, TID, gravity, ctrls); }
-__global__ void __launch_bounds__(BT_BLOCK) k_flip_only(DevWorld W) { t_flip_only(W, TID); }
+__global__ void __launch_bounds__(BT_BLOCK) k_begin_fused(DevWorld W, int gravity, int ctrls) { PDL_ENTRY(); t_begin_fused(W, TID, gravity, ctrls); }
+__global__ void __launch_bounds__(BT_BLOCK) k_flip_only(DevWorld W) { PDL_ENTRY(); t_flip_only(W, TID); }
 
-__global__ void __launch_bounds__(BT_BLOCK) k_bounds(DevWorld W) {
+__global__ void __launch_bounds__(BT_BLOCK) k_bounds(DevWorld W) { PDL_ENTRY();
 	/* warp-reduce before the atomics: 6 atomics per warp instead of per thread */
 	i32 e = TID;
 	int valid = e < W.n && bt_is_leaf_ent(W, e);
@@ -84,9 +93,9 @@ __global__ void __launch_bounds__(BT_BLOCK) k_bounds(DevWorld W) {
 		atomicAdd(&W.ctr[CT_N_LEAVES], cnt);
 	}
 }
-__global__ void __launch_bounds__(BT_BLOCK) k_morton(DevWorld W) { t_morton(W, TID); }
-__global__ void __launch_bounds__(BT_BLOCK) k_lbvh(DevWorld W) { t_lbvh_node(W, TID); }
-__global__ void __launch_bounds__(GS_BLOCK) k_refit(DevWorld W, int cond) {
+__global__ void __launch_bounds__(BT_BLOCK) k_morton(DevWorld W) { PDL_ENTRY(); t_morton(W, TID); }
+__global__ void __launch_bounds__(BT_BLOCK) k_lbvh(DevWorld W) { PDL_ENTRY(); t_lbvh_node(W, TID); }
+__global__ void __launch_bounds__(GS_BLOCK) k_refit(DevWorld W, int cond) { PDL_ENTRY();
 	if (cond && !W.ctr[CT_CACHE_INVALID]) return;
 	if (cond && bt_patch_mode(W)) {
 		GS_FOR(t, (i32)W.ctr[CT_DIRTY_N]) t_refit_patch(W, t);
@@ -97,7 +106,7 @@ __global__ void __launch_bounds__(GS_BLOCK) k_refit(DevWorld W, int cond) {
 
 /* traversal stacks live in shared memory, interleaved so that lane i's slot k is at
  * word k*128+i: the 32 lanes of a warp hit 32 different banks (no conflicts). */
-__global__ void __launch_bounds__(BT_BLOCK) k_collide(DevWorld W) {
+__global__ void __launch_bounds__(BT_BLOCK) k_collide(DevWorld W) { PDL_ENTRY();
 	__shared__ i32 stacks[BT_STACK * BT_BLOCK];
 	LocalStats st = {0, 0, 0, 0, 0};
 	u32 any = 0;
@@ -151,7 +160,7 @@ struct PairEmit {
 	}
 };
 
-__global__ void __launch_bounds__(BT_BLOCK) k_pairs(DevWorld W) {
+__global__ void __launch_bounds__(BT_BLOCK) k_pairs(DevWorld W) { PDL_ENTRY();
 	__shared__ i32 stacks[BT_STACK * BT_BLOCK];
 	__shared__ u64 pbuf[PAIR_BUF * BT_BLOCK];
 	if (!W.ctr[CT_CACHE_INVALID]) return; /* uniform: the cached pairs are still a superset */
@@ -189,7 +198,7 @@ static __device__ __forceinline__ void queue_push(u32 *q, u32 *count, int pred, 
 /* spec = 1: an iteration enqueued ahead of the host's knowledge (run-ahead).  It proceeds only
  * if the previous iteration proposed something and no push has invalidated the pair cache;
  * otherwise it records its id in CT_STOP and it and everything enqueued behind it stand down. */
-__global__ void __launch_bounds__(256) k_narrow(DevWorld W, int spec) {
+__global__ void __launch_bounds__(256) k_narrow(DevWorld W, int spec) { PDL_WAIT();
 	LocalStats st = {0, 0, 0, 0, 0};
 	u32 any = 0;
 	if (spec) {
@@ -220,12 +229,12 @@ __global__ void __launch_bounds__(256) k_narrow(DevWorld W, int spec) {
  * host knows whether anything was proposed (one host sync per iteration instead of two).  With
  * no proposal they are no-ops by construction; if the pair buffer overflowed they stand down
  * (CT_PAIR_OVERFLOW) and the host redoes the iteration through k_collide. */
-__global__ void __launch_bounds__(BT_BLOCK) k_decide(DevWorld W) {
+__global__ void __launch_bounds__(BT_BLOCK) k_decide(DevWorld W) { PDL_ENTRY();
 	if (W.ctr[CT_PAIR_OVERFLOW] | W.ctr[CT_STOP]) return;
 	t_decide(W, TID);
 }
 /* ready roots (typically 1 entity in 4) are re-packed into full warps before the push */
-__global__ void __launch_bounds__(BT_BLOCK) k_push(DevWorld W) {
+__global__ void __launch_bounds__(BT_BLOCK) k_push(DevWorld W) { PDL_WAIT();
 	__shared__ u32 queue[BT_BLOCK];
 	__shared__ u32 qn;
 	LocalStats st = {0, 0, 0, 0, 0};
@@ -238,7 +247,7 @@ __global__ void __launch_bounds__(BT_BLOCK) k_push(DevWorld W) {
 	if (threadIdx.x < qn) t_push(W, (i32)queue[threadIdx.x], st);
 	stats_flush(W, st);
 }
-__global__ void k_push_serial(DevWorld W) {
+__global__ void k_push_serial(DevWorld W) { PDL_ENTRY();
 	if (threadIdx.x != 0 || blockIdx.x != 0) return;
 	if (W.ctr[CT_SERIAL_N] == 0 || W.ctr[CT_PAIR_OVERFLOW] || W.ctr[CT_STOP]) return;
 	LocalStats st = {0, 0, 0, 0, 0};
@@ -246,14 +255,14 @@ __global__ void k_push_serial(DevWorld W) {
 	u64 *s = (u64 *)&W.ctr[CT_STAT0];
 	s[SK_PUSH] += st.push; s[SK_SERIAL] += st.push; s[SK_CRUSH] += st.crush; s[SK_FUMBLE] += st.fumble;
 }
-__global__ void __launch_bounds__(BT_BLOCK) k_post(DevWorld W) {
+__global__ void __launch_bounds__(BT_BLOCK) k_post(DevWorld W) { PDL_ENTRY();
 	if (W.ctr[CT_PAIR_OVERFLOW] | W.ctr[CT_STOP]) return;
 	t_post(W, TID);
 }
 
 /* host exchange: staging buffers hold [3*n_live] ints in live oldest-first order; while no
  * entity has died, live rank == slot (the common case, checked by the host) */
-__global__ void __launch_bounds__(BT_BLOCK) k_add_deltas(DevWorld W, const i32 *dc, const i32 *dv, const i32 *slot2rank) {
+__global__ void __launch_bounds__(BT_BLOCK) k_add_deltas(DevWorld W, const i32 *dc, const i32 *dv, const i32 *slot2rank) { PDL_ENTRY();
 	i32 e = TID;
 	if (e >= W.n || !W.inList[e]) return;
 	i32 r = slot2rank ? slot2rank[e] : e;
@@ -263,7 +272,7 @@ __global__ void __launch_bounds__(BT_BLOCK) k_add_deltas(DevWorld W, const i32 *
 	W.d_center[e] = a;
 	W.d_vel[e] = b;
 }
-__global__ void __launch_bounds__(BT_BLOCK) k_pack_state(DevWorld W, i32 *oc, i32 *ov, const i32 *slot2rank) {
+__global__ void __launch_bounds__(BT_BLOCK) k_pack_state(DevWorld W, i32 *oc, i32 *ov, const i32 *slot2rank) { PDL_ENTRY();
 	i32 e = TID;
 	if (e >= W.n || !W.inList[e]) return;
 	i32 r = slot2rank ? slot2rank[e] : e;
@@ -273,7 +282,7 @@ __global__ void __launch_bounds__(BT_BLOCK) k_pack_state(DevWorld W, i32 *oc, i3
 }
 
 /* per-world commutative hash: warp-level pre-reduction when the whole warp is one world */
-__global__ void __launch_bounds__(BT_BLOCK) k_hash(DevWorld W, u64 *sum, u32 *cnt) {
+__global__ void __launch_bounds__(BT_BLOCK) k_hash(DevWorld W, u64 *sum, u32 *cnt) { PDL_ENTRY();
 	i32 e = TID;
 	int live = e < W.n && W.inList[e];
 	u64 h = live ? bt_ent_hash(W, e) : 0;
@@ -303,7 +312,7 @@ __global__ void __launch_bounds__(BT_BLOCK) k_hash(DevWorld W, u64 *sum, u32 *cn
 #define SORT_ITEMS 16
 #define SORT_TILE (SORT_THREADS * SORT_ITEMS)
 
-__global__ void __launch_bounds__(SORT_THREADS) k_sort_hist(const u64 *keys, i32 n, int shift, u32 *hist, int nb) {
+__global__ void __launch_bounds__(SORT_THREADS) k_sort_hist(const u64 *keys, i32 n, int shift, u32 *hist, int nb) { PDL_ENTRY();
 	__shared__ u32 h[256];
 	h[threadIdx.x] = 0;
 	__syncthreads();
@@ -318,7 +327,7 @@ __global__ void __launch_bounds__(SORT_THREADS) k_sort_hist(const u64 *keys, i32
 }
 
 /* exclusive scan of `len` counters by one block of 1024 threads */
-__global__ void __launch_bounds__(1024) k_sort_scan(u32 *hist, int len) {
+__global__ void __launch_bounds__(1024) k_sort_scan(u32 *hist, int len) { PDL_ENTRY();
 	__shared__ u32 warpTot[32];
 	__shared__ u32 carry;
 	if (threadIdx.x == 0) carry = 0;
@@ -354,7 +363,7 @@ __global__ void __launch_bounds__(1024) k_sort_scan(u32 *hist, int len) {
 }
 
 __global__ void __launch_bounds__(SORT_THREADS) k_sort_scatter(const u64 *keys, const i32 *vals, u64 *okeys, i32 *ovals,
-                                                             i32 n, int shift, const u32 *hist, int nb) {
+                                                             i32 n, int shift, const u32 *hist, int nb) { PDL_ENTRY();
 	__shared__ u32 warpOff[SORT_THREADS / 32][256];
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 	for (int d = lane; d < 256; d += 32) warpOff[warp][d] = 0;

@@ -138,7 +138,7 @@ static BT_HD i32 t_raycast(const DevWorld &W, i32 p, const i32 look_in[3], i32 *
 /* origin/winner are LIVE RANKS (oldest-first order of bt_world_download); rank2slot /
  * slot2rank translate to device slots. */
 __global__ void __launch_bounds__(128) k_raycast(DevWorld W, const i32 *origin, const i32 *look, i32 n_rays,
-                                                  i32 *winner, const i32 *rank2slot, const i32 *slot2rank, i32 n_live) {
+                                                  i32 *winner, const i32 *rank2slot, const i32 *slot2rank, i32 n_live) { PDL_ENTRY();
 	__shared__ i32 stacks[BT_STACK * 128];
 	i32 i = (i32)(blockIdx.x * blockDim.x + threadIdx.x);
 	if (i >= n_rays) return;
@@ -150,7 +150,7 @@ __global__ void __launch_bounds__(128) k_raycast(DevWorld W, const i32 *origin, 
 }
 
 /* exclusive scan of inList -> live rank per slot (single block; raycast setup only) */
-__global__ void __launch_bounds__(1024) k_live_ranks(DevWorld W, i32 *rank2slot, i32 *slot2rank) {
+__global__ void __launch_bounds__(1024) k_live_ranks(DevWorld W, i32 *rank2slot, i32 *slot2rank) { PDL_ENTRY();
 	__shared__ u32 warpTot[32];
 	__shared__ u32 carry;
 	if (threadIdx.x == 0) carry = 0;

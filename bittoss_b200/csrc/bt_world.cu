@@ -74,6 +74,7 @@ struct bt_world {
 	bool tree_valid, deltas_pending;
 	std::unordered_map<u64, i32> uid_map; /* (world << 32 | uid) -> slot, built on the first bt_world_apply_requests */
 	bool uid_map_valid;
+	bool pdl;       /* option "pdl": programmatic dependent launches (default on) */
 	bool ctr_fresh; /* h_flag mirrors the device counters (nothing that can change CT_DEAD_N ran since the last fetch) */
 	bool any_ticks, any_rand; /* some entity has a tick handler / a TICK_RAND */
 	int bad_tick;             /* first tick handler id without a device implementation, 0 = none */
@@ -115,12 +116,28 @@ template <typename T> static int dalloc(bt_world *w, T **p, size_t count) {
 	return 0;
 }
 
+/* every kernel goes through here; pdl: programmatic dependent launch (see PDL_ENTRY in bt_kernels.cuh) */
+template <typename... KArgs, typename... Args>
+static inline void launch_k(bool pdl, void (*kern)(KArgs...), int grid, int block, cudaStream_t s, Args &&...args) {
+	cudaLaunchConfig_t cfg = {};
+	cfg.gridDim = dim3((unsigned)grid);
+	cfg.blockDim = dim3((unsigned)block);
+	cfg.dynamicSmemBytes = 0;
+	cfg.stream = s;
+	cudaLaunchAttribute at[1];
+	at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+	at[0].val.programmaticStreamSerializationAllowed = pdl ? 1 : 0;
+	cfg.attrs = at;
+	cfg.numAttrs = 1;
+	cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
+
 /* launch helper: counts launches and, while profiling, brackets each one with events */
 #define LAUNCH(w, cls, kern, grid, block, ...)                                         \
 	do {                                                                               \
 		if ((grid) > 0) {                                                              \
 			if ((w)->profiling) cudaEventRecord((w)->ev0, (w)->stream);                \
-			kern<<<(grid), (block), 0, (w)->stream>>>(__VA_ARGS__);                    \
+			launch_k((w)->pdl, kern, (grid), (block), (w)->stream, __VA_ARGS__);       \
 			(w)->stats.kernel_launches++;                                              \
 			(w)->prof_launches[cls]++;                                                 \
 			if ((w)->profiling) {                                                      \
@@ -194,7 +211,7 @@ int bt_world_create(bt_world **out, int device, int32_t max_ents, int32_t max_sl
 	w->device = device;
 	w->cap_ents = max_ents; w->cap_sliders = max_sliders; w->cap_wires = max_wires; w->cap_worlds = max_worlds;
 	w->tree_valid = false; w->deltas_pending = true; w->ticks_since_build = 0; w->full_flush_left = 2; w->ctrls_fused = false;
-	w->rebuild_every = 16; w->max_iterations = 100000; w->pair_cache = 1; w->pair_rebuilds = 0; w->pair_overflows = 0; w->seen_pair_builds = 0; w->seen_pair_patches = 0; w->pair_builds_at_tree = 0; w->profiling = false; w->ray_valid = false; w->uid_map_valid = false; w->ctr_fresh = false; w->d_reqs = NULL; w->d_req_starts = NULL; w->reqs_cap = 0; w->any_ticks = w->any_rand = false; w->bad_tick = 0; w->device_ticks = 1;
+	w->rebuild_every = 16; w->max_iterations = 100000; w->pair_cache = 1; w->pair_rebuilds = 0; w->pair_overflows = 0; w->seen_pair_builds = 0; w->seen_pair_patches = 0; w->pair_builds_at_tree = 0; w->profiling = false; w->ray_valid = false; w->uid_map_valid = false; w->ctr_fresh = false; w->pdl = getenv("BT_NO_PDL") == NULL; w->d_reqs = NULL; w->d_req_starts = NULL; w->reqs_cap = 0; w->any_ticks = w->any_rand = false; w->bad_tick = 0; w->device_ticks = 1;
 	w->h_flag = NULL; w->ev0 = w->ev1 = NULL; w->stream = NULL;
 	*out = w;
 #define TRY(x) do { int _r = (x); if (_r) { bt_world_destroy(w); *out = NULL; return _r; } } while (0)
@@ -263,6 +280,7 @@ int bt_world_set_option(bt_world *w, const char *name, int64_t value) {
 	if (!strcmp(name, "allow_unsupported")) { w->W.lenient = value != 0; return BT_OK; }
 	if (!strcmp(name, "pair_cache")) { w->pair_cache = value != 0; return BT_OK; }
 	if (!strcmp(name, "cache_horizon")) { w->W.horizon = value < 0 ? 0 : (value > 64 ? 64 : (i32)value); return BT_OK; }
+	if (!strcmp(name, "pdl")) { w->pdl = value != 0; return BT_OK; }
 	if (!strcmp(name, "device_ticks")) { w->device_ticks = value != 0; return BT_OK; }
 	if (!strcmp(name, "pair_patch")) { w->W.patch = value != 0; return BT_OK; }
 	if (!strcmp(name, "patch_shift")) { w->W.patch_shift = value < 0 ? 0 : (value > 20 ? 20 : (i32)value); return BT_OK; }
@@ -1007,7 +1025,7 @@ int bt_world_assign(bt_world *dst, bt_world *src) {
 	rebase(&dst->ray, sizeof(dst->ray), src, dst);
 	dst->tree_valid = src->tree_valid; dst->deltas_pending = src->deltas_pending; dst->any_rules = src->any_rules;
 	dst->full_flush_left = src->full_flush_left; dst->ctrls_fused = src->ctrls_fused;
-	dst->uid_map_valid = false; dst->ctr_fresh = false;
+	dst->uid_map_valid = false; dst->ctr_fresh = false; dst->pdl = src->pdl;
 	dst->any_ticks = src->any_ticks; dst->any_rand = src->any_rand; dst->bad_tick = src->bad_tick; dst->device_ticks = src->device_ticks;
 	dst->ticks_since_build = src->ticks_since_build; dst->rebuild_every = src->rebuild_every;
 	dst->max_iterations = src->max_iterations; dst->pair_cache = src->pair_cache;
