@@ -256,10 +256,16 @@ int bt_world_drain_events(bt_world *w, bt_event *out, int32_t max, int32_t *n);
 int bt_world_unsupported(bt_world *w, uint32_t *per_world);
 int bt_world_profile_enable(bt_world *w, int on);
 int bt_world_profile_read(bt_world *w, bt_profile *out, int reset);
-/* Knobs (integers): "rebuild_every" ticks between full LBVH rebuilds; "pair_cache" 0/1;
- * "cache_margin"; "allow_unsupported" 1 = bt_world_upload accepts handler IDs without a device
- * implementation, treats them as NIL and counts every would-be invocation in
- * bt_tick_stats.unsupported_events (used to measure handler coverage on real levels). */
+/* Knobs (integers).  None of them changes results, only how the work is scheduled:
+ * "rebuild_every" ticks between full LBVH rebuilds (16); "pair_cache" 0/1 cached candidate pairs;
+ * "cache_margin" inflation of the cached boxes (32); "cache_horizon" ticks of motion the cached box
+ * is stretched ahead by (0); "pair_patch" 0/1 incremental pair-list patches; "patch_shift" patch
+ * while dirty << shift <= leaves (4); "run_ahead" 0/1 speculative iterations; "max_iterations";
+ * "device_ticks" 0/1 bt_world_tick runs the tick handlers itself when all have device bodies;
+ * "pdl" 0/1 programmatic dependent launches.
+ * "allow_unsupported" 1 = bt_world_upload accepts handler IDs without a device implementation,
+ * treats them as NIL and counts every would-be invocation in bt_tick_stats.unsupported_events
+ * (used to measure handler coverage on real levels). */
 int bt_world_set_option(bt_world *w, const char *name, int64_t value);
 
 /* ---- raycast: replaces selectCast(gs, parent, look) (raycast.h:1, raycast.cpp:16-57),
