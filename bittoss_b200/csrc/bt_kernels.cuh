@@ -97,6 +97,10 @@ __global__ void __launch_bounds__(BT_BLOCK) k_morton(DevWorld W) { PDL_ENTRY(); 
 __global__ void __launch_bounds__(BT_BLOCK) k_lbvh(DevWorld W) { PDL_ENTRY(); t_lbvh_node(W, TID); }
 __global__ void __launch_bounds__(GS_BLOCK) k_refit(DevWorld W, int cond) { PDL_ENTRY();
 	if (cond && !W.ctr[CT_CACHE_INVALID]) return;
+	if (cond && W.small_mode) { /* no tree to refit: only the pair list is reset, k_pairs_small does the rest */
+		if (TID == 0) { W.ctr[CT_PAIR_N] = 0; atomicAdd(&W.ctr[CT_PAIR_BUILDS], 1u); }
+		return;
+	}
 	if (cond && bt_patch_mode(W)) {
 		GS_FOR(t, (i32)W.ctr[CT_DIRTY_N]) t_refit_patch(W, t);
 		return;
@@ -175,6 +179,41 @@ __global__ void __launch_bounds__(BT_BLOCK) k_pairs(DevWorld W) { PDL_ENTRY();
 	i32 chunk = (W.n_leaves + (i32)gridDim.x - 1) / (i32)gridDim.x;
 	i32 t0 = (i32)blockIdx.x * chunk, t1 = t0 + chunk < W.n_leaves ? t0 + chunk : W.n_leaves;
 	for (i32 t = t0 + (i32)threadIdx.x; t < t1; t += BT_BLOCK) t_pairs(W, t, stacks + threadIdx.x, BT_BLOCK, emit);
+	emit.finish();
+}
+
+/* small-world mode: one block per world, boxes in shared memory, all pairs (see t_pairs_small_world) */
+__global__ void __launch_bounds__(BT_SMALL_WORLD) k_pairs_small(DevWorld W) { PDL_ENTRY();
+	__shared__ int4 blo[BT_SMALL_WORLD], bhi[BT_SMALL_WORLD];
+	__shared__ u64 pbuf[PAIR_BUF * BT_SMALL_WORLD];
+	if (!W.ctr[CT_CACHE_INVALID]) return;
+	const int g = (int)blockIdx.x;
+	const i32 b0 = W.wbegin[g], cnt = W.wend[g] - b0;
+	const int i = (int)threadIdx.x;
+	int leaf = 0;
+	Box6 q;
+	q.lo = make_int4(INT32_MAX, INT32_MAX, INT32_MAX, 0); /* empty: touches nothing */
+	q.hi = make_int4(INT32_MIN, INT32_MIN, INT32_MIN, 0);
+	if (i < cnt && bt_is_leaf_ent(W, b0 + i)) {
+		leaf = 1;
+		q = bt_inflated_box(W, b0 + i);
+		W.ibox[b0 + i] = q;
+	}
+	blo[i] = q.lo; bhi[i] = q.hi;
+	__syncthreads();
+	PairEmit emit(W.pairs, &W.ctr[CT_PAIR_N], W.pair_cap, pbuf + threadIdx.x);
+	if (leaf) {
+		/* balanced triangle: entity i looks at the next (cnt-1)/2 entities cyclically, and at the
+		 * one opposite when cnt is even and i is in the lower half: every unordered pair once */
+		const int half = (cnt - 1) / 2;
+		for (int k = 1; k <= half + ((cnt & 1) == 0 && i < cnt / 2 ? 1 : 0); k++) {
+			int j = i + k;
+			if (j >= cnt) j -= cnt;
+			Box6 o;
+			o.lo = blo[j]; o.hi = bhi[j];
+			if (bt_box_touch(q, o)) emit(b0 + (i < j ? i : j), b0 + (i < j ? j : i));
+		}
+	}
 	emit.finish();
 }
 

@@ -864,7 +864,7 @@ static BT_HD int bt_max(int a, int b) { return a > b ? a : b; }
  * k_narrow that consumes the flags: none of the three writes a word this reads before the
  * last of them has read it. */
 static BT_HD int bt_patch_mode(const DevWorld &W) {
-	return W.patch && !W.ray_mode && !W.ctr[CT_CACHE_FULL] && ((u64)W.ctr[CT_DIRTY_N] << W.patch_shift) <= (u64)(u32)W.n_leaves;
+	return W.patch && !W.small_mode && !W.ray_mode && !W.ctr[CT_CACHE_FULL] && ((u64)W.ctr[CT_DIRTY_N] << W.patch_shift) <= (u64)(u32)W.n_leaves;
 }
 
 static BT_HD Box6 bt_inflated_box(const DevWorld &W, i32 e) {
@@ -1131,6 +1131,24 @@ template <class Emit> static BT_HD void t_pairs_patch(const DevWorld &W, int t, 
 			if (sp == 0) break;
 			node = stack[(--sp) * stride];
 		}
+	}
+}
+
+/* Small-world mode (every world <= BT_SMALL_WORLD entities, the batched-worlds case): the candidate
+ * pairs of a world are all pairs of its leaf entities whose inflated boxes touch -- the same set the
+ * tree walk yields -- found by brute force over the world's contiguous slot range, no sort, no
+ * tree, no refit.  This is the one-thread restatement (emulator); k_pairs_small does it with one
+ * block per world out of shared memory. */
+template <class Emit> static BT_HD void t_pairs_small_world(const DevWorld &W, int g, Emit &emit) {
+	if (g >= W.n_worlds || !W.ctr[CT_CACHE_INVALID]) return;
+	i32 b0 = W.wbegin[g], b1 = W.wend[g];
+	for (i32 e = b0; e < b1; e++)
+		if (bt_is_leaf_ent(W, e)) W.ibox[e] = bt_inflated_box(W, e);
+	for (i32 a = b0; a < b1; a++) {
+		if (!bt_is_leaf_ent(W, a)) continue;
+		const Box6 qa = W.ibox[a];
+		for (i32 b = a + 1; b < b1; b++)
+			if (bt_is_leaf_ent(W, b) && bt_box_touch(qa, W.ibox[b])) emit(a, b);
 	}
 }
 

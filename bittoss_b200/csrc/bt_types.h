@@ -130,6 +130,7 @@ struct DevWorld {
 	i32 horizon;  /* ticks of undisturbed motion (velocity + gravity) the cached box is stretched ahead by:
 	               * velbox's validity idea (velbox/box.h:32-34), a box in free flight stays covered */
 	i32 patch;    /* incremental pair-list patches allowed (option pair_patch) */
+	i32 small_mode; /* every world holds <= BT_SMALL_WORLD entities: candidate pairs by brute force per world, no tree */
 	i32 patch_shift; /* patch while dirty entities << patch_shift <= leaves, full build beyond */
 
 	i32 *wbegin, *wend, *flip, *gamerules, *rnd; /* per world */
@@ -179,6 +180,8 @@ struct DevWorld {
 };
 
 /* one deferred updater call made by host-side code (bt_world_apply_requests) */
+#define BT_SMALL_WORLD 128
+
 struct BtReq {
 	i32 kind, me, other, a0, a1, a2; /* me / other are entity slots here */
 };

@@ -74,6 +74,7 @@ struct bt_world {
 	bool tree_valid, deltas_pending;
 	std::unordered_map<u64, i32> uid_map; /* (world << 32 | uid) -> slot, built on the first bt_world_apply_requests */
 	bool uid_map_valid;
+	bool small_worlds; /* option "small_worlds": brute-force pair search when every world is small (default on) */
 	bool pdl;       /* option "pdl": programmatic dependent launches (default on) */
 	bool ctr_fresh; /* h_flag mirrors the device counters (nothing that can change CT_DEAD_N ran since the last fetch) */
 	bool any_ticks, any_rand; /* some entity has a tick handler / a TICK_RAND */
@@ -211,7 +212,7 @@ int bt_world_create(bt_world **out, int device, int32_t max_ents, int32_t max_sl
 	w->device = device;
 	w->cap_ents = max_ents; w->cap_sliders = max_sliders; w->cap_wires = max_wires; w->cap_worlds = max_worlds;
 	w->tree_valid = false; w->deltas_pending = true; w->ticks_since_build = 0; w->full_flush_left = 2; w->ctrls_fused = false;
-	w->rebuild_every = 16; w->max_iterations = 100000; w->pair_cache = 1; w->pair_rebuilds = 0; w->pair_overflows = 0; w->seen_pair_builds = 0; w->seen_pair_patches = 0; w->pair_builds_at_tree = 0; w->profiling = false; w->ray_valid = false; w->uid_map_valid = false; w->ctr_fresh = false; w->pdl = getenv("BT_NO_PDL") == NULL; w->d_reqs = NULL; w->d_req_starts = NULL; w->reqs_cap = 0; w->any_ticks = w->any_rand = false; w->bad_tick = 0; w->device_ticks = 1;
+	w->rebuild_every = 16; w->max_iterations = 100000; w->pair_cache = 1; w->pair_rebuilds = 0; w->pair_overflows = 0; w->seen_pair_builds = 0; w->seen_pair_patches = 0; w->pair_builds_at_tree = 0; w->profiling = false; w->ray_valid = false; w->uid_map_valid = false; w->ctr_fresh = false; w->pdl = getenv("BT_NO_PDL") == NULL; w->small_worlds = true; w->d_reqs = NULL; w->d_req_starts = NULL; w->reqs_cap = 0; w->any_ticks = w->any_rand = false; w->bad_tick = 0; w->device_ticks = 1;
 	w->h_flag = NULL; w->ev0 = w->ev1 = NULL; w->stream = NULL;
 	*out = w;
 #define TRY(x) do { int _r = (x); if (_r) { bt_world_destroy(w); *out = NULL; return _r; } } while (0)
@@ -281,6 +282,11 @@ int bt_world_set_option(bt_world *w, const char *name, int64_t value) {
 	if (!strcmp(name, "pair_cache")) { w->pair_cache = value != 0; return BT_OK; }
 	if (!strcmp(name, "cache_horizon")) { w->W.horizon = value < 0 ? 0 : (value > 64 ? 64 : (i32)value); return BT_OK; }
 	if (!strcmp(name, "pdl")) { w->pdl = value != 0; return BT_OK; }
+	if (!strcmp(name, "small_worlds")) { /* takes effect at the next upload */
+		w->small_worlds = value != 0;
+		if (!w->small_worlds && w->W.small_mode) { w->W.small_mode = 0; w->tree_valid = false; }
+		return BT_OK;
+	}
 	if (!strcmp(name, "device_ticks")) { w->device_ticks = value != 0; return BT_OK; }
 	if (!strcmp(name, "pair_patch")) { w->W.patch = value != 0; return BT_OK; }
 	if (!strcmp(name, "patch_shift")) { w->W.patch_shift = value < 0 ? 0 : (value > 20 ? 20 : (i32)value); return BT_OK; }
@@ -445,6 +451,11 @@ int bt_world_upload(bt_world *w, const bt_world_desc *d) {
 	w->deltas_pending = deltas;
 	w->full_flush_left = 2; /* both dead_max slots of the upload get looked at */
 	w->uid_map_valid = false; w->ctr_fresh = false;
+	{
+		i32 biggest = 0;
+		for (int g = 0; g < nw; g++) biggest = std::max(biggest, wend[g] - wbegin[g]);
+		W.small_mode = (w->small_worlds && biggest <= BT_SMALL_WORLD) ? 1 : 0;
+	}
 	w->any_ticks = any_ticks; w->any_rand = any_rand; w->bad_tick = bad_tick;
 	w->ticks_since_build = 0;
 	w->stats.live_ents = n;
@@ -563,8 +574,10 @@ static int do_physics(bt_world *w, bool gravity) {
 	/* leaf set changes (an entity gained a box) force a rebuild; deaths do not */
 	/* ... and an old tree is only rebuilt if pair lists are being rebuilt at all (a world at
 	 * rest keeps its cached pairs for as long as nobody leaves its inflated box) */
-	if (!w->tree_valid || (w->ticks_since_build >= w->rebuild_every &&
-	                       (!w->pair_cache || w->seen_pair_builds + w->seen_pair_patches > w->pair_builds_at_tree))) {
+	/* small-world mode finds its pairs without a tree: none is built unless the fallback needs it */
+	const bool need_tree = !(W.small_mode && w->pair_cache);
+	if (need_tree && (!w->tree_valid || (w->ticks_since_build >= w->rebuild_every &&
+	                       (!w->pair_cache || w->seen_pair_builds + w->seen_pair_patches > w->pair_builds_at_tree)))) {
 		int r = build_tree(w);
 		if (r) return r;
 	}
@@ -578,6 +591,11 @@ static int do_physics(bt_world *w, bool gravity) {
 	int iters_this_tick = 0;
 	CK(cudaMemsetAsync(&W.ctr[CT_STOP], 0, sizeof(u32), w->stream));
 	auto pair_build = [&](int cond) -> int {
+		if (W.small_mode) { /* one thread resets the list (k_refit, cond), then one block per world */
+			LAUNCH(w, PK_REFIT, k_refit, 1, GS_BLOCK, W, 1);
+			LAUNCH(w, PK_PAIRS, k_pairs_small, W.n_worlds, BT_SMALL_WORLD, W);
+			return 0;
+		}
 		int r = refit(w, cond != 0);
 		if (r) return r;
 		LAUNCH(w, PK_PAIRS, k_pairs, std::min(nblk(W.n_leaves), pairs_wave()), BT_BLOCK, W);
@@ -619,6 +637,7 @@ static int do_physics(bt_world *w, bool gravity) {
 				}
 			}
 		} else {
+			if (!w->tree_valid) { r = build_tree(w); if (r) return r; } /* small-world mode had none */
 			r = refit(w, false);
 			if (r) return r;
 			LAUNCH(w, PK_COLLIDE, k_collide, nblk(W.n_leaves), BT_BLOCK, W);
@@ -689,6 +708,7 @@ static int do_physics(bt_world *w, bool gravity) {
 	}
 	if (w->h_flag[CT_NEED_REBUILD]) {
 		w->tree_valid = false; /* build_tree raises CT_CACHE_INVALID */
+		if (W.small_mode) { int rr = raise_cache_invalid(w); if (rr) return rr; } /* no build_tree to do it */
 		CK(cudaMemsetAsync(&W.ctr[CT_NEED_REBUILD], 0, sizeof(u32), w->stream));
 	}
 	w->ray_valid = false;
@@ -1025,7 +1045,7 @@ int bt_world_assign(bt_world *dst, bt_world *src) {
 	rebase(&dst->ray, sizeof(dst->ray), src, dst);
 	dst->tree_valid = src->tree_valid; dst->deltas_pending = src->deltas_pending; dst->any_rules = src->any_rules;
 	dst->full_flush_left = src->full_flush_left; dst->ctrls_fused = src->ctrls_fused;
-	dst->uid_map_valid = false; dst->ctr_fresh = false; dst->pdl = src->pdl;
+	dst->uid_map_valid = false; dst->ctr_fresh = false; dst->pdl = src->pdl; dst->small_worlds = src->small_worlds;
 	dst->any_ticks = src->any_ticks; dst->any_rand = src->any_rand; dst->bad_tick = src->bad_tick; dst->device_ticks = src->device_ticks;
 	dst->ticks_since_build = src->ticks_since_build; dst->rebuild_every = src->rebuild_every;
 	dst->max_iterations = src->max_iterations; dst->pair_cache = src->pair_cache;

@@ -25,6 +25,7 @@ struct Emu {
 	DevWorld W;
 	std::vector<void *> allocs;
 	bool tree_valid, deltas_pending, ctrls_fused;
+	bool small_ok; /* every world <= BT_SMALL_WORLD entities */
 	int full_flush_left;
 	int ticks_since_build, rebuild_every;
 	int64_t iterations, ticks;
@@ -161,6 +162,12 @@ Emu *bte_create(const bt_world_desc *d, int rebuild_every, int shuffle_seed) {
 	E->pair_builds_at_tree = 0;
 	E->deltas_pending = deltas;
 	E->up_root_order.assign(d->root_order, d->root_order + n);
+	{
+		i32 biggest = 0;
+		for (int g = 0; g < nw; g++) biggest = std::max(biggest, W.wend[g] - W.wbegin[g]);
+		E->small_ok = biggest <= BT_SMALL_WORLD;
+		W.small_mode = E->small_ok ? 1 : 0;
+	}
 	return E;
 }
 
@@ -231,8 +238,9 @@ static int do_physics(Emu *E, bool gravity) {
 		for (i32 e = 0; e < n; e++) t_integrate(W, e);
 		E->deltas_pending = false;
 	}
-	if (!E->tree_valid || (E->ticks_since_build >= E->rebuild_every &&
-	                       (!E->pair_cache || W.ctr[CT_PAIR_BUILDS] + W.ctr[CT_PAIR_PATCHES] > E->pair_builds_at_tree)))
+	const bool need_tree = !(W.small_mode && E->pair_cache);
+	if (need_tree && (!E->tree_valid || (E->ticks_since_build >= E->rebuild_every &&
+	                       (!E->pair_cache || W.ctr[CT_PAIR_BUILDS] + W.ctr[CT_PAIR_PATCHES] > E->pair_builds_at_tree))))
 		build_tree(E);
 	E->ticks_since_build++;
 	W.iter_base = W.iter_id;
@@ -252,10 +260,17 @@ static int do_physics(Emu *E, bool gravity) {
 		if (E->pair_cache) {
 			if (cache_state != 2) {
 				u32 before = W.ctr[CT_PAIR_BUILDS], pbefore = W.ctr[CT_PAIR_PATCHES];
-				refit(E, 1);
+				if (W.small_mode) { /* k_refit(cond) in small-world mode: reset only */
+					if (W.ctr[CT_CACHE_INVALID]) { W.ctr[CT_PAIR_N] = 0; W.ctr[CT_PAIR_BUILDS]++; }
+				} else {
+					refit(E, 1);
+				}
 				{
 					HostEmit emit = {W};
-					if (W.ctr[CT_CACHE_INVALID] && bt_patch_mode(W)) {
+					if (W.small_mode) {
+						std::vector<i32> o = order(E, W.n_worlds);
+						for (i32 g : o) t_pairs_small_world(W, g, emit);
+					} else if (W.ctr[CT_CACHE_INVALID] && bt_patch_mode(W)) {
 						std::vector<i32> o = order(E, (i32)W.ctr[CT_DIRTY_N]);
 						for (i32 t : o) t_pairs_patch(W, t, stack.data(), 1, emit);
 					} else {
@@ -273,6 +288,7 @@ static int do_physics(Emu *E, bool gravity) {
 				for (i32 p : o) t_narrow(W, W.pairs[p], E->st, any);
 			}
 		} else {
+			if (!E->tree_valid) build_tree(E);
 			refit(E, 0);
 			std::vector<i32> o = order(E, W.n_leaves);
 			for (i32 t : o) t_collide(W, t, stack.data(), 1, E->st, any);
@@ -302,7 +318,10 @@ static int do_physics(Emu *E, bool gravity) {
 		W.ctr[CT_ANY_DELTA] = 0;
 	}
 	if (W.ctr[CT_ERROR]) return -(int)W.ctr[CT_ERROR];
-	if (W.ctr[CT_NEED_REBUILD]) { E->tree_valid = false; W.ctr[CT_NEED_REBUILD] = 0; }
+	if (W.ctr[CT_NEED_REBUILD]) {
+		E->tree_valid = false; W.ctr[CT_NEED_REBUILD] = 0;
+		if (W.small_mode) { W.ctr[CT_CACHE_INVALID] = 1; W.ctr[CT_CACHE_FULL] = 1; }
+	}
 	return 0;
 }
 
@@ -350,6 +369,7 @@ void bte_set_option(Emu *E, const char *name, int64_t v) {
 	if (!strcmp(name, "allow_unsupported")) E->W.lenient = v != 0;
 	if (!strcmp(name, "cache_margin")) E->W.margin = (i32)v;
 	if (!strcmp(name, "cache_horizon")) E->W.horizon = (i32)v;
+	if (!strcmp(name, "small_worlds")) { E->W.small_mode = v != 0 && E->small_ok; if (!v) E->tree_valid = false; }
 	if (!strcmp(name, "pair_patch")) E->W.patch = v != 0;
 	if (!strcmp(name, "patch_shift")) E->W.patch_shift = (i32)v;
 }

@@ -104,3 +104,24 @@ def test_incremental_pair_patches_agree(emu, name, rebuild_every):
     assert worlds[0].pair_patches() == 0
     if wa.n >= 1000:
         assert worlds[1].pair_patches() > 0
+
+
+@pytest.mark.parametrize("name", ["arena_kick", "stack512"])
+def test_small_world_pair_search_agrees_with_tree(emu, name):
+    """worlds of <= 128 entities find their candidate pairs by brute force (no tree); same results"""
+    if name == "stack512":
+        import bittoss_b200
+        from util import load_world, golden_path
+        wa = bittoss_b200.concat_worlds([load_scenario("arena_kick")[0]] * 3)   # a batch of small worlds
+        ref = load_scenario("arena_kick")[1]
+    else:
+        wa, ref = load_scenario(name)
+    a = emu.EmuWorld(wa, rebuild_every=3, shuffle_seed=2)
+    b = emu.EmuWorld(wa, rebuild_every=3, shuffle_seed=2)
+    b.set_option("small_worlds", 0)
+    for t in range(len(ref)):
+        a.step(31)
+        b.step(31)
+        assert a.hash() == b.hash(), t
+        assert a.hash()[0] == int(ref[t]), t
+    assert a.pair_rebuilds() > 0

@@ -224,3 +224,23 @@ def test_cuda_dup_and_rollback(bt):
     assert [int(x) for x in big.tick(10, hashes=True)[:, 0]] == [int(x) for x in twin.tick(10, hashes=True)[:, 0]]
     for x in (w, snap, snap2, big, twin):
         x.close()
+
+
+def test_cuda_small_world_pair_search_agrees_with_tree(bt):
+    """small-world mode (brute-force pairs per world, one block each) vs the LBVH path, single and batched"""
+    wa1, ref = load_scenario("arena_kick")
+    for wa in (wa1, bt.concat_worlds([wa1] * 40)):
+        streams = []
+        for small in (1, 0):
+            w = bt.World(wa)
+            w.set_option("small_worlds", small)
+            hs = []
+            for _ in range(len(ref)):
+                w.step(31)   # the fixture was stepped without the world rules bt_world_tick would add
+                hs.append(w.hash())
+            streams.append(np.array([[int(x) for x in h] for h in hs], dtype=np.uint64))
+            st = w.stats()
+            assert (st["tree_builds"] == 0) == bool(small)
+            w.close()
+        assert np.array_equal(streams[0], streams[1])
+        assert [int(x) for x in streams[0][:, 0]] == [int(x) for x in ref]

@@ -32,6 +32,7 @@ def main():
     ap.add_argument("--level", default=os.path.join(ROOT, "oracle", "_ref", "data", "arena.sav"))
     ap.add_argument("--check", type=int, default=4)
     ap.add_argument("--patch-shift", type=int, default=-1)
+    ap.add_argument("--small", type=int, default=1, help="0: force the LBVH path instead of the small-world pair search")
     ap.add_argument("--horizon", type=int, default=-1)
     ap.add_argument("--patch", type=int, default=1)
     ap.add_argument("--margin", type=int, default=-1)
@@ -67,6 +68,7 @@ def main():
         if args.patch_shift >= 0:
             w.set_option("patch_shift", args.patch_shift)
         w.set_option("pair_patch", args.patch)
+        w.set_option("small_worlds", args.small)
         if args.margin >= 0:
             w.set_option("cache_margin", args.margin)
         w.upload(batch)
