@@ -14,7 +14,7 @@ from .desc import BtWorldDesc, WorldArrays
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-LIB_SO = os.path.join(HERE, "libbittoss_b200.so")
+LIB_SO = os.environ.get("BT_LIB_SO", os.path.join(HERE, "libbittoss_b200.so"))  # override: A/B against another build
 INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 
 PHASE_CTRLS, PHASE_PREP, PHASE_GRAVITY, PHASE_PHYSICS, PHASE_FINISH, PHASE_ALL = 1, 2, 4, 8, 16, 31

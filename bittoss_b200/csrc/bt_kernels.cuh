@@ -36,10 +36,14 @@ static __device__ __forceinline__ void stats_flush(const DevWorld &W, const Loca
  * scheduled (its blocks fill SMs as ours drain, hiding launch latency and part of the tail), then
  * waits until its own predecessor has completed and its memory is visible.  Without the launch
  * attribute both instructions are no-ops. */
-#define PDL_ENTRY() asm volatile("griddepcontrol.launch_dependents;\ngriddepcontrol.wait;" ::: "memory")
+/* The instructions sit behind a launch-uniform flag: executed unconditionally they cost the 1 M-entity
+ * world 2.3 % even without the launch attribute (the asm is a compiler barrier at every kernel entry). */
+#define PDL_ENTRY() do { if (W.pdl) asm volatile("griddepcontrol.launch_dependents;\ngriddepcontrol.wait;" ::: "memory"); } while (0)
 /* the two long multi-wave kernels (k_narrow, k_push) only wait: their successor is released when they
  * complete, so that no waiting block holds registers while their last waves run */
-#define PDL_WAIT() asm volatile("griddepcontrol.wait;" ::: "memory")
+#define PDL_WAIT() do { if (W.pdl) asm volatile("griddepcontrol.wait;" ::: "memory"); } while (0)
+/* kernels without a DevWorld parameter (radix sort passes of the tree build) */
+#define PDL_ENTRY_ALWAYS() asm volatile("griddepcontrol.launch_dependents;\ngriddepcontrol.wait;" ::: "memory")
 #define TID ((i32)(blockIdx.x * blockDim.x + threadIdx.x))
 /* the proposal stamp of iteration `id` lives in one of two slots, by parity */
 #define ANY_SLOT(id) (((id) & 1) ? CT_ANY_ODD : CT_ANY_PROPOSAL)
@@ -351,7 +355,7 @@ __global__ void __launch_bounds__(BT_BLOCK) k_hash(DevWorld W, u64 *sum, u32 *cn
 #define SORT_ITEMS 16
 #define SORT_TILE (SORT_THREADS * SORT_ITEMS)
 
-__global__ void __launch_bounds__(SORT_THREADS) k_sort_hist(const u64 *keys, i32 n, int shift, u32 *hist, int nb) { PDL_ENTRY();
+__global__ void __launch_bounds__(SORT_THREADS) k_sort_hist(const u64 *keys, i32 n, int shift, u32 *hist, int nb) { PDL_ENTRY_ALWAYS();
 	__shared__ u32 h[256];
 	h[threadIdx.x] = 0;
 	__syncthreads();
@@ -366,7 +370,7 @@ __global__ void __launch_bounds__(SORT_THREADS) k_sort_hist(const u64 *keys, i32
 }
 
 /* exclusive scan of `len` counters by one block of 1024 threads */
-__global__ void __launch_bounds__(1024) k_sort_scan(u32 *hist, int len) { PDL_ENTRY();
+__global__ void __launch_bounds__(1024) k_sort_scan(u32 *hist, int len) { PDL_ENTRY_ALWAYS();
 	__shared__ u32 warpTot[32];
 	__shared__ u32 carry;
 	if (threadIdx.x == 0) carry = 0;
@@ -402,7 +406,7 @@ __global__ void __launch_bounds__(1024) k_sort_scan(u32 *hist, int len) { PDL_EN
 }
 
 __global__ void __launch_bounds__(SORT_THREADS) k_sort_scatter(const u64 *keys, const i32 *vals, u64 *okeys, i32 *ovals,
-                                                             i32 n, int shift, const u32 *hist, int nb) { PDL_ENTRY();
+                                                             i32 n, int shift, const u32 *hist, int nb) { PDL_ENTRY_ALWAYS();
 	__shared__ u32 warpOff[SORT_THREADS / 32][256];
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 	for (int d = lane; d < 256; d += 32) warpOff[warp][d] = 0;

@@ -121,6 +121,7 @@ template <typename T> static int dalloc(bt_world *w, T **p, size_t count) {
 /* every kernel goes through here; pdl: programmatic dependent launch (see PDL_ENTRY in bt_kernels.cuh) */
 template <typename... KArgs, typename... Args>
 static inline void launch_k(bool pdl, void (*kern)(KArgs...), int grid, int block, cudaStream_t s, Args &&...args) {
+	if (!pdl) { kern<<<grid, block, 0, s>>>(KArgs(args)...); return; }
 	cudaLaunchConfig_t cfg = {};
 	cfg.gridDim = dim3((unsigned)grid);
 	cfg.blockDim = dim3((unsigned)block);
@@ -213,7 +214,7 @@ int bt_world_create(bt_world **out, int device, int32_t max_ents, int32_t max_sl
 	w->device = device;
 	w->cap_ents = max_ents; w->cap_sliders = max_sliders; w->cap_wires = max_wires; w->cap_worlds = max_worlds;
 	w->tree_valid = false; w->deltas_pending = true; w->ticks_since_build = 0; w->full_flush_left = 2; w->ctrls_fused = false;
-	w->rebuild_every = 16; w->max_iterations = 100000; w->pair_cache = 1; w->pair_rebuilds = 0; w->pair_overflows = 0; w->seen_pair_builds = 0; w->seen_pair_patches = 0; w->pair_builds_at_tree = 0; w->profiling = false; w->ray_valid = false; w->uid_map_valid = false; w->ctr_fresh = false; w->pdl_opt = getenv("BT_NO_PDL") ? 0 : -1; w->pdl = w->pdl_opt != 0; w->small_worlds = true; w->d_reqs = NULL; w->d_req_starts = NULL; w->reqs_cap = 0; w->any_ticks = w->any_rand = false; w->bad_tick = 0; w->device_ticks = 1;
+	w->rebuild_every = 16; w->max_iterations = 100000; w->pair_cache = 1; w->pair_rebuilds = 0; w->pair_overflows = 0; w->seen_pair_builds = 0; w->seen_pair_patches = 0; w->pair_builds_at_tree = 0; w->profiling = false; w->ray_valid = false; w->uid_map_valid = false; w->ctr_fresh = false; w->pdl_opt = getenv("BT_NO_PDL") ? 0 : -1; w->pdl = false; /* decided at upload, together with W.pdl */ w->small_worlds = true; w->d_reqs = NULL; w->d_req_starts = NULL; w->reqs_cap = 0; w->any_ticks = w->any_rand = false; w->bad_tick = 0; w->device_ticks = 1;
 	w->h_flag = NULL; w->ev0 = w->ev1 = NULL; w->stream = NULL;
 	*out = w;
 #define TRY(x) do { int _r = (x); if (_r) { bt_world_destroy(w); *out = NULL; return _r; } } while (0)
@@ -285,6 +286,7 @@ int bt_world_set_option(bt_world *w, const char *name, int64_t value) {
 	if (!strcmp(name, "pdl")) {
 		w->pdl_opt = value < 0 ? -1 : (value != 0);
 		w->pdl = w->pdl_opt < 0 ? (w->W.n_worlds > 1 || w->W.n <= (1 << 18)) : w->pdl_opt != 0;
+		w->W.pdl = w->pdl ? 1 : 0;
 		return BT_OK;
 	}
 	if (!strcmp(name, "small_worlds")) { /* takes effect at the next upload */
@@ -463,7 +465,8 @@ int bt_world_upload(bt_world *w, const bt_world_desc *d) {
 		/* Dependent launches pay when a tick is many short kernels (batched or small worlds: +5-7 %).
 		 * One big world spends its tick in two long kernels; there the resident waiting blocks cost
 		 * 0.1-0.4 % instead (measured A/B on the 1 M-entity world), so "auto" leaves them off. */
-		if (w->pdl_opt < 0) w->pdl = nw > 1 || n <= (1 << 18);
+		w->pdl = w->pdl_opt < 0 ? (nw > 1 || n <= (1 << 18)) : w->pdl_opt != 0;
+		W.pdl = w->pdl ? 1 : 0; /* the launch attribute and the instructions in the kernels always go together */
 	}
 	w->any_ticks = any_ticks; w->any_rand = any_rand; w->bad_tick = bad_tick;
 	w->ticks_since_build = 0;
