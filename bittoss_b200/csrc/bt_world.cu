@@ -76,6 +76,7 @@ struct bt_world {
 	bool uid_map_valid;
 	bool small_worlds; /* option "small_worlds": brute-force pair search when every world is small (default on) */
 	bool pdl;       /* programmatic dependent launches in effect */
+	i32 margin_opt; /* option "cache_margin": -1 auto */
 	int pdl_opt;    /* option "pdl": 0 off, 1 on, -1 auto = on unless one big world (decided at upload) */
 	bool ctr_fresh; /* h_flag mirrors the device counters (nothing that can change CT_DEAD_N ran since the last fetch) */
 	bool any_ticks, any_rand; /* some entity has a tick handler / a TICK_RAND */
@@ -214,7 +215,7 @@ int bt_world_create(bt_world **out, int device, int32_t max_ents, int32_t max_sl
 	w->device = device;
 	w->cap_ents = max_ents; w->cap_sliders = max_sliders; w->cap_wires = max_wires; w->cap_worlds = max_worlds;
 	w->tree_valid = false; w->deltas_pending = true; w->ticks_since_build = 0; w->full_flush_left = 2; w->ctrls_fused = false;
-	w->rebuild_every = 16; w->max_iterations = 100000; w->pair_cache = 1; w->pair_rebuilds = 0; w->pair_overflows = 0; w->seen_pair_builds = 0; w->seen_pair_patches = 0; w->pair_builds_at_tree = 0; w->profiling = false; w->ray_valid = false; w->uid_map_valid = false; w->ctr_fresh = false; w->pdl_opt = getenv("BT_NO_PDL") ? 0 : -1; w->pdl = false; /* decided at upload, together with W.pdl */ w->small_worlds = true; w->d_reqs = NULL; w->d_req_starts = NULL; w->reqs_cap = 0; w->any_ticks = w->any_rand = false; w->bad_tick = 0; w->device_ticks = 1;
+	w->rebuild_every = 16; w->max_iterations = 100000; w->pair_cache = 1; w->pair_rebuilds = 0; w->pair_overflows = 0; w->seen_pair_builds = 0; w->seen_pair_patches = 0; w->pair_builds_at_tree = 0; w->profiling = false; w->ray_valid = false; w->uid_map_valid = false; w->ctr_fresh = false; w->margin_opt = -1; w->pdl_opt = getenv("BT_NO_PDL") ? 0 : -1; w->pdl = false; /* decided at upload, together with W.pdl */ w->small_worlds = true; w->d_reqs = NULL; w->d_req_starts = NULL; w->reqs_cap = 0; w->any_ticks = w->any_rand = false; w->bad_tick = 0; w->device_ticks = 1;
 	w->h_flag = NULL; w->ev0 = w->ev1 = NULL; w->stream = NULL;
 	*out = w;
 #define TRY(x) do { int _r = (x); if (_r) { bt_world_destroy(w); *out = NULL; return _r; } } while (0)
@@ -291,14 +292,21 @@ int bt_world_set_option(bt_world *w, const char *name, int64_t value) {
 	}
 	if (!strcmp(name, "small_worlds")) { /* takes effect at the next upload */
 		w->small_worlds = value != 0;
-		if (!w->small_worlds && w->W.small_mode) { w->W.small_mode = 0; w->tree_valid = false; }
+		if (!w->small_worlds && w->W.small_mode) {
+			w->W.small_mode = 0; w->tree_valid = false;
+			if (w->margin_opt < 0) w->W.margin = 32;
+		}
 		return BT_OK;
 	}
 	if (!strcmp(name, "device_ticks")) { w->device_ticks = value != 0; return BT_OK; }
 	if (!strcmp(name, "pair_patch")) { w->W.patch = value != 0; return BT_OK; }
 	if (!strcmp(name, "patch_shift")) { w->W.patch_shift = value < 0 ? 0 : (value > 20 ? 20 : (i32)value); return BT_OK; }
 	if (!strcmp(name, "run_ahead")) { w->run_ahead = value != 0; return BT_OK; }
-	if (!strcmp(name, "cache_margin")) { w->W.margin = value < 0 ? 0 : (i32)value; return BT_OK; }
+	if (!strcmp(name, "cache_margin")) { /* < 0: auto (32; 128 in small-world mode, where a rebuild is cheap but every one is global) */
+		w->margin_opt = value < 0 ? -1 : (i32)value;
+		w->W.margin = value < 0 ? (w->W.small_mode ? 128 : 32) : (i32)value;
+		return BT_OK;
+	}
 	return BT_ERR_ARG;
 }
 
@@ -462,6 +470,7 @@ int bt_world_upload(bt_world *w, const bt_world_desc *d) {
 		i32 biggest = 0;
 		for (int g = 0; g < nw; g++) biggest = std::max(biggest, wend[g] - wbegin[g]);
 		W.small_mode = (w->small_worlds && biggest <= BT_SMALL_WORLD) ? 1 : 0;
+		if (w->margin_opt < 0) W.margin = W.small_mode ? 128 : 32;
 		/* Dependent launches pay when a tick is many short kernels (batched or small worlds: +5-7 %).
 		 * One big world spends its tick in two long kernels; there the resident waiting blocks cost
 		 * 0.1-0.4 % instead (measured A/B on the 1 M-entity world), so "auto" leaves them off. */
@@ -1057,7 +1066,7 @@ int bt_world_assign(bt_world *dst, bt_world *src) {
 	rebase(&dst->ray, sizeof(dst->ray), src, dst);
 	dst->tree_valid = src->tree_valid; dst->deltas_pending = src->deltas_pending; dst->any_rules = src->any_rules;
 	dst->full_flush_left = src->full_flush_left; dst->ctrls_fused = src->ctrls_fused;
-	dst->uid_map_valid = false; dst->ctr_fresh = false; dst->pdl = src->pdl; dst->pdl_opt = src->pdl_opt; dst->small_worlds = src->small_worlds;
+	dst->uid_map_valid = false; dst->ctr_fresh = false; dst->pdl = src->pdl; dst->pdl_opt = src->pdl_opt; dst->margin_opt = src->margin_opt; dst->small_worlds = src->small_worlds;
 	dst->any_ticks = src->any_ticks; dst->any_rand = src->any_rand; dst->bad_tick = src->bad_tick; dst->device_ticks = src->device_ticks;
 	dst->ticks_since_build = src->ticks_since_build; dst->rebuild_every = src->rebuild_every;
 	dst->max_iterations = src->max_iterations; dst->pair_cache = src->pair_cache;

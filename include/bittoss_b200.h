@@ -258,7 +258,7 @@ int bt_world_profile_enable(bt_world *w, int on);
 int bt_world_profile_read(bt_world *w, bt_profile *out, int reset);
 /* Knobs (integers).  None of them changes results, only how the work is scheduled:
  * "rebuild_every" ticks between full LBVH rebuilds (16); "pair_cache" 0/1 cached candidate pairs;
- * "cache_margin" inflation of the cached boxes (32); "cache_horizon" ticks of motion the cached box
+ * "cache_margin" inflation of the cached boxes (auto: 32, 128 in small-world mode); "cache_horizon" ticks of motion the cached box
  * is stretched ahead by (0); "pair_patch" 0/1 incremental pair-list patches; "patch_shift" patch
  * while dirty << shift <= leaves (4); "run_ahead" 0/1 speculative iterations; "max_iterations";
  * "device_ticks" 0/1 bt_world_tick runs the tick handlers itself when all have device bodies;
