@@ -56,9 +56,62 @@ static __device__ __forceinline__ void stats_flush(const DevWorld &W, const Loca
 
 __global__ void __launch_bounds__(BT_BLOCK) k_pre(DevWorld W, u32 phases) { PDL_ENTRY(); t_pre(W, TID, phases); }
 __global__ void __launch_bounds__(BT_BLOCK) k_flush_scan(DevWorld W) { PDL_ENTRY(); t_flush_scan(W, TID); }
+/* flush1's ordered part, one WARP per world.  t_flush_serial (the one-thread restatement the emulator
+ * runs) walks the world's entities three times, newest first; almost every visit finds nothing.  Here
+ * the 32 lanes look at 32 entities at once and only the hits are handled, one at a time, in the
+ * same newest-first order by the lane that found them.  The candidate flags of a pass are not
+ * changed by the pass itself (a crush kills only its own entity, a fumble sets no drop flag, a
+ * pickup's handlers request no pickup), every other condition is re-evaluated when the hit is
+ * handled, so the result equals the sequential walk. */
 __global__ void __launch_bounds__(BT_BLOCK) k_flush_serial(DevWorld W) { PDL_ENTRY();
 	LocalStats st = {0, 0, 0, 0, 0};
-	t_flush_serial(W, TID, st);
+	const int lane = threadIdx.x & 31;
+	const i32 g = TID >> 5;
+	if (g < W.n_worlds) {
+		int work = 0;
+		if (lane == 0) {
+			W.flip[g] ^= 1;
+			work = W.wflush[g];
+			W.wflush[g] = 0;
+		}
+		work = __shfl_sync(0xffffffffu, work, 0);
+		if (work) {
+			const int slot = 1 ^ __shfl_sync(0xffffffffu, lane == 0 ? W.flip[g] : 0, 0);
+			const i32 b0 = W.wbegin[g], b1 = W.wend[g];
+			for (int pass = 0; pass < 3; pass++) {
+				for (i32 top = b1 - 1; top >= b0; top -= 32) {
+					const i32 i = top - lane; /* lane 0 = newest */
+					int hit = 0;
+					if (i >= b0 && W.inList[i]) {
+						if (pass == 0) hit = (slot ? W.dead_max1[i] : W.dead_max0[i]) != 0;
+						else if (pass == 1) hit = W.newDrop[i] != 0;
+						else hit = W.holder[i] < 0 && W.newHolder[i] >= 0;
+					}
+					u32 m = __ballot_sync(0xffffffffu, hit);
+					while (m) {
+						const int l = __ffs(m) - 1;
+						m &= m - 1;
+						if (lane == l && W.inList[i]) {
+							if (pass == 0) { /* flushDeaths ent.cpp:747-761 */
+								u8 d = slot ? W.dead_max1[i] : W.dead_max0[i];
+								bt_crush(W, i, 0xfffffu - ((u32)i & 0xfffffu), st, d);
+								W.dead[i] = d;
+							} else if (pass == 1) { /* flushDrops :765-773 */
+								W.newDrop[i] = 0;
+								bt_fumble(W, i, st);
+							} else if (W.holder[i] < 0) { /* flushPickups :775-792 */
+								i32 x = W.newHolder[i];
+								if (W.holdRoot[x] != i && !W.dead[x]) bt_pickup(W, x, i, W.newHoldFlags[i]);
+								W.newHolder[i] = -1;
+							}
+						}
+						__syncwarp();
+					}
+				}
+				__syncwarp();
+			}
+		}
+	}
 	stats_flush(W, st);
 }
 __global__ void __launch_bounds__(BT_BLOCK) k_flush_misc(DevWorld W) { PDL_ENTRY(); t_flush_misc(W, TID); }

@@ -565,7 +565,7 @@ static int flush1(bt_world *w, bool hint) {
 	w->ctr_fresh = false;
 	CK(cudaMemsetAsync(&W.ctr[CT_FLUSH_HINT], 0, sizeof(u32), w->stream));
 	LAUNCH(w, PK_FLUSH, k_flush_scan, nblk(W.n), BT_BLOCK, W);
-	LAUNCH(w, PK_FLUSH, k_flush_serial, nblk(W.n_worlds), BT_BLOCK, W);
+	LAUNCH(w, PK_FLUSH, k_flush_serial, nblk((i64)W.n_worlds * 32), BT_BLOCK, W); /* one warp per world */
 	LAUNCH(w, PK_FLUSH, k_flush_misc, nblk(W.n), BT_BLOCK, W);
 	return 0;
 }
