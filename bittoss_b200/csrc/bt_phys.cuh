@@ -267,6 +267,7 @@ static BT_HD int bt_bottle_push(const DevWorld &W, int id, i32 me, i32 him) {
 		else { /* uDead entUpdaters.c:20-22 */
 			int g = W.world[him];
 			if (W.flip[g]) W.dead_max1[him] |= 1; else W.dead_max0[him] |= 1;
+			W.wflush[g] = 1;
 			W.ctr[CT_FLUSH_HINT] = 1;
 		}
 	}
@@ -323,6 +324,7 @@ static BT_HD void bt_upickup(const DevWorld &W, i32 p, i32 e, i32 holdFlags) {
 	}
 	W.newHolder[e] = p;
 	W.newHoldFlags[e] = holdFlags;
+	W.wflush[W.world[e]] = 1; /* the world has ordered flush1 work (k_flush_scan only runs after an upload) */
 	W.ctr[CT_FLUSH_HINT] = 1;
 }
 
@@ -1511,6 +1513,7 @@ static BT_HD void bt_uslider_shared(const DevWorld &W, i32 e, int ix, i32 value)
 }
 static BT_HD void bt_udead(const DevWorld &W, i32 e) {
 	if (W.flip[W.world[e]]) W.dead_max1[e] |= 1; else W.dead_max0[e] |= 1;
+	W.wflush[W.world[e]] = 1;
 	W.ctr[CT_FLUSH_HINT] = 1;
 }
 /* logic_common_input logic.c:51-61 / logic_common_output :63-80 */
@@ -1612,7 +1615,7 @@ static BT_HD void t_tick(const DevWorld &W, i32 me) {
 	case TICK_SEAT_OLD: case TICK_SEAT: /* seat_tick(_old) seat.cpp:38-60 */
 		for (i32 k = 0; k < W.wire_cnt[me]; k++) {
 			i32 w = W.wire_to[W.wire_off[me] + k];
-			if (bt_button(W, w, 0)) { W.newDrop[w] = 1; W.ctr[CT_FLUSH_HINT] = 1; continue; } /* uDrop */
+			if (bt_button(W, w, 0)) { W.newDrop[w] = 1; W.wflush[W.world[w]] = 1; W.ctr[CT_FLUSH_HINT] = 1; continue; } /* uDrop */
 			if (id == TICK_SEAT_OLD) continue;
 			for (int i = 0; i < 5; i++) bt_uslider_shared(W, me, i, bt_getslider(W, w, i));
 			for (int i = 0; i < 4; i++)
@@ -1676,6 +1679,7 @@ static BT_HD void t_request(const DevWorld &W, const BtReq &q) {
 	case BT_REQ_COLLIDEMASK: W.fullFlush[e] = 1; W.ncollide[e] = (u32)q.a0; break; /* uMyCollideMask :80 */
 	default: W.ctr[CT_ERROR] = (u32)(-BT_ERR_ARG); break;
 	}
+	if (q.kind == BT_REQ_DROP || q.kind == BT_REQ_DEAD || q.kind == BT_REQ_ERASE) W.wflush[g] = 1;
 	W.ctr[CT_FLUSH_HINT] = 1;
 }
 
@@ -1691,7 +1695,9 @@ static BT_HD void t_pre(const DevWorld &W, i32 e, u32 phases) {
 	}
 }
 
-/* marks worlds whose flush1 has deaths / drops / pickups to apply */
+/* marks worlds whose flush1 has deaths / drops / pickups to apply.  Only needed for what an upload
+ * brought along (the first two flush1 after it: one per dead_max slot); everything requested on
+ * the device marks its world itself (bt_udead, bt_upickup, uDrop, world rules, host requests). */
 static BT_HD void t_flush_scan(const DevWorld &W, i32 e) {
 	if (e >= W.n || !W.inList[e]) return;
 	if (W.dead_max0[e] | W.dead_max1[e] | W.newDrop[e] | (W.newHolder[e] >= 0)) {
@@ -1770,10 +1776,12 @@ static BT_HD void t_flush_misc(const DevWorld &W, i32 e) {
 			}
 		}
 	}
-	i32 base = W.wire_off[e];
-	i32 cnt = W.wire_cnt[e];
 	i32 rm = W.wireRm[e];
-	W.wireRm[e] = -1;
+	if (rm >= 0) W.wireRm[e] = -1;
+	const i32 cnt0 = W.wire_cnt[e];
+	if (!cnt0) return; /* most entities have no wires: nothing to clean, nothing to write */
+	i32 base = W.wire_off[e];
+	i32 cnt = cnt0;
 	for (i32 i = 0; i < cnt; i++) {
 		i32 x = W.wire_to[base + i];
 		if (W.dead[x] || x == rm) { /* quickRmAt: pull the last wire into this place (list.h) */
@@ -1781,7 +1789,7 @@ static BT_HD void t_flush_misc(const DevWorld &W, i32 e) {
 			i--;
 		}
 	}
-	W.wire_cnt[e] = cnt;
+	if (cnt != cnt0) W.wire_cnt[e] = cnt;
 }
 
 /* world rules that are per-entity scans: crush() effects.cpp:48-60 (doCrushtainer 64000,
@@ -1816,6 +1824,7 @@ static BT_HD void t_world_rules(const DevWorld &W, i32 e) {
 	if (die) {
 		if (W.flip[g]) W.dead_max1[e] |= 1;
 		else W.dead_max0[e] |= 1;
+		W.wflush[g] = 1;
 		W.ctr[CT_FLUSH_HINT] = 1;
 	}
 }

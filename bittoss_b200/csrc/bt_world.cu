@@ -83,6 +83,7 @@ struct bt_world {
 	int bad_tick;             /* first tick handler id without a device implementation, 0 = none */
 	int device_ticks;         /* option: bt_world_tick runs the tick handlers itself when it can */
 	BtReq *d_reqs; i32 *d_req_starts; i32 reqs_cap;
+	int scan_flushes_left; /* of those, the ones that must look for pending requests themselves (k_flush_scan) */
 	int full_flush_left; /* flush1 calls that must run in full (after an upload); afterwards CT_FLUSH_HINT decides */
 	bool ctrls_fused;    /* flushCtrls of this step rides in k_begin_fused */
 	i32 ticks_since_build;
@@ -214,7 +215,7 @@ int bt_world_create(bt_world **out, int device, int32_t max_ents, int32_t max_sl
 	memset(&w->ray, 0, sizeof(w->ray));
 	w->device = device;
 	w->cap_ents = max_ents; w->cap_sliders = max_sliders; w->cap_wires = max_wires; w->cap_worlds = max_worlds;
-	w->tree_valid = false; w->deltas_pending = true; w->ticks_since_build = 0; w->full_flush_left = 2; w->ctrls_fused = false;
+	w->tree_valid = false; w->deltas_pending = true; w->ticks_since_build = 0; w->full_flush_left = 2; w->scan_flushes_left = 2; w->ctrls_fused = false;
 	w->rebuild_every = 16; w->max_iterations = 100000; w->pair_cache = 1; w->pair_rebuilds = 0; w->pair_overflows = 0; w->seen_pair_builds = 0; w->seen_pair_patches = 0; w->pair_builds_at_tree = 0; w->profiling = false; w->ray_valid = false; w->uid_map_valid = false; w->ctr_fresh = false; w->margin_opt = -1; w->pdl_opt = getenv("BT_NO_PDL") ? 0 : -1; w->pdl = false; /* decided at upload, together with W.pdl */ w->small_worlds = true; w->d_reqs = NULL; w->d_req_starts = NULL; w->reqs_cap = 0; w->any_ticks = w->any_rand = false; w->bad_tick = 0; w->device_ticks = 1;
 	w->h_flag = NULL; w->ev0 = w->ev1 = NULL; w->stream = NULL;
 	*out = w;
@@ -465,6 +466,7 @@ int bt_world_upload(bt_world *w, const bt_world_desc *d) {
 	for (int g = 0; g < nw; g++) w->any_rules = w->any_rules || (d->w_gamerules[g] & (1 | 2 | 16 | 32));
 	w->deltas_pending = deltas;
 	w->full_flush_left = 2; /* both dead_max slots of the upload get looked at */
+	w->scan_flushes_left = 2;
 	w->uid_map_valid = false; w->ctr_fresh = false;
 	{
 		i32 biggest = 0;
@@ -561,10 +563,12 @@ static int flush1(bt_world *w, bool hint) {
 		LAUNCH(w, PK_FLUSH, k_flip_only, nblk(W.n_worlds), BT_BLOCK, W);
 		return 0;
 	}
+	const bool scan = w->scan_flushes_left > 0; /* pending requests an upload brought along */
+	if (w->scan_flushes_left > 0) w->scan_flushes_left--;
 	if (w->full_flush_left > 0) w->full_flush_left--;
 	w->ctr_fresh = false;
 	CK(cudaMemsetAsync(&W.ctr[CT_FLUSH_HINT], 0, sizeof(u32), w->stream));
-	LAUNCH(w, PK_FLUSH, k_flush_scan, nblk(W.n), BT_BLOCK, W);
+	if (scan) LAUNCH(w, PK_FLUSH, k_flush_scan, nblk(W.n), BT_BLOCK, W);
 	LAUNCH(w, PK_FLUSH, k_flush_serial, nblk((i64)W.n_worlds * 32), BT_BLOCK, W); /* one warp per world */
 	LAUNCH(w, PK_FLUSH, k_flush_misc, nblk(W.n), BT_BLOCK, W);
 	return 0;
@@ -1065,7 +1069,7 @@ int bt_world_assign(bt_world *dst, bt_world *src) {
 	dst->ray = src->ray;
 	rebase(&dst->ray, sizeof(dst->ray), src, dst);
 	dst->tree_valid = src->tree_valid; dst->deltas_pending = src->deltas_pending; dst->any_rules = src->any_rules;
-	dst->full_flush_left = src->full_flush_left; dst->ctrls_fused = src->ctrls_fused;
+	dst->full_flush_left = src->full_flush_left; dst->scan_flushes_left = src->scan_flushes_left; dst->ctrls_fused = src->ctrls_fused;
 	dst->uid_map_valid = false; dst->ctr_fresh = false; dst->pdl = src->pdl; dst->pdl_opt = src->pdl_opt; dst->margin_opt = src->margin_opt; dst->small_worlds = src->small_worlds;
 	dst->any_ticks = src->any_ticks; dst->any_rand = src->any_rand; dst->bad_tick = src->bad_tick; dst->device_ticks = src->device_ticks;
 	dst->ticks_since_build = src->ticks_since_build; dst->rebuild_every = src->rebuild_every;

@@ -26,7 +26,7 @@ struct Emu {
 	std::vector<void *> allocs;
 	bool tree_valid, deltas_pending, ctrls_fused;
 	bool small_ok; /* every world <= BT_SMALL_WORLD entities */
-	int full_flush_left;
+	int full_flush_left, scan_flushes_left;
 	int ticks_since_build, rebuild_every;
 	int64_t iterations, ticks;
 	LocalStats st;
@@ -69,7 +69,7 @@ Emu *bte_create(const bt_world_desc *d, int rebuild_every, int shuffle_seed) {
 	Emu *E = new Emu();
 	memset(&E->W, 0, sizeof(E->W));
 	memset(&E->st, 0, sizeof(E->st));
-	E->tree_valid = false; E->ticks_since_build = 0; E->ctrls_fused = false; E->full_flush_left = 2; E->rebuild_every = rebuild_every > 0 ? rebuild_every : 1;
+	E->tree_valid = false; E->ticks_since_build = 0; E->ctrls_fused = false; E->full_flush_left = 2; E->scan_flushes_left = 2; E->rebuild_every = rebuild_every > 0 ? rebuild_every : 1;
 	E->iterations = 0; E->ticks = 0; E->shuffle_seed = shuffle_seed; E->pair_cache = 1; E->pair_rebuilds = 0; E->pair_patches = 0;
 	DevWorld &W = E->W;
 	const int n = d->n_ents, nw = d->n_worlds;
@@ -222,7 +222,10 @@ static void flush1(Emu *E, bool hint) {
 	}
 	if (E->full_flush_left > 0) E->full_flush_left--;
 	W.ctr[CT_FLUSH_HINT] = 0;
-	for (i32 e = 0; e < W.n; e++) t_flush_scan(W, e);
+	if (E->scan_flushes_left > 0) { /* only what the upload brought along needs looking for */
+		E->scan_flushes_left--;
+		for (i32 e = 0; e < W.n; e++) t_flush_scan(W, e);
+	}
 	for (i32 g = 0; g < W.n_worlds; g++) t_flush_serial(W, g, E->st);
 	for (i32 e = 0; e < W.n; e++) t_flush_misc(W, e);
 }
