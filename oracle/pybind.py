@@ -94,6 +94,7 @@ class RefLib:
         L.btref_lab_set_button.argtypes = [C.c_int32, C.c_int, C.c_int]
         L.btref_lab_request.argtypes = [C.c_int32, C.c_int, C.c_int32, C.c_int32]
         L.btref_lab_crush_log.argtypes = [_i32p, C.c_int]
+        L.btref_lab_request3.argtypes = [C.c_int32, C.c_int, C.c_int32, C.c_int32, C.c_int32]
         with stdout_to_stderr():
             rc = L.btref_init(REF_DATA_PARENT.encode())
         if rc != 0:
@@ -150,6 +151,11 @@ class RefLib:
 
     def lab_record_all_crushes(self):
         return int(self.L.btref_lab_record_all_crushes())
+
+    def lab_request3(self, uid, kind, a=(0, 0, 0)):
+        """kind = BT_REQ_VEL / CENTER / SLIDER / ERASE / TYPEMASK / COLLIDEMASK (include/bittoss_b200.h)"""
+        a = list(a) + [0] * (3 - len(a))
+        assert self.L.btref_lab_request3(uid, kind, int(a[0]), int(a[1]), int(a[2])) == 0
 
     def lab_crush_log(self):
         buf = (C.c_int32 * 4096)()

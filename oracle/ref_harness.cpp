@@ -325,6 +325,21 @@ int btref_lab_request(int32_t uid, int what, int32_t other, int32_t arg) {
 	return 0;
 }
 
+/* the remaining deferred updaters, numbered like BT_REQ_* of include/bittoss_b200.h */
+int btref_lab_request3(int32_t uid, int kind, int32_t a0, int32_t a1, int32_t a2) {
+	ent *e = by_uid(uid);
+	if (!e) return -1;
+	int32_t v[3] = {a0, a1, a2};
+	if (kind == BT_REQ_VEL) uVel(e, v);
+	else if (kind == BT_REQ_CENTER) uCenter(e, v);
+	else if (kind == BT_REQ_SLIDER) uSlider(e, a0, a1);
+	else if (kind == BT_REQ_ERASE) uErase(cur->gs, e);
+	else if (kind == BT_REQ_TYPEMASK) uMyTypeMask(e, (uint32_t)a0);
+	else if (kind == BT_REQ_COLLIDEMASK) uMyCollideMask(e, (uint32_t)a0);
+	else return -1;
+	return 0;
+}
+
 /* every entity that has a crush handler gets the recorder instead (same catalog id on export) */
 int btref_lab_record_all_crushes(void) {
 	int k = 0;

@@ -17,6 +17,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
 sys.path.insert(0, os.path.dirname(HERE))
 
 T_HEAVY, T_TERRAIN, T_OBSTACLE, T_DEBRIS, T_WEIGHTLESS, T_FLAG = 1, 2, 4, 8, 16, 32
+T_DECOR = 64
 T_INPUTS, T_EQUIP, T_EQUIP_SM = 1 << 11, 1 << 12, 1 << 13
 HOLD_DROP, HOLD_MOVE, HOLD_FREEZE, HOLD_SINGLE = 1, 2, 4, 8
 WM_ME, WM_WOOD = 1, 6
@@ -194,14 +195,44 @@ def lab_logic(R):
     return 100, script, 0
 
 
-# builders return ticks, or (ticks, script) with script = [(tick, what, uid, other, arg)] applied before
-# that tick's step: what 0 uDrop, 1 uDead, 2 uPickup(uid, other, arg), 3 pushBtn(uid, arg)
+REQ_DROP, REQ_DEAD, REQ_PICKUP, REQ_BUTTON, REQ_VEL, REQ_CENTER, REQ_SLIDER, REQ_ERASE, REQ_TYPEMASK, REQ_COLLIDEMASK = range(10)
+
+
+def lab_requests(R):
+    """every kind of host request (bt_world_apply_requests) against the reference's own updaters:
+    uVel / uCenter kicks, two uSlider calls on one slider in one tick (min/max averaging), uErase
+    (no crush handler call) vs uDead (crush handler call), uMyTypeMask taking an entity out of the
+    collision world and back in (it gains a box again: leaf set changes), uMyCollideMask"""
+    pad(R, 0, 0, r=(6000, 3000, 300))
+    a, b, c, d, e, f, g = [cube(R, -4500 + 1500 * i, 0, -320 - 10 * i) for i in range(7)]
+    top = cube(R, -4500 + 1500 * 4, 50, -1300)      # rests on `e`: falls through while e is not collidable
+    R.lab_set_sliders(c, [5, 0, -7])
+    R.lab_set_handlers(d, crush=1)
+    R.lab_set_handlers(g, crush=2)
+    script = [
+        (3, REQ_VEL, a, -1, 40, -25, -90),
+        (5, REQ_CENTER, b, -1, 130, 260, -40),
+        (6, REQ_SLIDER, c, -1, 0, 100, 0), (6, REQ_SLIDER, c, -1, 0, -31, 0), (6, REQ_SLIDER, c, -1, 2, 9, 0),
+        (6, REQ_SLIDER, c, -1, 7, 1, 0),             # no such slider: ignored (entUpdaters.c:55-60)
+        (8, REQ_ERASE, d, -1, 0, 0, 0),
+        (10, REQ_TYPEMASK, e, -1, T_DECOR, 0, 0), (10, REQ_COLLIDEMASK, e, -1, 0, 0, 0),
+        (12, REQ_COLLIDEMASK, f, -1, T_TERRAIN, 0, 0),
+        (14, REQ_DEAD, g, -1, 0, 0, 0),
+        (22, REQ_TYPEMASK, e, -1, CUBE, 0, 0), (22, REQ_COLLIDEMASK, e, -1, CUBE_COLLIDE, 0, 0),
+        (24, REQ_VEL, top, -1, 0, 0, -150), (24, REQ_VEL, top, -1, 10, 0, 0),   # two uVel in a tick add up
+    ]
+    return 45, script
+
+
+# builders return ticks, or (ticks, script[, btref step mode]) with script rows (tick, kind, uid, other, a0[, a1, a2])
+# applied before that tick's step; kind = BT_REQ_* (0 uDrop, 1 uDead, 2 uPickup(uid, other, a0), 3 pushBtn(uid, a0), ...)
 LABS = {
     "lab_teleport": lab_teleport,
     "lab_bottles": lab_bottles,
     "lab_seats": lab_seats,
     "lab_crush": lab_crush,
     "lab_logic": lab_logic,
+    "lab_requests": lab_requests,
 }
 
 
@@ -220,14 +251,19 @@ def make(name, verbose=False):
             mode = res[2]
     else:
         ticks = res
+    script = [tuple(r) + (0, 0) if len(r) == 5 else tuple(r) for r in script]   # (tick, kind, uid, other, a0, a1, a2)
     R.lab_crush_log()
     wa = R.export()
     hashes = np.zeros(ticks, dtype=np.uint64)
     crush_order = []
     for t in range(ticks):
-        for (tt, what, uid, other, arg) in script:
+        for row in script:
+            tt, what, uid, other, a0, a1, a2 = row
             if tt == t:
-                R.lab_request(uid, what, other, arg)
+                if what <= 3:
+                    R.lab_request(uid, what, other, a0)
+                else:
+                    R.lab_request3(uid, what, (a0, a1, a2))
         R.step(mode)
         hashes[t] = R.hash()
         for u in R.lab_crush_log():
@@ -236,7 +272,7 @@ def make(name, verbose=False):
     n_final = R.count()[0]
     R.free_world(w)
     extra = {"ref_hashes": hashes, "n_final": np.array([n_final]),
-             "script": np.array(script, dtype=np.int64).reshape(-1, 5), "mode": np.array([mode]),
+             "script": np.array(script, dtype=np.int64).reshape(-1, 7), "mode": np.array([mode]),
              "crush_order": np.array(crush_order, dtype=np.int64).reshape(-1, 2)}
     for k, v in final.a.items():
         extra["final_" + k] = v

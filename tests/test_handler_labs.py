@@ -8,7 +8,7 @@ import pytest
 
 from util import golden_path, load_world
 
-LABS = ["lab_teleport", "lab_bottles", "lab_seats", "lab_crush", "lab_logic"]
+LABS = ["lab_teleport", "lab_bottles", "lab_seats", "lab_crush", "lab_logic", "lab_requests"]
 TICKS = 64  # BT_PHASE_TICKS
 
 
@@ -34,8 +34,8 @@ def _run(name, make, request, step_hash, drain, misc):
     w = make(wa)
     crush = []
     for t in range(len(ref)):
-        for (_, what, uid, other, arg) in script[script[:, 0] == t]:
-            request(w, int(what), int(uid), int(other), int(arg))
+        for (_, what, uid, other, a0, a1, a2) in script[script[:, 0] == t]:
+            request(w, int(what), int(uid), int(other), (int(a0), int(a1), int(a2)))
         assert step_hash(w, phases) == int(ref[t]), (name, t)
         crush += [(t, ev["me_uid"]) for ev in drain(w) if ev["kind"] == 3]
     assert crush == [tuple(int(x) for x in r) for r in extra["crush_order"]], name
@@ -51,7 +51,7 @@ def test_emu_handler_labs(emu, name, shuffle):
         return w.hash()[0]
 
     w = _run(name, lambda wa: emu.EmuWorld(wa, rebuild_every=3, shuffle_seed=shuffle),
-             lambda w, what, uid, other, arg: w.request(what, uid, other, (arg, 0, 0)),
+             lambda w, what, uid, other, a: w.request(what, uid, other, a),
              step_hash, lambda w: w.drain_events(), lambda w: w.export_misc())
     assert w.unsupported() == 0
 
@@ -80,7 +80,7 @@ def test_oracle_handler_labs(oracle_lib, name):
         return w.hash()[0]
 
     _run(name, lambda wa: oracle_lib.create(wa),
-         lambda w, what, uid, other, arg: w.request(what, uid, other, (arg, 0, 0)),
+         lambda w, what, uid, other, a: w.request(what, uid, other, a),
          step_hash, lambda w: [dict(kind=3, me_uid=u) for u in w.crush_log()], lambda w: _desc_misc(w.export()))
 
 
@@ -95,7 +95,7 @@ def test_cuda_handler_labs(bt, name):
         return int(w.hash()[0])
 
     w = _run(name, lambda wa: bt.World(wa),
-             lambda w, what, uid, other, arg: w.apply_requests([(what, 0, uid, other, (arg, 0, 0))]),
+             lambda w, what, uid, other, a: w.apply_requests([(what, 0, uid, other, a)]),
              step_hash, lambda w: w.drain_events(), _cuda_misc)
     assert w.stats()["unsupported_events"] == 0
     w.close()
@@ -221,7 +221,7 @@ def test_cuda_requests_across_batched_worlds(bt):
     """three labs as three worlds of ONE device world, each driven by its own script through one
     bt_world_apply_requests call per tick (requests interleaved across worlds): every world must
     follow its own fixture"""
-    names = ["lab_seats", "lab_logic", "lab_seats"]
+    names = ["lab_seats", "lab_logic", "lab_requests", "lab_seats"]
     loaded = [load_world(golden_path(n)) for n in names]
     w = bt.World(bt.concat_worlds([wa for wa, _ in loaded]))
     ticks = min(len(ex["ref_hashes"]) for _, ex in loaded)
@@ -229,8 +229,8 @@ def test_cuda_requests_across_batched_worlds(bt):
         per_world = []
         for g, (_, ex) in enumerate(loaded):
             sc = ex["script"]
-            per_world.append([(int(what), g, int(uid), int(other), (int(arg), 0, 0))
-                              for (_, what, uid, other, arg) in sc[sc[:, 0] == t]])
+            per_world.append([(int(what), g, int(uid), int(other), (int(a0), int(a1), int(a2)))
+                              for (_, what, uid, other, a0, a1, a2) in sc[sc[:, 0] == t]])
         reqs = []                              # round-robin merge: worlds interleaved, per-world order kept
         for i in range(max(len(p) for p in per_world)):
             reqs += [p[i] for p in per_world if i < len(p)]
