@@ -76,6 +76,8 @@ struct bt_world {
 	bool uid_map_valid;
 	bool small_worlds; /* option "small_worlds": brute-force pair search when every world is small (default on) */
 	bool pdl;       /* programmatic dependent launches in effect */
+	int narrow_threads;
+	int narrow_blocks; /* grid of the grid-stride narrow phase (option "narrow_blocks") */
 	i32 margin_opt; /* option "cache_margin": -1 auto */
 	int pdl_opt;    /* option "pdl": 0 off, 1 on, -1 auto = on unless one big world (decided at upload) */
 	bool ctr_fresh; /* h_flag mirrors the device counters (nothing that can change CT_DEAD_N ran since the last fetch) */
@@ -216,7 +218,7 @@ int bt_world_create(bt_world **out, int device, int32_t max_ents, int32_t max_sl
 	w->device = device;
 	w->cap_ents = max_ents; w->cap_sliders = max_sliders; w->cap_wires = max_wires; w->cap_worlds = max_worlds;
 	w->tree_valid = false; w->deltas_pending = true; w->ticks_since_build = 0; w->full_flush_left = 2; w->scan_flushes_left = 2; w->ctrls_fused = false;
-	w->rebuild_every = 16; w->max_iterations = 100000; w->pair_cache = 1; w->pair_rebuilds = 0; w->pair_overflows = 0; w->seen_pair_builds = 0; w->seen_pair_patches = 0; w->pair_builds_at_tree = 0; w->profiling = false; w->ray_valid = false; w->uid_map_valid = false; w->ctr_fresh = false; w->margin_opt = -1; w->pdl_opt = getenv("BT_NO_PDL") ? 0 : -1; w->pdl = false; /* decided at upload, together with W.pdl */ w->small_worlds = true; w->d_reqs = NULL; w->d_req_starts = NULL; w->reqs_cap = 0; w->any_ticks = w->any_rand = false; w->bad_tick = 0; w->device_ticks = 1;
+	w->rebuild_every = 16; w->max_iterations = 100000; w->pair_cache = 1; w->pair_rebuilds = 0; w->pair_overflows = 0; w->seen_pair_builds = 0; w->seen_pair_patches = 0; w->pair_builds_at_tree = 0; w->profiling = false; w->ray_valid = false; w->uid_map_valid = false; w->ctr_fresh = false; w->margin_opt = -1; w->narrow_blocks = 148 * 8; w->narrow_threads = 256; w->pdl_opt = getenv("BT_NO_PDL") ? 0 : -1; w->pdl = false; /* decided at upload, together with W.pdl */ w->small_worlds = true; w->d_reqs = NULL; w->d_req_starts = NULL; w->reqs_cap = 0; w->any_ticks = w->any_rand = false; w->bad_tick = 0; w->device_ticks = 1;
 	w->h_flag = NULL; w->ev0 = w->ev1 = NULL; w->stream = NULL;
 	*out = w;
 #define TRY(x) do { int _r = (x); if (_r) { bt_world_destroy(w); *out = NULL; return _r; } } while (0)
@@ -285,6 +287,8 @@ int bt_world_set_option(bt_world *w, const char *name, int64_t value) {
 	if (!strcmp(name, "allow_unsupported")) { w->W.lenient = value != 0; return BT_OK; }
 	if (!strcmp(name, "pair_cache")) { w->pair_cache = value != 0; return BT_OK; }
 	if (!strcmp(name, "cache_horizon")) { w->W.horizon = value < 0 ? 0 : (value > 64 ? 64 : (i32)value); return BT_OK; }
+	if (!strcmp(name, "narrow_threads")) { w->narrow_threads = value <= 64 ? 64 : (value <= 128 ? 128 : 256); return BT_OK; }
+	if (!strcmp(name, "narrow_blocks")) { w->narrow_blocks = value < 1 ? 1 : (int)value; return BT_OK; }
 	if (!strcmp(name, "pdl")) {
 		w->pdl_opt = value < 0 ? -1 : (value != 0);
 		w->pdl = w->pdl_opt < 0 ? (w->W.n_worlds > 1 || w->W.n <= (1 << 18)) : w->pdl_opt != 0;
@@ -647,7 +651,7 @@ static int do_physics(bt_world *w, bool gravity) {
 			 * lists for the re-armed entities only -- 2.6x slower per launch at 1 M entities: one
 			 * thread per scanner serialises its 2-5 neighbours' gather chains, one thread per pair
 			 * keeps them all in flight.) */
-			LAUNCH(w, PK_NARROW, k_narrow, 148 * 8, 256, W, 0);
+			LAUNCH(w, PK_NARROW, k_narrow, w->narrow_blocks, w->narrow_threads, W, 0);
 			resolve();
 			if (w->run_ahead) {
 				/* run-ahead: as many further iterations as the previous tick needed, each of which
@@ -656,7 +660,7 @@ static int do_physics(bt_world *w, bool gravity) {
 				int more = (iters_this_tick == 0 ? w->predicted_iters - 1 : 2);
 				for (int k = 0; k < more; k++) {
 					W.iter_id++;
-					LAUNCH(w, PK_NARROW, k_narrow, 148 * 8, 256, W, 1);
+					LAUNCH(w, PK_NARROW, k_narrow, w->narrow_blocks, w->narrow_threads, W, 1);
 					resolve();
 					enq++;
 				}
@@ -1070,7 +1074,7 @@ int bt_world_assign(bt_world *dst, bt_world *src) {
 	rebase(&dst->ray, sizeof(dst->ray), src, dst);
 	dst->tree_valid = src->tree_valid; dst->deltas_pending = src->deltas_pending; dst->any_rules = src->any_rules;
 	dst->full_flush_left = src->full_flush_left; dst->scan_flushes_left = src->scan_flushes_left; dst->ctrls_fused = src->ctrls_fused;
-	dst->uid_map_valid = false; dst->ctr_fresh = false; dst->pdl = src->pdl; dst->pdl_opt = src->pdl_opt; dst->margin_opt = src->margin_opt; dst->small_worlds = src->small_worlds;
+	dst->uid_map_valid = false; dst->ctr_fresh = false; dst->pdl = src->pdl; dst->pdl_opt = src->pdl_opt; dst->margin_opt = src->margin_opt; dst->narrow_blocks = src->narrow_blocks; dst->narrow_threads = src->narrow_threads; dst->small_worlds = src->small_worlds;
 	dst->any_ticks = src->any_ticks; dst->any_rand = src->any_rand; dst->bad_tick = src->bad_tick; dst->device_ticks = src->device_ticks;
 	dst->ticks_since_build = src->ticks_since_build; dst->rebuild_every = src->rebuild_every;
 	dst->max_iterations = src->max_iterations; dst->pair_cache = src->pair_cache;
