@@ -207,3 +207,44 @@ def test_ragged_batch_cuda_vs_oracle(bt, oracle_lib):
     look[np.abs(look).sum(1) == 0] = (0, 0, 64)
     assert np.array_equal(ow.selectcast(origin, look), w.raycast(origin, look))
     w.close()
+
+
+def _two_supporters():
+    """a cube resting symmetrically on two cubes: its two candidate collisions tie in every
+    collisionBetter criterion, the case `order_ties` counts"""
+    wa = tiny_world(4)
+    pos = [(0, 0, 2000), (-450, 0, 0), (450, 0, 0), (0, 0, -900)]    # a floor slab, two blocks side by side, one on top
+    rad = [(3000, 3000, 300), (450, 450, 450), (450, 450, 450), (450, 450, 450)]
+    for i, (p, r) in enumerate(zip(pos, rad)):
+        wa.a["center"][3 * i: 3 * i + 3] = p
+        wa.a["old"][3 * i: 3 * i + 3] = p
+        wa.a["radius"][3 * i: 3 * i + 3] = r
+    wa.a["center"][2] = wa.a["old"][2] = 750             # floor top at z = 450 = bottom of the two blocks
+    wa.a["type_mask"][0] = wa.a["new_type_mask"][0] = 19  # terrain | heavy | weightless
+    wa.a["collide_mask"][0] = wa.a["new_collide_mask"][0] = 0
+    wa.a["handlers"][0] = 1                               # WHOMOVES_ME
+    return wa
+
+
+def test_full_ties_are_counted(oracle_lib, emu):
+    wa = _two_supporters()
+    ow = oracle_lib.create(wa)
+    ew = emu.EmuWorld(wa, rebuild_every=2, shuffle_seed=1)
+    for t in range(12):
+        ow.step(31)
+        ew.step(31)
+        assert ew.hash() == ow.hash(), t
+    assert ow.order_ties() > 0 and ew.order_ties() > 0
+
+
+@pytest.mark.gpu
+def test_full_ties_are_counted_cuda(bt, oracle_lib):
+    wa = _two_supporters()
+    ow = oracle_lib.create(wa)
+    w = bt.World(wa)
+    for t in range(12):
+        ow.step(31)
+        w.step(31)
+        assert [int(x) for x in w.hash()] == ow.hash(), t
+    assert w.stats()["order_ties"] > 0 and int(w.order_ties_per_world()[0]) > 0
+    w.close()
