@@ -38,10 +38,10 @@ static __device__ __forceinline__ void stats_flush(const DevWorld &W, const Loca
  * attribute both instructions are no-ops. */
 /* The instructions sit behind a launch-uniform flag: executed unconditionally they cost the 1 M-entity
  * world 2.3 % even without the launch attribute (the asm is a compiler barrier at every kernel entry). */
-#define PDL_ENTRY() do { if (W.pdl) asm volatile("griddepcontrol.launch_dependents;\ngriddepcontrol.wait;" ::: "memory"); } while (0)
+#define PDL_ENTRY() do { if (W.pdl & 1) asm volatile("griddepcontrol.launch_dependents;\ngriddepcontrol.wait;" ::: "memory"); } while (0)
 /* the two long multi-wave kernels (k_narrow, k_push) only wait: their successor is released when they
  * complete, so that no waiting block holds registers while their last waves run */
-#define PDL_WAIT() do { if (W.pdl) asm volatile("griddepcontrol.wait;" ::: "memory"); } while (0)
+#define PDL_WAIT() do { if (W.pdl & 2) asm volatile("griddepcontrol.wait;" ::: "memory"); } while (0)
 /* kernels without a DevWorld parameter (radix sort passes of the tree build) */
 #define PDL_ENTRY_ALWAYS() asm volatile("griddepcontrol.launch_dependents;\ngriddepcontrol.wait;" ::: "memory")
 #define TID ((i32)(blockIdx.x * blockDim.x + threadIdx.x))

@@ -130,7 +130,8 @@ struct DevWorld {
 	i32 horizon;  /* ticks of undisturbed motion (velocity + gravity) the cached box is stretched ahead by:
 	               * velbox's validity idea (velbox/box.h:32-34), a box in free flight stays covered */
 	i32 patch;    /* incremental pair-list patches allowed (option pair_patch) */
-	i32 pdl;        /* kernels were launched as programmatic dependents: release the successor, wait for the predecessor */
+	i32 pdl;        /* bit 0: the short kernels are launched as programmatic dependents (release the successor, wait for
+	                 * the predecessor); bit 1: so are the two long ones, k_narrow and k_push (they only wait) */
 	i32 small_mode; /* every world holds <= BT_SMALL_WORLD entities: candidate pairs by brute force per world, no tree */
 	i32 patch_shift; /* patch while dirty entities << patch_shift <= leaves, full build beyond */
 

@@ -75,7 +75,8 @@ struct bt_world {
 	std::unordered_map<u64, i32> uid_map; /* (world << 32 | uid) -> slot, built on the first bt_world_apply_requests */
 	bool uid_map_valid;
 	bool small_worlds; /* option "small_worlds": brute-force pair search when every world is small (default on) */
-	bool pdl;       /* programmatic dependent launches in effect */
+	bool pdl;       /* programmatic dependent launches in effect for the short kernels ... */
+	bool pdl_long;  /* ... and for k_narrow / k_push (+ k_push_serial) */
 	int narrow_threads;
 	int narrow_blocks; /* grid of the grid-stride narrow phase (option "narrow_blocks") */
 	i32 margin_opt; /* option "cache_margin": -1 auto */
@@ -125,6 +126,7 @@ template <typename T> static int dalloc(bt_world *w, T **p, size_t count) {
 /* "pdl" auto: measured on single box-stack worlds, dependent launches gain 34 % at 20 k entities, 15 % at
  * 200 k, 8 % at 400 k, 2 % at 700 k and lose 3 % at 1 M */
 #define BT_PDL_MAX_ENTS (3 << 18)
+#define BT_PDL_BIG_WORLD_MODE 1 /* beyond that only the short kernels: +0.1-0.9 % at 1 M, all kernels would lose 3 % */
 
 /* every kernel goes through here; pdl: programmatic dependent launch (see PDL_ENTRY in bt_kernels.cuh) */
 template <typename... KArgs, typename... Args>
@@ -143,12 +145,15 @@ static inline void launch_k(bool pdl, void (*kern)(KArgs...), int grid, int bloc
 	cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
 }
 
+/* the two long kernels (classes narrow and push; k_push_serial rides along) follow pdl_long */
+#define pdl_for(w, cls) (((cls) == PK_NARROW || (cls) == PK_PUSH) ? (w)->pdl_long : (w)->pdl)
+
 /* launch helper: counts launches and, while profiling, brackets each one with events */
 #define LAUNCH(w, cls, kern, grid, block, ...)                                         \
 	do {                                                                               \
 		if ((grid) > 0) {                                                              \
 			if ((w)->profiling) cudaEventRecord((w)->ev0, (w)->stream);                \
-			launch_k((w)->pdl, kern, (grid), (block), (w)->stream, __VA_ARGS__);       \
+			launch_k(pdl_for((w), cls), kern, (grid), (block), (w)->stream, __VA_ARGS__); \
 			(w)->stats.kernel_launches++;                                              \
 			(w)->prof_launches[cls]++;                                                 \
 			if ((w)->profiling) {                                                      \
@@ -177,6 +182,7 @@ static int pairs_wave() {
 	return wave;
 }
 
+static void set_pdl(struct bt_world *w, int n_worlds, long long n_ents);
 extern "C" {
 
 const char *bt_version(void) { return "bittoss_b200 0.1 (sm_100a)"; }
@@ -222,7 +228,7 @@ int bt_world_create(bt_world **out, int device, int32_t max_ents, int32_t max_sl
 	w->device = device;
 	w->cap_ents = max_ents; w->cap_sliders = max_sliders; w->cap_wires = max_wires; w->cap_worlds = max_worlds;
 	w->tree_valid = false; w->deltas_pending = true; w->ticks_since_build = 0; w->full_flush_left = 2; w->scan_flushes_left = 2; w->ctrls_fused = false;
-	w->rebuild_every = 16; w->max_iterations = 100000; w->pair_cache = 1; w->pair_rebuilds = 0; w->pair_overflows = 0; w->seen_pair_builds = 0; w->seen_pair_patches = 0; w->pair_builds_at_tree = 0; w->profiling = false; w->ray_valid = false; w->uid_map_valid = false; w->ctr_fresh = false; w->margin_opt = -1; w->narrow_blocks = 148 * 8; w->narrow_threads = 256; w->pdl_opt = getenv("BT_NO_PDL") ? 0 : -1; w->pdl = false; /* decided at upload, together with W.pdl */ w->small_worlds = true; w->d_reqs = NULL; w->d_req_starts = NULL; w->reqs_cap = 0; w->any_ticks = w->any_rand = false; w->bad_tick = 0; w->device_ticks = 1;
+	w->rebuild_every = 16; w->max_iterations = 100000; w->pair_cache = 1; w->pair_rebuilds = 0; w->pair_overflows = 0; w->seen_pair_builds = 0; w->seen_pair_patches = 0; w->pair_builds_at_tree = 0; w->profiling = false; w->ray_valid = false; w->uid_map_valid = false; w->ctr_fresh = false; w->margin_opt = -1; w->narrow_blocks = 148 * 8; w->narrow_threads = 256; w->pdl_opt = getenv("BT_NO_PDL") ? 0 : -1; w->pdl = false; w->pdl_long = false; /* decided at upload, together with W.pdl */ w->small_worlds = true; w->d_reqs = NULL; w->d_req_starts = NULL; w->reqs_cap = 0; w->any_ticks = w->any_rand = false; w->bad_tick = 0; w->device_ticks = 1;
 	w->h_flag = NULL; w->ev0 = w->ev1 = NULL; w->stream = NULL;
 	*out = w;
 #define TRY(x) do { int _r = (x); if (_r) { bt_world_destroy(w); *out = NULL; return _r; } } while (0)
@@ -294,9 +300,8 @@ int bt_world_set_option(bt_world *w, const char *name, int64_t value) {
 	if (!strcmp(name, "narrow_threads")) { w->narrow_threads = value <= 64 ? 64 : (value <= 128 ? 128 : 256); return BT_OK; }
 	if (!strcmp(name, "narrow_blocks")) { w->narrow_blocks = value < 1 ? 1 : (int)value; return BT_OK; }
 	if (!strcmp(name, "pdl")) {
-		w->pdl_opt = value < 0 ? -1 : (value != 0);
-		w->pdl = w->pdl_opt < 0 ? (w->W.n_worlds > 1 || w->W.n <= BT_PDL_MAX_ENTS) : w->pdl_opt != 0;
-		w->W.pdl = w->pdl ? 1 : 0;
+		w->pdl_opt = value < 0 ? -1 : (int)(value > 3 ? 3 : value);
+		set_pdl(w, w->W.n_worlds, w->W.n);
 		return BT_OK;
 	}
 	if (!strcmp(name, "small_worlds")) { /* takes effect at the next upload */
@@ -329,6 +334,16 @@ template <typename T> static int h2d(bt_world *w, T *dst, const std::vector<T> &
 }
 
 static bool supported(uint32_t mask, int id) { return id < 32 && ((mask >> id) & 1u); }
+/* option "pdl": 0 off, 1 short kernels only, 3 all kernels, -1 auto (all up to BT_PDL_MAX_ENTS entities or when
+ * worlds are batched, short kernels only beyond).  The launch attribute and the instructions in the
+ * kernels always switch together. */
+static void set_pdl(bt_world *w, int n_worlds, long long n_ents) {
+	int mode = w->pdl_opt < 0 ? ((n_worlds > 1 || n_ents <= BT_PDL_MAX_ENTS) ? 3 : BT_PDL_BIG_WORLD_MODE) : w->pdl_opt;
+	w->pdl = (mode & 1) != 0;
+	w->pdl_long = (mode & 2) != 0;
+	w->W.pdl = mode & 3;
+}
+
 extern "C" {
 
 static int raise_cache_invalid(bt_world *w);
@@ -484,8 +499,7 @@ int bt_world_upload(bt_world *w, const bt_world_desc *d) {
 		/* Dependent launches pay when a tick is many short kernels (batched or small worlds: +5-7 %).
 		 * One big world spends its tick in two long kernels; there the resident waiting blocks cost
 		 * 0.1-0.4 % instead (measured A/B on the 1 M-entity world), so "auto" leaves them off. */
-		w->pdl = w->pdl_opt < 0 ? (nw > 1 || n <= BT_PDL_MAX_ENTS) : w->pdl_opt != 0;
-		W.pdl = w->pdl ? 1 : 0; /* the launch attribute and the instructions in the kernels always go together */
+		set_pdl(w, nw, n);
 	}
 	w->any_ticks = any_ticks; w->any_rand = any_rand; w->bad_tick = bad_tick;
 	w->ticks_since_build = 0;
@@ -1078,7 +1092,7 @@ int bt_world_assign(bt_world *dst, bt_world *src) {
 	rebase(&dst->ray, sizeof(dst->ray), src, dst);
 	dst->tree_valid = src->tree_valid; dst->deltas_pending = src->deltas_pending; dst->any_rules = src->any_rules;
 	dst->full_flush_left = src->full_flush_left; dst->scan_flushes_left = src->scan_flushes_left; dst->ctrls_fused = src->ctrls_fused;
-	dst->uid_map_valid = false; dst->ctr_fresh = false; dst->pdl = src->pdl; dst->pdl_opt = src->pdl_opt; dst->margin_opt = src->margin_opt; dst->narrow_blocks = src->narrow_blocks; dst->narrow_threads = src->narrow_threads; dst->small_worlds = src->small_worlds;
+	dst->uid_map_valid = false; dst->ctr_fresh = false; dst->pdl = src->pdl; dst->pdl_long = src->pdl_long; dst->pdl_opt = src->pdl_opt; dst->margin_opt = src->margin_opt; dst->narrow_blocks = src->narrow_blocks; dst->narrow_threads = src->narrow_threads; dst->small_worlds = src->small_worlds;
 	dst->any_ticks = src->any_ticks; dst->any_rand = src->any_rand; dst->bad_tick = src->bad_tick; dst->device_ticks = src->device_ticks;
 	dst->ticks_since_build = src->ticks_since_build; dst->rebuild_every = src->rebuild_every;
 	dst->max_iterations = src->max_iterations; dst->pair_cache = src->pair_cache;

@@ -262,7 +262,8 @@ int bt_world_profile_read(bt_world *w, bt_profile *out, int reset);
  * is stretched ahead by (0); "pair_patch" 0/1 incremental pair-list patches; "patch_shift" patch
  * while dirty << shift <= leaves (4); "run_ahead" 0/1 speculative iterations; "max_iterations";
  * "device_ticks" 0/1 bt_world_tick runs the tick handlers itself when all have device bodies;
- * "pdl" 0/1/-1 programmatic dependent launches (-1 = auto: on unless one big world); "small_worlds" 0/1 brute-force pair search per world
+ * "pdl" programmatic dependent launches: 0 off, 1 short kernels only, 3 all kernels, -1 auto (all
+ * for batched worlds and up to 786 k entities, short kernels only beyond); "small_worlds" 0/1 brute-force pair search per world
  * when every world holds <= 128 entities (read at upload); "narrow_blocks" / "narrow_threads" grid of
  * the narrow phase (148*8 x 256, the measured optimum).
  * "allow_unsupported" 1 = bt_world_upload accepts handler IDs without a device implementation,
