@@ -1,9 +1,11 @@
-""".sav / .itm reader straight into the plain SoA arrays of `bt_world_desc`,
-without the reference's AoS `ent` round trip.  Restates `deserialize` / `deserializeEnt`
+""".sav / .itm reader AND writer straight from / into the plain SoA arrays of `bt_world_desc`
+(SURVEY.md §8f-3), without the reference's AoS `ent` round trip.  Restates `deserialize` / `deserializeEnt`
 (serialize.cpp:277-334, 385-439, format notes :30-44): big-endian int32 stream "gam0".."gam7",
 checksum bytes 128-133, handlers as catalog IDs behind a bitfield.  Host-side plumbing, no
 physics; tests compare it field by field with the reference's own loader on all 17 shipped
-levels.  Players, gamestrings and colours are parsed past but not kept (not on the path)."""
+levels.  `save_sav` restates `serialize` / `serializeEnt` (serialize.cpp:127-212) and is checked byte for
+byte against the reference's own writer.  Players, gamestrings and colours are not on the physics path:
+the reader hands them back in its info dict and the writer passes them through."""
 import struct
 
 import numpy as np
@@ -43,6 +45,12 @@ class _Reader:
         self.i += 1
         return v
 
+    def str(self):  # readStr: length byte + that many bytes
+        ln = self.u8()
+        v = bytes(self.d[self.i: self.i + ln])
+        self.i += ln
+        return v
+
     def check(self, expected):  # checksum serialize.cpp:262-268 (the reference only warns)
         v = self.u8()
         if v != expected:
@@ -78,7 +86,7 @@ def load_sav(path_or_bytes, rand_seed=12345):
             ns += 1
         n_wires = r.i32()
         r.check(130)
-        r.i32()  # colour
+        e["color"] = r.i32()
         btn = r.u8() if version >= 1 else 0
         e["btn_v2"] = [(btn >> k) & 1 for k in range(4)]  # pushBtn: pressed for the coming tick
         e["sliders"] = [0 if (equip_fix and k == 0) else r.i32() for k in range(ns)]
@@ -104,16 +112,16 @@ def load_sav(path_or_bytes, rand_seed=12345):
         e["hold_flags_raw"] = r.i32() if version >= 2 else 0
         ents.append(e)
     n_players = r.i32()
+    players = []
     for _ in range(n_players):
-        r.i32(); r.i32()
-        if version >= 3:
-            r.i32()
+        p = {"color": r.i32(), "revive": r.i32(), "data": r.i32() if version >= 3 else 0, "name": b""}
         if version >= 5:
-            ln = r.u8()
-            r.i += ln
-        r.i32()
-    r.i32()  # rand (only taken over on a full-state load, serialize.cpp:430-432)
+            p["name"] = r.str()
+        p["entity"] = r.i32()
+        players.append(p)
+    rand = r.i32()  # only taken over on a full-state load, serialize.cpp:430-432
     gamerules = r.i32()
+    gamestrings = [r.str() for _ in range(r.u8())] if version >= 6 else []  # serialize.cpp:372-383
 
     ns_total = sum(len(e["sliders"]) for e in ents)
     nw_total = sum(len(e["wires"]) for e in ents)
@@ -163,4 +171,78 @@ def load_sav(path_or_bytes, rand_seed=12345):
     a["root_order"][:n] = -1
     for pos, i in enumerate(reversed(roots)):
         a["root_order"][i] = pos
-    return wa, {"version": version, "gamerules": gamerules, "n_players": n_players}
+    return wa, {"version": version, "gamerules": gamerules, "n_players": n_players, "players": players, "rand": rand,
+                "gamestrings": gamestrings, "colors": [e["color"] for e in ents]}
+
+
+def save_sav(wa, colors=None, players=(), rand=0, gamerules=None, gamestrings=()):
+    """WorldArrays -> the bytes `serialize` (serialize.cpp:187-212) writes for that state: "gam7",
+    entity count, one `serializeEnt` record (:127-173) per entity in index order (= oldest first,
+    the order `enumerateAll` numbers them, :87-93), players, rand, gamerules, gamestrings.
+    Like the reference it writes flushed state only (no pending deltas).  `colors` (render only,
+    not part of bt_world_desc), `players` (dicts as `load_sav` returns them) and `gamestrings`
+    are passed through; entities of ONE world (the format has no world id)."""
+    a, n = wa.a, wa.n
+    if n and int(np.max(a["world_id"][:n])) != int(np.min(a["world_id"][:n])):
+        raise SavError("save_sav writes one world; split the batch first")
+    out = bytearray(b"gam%d" % VERSION)
+    p32 = struct.Struct(">i").pack
+    u32 = struct.Struct(">I").pack
+
+    def wstr(b):  # writeStr serialize.cpp:68-77
+        b = bytes(b)[:255]
+        out.append(len(b))
+        out.extend(b)
+
+    out += p32(n)
+    for i in range(n):
+        out.append(128)
+        for f in ("center", "vel", "radius"):
+            for k in range(3):
+                out += p32(int(a[f][3 * i + k]))
+        out.append(129)
+        s0, s1 = int(a["slider_off"][i]), int(a["slider_off"][i + 1])
+        w0, w1 = int(a["wire_off"][i]), int(a["wire_off"][i + 1])
+        out += p32(s1 - s0)
+        out += u32(int(a["type_mask"][i]) & 0xFFFFFFFF)
+        out += u32(int(a["collide_mask"][i]) & 0xFFFFFFFF)
+        wires = [int(w) for w in a["wire_to"][w0:w1] if 0 <= int(w) < n]
+        out += p32(len(wires))
+        out.append(130)
+        out += p32(int(colors[i]) if colors is not None else 0)
+        out.append(sum(1 << k for k in range(4) if a["btn"][8 * i + k]))  # buttonByte: getButton = btns[k].v
+        for k in range(s0, s1):
+            out += p32(int(a["slider_v"][k]))
+        out.append(131)
+        for w in wires:
+            out += p32(w)
+        out.append(132)
+        at = len(out)
+        out += p32(0)
+        bits = 0
+        for k in range(10):  # processEnt serialize.cpp:30-44: only handlers other than catalog entry 0
+            hid = int(a["handlers"][10 * i + _FILE_TO_SLOT[k]])
+            if hid:
+                out += p32(hid)
+                bits |= 1 << k
+        out.append(133)
+        if int(a["friction"][i]) != DEFAULT_FRICTION:
+            bits |= 1 << 31
+            out += p32(int(a["friction"][i]))
+        out[at: at + 4] = u32(bits)
+        out += p32(int(a["holder"][i]) if 0 <= int(a["holder"][i]) < n else -1)
+        out += p32(int(a["hold_flags"][i]))
+    out += p32(len(players))
+    for p in players:
+        out += p32(p["color"]) + p32(p["revive"]) + p32(p["data"])
+        wstr(p["name"])
+        out += p32(p["entity"])
+    out += p32(int(rand))
+    out += p32(int(a["w_gamerules"][0]) if gamerules is None else int(gamerules))
+    gs = list(gamestrings)
+    while gs and not gs[-1]:
+        gs.pop()  # serializeGamestrings :177-185: up to the last non-empty one
+    out.append(len(gs))
+    for g in gs:
+        wstr(g)
+    return bytes(out)

@@ -77,6 +77,7 @@ class RefLib:
         L.btref_init.argtypes = [C.c_char_p]
         L.btref_load_sav.argtypes = [C.c_char_p, C.c_int, _i32p, C.c_int32]
         L.btref_set_options.argtypes = [C.c_int, C.c_uint32]
+        L.btref_serialize.argtypes = [C.c_char_p, C.c_int]
         L.btref_make_boxstack.argtypes = [C.c_int32, C.c_int32, C.c_uint32, C.c_int32, C.c_int32]
         L.btref_strip_handlers.argtypes = [C.c_int, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32]
         L.btref_kick.argtypes = [C.c_uint32, C.c_int32, C.c_int32]
@@ -170,6 +171,16 @@ class RefLib:
 
     def get_gamerules(self):
         return self.L.btref_get_gamerules()
+
+    def serialize(self):
+        """bytes the reference's own `serialize` writes for the current world"""
+        cap = 1 << 20
+        while True:
+            buf = C.create_string_buffer(cap)
+            n = self.L.btref_serialize(buf, cap)
+            if n <= cap:
+                return buf.raw[:n]
+            cap = n
 
     # -- stepping --
     def step(self, mode=1):

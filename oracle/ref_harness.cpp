@@ -191,6 +191,18 @@ int btref_load_sav(const char *name, int n_players, const int32_t *pdata, int32_
 	return 0;
 }
 
+/* the reference's own writer (serialize.cpp:187-212) on the current world: bytes into `out`, returns
+ * their number (also when it exceeds `cap`: call again with a bigger buffer) */
+int btref_serialize(char *out, int cap) {
+	list<char> data;
+	data.init();
+	serialize(cur->gs, &data);
+	int n = data.num;
+	if (n <= cap) memcpy(out, data.items, n);
+	data.destroy();
+	return n;
+}
+
 void btref_set_options(int spacetrash_on, uint32_t input_key) {
 	cur->spacetrash_on = spacetrash_on;
 	cur->input_key = input_key;
