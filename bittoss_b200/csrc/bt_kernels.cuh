@@ -13,6 +13,9 @@
 #include "bt_phys.cuh"
 
 #define BT_BLOCK 128
+#ifndef BT_NARROW_BATCH
+#define BT_NARROW_BATCH 2 /* pairs whose cheap filter one k_narrow thread runs at once */
+#endif
 
 static __device__ __forceinline__ u32 warp_sum(u32 v) {
 	return __reduce_add_sync(0xffffffffu, v);
@@ -315,8 +318,35 @@ __global__ void __launch_bounds__(256) k_narrow(DevWorld W, int spec) { PDL_WAIT
 	/* k_refit / k_pairs of this iteration have consumed the flag; pushes may raise it again
 	 * (a run-ahead iteration only gets here with the flag down, and other blocks are reading it) */
 	if (!spec && blockIdx.x == 0 && threadIdx.x == 0) bt_consume_cache_flags(W, np);
-	for (u32 p = blockIdx.x * blockDim.x + threadIdx.x; p < np; p += gridDim.x * blockDim.x)
-		t_narrow(W, W.pairs[p], st, any);
+	const u32 stride = gridDim.x * blockDim.x;
+	u32 p = blockIdx.x * blockDim.x + threadIdx.x;
+#if BT_NARROW_BATCH > 1
+	/* The cheap filter (pair word -> needsCollision bytes of both ends: two dependent memory hops
+	 * that most pairs end with after the first iteration) runs on BT_NARROW_BATCH pairs at once, so
+	 * the hops of different pairs overlap; the survivors then go through the narrow phase proper, one
+	 * inlined copy picked by a bit mask.  Proposals are CAS-maxima and the statistics are sums, so
+	 * the order in which a thread visits its pairs is not observable.  Measured on the 1 M world
+	 * (same box, A/B): batch 2 = -2.5 % tick time (k_narrow -5 %), 4 = -1.5 %, 8 = 0 (the heavy
+	 * path of a thread's survivors is serial, so wide batches lengthen its chain). */
+	for (; p + (BT_NARROW_BATCH - 1) * stride < np && p + (BT_NARROW_BATCH - 1) * stride >= p; p += BT_NARROW_BATCH * stride) {
+		u64 q[BT_NARROW_BATCH];
+		u32 m = 0;
+#pragma unroll
+		for (int k = 0; k < BT_NARROW_BATCH; k++) q[k] = W.pairs[p + k * stride];
+#pragma unroll
+		for (int k = 0; k < BT_NARROW_BATCH; k++)
+			m |= (u32)((W.needsCollision[(u32)q[k]] | W.needsCollision[(u32)(q[k] >> 32)]) != 0) << k;
+		while (m) {
+			int k = __ffs(m) - 1;
+			m &= m - 1;
+			u64 qq = q[0];
+#pragma unroll
+			for (int j = 1; j < BT_NARROW_BATCH; j++) qq = k == j ? q[j] : qq;
+			t_narrow(W, qq, st, any);
+		}
+	}
+#endif
+	for (; p < np; p += stride) t_narrow(W, W.pairs[p], st, any);
 	stats_flush(W, st);
 	if (__any_sync(0xffffffffu, any) && (threadIdx.x & 31) == 0) W.ctr[ANY_SLOT(W.iter_id)] = (u32)W.iter_id;
 }

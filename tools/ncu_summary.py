@@ -1,7 +1,8 @@
 """Summarise ncu outputs into profiles/: launch list CSV -> per-kernel totals/shares;
 `--set full` raw CSV -> per-launch table of the metrics that matter for an HBM-bound path.
     python tools/ncu_summary.py launches <launches.csv>
-    python tools/ncu_summary.py full <report.ncu-rep>            (needs ncu on PATH)"""
+    python tools/ncu_summary.py full <report.ncu-rep>            (needs ncu on PATH)
+    python tools/ncu_summary.py grep <report.ncu-rep> <kernel regex> <metric regex>   (any raw-page columns, per launch)"""
 import collections
 import csv
 import json
@@ -58,5 +59,21 @@ def full(rep):
     print(json.dumps({k: {"launches": len(v), "dram_bytes_per_launch": sum(v) / len(v)} for k, v in per.items()}))
 
 
+def grep(rep, kernel_re, metric_re):
+    """every raw-page column whose name matches metric_re, for the launches whose kernel matches kernel_re
+    (what bounds a latency-looking kernel: l1tex / lts throughput %, warp stall reasons per issue)"""
+    import re
+    out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(out.splitlines()))
+    hdr, units = rows[0], rows[1]
+    ki = hdr.index("Kernel Name")
+    cols = [i for i, h in enumerate(hdr) if re.search(metric_re, h)]
+    sel = [r for r in rows[2:] if re.search(kernel_re, r[ki])]
+    print("| metric | unit | " + " | ".join("%s #%d" % (r[ki].split("(")[0], n) for n, r in enumerate(sel)) + " |")
+    print("|---|---|" + "---|" * len(sel))
+    for i in cols:
+        print("| %s | %s | " % (hdr[i], units[i]) + " | ".join(r[i][:10] for r in sel) + " |")
+
+
 if __name__ == "__main__":
-    {"launches": launches, "full": full}[sys.argv[1]](sys.argv[2])
+    {"launches": launches, "full": full, "grep": grep}[sys.argv[1]](*sys.argv[2:])

@@ -23,4 +23,7 @@ w.sync()
 _cu.cuProfilerStop()
 s = w.stats()
 print("ticks", ticks, "launches", s["kernel_launches"], "iterations", s["iterations"], "hash", hex(w.hash()[0]))
+print("warm-up: pair builds", s0["pair_builds"], "pairs cached per build", s0["pairs_cached"] // max(1, s0["pair_builds"]),
+      "| measured: candidate pairs per iteration", s["candidate_pairs"] // max(1, s["iterations"]), "positives per iteration",
+      s["positives"] // max(1, s["iterations"]))
 w.close()
