@@ -13,9 +13,6 @@
 #include "bt_phys.cuh"
 
 #define BT_BLOCK 128
-#ifndef BT_NARROW_CHUNK
-#define BT_NARROW_CHUNK 0 /* trips of k_narrow's cheap filter collected before the queued survivors are processed; 0: off */
-#endif
 #ifndef BT_NARROW_BATCH
 #define BT_NARROW_BATCH 2 /* pairs whose cheap filter one k_narrow thread runs at once */
 #endif
@@ -293,20 +290,14 @@ static __device__ __forceinline__ void queue_push(u32 *q, u32 *count, int pred, 
 	if (pred) q[base + __popc(m & ((1u << lane) - 1))] = item;
 }
 
-static __device__ __forceinline__ void queue_push64(u64 *q, u32 *count, int pred, u64 item) {
-	u32 m = __ballot_sync(0xffffffffu, pred);
-	if (!m) return;
-	int lane = threadIdx.x & 31;
-	u32 base = 0;
-	if (lane == 0) base = atomicAdd(count, (u32)__popc(m));
-	base = __shfl_sync(0xffffffffu, base, 0);
-	if (pred) q[base + __popc(m & ((1u << lane) - 1))] = item;
-}
-
 /* one thread per cached pair, grid-stride so the launch does not need the pair count.
  * (A two-step variant that re-packs the survivors of the cheap tests into full warps was
  * measured 20 % slower here: the step is bound by the latency of its gathers, which the
- * re-packing doubles, not by divergent ALU work.  k_push below does gain from re-packing.) */
+ * re-packing doubles, not by divergent ALU work.  Collecting the survivors of a whole chunk of
+ * trips -- 4 / 8 / 16 -- in a shared-memory queue first and running the narrow phase over the
+ * queue on full warps was measured too: +1 % tick time at 1 M entities, so the cost follows the
+ * number of scanning pairs, not the number of warps that carry them.  k_push below does gain
+ * from re-packing.) */
 /* spec = 1: an iteration enqueued ahead of the host's knowledge (run-ahead).  It proceeds only
  * if the previous iteration proposed something and no push has invalidated the pair cache;
  * otherwise it records its id in CT_STOP and it and everything enqueued behind it stand down. */
@@ -331,43 +322,6 @@ __global__ void __launch_bounds__(256) k_narrow(DevWorld W, int spec) { PDL_WAIT
 	/* k_refit / k_pairs of this iteration have consumed the flag; pushes may raise it again
 	 * (a run-ahead iteration only gets here with the flag down, and other blocks are reading it) */
 	if (!spec && blockIdx.x == 0 && threadIdx.x == 0) bt_consume_cache_flags(W, np);
-#if BT_NARROW_CHUNK > 0
-	/* Two phases per chunk of BT_NARROW_CHUNK x blockDim pairs.  (1) The cheap filter -- pair word ->
-	 * needsCollision of both ends, two dependent memory hops -- for the whole chunk at once (all
-	 * loads of a thread independent); pairs with a scanning end go into a shared-memory queue
-	 * (warp ballot + one shared atomic per warp).  (2) The narrow phase proper over the queue, on
-	 * FULL warps.  After the first iteration only the pairs of the entities pushed last iteration
-	 * scan (about one in four on the box-stack world, evenly spread over the list): without the
-	 * queue every warp of every trip still walks the whole 5-hop dependent chain for its few
-	 * survivors (long-scoreboard stalls at 4 warps per scheduler: profiles/r1_final2_k_narrow_bounds.md);
-	 * with it a block walks the chain once per ~blockDim survivors.  Unlike re-packing within ONE
-	 * trip (measured slower: same number of chains per block, plus a barrier), the queue collects
-	 * over the chunk.  Proposals are CAS-maxima and statistics are sums: visiting order is not
-	 * observable.  The chunk loop is block-uniform (barriers inside). */
-	__shared__ u64 hq[BT_NARROW_CHUNK * 256];
-	__shared__ u32 hqn;
-	const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
-	for (unsigned long long base = (unsigned long long)blockIdx.x * blockDim.x; base < np; base += BT_NARROW_CHUNK * stride) {
-		if (threadIdx.x == 0) hqn = 0;
-		__syncthreads();
-		u64 q[BT_NARROW_CHUNK];
-		u32 need = 0;
-#pragma unroll
-		for (int k = 0; k < BT_NARROW_CHUNK; k++) {
-			unsigned long long pi = base + k * stride + threadIdx.x;
-			q[k] = pi < np ? W.pairs[pi] : ~0ull;
-		}
-#pragma unroll
-		for (int k = 0; k < BT_NARROW_CHUNK; k++)
-			if (q[k] != ~0ull) need |= (u32)((W.needsCollision[(u32)q[k]] | W.needsCollision[(u32)(q[k] >> 32)]) != 0) << k;
-#pragma unroll
-		for (int k = 0; k < BT_NARROW_CHUNK; k++) queue_push64(hq, &hqn, (need >> k) & 1, q[k]);
-		__syncthreads();
-		const u32 nq = hqn;
-		for (u32 i = threadIdx.x; i < nq; i += blockDim.x) t_narrow(W, hq[i], st, any);
-		__syncthreads(); /* everyone has read hqn / the queue before the next chunk resets them */
-	}
-#else
 	const u32 stride = gridDim.x * blockDim.x;
 	u32 p = blockIdx.x * blockDim.x + threadIdx.x;
 #if BT_NARROW_BATCH > 1
@@ -397,7 +351,6 @@ __global__ void __launch_bounds__(256) k_narrow(DevWorld W, int spec) { PDL_WAIT
 	}
 #endif
 	for (; p < np; p += stride) t_narrow(W, W.pairs[p], st, any);
-#endif
 	stats_flush(W, st);
 	if (__any_sync(0xffffffffu, any) && (threadIdx.x & 31) == 0) W.ctr[ANY_SLOT(W.iter_id)] = (u32)W.iter_id;
 }
