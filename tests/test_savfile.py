@@ -84,3 +84,35 @@ def test_sav_write_read_round_trip(name):
         if k == "btn":
             continue  # a file carries one button byte: it loads as "pressed next tick" (v2), is written from v
         assert np.array_equal(a[k], b[k]), k
+
+
+def test_sav_writer_refuses_a_batch_and_keeps_passthrough_fields():
+    """the format has no world id: a batched desc must be split first; colours, players, rand and
+    gamestrings handed to the writer come back from the reader unchanged"""
+    from bittoss_b200.capi import concat_worlds
+    from bittoss_b200.desc import WorldArrays
+    from bittoss_b200.savfile import SavError, load_sav, save_sav
+    one = WorldArrays(2, 1, 1, 1)
+    a = one.a
+    a["uid"][:2] = (0, 1)
+    a["center"][:6] = (1, 2, 3, -4, -5, -6)
+    a["radius"][:6] = 100
+    a["holder"][:2] = -1
+    a["holdee_head"][:2] = -1
+    a["holdee_next"][:2] = -1
+    a["new_holder"][:2] = -1
+    a["friction"][:2] = (16, 3)
+    a["slider_off"][:3] = (0, 1, 1)
+    a["slider_v"][0] = 77
+    a["wire_off"][:3] = (0, 0, 1)
+    a["wire_to"][0] = 0
+    a["handlers"][10 + 4] = 5  # entity 1: push handler id 5 (file position 4)
+    players = [{"color": 0x112233, "revive": 9, "data": 4, "name": b"ann", "entity": 1}]
+    data = save_sav(one, colors=[7, -8], players=players, rand=424242, gamerules=12, gamestrings=[b"hello", b"", b"x", b""])
+    wb, info = load_sav(data)
+    assert info["colors"] == [7, -8] and info["players"] == players and info["rand"] == 424242
+    assert info["gamerules"] == 12 and info["gamestrings"] == [b"hello", b"", b"x"]
+    assert list(wb.a["center"][:6]) == [1, 2, 3, -4, -5, -6] and list(wb.a["friction"][:2]) == [16, 3]
+    assert wb.a["slider_v"][0] == 77 and wb.a["wire_to"][0] == 0 and wb.a["handlers"][10 + 4] == 5
+    with pytest.raises(SavError):
+        save_sav(concat_worlds([one, one]))
