@@ -41,12 +41,12 @@ class ClockSampler:
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        self.index, self.rows, self.p = index, [], None
+        self.index, self.rows, self.p, self.first = index, [], None, 0
 
     def start(self):
         try:
             self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                       "--format=csv,noheader,nounits", "-lms", "100"],
+                                       "--format=csv,noheader,nounits", "-lms", "50"],
                                       stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -57,6 +57,14 @@ class ClockSampler:
         for line in self.p.stdout:
             self.rows.append([x.strip() for x in line.split(",")])
 
+    def mark(self):
+        """rows read so far were taken before the load of interest began (nvidia-smi needs a few
+        hundred ms to start: it is launched ahead of the timed region and the early rows dropped)"""
+        self.first = len(self.rows)
+
+    def since_mark(self):
+        return len(self.rows) - self.first
+
     def stop(self):
         if not self.p:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
@@ -65,7 +73,7 @@ class ClockSampler:
         self.t.join(timeout=2)
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        for r in self.rows[self.first:]:
             try:
                 sm.append(float(r[0])); mx.append(float(r[1]))
             except (ValueError, IndexError):
@@ -160,16 +168,36 @@ def run_cuda(args):
     settle_ms = w.tick_timed(args.settle) if args.settle > 0 else 0.0
     settle_stats = w.stats(reset=True)
     # ---- (1) device-resident throughput: `value` ----
+    sampler = ClockSampler(local_rank)
+    sampler.start()  # ahead of the warm-up, so that nvidia-smi is already reporting when the timed region begins
     w.tick(args.warmup)
     w.stats(reset=True)
-    sampler = ClockSampler(local_rank)
     barrier()
-    sampler.start()
+    sampler.mark()
     ms = w.tick_timed(args.steps)
     barrier()
-    clocks = sampler.stop()
     st = w.stats()
     h_final = w.hash()[0]
+    # K ticks of 0.8 ms are over before nvidia-smi's next sample: when the timed region was shorter than
+    # 0.6 s the SAME ticks keep running, untimed, right behind it until the sampler has 8 readings under that
+    # load (3 s at most; value / ms_per_step are already fixed; the state hash above was taken before)
+    in_region = sampler.since_mark()
+    clock_window = "timed region"
+    try:
+        if ms < 600.0 and sampler.p:
+            per_tick = max(ms / max(1, args.steps), 1e-3)
+            chunk = int(min(1000, max(1, 100.0 / per_tick)))  # about 100 ms of ticks at a time
+            extra, t_end = 0, time.perf_counter() + 3.0
+            while sampler.since_mark() < 8 and time.perf_counter() < t_end:
+                w.tick(chunk)
+                w.sync()
+                extra += chunk
+            clock_window = "timed region (%.0f ms) + %d untimed ticks of the same world right behind it" % (ms, extra)
+    except Exception as e:  # never let the clock evidence take the measurement down
+        clock_window = "timed region (extension failed: %s)" % e
+    clocks = sampler.stop()
+    clocks["samples_in_timed_region"] = in_region
+    clocks["window"] = clock_window
     from bittoss_b200.parallel import gather_hashes, reduce_time_and_work, shard_range
     assert shard_range(world_size, rank, world_size) == (rank, rank + 1)  # one whole world per rank
     ms_max, et_sum = reduce_time_and_work(ms, float(st["entity_ticks"]), device="cuda")
