@@ -68,6 +68,7 @@ __global__ void __launch_bounds__(BT_BLOCK) k_flush_scan(DevWorld W) { PDL_ENTRY
  * handled, so the result equals the sequential walk. */
 __global__ void __launch_bounds__(BT_BLOCK) k_flush_serial(DevWorld W) { PDL_ENTRY();
 	LocalStats st = {0, 0, 0, 0, 0};
+	st.rk_ordered = 1; /* fumbles of this launch take their place in gs->rootEnts from the world's counter */
 	const int lane = threadIdx.x & 31;
 	const i32 g = TID >> 5;
 	if (g < W.n_worlds) {
@@ -76,19 +77,19 @@ __global__ void __launch_bounds__(BT_BLOCK) k_flush_serial(DevWorld W) { PDL_ENT
 			W.flip[g] ^= 1;
 			work = W.wflush[g];
 			W.wflush[g] = 0;
+			W.wrootseq[g] = 0;
 		}
 		work = __shfl_sync(0xffffffffu, work, 0);
 		if (work) {
 			const int slot = 1 ^ __shfl_sync(0xffffffffu, lane == 0 ? W.flip[g] : 0, 0);
 			const i32 b0 = W.wbegin[g], b1 = W.wend[g];
-			for (int pass = 0; pass < 3; pass++) {
+			for (int pass = 0; pass < 2; pass++) {
 				for (i32 top = b1 - 1; top >= b0; top -= 32) {
 					const i32 i = top - lane; /* lane 0 = newest */
 					int hit = 0;
 					if (i >= b0 && W.inList[i]) {
 						if (pass == 0) hit = (slot ? W.dead_max1[i] : W.dead_max0[i]) != 0;
-						else if (pass == 1) hit = W.newDrop[i] != 0;
-						else hit = W.holder[i] < 0 && W.newHolder[i] >= 0;
+						else hit = W.newDrop[i] != 0;
 					}
 					u32 m = __ballot_sync(0xffffffffu, hit);
 					while (m) {
@@ -99,18 +100,35 @@ __global__ void __launch_bounds__(BT_BLOCK) k_flush_serial(DevWorld W) { PDL_ENT
 								u8 d = slot ? W.dead_max1[i] : W.dead_max0[i];
 								bt_crush(W, i, 0xfffffu - ((u32)i & 0xfffffu), st, d);
 								W.dead[i] = d;
-							} else if (pass == 1) { /* flushDrops :765-773 */
+							} else { /* flushDrops :765-773 */
 								W.newDrop[i] = 0;
 								bt_fumble(W, i, st);
-							} else if (W.holder[i] < 0) { /* flushPickups :775-792 */
-								i32 x = W.newHolder[i];
-								if (W.holdRoot[x] != i && !W.dead[x]) bt_pickup(W, x, i, W.newHoldFlags[i]);
-								W.newHolder[i] = -1;
 							}
 						}
 						__syncwarp();
 					}
 				}
+				__syncwarp();
+			}
+			/* flushPickups ent.cpp:775-792 walks gs->rootEnts head first = descending rootKey: the lanes
+			 * look for the requesting root with the largest key, lane 0 serves it, until none is left
+			 * (normally the first look finds none) */
+			while (1) {
+				u64 bk = 0;
+				i32 bi = -1;
+				for (i32 i = b0 + lane; i < b1; i += 32) {
+					if (!W.inList[i] || W.holder[i] >= 0 || W.newHolder[i] < 0) continue;
+					const u64 k = W.rootKey[i];
+					if (bi < 0 || k > bk) { bk = k; bi = i; }
+				}
+#pragma unroll
+				for (int off = 16; off > 0; off >>= 1) {
+					const u64 ok = __shfl_xor_sync(0xffffffffu, bk, off);
+					const i32 oi = __shfl_xor_sync(0xffffffffu, bi, off);
+					if (oi >= 0 && (bi < 0 || ok > bk || (ok == bk && oi > bi))) { bk = ok; bi = oi; }
+				}
+				if (bi < 0) break;
+				if (lane == 0) bt_flush_pickup_one(W, bi);
 				__syncwarp();
 			}
 		}
@@ -411,11 +429,22 @@ __global__ void __launch_bounds__(BT_BLOCK) k_pack_state(DevWorld W, i32 *oc, i3
 	ov[3 * r] = v.x; ov[3 * r + 1] = v.y; ov[3 * r + 2] = v.z;
 }
 
+__global__ void __launch_bounds__(BT_BLOCK) k_poke_raw(DevWorld W, DevArrays A, const bt_poke *pk, i32 n) { PDL_ENTRY(); t_poke_raw(W, A, pk, TID, n); }
+__global__ void k_poke_ops(DevWorld W, const bt_poke *ops, i32 n) { PDL_ENTRY();
+	if (threadIdx.x != 0 || blockIdx.x != 0) return;
+	for (i32 k = 0; k < n; k++) t_poke_op(W, ops[k]);
+}
+/* bt_world_grow: blank slots [first, first + cnt) */
+__global__ void __launch_bounds__(BT_BLOCK) k_grow_init(DevWorld W, i32 first, i32 cnt, i32 world) { PDL_ENTRY();
+	if (TID >= cnt) return;
+	t_grow_init(W, first + TID, world);
+}
+
 /* per-world commutative hash: warp-level pre-reduction when the whole warp is one world */
-__global__ void __launch_bounds__(BT_BLOCK) k_hash(DevWorld W, u64 *sum, u32 *cnt) { PDL_ENTRY();
+__global__ void __launch_bounds__(BT_BLOCK) k_hash(DevWorld W, u64 *sum, u32 *cnt, int full) { PDL_ENTRY();
 	i32 e = TID;
 	int live = e < W.n && W.inList[e];
-	u64 h = live ? bt_ent_hash(W, e) : 0;
+	u64 h = live ? (full ? bt_ent_hash_full(W, e) : bt_ent_hash(W, e)) : 0;
 	i32 g = live ? W.world[e] : -1;
 	i32 g0 = __shfl_sync(0xffffffffu, g, 0);
 	int uniform = __all_sync(0xffffffffu, g == g0 || g < 0);

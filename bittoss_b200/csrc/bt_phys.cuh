@@ -60,7 +60,15 @@ static BT_HD void bt_prefetch(const void *p) { asm volatile("prefetch.global.L1 
 
 struct LocalStats {
 	u32 cand, pos, push, crush, fumble;
+	/* where the next fumble of this thread puts the new root in gs->rootEnts order (see bt_fumble):
+	 * rk_ordered = 0: rk_base | rk_local++ (a push: base = phase, pushing root); 1: phase | the world's counter */
+	u32 rk_ordered, rk_local;
+	u64 rk_base;
 };
+#define BT_ROOTKEY_SHIFT 37
+static BT_HD u64 bt_push_rootkey(const DevWorld &W, i32 root) {
+	return ((u64)(u32)W.root_phase << BT_ROOTKEY_SHIFT) | ((u64)(u32)(BT_MAX_ENTS - 1 - root) << 8);
+}
 
 static BT_HD void bt_check_cover(const DevWorld &W, i32 e, const int4 &o, const int4 &c);
 static BT_HD void bt_upickup(const DevWorld &W, i32 p, i32 e, i32 holdFlags);
@@ -196,17 +204,54 @@ static BT_HD int bt_player_push(const DevWorld &W, i32 me, i32 him) {
 
 /* uWire / uUnwire entUpdaters.c:66-73: one pending request of each kind per entity and flush
  * (a seat wires / unwires its single rider); a second, different one cannot be represented */
+/* The pending lists e->wiresAdd / e->wiresRm (ent.h:121-122): almost always empty or one entry, kept in
+ * the word itself; a second, different target moves the list into the pool (request order kept; a repeated
+ * target is dropped, flushMisc would skip it anyway: `if (!e->wires.has(w))`, ent.cpp:695-697). */
+static BT_HD void bt_wq_append(const DevWorld &W, i32 e, i32 *slot, i32 w, int kind) {
+	i32 v = *slot;
+	if (v == -1) { *slot = w; return; }
+	if (v >= 0) {
+		if (v == w) return;
+		u32 a = bt_add32(&W.ctr[CT_WQ_N], 2u);
+		if ((i32)a + 2 > W.wq_cap) { bt_unsup(W, e, 5, kind); return; }
+		W.wq_to[a] = v; W.wq_next[a] = (i32)a + 1;
+		W.wq_to[a + 1] = w; W.wq_next[a + 1] = -1;
+		*slot = -2 - (i32)a;
+		return;
+	}
+	i32 h = -2 - v;
+	while (1) {
+		if (W.wq_to[h] == w) return;
+		if (W.wq_next[h] < 0) break;
+		h = W.wq_next[h];
+	}
+	u32 a = bt_add32(&W.ctr[CT_WQ_N], 1u);
+	if ((i32)a + 1 > W.wq_cap) { bt_unsup(W, e, 5, kind); return; }
+	W.wq_to[a] = w; W.wq_next[a] = -1;
+	W.wq_next[h] = (i32)a;
+}
 static BT_HD void bt_uwire(const DevWorld &W, i32 e, i32 w) {
 	W.fullFlush[e] = 1;
 	W.ctr[CT_FLUSH_HINT] = 1;
-	if (W.wireAdd[e] >= 0 && W.wireAdd[e] != w) bt_unsup(W, e, 5, 0);
-	W.wireAdd[e] = w;
+	bt_wq_append(W, e, &W.wireAdd[e], w, 0);
 }
 static BT_HD void bt_uunwire(const DevWorld &W, i32 e, i32 w) {
 	W.ctr[CT_FLUSH_HINT] = 1;
-	if (W.wireRm[e] >= 0 && W.wireRm[e] != w) bt_unsup(W, e, 5, 1);
-	W.wireRm[e] = w;
+	bt_wq_append(W, e, &W.wireRm[e], w, 1);
 }
+/* walk a pending list in request order: BT_WQ_FOR(W, word, t) { ... t ... } */
+static BT_HD i32 bt_wq_first(const DevWorld &W, i32 word, i32 &h) {
+	h = -1;
+	if (word >= -1) return word;
+	h = -2 - word;
+	return W.wq_to[h];
+}
+static BT_HD i32 bt_wq_next(const DevWorld &W, i32 &h) {
+	if (h < 0) return -1;
+	h = W.wq_next[h];
+	return h >= 0 ? W.wq_to[h] : -1;
+}
+#define BT_WQ_FOR(W, word, t) for (i32 _h, t = bt_wq_first(W, word, _h); t >= 0; t = bt_wq_next(W, _h))
 
 /* teleport_push teleport.c:12-37.  Serial lane only.  It reads the pad's and the destination's
  * position while other pushes of the same iteration may move them; the reference interleaves
@@ -449,6 +494,17 @@ static BT_HD void bt_fumble(const DevWorld &W, i32 h, LocalStats &st) {
 	W.LLn[h] = -1;
 	W.LLp[h] = -1;
 	BT_FOR_SUBTREE(W, h, it, W.holdRoot[it] = h); /* recursiveHoldRoot ent.cpp:39-45 */
+	/* addRootEnt ent.cpp:60-66 prepends to gs->rootEnts: the newest root gets the largest key.  Inside one
+	 * launch: the ordered lane (flush1) counts per world; pushes order by canonical push order (descending
+	 * root), then by the fumbles of that one push. */
+	if (st.rk_ordered) {
+		W.rootKey[h] = ((u64)(u32)W.root_phase << BT_ROOTKEY_SHIFT) | (u64)bt_add32(&W.wrootseq[W.world[h]], 1u);
+	} else {
+		if (st.rk_local > 255u) bt_unsup(W, h, 8, 0); /* > 256 fumbles by one push: their mutual order is lost */
+		W.rootKey[h] = st.rk_base | (u64)(st.rk_local > 255u ? 255u : st.rk_local);
+		st.rk_local++;
+	}
+	bt_add32(&W.ctr[CT_TREE_EDITS], 1u);
 }
 
 /* killEntNoHandlers ent.cpp:190-208 + crushEnt :211-217.  The dead list replaces
@@ -461,6 +517,7 @@ static BT_HD void bt_crush(const DevWorld &W, i32 e, u32 key, LocalStats &st, in
 	W.inList[e] = 0;
 	W.hasBox[e] = 0;
 	W.dead[e] = 1;
+	bt_add32(&W.ctr[CT_TREE_EDITS], 1u);
 	W.ctr[CT_FLUSH_HINT] = 1; /* wires that point at it must go (flushMisc ent.cpp:706-712) */
 	int cid = (int)((W.hphys[e] >> 24) & 0xff);
 	if (cid > 2) bt_unsup(W, e, 3, cid);
@@ -1350,6 +1407,7 @@ static BT_HD void bt_pickup(const DevWorld &W, i32 x, i32 y, i32 holdFlags) {
 	i32 r = W.holdRoot[x];
 	BT_FOR_SUBTREE(W, y, it, W.holdRoot[it] = r);
 	W.holdFlags[y] = HOLD_MASK & holdFlags;
+	bt_add32(&W.ctr[CT_TREE_EDITS], 1u);
 	if (holdFlags & HOLD_FREEZE) {
 		int4 vx = W.vel[x], vy = W.vel[y];
 		W.d_vel[y] = make_int4(vx.x - vy.x, vx.y - vy.y, vx.z - vy.z, 0);
@@ -1456,6 +1514,7 @@ static BT_HD void t_push(const DevWorld &W, i32 e, LocalStats &st) {
 			return;
 		}
 	}
+	st.rk_ordered = 0; st.rk_local = 0; st.rk_base = bt_push_rootkey(W, e);
 	bt_push(W, bt_unpack_coll(W.pend[e]), bt_push_key(W, e), st);
 }
 
@@ -1471,6 +1530,7 @@ static BT_HD void t_push_serial(const DevWorld &W, LocalStats &st) {
 	}
 	for (i32 i = 0; i < n; i++) {
 		i32 e = W.serialList[i];
+		st.rk_ordered = 0; st.rk_local = 0; st.rk_base = bt_push_rootkey(W, e);
 		bt_push(W, bt_unpack_coll(W.pend[e]), bt_push_key(W, e), st);
 	}
 	W.ctr[CT_SERIAL_N] = 0;
@@ -1706,6 +1766,12 @@ static BT_HD void t_flush_scan(const DevWorld &W, i32 e) {
 	}
 }
 
+static BT_HD void bt_flush_pickup_one(const DevWorld &W, i32 i) {
+	i32 x = W.newHolder[i];
+	if (W.holdRoot[x] != i && !W.dead[x]) bt_pickup(W, x, i, W.newHoldFlags[i]);
+	W.newHolder[i] = -1;
+}
+
 /* flush1 ent.cpp:794-802, serial part, one thread per world: flushDeaths :747-761,
  * flushDrops :765-773, flushPickups :775-792.  Worlds with nothing pending (wflush) return at once. */
 static BT_HD void t_flush_serial(const DevWorld &W, i32 g, LocalStats &st) {
@@ -1713,6 +1779,8 @@ static BT_HD void t_flush_serial(const DevWorld &W, i32 g, LocalStats &st) {
 	W.flip[g] ^= 1;
 	if (!W.wflush[g]) return;
 	W.wflush[g] = 0;
+	W.wrootseq[g] = 0;
+	st.rk_ordered = 1;
 	int slot = 1 ^ W.flip[g];
 	for (i32 i = W.wend[g] - 1; i >= W.wbegin[g]; i--) {
 		if (!W.inList[i]) continue;
@@ -1729,15 +1797,17 @@ static BT_HD void t_flush_serial(const DevWorld &W, i32 g, LocalStats &st) {
 			bt_fumble(W, i, st);
 		}
 	}
-	/* flushPickups ent.cpp:775-792.  The reference walks gs->rootEnts (newest root first); there
-	 * is no such list here, the walk is newest entity first, which is the same order unless a
-	 * fumble re-rooted an older entity this tick (only observable for mutual pickup requests) */
-	for (i32 i = W.wend[g] - 1; i >= W.wbegin[g]; i--) {
-		if (!W.inList[i] || W.holder[i] >= 0) continue;
-		i32 x = W.newHolder[i];
-		if (x < 0) continue;
-		if (W.holdRoot[x] != i && !W.dead[x]) bt_pickup(W, x, i, W.newHoldFlags[i]);
-		W.newHolder[i] = -1;
+	/* flushPickups ent.cpp:775-792 walks gs->rootEnts, head first = descending rootKey.  Each root with a
+	 * request is visited once (its request is cleared), nothing visited adds a root or a request. */
+	while (1) {
+		i32 best = -1;
+		u64 bk = 0;
+		for (i32 i = W.wbegin[g]; i < W.wend[g]; i++) {
+			if (!W.inList[i] || W.holder[i] >= 0 || W.newHolder[i] < 0) continue;
+			if (best < 0 || W.rootKey[i] > bk) { best = i; bk = W.rootKey[i]; }
+		}
+		if (best < 0) break;
+		bt_flush_pickup_one(W, best);
 	}
 }
 
@@ -1764,27 +1834,31 @@ static BT_HD void t_flush_misc(const DevWorld &W, i32 e) {
 			if (nb && !W.hasBox[e]) W.ctr[CT_NEED_REBUILD] = 1;
 			W.hasBox[e] = nb;
 		}
-		i32 add = W.wireAdd[e];
-		if (add >= 0) { /* wiresAdd ent.cpp:694-698 */
+		const i32 addw = W.wireAdd[e];
+		if (addw != -1) { /* wiresAdd ent.cpp:694-698, in request order */
 			W.wireAdd[e] = -1;
-			i32 b0 = W.wire_off[e], c0 = W.wire_cnt[e];
-			int has = 0;
-			for (i32 i = 0; i < c0; i++) has |= W.wire_to[b0 + i] == add;
-			if (!has) {
-				if (b0 + c0 < W.wire_off[e + 1]) { W.wire_to[b0 + c0] = add; W.wire_cnt[e] = c0 + 1; }
+			const i32 b0 = W.wire_off[e];
+			BT_WQ_FOR(W, addw, add) {
+				i32 c0 = W.wire_cnt[e];
+				int has = 0;
+				for (i32 i = 0; i < c0; i++) has |= W.wire_to[b0 + i] == add;
+				if (has) continue;
+				if (c0 < W.wire_cap[e]) { W.wire_to[b0 + c0] = add; W.wire_cnt[e] = c0 + 1; }
 				else W.ctr[CT_ERROR] = (u32)(-BT_ERR_CAPACITY);
 			}
 		}
 	}
-	i32 rm = W.wireRm[e];
-	if (rm >= 0) W.wireRm[e] = -1;
+	const i32 rmw = W.wireRm[e];
+	if (rmw != -1) W.wireRm[e] = -1;
 	const i32 cnt0 = W.wire_cnt[e];
 	if (!cnt0) return; /* most entities have no wires: nothing to clean, nothing to write */
 	i32 base = W.wire_off[e];
 	i32 cnt = cnt0;
 	for (i32 i = 0; i < cnt; i++) {
 		i32 x = W.wire_to[base + i];
-		if (W.dead[x] || x == rm) { /* quickRmAt: pull the last wire into this place (list.h) */
+		int gone = W.dead[x];
+		if (!gone && rmw != -1) BT_WQ_FOR(W, rmw, rm) gone |= rm == x;
+		if (gone) { /* quickRmAt: pull the last wire into this place (list.h) */
 			W.wire_to[base + i] = W.wire_to[base + (--cnt)];
 			i--;
 		}
@@ -1923,6 +1997,117 @@ static BT_HD u64 bt_ent_hash(const DevWorld &W, i32 e) {
 	              hd >= 0 && W.inList[hd] ? W.uid[hd] : -1, W.holdFlags[e]};
 	u64 h = bt_mix64((u64)(u32)W.uid[e] + 0x9E3779B97F4A7C15ULL);
 	for (int k = 0; k < 10; k++) h = bt_mix64(h + (u64)(u32)wd[k] + 0x9E3779B97F4A7C15ULL);
+	return h;
+}
+
+
+/* ------------------------------------------------------------------------- */
+/* incremental host binding (bt_world_poke): sparse writes of what HOST code changed on its own
+ * `ent`s since the last exchange. */
+struct DevArrays { /* BT_A_* -> base pointer, bytes per element, ints written by a poke */
+	void *base[BT_A_NUM];
+};
+#define BT_OP_REBOX 99 /* internal: a direct typeMask / collideMask write landed on this slot, the box follows (ent.cpp:75-89) */
+/* step 1, one thread per poke: the raw array writes (no two pokes name the same element) */
+static BT_HD void t_poke_raw(const DevWorld &W, const DevArrays &A, const bt_poke *pk, i32 t, i32 n) {
+	if (t >= n) return;
+	const bt_poke p = pk[t];
+	const i32 e = p.index;
+	if (p.array < 0 || p.array >= BT_A_NUM) return; /* an operation: step 2 */
+	switch (p.array) {
+	case BT_A_CENTER: case BT_A_VEL: case BT_A_OLD: case BT_A_DCENTER: case BT_A_DVEL: case BT_A_RADIUS:
+		((int4 *)A.base[p.array])[e] = make_int4(p.v[0], p.v[1], p.v[2], 0);
+		if (p.array == BT_A_DCENTER || p.array == BT_A_DVEL) W.ctr[CT_ANY_DELTA] = 1;
+		break;
+	case BT_A_NEWDROP: case BT_A_DEADMAX0: case BT_A_DEADMAX1: case BT_A_FULLFLUSH: case BT_A_DEAD: case BT_A_INLIST:
+		((u8 *)A.base[p.array])[e] = (u8)p.v[0];
+		W.ctr[CT_FLUSH_HINT] = 1;
+		break;
+	case BT_A_ROOTKEY:
+		W.rootKey[e] = (u64)(u32)p.v[0] | ((u64)(u32)p.v[1] << 32);
+		break;
+	case BT_A_DEADLIST:
+		W.ctr[CT_ERROR] = (u32)(-BT_ERR_ARG);
+		break;
+	default: /* every other array has 4-byte elements */
+		((i32 *)A.base[p.array])[e] = p.v[0];
+		if (p.array == BT_A_SMIN || p.array == BT_A_SMAX || p.array == BT_A_NEWHOLDER) W.ctr[CT_FLUSH_HINT] = 1;
+		break;
+	}
+}
+/* step 2, one thread, in the order given: the operations */
+static BT_HD void t_poke_op(const DevWorld &W, const bt_poke &p) {
+	const i32 e = p.index;
+	switch (p.array) {
+	case BT_OP_SPAWN: /* addEnt ent.cpp:107-113 */
+		W.inList[e] = 1;
+		W.dead[e] = 0;
+		W.hasBox[e] = (u8)bt_needs_box(W.type[e], W.collide[e]);
+		if (W.hasBox[e]) W.ctr[CT_NEED_REBUILD] = 1;
+		W.needsCollision[e] = 0;
+		W.pend[e] = 0; W.ready[e] = 0; W.forced[e] = 0;
+		W.forcedHoldees[e] = make_int4(-1, -1, -1, 0);
+		bt_add32(&W.ctr[CT_TREE_EDITS], 1u);
+		break;
+	case BT_OP_REBOX:
+		if (W.inList[e]) {
+			u8 nb = (u8)bt_needs_box(W.type[e], W.collide[e]);
+			if (nb && !W.hasBox[e]) W.ctr[CT_NEED_REBUILD] = 1;
+			W.hasBox[e] = nb;
+		}
+		break;
+	case BT_OP_UWIRE: bt_uwire(W, e, p.v[0]); break;
+	case BT_OP_UUNWIRE: bt_uunwire(W, e, p.v[0]); break;
+	default: W.ctr[CT_ERROR] = (u32)(-BT_ERR_ARG); break;
+	}
+}
+
+/* bt_world_grow: one blank slot (out of the world until BT_OP_SPAWN) */
+static BT_HD void t_grow_init(const DevWorld &W, i32 e, i32 world) {
+	const int4 z = make_int4(0, 0, 0, 0);
+	W.world[e] = world; W.uid[e] = -1;
+	W.center[e] = z; W.old[e] = z; W.vel[e] = z; W.radius[e] = z; W.d_center[e] = z; W.d_vel[e] = z;
+	W.type[e] = 0; W.collide[e] = 0; W.ntype[e] = 0; W.ncollide[e] = 0;
+	W.friction[e] = 0; W.holder[e] = -1; W.holdFlags[e] = 0; W.holdRoot[e] = e; W.holdee[e] = -1;
+	W.LLn[e] = -1; W.LLp[e] = -1; W.newHolder[e] = -1; W.newHoldFlags[e] = 0;
+	W.hphys[e] = 0; W.hpair[e] = 0; W.htick[e] = 0; W.btn_v[e] = 0; W.btn_v2[e] = 0;
+	W.newDrop[e] = 0; W.dead_max0[e] = 0; W.dead_max1[e] = 0; W.fullFlush[e] = 0; W.dead[e] = 0; W.inList[e] = 0;
+	W.needsCollision[e] = 0; W.hasBox[e] = 0; W.ready[e] = 0; W.forced[e] = 0;
+	W.forcedHoldees[e] = make_int4(-1, -1, -1, 0); W.pend[e] = 0;
+	W.wire_cnt[e] = 0; W.wireAdd[e] = -1; W.wireRm[e] = -1; W.rootKey[e] = 0;
+	W.dirtyStamp[e] = 0; W.nodeCount[e] = 0; W.leafOf[e] = 0;
+	Box6 b;
+	b.lo = make_int4(INT32_MAX, INT32_MAX, INT32_MAX, 0); b.hi = make_int4(INT32_MIN, INT32_MIN, INT32_MIN, 0);
+	W.ibox[e] = b; W.iboxOld[e] = b;
+}
+
+/* bt_world_hash_full (include/bittoss_b200.h): everything serialize() writes (serialize.cpp:119-164) plus
+ * the flush state a tick leaves behind.  Restated by oracle/ref_harness.cpp (btref_hash_full) and the host
+ * binding (host/bt_glue.cpp) over `ent`s. */
+static BT_HD u64 bt_hash_word(u64 h, i32 w) { return bt_mix64(h + (u64)(u32)w + 0x9E3779B97F4A7C15ULL); }
+static BT_HD i32 bt_uid_or_none(const DevWorld &W, i32 e) { return e >= 0 && W.inList[e] ? W.uid[e] : -1; }
+static BT_HD u64 bt_ent_hash_full(const DevWorld &W, i32 e) {
+	u64 h = bt_ent_hash(W, e);
+	const int4 r = W.radius[e], o = W.old[e], fh = W.forcedHoldees[e];
+	(void)fh;
+	h = bt_hash_word(h, r.x); h = bt_hash_word(h, r.y); h = bt_hash_word(h, r.z);
+	h = bt_hash_word(h, o.x); h = bt_hash_word(h, o.y); h = bt_hash_word(h, o.z);
+	h = bt_hash_word(h, W.friction[e]);
+	h = bt_hash_word(h, (i32)W.ntype[e]); h = bt_hash_word(h, (i32)W.ncollide[e]);
+	h = bt_hash_word(h, (i32)W.hphys[e]); h = bt_hash_word(h, (i32)W.hpair[e]); h = bt_hash_word(h, (i32)W.htick[e]);
+	h = bt_hash_word(h, (i32)W.btn_v[e]); h = bt_hash_word(h, (i32)W.btn_v2[e]);
+	{
+		i32 nh = W.newHolder[e];
+		h = bt_hash_word(h, nh == e ? -2 : bt_uid_or_none(W, nh)); /* newHolder == itself: contested request (entUpdaters.c:51) */
+		h = bt_hash_word(h, nh >= 0 ? W.newHoldFlags[e] : 0);
+	}
+	h = bt_hash_word(h, (i32)W.newDrop[e] | ((i32)W.dead_max0[e] << 8) | ((i32)W.dead_max1[e] << 16) | ((i32)W.fullFlush[e] << 24));
+	const i32 s0 = W.slider_off[e], s1 = W.slider_off[e + 1];
+	h = bt_hash_word(h, s1 - s0);
+	for (i32 s = s0; s < s1; s++) { h = bt_hash_word(h, W.sv[s]); h = bt_hash_word(h, W.smin[s]); h = bt_hash_word(h, W.smax[s]); }
+	const i32 wc = W.wire_cnt[e], w0 = W.wire_off[e];
+	h = bt_hash_word(h, wc);
+	for (i32 k = 0; k < wc; k++) h = bt_hash_word(h, bt_uid_or_none(W, W.wire_to[w0 + k]));
 	return h;
 }
 

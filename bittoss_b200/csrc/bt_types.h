@@ -109,6 +109,8 @@ enum {
 	CT_PAIR_N_FULL = 44, /* CT_PAIR_N right after the last full build */
 	CT_PAIR_PATCHES = 45, /* incremental pair-list patches (k_refit / k_pairs in patch mode) */
 	CT_ORDER_TIES = 46,  /* full collisionBetter ties between different collisions (resolved by the canonical key) */
+	CT_WQ_N = 47,        /* nodes handed out from the pending-wire pool (wq_next / wq_to) since the last flushMisc */
+	CT_TREE_EDITS = 48,  /* fumbles + pickups + deaths so far: a host binding re-reads the hold tree only when it moved */
 	CT_WORDS = 64
 };
 enum { SK_ITERS = 0, SK_CAND, SK_POS, SK_PUSH, SK_SERIAL, SK_CRUSH, SK_FUMBLE, SK_NUM };
@@ -134,6 +136,8 @@ struct DevWorld {
 	                 * the predecessor); bit 1: so are the two long ones, k_narrow and k_push (they only wait) */
 	i32 small_mode; /* every world holds <= BT_SMALL_WORLD entities: candidate pairs by brute force per world, no tree */
 	i32 patch_shift; /* patch while dirty entities << patch_shift <= leaves, full build beyond */
+	i32 root_phase;  /* launch-uniform: upper bits of the rootKey a fumble of this launch hands out (host counter) */
+	i32 wq_cap;      /* nodes in the pending-wire pool */
 
 	i32 *wbegin, *wend, *flip, *gamerules, *rnd; /* per world */
 	u32 *wunsup;                                 /* per world: would-be invocations of unimplemented handlers */
@@ -154,8 +158,14 @@ struct DevWorld {
 	int4 *forcedHoldees;
 	u64 *pend;
 	i32 *slider_off, *sv, *smin, *smax;
-	i32 *wire_off, *wire_cnt, *wire_to; /* wire_off leaves one spare slot behind every seat (PICKUP_SEAT wires its rider) */
-	i32 *wireAdd, *wireRm;              /* pending uWire / uUnwire target, -1 = none */
+	i32 *wire_off, *wire_cap, *wire_cnt, *wire_to; /* block start / capacity / wires in use; one spare slot behind every
+	                                                 * seat (PICKUP_SEAT wires its rider); blocks never move on the device */
+	i32 *wireAdd, *wireRm;              /* pending uWire / uUnwire: -1 none, >= 0 the one target, <= -2 a list in the
+	                                     * pool starting at node ~v - 1 ... see bt_uwire */
+	i32 *wq_next, *wq_to;               /* pending-wire pool: singly linked lists in request order */
+	u64 *rootKey;                       /* gs->rootEnts order (ent.cpp:60-66: newest root first) = descending key;
+	                                     * phase << 37 | order inside the phase, see bt_fumble */
+	u32 *wrootseq;                      /* per world: roots handed a key by the ordered (flush1) lane in this phase */
 
 	/* broadphase */
 	u64 *keys, *keys_alt;

@@ -108,6 +108,13 @@ struct bt_world {
 	bool ray_valid;
 	i32 *d_stage_a, *d_stage_b; /* 3*cap ints each, staging for the per-tick host exchange */
 	bool ranks_valid;           /* ray.slot2rank reflects the current live set */
+	/* incremental host binding */
+	i32 root_phase_ctr;         /* last value handed to a launch / the host as W.root_phase */
+	i32 sliders_used, wires_used; /* high-water marks of the slider / wire arenas */
+	bt_poke *d_pokes; i32 pokes_cap;
+	bool poked;                 /* the host wrote into the world since the counters were last fetched */
+	cudaError_t launch_err;     /* first failed kernel launch since the last check (reported at the next sync point) */
+	DevArrays arrays;
 };
 template <typename T> static int dalloc(bt_world *w, T **p, size_t count) {
 	void *q = NULL;
@@ -130,8 +137,8 @@ template <typename T> static int dalloc(bt_world *w, T **p, size_t count) {
 
 /* every kernel goes through here; pdl: programmatic dependent launch (see PDL_ENTRY in bt_kernels.cuh) */
 template <typename... KArgs, typename... Args>
-static inline void launch_k(bool pdl, void (*kern)(KArgs...), int grid, int block, cudaStream_t s, Args &&...args) {
-	if (!pdl) { kern<<<grid, block, 0, s>>>(KArgs(args)...); return; }
+static inline cudaError_t launch_k(bool pdl, void (*kern)(KArgs...), int grid, int block, cudaStream_t s, Args &&...args) {
+	if (!pdl) { kern<<<grid, block, 0, s>>>(KArgs(args)...); return cudaPeekAtLastError(); }
 	cudaLaunchConfig_t cfg = {};
 	cfg.gridDim = dim3((unsigned)grid);
 	cfg.blockDim = dim3((unsigned)block);
@@ -142,8 +149,11 @@ static inline void launch_k(bool pdl, void (*kern)(KArgs...), int grid, int bloc
 	at[0].val.programmaticStreamSerializationAllowed = pdl ? 1 : 0;
 	cfg.attrs = at;
 	cfg.numAttrs = 1;
-	cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+	return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
 }
+/* a launch that failed (bad grid, sticky fault of an earlier kernel) is remembered with its own name and
+ * line and turns the next sync point (fetch_ctr, the end of a step) into BT_ERR_CUDA */
+static void note_launch_error(struct bt_world *w, cudaError_t e, const char *kern, int line);
 
 /* the two long kernels (classes narrow and push; k_push_serial rides along) follow pdl_long */
 #define pdl_for(w, cls) (((cls) == PK_NARROW || (cls) == PK_PUSH) ? (w)->pdl_long : (w)->pdl)
@@ -153,7 +163,8 @@ static inline void launch_k(bool pdl, void (*kern)(KArgs...), int grid, int bloc
 	do {                                                                               \
 		if ((grid) > 0) {                                                              \
 			if ((w)->profiling) cudaEventRecord((w)->ev0, (w)->stream);                \
-			launch_k(pdl_for((w), cls), kern, (grid), (block), (w)->stream, __VA_ARGS__); \
+			cudaError_t _le = launch_k(pdl_for((w), cls), kern, (grid), (block), (w)->stream, __VA_ARGS__); \
+			if (_le != cudaSuccess) note_launch_error((w), _le, #kern, __LINE__);      \
 			(w)->stats.kernel_launches++;                                              \
 			(w)->prof_launches[cls]++;                                                 \
 			if ((w)->profiling) {                                                      \
@@ -183,6 +194,12 @@ static int pairs_wave() {
 }
 
 static void set_pdl(struct bt_world *w, int n_worlds, long long n_ents);
+static void note_launch_error(bt_world *w, cudaError_t e, const char *kern, int line) {
+	if (w->launch_err != cudaSuccess) return;
+	w->launch_err = e;
+	snprintf(g_err, sizeof g_err, "launch of %s failed: %s (bt_world.cu:%d)", kern, cudaGetErrorString(e), line);
+}
+#define CHECK_LAUNCHES(w) do { if ((w)->launch_err != cudaSuccess) { (w)->launch_err = cudaSuccess; cudaGetLastError(); return BT_ERR_CUDA; } } while (0)
 extern "C" {
 
 const char *bt_version(void) { return "bittoss_b200 0.1 (sm_100a)"; }
@@ -205,6 +222,7 @@ void bt_world_destroy(bt_world *w) {
 	if (w->h_flag) cudaFreeHost(w->h_flag);
 	if (w->d_reqs) cudaFree(w->d_reqs);
 	if (w->d_req_starts) cudaFree(w->d_req_starts);
+	if (w->d_pokes) cudaFree(w->d_pokes);
 	if (w->ev0) cudaEventDestroy(w->ev0);
 	if (w->ev1) cudaEventDestroy(w->ev1);
 	if (w->stream) cudaStreamDestroy(w->stream);
@@ -230,6 +248,8 @@ int bt_world_create(bt_world **out, int device, int32_t max_ents, int32_t max_sl
 	w->tree_valid = false; w->deltas_pending = true; w->ticks_since_build = 0; w->full_flush_left = 2; w->scan_flushes_left = 2; w->ctrls_fused = false;
 	w->rebuild_every = 16; w->max_iterations = 100000; w->pair_cache = 1; w->pair_rebuilds = 0; w->pair_overflows = 0; w->seen_pair_builds = 0; w->seen_pair_patches = 0; w->pair_builds_at_tree = 0; w->profiling = false; w->ray_valid = false; w->uid_map_valid = false; w->ctr_fresh = false; w->margin_opt = -1; w->narrow_blocks = 148 * 8; w->narrow_threads = 256; w->pdl_opt = getenv("BT_NO_PDL") ? 0 : -1; w->pdl = false; w->pdl_long = false; /* decided at upload, together with W.pdl */ w->small_worlds = true; w->d_reqs = NULL; w->d_req_starts = NULL; w->reqs_cap = 0; w->any_ticks = w->any_rand = false; w->bad_tick = 0; w->device_ticks = 1;
 	w->h_flag = NULL; w->ev0 = w->ev1 = NULL; w->stream = NULL;
+	w->root_phase_ctr = 0; w->sliders_used = 0; w->wires_used = 0; w->d_pokes = NULL; w->pokes_cap = 0; w->poked = false;
+	w->launch_err = cudaSuccess;
 	*out = w;
 #define TRY(x) do { int _r = (x); if (_r) { bt_world_destroy(w); *out = NULL; return _r; } } while (0)
 #define TRYCU(x) do { cudaError_t _e = (x); if (_e != cudaSuccess) { set_err("%s failed: %s (bt_world.cu:%d)", #x, cudaGetErrorString(_e), __LINE__); bt_world_destroy(w); *out = NULL; return BT_ERR_CUDA; } } while (0)
@@ -258,7 +278,10 @@ int bt_world_create(bt_world **out, int device, int32_t max_ents, int32_t max_sl
 	TRY(dalloc(w, &W.slider_off, n + 1)); TRY(dalloc(w, &W.sv, (size_t)max_sliders));
 	TRY(dalloc(w, &W.smin, (size_t)max_sliders)); TRY(dalloc(w, &W.smax, (size_t)max_sliders));
 	TRY(dalloc(w, &W.wire_off, n + 1)); TRY(dalloc(w, &W.wire_cnt, n)); TRY(dalloc(w, &W.wire_to, (size_t)max_wires + n)); /* + one spare slot per (seat) entity at worst */
-	TRY(dalloc(w, &W.wireAdd, n)); TRY(dalloc(w, &W.wireRm, n));
+	TRY(dalloc(w, &W.wireAdd, n)); TRY(dalloc(w, &W.wireRm, n)); TRY(dalloc(w, &W.wire_cap, n));
+	TRY(dalloc(w, &W.rootKey, n)); TRY(dalloc(w, &W.wrootseq, nw));
+	W.wq_cap = (i32)std::min<size_t>((size_t)1 << 24, 2 * n + 1024);
+	TRY(dalloc(w, &W.wq_next, (size_t)W.wq_cap)); TRY(dalloc(w, &W.wq_to, (size_t)W.wq_cap));
 	TRY(dalloc(w, &W.keys, n)); TRY(dalloc(w, &W.keys_alt, n));
 	TRY(dalloc(w, &W.leafEnt, n)); TRY(dalloc(w, &W.leafEnt_alt, n));
 	TRY(dalloc(w, &W.leafParent, n)); TRY(dalloc(w, &W.nodeParent, n)); TRY(dalloc(w, &W.nodeCount, n));
@@ -285,6 +308,20 @@ int bt_world_create(bt_world **out, int device, int32_t max_ents, int32_t max_sl
 	w->ranks_valid = false;
 #undef TRY
 #undef TRYCU
+	{
+		void **b = w->arrays.base;
+		b[BT_A_CENTER] = W.center; b[BT_A_VEL] = W.vel; b[BT_A_OLD] = W.old; b[BT_A_DCENTER] = W.d_center; b[BT_A_DVEL] = W.d_vel;
+		b[BT_A_RADIUS] = W.radius; b[BT_A_TYPE] = W.type; b[BT_A_COLLIDE] = W.collide; b[BT_A_NTYPE] = W.ntype;
+		b[BT_A_NCOLLIDE] = W.ncollide; b[BT_A_FRICTION] = W.friction; b[BT_A_HOLDER] = W.holder; b[BT_A_HOLDFLAGS] = W.holdFlags;
+		b[BT_A_HOLDROOT] = W.holdRoot; b[BT_A_HOLDEE] = W.holdee; b[BT_A_LLN] = W.LLn; b[BT_A_LLP] = W.LLp;
+		b[BT_A_NEWHOLDER] = W.newHolder; b[BT_A_NEWHOLDFLAGS] = W.newHoldFlags; b[BT_A_UID] = W.uid; b[BT_A_WORLD] = W.world;
+		b[BT_A_HPHYS] = W.hphys; b[BT_A_HPAIR] = W.hpair; b[BT_A_HTICK] = W.htick; b[BT_A_BTN_V] = W.btn_v; b[BT_A_BTN_V2] = W.btn_v2;
+		b[BT_A_NEWDROP] = W.newDrop; b[BT_A_DEADMAX0] = W.dead_max0; b[BT_A_DEADMAX1] = W.dead_max1; b[BT_A_FULLFLUSH] = W.fullFlush;
+		b[BT_A_DEAD] = W.dead; b[BT_A_INLIST] = W.inList; b[BT_A_ROOTKEY] = W.rootKey; b[BT_A_SLIDER_OFF] = W.slider_off;
+		b[BT_A_WIRE_OFF] = W.wire_off; b[BT_A_WIRE_CAP] = W.wire_cap; b[BT_A_WIRE_CNT] = W.wire_cnt; b[BT_A_SV] = W.sv;
+		b[BT_A_SMIN] = W.smin; b[BT_A_SMAX] = W.smax; b[BT_A_WIRE_TO] = W.wire_to; b[BT_A_W_FLIP] = W.flip;
+		b[BT_A_W_GAMERULES] = W.gamerules; b[BT_A_W_RAND] = W.rnd; b[BT_A_DEADLIST] = W.deadList;
+	}
 	return BT_OK;
 }
 
@@ -371,13 +408,28 @@ int bt_world_upload(bt_world *w, const bt_world_desc *d) {
 		}
 	}
 	std::vector<i32> world(n), wbegin(nw, n), wend(nw, 0);
+#define BAD_DESC(...) do { snprintf(g_err, sizeof g_err, __VA_ARGS__); return BT_ERR_ARG; } while (0)
 	for (int i = 0; i < n; i++) {
 		int g = d->world_id ? d->world_id[i] : 0;
-		if (g < 0 || g >= nw) return BT_ERR_ARG;
+		if (g < 0 || g >= nw) BAD_DESC("entity %d: world id %d outside [0, %d)", i, g, nw);
+		if (i > 0 && g < world[i - 1]) BAD_DESC("entity %d: world ids must be non-decreasing (the entities of one world are contiguous)", i);
 		world[i] = g;
 		wbegin[g] = std::min(wbegin[g], i);
 		wend[g] = std::max(wend[g], i + 1);
 	}
+	/* every reference stays inside [-1, n) and inside its own world; the CSR offsets are monotonic and match the totals */
+	if (d->slider_off[0] != 0 || d->wire_off[0] != 0 || d->slider_off[n] != d->n_sliders || d->wire_off[n] != d->n_wires)
+		BAD_DESC("slider_off / wire_off do not start at 0 or do not end at n_sliders / n_wires");
+	for (int i = 0; i < n; i++) {
+		if (d->slider_off[i + 1] < d->slider_off[i] || d->wire_off[i + 1] < d->wire_off[i]) BAD_DESC("entity %d: CSR offsets decrease", i);
+		const i32 refs[4] = {d->holder[i], d->holdee_head[i], d->holder[i] >= 0 ? d->holdee_next[i] : -1, d->new_holder[i]};
+		for (int k = 0; k < 4; k++)
+			if (refs[k] < -1 || refs[k] >= n || (refs[k] >= 0 && world[refs[k]] != world[i]))
+				BAD_DESC("entity %d: %s %d is outside its world", i, k == 0 ? "holder" : k == 1 ? "holdee_head" : k == 2 ? "holdee_next" : "new_holder", refs[k]);
+		for (i32 k = d->wire_off[i]; k < d->wire_off[i + 1]; k++)
+			if (d->wire_to[k] < 0 || d->wire_to[k] >= n || world[d->wire_to[k]] != world[i]) BAD_DESC("entity %d: wire target %d is outside its world", i, d->wire_to[k]);
+	}
+#undef BAD_DESC
 	for (int g = 0; g < nw; g++)
 		if (wbegin[g] > wend[g]) wbegin[g] = wend[g] = 0;
 	auto v3 = [&](const int32_t *src) {
@@ -387,6 +439,9 @@ int bt_world_upload(bt_world *w, const bt_world_desc *d) {
 	};
 	bool deltas = false;
 	for (int i = 0; i < 3 * n && !deltas; i++) deltas = d->d_center[i] || d->d_vel[i];
+	/* a pending pickup with HOLD_FREEZE leaves a d_vel behind when prepPhysics applies it (ent.cpp:176-181):
+	 * the flush2 at the start of doPhysics has to look (the fused begin kernel never reads d_vel) */
+	for (int i = 0; i < n && !deltas; i++) deltas = d->new_holder[i] >= 0 && (d->new_hold_flags[i] & HOLD_FREEZE);
 	std::vector<i32> holdRoot(n), LLn(n, -1), LLp(n, -1);
 	for (int i = 0; i < n; i++) {
 		i32 h = d->holder[i];
@@ -407,7 +462,8 @@ int bt_world_upload(bt_world *w, const bt_world_desc *d) {
 	std::vector<u8> newDrop(n), dm0(n), dm1(n), ff(n), dead(n, 0), inList(n, 1), needsC(n, 0), hasBox(n), ready(n, 0);
 	std::vector<int4> fh(n, make_int4(-1, -1, -1, 0));
 	std::vector<u64> pend(n, 0);
-	std::vector<i32> wire_cnt(n);
+	std::vector<i32> wire_cnt(n), wire_cap(n);
+	std::vector<u64> rootKey(n, 0);
 	bool any_ticks = false, any_rand = false;
 	int bad_tick = 0;
 	for (int i = 0; i < n; i++) {
@@ -435,9 +491,13 @@ int bt_world_upload(bt_world *w, const bt_world_desc *d) {
 		i32 o = 0;
 		for (int i = 0; i < n; i++) {
 			wire_off[i] = o;
-			o += wire_cnt[i] + (d->handlers[(size_t)BT_H_NUM * i + BT_H_ONPICKUP] == 1 ? 1 : 0);
+			wire_cap[i] = wire_cnt[i] + (d->handlers[(size_t)BT_H_NUM * i + BT_H_ONPICKUP] == 1 ? 1 : 0);
+			o += wire_cap[i];
+			/* gs->rootEnts order (0 = head) as a key that sorts the head highest; phase 0 */
+			if (d->holder[i] < 0) rootKey[i] = (u64)(n - (d->root_order[i] >= 0 ? d->root_order[i] : n - 1 - i));
 		}
 		wire_off[n] = o;
+		w->wires_used = o;
 		if (o > w->cap_wires + w->cap_ents) {
 			snprintf(g_err, sizeof g_err, "world needs %d wire slots (incl. one spare per seat), capacity %d", o, w->cap_wires);
 			return BT_ERR_CAPACITY;
@@ -472,8 +532,9 @@ int bt_world_upload(bt_world *w, const bt_world_desc *d) {
 	UP(W.forced, forced); UP(W.forcedHoldees, fh); UP(W.pend, pend);
 	UPRAW(W.slider_off, d->slider_off, n + 1, i32); UPRAW(W.sv, d->slider_v, d->n_sliders, i32);
 	UPRAW(W.smin, d->slider_min, d->n_sliders, i32); UPRAW(W.smax, d->slider_max, d->n_sliders, i32);
-	UP(W.wire_off, wire_off); UP(W.wire_to, wire_to);
+	UP(W.wire_off, wire_off); UP(W.wire_to, wire_to); UP(W.wire_cap, wire_cap); UP(W.rootKey, rootKey);
 	UP(W.wire_cnt, wire_cnt); UP(W.wireAdd, minus1); UP(W.wireRm, minus1);
+	w->sliders_used = d->n_sliders; w->root_phase_ctr = 0; w->poked = false;
 	CK(cudaMemsetAsync(W.ctr, 0, sizeof(u32) * CT_WORDS, w->stream));
 	{ int rr = raise_cache_invalid(w); if (rr) return rr; }
 	CK(cudaMemsetAsync(W.dirtyStamp, 0, sizeof(u32) * (size_t)w->cap_ents, w->stream));
@@ -591,14 +652,18 @@ static int flush1(bt_world *w, bool hint) {
 	w->ctr_fresh = false;
 	CK(cudaMemsetAsync(&W.ctr[CT_FLUSH_HINT], 0, sizeof(u32), w->stream));
 	if (scan) LAUNCH(w, PK_FLUSH, k_flush_scan, nblk(W.n), BT_BLOCK, W);
+	W.root_phase = ++w->root_phase_ctr; /* roots this flush makes go ahead of every older one in gs->rootEnts */
 	LAUNCH(w, PK_FLUSH, k_flush_serial, nblk((i64)W.n_worlds * 32), BT_BLOCK, W); /* one warp per world */
 	LAUNCH(w, PK_FLUSH, k_flush_misc, nblk(W.n), BT_BLOCK, W);
+	CK(cudaMemsetAsync(&W.ctr[CT_WQ_N], 0, sizeof(u32), w->stream)); /* every pending-wire list has been consumed */
 	return 0;
 }
 
 static int fetch_ctr(bt_world *w) {
+	CHECK_LAUNCHES(w);
 	CK(cudaMemcpyAsync(w->h_flag, w->W.ctr, sizeof(u32) * CT_WORDS, cudaMemcpyDeviceToHost, w->stream));
 	CK(cudaStreamSynchronize(w->stream));
+	w->poked = false;
 	if (w->h_flag[CT_ERROR]) {
 		int code = -(int)w->h_flag[CT_ERROR];
 		snprintf(g_err, sizeof g_err, "device raised error %d (overflow of a work list or unsupported flush)", code);
@@ -607,7 +672,8 @@ static int fetch_ctr(bt_world *w) {
 	return 0;
 }
 
-static int do_physics(bt_world *w, bool gravity) {
+/* doPhysics up to and including the resolution loop (ent.cpp:843-905) */
+static int do_physics_iter(bt_world *w, bool gravity) {
 	DevWorld &W = w->W;
 	const i32 n = W.n;
 	if (!w->deltas_pending) {
@@ -651,6 +717,7 @@ static int do_physics(bt_world *w, bool gravity) {
 	auto resolve = [&]() {
 		/* speculative behind the narrow phase (see k_decide) */
 		LAUNCH(w, PK_DECIDE, k_decide, nblk(n), BT_BLOCK, W);
+		W.root_phase = ++w->root_phase_ctr; /* both push lanes of one iteration share it (canonical push order inside) */
 		LAUNCH(w, PK_PUSH, k_push, nblk(n), BT_BLOCK, W);
 		LAUNCH(w, PK_PUSH, k_push_serial, 1, 32, W);
 		LAUNCH(w, PK_POST, k_post, nblk(n), BT_BLOCK, W);
@@ -731,8 +798,17 @@ static int do_physics(bt_world *w, bool gravity) {
 		int rr = raise_cache_invalid(w);
 		if (rr) return rr;
 	}
-	/* invokeOnCrush (ent.cpp:907): crush handlers are host-side events (dead list) */
-	/* h_flag holds the counters fetched after the last k_narrow, i.e. after every push */
+	return 0;
+}
+
+/* invokeOnCrush (ent.cpp:907) lies between the two halves: crush handlers are host-side events (dead list).
+ * This is the rest of doPhysics: flush1; flush2 (ent.cpp:909-910). */
+static int do_physics_end(bt_world *w) {
+	DevWorld &W = w->W;
+	const i32 n = W.n;
+	/* h_flag holds the counters fetched after the last k_narrow, i.e. after every push -- unless the host
+	 * has written into the world since (crush handlers of a host binding): look again */
+	if (w->poked) { int rr = fetch_ctr(w); if (rr) return rr; }
 	W.flush_stage = 1; /* deaths flushed from here on are past invokeOnCrush (ent.cpp:907-909) */
 	const bool full_flush = w->full_flush_left > 0 || w->h_flag[CT_FLUSH_HINT] != 0;
 	int r = flush1(w, w->h_flag[CT_FLUSH_HINT] != 0);
@@ -779,7 +855,7 @@ int bt_world_step(bt_world *w, uint32_t phases) {
 		snprintf(g_err, sizeof g_err, "BT_PHASE_TICKS: tick handler id %d has no device implementation", w->bad_tick);
 		return BT_ERR_UNSUPPORTED;
 	}
-	w->ctrls_fused = (phases & BT_PHASE_CTRLS) && (phases & BT_PHASE_PHYSICS) && !w->deltas_pending && !(phases & BT_PHASE_TICKS);
+	w->ctrls_fused = (phases & BT_PHASE_CTRLS) && (phases & (BT_PHASE_PHYSICS | BT_PHASE_PHYSICS_ITER)) && !w->deltas_pending && !(phases & BT_PHASE_TICKS);
 	if ((phases & BT_PHASE_CTRLS) && !w->ctrls_fused) LAUNCH(w, PK_PRE, k_pre, nblk(n), BT_BLOCK, W, phases);
 	if ((phases & BT_PHASE_TICKS) && w->any_ticks) {
 		LAUNCH(w, PK_TICK, k_tick, nblk(n), BT_BLOCK, W);
@@ -791,12 +867,16 @@ int bt_world_step(bt_world *w, uint32_t phases) {
 		int r = flush1(w, false);
 		if (r) return r;
 	}
-	if ((phases & BT_PHASE_GRAVITY) && !(phases & BT_PHASE_PHYSICS)) {
+	if ((phases & BT_PHASE_GRAVITY) && !(phases & (BT_PHASE_PHYSICS | BT_PHASE_PHYSICS_ITER))) {
 		LAUNCH(w, PK_BEGIN, k_gravity, nblk(n), BT_BLOCK, W);
 		w->deltas_pending = true;
 	}
-	if (phases & BT_PHASE_PHYSICS) {
-		int r = do_physics(w, (phases & BT_PHASE_GRAVITY) != 0);
+	if (phases & (BT_PHASE_PHYSICS | BT_PHASE_PHYSICS_ITER)) {
+		int r = do_physics_iter(w, (phases & BT_PHASE_GRAVITY) != 0);
+		if (r) return r;
+	}
+	if (phases & (BT_PHASE_PHYSICS | BT_PHASE_PHYSICS_END)) {
+		int r = do_physics_end(w);
 		if (r) return r;
 		w->stats.ticks++;
 	}
@@ -814,6 +894,7 @@ int bt_world_step(bt_world *w, uint32_t phases) {
 		}
 		w->stats.entity_ticks += w->stats.live_ents;
 	}
+	CHECK_LAUNCHES(w);
 	return BT_OK;
 }
 
@@ -823,20 +904,37 @@ static uint32_t tick_phases(const bt_world *w) {
 	       (w->device_ticks && w->any_ticks && !w->bad_tick ? BT_PHASE_TICKS : 0u);
 }
 
-static int hash_into(bt_world *w, uint64_t *out) {
+static inline u64 h_mix64(u64 x) {
+	x ^= x >> 30; x *= 0xbf58476d1ce4e5b9ULL;
+	x ^= x >> 27; x *= 0x94d049bb133111ebULL;
+	x ^= x >> 31;
+	return x;
+}
+static int hash_into(bt_world *w, uint64_t *out, int full = 0) {
 	DevWorld &W = w->W;
 	CK(cudaMemsetAsync(w->d_hsum, 0, sizeof(u64) * (size_t)W.n_worlds, w->stream));
 	CK(cudaMemsetAsync(w->d_hcnt, 0, sizeof(u32) * (size_t)W.n_worlds, w->stream));
-	LAUNCH(w, PK_HASH, k_hash, nblk(W.n), BT_BLOCK, W, w->d_hsum, w->d_hcnt);
+	LAUNCH(w, PK_HASH, k_hash, nblk(W.n), BT_BLOCK, W, w->d_hsum, w->d_hcnt, full);
 	std::vector<u64> s(W.n_worlds);
 	std::vector<u32> c(W.n_worlds);
 	CK(cudaMemcpyAsync(s.data(), w->d_hsum, sizeof(u64) * s.size(), cudaMemcpyDeviceToHost, w->stream));
 	CK(cudaMemcpyAsync(c.data(), w->d_hcnt, sizeof(u32) * c.size(), cudaMemcpyDeviceToHost, w->stream));
 	CK(cudaStreamSynchronize(w->stream));
+	std::vector<i32> flip, rules, rnd;
+	if (full) {
+		flip.resize(W.n_worlds); rules.resize(W.n_worlds); rnd.resize(W.n_worlds);
+		CK(cudaMemcpy(flip.data(), W.flip, sizeof(i32) * flip.size(), cudaMemcpyDeviceToHost));
+		CK(cudaMemcpy(rules.data(), W.gamerules, sizeof(i32) * rules.size(), cudaMemcpyDeviceToHost));
+		CK(cudaMemcpy(rnd.data(), W.rnd, sizeof(i32) * rnd.size(), cudaMemcpyDeviceToHost));
+	}
 	for (int g = 0; g < W.n_worlds; g++) {
-		u64 x = (u64)c[g];
-		x ^= x >> 30; x *= 0xbf58476d1ce4e5b9ULL; x ^= x >> 27; x *= 0x94d049bb133111ebULL; x ^= x >> 31;
-		out[g] = s[g] + x;
+		out[g] = s[g] + h_mix64((u64)c[g]);
+		if (full) { /* the gamestate scalars: flipFlop_death, rand, gamerules (ent.h:187-189) */
+			u64 h = h_mix64((u64)(u32)flip[g] + 0x9E3779B97F4A7C15ULL);
+			h = h_mix64(h + (u64)(u32)rnd[g] + 0x9E3779B97F4A7C15ULL);
+			h = h_mix64(h + (u64)(u32)rules[g] + 0x9E3779B97F4A7C15ULL);
+			out[g] += h;
+		}
 	}
 	return 0;
 }
@@ -845,6 +943,12 @@ int bt_world_hash(bt_world *w, uint64_t *out) {
 	if (!w || !out) return BT_ERR_ARG;
 	CK(cudaSetDevice(w->device));
 	return hash_into(w, out);
+}
+
+int bt_world_hash_full(bt_world *w, uint64_t *out) {
+	if (!w || !out) return BT_ERR_ARG;
+	CK(cudaSetDevice(w->device));
+	return hash_into(w, out, 1);
 }
 
 int bt_world_tick(bt_world *w, int32_t n_ticks, uint64_t *hashes) {
@@ -942,7 +1046,8 @@ int bt_world_apply_requests(bt_world *w, const bt_request *reqs, int32_t n) {
 			q[i].other = jt->second;
 		}
 		q[i].a0 = r.a[0]; q[i].a1 = r.a[1]; q[i].a2 = r.a[2];
-		deltas |= r.kind == BT_REQ_VEL || r.kind == BT_REQ_CENTER;
+		/* a HOLD_FREEZE pickup leaves a d_vel behind when prepPhysics applies it (ent.cpp:176-181) */
+		deltas |= r.kind == BT_REQ_VEL || r.kind == BT_REQ_CENTER || (r.kind == BT_REQ_PICKUP && (r.a[0] & HOLD_FREEZE));
 	}
 	starts.push_back(n);
 	const i32 n_groups = (i32)starts.size() - 1;
@@ -1022,7 +1127,12 @@ int bt_world_drain_events(bt_world *w, bt_event *out, int32_t max, int32_t *n) {
 	CK(cudaMemcpy(&cnt, &w->W.ctr[CT_EVENT_N], sizeof(u32), cudaMemcpyDeviceToHost));
 	bool overflow = cnt > (u32)w->W.event_cap;
 	if (overflow) cnt = (u32)w->W.event_cap;
-	u32 take = cnt < (u32)max ? cnt : (u32)max;
+	if (cnt > (u32)max) { /* nothing is consumed: the caller comes back with room for all of them */
+		*n = (int32_t)cnt;
+		snprintf(g_err, sizeof g_err, "bt_world_drain_events: %u events queued, room for %d", cnt, max);
+		return BT_ERR_CAPACITY;
+	}
+	u32 take = cnt;
 	std::vector<int4> ev(take);
 	std::vector<i32> uid(w->W.n), world(w->W.n);
 	if (take) {
@@ -1090,6 +1200,9 @@ int bt_world_assign(bt_world *dst, bt_world *src) {
 	rebase(&dst->W, sizeof(dst->W), src, dst);
 	dst->ray = src->ray;
 	rebase(&dst->ray, sizeof(dst->ray), src, dst);
+	dst->arrays = src->arrays;
+	rebase(&dst->arrays, sizeof(dst->arrays), src, dst);
+	dst->root_phase_ctr = src->root_phase_ctr; dst->sliders_used = src->sliders_used; dst->wires_used = src->wires_used; dst->poked = src->poked;
 	dst->tree_valid = src->tree_valid; dst->deltas_pending = src->deltas_pending; dst->any_rules = src->any_rules;
 	dst->full_flush_left = src->full_flush_left; dst->scan_flushes_left = src->scan_flushes_left; dst->ctrls_fused = src->ctrls_fused;
 	dst->uid_map_valid = false; dst->ctr_fresh = false; dst->pdl = src->pdl; dst->pdl_long = src->pdl_long; dst->pdl_opt = src->pdl_opt; dst->margin_opt = src->margin_opt; dst->narrow_blocks = src->narrow_blocks; dst->narrow_threads = src->narrow_threads; dst->small_worlds = src->small_worlds;
@@ -1200,16 +1313,15 @@ int bt_world_download(bt_world *w, bt_world_desc *d) {
 	CK(cudaMemcpy(rules.data(), W.gamerules, sizeof(i32) * nw, cudaMemcpyDeviceToHost));
 	CK(cudaMemcpy(rnd.data(), W.rnd, sizeof(i32) * nw, cudaMemcpyDeviceToHost));
 	for (int g = 0; g < nw; g++) { d->w_flip_flop[g] = flip[g]; d->w_gamerules[g] = rules[g]; d->w_rand[g] = rnd[g]; }
-	/* rootEnts order: roots created on the device (fumbles) come first, newest index first,
-	 * then the surviving upload-time roots in their uploaded order */
+	/* gs->rootEnts order (0 = head) = descending rootKey inside a world */
 	{
-		std::vector<std::vector<std::pair<i64, i32>>> per(nw);
+		std::vector<u64> rk;
+		int rr = d2h(rk, (const u64 *)W.rootKey, (size_t)n);
+		if (rr) return rr;
+		std::vector<std::vector<std::pair<u64, i32>>> per(nw);
 		for (int i = 0; i < n; i++) {
 			if (!inList[i] || holder[i] >= 0) continue;
-			i32 ro = (i < (int)w->up_root_order.size()) ? w->up_root_order[i] : -1;
-			i64 key = ro >= 0 ? (i64)ro : (i64)-1 - (i64)i - ((i64)1 << 32);
-			if (ro < 0) key = -((i64)i) - 1; /* negative: ahead of every uploaded root, larger index first */
-			per[world[i]].push_back(std::make_pair(key, (i32)i));
+			per[world[i]].push_back(std::make_pair(~rk[i], (i32)i));
 		}
 		for (int g = 0; g < nw; g++) {
 			std::sort(per[g].begin(), per[g].end());
@@ -1254,6 +1366,200 @@ int bt_world_download(bt_world *w, bt_world_desc *d) {
 	}
 	d->slider_off[k] = sOut; d->wire_off[k] = wOut;
 	d->n_ents = k; d->n_sliders = sOut; d->n_wires = wOut; d->n_worlds = nw;
+	return BT_OK;
+}
+
+/* ---------------------------------------------------------------- incremental host binding */
+
+/* bytes per element of a BT_A_* array */
+static int array_elem_bytes(int a) {
+	if (a >= BT_A_CENTER && a <= BT_A_RADIUS) return 16;
+	if (a >= BT_A_NEWDROP && a <= BT_A_INLIST) return 1;
+	if (a == BT_A_ROOTKEY || a == BT_A_DEADLIST) return 8;
+	return 4;
+}
+static int array_extent(bt_world *w, int a, i32 *count) {
+	if (a < 0 || a >= BT_A_NUM) return BT_ERR_ARG;
+	if (a >= BT_A_SV && a <= BT_A_SMAX) *count = w->sliders_used;
+	else if (a == BT_A_WIRE_TO) *count = w->wires_used;
+	else if (a >= BT_A_W_FLIP && a <= BT_A_W_RAND) *count = w->W.n_worlds;
+	else if (a == BT_A_SLIDER_OFF) *count = w->W.n + 1;
+	else if (a == BT_A_DEADLIST) {
+		if (!w->ctr_fresh || w->poked) { int r = fetch_ctr(w); if (r) return r; }
+		*count = (i32)std::min<u32>(w->h_flag[CT_DEAD_N], (u32)w->W.dead_cap);
+	} else *count = w->W.n;
+	return BT_OK;
+}
+
+int bt_world_extent(bt_world *w, int32_t array, int32_t *count) {
+	if (!w || !count) return BT_ERR_ARG;
+	CK(cudaSetDevice(w->device));
+	return array_extent(w, array, count);
+}
+
+int bt_world_pull(bt_world *w, int32_t array, int32_t first, int32_t count, void *dst) {
+	if (!w || first < 0 || count < 0 || (count > 0 && !dst)) return BT_ERR_ARG;
+	CK(cudaSetDevice(w->device));
+	i32 ext = 0;
+	int r = array_extent(w, array, &ext);
+	if (r) return r;
+	if ((i64)first + count > ext) { snprintf(g_err, sizeof g_err, "bt_world_pull: [%d, %d) exceeds the %d elements of array %d", first, first + count, ext, array); return BT_ERR_ARG; }
+	if (!count) return BT_OK;
+	const size_t eb = (size_t)array_elem_bytes(array);
+	CHECK_LAUNCHES(w);
+	CK(cudaMemcpyAsync(dst, (const char *)w->arrays.base[array] + eb * (size_t)first, eb * (size_t)count, cudaMemcpyDeviceToHost, w->stream));
+	CK(cudaStreamSynchronize(w->stream));
+	return BT_OK;
+}
+
+int64_t bt_world_next_root_phase(bt_world *w) { return w ? (int64_t)++w->root_phase_ctr : (int64_t)BT_ERR_ARG; }
+
+int bt_world_tree_edits(bt_world *w, uint32_t *count) {
+	if (!w || !count) return BT_ERR_ARG;
+	CK(cudaSetDevice(w->device));
+	if (!w->ctr_fresh || w->poked) { int r = fetch_ctr(w); if (r) return r; }
+	*count = w->h_flag[CT_TREE_EDITS];
+	return BT_OK;
+}
+
+/* after anything the host wrote: the next flush1 looks at everything (both dead_max slots), flush2 runs in
+ * full, the device counters are stale */
+static void host_wrote(bt_world *w) {
+	w->poked = true;
+	w->ctr_fresh = false;
+	w->deltas_pending = true;
+	if (w->full_flush_left < 2) w->full_flush_left = 2;
+	if (w->scan_flushes_left < 2) w->scan_flushes_left = 2;
+	w->uid_map_valid = false;
+	w->ray_valid = false;
+}
+
+int bt_world_grow(bt_world *w, int32_t n_new, const int32_t *n_sliders, const int32_t *wire_cap, int32_t world, int32_t *first_slot) {
+	if (!w || n_new < 0 || !first_slot || (n_new > 0 && (!n_sliders || !wire_cap))) return BT_ERR_ARG;
+	CK(cudaSetDevice(w->device));
+	DevWorld &W = w->W;
+	if (world < 0 || world >= W.n_worlds) return BT_ERR_ARG;
+	if (W.n_worlds > 1) { snprintf(g_err, sizeof g_err, "bt_world_grow: batched device worlds keep the entities of one world contiguous and cannot grow"); return BT_ERR_UNSUPPORTED; }
+	*first_slot = W.n;
+	if (!n_new) return BT_OK;
+	i64 ns = 0, nwc = 0;
+	for (i32 i = 0; i < n_new; i++) {
+		if (n_sliders[i] < 0 || wire_cap[i] < 0) return BT_ERR_ARG;
+		ns += n_sliders[i]; nwc += wire_cap[i];
+	}
+	if ((i64)W.n + n_new > w->cap_ents || w->sliders_used + ns > w->cap_sliders || w->wires_used + nwc > (i64)w->cap_wires + w->cap_ents) {
+		snprintf(g_err, sizeof g_err, "bt_world_grow: %d more entities / %lld sliders / %lld wire slots exceed the capacities given to bt_world_create", n_new, (long long)ns, (long long)nwc);
+		return BT_ERR_CAPACITY;
+	}
+	std::vector<i32> so((size_t)n_new + 1), wo((size_t)n_new), wc((size_t)n_new);
+	std::vector<i32> sinit((size_t)ns * 3);
+	i32 s = w->sliders_used, q = w->wires_used;
+	for (i32 i = 0; i < n_new; i++) {
+		so[i] = s; wo[i] = q; wc[i] = wire_cap[i];
+		s += n_sliders[i]; q += wire_cap[i];
+	}
+	so[n_new] = s;
+	const i32 first = W.n;
+	LAUNCH(w, PK_EXCHANGE, k_grow_init, nblk(n_new), BT_BLOCK, W, first, n_new, world);
+	/* slider_off[first] already holds sliders_used (the CSR end of the slots before) */
+	CK(cudaMemcpyAsync(W.slider_off + first, so.data(), sizeof(i32) * ((size_t)n_new + 1), cudaMemcpyHostToDevice, w->stream));
+	CK(cudaMemcpyAsync(W.wire_off + first, wo.data(), sizeof(i32) * (size_t)n_new, cudaMemcpyHostToDevice, w->stream));
+	CK(cudaMemcpyAsync(W.wire_cap + first, wc.data(), sizeof(i32) * (size_t)n_new, cudaMemcpyHostToDevice, w->stream));
+	if (ns) { /* prepNewSliders entFuncs.c:13-18: v 0, max INT32_MIN, min INT32_MAX */
+		std::vector<i32> z((size_t)ns, 0), mn((size_t)ns, INT32_MAX), mx((size_t)ns, INT32_MIN);
+		CK(cudaMemcpyAsync(W.sv + w->sliders_used, z.data(), sizeof(i32) * (size_t)ns, cudaMemcpyHostToDevice, w->stream));
+		CK(cudaMemcpyAsync(W.smin + w->sliders_used, mn.data(), sizeof(i32) * (size_t)ns, cudaMemcpyHostToDevice, w->stream));
+		CK(cudaMemcpyAsync(W.smax + w->sliders_used, mx.data(), sizeof(i32) * (size_t)ns, cudaMemcpyHostToDevice, w->stream));
+		CK(cudaStreamSynchronize(w->stream));
+	}
+	const i32 wend = first + n_new;
+	CK(cudaMemcpyAsync(W.wend + world, &wend, sizeof(i32), cudaMemcpyHostToDevice, w->stream));
+	CK(cudaStreamSynchronize(w->stream));
+	W.n = first + n_new;
+	w->sliders_used = s; w->wires_used = q;
+	if (W.small_mode && W.n > BT_SMALL_WORLD) { /* the brute-force pair search holds one world per block */
+		W.small_mode = 0;
+		if (w->margin_opt < 0) W.margin = 32;
+	}
+	w->tree_valid = false; /* the leaf set is about to change */
+	{ int rr = raise_cache_invalid(w); if (rr) return rr; }
+	host_wrote(w);
+	CHECK_LAUNCHES(w);
+	return BT_OK;
+}
+
+int bt_world_poke(bt_world *w, const bt_poke *pokes, int32_t n) {
+	if (!w || n < 0 || (n > 0 && !pokes)) return BT_ERR_ARG;
+	if (!n) return BT_OK;
+	CK(cudaSetDevice(w->device));
+	DevWorld &W = w->W;
+	std::vector<bt_poke> raw, ops;
+	raw.reserve((size_t)n);
+	bool leafset = false;
+	i32 last_rebox = -1;
+	for (i32 i = 0; i < n; i++) {
+		const bt_poke &p = pokes[i];
+		if (p.array >= 0 && p.array < BT_A_NUM) {
+			i32 ext = 0;
+			if (p.array == BT_A_DEADLIST || p.array == BT_A_SLIDER_OFF || p.array == BT_A_WIRE_OFF || p.array == BT_A_WIRE_CAP) { snprintf(g_err, sizeof g_err, "poke %d: array %d is read-only", i, p.array); return BT_ERR_ARG; }
+			int r = array_extent(w, p.array, &ext);
+			if (r) return r;
+			if (p.index < 0 || p.index >= ext) { snprintf(g_err, sizeof g_err, "poke %d: element %d outside the %d of array %d", i, p.index, ext, p.array); return BT_ERR_ARG; }
+			raw.push_back(p);
+			if ((p.array == BT_A_TYPE || p.array == BT_A_COLLIDE) && last_rebox != p.index) {
+				bt_poke o = p; o.array = BT_OP_REBOX; ops.push_back(o); last_rebox = p.index; leafset = true;
+			}
+			if (p.array == BT_A_INLIST || p.array == BT_A_DEAD) leafset = true;
+		} else if (p.array == BT_OP_SPAWN || p.array == BT_OP_UWIRE || p.array == BT_OP_UUNWIRE) {
+			if (p.index < 0 || p.index >= W.n || (p.array != BT_OP_SPAWN && (p.v[0] < 0 || p.v[0] >= W.n))) { snprintf(g_err, sizeof g_err, "poke %d: slot out of range", i); return BT_ERR_ARG; }
+			ops.push_back(p);
+			if (p.array == BT_OP_SPAWN) leafset = true;
+		} else { snprintf(g_err, sizeof g_err, "poke %d: unknown array / operation %d", i, p.array); return BT_ERR_ARG; }
+	}
+	const i32 total = (i32)(raw.size() + ops.size());
+	if (total > w->pokes_cap) {
+		if (w->d_pokes) cudaFree(w->d_pokes);
+		w->d_pokes = NULL; w->pokes_cap = 0;
+		const i32 cap = std::max(total * 2, 1024);
+		CK(cudaMalloc(&w->d_pokes, sizeof(bt_poke) * (size_t)cap));
+		w->pokes_cap = cap;
+	}
+	if (!raw.empty()) CK(cudaMemcpyAsync(w->d_pokes, raw.data(), sizeof(bt_poke) * raw.size(), cudaMemcpyHostToDevice, w->stream));
+	if (!ops.empty()) CK(cudaMemcpyAsync(w->d_pokes + raw.size(), ops.data(), sizeof(bt_poke) * ops.size(), cudaMemcpyHostToDevice, w->stream));
+	if (!raw.empty()) LAUNCH(w, PK_EXCHANGE, k_poke_raw, nblk((i64)raw.size()), BT_BLOCK, W, w->arrays, (const bt_poke *)w->d_pokes, (i32)raw.size());
+	if (!ops.empty()) LAUNCH(w, PK_EXCHANGE, k_poke_ops, 1, 32, W, (const bt_poke *)(w->d_pokes + raw.size()), (i32)ops.size());
+	CK(cudaStreamSynchronize(w->stream)); /* raw / ops go out of scope */
+	if (leafset) {
+		w->tree_valid = false; w->ranks_valid = false;
+		int rr = raise_cache_invalid(w);
+		if (rr) return rr;
+	}
+	host_wrote(w);
+	CHECK_LAUNCHES(w);
+	return BT_OK;
+}
+
+int bt_world_set_wires(bt_world *w, int32_t slot, const int32_t *targets, int32_t n, int32_t reserve) {
+	if (!w || slot < 0 || slot >= w->W.n || n < 0 || (n > 0 && !targets) || reserve < 0) return BT_ERR_ARG;
+	CK(cudaSetDevice(w->device));
+	DevWorld &W = w->W;
+	for (i32 k = 0; k < n; k++)
+		if (targets[k] < 0 || targets[k] >= W.n) return BT_ERR_ARG;
+	i32 hdr[2] = {0, 0}; /* off, cap */
+	CK(cudaStreamSynchronize(w->stream));
+	CK(cudaMemcpy(&hdr[0], W.wire_off + slot, sizeof(i32), cudaMemcpyDeviceToHost));
+	CK(cudaMemcpy(&hdr[1], W.wire_cap + slot, sizeof(i32), cudaMemcpyDeviceToHost));
+	if (n + reserve > hdr[1]) { /* a fresh block at the end of the arena; the old one is abandoned */
+		const i32 cap = n + reserve + 2;
+		if ((i64)w->wires_used + cap > (i64)w->cap_wires + w->cap_ents) { snprintf(g_err, sizeof g_err, "bt_world_set_wires: wire arena exhausted"); return BT_ERR_CAPACITY; }
+		hdr[0] = w->wires_used; hdr[1] = cap;
+		w->wires_used += cap;
+		CK(cudaMemcpy(W.wire_off + slot, &hdr[0], sizeof(i32), cudaMemcpyHostToDevice));
+		CK(cudaMemcpy(W.wire_cap + slot, &hdr[1], sizeof(i32), cudaMemcpyHostToDevice));
+	}
+	if (n) CK(cudaMemcpy(W.wire_to + hdr[0], targets, sizeof(i32) * (size_t)n, cudaMemcpyHostToDevice));
+	CK(cudaMemcpy(W.wire_cnt + slot, &n, sizeof(i32), cudaMemcpyHostToDevice));
+	host_wrote(w);
 	return BT_OK;
 }
 

@@ -117,6 +117,13 @@ typedef struct bt_world_desc {
  * by itself when every tick handler of the world is in that set (option "device_ticks", default
  * 1; 0 = never). */
 #define BT_PHASE_TICKS 64u
+/* doPhysics in two halves, for a host that runs the crush handlers itself (they create entities):
+ * ..._ITER = flush2, integrate, broadphase and the whole resolution loop (ent.cpp:843-905);
+ * ..._END  = what follows invokeOnCrush (ent.cpp:907): flush1; flush2 (ent.cpp:909-910).
+ * BT_PHASE_PHYSICS == both, back to back.  Between the halves the host drains the events, runs
+ * `crush` (and the TEAMSELECT / LOADBLOCK push handlers) on its own `ent`s and sends what they did. */
+#define BT_PHASE_PHYSICS_ITER 128u
+#define BT_PHASE_PHYSICS_END 256u
 
 typedef struct bt_tick_stats {
 	int64_t ticks;
@@ -270,6 +277,65 @@ int bt_world_profile_read(bt_world *w, bt_profile *out, int reset);
  * treats them as NIL and counts every would-be invocation in bt_tick_stats.unsupported_events
  * (used to measure handler coverage on real levels). */
 int bt_world_set_option(bt_world *w, const char *name, int64_t value);
+
+/* ---- incremental host binding: what host/bt_glue.cpp (the `gamestate*` <-> device bridge) is built on.
+ *      The world stays resident; the host sends only what its own code changed and reads back what
+ *      the device changed.  Entities are named by SLOT: the index an upload gave them (slot i =
+ *      desc index i), or the one bt_world_grow returned.  Slots are never reused. ----
+ *
+ * Device arrays, by id.  Element type in brackets; "vec" = 4 x int32 per slot (xyz + pad).
+ * Packed words: HPHYS = whoMoves | push<<8 | pushed<<16 | crush<<24, HPAIR = onFumble | onFumbled<<8 |
+ * onPickUp<<16 | onPickedUp<<24, HTICK = tick | tickHeld<<8 (catalog ids, handlerRegistrar.h:79-187);
+ * BTN_V / BTN_V2 = ctrl.btns[0..3].v / .v2, one byte each.  ROOTKEY: gs->rootEnts order, larger = nearer
+ * the head (ent.cpp:60-66); fresh keys for host-made roots come from bt_world_next_root_phase. */
+enum {
+	BT_A_CENTER = 0, BT_A_VEL, BT_A_OLD, BT_A_DCENTER, BT_A_DVEL, BT_A_RADIUS,          /* vec           */
+	BT_A_TYPE, BT_A_COLLIDE, BT_A_NTYPE, BT_A_NCOLLIDE,                                 /* u32 per slot  */
+	BT_A_FRICTION, BT_A_HOLDER, BT_A_HOLDFLAGS, BT_A_HOLDROOT, BT_A_HOLDEE, BT_A_LLN, BT_A_LLP, /* i32   */
+	BT_A_NEWHOLDER, BT_A_NEWHOLDFLAGS, BT_A_UID, BT_A_WORLD,                            /* i32           */
+	BT_A_HPHYS, BT_A_HPAIR, BT_A_HTICK, BT_A_BTN_V, BT_A_BTN_V2,                        /* u32           */
+	BT_A_NEWDROP, BT_A_DEADMAX0, BT_A_DEADMAX1, BT_A_FULLFLUSH, BT_A_DEAD, BT_A_INLIST, /* u8            */
+	BT_A_ROOTKEY,                                                                       /* u64           */
+	BT_A_SLIDER_OFF, BT_A_WIRE_OFF, BT_A_WIRE_CAP, BT_A_WIRE_CNT,                       /* i32 per slot  */
+	BT_A_SV, BT_A_SMIN, BT_A_SMAX,                                                      /* i32 per slider */
+	BT_A_WIRE_TO,                                                                       /* i32 per wire slot */
+	BT_A_W_FLIP, BT_A_W_GAMERULES, BT_A_W_RAND,                                         /* i32 per world */
+	BT_A_DEADLIST,                                                                      /* u64: key<<32 | slot, in no order */
+	BT_A_NUM,
+	/* poke-only operations (array field of a bt_poke) */
+	BT_OP_SPAWN = 100,   /* index = fresh slot from bt_world_grow whose fields have been poked: it joins the world
+	                      * (addEnt ent.cpp:107-113: in gs->ents, a root, boxed if needsVelbox) */
+	BT_OP_UWIRE,         /* uWire(index, v[0])   entUpdaters.c:66: queued for the next flushMisc, order kept */
+	BT_OP_UUNWIRE        /* uUnwire(index, v[0]) entUpdaters.c:71 */
+};
+/* one sparse write: v[0..k) into array `array` at element `index` (k = 3 for vec, 2 for u64 lo/hi, else 1).
+ * No two writes of one call may name the same element; the BT_OP_* operations are applied after every
+ * write of the call, in the order given. */
+typedef struct bt_poke {
+	int32_t array, index;
+	int32_t v[3];
+} bt_poke;
+int bt_world_poke(bt_world *w, const bt_poke *pokes, int32_t n);
+/* `count` elements of array `array` from element `first` into dst (host memory, the array's element type). */
+int bt_world_pull(bt_world *w, int32_t array, int32_t first, int32_t count, void *dst);
+/* elements currently in use of the array's index space: slots, sliders, wire slots, worlds, dead-list entries */
+int bt_world_extent(bt_world *w, int32_t array, int32_t *count);
+/* n_new blank slots behind the ones in use (addEnt's malloc): slider storage for n_sliders[i] sliders and
+ * room for wire_cap[i] wires each.  *first_slot = slot of the first.  They stay out of the world until
+ * BT_OP_SPAWN.  `world` = the world they belong to (0 for a single gamestate). */
+int bt_world_grow(bt_world *w, int32_t n_new, const int32_t *n_sliders, const int32_t *wire_cap, int32_t world,
+                  int32_t *first_slot);
+/* replaces e->wires of one slot (list order kept); moves the block when it has outgrown its room */
+int bt_world_set_wires(bt_world *w, int32_t slot, const int32_t *targets, int32_t n, int32_t reserve);
+/* a fresh upper part for BT_A_ROOTKEY values: keys phase<<37 | k sort above every key handed out so far */
+int64_t bt_world_next_root_phase(bt_world *w);
+/* fumbles + pickups + deaths the device has done since the upload: unchanged = the hold tree did not move */
+int bt_world_tree_edits(bt_world *w, uint32_t *count);
+/* bt_world_hash widened to everything a `.sav` holds and the per-tick flush state: the words of bt_world_hash
+ * plus radius, old, friction, sliders (v, min, max), buttons (v, v2), wire targets (uids, in list order),
+ * handler ids, new*Mask, newHolder uid / flags, newDrop, dead_max, fullFlush, forced, and per world
+ * flipFlop_death, rand, gamerules.  out: [n_worlds]. */
+int bt_world_hash_full(bt_world *w, uint64_t *out);
 
 /* ---- raycast: replaces selectCast(gs, parent, look) (raycast.h:1, raycast.cpp:16-57),
  *      batched.  origin_ent[i] = index of the casting entity (its hold tree is skipped),

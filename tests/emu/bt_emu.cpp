@@ -35,6 +35,10 @@ struct Emu {
 	u32 pair_builds_at_tree;
 	int64_t pair_rebuilds, pair_patches;
 	int shuffle_seed; /* != 0: run the threads of order-sensitive kernels in a scrambled order */
+	/* incremental host binding (mirrors bt_world.cu) */
+	i32 cap_ents, cap_sliders, cap_wires;
+	i32 root_phase_ctr, sliders_used, wires_used;
+	DevArrays arrays;
 };
 
 template <typename T> static void A(Emu *E, T **p, size_t n) {
@@ -65,15 +69,24 @@ void bte_destroy(Emu *E) {
 	delete E;
 }
 
+Emu *bte_create_cap(const bt_world_desc *d, int rebuild_every, int shuffle_seed, int cap_ents, int cap_sliders, int cap_wires);
 Emu *bte_create(const bt_world_desc *d, int rebuild_every, int shuffle_seed) {
+	return bte_create_cap(d, rebuild_every, shuffle_seed, d->n_ents, d->n_sliders, d->n_wires);
+}
+/* capacities beyond the uploaded world leave room for bt_world_grow */
+Emu *bte_create_cap(const bt_world_desc *d, int rebuild_every, int shuffle_seed, int cap_ents, int cap_sliders, int cap_wires) {
+	if (cap_ents < d->n_ents || cap_sliders < d->n_sliders || cap_wires < d->n_wires) return NULL;
 	Emu *E = new Emu();
+	E->cap_ents = cap_ents; E->cap_sliders = cap_sliders; E->cap_wires = cap_wires;
+	E->root_phase_ctr = 0;
 	memset(&E->W, 0, sizeof(E->W));
 	memset(&E->st, 0, sizeof(E->st));
 	E->tree_valid = false; E->ticks_since_build = 0; E->ctrls_fused = false; E->full_flush_left = 2; E->scan_flushes_left = 2; E->rebuild_every = rebuild_every > 0 ? rebuild_every : 1;
 	E->iterations = 0; E->ticks = 0; E->shuffle_seed = shuffle_seed; E->pair_cache = 1; E->pair_rebuilds = 0; E->pair_patches = 0;
 	DevWorld &W = E->W;
-	const int n = d->n_ents, nw = d->n_worlds;
-	W.n = n; W.n_worlds = nw;
+	const int nw = d->n_worlds;
+	{
+	const int n = cap_ents; /* every per-slot array is allocated at capacity */
 	A(E, &W.wbegin, nw); A(E, &W.wend, nw); A(E, &W.flip, nw); A(E, &W.gamerules, nw); A(E, &W.rnd, nw); A(E, &W.wflush, nw); A(E, &W.wunsup, nw); A(E, &W.wties, nw);
 	A(E, &W.world, n); A(E, &W.uid, n); A(E, &W.center, n); A(E, &W.old, n); A(E, &W.vel, n); A(E, &W.radius, n);
 	A(E, &W.d_center, n); A(E, &W.d_vel, n); A(E, &W.type, n); A(E, &W.collide, n); A(E, &W.ntype, n); A(E, &W.ncollide, n);
@@ -83,9 +96,11 @@ Emu *bte_create(const bt_world_desc *d, int rebuild_every, int shuffle_seed) {
 	A(E, &W.newDrop, n); A(E, &W.dead_max0, n); A(E, &W.dead_max1, n); A(E, &W.fullFlush, n); A(E, &W.dead, n);
 	A(E, &W.inList, n); A(E, &W.needsCollision, n); A(E, &W.hasBox, n); A(E, &W.ready, n);
 	A(E, &W.forced, n); A(E, &W.forcedHoldees, n); A(E, &W.pend, n);
-	A(E, &W.slider_off, n + 1); A(E, &W.sv, d->n_sliders); A(E, &W.smin, d->n_sliders); A(E, &W.smax, d->n_sliders);
-	A(E, &W.wire_off, n + 1); A(E, &W.wire_cnt, n); A(E, &W.wire_to, d->n_wires + n);
-	A(E, &W.wireAdd, n); A(E, &W.wireRm, n);
+	A(E, &W.slider_off, n + 1); A(E, &W.sv, cap_sliders); A(E, &W.smin, cap_sliders); A(E, &W.smax, cap_sliders);
+	A(E, &W.wire_off, n + 1); A(E, &W.wire_cnt, n); A(E, &W.wire_to, cap_wires + n);
+	A(E, &W.wireAdd, n); A(E, &W.wireRm, n); A(E, &W.wire_cap, n); A(E, &W.rootKey, n); A(E, &W.wrootseq, nw);
+	W.wq_cap = 2 * n + 1024;
+	A(E, &W.wq_next, W.wq_cap); A(E, &W.wq_to, W.wq_cap);
 	A(E, &W.keys, n); A(E, &W.keys_alt, n); A(E, &W.leafEnt, n); A(E, &W.leafEnt_alt, n);
 	A(E, &W.leafParent, n); A(E, &W.nodeParent, n); A(E, &W.nodeCount, n); A(E, &W.nodes, n);
 	A(E, &W.nodeBox, n); A(E, &W.leafBox, n); A(E, &W.nodeHi, n); A(E, &W.ibox, n);
@@ -97,6 +112,23 @@ Emu *bte_create(const bt_world_desc *d, int rebuild_every, int shuffle_seed) {
 	W.serial_cap = 1 << 16; W.dead_cap = n ? n : 1; W.event_cap = 1 << 16;
 	A(E, &W.events, W.event_cap);
 	A(E, &W.serialList, W.serial_cap); A(E, &W.deadList, W.dead_cap); A(E, &W.hash, nw); A(E, &W.ctr, CT_WORDS);
+	}
+	const int n = d->n_ents;
+	W.n = n; W.n_worlds = nw;
+	{
+		void **b = E->arrays.base;
+		b[BT_A_CENTER] = W.center; b[BT_A_VEL] = W.vel; b[BT_A_OLD] = W.old; b[BT_A_DCENTER] = W.d_center; b[BT_A_DVEL] = W.d_vel;
+		b[BT_A_RADIUS] = W.radius; b[BT_A_TYPE] = W.type; b[BT_A_COLLIDE] = W.collide; b[BT_A_NTYPE] = W.ntype;
+		b[BT_A_NCOLLIDE] = W.ncollide; b[BT_A_FRICTION] = W.friction; b[BT_A_HOLDER] = W.holder; b[BT_A_HOLDFLAGS] = W.holdFlags;
+		b[BT_A_HOLDROOT] = W.holdRoot; b[BT_A_HOLDEE] = W.holdee; b[BT_A_LLN] = W.LLn; b[BT_A_LLP] = W.LLp;
+		b[BT_A_NEWHOLDER] = W.newHolder; b[BT_A_NEWHOLDFLAGS] = W.newHoldFlags; b[BT_A_UID] = W.uid; b[BT_A_WORLD] = W.world;
+		b[BT_A_HPHYS] = W.hphys; b[BT_A_HPAIR] = W.hpair; b[BT_A_HTICK] = W.htick; b[BT_A_BTN_V] = W.btn_v; b[BT_A_BTN_V2] = W.btn_v2;
+		b[BT_A_NEWDROP] = W.newDrop; b[BT_A_DEADMAX0] = W.dead_max0; b[BT_A_DEADMAX1] = W.dead_max1; b[BT_A_FULLFLUSH] = W.fullFlush;
+		b[BT_A_DEAD] = W.dead; b[BT_A_INLIST] = W.inList; b[BT_A_ROOTKEY] = W.rootKey; b[BT_A_SLIDER_OFF] = W.slider_off;
+		b[BT_A_WIRE_OFF] = W.wire_off; b[BT_A_WIRE_CAP] = W.wire_cap; b[BT_A_WIRE_CNT] = W.wire_cnt; b[BT_A_SV] = W.sv;
+		b[BT_A_SMIN] = W.smin; b[BT_A_SMAX] = W.smax; b[BT_A_WIRE_TO] = W.wire_to; b[BT_A_W_FLIP] = W.flip;
+		b[BT_A_W_GAMERULES] = W.gamerules; b[BT_A_W_RAND] = W.rnd; b[BT_A_DEADLIST] = W.deadList;
+	}
 	for (int g = 0; g < nw; g++) {
 		W.wbegin[g] = n; W.wend[g] = 0;
 		W.flip[g] = d->w_flip_flop[g]; W.gamerules[g] = d->w_gamerules[g]; W.rnd[g] = d->w_rand[g];
@@ -112,6 +144,8 @@ Emu *bte_create(const bt_world_desc *d, int rebuild_every, int shuffle_seed) {
 		V3(W.d_center, d->d_center); V3(W.d_vel, d->d_vel);
 #undef V3
 		for (int k = 0; k < 3; k++) deltas = deltas || d->d_center[3 * i + k] || d->d_vel[3 * i + k];
+		deltas = deltas || (d->new_holder[i] >= 0 && (d->new_hold_flags[i] & HOLD_FREEZE)); /* ent.cpp:176-181 */
+		if (d->holder[i] < 0) W.rootKey[i] = (u64)(n - (d->root_order[i] >= 0 ? d->root_order[i] : n - 1 - i));
 		W.type[i] = d->type_mask[i]; W.collide[i] = d->collide_mask[i];
 		W.ntype[i] = d->new_type_mask[i]; W.ncollide[i] = d->new_collide_mask[i];
 		W.friction[i] = d->friction[i]; W.holder[i] = d->holder[i]; W.holdFlags[i] = d->hold_flags[i];
@@ -139,9 +173,11 @@ Emu *bte_create(const bt_world_desc *d, int rebuild_every, int shuffle_seed) {
 		i32 o = 0;
 		for (int i = 0; i < n; i++) {
 			W.wire_off[i] = o;
-			o += W.wire_cnt[i] + (d->handlers[(size_t)BT_H_NUM * i + BT_H_ONPICKUP] == 1 ? 1 : 0);
+			W.wire_cap[i] = W.wire_cnt[i] + (d->handlers[(size_t)BT_H_NUM * i + BT_H_ONPICKUP] == 1 ? 1 : 0);
+			o += W.wire_cap[i];
 		}
 		W.wire_off[n] = o;
+		E->wires_used = o; E->sliders_used = d->n_sliders;
 	}
 	for (int s = 0; s < d->n_sliders; s++) { W.sv[s] = d->slider_v[s]; W.smin[s] = d->slider_min[s]; W.smax[s] = d->slider_max[s]; }
 	for (int i = 0; i < n; i++)
@@ -226,11 +262,14 @@ static void flush1(Emu *E, bool hint) {
 		E->scan_flushes_left--;
 		for (i32 e = 0; e < W.n; e++) t_flush_scan(W, e);
 	}
+	W.root_phase = ++E->root_phase_ctr;
 	for (i32 g = 0; g < W.n_worlds; g++) t_flush_serial(W, g, E->st);
+	E->st.rk_ordered = 0;
 	for (i32 e = 0; e < W.n; e++) t_flush_misc(W, e);
+	W.ctr[CT_WQ_N] = 0;
 }
 
-static int do_physics(Emu *E, bool gravity) {
+static int do_physics_iter(Emu *E, bool gravity) {
 	DevWorld &W = E->W;
 	const i32 n = W.n;
 	if (!E->deltas_pending) {
@@ -299,6 +338,7 @@ static int do_physics(Emu *E, bool gravity) {
 		if (W.ctr[CT_ERROR]) return -(int)W.ctr[CT_ERROR];
 		/* the resolve kernels run speculatively behind the narrow phase (no-ops without proposals) */
 		for (i32 e = 0; e < n; e++) t_decide(W, e);
+		W.root_phase = ++E->root_phase_ctr;
 		{
 			std::vector<i32> o = order(E, n);
 			for (i32 e : o) t_push(W, e, E->st);
@@ -311,6 +351,13 @@ static int do_physics(Emu *E, bool gravity) {
 		it++;
 		if (++guard > 100000) return BT_ERR_OVERFLOW;
 	}
+	return 0;
+}
+
+/* what follows invokeOnCrush: flush1; flush2 (ent.cpp:909-910) */
+static int do_physics_end(Emu *E) {
+	DevWorld &W = E->W;
+	const i32 n = W.n;
 	W.flush_stage = 1;
 	flush1(E, W.ctr[CT_FLUSH_HINT] != 0);
 	W.flush_stage = 0;
@@ -334,7 +381,7 @@ int bte_step(Emu *E, uint32_t phases) {
 		for (i32 e = 0; e < W.n; e++) t_world_rules(W, e);
 		if (E->full_flush_left < 1) E->full_flush_left = 1;
 	}
-	E->ctrls_fused = (phases & BT_PHASE_CTRLS) && (phases & BT_PHASE_PHYSICS) && !E->deltas_pending && !(phases & BT_PHASE_TICKS);
+	E->ctrls_fused = (phases & BT_PHASE_CTRLS) && (phases & (BT_PHASE_PHYSICS | BT_PHASE_PHYSICS_ITER)) && !E->deltas_pending && !(phases & BT_PHASE_TICKS);
 	if ((phases & BT_PHASE_CTRLS) && !E->ctrls_fused) for (i32 e = 0; e < W.n; e++) t_pre(W, e, phases);
 	if (phases & BT_PHASE_TICKS) {
 		std::vector<i32> o = order(E, W.n);
@@ -344,12 +391,16 @@ int bte_step(Emu *E, uint32_t phases) {
 		if (E->full_flush_left < 1) E->full_flush_left = 1;
 	}
 	if (phases & BT_PHASE_PREP) flush1(E, false);
-	if ((phases & BT_PHASE_GRAVITY) && !(phases & BT_PHASE_PHYSICS)) {
+	if ((phases & BT_PHASE_GRAVITY) && !(phases & (BT_PHASE_PHYSICS | BT_PHASE_PHYSICS_ITER))) {
 		for (i32 e = 0; e < W.n; e++) t_gravity(W, e);
 		E->deltas_pending = true;
 	}
-	if (phases & BT_PHASE_PHYSICS) {
-		int r = do_physics(E, (phases & BT_PHASE_GRAVITY) != 0);
+	if (phases & (BT_PHASE_PHYSICS | BT_PHASE_PHYSICS_ITER)) {
+		int r = do_physics_iter(E, (phases & BT_PHASE_GRAVITY) != 0);
+		if (r) return r;
+	}
+	if (phases & (BT_PHASE_PHYSICS | BT_PHASE_PHYSICS_END)) {
+		int r = do_physics_end(E);
 		if (r) return r;
 		E->ticks++;
 	}
@@ -482,6 +533,212 @@ int bte_raycast(Emu *E, const int32_t *origin, const int32_t *look, int32_t n_ra
 		winner[i] = win >= 0 ? slot2rank[win] : -1;
 	}
 	return ctr[CT_ERROR] ? -(int)ctr[CT_ERROR] : 0;
+}
+
+} /* extern "C" */
+
+/* ---------------------------------------------------------------------------------------------
+ * The part of the C ABI (include/bittoss_b200.h) the host binding host/bt_glue.cpp is built on, served by
+ * the emulator: lets the `-m "not gpu"` tests run the reference's own host code (tick handlers, players,
+ * spawners) against the kernel bodies on a machine without a GPU.  Same entry-point names as
+ * libbittoss_b200.so; the glue is bound to one library or the other at run time (bt_glue_bind).
+ * --------------------------------------------------------------------------------------------- */
+struct bt_world {
+	Emu *E;
+	int cap_ents, cap_sliders, cap_wires, cap_worlds;
+	bool poked;
+};
+static char emu_err[256] = "";
+typedef long long i64;
+
+extern "C" {
+
+const char *bt_version(void) { return "bittoss_b200 kernel-body emulator (tests only)"; }
+const char *bt_last_error(void) { return emu_err; }
+
+int bt_world_create(bt_world **out, int device, int32_t max_ents, int32_t max_sliders, int32_t max_wires, int32_t max_worlds) {
+	(void)device;
+	if (!out || max_ents < 0 || max_worlds < 1) return BT_ERR_ARG;
+	bt_world *w = new bt_world();
+	w->E = NULL; w->cap_ents = max_ents; w->cap_sliders = max_sliders; w->cap_wires = max_wires; w->cap_worlds = max_worlds; w->poked = false;
+	*out = w;
+	return BT_OK;
+}
+void bt_world_destroy(bt_world *w) {
+	if (!w) return;
+	bte_destroy(w->E);
+	delete w;
+}
+int bt_world_upload(bt_world *w, const bt_world_desc *d) {
+	if (!w || !d) return BT_ERR_ARG;
+	if (d->n_ents > w->cap_ents || d->n_sliders > w->cap_sliders || d->n_wires > w->cap_wires || d->n_worlds > w->cap_worlds) return BT_ERR_CAPACITY;
+	bte_destroy(w->E);
+	w->E = bte_create_cap(d, 16, 0, w->cap_ents, w->cap_sliders, w->cap_wires);
+	return w->E ? BT_OK : BT_ERR_ARG;
+}
+int bt_world_set_option(bt_world *w, const char *name, int64_t value) {
+	if (!w || !w->E) return BT_ERR_ARG;
+	if (!strcmp(name, "shuffle_seed")) { w->E->shuffle_seed = (int)value; return BT_OK; }
+	bte_set_option(w->E, name, value);
+	return BT_OK;
+}
+int bt_world_step(bt_world *w, uint32_t phases) {
+	if (!w || !w->E) return BT_ERR_ARG;
+	int r = bte_step(w->E, phases);
+	if (r) snprintf(emu_err, sizeof emu_err, "emulated step failed: %d", r);
+	return r;
+}
+int bt_world_hash(bt_world *w, uint64_t *out) { if (!w || !w->E) return BT_ERR_ARG; bte_hash(w->E, out); return BT_OK; }
+int bt_world_hash_full(bt_world *w, uint64_t *out) {
+	if (!w || !w->E) return BT_ERR_ARG;
+	DevWorld &W = w->E->W;
+	std::vector<u64> cnt(W.n_worlds, 0);
+	for (int g = 0; g < W.n_worlds; g++) out[g] = 0;
+	for (i32 e = 0; e < W.n; e++)
+		if (W.inList[e]) { out[W.world[e]] += bt_ent_hash_full(W, e); cnt[W.world[e]]++; }
+	for (int g = 0; g < W.n_worlds; g++) {
+		u64 h = bt_mix64((u64)(u32)W.flip[g] + 0x9E3779B97F4A7C15ULL);
+		h = bt_mix64(h + (u64)(u32)W.rnd[g] + 0x9E3779B97F4A7C15ULL);
+		h = bt_mix64(h + (u64)(u32)W.gamerules[g] + 0x9E3779B97F4A7C15ULL);
+		out[g] += bt_mix64(cnt[g]) + h;
+	}
+	return BT_OK;
+}
+int bt_world_drain_events(bt_world *w, bt_event *out, int32_t max, int32_t *n) {
+	if (!w || !w->E || !n) return BT_ERR_ARG;
+	DevWorld &W = w->E->W;
+	int cnt = (int)W.ctr[CT_EVENT_N];
+	if (cnt > max) { *n = cnt; return BT_ERR_CAPACITY; }
+	std::vector<int32_t> rows((size_t)5 * (cnt ? cnt : 1));
+	std::vector<int4> ev(W.events, W.events + cnt);
+	std::stable_sort(ev.begin(), ev.end(), [](const int4 &a, const int4 &b) {
+		int ka = a.x >> 8, kb = b.x >> 8;
+		if (ka != kb) return ka < kb;
+		return ka == 3 && (u32)a.w > (u32)b.w;
+	});
+	for (int i = 0; i < cnt; i++) {
+		out[i].kind = ev[i].x >> 8; out[i].handler = ev[i].x & 0xff; out[i].world = W.world[ev[i].y];
+		out[i].me_uid = W.uid[ev[i].y]; out[i].him_uid = W.uid[ev[i].z]; out[i].arg = ev[i].w;
+	}
+	W.ctr[CT_EVENT_N] = 0;
+	*n = cnt;
+	return BT_OK;
+}
+
+static int emu_elem_bytes(int a) {
+	if (a >= BT_A_CENTER && a <= BT_A_RADIUS) return 16;
+	if (a >= BT_A_NEWDROP && a <= BT_A_INLIST) return 1;
+	if (a == BT_A_ROOTKEY || a == BT_A_DEADLIST) return 8;
+	return 4;
+}
+int bt_world_extent(bt_world *w, int32_t a, int32_t *count) {
+	if (!w || !w->E || !count || a < 0 || a >= BT_A_NUM) return BT_ERR_ARG;
+	Emu *E = w->E;
+	if (a >= BT_A_SV && a <= BT_A_SMAX) *count = E->sliders_used;
+	else if (a == BT_A_WIRE_TO) *count = E->wires_used;
+	else if (a >= BT_A_W_FLIP && a <= BT_A_W_RAND) *count = E->W.n_worlds;
+	else if (a == BT_A_SLIDER_OFF) *count = E->W.n + 1;
+	else if (a == BT_A_DEADLIST) *count = (i32)E->W.ctr[CT_DEAD_N];
+	else *count = E->W.n;
+	return BT_OK;
+}
+int bt_world_pull(bt_world *w, int32_t a, int32_t first, int32_t count, void *dst) {
+	i32 ext = 0;
+	int r = bt_world_extent(w, a, &ext);
+	if (r) return r;
+	if (first < 0 || count < 0 || first + count > ext) return BT_ERR_ARG;
+	const size_t eb = (size_t)emu_elem_bytes(a);
+	memcpy(dst, (const char *)w->E->arrays.base[a] + eb * (size_t)first, eb * (size_t)count);
+	return BT_OK;
+}
+int64_t bt_world_next_root_phase(bt_world *w) { return w && w->E ? (int64_t)++w->E->root_phase_ctr : (int64_t)BT_ERR_ARG; }
+int bt_world_tree_edits(bt_world *w, uint32_t *count) {
+	if (!w || !w->E || !count) return BT_ERR_ARG;
+	*count = w->E->W.ctr[CT_TREE_EDITS];
+	return BT_OK;
+}
+static void emu_host_wrote(Emu *E) {
+	E->deltas_pending = true;
+	if (E->full_flush_left < 2) E->full_flush_left = 2;
+	if (E->scan_flushes_left < 2) E->scan_flushes_left = 2;
+}
+static void emu_leafset_changed(Emu *E) {
+	E->tree_valid = false;
+	E->W.ctr[CT_CACHE_INVALID] = 1; E->W.ctr[CT_CACHE_FULL] = 1;
+}
+int bt_world_grow(bt_world *w, int32_t n_new, const int32_t *n_sliders, const int32_t *wire_cap, int32_t world, int32_t *first_slot) {
+	if (!w || !w->E || n_new < 0 || !first_slot) return BT_ERR_ARG;
+	Emu *E = w->E;
+	DevWorld &W = E->W;
+	if (W.n_worlds > 1) return BT_ERR_UNSUPPORTED;
+	*first_slot = W.n;
+	if (!n_new) return BT_OK;
+	i64 ns = 0, nwc = 0;
+	for (i32 i = 0; i < n_new; i++) { ns += n_sliders[i]; nwc += wire_cap[i]; }
+	if ((i64)W.n + n_new > E->cap_ents || E->sliders_used + ns > E->cap_sliders || E->wires_used + nwc > (i64)E->cap_wires + E->cap_ents) return BT_ERR_CAPACITY;
+	i32 s = E->sliders_used, q = E->wires_used;
+	const i32 first = W.n;
+	for (i32 i = 0; i < n_new; i++) {
+		const i32 e = first + i;
+		t_grow_init(W, e, world);
+		W.slider_off[e] = s; W.wire_off[e] = q; W.wire_cap[e] = wire_cap[i];
+		for (i32 k = 0; k < n_sliders[i]; k++) { W.sv[s + k] = 0; W.smin[s + k] = INT32_MAX; W.smax[s + k] = INT32_MIN; }
+		s += n_sliders[i]; q += wire_cap[i];
+	}
+	W.slider_off[first + n_new] = s;
+	W.n = first + n_new;
+	W.wend[world] = W.n;
+	E->sliders_used = s; E->wires_used = q;
+	if (W.n > BT_SMALL_WORLD) { E->small_ok = false; W.small_mode = 0; }
+	emu_leafset_changed(E);
+	emu_host_wrote(E);
+	return BT_OK;
+}
+int bt_world_poke(bt_world *w, const bt_poke *pokes, int32_t n) {
+	if (!w || !w->E || n < 0) return BT_ERR_ARG;
+	Emu *E = w->E;
+	DevWorld &W = E->W;
+	std::vector<bt_poke> raw, ops;
+	bool leafset = false;
+	i32 last_rebox = -1;
+	for (i32 i = 0; i < n; i++) {
+		const bt_poke &p = pokes[i];
+		if (p.array >= 0 && p.array < BT_A_NUM) {
+			i32 ext = 0;
+			if (p.array == BT_A_DEADLIST || p.array == BT_A_SLIDER_OFF || p.array == BT_A_WIRE_OFF || p.array == BT_A_WIRE_CAP) return BT_ERR_ARG;
+			bt_world_extent(w, p.array, &ext);
+			if (p.index < 0 || p.index >= ext) { snprintf(emu_err, sizeof emu_err, "poke %d: element %d outside the %d of array %d", i, p.index, ext, p.array); return BT_ERR_ARG; }
+			raw.push_back(p);
+			if ((p.array == BT_A_TYPE || p.array == BT_A_COLLIDE) && last_rebox != p.index) {
+				bt_poke o = p; o.array = BT_OP_REBOX; ops.push_back(o); last_rebox = p.index; leafset = true;
+			}
+			if (p.array == BT_A_INLIST || p.array == BT_A_DEAD) leafset = true;
+		} else if (p.array == BT_OP_SPAWN || p.array == BT_OP_UWIRE || p.array == BT_OP_UUNWIRE) {
+			if (p.index < 0 || p.index >= W.n) return BT_ERR_ARG;
+			ops.push_back(p);
+			if (p.array == BT_OP_SPAWN) leafset = true;
+		} else return BT_ERR_ARG;
+	}
+	for (i32 t = 0; t < (i32)raw.size(); t++) t_poke_raw(W, E->arrays, raw.data(), t, (i32)raw.size());
+	for (const bt_poke &p : ops) t_poke_op(W, p);
+	if (leafset) emu_leafset_changed(E);
+	emu_host_wrote(E);
+	return W.ctr[CT_ERROR] ? -(int)W.ctr[CT_ERROR] : BT_OK;
+}
+int bt_world_set_wires(bt_world *w, int32_t slot, const int32_t *targets, int32_t n, int32_t reserve) {
+	if (!w || !w->E || slot < 0 || slot >= w->E->W.n || n < 0) return BT_ERR_ARG;
+	Emu *E = w->E;
+	DevWorld &W = E->W;
+	if (n + reserve > W.wire_cap[slot]) {
+		const i32 cap = n + reserve + 2;
+		if ((i64)E->wires_used + cap > (i64)E->cap_wires + E->cap_ents) return BT_ERR_CAPACITY;
+		W.wire_off[slot] = E->wires_used; W.wire_cap[slot] = cap;
+		E->wires_used += cap;
+	}
+	for (i32 k = 0; k < n; k++) W.wire_to[W.wire_off[slot] + k] = targets[k];
+	W.wire_cnt[slot] = n;
+	emu_host_wrote(E);
+	return BT_OK;
 }
 
 } /* extern "C" */
