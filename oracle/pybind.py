@@ -85,6 +85,7 @@ class RefLib:
         L.btref_export.argtypes = [C.POINTER(BtWorldDesc)]
         L.btref_export_at.argtypes = [C.POINTER(BtWorldDesc), C.c_int32, C.c_int32, C.c_int32, C.c_int32]
         L.btref_hash.restype = C.c_uint64
+        L.btref_hash_full.restype = C.c_uint64
         L.btref_selectcast_batch.argtypes = [_i32p, _i32p, C.c_int32, _i32p]
         L.btref_time_steps.argtypes = [C.c_int, C.c_int32, C.POINTER(C.c_int64)]
         L.btref_time_steps.restype = C.c_double
@@ -150,6 +151,9 @@ class RefLib:
         """what: 0 uDrop, 1 uDead, 2 uPickup(uid picks up other, arg = hold flags)"""
         assert self.L.btref_lab_request(uid, what, other, arg) == 0
 
+    def lab_real_crush(self, on=True):
+        self.L.btref_lab_real_crush(int(on))
+
     def lab_record_all_crushes(self):
         return int(self.L.btref_lab_record_all_crushes())
 
@@ -194,6 +198,10 @@ class RefLib:
 
     def hash(self):
         return int(self.L.btref_hash())
+
+    def hash_full(self):
+        """bt_world_hash_full restated over the reference's `ent`s (everything a .sav holds + the flush state)"""
+        return int(self.L.btref_hash_full())
 
     def count(self):
         a, b, c = C.c_int32(), C.c_int32(), C.c_int32()

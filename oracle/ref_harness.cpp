@@ -280,6 +280,11 @@ static void lab_crush_recorder(gamestate *gs, ent *me) {
 	lab_crush_log.push_back(cur->uid.count(me) ? cur->uid[me] : -1);
 }
 
+/* 1: btref_lab_set_handlers installs the catalog's own crush handler instead of the recorder (free-running
+ * tests want flag_crush / platform_crush to really run: they create entities and write sliders) */
+static int lab_real_crush = 0;
+void btref_lab_real_crush(int on) { lab_real_crush = on; }
+
 /* ids < 0 leave the slot alone.  pair = {onFumble, onFumbled, onPickUp, onPickedUp} */
 int btref_lab_set_handlers(int32_t uid, int push, int pushed, int crush, const int32_t *pair, int tick, int tickHeld) {
 	ent *e = by_uid(uid);
@@ -287,7 +292,8 @@ int btref_lab_set_handlers(int32_t uid, int push, int pushed, int crush, const i
 	if (push >= 0) e->push = pushHandlers.get(push);
 	if (pushed >= 0) e->pushed = pushed ? pushedHandlers.get(pushed) : NULL;
 	if (crush >= 0) {
-		if (crush) { e->crush = lab_crush_recorder; lab_crush_id[e] = crush; }
+		if (crush && lab_real_crush) e->crush = crushHandlers.get(crush);
+		else if (crush) { e->crush = lab_crush_recorder; lab_crush_id[e] = crush; }
 		else e->crush = NULL;
 	}
 	if (pair) {
@@ -664,6 +670,51 @@ uint64_t btref_hash(void) {
 		n++;
 	}
 	return sum + mix64((uint64_t)n);
+}
+
+/* full-state hash, bt_world_hash_full of include/bittoss_b200.h restated over the reference's `ent`s: the ten
+ * words above, then radius, old, friction, new*Mask, packed handler ids, buttons v / v2, newHolder uid (-2 = the
+ * entity itself, entUpdaters.c:51) and flags, newDrop | dead_max[0]<<8 | dead_max[1]<<16 | fullFlush<<24, sliders
+ * (count; v, min, max each), wires (count; uid each); plus mix of flipFlop_death, rand, gamerules per world */
+static inline uint64_t hword(uint64_t h, int32_t w) { return mix64(h + (uint64_t)(uint32_t)w + 0x9E3779B97F4A7C15ULL); }
+uint64_t btref_hash_full(void) {
+	RefWorld *w = cur;
+	gamestate *gs = w->gs;
+	uint64_t sum = 0;
+	int64_t n = 0;
+	auto uid_live = [&](ent *p) -> int32_t { return p && !p->dead && w->uid.count(p) ? w->uid[p] : -1; };
+	for (ent *e = gs->ents; e; e = e->ll.n) {
+		int32_t wd[10] = {e->center[0], e->center[1], e->center[2], e->vel[0], e->vel[1], e->vel[2],
+		                  (int32_t)e->typeMask, (int32_t)e->collideMask, uid_live(e->holder), e->holdFlags};
+		uint64_t h = hash_words(w->uid.count(e) ? w->uid[e] : -1, wd, 10);
+		for (int k = 0; k < 3; k++) h = hword(h, e->radius[k]);
+		for (int k = 0; k < 3; k++) h = hword(h, e->old[k]);
+		h = hword(h, e->friction);
+		h = hword(h, (int32_t)e->newTypeMask); h = hword(h, (int32_t)e->newCollideMask);
+		uint32_t crush_id = e->crush ? (e->crush == lab_crush_recorder ? lab_crush_id[e] : crushHandlers.reverseLookup(e->crush)) : 0;
+		h = hword(h, (int32_t)((uint32_t)whoMovesHandlers.reverseLookup(e->whoMoves) | ((uint32_t)pushHandlers.reverseLookup(e->push) << 8) |
+		                       ((uint32_t)(e->pushed ? pushedHandlers.reverseLookup(e->pushed) : 0) << 16) | (crush_id << 24)));
+		h = hword(h, (int32_t)((uint32_t)entPairHandlers.reverseLookup(e->onFumble) | ((uint32_t)entPairHandlers.reverseLookup(e->onFumbled) << 8) |
+		                       ((uint32_t)entPairHandlers.reverseLookup(e->onPickUp) << 16) | ((uint32_t)entPairHandlers.reverseLookup(e->onPickedUp) << 24)));
+		h = hword(h, (int32_t)((uint32_t)(e->tick ? tickHandlers.reverseLookup(e->tick) : 0) | ((uint32_t)(e->tickHeld ? tickHandlers.reverseLookup(e->tickHeld) : 0) << 8)));
+		uint32_t bv = 0, bv2 = 0;
+		for (int k = 0; k < 4; k++) { bv |= (uint32_t)(uint8_t)e->ctrl.btns[k].v << (8 * k); bv2 |= (uint32_t)(uint8_t)e->ctrl.btns[k].v2 << (8 * k); }
+		h = hword(h, (int32_t)bv); h = hword(h, (int32_t)bv2);
+		h = hword(h, e->newHolder == e ? -2 : uid_live(e->newHolder));
+		h = hword(h, e->newHolder ? e->newHoldFlags : 0);
+		h = hword(h, (int32_t)(uint8_t)e->newDrop | ((int32_t)(uint8_t)e->dead_max[0] << 8) | ((int32_t)(uint8_t)e->dead_max[1] << 16) |
+		                 ((int32_t)(uint8_t)e->fullFlush << 24));
+		h = hword(h, e->numSliders);
+		for (int k = 0; k < e->numSliders; k++) { h = hword(h, e->sliders[k].v); h = hword(h, e->sliders[k].min); h = hword(h, e->sliders[k].max); }
+		h = hword(h, e->wires.num);
+		for (int k = 0; k < e->wires.num; k++) h = hword(h, uid_live(e->wires[k]));
+		sum += h;
+		n++;
+	}
+	uint64_t g = mix64((uint64_t)(uint32_t)gs->flipFlop_death + 0x9E3779B97F4A7C15ULL);
+	g = hword(g, gs->rand);
+	g = hword(g, gs->gamerules);
+	return sum + mix64((uint64_t)n) + g;
 }
 
 int32_t btref_tick_index(void) { return cur->tick; }

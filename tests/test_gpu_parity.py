@@ -62,6 +62,43 @@ def test_cuda_100k_stack_vs_oracle(bt, oracle_lib):
     w.close()
 
 
+def _golden_stream(name):
+    import os
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", name))
+    return z, [int(x) for x in z["hashes"]]
+
+
+def test_cuda_1m_stack_vs_reference(bt):
+    """BASELINE.json configs[2] AT ITS NAMED SIZE against the unmodified reference: 1 000 000 cubes + 6 400 ground tiles,
+    the exact world bench.py times on rank 0, 75 ticks (50 settle + 5 warm-up + 20 timed) of per-tick hashes from
+    tests/golden/stack1m_ref_hashes.npz (made by tests/golden/make_stack1m_ref.py from oracle/_ref: 15 minutes of CPU)"""
+    z, ref = _golden_stream("stack1m_ref_hashes.npz")
+    wa = bt.synth_boxstack(int(z["cubes"]), int(z["height"]), int(z["seed"]), int(z["push_every"]), int(z["push_max"]))
+    assert wa.n == int(z["entities"])
+    w = bt.World(wa)
+    got = [int(x) for x in w.tick(75, hashes=True)[:, 0]]
+    assert got == ref[:75], "first differing tick: %d" % next(i for i in range(75) if got[i] != ref[i])
+    assert w.stats()["live_ents"] == int(z["live"][74])
+    w.close()
+
+
+def test_cuda_1m_pushall_vs_reference(bt):
+    """the same world with the top cube of EVERY column kicked (250 000 sliding cubes: pair lists are patched and
+    rebuilt while they move), against the reference's stream for it"""
+    import os
+    if not os.path.exists(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "stack1m_pushall_ref_hashes.npz")):
+        pytest.skip("fixture not generated")
+    z, ref = _golden_stream("stack1m_pushall_ref_hashes.npz")
+    wa = bt.synth_boxstack(int(z["cubes"]), int(z["height"]), int(z["seed"]), int(z["push_every"]), int(z["push_max"]))
+    w = bt.World(wa)
+    n = len(ref)
+    got = [int(x) for x in w.tick(n, hashes=True)[:, 0]]
+    assert got == ref, "first differing tick: %d" % next(i for i in range(n) if got[i] != ref[i])
+    st = w.stats()
+    assert st["pair_builds"] + st["pair_patches"] > 1
+    w.close()
+
+
 def test_cuda_1m_stack_properties(bt):
     """full BASELINE size: no oracle run (minutes on a CPU); size-independent properties:
     determinism run-to-run, independence from the tree rebuild period, entity conservation"""
