@@ -85,10 +85,15 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def cpu_baseline(n_cubes, warm_ticks, ticks, settle=0):
+REF_HASH_FILE = os.path.join(os.environ.get("TMPDIR", "/tmp"), "bittoss_b200_reference_arm_hashes_%d.json")
+GOLDEN_1M = os.path.join(ROOT, "tests", "golden", "stack1m_ref_hashes.npz")
+
+
+def cpu_baseline(n_cubes, warm_ticks, ticks, settle=0, keep_hashes=False):
     """The UNMODIFIED reference's CPU tick (oracle/_ref) when it was compiled, else the C port."""
     from oracle import pybind
     cores = 1  # the reference tick is single-threaded and non-reentrant (ent.cpp:17, velbox/box.cpp:17-18)
+    hashes = []
     if pybind.have_ref():
         with pybind.stdout_to_stderr():  # the reference chats on stdout ("Safety crush!" ...)
             R = pybind.RefLib()
@@ -96,7 +101,17 @@ def cpu_baseline(n_cubes, warm_ticks, ticks, settle=0):
             R.make_boxstack(n_cubes, 4, 777, 64, 60)
             for _ in range(settle + warm_ticks):
                 R.step(1)
-            secs, et = R.time_steps(ticks, 1)
+                if keep_hashes:
+                    hashes.append(R.hash())
+            if keep_hashes:  # tick by tick, so that every tick's state hash can be kept (the hash walk is outside the clock)
+                secs, et = 0.0, 0
+                for _ in range(ticks):
+                    s1, e1 = R.time_steps(1, 1)
+                    secs += s1
+                    et += e1
+                    hashes.append(R.hash())
+            else:
+                secs, et = R.time_steps(ticks, 1)
         kind = "reference"
     else:
         import bittoss_b200
@@ -106,28 +121,85 @@ def cpu_baseline(n_cubes, warm_ticks, ticks, settle=0):
             ow.step(31)
         secs, et = ow.time_steps(ticks)
         kind = "port"
-    return {"value": et / secs, "unit": UNIT, "cores": cores, "kind": kind, "seconds": round(secs, 3),
-            "sample": "%d whole ticks of the %d-cube box-stack world after %d settle + %d warm-up ticks, 1 thread"
-                      % (ticks, n_cubes, settle, warm_ticks)}
+    out = {"value": et / secs, "unit": UNIT, "cores": cores, "kind": kind, "seconds": round(secs, 3),
+           "sample": "%d whole ticks of the %d-cube box-stack world after %d settle + %d warm-up ticks, 1 thread"
+                     % (ticks, n_cubes, settle, warm_ticks)}
+    if keep_hashes:
+        out["_hashes"] = hashes
+    return out
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    ticks = args.steps + args.warmup + args.settle
-    # bounded sample: keep the whole run within ~2.5 minutes at ~4 us per entity-tick on one core
-    n_cubes = int(min(args.entities, max(20000, 150.0 / (ticks * 4e-6))))
-    cb = cpu_baseline(n_cubes, args.warmup, args.steps, args.settle)
+    # the SAME world the CUDA arm times (configs[2] at its named size): about 3 s per tick at 1 M cubes on one core, so
+    # settle + warm-up + K timed ticks is a few minutes; the per-tick state hashes are left behind for the CUDA arm of
+    # the same box to compare its own stream with (`parity.vs_reference_arm` in its line)
+    n_cubes = int(args.entities)
+    cb = cpu_baseline(n_cubes, args.warmup, args.steps, args.settle, keep_hashes=True)
+    hashes = cb.pop("_hashes", [])
+    try:
+        with open(REF_HASH_FILE % n_cubes, "w") as f:
+            json.dump({"cubes": n_cubes, "seed": 777, "height": 4, "push_every": 64, "push_max": 60, "kind": cb["kind"],
+                       "hashes": ["%016x" % h for h in hashes]}, f)
+    except OSError:
+        pass
     line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * cb["seconds"] / max(1, args.steps),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
-            "config": {"workload": "synthetic box-stack world, gravity + pushes (BASELINE.json configs[2])",
-                       "entities": n_cubes, "height": 4, "settle_ticks": args.settle, "sample": cb["sample"]},
+            "config": {"workload": "synthetic 1M-entity integer AABB box-stack world with gravity and pushes "
+                                   "(BASELINE.json configs[2]), one independent world per GPU",
+                       "cubes": n_cubes, "height": 4, "push_every": 64, "push_max": 60, "settle_ticks": args.settle,
+                       "sample": cb["sample"], "state_hashes_kept": len(hashes)},
             "cpu_baseline": cb,
             "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     emit(line)
+
+
+def parity_record(bittoss_b200, args, device, checkpoints):
+    """Bit-exactness of THIS run against the unmodified reference at the named size (rank 0: seed 777).
+    `checkpoints` = {ticks done: state hash} taken around the timed region of the benchmarked world itself; a second
+    world of the same recipe is then replayed with a hash after EVERY tick (outside every clock).  Both are compared
+    with (a) the committed stream tests/golden/stack1m_ref_hashes.npz, written by tests/golden/make_stack1m_ref.py from
+    oracle/_ref, and (b) the stream the reference arm of this bench left behind on this box, if it ran here."""
+    import numpy as np
+    total = args.settle + args.warmup + args.steps
+    rec = {"ticks_checked": 0, "equal": None, "against": []}
+    streams = []
+    if args.entities == 1000000 and os.path.exists(GOLDEN_1M):
+        z = np.load(GOLDEN_1M)
+        if int(z["cubes"]) == args.entities:
+            streams.append(("tests/golden/stack1m_ref_hashes.npz (unmodified reference, %d cubes, committed)" % args.entities,
+                            [int(x) for x in z["hashes"]]))
+    rf = REF_HASH_FILE % args.entities
+    if os.path.exists(rf):
+        try:
+            j = json.load(open(rf))
+            if j.get("cubes") == args.entities and j.get("kind") == "reference":
+                streams.append(("reference arm of this bench on this box (%s)" % rf, [int(h, 16) for h in j["hashes"]]))
+        except (OSError, ValueError, KeyError):
+            pass
+    if not streams:
+        rec["against"] = ["no reference stream for %d cubes on this box" % args.entities]
+        return rec
+    w2 = bittoss_b200.World(bittoss_b200.synth_boxstack(args.entities, 4, 777, 64, 60), device=device)
+    w2.set_option("rebuild_every", args.rebuild_every)
+    mine = [int(x) for x in w2.tick(total, hashes=True)[:, 0]]
+    w2.close()
+    equal, checked = True, 0
+    for name, ref in streams:
+        k = min(len(ref), total)
+        ok = mine[:k] == ref[:k]
+        cp_ok = all(t - 1 >= len(ref) or ref[t - 1] == h for t, h in checkpoints.items() if t >= 1)
+        rec["against"].append({"stream": name, "ticks": k, "equal": bool(ok), "timed_world_checkpoints_equal": bool(cp_ok),
+                               "first_difference": None if ok else next(i for i in range(k) if mine[i] != ref[i])})
+        equal = equal and ok and cp_ok
+        checked = max(checked, k)
+    rec["ticks_checked"], rec["equal"] = checked, bool(equal)
+    rec["checkpoints"] = {str(t): "%016x" % h for t, h in sorted(checkpoints.items())}
+    return rec
 
 
 def run_cuda(args):
@@ -167,17 +239,20 @@ def run_cuda(args):
     #      both phases"): the cubes start 100-164 units apart and drop onto each other ----
     settle_ms = w.tick_timed(args.settle) if args.settle > 0 else 0.0
     settle_stats = w.stats(reset=True)
+    checkpoints = {args.settle: int(w.hash()[0])}
     # ---- (1) device-resident throughput: `value` ----
     sampler = ClockSampler(local_rank)
     sampler.start()  # ahead of the warm-up, so that nvidia-smi is already reporting when the timed region begins
     w.tick(args.warmup)
     w.stats(reset=True)
+    checkpoints[args.settle + args.warmup] = int(w.hash()[0])
     barrier()
     sampler.mark()
     ms = w.tick_timed(args.steps)
     barrier()
     st = w.stats()
     h_final = w.hash()[0]
+    checkpoints[args.settle + args.warmup + args.steps] = int(h_final)
     # K ticks of 0.8 ms are over before nvidia-smi's next sample: when the timed region was shorter than
     # 0.6 s the SAME ticks keep running, untimed, right behind it until the sampler has 8 readings under that
     # load (3 s at most; value / ms_per_step are already fixed; the state hash above was taken before)
@@ -291,6 +366,7 @@ def run_cuda(args):
         if world_size == 1 and not args.no_cpu_baseline:
             # bounded sample of the same workload (same recipe, settle included), sized for ~30 s
             cb = cpu_baseline(min(args.entities, 100000), 1, args.cpu_ticks, args.settle)
+        parity = parity_record(bittoss_b200, args, local_rank, checkpoints) if not args.no_parity else None
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world_size, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
@@ -314,6 +390,7 @@ def run_cuda(args):
                         "d2h_bytes_per_step": 24 * live + 8, "steps": e2e_steps},
                 "gpu_launches": st["kernel_launches"],
                 "roofline": roofline,
+                "parity": parity,
                 "cpu_baseline": cb}
         emit(line)
     w.close()
@@ -346,6 +423,7 @@ def main():
     ap.add_argument("--cpu-ticks", type=int, default=10)
     ap.add_argument("--settle", type=int, default=50)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the replay against the reference hash streams")
     ap.add_argument("--opt", action="append", default=[], help="name=value for bt_world_set_option (tuning experiments)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "cuda":

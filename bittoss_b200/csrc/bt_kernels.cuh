@@ -378,7 +378,7 @@ __global__ void __launch_bounds__(256) k_narrow(DevWorld W, int spec) { PDL_WAIT
  * no proposal they are no-ops by construction; if the pair buffer overflowed they stand down
  * (CT_PAIR_OVERFLOW) and the host redoes the iteration through k_collide. */
 __global__ void __launch_bounds__(BT_BLOCK) k_decide(DevWorld W) { PDL_ENTRY();
-	if (W.ctr[CT_PAIR_OVERFLOW] | W.ctr[CT_STOP]) return;
+	if (W.ctr[CT_PAIR_OVERFLOW] | W.ctr[CT_STOP] | W.ctr[CT_ERROR]) return; /* a raised error (traversal stack, work list) stops the iteration: nobody acts on a partial candidate set */
 	t_decide(W, TID);
 }
 /* ready roots (typically 1 entity in 4) are re-packed into full warps before the push */
@@ -386,7 +386,7 @@ __global__ void __launch_bounds__(BT_BLOCK) k_push(DevWorld W) { PDL_WAIT();
 	__shared__ u32 queue[BT_BLOCK];
 	__shared__ u32 qn;
 	LocalStats st = {0, 0, 0, 0, 0};
-	if (W.ctr[CT_PAIR_OVERFLOW] | W.ctr[CT_STOP]) return;
+	if (W.ctr[CT_PAIR_OVERFLOW] | W.ctr[CT_STOP] | W.ctr[CT_ERROR]) return; /* a raised error (traversal stack, work list) stops the iteration: nobody acts on a partial candidate set */
 	if (threadIdx.x == 0) qn = 0;
 	__syncthreads();
 	i32 e = TID;
@@ -395,16 +395,16 @@ __global__ void __launch_bounds__(BT_BLOCK) k_push(DevWorld W) { PDL_WAIT();
 	if (threadIdx.x < qn) t_push(W, (i32)queue[threadIdx.x], st);
 	stats_flush(W, st);
 }
-__global__ void k_push_serial(DevWorld W) { PDL_ENTRY();
+__global__ void k_push_serial(DevWorld W) { PDL_ENTRY(); PDL_WAIT(); /* launched with k_push's attribute (class push): with option pdl = 2 only the second applies */
 	if (threadIdx.x != 0 || blockIdx.x != 0) return;
-	if (W.ctr[CT_SERIAL_N] == 0 || W.ctr[CT_PAIR_OVERFLOW] || W.ctr[CT_STOP]) return;
+	if (W.ctr[CT_SERIAL_N] == 0 || W.ctr[CT_PAIR_OVERFLOW] || W.ctr[CT_STOP] || W.ctr[CT_ERROR]) return;
 	LocalStats st = {0, 0, 0, 0, 0};
 	t_push_serial(W, st);
 	u64 *s = (u64 *)&W.ctr[CT_STAT0];
 	s[SK_PUSH] += st.push; s[SK_SERIAL] += st.push; s[SK_CRUSH] += st.crush; s[SK_FUMBLE] += st.fumble;
 }
 __global__ void __launch_bounds__(BT_BLOCK) k_post(DevWorld W) { PDL_ENTRY();
-	if (W.ctr[CT_PAIR_OVERFLOW] | W.ctr[CT_STOP]) return;
+	if (W.ctr[CT_PAIR_OVERFLOW] | W.ctr[CT_STOP] | W.ctr[CT_ERROR]) return; /* a raised error (traversal stack, work list) stops the iteration: nobody acts on a partial candidate set */
 	t_post(W, TID);
 }
 

@@ -1584,13 +1584,14 @@ static void ray_swap(bt_world *w) {
 static int ray_build(bt_world *w) {
 	bool tv = w->tree_valid;
 	i32 tsb = w->ticks_since_build;
+	const u32 pbat = w->pair_builds_at_tree; /* build_tree bumps it: the collision tree's rebuild schedule must not notice */
 	i64 builds = w->stats.tree_builds, refits = w->stats.tree_refits;
 	ray_swap(w);
 	int r = build_tree(w);
 	if (!r) r = refit(w, false);
 	if (!r) { LAUNCH(w, PK_RAY_BUILD, k_live_ranks, 1, 1024, w->W, w->ray.rank2slot, w->ray.slot2rank); w->ranks_valid = true; }
 	ray_swap(w);
-	w->tree_valid = tv; w->ticks_since_build = tsb;
+	w->tree_valid = tv; w->ticks_since_build = tsb; w->pair_builds_at_tree = pbat;
 	w->stats.tree_builds = builds; w->stats.tree_refits = refits;
 	if (r) return r;
 	w->ray_valid = true;

@@ -13,9 +13,9 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 HOST_DIR = os.path.join(ROOT, "host")
 HOST_SO = os.path.join(HOST_DIR, "_build", "libbthost.so")
-# the reference's data/ directory travels with the compiled reference (oracle/_ref/data, a plain copy of the
-# shipped levels): the host loads its .sav files from there
-DATA_PARENT = os.environ.get("BT_HOST_DATA", os.path.join(ROOT, "oracle", "_ref"))
+# the shipped levels (a plain copy of the reference's data/, made by host/Makefile): the host loads its .sav files
+# from <DATA_PARENT>/data like the real client does from its working directory (file.cpp:10-17)
+DATA_PARENT = os.environ.get("BT_HOST_DATA", os.path.join(HOST_DIR, "_build"))
 
 
 def build():

@@ -120,8 +120,9 @@ def _crush_lab_sav(name):
     finally:
         R.lab_real_crush(False)
         R.free_world(w)
-    with open(os.path.join(pybind.REF_DATA_PARENT, "data", name), "wb") as f:
-        f.write(data)
+    for parent in (pybind.REF_DATA_PARENT, hostlib.DATA_PARENT):  # each side loads it from its own data/
+        with open(os.path.join(parent, "data", name), "wb") as f:
+            f.write(data)
 
 
 @needs_ref
