@@ -322,7 +322,7 @@ static __device__ __forceinline__ void queue_push(u32 *q, u32 *count, int pred, 
 __global__ void __launch_bounds__(256) k_narrow(DevWorld W, int spec) { PDL_WAIT();
 	LocalStats st = {0, 0, 0, 0, 0};
 	u32 any = 0;
-	if (spec) {
+	if (spec & 1) {
 		/* none of these words is written by this kernel while `go` holds (the stamp of THIS
 		 * iteration goes to the other parity slot), so early and late blocks agree */
 		int go = W.ctr[CT_STOP] == 0 && W.ctr[ANY_SLOT(W.iter_id - 1)] == (u32)(W.iter_id - 1) && !W.ctr[CT_CACHE_INVALID] &&
@@ -339,9 +339,17 @@ __global__ void __launch_bounds__(256) k_narrow(DevWorld W, int spec) { PDL_WAIT
 	}
 	/* k_refit / k_pairs of this iteration have consumed the flag; pushes may raise it again
 	 * (a run-ahead iteration only gets here with the flag down, and other blocks are reading it) */
-	if (!spec && blockIdx.x == 0 && threadIdx.x == 0) bt_consume_cache_flags(W, np);
+	if (!(spec & 1) && blockIdx.x == 0 && threadIdx.x == 0) bt_consume_cache_flags(W, np);
 	const u32 stride = gridDim.x * blockDim.x;
 	u32 p = blockIdx.x * blockDim.x + threadIdx.x;
+#ifndef BT_NO_NARROW_FIRST
+	if (spec & 2) { /* first iteration of the tick: everybody scans, no flag gathers (see t_narrow_t) */
+		for (; p < np; p += stride) t_narrow_t<1>(W, W.pairs[p], st, any);
+		stats_flush(W, st);
+		if (__any_sync(0xffffffffu, any) && (threadIdx.x & 31) == 0) W.ctr[ANY_SLOT(W.iter_id)] = (u32)W.iter_id;
+		return;
+	}
+#endif
 #if BT_NARROW_BATCH > 1
 	/* The cheap filter (pair word -> needsCollision bytes of both ends: two dependent memory hops
 	 * that most pairs end with after the first iteration) runs on BT_NARROW_BATCH pairs at once, so
@@ -379,7 +387,7 @@ __global__ void __launch_bounds__(256) k_narrow(DevWorld W, int spec) { PDL_WAIT
  * (CT_PAIR_OVERFLOW) and the host redoes the iteration through k_collide. */
 __global__ void __launch_bounds__(BT_BLOCK) k_decide(DevWorld W) { PDL_ENTRY();
 	if (W.ctr[CT_PAIR_OVERFLOW] | W.ctr[CT_STOP] | W.ctr[CT_ERROR]) return; /* a raised error (traversal stack, work list) stops the iteration: nobody acts on a partial candidate set */
-	t_decide(W, TID);
+	GS_FOR(e, W.n) t_decide(W, e); /* 148 x 16 blocks, grid-stride: 53 blocks of 128 threads per SM cost more to schedule than to run */
 }
 /* ready roots (typically 1 entity in 4) are re-packed into full warps before the push */
 __global__ void __launch_bounds__(BT_BLOCK) k_push(DevWorld W) { PDL_WAIT();
@@ -405,7 +413,7 @@ __global__ void k_push_serial(DevWorld W) { PDL_ENTRY(); PDL_WAIT(); /* launched
 }
 __global__ void __launch_bounds__(BT_BLOCK) k_post(DevWorld W) { PDL_ENTRY();
 	if (W.ctr[CT_PAIR_OVERFLOW] | W.ctr[CT_STOP] | W.ctr[CT_ERROR]) return; /* a raised error (traversal stack, work list) stops the iteration: nobody acts on a partial candidate set */
-	t_post(W, TID);
+	GS_FOR(e, W.n) t_post(W, e);
 }
 
 /* host exchange: staging buffers hold [3*n_live] ints in live oldest-first order; while no

@@ -724,7 +724,14 @@ static BT_HD void bt_propose_v(const GeoView &W, i32 leaf, i32 buddy, int axis, 
 	Coll c;
 	c.leaf = leaf; c.buddy = buddy; c.axis = axis; c.dir = dir; c.mutual = mutual;
 	u64 mine = bt_pack_coll(c);
+#ifndef BT_PROPOSE_LOAD_FIRST
+	/* a root usually gets ONE collision per iteration (seen from both ends of its pair at most): try the empty slot
+	 * straight away -- one round trip to L2 instead of a load and then the CAS */
+	u64 cur = bt_cas64(&W.pend[root], 0ull, mine);
+	if (cur == 0) return;
+#else
 	u64 cur = bt_ld64(&W.pend[root]);
+#endif
 	while (1) {
 		if (cur == mine) return; /* the same collision seen from the other end of the pair */
 		if (cur != 0) {
@@ -1252,9 +1259,12 @@ template <class Emit> static BT_HD void t_pairs(const DevWorld &W, int t, i32 *s
 /* checkCollision ent.cpp:398-435 for one cached pair, from whichever ends are scanning: all
  * loads of both ends first (they are independent), then one copy of the narrow phase run from
  * each scanning end */
-static BT_HD void t_narrow(const DevWorld &W, u64 pr, LocalStats &st, u32 &any) {
+/* FIRST = the first doIteration of a tick: the integrate kernel has just set needsCollision on every entity that is
+ * in gs->ents (ent.cpp:856), so the two byte gathers -- one dependent hop of the chain pair -> flags -> fields ->
+ * proposal -- are skipped; entities without a box or out of the list fall to the inList / hasBox test below */
+template <int FIRST> static BT_HD void t_narrow_t(const DevWorld &W, u64 pr, LocalStats &st, u32 &any) {
 	i32 a = (i32)(u32)pr, b = (i32)(pr >> 32);
-	int na = W.needsCollision[a], nb = W.needsCollision[b];
+	int na = FIRST ? 1 : W.needsCollision[a], nb = FIRST ? 1 : W.needsCollision[b];
 	if (!(na | nb)) return; /* the common case after the first iteration: two byte loads */
 	/* everything else in ONE batch of independent loads (no branch in between, or the compiler
 	 * must wait for each test before it may issue the next gather) */
@@ -1278,6 +1288,8 @@ static BT_HD void t_narrow(const DevWorld &W, u64 pr, LocalStats &st, u32 &any) 
 		{ int t_ = na; na = nb; nb = t_; }
 	}
 }
+
+static BT_HD void t_narrow(const DevWorld &W, u64 pr, LocalStats &st, u32 &any) { t_narrow_t<0>(W, pr, st, any); }
 
 /* ------------------------------------------------------------------------- */
 /* resolution                                                                */

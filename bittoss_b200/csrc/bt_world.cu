@@ -180,6 +180,10 @@ static void note_launch_error(struct bt_world *w, cudaError_t e, const char *ker
 static inline int nblk(i64 n, int b = BT_BLOCK) { return (int)((n + b - 1) / b); }
 /* fixed one-wave grid for the grid-stride kernels: 148 SMs x 8 blocks of 256 threads */
 static inline int gsblk(i64 n) { return (int)std::min<i64>((n + GS_BLOCK - 1) / GS_BLOCK, 148 * 8); }
+/* the two full-N scans of every iteration (decide, post): grid-stride over 148 SMs x 16 blocks of 128 threads.  One
+ * thread per entity (7 863 blocks at 1 M) spends its time in block scheduling: measured 75 -> 63 us (decide) and
+ * 74 -> 57 us (post) per tick on the 1 M-cube world, state hash unchanged (profiles/r2_ab_experiments.md) */
+static inline int scanblk(i64 n) { return (int)std::min<i64>((n + BT_BLOCK - 1) / BT_BLOCK, 148 * 16); }
 /* one full wave of k_pairs: SM count x resident blocks per SM (occupancy API, cached) */
 static int pairs_wave() {
 	static int wave = 0;
@@ -716,11 +720,11 @@ static int do_physics_iter(bt_world *w, bool gravity) {
 	};
 	auto resolve = [&]() {
 		/* speculative behind the narrow phase (see k_decide) */
-		LAUNCH(w, PK_DECIDE, k_decide, nblk(n), BT_BLOCK, W);
+		LAUNCH(w, PK_DECIDE, k_decide, scanblk(n), BT_BLOCK, W);
 		W.root_phase = ++w->root_phase_ctr; /* both push lanes of one iteration share it (canonical push order inside) */
 		LAUNCH(w, PK_PUSH, k_push, nblk(n), BT_BLOCK, W);
 		LAUNCH(w, PK_PUSH, k_push_serial, 1, 32, W);
-		LAUNCH(w, PK_POST, k_post, nblk(n), BT_BLOCK, W);
+		LAUNCH(w, PK_POST, k_post, scanblk(n), BT_BLOCK, W);
 	};
 	while (1) {
 		int r;
@@ -736,7 +740,8 @@ static int do_physics_iter(bt_world *w, bool gravity) {
 			 * lists for the re-armed entities only -- 2.6x slower per launch at 1 M entities: one
 			 * thread per scanner serialises its 2-5 neighbours' gather chains, one thread per pair
 			 * keeps them all in flight.) */
-			LAUNCH(w, PK_NARROW, k_narrow, w->narrow_blocks, w->narrow_threads, W, 0);
+			/* bit 1: the first doIteration of the tick, right behind the integrate kernel (every listed entity scans) */
+			LAUNCH(w, PK_NARROW, k_narrow, w->narrow_blocks, w->narrow_threads, W, iters_this_tick == 0 ? 2 : 0);
 			resolve();
 			if (w->run_ahead) {
 				/* run-ahead: as many further iterations as the previous tick needed, each of which
