@@ -202,6 +202,164 @@ def parity_record(bittoss_b200, args, device, checkpoints):
     return rec
 
 
+GOLDEN_1M_PUSHALL = os.path.join(ROOT, "tests", "golden", "stack1m_pushall_ref_hashes.npz")
+ALG_BYTES = {  # ALGORITHMIC bytes per unit of each kernel class (DESIGN.md §3 states the per-unit figures)
+    "begin_integrate": 94, "decide": 10, "post": 9, "flush1": 5, "hash": 61, "collide": COLLIDE_BYTES_PER_LEAF,
+    "morton_keys": 24, "radix_sort": 24, "lbvh_build": 72, "refit": 212, "push": 200}
+
+
+def kernel_table(prof, ps, n, ticks, peak):
+    """per kernel class: launches, device time (CUDA events around every launch) and achieved algorithmic GB/s"""
+    total_ms = sum(v[1] for v in prof.values()) or 1.0
+    builds = max(1, ps["pair_builds"])
+    P = ps["pairs_cached"] / builds            # cached pairs per full k_pairs run
+    sort_passes = 4                            # 8-bit LSD radix passes over 30 + world bits
+    work = {  # bytes moved by ALL launches of the class in the profiled ticks
+        "narrow": 8 * P * prof.get("narrow", (0, 0))[0] + 64 * ps["candidate_pairs"],
+        "pairs": (32 * n + 8 * P) * ps["pair_builds"], "refit": 212 * n * ps["pair_builds"],
+        "push": 200 * ps["pushes"], "morton_keys": 24 * n * ps["tree_builds"],
+        "radix_sort": 24 * n * sort_passes * ps["tree_builds"], "lbvh_build": 72 * n * ps["tree_builds"]}
+    out = {}
+    for k, (launches, kms) in prof.items():
+        if not launches:
+            continue
+        b = work[k] if k in work else (ALG_BYTES[k] * n * launches if k in ALG_BYTES else None)
+        ach = b / (kms * 1e-3) / 1e9 if b and kms > 0 else None
+        out[k] = {"launches_per_tick": launches / ticks, "avg_launch_ms": round(kms / launches, 5),
+                  "ms_per_tick": round(kms / ticks, 5), "share_of_step": round(kms / total_ms, 4),
+                  "alg_gbs": round(ach, 2) if ach else None, "frac": round(ach / peak, 5) if ach else None}
+    return out
+
+
+def dynamic_phase(bittoss_b200, args, device, peak):
+    """The regime in which the broadphase runs: the same world with the top cube of EVERY column kicked (250 000
+    sliding cubes, 4 067 crushed): first ticks from the upload, so the Morton sort, the LBVH build, refits, full
+    pair builds and patches are all inside.  Device-timed unprofiled, then a second world with events around every
+    launch for the per-kernel table; the per-tick hashes of a third are compared with the reference's stream."""
+    import numpy as np
+    ticks = args.dynamic_ticks
+    mk = lambda: bittoss_b200.World(bittoss_b200.synth_boxstack(args.entities, 4, 777, 1, 60), device=device)
+    w = mk()
+    n = w.count()[0]
+    ms = w.tick_timed(ticks)
+    st = w.stats()
+    w.close()
+    w = mk()
+    w.profile_enable(True)
+    w.tick(ticks)
+    prof, ps = w.profile(), w.stats()
+    w.close()
+    rec = {"workload": "the box-stack world with the top cube of every column kicked (push_every=1, |v| <= 60), "
+                       "first %d ticks from the upload" % ticks,
+           "ticks": ticks, "ms_per_step": ms / ticks, "value": st["entity_ticks"] / (ms * 1e-3),
+           "iterations_per_tick": st["iterations"] / ticks, "tree_builds": st["tree_builds"],
+           "pair_builds": st["pair_builds"], "pair_patches": st["pair_patches"], "crushes": st["crushes"],
+           "pairs_cached": st["pairs_cached"], "per_kernel": kernel_table(prof, ps, n, ticks, peak), "parity": None}
+    if args.entities == 1000000 and os.path.exists(GOLDEN_1M_PUSHALL) and not args.no_parity:
+        z = np.load(GOLDEN_1M_PUSHALL)
+        ref = [int(x) for x in z["hashes"]]
+        k = min(len(ref), ticks)
+        w = mk()
+        mine = [int(x) for x in w.tick(k, hashes=True)[:, 0]]
+        w.close()
+        rec["parity"] = {"ticks_checked": k, "equal": mine == ref[:k],
+                         "against": "tests/golden/stack1m_pushall_ref_hashes.npz (unmodified reference, committed)"}
+    return rec
+
+
+def raycast_record(bittoss_b200, w, args, peak):
+    """BASELINE.json configs[4]: 4 M rays against the settled 1 M-entity world `w`; a subsample is checked against the
+    reference's own selectCast (raycast.cpp:16-57) on a gamestate rebuilt from the downloaded device state."""
+    import numpy as np
+    from bittoss_b200 import workloads
+    ms, winners, origin, look, build_ms = workloads.raycast_sweep(w, args.rays)
+    t0 = time.perf_counter()
+    host_out = w.raycast(origin, look)
+    host_s = time.perf_counter() - t0
+    rays_s = args.rays / (ms * 1e-3)
+    rec = {"metric": "rays_per_sec", "value": rays_s, "unit": "rays/s", "rays": args.rays, "entities": w.count()[0],
+           "ms": ms, "tree_build_ms": build_ms, "hit_fraction": float((winners >= 0).mean()),
+           "host_buffer_rays_per_sec": args.rays / host_s, "host_buffer_equals_device": bool(np.array_equal(winners, host_out)),
+           "roofline": {"bound": "hbm", "alg_bytes_per_ray": 40, "achieved_gbs": rays_s * 40 / 1e9, "peak": peak,
+                        "frac": rays_s * 40 / 1e9 / peak}}
+    if args.ray_check > 0:
+        from oracle import pybind
+        state = w.download()
+        k = min(args.ray_check, args.rays)
+        if pybind.have_ref():
+            with pybind.stdout_to_stderr():
+                R = pybind.RefLib()
+                rw = R.new_world()
+                R.build_from(state)
+                t0 = time.perf_counter()
+                want = R.selectcast(origin[:k], look[:k])
+                cpu_s = time.perf_counter() - t0
+                R.free_world(rw)
+            kind = "reference"
+        else:
+            ow = pybind.OracleLib().create(state)
+            t0 = time.perf_counter()
+            want = ow.selectcast(origin[:k], look[:k])
+            cpu_s = time.perf_counter() - t0
+            kind = "port"
+        rec["parity_subsample"] = k
+        rec["parity_ok"] = bool(np.array_equal(want, winners[:k]))
+        rec["cpu_baseline"] = {"kind": kind, "cores": 1, "rays_per_sec": k / cpu_s,
+                               "sample": "%d rays, selectCast brute force over %d entities" % (k, state.n)}
+    return rec
+
+
+def arena_record(bittoss_b200, args, device, rank, world_size):
+    """BASELINE.json configs[3]: `--arena-worlds` independent arena.sav worlds split over the ranks in contiguous
+    blocks (parallel.shard_range), no collective on the tick path, the per-world state hashes all-gathered at the end;
+    rank 0 then runs ALL the worlds in one process and checks every gathered hash against that run."""
+    from bittoss_b200 import workloads
+    from bittoss_b200.parallel import gather_hashes, reduce_time_and_work, shard_range
+    level = os.path.join(ROOT, "host", "_build", "data", "arena.sav")
+    if not os.path.exists(level):
+        level = os.path.join(ROOT, "oracle", "_ref", "data", "arena.sav")
+    if not os.path.exists(level):
+        return {"skipped": "arena.sav not shipped (host/_build/data is built from the reference tree)"}
+    b, e = shard_range(args.arena_worlds, rank, world_size)
+    batch, n1 = workloads.arena_batch(level, list(range(b, e)))
+    w = workloads.arena_world(batch, device)
+    ms = w.tick_timed(args.arena_ticks)
+    st = w.stats()
+    hashes = w.hash()
+    w.close()
+    dev = "cuda" if world_size > 1 else None
+    ms_max, et = reduce_time_and_work(ms, float(st["entity_ticks"]), device=dev)
+    all_hashes = gather_hashes(hashes, args.arena_worlds, device=dev)
+    rec = None
+    if rank == 0:
+        rec = {"workload": "%d independent arena.sav worlds (BASELINE.json configs[3]), each with its own seeded kick, "
+                           "contiguous shards over %d GPU(s), %d ticks" % (args.arena_worlds, world_size, args.arena_ticks),
+               "metric": "world_ticks_per_sec", "value": args.arena_worlds * args.arena_ticks / (ms_max * 1e-3),
+               "unit": "world-ticks/s", "entity_ticks_per_sec": et / (ms_max * 1e-3), "n_gpus": world_size,
+               "worlds": args.arena_worlds, "worlds_per_gpu": e - b, "entities_per_world": n1, "ticks": args.arena_ticks,
+               "ms_per_tick": ms_max / args.arena_ticks, "iterations_per_tick": st["iterations"] / max(1, st["ticks"]),
+               "unsupported_events": st["unsupported_events"], "distinct_hashes": len(set(all_hashes)),
+               "hash_gather": "all_gather of 8 B per world (NCCL)" if world_size > 1 else "single process"}
+        if world_size > 1:
+            full, _ = workloads.arena_batch(level, list(range(args.arena_worlds)))
+            w1 = workloads.arena_world(full, device)
+            w1.tick(args.arena_ticks)
+            alone = w1.hash()
+            w1.close()
+            rec["sharded_equals_single_process"] = bool([int(x) for x in alone] == [int(x) for x in all_hashes])
+        else:
+            k = min(4, args.arena_worlds)   # the same worlds alone must give the same hashes
+            ok = True
+            for g in range(k):
+                one, _ = workloads.arena_batch(level, [g])
+                w1 = workloads.arena_world(one, device)
+                w1.tick(args.arena_ticks)
+                ok = ok and int(w1.hash()[0]) == int(all_hashes[g])
+                w1.close()
+            rec["alone_equals_batched"] = {"worlds_checked": k, "equal": bool(ok)}
+    return rec
+
+
 def run_cuda(args):
     import numpy as np
     import torch
@@ -316,36 +474,8 @@ def run_cuda(args):
     prof = w.profile()
     ps = w.stats()
     w.profile_enable(False)
-    total_ms = sum(v[1] for v in prof.values()) or 1.0
     peak, peak_src = peaks()
-    n_leaves = n  # every entity of this world is boxed
-    P = ps["pairs_cached"] / max(1, ps["pair_builds"])            # cached pairs per k_pairs launch
-    # ALGORITHMIC bytes per launch of each kernel class (DESIGN.md "Kernels" states the per-unit figures)
-    alg = {
-        "narrow": lambda L: 8 * P + 64 * ps["candidate_pairs"] / max(1, L),
-        # k_refit / k_pairs return at once unless the pair cache was invalidated: only the launches
-        # that did the work (pair_builds of them) move bytes
-        "pairs": lambda L: (32 * n_leaves + 8 * P) * ps["pair_builds"] / max(1, L),
-        "collide": lambda L: COLLIDE_BYTES_PER_LEAF * n_leaves,
-        "refit": lambda L: 212 * n_leaves * ps["pair_builds"] / max(1, L),
-        "push": lambda L: 200 * ps["pushes"] / max(1, L),
-        "begin_integrate": lambda L: 94 * n,
-        "decide": lambda L: 10 * n,
-        "post": lambda L: 9 * n,
-        "flush1": lambda L: 5 * n,
-        "hash": lambda L: 61 * n,
-    }
-    per_kernel = {}
-    for k, (launches, kms) in prof.items():
-        if not launches:
-            continue
-        avg_ms = kms / launches
-        ach = alg[k](launches) / (avg_ms * 1e-3) / 1e9 if k in alg and avg_ms > 0 else None
-        if ach is not None and ach <= 0:
-            ach = None
-        per_kernel[k] = {"launches_per_tick": launches / prof_ticks, "avg_launch_ms": round(avg_ms, 5),
-                         "ms_per_tick": round(kms / prof_ticks, 5), "share_of_step": round(kms / total_ms, 4),
-                         "alg_gbs": round(ach, 2) if ach else None, "frac": round(ach / peak, 5) if ach else None}
+    per_kernel = kernel_table(prof, ps, n, prof_ticks, peak)
     name = max(per_kernel, key=lambda k: per_kernel[k]["ms_per_tick"])
     top = per_kernel[name]
     traffic = None
@@ -361,6 +491,14 @@ def run_cuda(args):
                 "whole_tick_frac": value * BYTES_PER_ENTITY_TICK / 1e9 / peak,
                 "per_kernel": per_kernel}
 
+    # ---- (4) the other two BASELINE workloads and the regime in which the broadphase runs ----
+    rays = dyn = None
+    if rank == 0 and world_size == 1 and not args.no_extras:
+        rays = raycast_record(bittoss_b200, w, args, peak)
+    w.close()
+    if rank == 0 and world_size == 1 and not args.no_extras:
+        dyn = dynamic_phase(bittoss_b200, args, local_rank, peak)
+    arena = None if args.no_extras else arena_record(bittoss_b200, args, local_rank, rank, world_size)
     if rank == 0:
         cb = None
         if world_size == 1 and not args.no_cpu_baseline:
@@ -391,9 +529,11 @@ def run_cuda(args):
                 "gpu_launches": st["kernel_launches"],
                 "roofline": roofline,
                 "parity": parity,
+                "dynamic_phase": dyn,
+                "raycast": rays,
+                "batched_arena": arena,
                 "cpu_baseline": cb}
         emit(line)
-    w.close()
     if dist is not None:
         dist.destroy_process_group()
 
@@ -424,6 +564,12 @@ def main():
     ap.add_argument("--settle", type=int, default=50)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-parity", action="store_true", help="skip the replay against the reference hash streams")
+    ap.add_argument("--no-extras", action="store_true", help="skip the dynamic phase, the raycast sweep and the batched arena worlds")
+    ap.add_argument("--dynamic-ticks", type=int, default=12)
+    ap.add_argument("--rays", type=int, default=4000000)
+    ap.add_argument("--ray-check", type=int, default=1024, help="rays checked against the reference's selectCast (brute force on the CPU)")
+    ap.add_argument("--arena-worlds", type=int, default=8192)
+    ap.add_argument("--arena-ticks", type=int, default=200)
     ap.add_argument("--opt", action="append", default=[], help="name=value for bt_world_set_option (tuning experiments)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "cuda":

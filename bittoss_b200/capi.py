@@ -99,6 +99,7 @@ def lib():
     L.bt_world_stream.argtypes = [C.c_void_p]
     L.bt_world_stream.restype = C.c_void_p
     L.bt_world_hash.argtypes = [C.c_void_p, _u64p]
+    L.bt_world_hash_full.argtypes = [C.c_void_p, _u64p]
     L.bt_world_stats.argtypes = [C.c_void_p, C.POINTER(BtTickStats), C.c_int]
     L.bt_world_order_ties.argtypes = [C.c_void_p, C.POINTER(C.c_uint32)]
     L.bt_world_apply_requests.argtypes = [C.c_void_p, C.POINTER(BtRequest), C.c_int32]
@@ -255,6 +256,12 @@ class World:
     def hash(self):
         out = np.zeros(self.n_worlds, dtype=np.uint64)
         _ck(self.L.bt_world_hash(self.h, out.ctypes.data_as(_u64p)), "bt_world_hash")
+        return [int(x) for x in out]
+
+    def hash_full(self):
+        """per-world hash of everything a .sav holds plus the flush state (bt_world_hash_full)"""
+        out = np.zeros(self.n_worlds, dtype=np.uint64)
+        _ck(self.L.bt_world_hash_full(self.h, out.ctypes.data_as(_u64p)), "bt_world_hash_full")
         return [int(x) for x in out]
 
     def count(self):

@@ -83,6 +83,7 @@ class RefLib:
         L.btref_kick.argtypes = [C.c_uint32, C.c_int32, C.c_int32]
         L.btref_count.argtypes = [_i32p, _i32p, _i32p]
         L.btref_export.argtypes = [C.POINTER(BtWorldDesc)]
+        L.btref_build_from_desc.argtypes = [C.POINTER(BtWorldDesc)]
         L.btref_export_at.argtypes = [C.POINTER(BtWorldDesc), C.c_int32, C.c_int32, C.c_int32, C.c_int32]
         L.btref_hash.restype = C.c_uint64
         L.btref_hash_full.restype = C.c_uint64
@@ -117,6 +118,10 @@ class RefLib:
         arr = (C.c_int32 * max(1, len(players)))(*players)
         if self.L.btref_load_sav(name.encode(), len(players), arr, rand_seed) != 0:
             raise RuntimeError("cannot load %s" % name)
+
+    def build_from(self, wa):
+        """the current (empty) world := the entities of a WorldArrays, made by the reference's own initEnt"""
+        return int(self.L.btref_build_from_desc(wa.ref()))
 
     def make_boxstack(self, n_cubes, height=4, seed=777, push_every=64, push_max=60):
         return self.L.btref_make_boxstack(n_cubes, height, seed, push_every, push_max)

@@ -253,6 +253,42 @@ int btref_make_boxstack(int32_t n_cubes, int32_t H, uint32_t seed, int32_t push_
 	return w->next_uid;
 }
 
+/* A world from plain arrays, built through the reference's own initEnt / catalogs / pickupNoHandlers the way its
+ * loader does (serialize.cpp:277-334): entity i of the desc becomes the i-th oldest `ent`.  Used to hand a state the
+ * CUDA path has reached (bt_world_download) to the reference's selectCast without replaying the ticks on the CPU. */
+int btref_build_from_desc(const bt_world_desc *d) {
+	RefWorld *w = cur;
+	gamestate *gs = w->gs;
+	std::vector<ent *> made((size_t)d->n_ents);
+	for (int i = 0; i < d->n_ents; i++) {
+		const int ns = d->slider_off[i + 1] - d->slider_off[i];
+		ent *e = initEnt(gs, NULL, d->center + 3 * i, d->vel + 3 * i, d->radius + 3 * i, ns, (int32_t)d->type_mask[i], (int32_t)d->collide_mask[i]);
+		const uint8_t *h = d->handlers + (size_t)BT_H_NUM * i;
+		e->whoMoves = whoMovesHandlers.get(h[BT_H_WHOMOVES]);
+		e->tick = h[BT_H_TICK] ? tickHandlers.get(h[BT_H_TICK]) : NULL;
+		e->tickHeld = h[BT_H_TICKHELD] ? tickHandlers.get(h[BT_H_TICKHELD]) : NULL;
+		e->crush = h[BT_H_CRUSH] ? crushHandlers.get(h[BT_H_CRUSH]) : NULL;
+		e->push = pushHandlers.get(h[BT_H_PUSH]);
+		e->pushed = h[BT_H_PUSHED] ? pushedHandlers.get(h[BT_H_PUSHED]) : NULL;
+		e->onFumble = entPairHandlers.get(h[BT_H_ONFUMBLE]); e->onFumbled = entPairHandlers.get(h[BT_H_ONFUMBLED]);
+		e->onPickUp = entPairHandlers.get(h[BT_H_ONPICKUP]); e->onPickedUp = entPairHandlers.get(h[BT_H_ONPICKEDUP]);
+		e->friction = d->friction[i];
+		for (int k = 0; k < 3; k++) e->old[k] = d->old[3 * i + k];
+		for (int k = 0; k < ns; k++) e->sliders[k].v = d->slider_v[d->slider_off[i] + k];
+		for (int k = 0; k < 4; k++) { e->ctrl.btns[k].v = (char)d->btn[8 * i + k]; e->ctrl.btns[k].v2 = (char)d->btn[8 * i + 4 + k]; }
+		made[i] = e;
+	}
+	for (int i = 0; i < d->n_ents; i++) {
+		for (int k = d->wire_off[i]; k < d->wire_off[i + 1]; k++) made[i]->wires.add(made[d->wire_to[k]]);
+		if (d->holder[i] >= 0) pickupNoHandlers(gs, made[d->holder[i]], made[i], d->hold_flags[i]);
+	}
+	gs->flipFlop_death = (byte)d->w_flip_flop[0];
+	gs->gamerules = d->w_gamerules[0];
+	gs->rand = d->w_rand[0];
+	assign_new_uids(w);
+	return d->n_ents;
+}
+
 /* one entity through the reference's own initEnt (entFuncs.c:88-111); whoMoves by catalog id */
 int btref_add_ent(const int32_t *c, const int32_t *v, const int32_t *r, uint32_t typeMask, uint32_t collideMask,
                   int whoMovesId) {
