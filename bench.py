@@ -567,7 +567,7 @@ def main():
     ap.add_argument("--no-extras", action="store_true", help="skip the dynamic phase, the raycast sweep and the batched arena worlds")
     ap.add_argument("--dynamic-ticks", type=int, default=12)
     ap.add_argument("--rays", type=int, default=4000000)
-    ap.add_argument("--ray-check", type=int, default=1024, help="rays checked against the reference's selectCast (brute force on the CPU)")
+    ap.add_argument("--ray-check", type=int, default=256, help="rays checked against the reference's selectCast (brute force on the CPU)")
     ap.add_argument("--arena-worlds", type=int, default=8192)
     ap.add_argument("--arena-ticks", type=int, default=200)
     ap.add_argument("--opt", action="append", default=[], help="name=value for bt_world_set_option (tuning experiments)")
