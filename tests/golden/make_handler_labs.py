@@ -224,6 +224,24 @@ def lab_requests(R):
     return 45, script
 
 
+def lab_rootorder(R):
+    """flushPickups walks gs->rootEnts, newest ROOT first (ent.cpp:775-792), which is not newest ENTITY first once a
+    fumble has re-rooted an older entity (addRootEnt prepends, ent.cpp:60-66).  H holds O; O is dropped at tick 3 and
+    so becomes the head of the root list, ahead of the younger N; at tick 5 O and N each ask to pick the other up: the
+    one visited first ends up HELD (the second request then fails the `x->holdRoot != i` test).  The reference's
+    order makes N the holder; a walk in entity order would make O the holder."""
+    mk = lambda x: R.add_ent((x, 0, -5000), (0, 0, 0), (50, 50, 50), T_WEIGHTLESS, 0, WM_ME)
+    H, O = mk(0), mk(2000)
+    R.lab_request(H, 2, O, HOLD_MOVE)       # applied by the first flush1
+    filler = [mk(4000 + 2000 * i) for i in range(3)]
+    N = mk(12000)
+    P, Q = mk(14000), mk(16000)             # the same with the roles of old and young swapped, never fumbled: control
+    script = [(3, 0, O, -1, 0),
+              (5, 2, N, O, HOLD_MOVE), (5, 2, O, N, HOLD_MOVE),
+              (5, 2, P, Q, HOLD_MOVE), (5, 2, Q, P, HOLD_MOVE)]
+    return 10, script
+
+
 # builders return ticks, or (ticks, script[, btref step mode]) with script rows (tick, kind, uid, other, a0[, a1, a2])
 # applied before that tick's step; kind = BT_REQ_* (0 uDrop, 1 uDead, 2 uPickup(uid, other, a0), 3 pushBtn(uid, a0), ...)
 LABS = {
@@ -233,6 +251,7 @@ LABS = {
     "lab_crush": lab_crush,
     "lab_logic": lab_logic,
     "lab_requests": lab_requests,
+    "lab_rootorder": lab_rootorder,
 }
 
 
