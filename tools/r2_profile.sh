@@ -17,4 +17,8 @@ ncu --profile-from-start off --set full --clock-control none --import-source on 
 ncu --profile-from-start off --set full --clock-control none --import-source on \
     -k regex:'k_raycast|k_live_ranks' -c 4 -o $O/r2_full_raycast \
     python tools/ncu_target2.py raycast > $O/r2_ncu_f3.log 2>&1
+# the reports (with source) exceed what gpurun brings back: keep their raw pages as CSV
+for r in r2_full_dynamic r2_full_steady r2_full_raycast; do
+  if [ -f $O/$r.ncu-rep ]; then ncu -i $O/$r.ncu-rep --page raw --csv > $O/$r.raw.csv 2> /dev/null; rm -f $O/$r.ncu-rep; fi
+done
 ls -la $O | tail -12
