@@ -360,6 +360,35 @@ def arena_record(bittoss_b200, args, device, rank, world_size):
     return rec
 
 
+def pin_to_gpu_numa_node(local_rank):
+    """Run this rank on the CPUs next to its GPU, so that the pinned staging buffers of the end-to-end loop (allocated
+    below, first touched here) land on that NUMA node instead of all eight ranks sharing node 0's memory controller."""
+    try:
+        import torch
+        bdf = torch.cuda.get_device_properties(local_rank).pci_bus_id if hasattr(torch.cuda.get_device_properties(local_rank), "pci_bus_id") else None
+        if bdf is None:
+            out = subprocess.run(["nvidia-smi", "-i", str(local_rank), "--query-gpu=pci.bus_id", "--format=csv,noheader"],
+                                 capture_output=True, text=True, timeout=10).stdout.strip()
+            bdf = out[-12:].lower() if out else None
+        else:
+            bdf = "%04x:%02x:%02x.0" % (torch.cuda.get_device_properties(local_rank).pci_domain_id,
+                                        torch.cuda.get_device_properties(local_rank).pci_bus_id,
+                                        torch.cuda.get_device_properties(local_rank).pci_device_id)
+        base = "/sys/bus/pci/devices/%s" % bdf
+        node = int(open(base + "/numa_node").read().strip())
+        cpus = open(base + "/local_cpulist").read().strip()
+        ids = set()
+        for part in cpus.split(","):
+            lo, _, hi = part.partition("-")
+            ids.update(range(int(lo), int(hi or lo) + 1))
+        ids &= os.sched_getaffinity(0)
+        if ids:
+            os.sched_setaffinity(0, ids)
+        return {"gpu": local_rank, "pci": bdf, "numa_node": node, "cpus": cpus, "pinned": bool(ids)}
+    except Exception as e:  # topology files are best effort: never take the measurement down
+        return {"gpu": local_rank, "error": str(e)[:120]}
+
+
 def run_cuda(args):
     import numpy as np
     import torch
@@ -380,6 +409,7 @@ def run_cuda(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    numa = pin_to_gpu_numa_node(local_rank) if world_size > 1 else None
     # a throw-away small world first: pays CUDA's lazy module loading outside every measured phase
     _warm = bittoss_b200.World(bittoss_b200.synth_boxstack(4096, 4, 1, 64, 60), device=local_rank)
     _warm.tick(3)
@@ -453,7 +483,7 @@ def run_cuda(args):
     for _ in range(e2e_steps):
         w.apply_host_deltas(dc, dv)
         w.step(31)
-        live_now = w.stats()["live_ents"]
+        live_now = w.live_ents()   # host-side bookkeeping of the step that just finished: no extra round trip
         if live_now != live:  # an entity died: the host arrays shrink with the world
             live = live_now
             dc, dv, oc, ov = dc[:live], dv[:live], oc[:live], ov[:live]
@@ -525,7 +555,9 @@ def run_cuda(args):
                            "pair_builds_per_tick": st["pair_builds"] / max(1, st["ticks"])},
                 "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 24 * live,
-                        "d2h_bytes_per_step": 24 * live + 8, "steps": e2e_steps},
+                        "d2h_bytes_per_step": 24 * live + 8, "steps": e2e_steps,
+                        "exchange": "serial per step: H2D deltas -> tick -> D2H centre + velocity -> D2H hash",
+                        "rank0_numa": numa},
                 "gpu_launches": st["kernel_launches"],
                 "roofline": roofline,
                 "parity": parity,

@@ -99,8 +99,12 @@ def lib():
     L.bt_world_stream.argtypes = [C.c_void_p]
     L.bt_world_stream.restype = C.c_void_p
     L.bt_world_hash.argtypes = [C.c_void_p, _u64p]
-    L.bt_world_hash_full.argtypes = [C.c_void_p, _u64p]
+    if hasattr(L, "bt_world_hash_full"):
+        L.bt_world_hash_full.argtypes = [C.c_void_p, _u64p]
     L.bt_world_stats.argtypes = [C.c_void_p, C.POINTER(BtTickStats), C.c_int]
+    if hasattr(L, "bt_world_live_ents"):  # absent only from older builds named with BT_LIB_SO for an A/B run
+        L.bt_world_live_ents.argtypes = [C.c_void_p]
+        L.bt_world_live_ents.restype = C.c_int64
     L.bt_world_order_ties.argtypes = [C.c_void_p, C.POINTER(C.c_uint32)]
     L.bt_world_apply_requests.argtypes = [C.c_void_p, C.POINTER(BtRequest), C.c_int32]
     L.bt_world_drain_events.argtypes = [C.c_void_p, C.POINTER(BtEvent), C.c_int32, C.POINTER(C.c_int32)]
@@ -274,6 +278,10 @@ class World:
         wa = WorldArrays(n, ns, nw, self.n_worlds)
         _ck(self.L.bt_world_download(self.h, wa.ref()), "bt_world_download")
         return wa
+
+    def live_ents(self):
+        """live entities after the last finished step (host-side bookkeeping, no synchronisation)"""
+        return int(self.L.bt_world_live_ents(self.h))
 
     def stats(self, reset=False):
         s = BtTickStats()

@@ -153,22 +153,44 @@ __global__ void __launch_bounds__(BT_BLOCK) k_integrate(DevWorld W) { PDL_ENTRY(
 __global__ void __launch_bounds__(BT_BLOCK) k_begin_fused(DevWorld W, int gravity, int ctrls) { PDL_ENTRY(); t_begin_fused(W, TID, gravity, ctrls); }
 __global__ void __launch_bounds__(BT_BLOCK) k_flip_only(DevWorld W) { PDL_ENTRY(); t_flip_only(W, TID); }
 
-__global__ void __launch_bounds__(BT_BLOCK) k_bounds(DevWorld W) { PDL_ENTRY();
-	/* warp-reduce before the atomics: 6 atomics per warp instead of per thread */
-	i32 e = TID;
-	int valid = e < W.n && bt_is_leaf_ent(W, e);
-	int4 c = valid ? W.center[e] : make_int4(INT32_MAX, INT32_MAX, INT32_MAX, 0);
-	int4 d = valid ? c : make_int4(INT32_MIN, INT32_MIN, INT32_MIN, 0);
-	i32 mnx = __reduce_min_sync(0xffffffffu, c.x), mny = __reduce_min_sync(0xffffffffu, c.y),
-	    mnz = __reduce_min_sync(0xffffffffu, c.z);
-	i32 mxx = __reduce_max_sync(0xffffffffu, d.x), mxy = __reduce_max_sync(0xffffffffu, d.y),
-	    mxz = __reduce_max_sync(0xffffffffu, d.z);
-	u32 cnt = warp_sum((u32)valid);
-	if ((threadIdx.x & 31) == 0 && cnt) {
-		i32 *b = (i32 *)&W.ctr[CT_BOUNDS];
-		atomicMin(&b[0], mnx); atomicMin(&b[1], mny); atomicMin(&b[2], mnz);
-		atomicMax(&b[3], mxx); atomicMax(&b[4], mxy); atomicMax(&b[5], mxz);
-		atomicAdd(&W.ctr[CT_N_LEAVES], cnt);
+/* bounds of the leaf centres + leaf count: per-thread partials over a grid-stride loop, warp shuffles, then ONE set
+ * of atomics per block (one per warp of a one-thread-per-entity grid made 31 000 warps queue on the same seven
+ * words: 145 us at 1 M entities; this is a 4 MB read) */
+__global__ void __launch_bounds__(GS_BLOCK) k_bounds(DevWorld W) { PDL_ENTRY();
+	__shared__ i32 part[7][GS_BLOCK / 32];
+	i32 mn[3] = {INT32_MAX, INT32_MAX, INT32_MAX}, mx[3] = {INT32_MIN, INT32_MIN, INT32_MIN};
+	u32 cnt = 0;
+	GS_FOR(e, W.n) {
+		if (!bt_is_leaf_ent(W, e)) continue;
+		const int4 c = W.center[e];
+		mn[0] = min(mn[0], c.x); mn[1] = min(mn[1], c.y); mn[2] = min(mn[2], c.z);
+		mx[0] = max(mx[0], c.x); mx[1] = max(mx[1], c.y); mx[2] = max(mx[2], c.z);
+		cnt++;
+	}
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+	for (int k = 0; k < 3; k++) {
+		mn[k] = __reduce_min_sync(0xffffffffu, mn[k]);
+		mx[k] = __reduce_max_sync(0xffffffffu, mx[k]);
+	}
+	cnt = warp_sum(cnt);
+	if (lane == 0) {
+		for (int k = 0; k < 3; k++) { part[k][warp] = mn[k]; part[3 + k][warp] = mx[k]; }
+		part[6][warp] = (i32)cnt;
+	}
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		u32 total = 0;
+		for (int w2 = 0; w2 < GS_BLOCK / 32; w2++) {
+			for (int k = 0; k < 3; k++) { mn[k] = min(mn[k], part[k][w2]); mx[k] = max(mx[k], part[3 + k][w2]); }
+			total += (u32)part[6][w2];
+		}
+		if (total) {
+			i32 *b = (i32 *)&W.ctr[CT_BOUNDS];
+			atomicMin(&b[0], mn[0]); atomicMin(&b[1], mn[1]); atomicMin(&b[2], mn[2]);
+			atomicMax(&b[3], mx[0]); atomicMax(&b[4], mx[1]); atomicMax(&b[5], mx[2]);
+			atomicAdd(&W.ctr[CT_N_LEAVES], total);
+		}
 	}
 }
 __global__ void __launch_bounds__(BT_BLOCK) k_morton(DevWorld W) { PDL_ENTRY(); t_morton(W, TID); }
@@ -319,7 +341,12 @@ static __device__ __forceinline__ void queue_push(u32 *q, u32 *count, int pred, 
 /* spec = 1: an iteration enqueued ahead of the host's knowledge (run-ahead).  It proceeds only
  * if the previous iteration proposed something and no push has invalidated the pair cache;
  * otherwise it records its id in CT_STOP and it and everything enqueued behind it stand down. */
-__global__ void __launch_bounds__(256) k_narrow(DevWorld W, int spec) { PDL_WAIT();
+#ifndef BT_NARROW_MINBLOCKS
+#define BT_NARROW_MINBLOCKS 3 /* resident 256-thread blocks per SM the register allocation is held to: 80 registers,
+                               * 20 bytes of spills, 24 warps per SM instead of 16 (101 registers uncapped): k_narrow -7 %,
+                               * 4 blocks (64 registers, 324 bytes of spills) +5 % (profiles/r2_ab_experiments.md) */
+#endif
+__global__ void __launch_bounds__(256, BT_NARROW_MINBLOCKS) k_narrow(DevWorld W, int spec) { PDL_WAIT();
 	LocalStats st = {0, 0, 0, 0, 0};
 	u32 any = 0;
 	if (spec & 1) {
@@ -493,39 +520,41 @@ __global__ void __launch_bounds__(SORT_THREADS) k_sort_hist(const u64 *keys, i32
 	hist[threadIdx.x * nb + blockIdx.x] = h[threadIdx.x]; /* digit-major */
 }
 
-/* exclusive scan of `len` counters by one block of 1024 threads */
+/* exclusive scan of `len` counters (256 digits x tiles, digit-major) by one block of 1024 threads: every thread owns
+ * one contiguous chunk -- sums it, the 1024 chunk sums are scanned once through shared memory, then the chunk is
+ * rewritten with running offsets.  Two passes over a table that sits in L2 and three barriers in all (a block-wide
+ * scan per 1024 counters needed 4 barriers x 62 rounds: 58 us per radix pass at 1 M keys). */
 __global__ void __launch_bounds__(1024) k_sort_scan(u32 *hist, int len) { PDL_ENTRY_ALWAYS();
 	__shared__ u32 warpTot[32];
-	__shared__ u32 carry;
-	if (threadIdx.x == 0) carry = 0;
+	const int chunk = (len + 1023) / 1024;
+	const int b0 = min(len, (int)threadIdx.x * chunk), b1 = min(len, b0 + chunk);
+	u32 sum = 0;
+#pragma unroll 8
+	for (int i = b0; i < b1; i++) sum += hist[i];
+	u32 x = sum;
+#pragma unroll
+	for (int off = 1; off < 32; off <<= 1) {
+		u32 y = __shfl_up_sync(0xffffffffu, x, off);
+		if ((threadIdx.x & 31) >= off) x += y;
+	}
+	if ((threadIdx.x & 31) == 31) warpTot[threadIdx.x >> 5] = x;
 	__syncthreads();
-	for (int base = 0; base < len; base += 1024) {
-		int i = base + threadIdx.x;
-		u32 v = i < len ? hist[i] : 0;
-		u32 x = v;
+	if (threadIdx.x < 32) {
+		u32 w = warpTot[threadIdx.x], t = w;
 #pragma unroll
 		for (int off = 1; off < 32; off <<= 1) {
-			u32 y = __shfl_up_sync(0xffffffffu, x, off);
-			if ((threadIdx.x & 31) >= off) x += y;
+			u32 y = __shfl_up_sync(0xffffffffu, t, off);
+			if (threadIdx.x >= off) t += y;
 		}
-		if ((threadIdx.x & 31) == 31) warpTot[threadIdx.x >> 5] = x;
-		__syncthreads();
-		if (threadIdx.x < 32) {
-			u32 w = warpTot[threadIdx.x];
-			u32 s = w;
-#pragma unroll
-			for (int off = 1; off < 32; off <<= 1) {
-				u32 y = __shfl_up_sync(0xffffffffu, s, off);
-				if (threadIdx.x >= off) s += y;
-			}
-			warpTot[threadIdx.x] = s - w; /* exclusive over warps */
-		}
-		__syncthreads();
-		u32 excl = carry + warpTot[threadIdx.x >> 5] + x - v;
-		if (i < len) hist[i] = excl;
-		__syncthreads();
-		if (threadIdx.x == 1023) carry = excl + v;
-		__syncthreads();
+		warpTot[threadIdx.x] = t - w; /* exclusive over warps */
+	}
+	__syncthreads();
+	u32 run = warpTot[threadIdx.x >> 5] + x - sum;
+#pragma unroll 8
+	for (int i = b0; i < b1; i++) {
+		const u32 v = hist[i];
+		hist[i] = run;
+		run += v;
 	}
 }
 

@@ -677,66 +677,66 @@ static BT_HD EntGeo bt_geo(const DevWorld &W, i32 e) {
 
 /* collisionBetter ent.cpp:317-382 as a three-way compare of two explicit records:
  * +1 c0 strictly better, -1 strictly worse, 0 full tie.  32-bit products wrap
- * exactly like the reference's `delta * speed` (ent.cpp:343). */
-static BT_HD int bt_collision_cmp(const GeoView &W, const Coll &c0, const Coll &c1) {
-	EntGeo l0 = bt_geo(W, c0.leaf), f0 = bt_geo(W, c0.buddy);
-	EntGeo l1 = bt_geo(W, c1.leaf), f1 = bt_geo(W, c1.buddy);
-	int a0 = c0.axis, a1 = c1.axis;
-	i32 delta0 = (i32)((u32)(bt_get3(l0.old, a0) - bt_get3(f0.old, a0)) * (u32)c0.dir) - bt_get3(f0.radius, a0) -
-	             bt_get3(l0.radius, a0);
-	i32 delta1 = (i32)((u32)(bt_get3(l1.old, a1) - bt_get3(f1.old, a1)) * (u32)c1.dir) - bt_get3(f1.radius, a1) -
-	             bt_get3(l1.radius, a1);
-	/* speed of the OTHER record (ent.cpp:340) */
-	i32 speed1 = (i32)((u32)(bt_get3(f1.center, a1) - bt_get3(f1.old, a1) + bt_get3(l1.old, a1) -
-	                         bt_get3(l1.center, a1)) * (u32)c1.dir);
-	i32 speed0 = (i32)((u32)(bt_get3(f0.center, a0) - bt_get3(f0.old, a0) + bt_get3(l0.old, a0) -
-	                         bt_get3(l0.center, a0)) * (u32)c0.dir);
-	if (speed1 < 1) speed1 = 1;
-	if (speed0 < 1) speed0 = 1;
-	long long v0 = (i32)((u32)delta0 * (u32)speed1);
-	long long v1 = (i32)((u32)delta1 * (u32)speed0);
+ * exactly like the reference's `delta * speed` (ent.cpp:343).
+ * Every term of the comparison belongs to ONE of the two collisions, so each is first boiled down to a key of
+ * four numbers from its own leaf and buddy (two entities in registers at a time, not four):
+ *   delta  distance still to go along the axis at `old`          (ent.cpp:338-339)
+ *   speed  closing speed along the axis, clamped to >= 1          (:340-342); the OTHER record's speed scales delta
+ *   lat    smaller of the two lateral overlaps at `old`           (:352-368)
+ *   depth  displacement the push would need at `center`           (:370-378) */
+struct CKey {
+	i32 delta, speed, lat, depth;
+	int mutual;
+};
+static BT_HD CKey bt_ckey(const EntGeo &l, const EntGeo &f, int a, int dir, int mutual) {
+	CKey k;
+	k.delta = (i32)((u32)(bt_get3(l.old, a) - bt_get3(f.old, a)) * (u32)dir) - bt_get3(f.radius, a) - bt_get3(l.radius, a);
+	i32 sp = (i32)((u32)(bt_get3(f.center, a) - bt_get3(f.old, a) + bt_get3(l.old, a) - bt_get3(l.center, a)) * (u32)dir);
+	k.speed = sp < 1 ? 1 : sp;
+	int x1 = (a + 1) % 3, x2 = (a + 2) % 3;
+	i32 p = bt_get3(f.radius, x1) + bt_get3(l.radius, x1) - bt_abs(bt_get3(f.old, x1) - bt_get3(l.old, x1));
+	i32 q = bt_get3(f.radius, x2) + bt_get3(l.radius, x2) - bt_abs(bt_get3(f.old, x2) - bt_get3(l.old, x2));
+	k.lat = p < q ? p : q;
+	k.depth = bt_get3(f.radius, a) + bt_get3(l.radius, a) + (bt_get3(f.center, a) - bt_get3(l.center, a)) * dir;
+	k.mutual = mutual;
+	return k;
+}
+static BT_HD int bt_ckey_cmp(const CKey &k0, const CKey &k1) {
+	long long v0 = (i32)((u32)k0.delta * (u32)k1.speed);
+	long long v1 = (i32)((u32)k1.delta * (u32)k0.speed);
 	if (v0 != v1) return v0 < v1 ? 1 : -1;
-	int m0 = !c0.mutual, m1 = !c1.mutual;
+	int m0 = !k0.mutual, m1 = !k1.mutual;
 	if (m0 != m1) return m0 > m1 ? 1 : -1;
-	i32 k0, k1;
-	{
-		int x1 = (a0 + 1) % 3, x2 = (a0 + 2) % 3;
-		i32 p = bt_get3(f0.radius, x1) + bt_get3(l0.radius, x1) - bt_abs(bt_get3(f0.old, x1) - bt_get3(l0.old, x1));
-		i32 q = bt_get3(f0.radius, x2) + bt_get3(l0.radius, x2) - bt_abs(bt_get3(f0.old, x2) - bt_get3(l0.old, x2));
-		k0 = p < q ? p : q;
-	}
-	{
-		int x1 = (a1 + 1) % 3, x2 = (a1 + 2) % 3;
-		i32 p = bt_get3(f1.radius, x1) + bt_get3(l1.radius, x1) - bt_abs(bt_get3(f1.old, x1) - bt_get3(l1.old, x1));
-		i32 q = bt_get3(f1.radius, x2) + bt_get3(l1.radius, x2) - bt_abs(bt_get3(f1.old, x2) - bt_get3(l1.old, x2));
-		k1 = p < q ? p : q;
-	}
-	if (k0 != k1) return k0 > k1 ? 1 : -1;
-	k0 = bt_get3(f0.radius, a0) + bt_get3(l0.radius, a0) + (bt_get3(f0.center, a0) - bt_get3(l0.center, a0)) * c0.dir;
-	k1 = bt_get3(f1.radius, a1) + bt_get3(l1.radius, a1) + (bt_get3(f1.center, a1) - bt_get3(l1.center, a1)) * c1.dir;
-	if (k0 != k1) return k0 > k1 ? 1 : -1;
+	if (k0.lat != k1.lat) return k0.lat > k1.lat ? 1 : -1;
+	if (k0.depth != k1.depth) return k0.depth > k1.depth ? 1 : -1;
 	return 0;
 }
+static BT_HD CKey bt_ckey_of(const GeoView &W, const Coll &c) {
+	const EntGeo l = bt_geo(W, c.leaf), f = bt_geo(W, c.buddy);
+	return bt_ckey(l, f, c.axis, c.dir, c.mutual);
+}
+static BT_HD int bt_collision_cmp(const GeoView &W, const Coll &c0, const Coll &c1) {
+	const CKey k0 = bt_ckey_of(W, c0);
+	const CKey k1 = bt_ckey_of(W, c1);
+	return bt_ckey_cmp(k0, k1);
+}
 
-/* tryCollide ent.cpp:384-396 as an order-independent atomic maximum on pend[root] */
-static BT_HD void bt_propose_v(const GeoView &W, i32 leaf, i32 buddy, int axis, int dir, int mutual) {
+/* tryCollide ent.cpp:384-396 as an order-independent atomic maximum on pend[root].  gl / gf = the proposal's own
+ * leaf and buddy, which the caller holds in registers: its key costs no load, only an incumbent's does. */
+static BT_HD void bt_propose_g(const GeoView &W, i32 leaf, i32 buddy, int axis, int dir, int mutual, const EntGeo &gl, const EntGeo &gf) {
 	i32 root = W.holdRoot[leaf];
 	Coll c;
 	c.leaf = leaf; c.buddy = buddy; c.axis = axis; c.dir = dir; c.mutual = mutual;
 	u64 mine = bt_pack_coll(c);
-#ifndef BT_PROPOSE_LOAD_FIRST
 	/* a root usually gets ONE collision per iteration (seen from both ends of its pair at most): try the empty slot
 	 * straight away -- one round trip to L2 instead of a load and then the CAS */
 	u64 cur = bt_cas64(&W.pend[root], 0ull, mine);
-	if (cur == 0) return;
-#else
-	u64 cur = bt_ld64(&W.pend[root]);
-#endif
+	if (cur == 0 || cur == mine) return;
+	const CKey mk = bt_ckey(gl, gf, axis, dir, mutual);
 	while (1) {
 		if (cur == mine) return; /* the same collision seen from the other end of the pair */
 		if (cur != 0) {
-			Coll inc = bt_unpack_coll(cur);
-			int r = bt_collision_cmp(W, c, inc);
+			int r = bt_ckey_cmp(mk, bt_ckey_of(W, bt_unpack_coll(cur)));
 			if (r < 0) return;
 			if (r == 0) {
 				/* A full tie between two different collisions: the reference keeps whichever its list
@@ -752,6 +752,9 @@ static BT_HD void bt_propose_v(const GeoView &W, i32 leaf, i32 buddy, int axis, 
 		if (prev == cur) return;
 		cur = prev;
 	}
+}
+static BT_HD void bt_propose_v(const GeoView &W, i32 leaf, i32 buddy, int axis, int dir, int mutual) {
+	bt_propose_g(W, leaf, buddy, axis, dir, mutual, bt_geo(W, leaf), bt_geo(W, buddy));
 }
 
 static BT_HD void bt_propose(const DevWorld &W, i32 leaf, i32 buddy, int axis, int dir, int mutual) {
@@ -800,8 +803,8 @@ static BT_HD void bt_check_loaded(const DevWorld &W, i32 a, const EntGeo &ga, u3
 	for (int k = 0; k < 1 + both; k++) {
 		int forA = k == 0 ? first_is_a : 0;
 		int mutual = both ? ((forA ? coordA : !coordA) ? 1 : 2) : 0;
-		if (forA) bt_propose_v(V, a, b, axis, dir, mutual);
-		else bt_propose_v(V, b, a, axis, -dir, mutual);
+		if (forA) bt_propose_g(V, a, b, axis, dir, mutual, ga, gb);
+		else bt_propose_g(V, b, a, axis, -dir, mutual, gb, ga);
 	}
 }
 

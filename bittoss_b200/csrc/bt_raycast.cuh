@@ -149,41 +149,69 @@ __global__ void __launch_bounds__(128) k_raycast(DevWorld W, const i32 *origin, 
 	winner[i] = win >= 0 ? slot2rank[win] : -1;
 }
 
-/* exclusive scan of inList -> live rank per slot (single block; raycast setup only) */
-__global__ void __launch_bounds__(1024) k_live_ranks(DevWorld W, i32 *rank2slot, i32 *slot2rank) { PDL_ENTRY();
+/* inList -> live rank per slot (rank2slot / slot2rank), three small launches over tiles of RANK_TILE slots:
+ * count the live slots of every tile, scan the tile counts (one block), rank inside each tile from its base.
+ * (One block looping over the whole world took 0.89 ms at 1 M slots.) */
+#define RANK_TILE 1024
+__global__ void __launch_bounds__(RANK_TILE) k_rank_count(DevWorld W, u32 *tileCount) { PDL_ENTRY();
+	const i32 i = (i32)(blockIdx.x * RANK_TILE + threadIdx.x);
+	const int live = i < W.n && W.inList[i];
+	const int c = __syncthreads_count(live);
+	if (threadIdx.x == 0) tileCount[blockIdx.x] = (u32)c;
+}
+__global__ void __launch_bounds__(1024) k_rank_scan(u32 *tileCount, int tiles) { PDL_ENTRY_ALWAYS();
 	__shared__ u32 warpTot[32];
-	__shared__ u32 carry;
-	if (threadIdx.x == 0) carry = 0;
+	const int chunk = (tiles + 1023) / 1024;
+	const int b0 = min(tiles, (int)threadIdx.x * chunk), b1 = min(tiles, b0 + chunk);
+	u32 sum = 0;
+	for (int i = b0; i < b1; i++) sum += tileCount[i];
+	u32 x = sum;
+#pragma unroll
+	for (int off = 1; off < 32; off <<= 1) {
+		u32 y = __shfl_up_sync(0xffffffffu, x, off);
+		if ((threadIdx.x & 31) >= off) x += y;
+	}
+	if ((threadIdx.x & 31) == 31) warpTot[threadIdx.x >> 5] = x;
 	__syncthreads();
-	for (int base = 0; base < W.n; base += 1024) {
-		int i = base + threadIdx.x;
-		u32 v = (i < W.n && W.inList[i]) ? 1u : 0u;
-		u32 x = v;
+	if (threadIdx.x < 32) {
+		u32 w = warpTot[threadIdx.x], t = w;
 #pragma unroll
 		for (int off = 1; off < 32; off <<= 1) {
-			u32 y = __shfl_up_sync(0xffffffffu, x, off);
-			if ((threadIdx.x & 31) >= off) x += y;
+			u32 y = __shfl_up_sync(0xffffffffu, t, off);
+			if (threadIdx.x >= off) t += y;
 		}
-		if ((threadIdx.x & 31) == 31) warpTot[threadIdx.x >> 5] = x;
-		__syncthreads();
-		if (threadIdx.x < 32) {
-			u32 t = warpTot[threadIdx.x], s = t;
+		warpTot[threadIdx.x] = t - w;
+	}
+	__syncthreads();
+	u32 run = warpTot[threadIdx.x >> 5] + x - sum;
+	for (int i = b0; i < b1; i++) {
+		const u32 v = tileCount[i];
+		tileCount[i] = run;
+		run += v;
+	}
+}
+__global__ void __launch_bounds__(RANK_TILE) k_rank_apply(DevWorld W, const u32 *tileBase, i32 *rank2slot, i32 *slot2rank) { PDL_ENTRY();
+	__shared__ u32 warpTot[RANK_TILE / 32];
+	const i32 i = (i32)(blockIdx.x * RANK_TILE + threadIdx.x);
+	const u32 v = (i < W.n && W.inList[i]) ? 1u : 0u;
+	const u32 m = __ballot_sync(0xffffffffu, v);
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	if (lane == 0) warpTot[warp] = (u32)__popc(m);
+	__syncthreads();
+	if (warp == 0) {
+		u32 w = warpTot[lane], t = w;
 #pragma unroll
-			for (int off = 1; off < 32; off <<= 1) {
-				u32 y = __shfl_up_sync(0xffffffffu, s, off);
-				if (threadIdx.x >= off) s += y;
-			}
-			warpTot[threadIdx.x] = s - t;
+		for (int off = 1; off < 32; off <<= 1) {
+			u32 y = __shfl_up_sync(0xffffffffu, t, off);
+			if (lane >= off) t += y;
 		}
-		__syncthreads();
-		u32 excl = carry + warpTot[threadIdx.x >> 5] + x - v;
-		if (i < W.n) {
-			slot2rank[i] = v ? (i32)excl : -1;
-			if (v) rank2slot[excl] = i;
-		}
-		__syncthreads();
-		if (threadIdx.x == 1023) carry = excl + v;
-		__syncthreads();
+		warpTot[lane] = t - w;
+	}
+	__syncthreads();
+	if (i < W.n) {
+		const u32 r = tileBase[blockIdx.x] + warpTot[warp] + (u32)__popc(m & ((1u << lane) - 1));
+		slot2rank[i] = v ? (i32)r : -1;
+		if (v) rank2slot[r] = i;
 	}
 }
 #endif

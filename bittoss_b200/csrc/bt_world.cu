@@ -598,7 +598,7 @@ static int build_tree(bt_world *w) {
 	const i32 n = W.n;
 	i32 init[8] = {0, INT32_MAX, INT32_MAX, INT32_MAX, INT32_MIN, INT32_MIN, INT32_MIN, 0};
 	CK(cudaMemcpyAsync(&W.ctr[CT_N_LEAVES], init, sizeof(i32) * 7, cudaMemcpyHostToDevice, w->stream));
-	LAUNCH(w, PK_BUILD_KEYS, k_bounds, nblk(n), BT_BLOCK, W);
+	LAUNCH(w, PK_BUILD_KEYS, k_bounds, gsblk(n), GS_BLOCK, W);
 	CK(cudaMemcpyAsync(w->h_flag, W.ctr, sizeof(u32) * CT_WORDS, cudaMemcpyDeviceToHost, w->stream));
 	CK(cudaStreamSynchronize(w->stream));
 	W.n_leaves = (i32)w->h_flag[CT_N_LEAVES];
@@ -992,11 +992,18 @@ int bt_world_tick_timed(bt_world *w, int32_t n_ticks, float *ms) {
 }
 
 /* live-rank maps (shared with the raycast path) */
-static int ensure_ranks(bt_world *w) {
-	if (w->ranks_valid) return 0;
-	LAUNCH(w, PK_EXCHANGE, k_live_ranks, 1, 1024, w->W, w->ray.rank2slot, w->ray.slot2rank);
+static int live_ranks(bt_world *w, int cls) {
+	const int tiles = (w->W.n + RANK_TILE - 1) / RANK_TILE;
+	if (tiles > w->sorthist_len) return BT_ERR_CAPACITY; /* the radix sort's histogram table doubles as scratch */
+	LAUNCH(w, cls, k_rank_count, tiles, RANK_TILE, w->W, w->d_sorthist);
+	LAUNCH(w, cls, k_rank_scan, 1, 1024, w->d_sorthist, tiles);
+	LAUNCH(w, cls, k_rank_apply, tiles, RANK_TILE, w->W, (const u32 *)w->d_sorthist, w->ray.rank2slot, w->ray.slot2rank);
 	w->ranks_valid = true;
 	return 0;
+}
+static int ensure_ranks(bt_world *w) {
+	if (w->ranks_valid) return 0;
+	return live_ranks(w, PK_EXCHANGE);
 }
 
 int bt_world_apply_host_deltas(bt_world *w, const int32_t *d_center, const int32_t *d_vel, int32_t n_ents) {
@@ -1093,6 +1100,8 @@ int bt_world_sync(bt_world *w) {
 	CK(cudaStreamSynchronize(w->stream));
 	return BT_OK;
 }
+
+int64_t bt_world_live_ents(bt_world *w) { return w ? (int64_t)w->stats.live_ents : (int64_t)BT_ERR_ARG; }
 
 int bt_world_stats(bt_world *w, bt_tick_stats *out, int reset) {
 	if (!w || !out) return BT_ERR_ARG;
@@ -1594,7 +1603,7 @@ static int ray_build(bt_world *w) {
 	ray_swap(w);
 	int r = build_tree(w);
 	if (!r) r = refit(w, false);
-	if (!r) { LAUNCH(w, PK_RAY_BUILD, k_live_ranks, 1, 1024, w->W, w->ray.rank2slot, w->ray.slot2rank); w->ranks_valid = true; }
+	if (!r) r = live_ranks(w, PK_RAY_BUILD);
 	ray_swap(w);
 	w->tree_valid = tv; w->ticks_since_build = tsb; w->pair_builds_at_tree = pbat;
 	w->stats.tree_builds = builds; w->stats.tree_refits = refits;

@@ -254,6 +254,9 @@ void *bt_world_stream(bt_world *w); /* the cudaStream_t every kernel of w runs o
  * out: [n_worlds]. */
 int bt_world_hash(bt_world *w, uint64_t *out);
 int bt_world_stats(bt_world *w, bt_tick_stats *out, int reset);
+/* live entities after the last finished step, from the host-side bookkeeping: no device access, no synchronisation
+ * (what a per-tick exchange loop sizes its buffers with) */
+int64_t bt_world_live_ents(bt_world *w);
 /* Copies out (and clears) the events queued since the last drain; *n = how many were written,
  * at most max.  Returns BT_ERR_OVERFLOW if the device queue (65536 entries) had overflowed. */
 /* per world: full ties since the last stats reset (see bt_tick_stats.order_ties) */
