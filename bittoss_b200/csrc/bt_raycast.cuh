@@ -135,13 +135,33 @@ static BT_HD i32 t_raycast(const DevWorld &W, i32 p, const i32 look_in[3], i32 *
 }
 
 #ifndef BT_EMU
+/* Ray order.  A batch arrives in the caller's order (origins hashed all over the world), so the
+ * 32 rays of a warp would start in 32 different corners of the tree and share nothing.  Rays are therefore traversed
+ * in the order of their origin's position in the ray tree's Morton-sorted leaf array: neighbours in a warp start in
+ * the same leaves and walk the same upper nodes.  k_ray_leafpos inverts leafEnt once per tree build, k_ray_keys makes
+ * (leaf position, ray index) pairs for the radix sort; the winners are written back by ray index, so the caller sees
+ * no reordering. */
+__global__ void __launch_bounds__(256) k_ray_leafpos(DevWorld W, i32 *leafPos) { PDL_ENTRY();
+	GS_FOR(t, W.n_leaves) leafPos[W.leafEnt[t]] = t;
+}
+__global__ void __launch_bounds__(256) k_ray_keys(const i32 *origin, i32 n_rays, const i32 *rank2slot, const i32 *leafPos,
+                                                   i32 n_live, u64 *keys, i32 *idx) { PDL_ENTRY_ALWAYS();
+	for (i32 i = TID; i < n_rays; i += (i32)(gridDim.x * blockDim.x)) {
+		const i32 og = origin[i];
+		keys[i] = (og < 0 || og >= n_live) ? 0ull : (u64)(u32)leafPos[rank2slot[og]];
+		idx[i] = i;
+	}
+}
+
 /* origin/winner are LIVE RANKS (oldest-first order of bt_world_download); rank2slot /
- * slot2rank translate to device slots. */
+ * slot2rank translate to device slots.  order: NULL, or the ray index each thread takes. */
 __global__ void __launch_bounds__(128) k_raycast(DevWorld W, const i32 *origin, const i32 *look, i32 n_rays,
-                                                  i32 *winner, const i32 *rank2slot, const i32 *slot2rank, i32 n_live) { PDL_ENTRY();
+                                                  i32 *winner, const i32 *rank2slot, const i32 *slot2rank, i32 n_live,
+                                                  const i32 *order) { PDL_ENTRY();
 	__shared__ i32 stacks[BT_STACK * 128];
 	i32 i = (i32)(blockIdx.x * blockDim.x + threadIdx.x);
 	if (i >= n_rays) return;
+	if (order) i = order[i];
 	i32 lk[3] = {look[3 * i], look[3 * i + 1], look[3 * i + 2]};
 	i32 og = origin[i];
 	if (og < 0 || og >= n_live) { winner[i] = -1; return; } /* not a live entity: no caster, no hit */

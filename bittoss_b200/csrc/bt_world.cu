@@ -55,6 +55,7 @@ struct RayTree {
 	BvhNode *nodes;
 	Box6 *nodeBox, *leafBox;
 	i32 *rank2slot, *slot2rank;
+	i32 *leafPos; /* entity -> position in this tree's sorted leaf array (ray ordering) */
 	i32 *wroot;
 	i32 n_leaves;
 	i32 key_shift[3];
@@ -112,6 +113,9 @@ struct bt_world {
 	i32 root_phase_ctr;         /* last value handed to a launch / the host as W.root_phase */
 	i32 sliders_used, wires_used; /* high-water marks of the slider / wire arenas */
 	bt_poke *d_pokes; i32 pokes_cap;
+	/* ray ordering scratch (grows with the largest batch seen) */
+	u64 *d_raykeys, *d_raykeys_alt; i32 *d_rayidx, *d_rayidx_alt; u32 *d_rayhist; i32 rays_cap;
+	i64 sort_rays; /* option "sort_rays": order the rays of a batch by the leaf position of their origin (default 1) */
 	bool poked;                 /* the host wrote into the world since the counters were last fetched */
 	cudaError_t launch_err;     /* first failed kernel launch since the last check (reported at the next sync point) */
 	DevArrays arrays;
@@ -227,6 +231,11 @@ void bt_world_destroy(bt_world *w) {
 	if (w->d_reqs) cudaFree(w->d_reqs);
 	if (w->d_req_starts) cudaFree(w->d_req_starts);
 	if (w->d_pokes) cudaFree(w->d_pokes);
+	if (w->d_raykeys) cudaFree(w->d_raykeys);
+	if (w->d_raykeys_alt) cudaFree(w->d_raykeys_alt);
+	if (w->d_rayidx) cudaFree(w->d_rayidx);
+	if (w->d_rayidx_alt) cudaFree(w->d_rayidx_alt);
+	if (w->d_rayhist) cudaFree(w->d_rayhist);
 	if (w->ev0) cudaEventDestroy(w->ev0);
 	if (w->ev1) cudaEventDestroy(w->ev1);
 	if (w->stream) cudaStreamDestroy(w->stream);
@@ -254,6 +263,7 @@ int bt_world_create(bt_world **out, int device, int32_t max_ents, int32_t max_sl
 	w->h_flag = NULL; w->ev0 = w->ev1 = NULL; w->stream = NULL;
 	w->root_phase_ctr = 0; w->sliders_used = 0; w->wires_used = 0; w->d_pokes = NULL; w->pokes_cap = 0; w->poked = false;
 	w->launch_err = cudaSuccess;
+	w->d_raykeys = w->d_raykeys_alt = NULL; w->d_rayidx = w->d_rayidx_alt = NULL; w->d_rayhist = NULL; w->rays_cap = 0; w->sort_rays = 1;
 	*out = w;
 #define TRY(x) do { int _r = (x); if (_r) { bt_world_destroy(w); *out = NULL; return _r; } } while (0)
 #define TRYCU(x) do { cudaError_t _e = (x); if (_e != cudaSuccess) { set_err("%s failed: %s (bt_world.cu:%d)", #x, cudaGetErrorString(_e), __LINE__); bt_world_destroy(w); *out = NULL; return BT_ERR_CUDA; } } while (0)
@@ -307,7 +317,7 @@ int bt_world_create(bt_world **out, int device, int32_t max_ents, int32_t max_sl
 	TRY(dalloc(w, &w->ray.leafEnt, n)); TRY(dalloc(w, &w->ray.leafEnt_alt, n));
 	TRY(dalloc(w, &w->ray.leafParent, n)); TRY(dalloc(w, &w->ray.nodeParent, n)); TRY(dalloc(w, &w->ray.nodeCount, n));
 	TRY(dalloc(w, &w->ray.nodes, n)); TRY(dalloc(w, &w->ray.nodeBox, n)); TRY(dalloc(w, &w->ray.leafBox, n));
-	TRY(dalloc(w, &w->ray.rank2slot, n)); TRY(dalloc(w, &w->ray.slot2rank, n));
+	TRY(dalloc(w, &w->ray.rank2slot, n)); TRY(dalloc(w, &w->ray.slot2rank, n)); TRY(dalloc(w, &w->ray.leafPos, n));
 	TRY(dalloc(w, &w->d_stage_a, 3 * n)); TRY(dalloc(w, &w->d_stage_b, 3 * n));
 	w->ranks_valid = false;
 #undef TRY
@@ -354,6 +364,7 @@ int bt_world_set_option(bt_world *w, const char *name, int64_t value) {
 		return BT_OK;
 	}
 	if (!strcmp(name, "device_ticks")) { w->device_ticks = value != 0; return BT_OK; }
+	if (!strcmp(name, "sort_rays")) { w->sort_rays = value != 0; return BT_OK; }
 	if (!strcmp(name, "pair_patch")) { w->W.patch = value != 0; return BT_OK; }
 	if (!strcmp(name, "patch_shift")) { w->W.patch_shift = value < 0 ? 0 : (value > 20 ? 20 : (i32)value); return BT_OK; }
 	if (!strcmp(name, "run_ahead")) { w->run_ahead = value != 0; return BT_OK; }
@@ -574,19 +585,22 @@ int bt_world_upload(bt_world *w, const bt_world_desc *d) {
 
 /* ---------------------------------------------------------------- tick */
 
-static int radix_sort(bt_world *w, int key_bits) {
-	DevWorld &W = w->W;
-	const i32 n = W.n;
+/* stable LSD radix sort of (key, payload) pairs, 8 bits per pass; the sorted data ends up in *keys / *vals (the
+ * pointers are swapped with their alternates after every pass).  hist: 256 x tiles counters. */
+static int radix_sort_buf(bt_world *w, int cls, u64 **keys, i32 **vals, u64 **keys_alt, i32 **vals_alt, i32 n, int key_bits, u32 *hist) {
 	const int nb = (n + SORT_TILE - 1) / SORT_TILE;
 	for (int shift = 0; shift < key_bits; shift += 8) {
-		LAUNCH(w, PK_SORT, k_sort_hist, nb, SORT_THREADS, W.keys, n, shift, w->d_sorthist, nb);
-		LAUNCH(w, PK_SORT, k_sort_scan, 1, 1024, w->d_sorthist, 256 * nb);
-		LAUNCH(w, PK_SORT, k_sort_scatter, nb, SORT_THREADS, W.keys, W.leafEnt, W.keys_alt, W.leafEnt_alt, n, shift,
-		       w->d_sorthist, nb);
-		std::swap(W.keys, W.keys_alt);
-		std::swap(W.leafEnt, W.leafEnt_alt);
+		LAUNCH(w, cls, k_sort_hist, nb, SORT_THREADS, (const u64 *)*keys, n, shift, hist, nb);
+		LAUNCH(w, cls, k_sort_scan, 1, 1024, hist, 256 * nb);
+		LAUNCH(w, cls, k_sort_scatter, nb, SORT_THREADS, (const u64 *)*keys, (const i32 *)*vals, *keys_alt, *vals_alt, n, shift, (const u32 *)hist, nb);
+		std::swap(*keys, *keys_alt);
+		std::swap(*vals, *vals_alt);
 	}
 	return 0;
+}
+static int radix_sort(bt_world *w, int key_bits) {
+	DevWorld &W = w->W;
+	return radix_sort_buf(w, PK_SORT, &W.keys, &W.leafEnt, &W.keys_alt, &W.leafEnt_alt, W.n, key_bits, w->d_sorthist);
 }
 
 static int bits_for(u32 x) { int b = 0; while (x) { b++; x >>= 1; } return b; }
@@ -1604,6 +1618,7 @@ static int ray_build(bt_world *w) {
 	int r = build_tree(w);
 	if (!r) r = refit(w, false);
 	if (!r) r = live_ranks(w, PK_RAY_BUILD);
+	if (!r && w->W.n_leaves > 0) LAUNCH(w, PK_RAY_BUILD, k_ray_leafpos, gsblk(w->W.n_leaves), GS_BLOCK, w->W, w->ray.leafPos);
 	ray_swap(w);
 	w->tree_valid = tv; w->ticks_since_build = tsb; w->pair_builds_at_tree = pbat;
 	w->stats.tree_builds = builds; w->stats.tree_refits = refits;
@@ -1613,9 +1628,28 @@ static int ray_build(bt_world *w) {
 }
 
 static int ray_cast(bt_world *w, const i32 *d_origin, const i32 *d_look, i32 n_rays, i32 *d_winner) {
+	const i32 *order = NULL;
+	if (w->sort_rays && n_rays >= 4096 && w->ray.n_leaves > 1) {
+		/* (leaf position of the origin, ray index) sorted by position: see k_ray_keys */
+		if (n_rays > w->rays_cap) {
+			cudaFree(w->d_raykeys); cudaFree(w->d_raykeys_alt); cudaFree(w->d_rayidx); cudaFree(w->d_rayidx_alt); cudaFree(w->d_rayhist);
+			w->d_raykeys = w->d_raykeys_alt = NULL; w->d_rayidx = w->d_rayidx_alt = NULL; w->d_rayhist = NULL; w->rays_cap = 0;
+			const size_t nr = (size_t)n_rays;
+			CK(cudaMalloc(&w->d_raykeys, sizeof(u64) * nr)); CK(cudaMalloc(&w->d_raykeys_alt, sizeof(u64) * nr));
+			CK(cudaMalloc(&w->d_rayidx, sizeof(i32) * nr)); CK(cudaMalloc(&w->d_rayidx_alt, sizeof(i32) * nr));
+			CK(cudaMalloc(&w->d_rayhist, sizeof(u32) * 256 * ((nr + SORT_TILE - 1) / SORT_TILE + 1)));
+			w->rays_cap = n_rays;
+		}
+		LAUNCH(w, PK_RAYCAST, k_ray_keys, gsblk(n_rays), GS_BLOCK, d_origin, n_rays, (const i32 *)w->ray.rank2slot, (const i32 *)w->ray.leafPos,
+		       (i32)w->stats.live_ents, w->d_raykeys, w->d_rayidx);
+		int r = radix_sort_buf(w, PK_RAYCAST, &w->d_raykeys, &w->d_rayidx, &w->d_raykeys_alt, &w->d_rayidx_alt, n_rays,
+		                       bits_for((u32)w->ray.n_leaves), w->d_rayhist);
+		if (r) return r;
+		order = w->d_rayidx;
+	}
 	ray_swap(w);
 	LAUNCH(w, PK_RAYCAST, k_raycast, nblk(n_rays, 128), 128, w->W, d_origin, d_look, n_rays, d_winner,
-	       w->ray.rank2slot, w->ray.slot2rank, (i32)w->stats.live_ents);
+	       (const i32 *)w->ray.rank2slot, (const i32 *)w->ray.slot2rank, (i32)w->stats.live_ents, order);
 	ray_swap(w);
 	return 0;
 }
