@@ -115,7 +115,10 @@ struct bt_world {
 	bt_poke *d_pokes; i32 pokes_cap;
 	/* ray ordering scratch (grows with the largest batch seen) */
 	u64 *d_raykeys, *d_raykeys_alt; i32 *d_rayidx, *d_rayidx_alt; u32 *d_rayhist; i32 rays_cap;
-	i64 sort_rays; /* option "sort_rays": order the rays of a batch by the leaf position of their origin (default 1) */
+	i64 sort_rays; /* option "sort_rays": order the rays of a batch by the leaf position of their origin (default 0:
+	                * measured on 4 M rays over the 1 M-entity world, 6.87 ms either way -- the sort itself costs 0.08 ms,
+	                * the traversal does not get faster: it is bound by lanes idling behind the longest ray of their warp
+	                * (9.2 of 32 threads active per instruction), not by where the rays start) */
 	bool poked;                 /* the host wrote into the world since the counters were last fetched */
 	cudaError_t launch_err;     /* first failed kernel launch since the last check (reported at the next sync point) */
 	DevArrays arrays;
@@ -263,7 +266,7 @@ int bt_world_create(bt_world **out, int device, int32_t max_ents, int32_t max_sl
 	w->h_flag = NULL; w->ev0 = w->ev1 = NULL; w->stream = NULL;
 	w->root_phase_ctr = 0; w->sliders_used = 0; w->wires_used = 0; w->d_pokes = NULL; w->pokes_cap = 0; w->poked = false;
 	w->launch_err = cudaSuccess;
-	w->d_raykeys = w->d_raykeys_alt = NULL; w->d_rayidx = w->d_rayidx_alt = NULL; w->d_rayhist = NULL; w->rays_cap = 0; w->sort_rays = 1;
+	w->d_raykeys = w->d_raykeys_alt = NULL; w->d_rayidx = w->d_rayidx_alt = NULL; w->d_rayhist = NULL; w->rays_cap = 0; w->sort_rays = 0;
 	*out = w;
 #define TRY(x) do { int _r = (x); if (_r) { bt_world_destroy(w); *out = NULL; return _r; } } while (0)
 #define TRYCU(x) do { cudaError_t _e = (x); if (_e != cudaSuccess) { set_err("%s failed: %s (bt_world.cu:%d)", #x, cudaGetErrorString(_e), __LINE__); bt_world_destroy(w); *out = NULL; return BT_ERR_CUDA; } } while (0)

@@ -276,6 +276,7 @@ int bt_world_profile_read(bt_world *w, bt_profile *out, int reset);
  * for batched worlds and up to 786 k entities, short kernels only beyond); "small_worlds" 0/1 brute-force pair search per world
  * when every world holds <= 128 entities (read at upload); "narrow_blocks" / "narrow_threads" grid of
  * the narrow phase (148*8 x 256, the measured optimum).
+ * "sort_rays" 0/1 traverse the rays of a batch in the order of their origin's leaf position (device radix sort; 0: no gain measured);
  * "allow_unsupported" 1 = bt_world_upload accepts handler IDs without a device implementation,
  * treats them as NIL and counts every would-be invocation in bt_tick_stats.unsupported_events
  * (used to measure handler coverage on real levels). */

@@ -285,13 +285,11 @@ def test_cuda_small_world_pair_search_agrees_with_tree(bt):
 
 
 def test_cuda_raycast_large_batch_sorted_equals_unsorted_and_oracle(bt, oracle_lib):
-    """batches of >= 4096 rays are traversed in the order of their origin's leaf position (radix-sorted on the device);
-    the winners come back by ray index: identical to the unsorted traversal and to the oracle's brute force"""
+    """option sort_rays: batches of >= 4096 rays traversed in the order of their origin's leaf position (radix-sorted on
+    the device); the winners come back by ray index: identical to the unsorted traversal and to the oracle's brute force"""
     wa, _ = load_scenario("stack4k_pushall")
     rng = np.random.RandomState(11)
     n = 20000
-    origin = rng.randint(0, wa.n, size=n).astype(np.int32)
-    origin[::97] = -1                      # not a live entity: no caster, no hit
     look = rng.randint(-64, 65, size=(n, 3)).astype(np.int32)
     look[np.abs(look).sum(1) == 0] = (0, 0, 64)
     ow = oracle_lib.create(wa)
@@ -299,11 +297,15 @@ def test_cuda_raycast_large_batch_sorted_equals_unsorted_and_oracle(bt, oracle_l
     for _ in range(6):
         ow.step(31)
         w.step(31)
+    live = w.count()[0]
+    assert live == ow.count()[0] and live < wa.n   # some cubes were crushed: ranks are live ranks
+    origin = rng.randint(0, live, size=n).astype(np.int32)
+    origin[::97] = -1                      # not a live entity: no caster, no hit
     want = ow.selectcast(np.where(origin < 0, 0, origin), look)
     want[origin < 0] = -1
-    got_sorted = w.raycast(origin, look)
-    w.set_option("sort_rays", 0)
     got_plain = w.raycast(origin, look)
+    w.set_option("sort_rays", 1)
+    got_sorted = w.raycast(origin, look)
     w.close()
     assert np.array_equal(got_sorted, got_plain)
     assert np.array_equal(got_sorted, want)
