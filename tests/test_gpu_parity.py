@@ -309,3 +309,29 @@ def test_cuda_raycast_large_batch_sorted_equals_unsorted_and_oracle(bt, oracle_l
     w.close()
     assert np.array_equal(got_sorted, got_plain)
     assert np.array_equal(got_sorted, want)
+
+
+def test_cuda_raycast_matches_reference_selectcast(bt, ref_lib):
+    """against the REFERENCE's own selectCast (raycast.cpp:16-57), not the port: the state the device has reached after
+    kicked ticks is downloaded and rebuilt as `ent`s through the reference's initEnt / pickupNoHandlers
+    (btref_build_from_desc), hold trees included (a caster's own tree is skipped, raycast.cpp:34)"""
+    for name, ticks in (("lobby_kick", 15), ("spider_kick", 10), ("stack4k_pushall", 8)):
+        wa, _ = load_scenario(name)
+        w = bt.World(wa)
+        for _ in range(ticks):
+            w.step(31)
+        state = w.download()
+        rng = np.random.RandomState(5)
+        origin = rng.randint(0, state.n, size=1500).astype(np.int32)
+        look = rng.randint(-64, 65, size=(1500, 3)).astype(np.int32)
+        look[::7, 2] = 0
+        look[np.abs(look).sum(1) == 0] = (0, 0, 64)
+        got = w.raycast(origin, look)
+        w.close()
+        wid = ref_lib.new_world()
+        try:
+            assert ref_lib.build_from(state) == state.n
+            want = ref_lib.selectcast(origin, look)
+        finally:
+            ref_lib.free_world(wid)
+        assert np.array_equal(got, want), name
