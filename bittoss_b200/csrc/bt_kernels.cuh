@@ -66,12 +66,11 @@ __global__ void __launch_bounds__(BT_BLOCK) k_flush_scan(DevWorld W) { PDL_ENTRY
  * changed by the pass itself (a crush kills only its own entity, a fumble sets no drop flag, a
  * pickup's handlers request no pickup), every other condition is re-evaluated when the hit is
  * handled, so the result equals the sequential walk. */
-__global__ void __launch_bounds__(BT_BLOCK) k_flush_serial(DevWorld W) { PDL_ENTRY();
-	LocalStats st = {0, 0, 0, 0, 0};
-	st.rk_ordered = 1; /* fumbles of this launch take their place in gs->rootEnts from the world's counter */
+/* the body: all 32 lanes of ONE warp, world g */
+static __device__ __forceinline__ void bt_flush_serial_warp(const DevWorld &W, const i32 g, LocalStats &st) {
 	const int lane = threadIdx.x & 31;
-	const i32 g = TID >> 5;
-	if (g < W.n_worlds) {
+	st.rk_ordered = 1; /* fumbles of this launch take their place in gs->rootEnts from the world's counter */
+	{
 		int work = 0;
 		if (lane == 0) {
 			W.flip[g] ^= 1;
@@ -133,6 +132,12 @@ __global__ void __launch_bounds__(BT_BLOCK) k_flush_serial(DevWorld W) { PDL_ENT
 			}
 		}
 	}
+	st.rk_ordered = 0;
+}
+__global__ void __launch_bounds__(BT_BLOCK) k_flush_serial(DevWorld W) { PDL_ENTRY();
+	LocalStats st = {0, 0, 0, 0, 0};
+	const i32 g = TID >> 5;
+	if (g < W.n_worlds) bt_flush_serial_warp(W, g, st);
 	stats_flush(W, st);
 }
 __global__ void __launch_bounds__(BT_BLOCK) k_flush_misc(DevWorld W) { PDL_ENTRY(); t_flush_misc(W, TID); }

@@ -113,7 +113,9 @@ enum {
 	CT_TREE_EDITS = 48,  /* fumbles + pickups + deaths so far: a host binding re-reads the hold tree only when it moved */
 	CT_WORDS = 64
 };
-enum { SK_ITERS = 0, SK_CAND, SK_POS, SK_PUSH, SK_SERIAL, SK_CRUSH, SK_FUMBLE, SK_NUM };
+enum { SK_ITERS = 0, SK_CAND, SK_POS, SK_PUSH, SK_SERIAL, SK_CRUSH, SK_FUMBLE, SK_ETICKS, SK_NUM };
+/* SK_ITERS / SK_ETICKS are only written by the one-block-per-world tick (k_tick_small): doIteration rounds summed over
+ * the worlds, and live entities summed over the finished ticks; the generic schedule keeps both on the host */
 
 struct DevWorld {
 	i32 n;        /* slots in use */

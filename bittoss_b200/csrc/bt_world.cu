@@ -39,11 +39,11 @@ static void set_err(const char *fmt, const char *a, const char *b, int line) {
 
 enum {
 	PK_PRE = 0, PK_FLUSH, PK_BEGIN, PK_BUILD_KEYS, PK_SORT, PK_LBVH, PK_REFIT, PK_PAIRS, PK_NARROW, PK_COLLIDE, PK_DECIDE, PK_PUSH,
-	PK_POST, PK_HASH, PK_RAY_BUILD, PK_RAYCAST, PK_EXCHANGE, PK_TICK, PK_NUM
+	PK_POST, PK_HASH, PK_RAY_BUILD, PK_RAYCAST, PK_EXCHANGE, PK_TICK, PK_FUSED, PK_NUM
 };
 static const char *PK_NAMES[PK_NUM] = {"pre",    "flush1", "begin_integrate", "morton_keys", "radix_sort",
                                        "lbvh_build", "refit", "pairs", "narrow", "collide",       "decide",      "push",
-                                       "post",   "hash",   "ray_tree_build",  "raycast", "host_exchange", "tick_handlers"};
+                                       "post",   "hash",   "ray_tree_build",  "raycast", "host_exchange", "tick_handlers", "world_tick_small"};
 
 typedef long long i64;
 
@@ -100,6 +100,7 @@ struct bt_world {
 	i64 run_ahead;       /* option: 1 = enqueue the predicted iterations without waiting for the host */
 	bt_tick_stats stats;
 	bool profiling;
+	bool profiling_generic; /* unused knob kept false: per-kernel profiles of small worlds use option fused_small = 0 */
 	cudaEvent_t ev0, ev1;
 	i64 prof_launches[PK_NUM];
 	double prof_ms[PK_NUM];
@@ -121,6 +122,9 @@ struct bt_world {
 	                * (9.2 of 32 threads active per instruction), not by where the rays start) */
 	bool poked;                 /* the host wrote into the world since the counters were last fetched */
 	cudaError_t launch_err;     /* first failed kernel launch since the last check (reported at the next sync point) */
+	i64 fused_small;            /* option "fused_small": whole ticks of small worlds in one block per world (k_tick_small) */
+	i32 small_biggest;          /* slots of the largest world of the last upload */
+	bool fused_dirty;           /* fused ticks ran since the host last looked: counters, live count, cached pairs are stale */
 	DevArrays arrays;
 };
 template <typename T> static int dalloc(bt_world *w, T **p, size_t count) {
@@ -262,10 +266,10 @@ int bt_world_create(bt_world **out, int device, int32_t max_ents, int32_t max_sl
 	w->device = device;
 	w->cap_ents = max_ents; w->cap_sliders = max_sliders; w->cap_wires = max_wires; w->cap_worlds = max_worlds;
 	w->tree_valid = false; w->deltas_pending = true; w->ticks_since_build = 0; w->full_flush_left = 2; w->scan_flushes_left = 2; w->ctrls_fused = false;
-	w->rebuild_every = 16; w->max_iterations = 100000; w->pair_cache = 1; w->pair_rebuilds = 0; w->pair_overflows = 0; w->seen_pair_builds = 0; w->seen_pair_patches = 0; w->pair_builds_at_tree = 0; w->profiling = false; w->ray_valid = false; w->uid_map_valid = false; w->ctr_fresh = false; w->margin_opt = -1; w->narrow_blocks = 148 * 8; w->narrow_threads = 256; w->pdl_opt = getenv("BT_NO_PDL") ? 0 : -1; w->pdl = false; w->pdl_long = false; /* decided at upload, together with W.pdl */ w->small_worlds = true; w->d_reqs = NULL; w->d_req_starts = NULL; w->reqs_cap = 0; w->any_ticks = w->any_rand = false; w->bad_tick = 0; w->device_ticks = 1;
+	w->rebuild_every = 16; w->max_iterations = 100000; w->pair_cache = 1; w->pair_rebuilds = 0; w->pair_overflows = 0; w->seen_pair_builds = 0; w->seen_pair_patches = 0; w->pair_builds_at_tree = 0; w->profiling = false; w->profiling_generic = false; w->ray_valid = false; w->uid_map_valid = false; w->ctr_fresh = false; w->margin_opt = -1; w->narrow_blocks = 148 * 8; w->narrow_threads = 256; w->pdl_opt = getenv("BT_NO_PDL") ? 0 : -1; w->pdl = false; w->pdl_long = false; /* decided at upload, together with W.pdl */ w->small_worlds = true; w->d_reqs = NULL; w->d_req_starts = NULL; w->reqs_cap = 0; w->any_ticks = w->any_rand = false; w->bad_tick = 0; w->device_ticks = 1;
 	w->h_flag = NULL; w->ev0 = w->ev1 = NULL; w->stream = NULL;
 	w->root_phase_ctr = 0; w->sliders_used = 0; w->wires_used = 0; w->d_pokes = NULL; w->pokes_cap = 0; w->poked = false;
-	w->launch_err = cudaSuccess;
+	w->launch_err = cudaSuccess; w->fused_small = 1; w->fused_dirty = false;
 	w->d_raykeys = w->d_raykeys_alt = NULL; w->d_rayidx = w->d_rayidx_alt = NULL; w->d_rayhist = NULL; w->rays_cap = 0; w->sort_rays = 0;
 	*out = w;
 #define TRY(x) do { int _r = (x); if (_r) { bt_world_destroy(w); *out = NULL; return _r; } } while (0)
@@ -368,6 +372,7 @@ int bt_world_set_option(bt_world *w, const char *name, int64_t value) {
 	}
 	if (!strcmp(name, "device_ticks")) { w->device_ticks = value != 0; return BT_OK; }
 	if (!strcmp(name, "sort_rays")) { w->sort_rays = value != 0; return BT_OK; }
+	if (!strcmp(name, "fused_small")) { w->fused_small = value != 0; return BT_OK; }
 	if (!strcmp(name, "pair_patch")) { w->W.patch = value != 0; return BT_OK; }
 	if (!strcmp(name, "patch_shift")) { w->W.patch_shift = value < 0 ? 0 : (value > 20 ? 20 : (i32)value); return BT_OK; }
 	if (!strcmp(name, "run_ahead")) { w->run_ahead = value != 0; return BT_OK; }
@@ -552,7 +557,7 @@ int bt_world_upload(bt_world *w, const bt_world_desc *d) {
 	UPRAW(W.smin, d->slider_min, d->n_sliders, i32); UPRAW(W.smax, d->slider_max, d->n_sliders, i32);
 	UP(W.wire_off, wire_off); UP(W.wire_to, wire_to); UP(W.wire_cap, wire_cap); UP(W.rootKey, rootKey);
 	UP(W.wire_cnt, wire_cnt); UP(W.wireAdd, minus1); UP(W.wireRm, minus1);
-	w->sliders_used = d->n_sliders; w->root_phase_ctr = 0; w->poked = false;
+	w->sliders_used = d->n_sliders; w->root_phase_ctr = 0; w->poked = false; w->fused_dirty = false;
 	CK(cudaMemsetAsync(W.ctr, 0, sizeof(u32) * CT_WORDS, w->stream));
 	{ int rr = raise_cache_invalid(w); if (rr) return rr; }
 	CK(cudaMemsetAsync(W.dirtyStamp, 0, sizeof(u32) * (size_t)w->cap_ents, w->stream));
@@ -574,6 +579,7 @@ int bt_world_upload(bt_world *w, const bt_world_desc *d) {
 		i32 biggest = 0;
 		for (int g = 0; g < nw; g++) biggest = std::max(biggest, wend[g] - wbegin[g]);
 		W.small_mode = (w->small_worlds && biggest <= BT_SMALL_WORLD) ? 1 : 0;
+		w->small_biggest = biggest;
 		if (w->margin_opt < 0) W.margin = W.small_mode ? 128 : 32;
 		/* Dependent launches pay when a tick is many short kernels (batched or small worlds: +5-7 %).
 		 * One big world spends its tick in two long kernels; there the resident waiting blocks cost
@@ -861,11 +867,74 @@ static int do_physics_end(bt_world *w) {
 	return 0;
 }
 
+} /* extern "C" */
+
+/* After ticks of the one-block-per-world kernel the host has not looked at the device: the dead entities of those
+ * ticks are still on the dead list, the live count and entity-ticks are in device counters, and the generic schedule's
+ * cached pairs / flush hints know nothing of what happened.  Called before anything that needs them. */
+static int fused_settle(bt_world *w, bool leaving) {
+	if (!w->fused_dirty) return 0;
+	DevWorld &W = w->W;
+	int r = fetch_ctr(w);
+	if (r) return r;
+	const u64 *s = (const u64 *)&w->h_flag[CT_STAT0];
+	w->stats.entity_ticks += (i64)s[SK_ETICKS];
+	w->stats.iterations += (i64)((s[SK_ITERS] + (u64)W.n_worlds / 2) / (u64)(W.n_worlds ? W.n_worlds : 1)); /* mean over the worlds */
+	CK(cudaMemsetAsync(((u64 *)&W.ctr[CT_STAT0]) + SK_ETICKS, 0, sizeof(u64), w->stream));
+	CK(cudaMemsetAsync(((u64 *)&W.ctr[CT_STAT0]) + SK_ITERS, 0, sizeof(u64), w->stream));
+	if (w->h_flag[CT_DEAD_N]) {
+		w->stats.live_ents -= (i64)w->h_flag[CT_DEAD_N];
+		w->ranks_valid = false;
+		CK(cudaMemsetAsync(&W.ctr[CT_DEAD_N], 0, sizeof(u32), w->stream));
+		w->h_flag[CT_DEAD_N] = 0;
+	}
+	if (w->h_flag[CT_NEED_REBUILD]) CK(cudaMemsetAsync(&W.ctr[CT_NEED_REBUILD], 0, sizeof(u32), w->stream));
+	if (leaving) { /* the generic schedule takes over: it must rebuild its pair list and look at every flush flag */
+		r = raise_cache_invalid(w);
+		if (r) return r;
+		w->tree_valid = false;
+		w->deltas_pending = true;
+		if (w->full_flush_left < 2) w->full_flush_left = 2;
+		if (w->scan_flushes_left < 2) w->scan_flushes_left = 2;
+		w->fused_dirty = false;
+		w->ctr_fresh = false;
+	}
+	return 0;
+}
+
+static int step_small_fused(bt_world *w, uint32_t phases) {
+	DevWorld &W = w->W;
+	if ((phases & BT_PHASE_TICKS) && w->bad_tick && !W.lenient) {
+		snprintf(g_err, sizeof g_err, "BT_PHASE_TICKS: tick handler id %d has no device implementation", w->bad_tick);
+		return BT_ERR_UNSUPPORTED;
+	}
+	if ((phases & BT_PHASE_TICKS) && !w->any_ticks) phases &= ~BT_PHASE_TICKS;
+	if (w->root_phase_ctr > (1 << 27) - 2 * SW_PHASES) { snprintf(g_err, sizeof g_err, "root-order phases exhausted: download and upload the world again"); return BT_ERR_OVERFLOW; }
+	W.root_phase = w->root_phase_ctr + 1;
+	w->root_phase_ctr += SW_PHASES;
+	if (w->small_biggest <= 64) LAUNCH(w, PK_FUSED, k_tick_small<64>, W.n_worlds, 64, W, phases);
+	else LAUNCH(w, PK_FUSED, k_tick_small<BT_SMALL_WORLD>, W.n_worlds, BT_SMALL_WORLD, W, phases);
+	w->fused_dirty = true;
+	w->ctr_fresh = false; w->ray_valid = false; w->uid_map_valid = w->uid_map_valid;
+	if (phases & BT_PHASE_PHYSICS) { w->deltas_pending = false; w->stats.ticks++; }
+	else if (phases & BT_PHASE_GRAVITY) w->deltas_pending = true;
+	if (phases & BT_PHASE_PREP) { w->full_flush_left = 0; w->scan_flushes_left = 0; }
+	CHECK_LAUNCHES(w);
+	return BT_OK;
+}
+
+extern "C" {
+
 int bt_world_step(bt_world *w, uint32_t phases) {
 	if (!w) return BT_ERR_ARG;
 	CK(cudaSetDevice(w->device));
 	DevWorld &W = w->W;
 	const i32 n = W.n;
+	/* small worlds: the whole step in one launch, one block per world, nothing comes back to the host */
+	if (W.small_mode && w->fused_small && w->pair_cache && !w->profiling_generic &&
+	    !(phases & ~(BT_PHASE_ALL | BT_PHASE_WORLD_RULES | BT_PHASE_TICKS)))
+		return step_small_fused(w, phases);
+	{ int rr = fused_settle(w, true); if (rr) return rr; }
 	if (phases & BT_PHASE_WORLD_RULES) {
 		LAUNCH(w, PK_PRE, k_world_rules, nblk(n), BT_BLOCK, W);
 		/* a death requested here is flushed by this step's prepPhysics: make sure it looks */
@@ -1026,6 +1095,7 @@ static int ensure_ranks(bt_world *w) {
 int bt_world_apply_host_deltas(bt_world *w, const int32_t *d_center, const int32_t *d_vel, int32_t n_ents) {
 	if (!w || !d_center || !d_vel || n_ents < 0) return BT_ERR_ARG;
 	CK(cudaSetDevice(w->device));
+	{ int rr = fused_settle(w, false); if (rr) return rr; }
 	if ((i64)n_ents != w->stats.live_ents) return BT_ERR_ARG;
 	CK(cudaMemcpyAsync(w->d_stage_a, d_center, sizeof(i32) * 3 * (size_t)n_ents, cudaMemcpyHostToDevice, w->stream));
 	CK(cudaMemcpyAsync(w->d_stage_b, d_vel, sizeof(i32) * 3 * (size_t)n_ents, cudaMemcpyHostToDevice, w->stream));
@@ -1100,6 +1170,7 @@ int bt_world_apply_requests(bt_world *w, const bt_request *reqs, int32_t n) {
 int bt_world_read_state(bt_world *w, int32_t *center, int32_t *vel, int32_t n_ents) {
 	if (!w || !center || !vel || n_ents < 0) return BT_ERR_ARG;
 	CK(cudaSetDevice(w->device));
+	{ int rr = fused_settle(w, false); if (rr) return rr; }
 	if ((i64)n_ents != w->stats.live_ents) return BT_ERR_ARG;
 	bool dense = (i64)w->W.n == w->stats.live_ents;
 	if (!dense) { int r = ensure_ranks(w); if (r) return r; }
@@ -1118,11 +1189,20 @@ int bt_world_sync(bt_world *w) {
 	return BT_OK;
 }
 
-int64_t bt_world_live_ents(bt_world *w) { return w ? (int64_t)w->stats.live_ents : (int64_t)BT_ERR_ARG; }
+int64_t bt_world_live_ents(bt_world *w) {
+	if (!w) return (int64_t)BT_ERR_ARG;
+	if (w->fused_dirty) { /* one-block-per-world ticks keep their dead on the device until somebody asks */
+		if (cudaSetDevice(w->device) != cudaSuccess) return (int64_t)BT_ERR_CUDA;
+		int r = fused_settle(w, false);
+		if (r) return (int64_t)r;
+	}
+	return (int64_t)w->stats.live_ents;
+}
 
 int bt_world_stats(bt_world *w, bt_tick_stats *out, int reset) {
 	if (!w || !out) return BT_ERR_ARG;
 	CK(cudaSetDevice(w->device));
+	{ int rr = fused_settle(w, false); if (rr) return rr; }
 	u64 s[SK_NUM];
 	CK(cudaMemcpyAsync(s, &w->W.ctr[CT_STAT0], sizeof(s), cudaMemcpyDeviceToHost, w->stream));
 	CK(cudaStreamSynchronize(w->stream));
@@ -1233,6 +1313,7 @@ int bt_world_assign(bt_world *dst, bt_world *src) {
 	rebase(&dst->ray, sizeof(dst->ray), src, dst);
 	dst->arrays = src->arrays;
 	rebase(&dst->arrays, sizeof(dst->arrays), src, dst);
+	dst->fused_small = src->fused_small; dst->fused_dirty = src->fused_dirty; dst->small_biggest = src->small_biggest;
 	dst->root_phase_ctr = src->root_phase_ctr; dst->sliders_used = src->sliders_used; dst->wires_used = src->wires_used; dst->poked = src->poked;
 	dst->tree_valid = src->tree_valid; dst->deltas_pending = src->deltas_pending; dst->any_rules = src->any_rules;
 	dst->full_flush_left = src->full_flush_left; dst->scan_flushes_left = src->scan_flushes_left; dst->ctrls_fused = src->ctrls_fused;
@@ -1507,6 +1588,7 @@ int bt_world_grow(bt_world *w, int32_t n_new, const int32_t *n_sliders, const in
 	CK(cudaMemcpyAsync(W.wend + world, &wend, sizeof(i32), cudaMemcpyHostToDevice, w->stream));
 	CK(cudaStreamSynchronize(w->stream));
 	W.n = first + n_new;
+	w->small_biggest = W.n; /* one world: its slot count */
 	w->sliders_used = s; w->wires_used = q;
 	if (W.small_mode && W.n > BT_SMALL_WORLD) { /* the brute-force pair search holds one world per block */
 		W.small_mode = 0;
@@ -1662,6 +1744,7 @@ extern "C" {
 int bt_raycast_build(bt_world *w) {
 	if (!w) return BT_ERR_ARG;
 	CK(cudaSetDevice(w->device));
+	{ int rr = fused_settle(w, false); if (rr) return rr; }
 	return ray_build(w);
 }
 
@@ -1669,6 +1752,7 @@ int bt_raycast_batch_device(bt_world *w, const int32_t *d_origin, const int32_t 
                             int32_t *d_winner) {
 	if (!w || n_rays < 0) return BT_ERR_ARG;
 	CK(cudaSetDevice(w->device));
+	{ int rr = fused_settle(w, false); if (rr) return rr; }
 	if (!w->ray_valid) {
 		int r = ray_build(w);
 		if (r) return r;
