@@ -56,15 +56,30 @@ class BtProfile(C.Structure):
 
 
 def build(force=False, verbose=False):
-    """Compile the CUDA library for sm_100a with nvcc (cross-compiles without a GPU)."""
-    srcs = [os.path.join(CSRC, "bt_world.cu"), os.path.join(CSRC, "bt_synth.cpp")]
-    deps = srcs + [os.path.join(CSRC, f) for f in ("bt_kernels.cuh", "bt_phys.cuh", "bt_raycast.cuh", "bt_types.h")]
-    deps.append(os.path.join(INCLUDE, "bittoss_b200.h"))
-    if not force and os.path.exists(LIB_SO) and all(os.path.getmtime(LIB_SO) >= os.path.getmtime(d) for d in deps):
-        return LIB_SO
+    """Compile the CUDA library for sm_100a with nvcc (cross-compiles without a GPU).  Two translation units, compiled
+    side by side: bt_world.cu (every kernel of the generic schedule + the host side of the C ABI) and bt_small.cu (the
+    one-block-per-world step, by far the longest compile); objects are kept in build/obj and reused while their sources
+    are older."""
+    hdrs = [os.path.join(CSRC, f) for f in ("bt_kernels.cuh", "bt_small.h", "bt_phys.cuh", "bt_raycast.cuh", "bt_types.h")]
+    hdrs.append(os.path.join(INCLUDE, "bittoss_b200.h"))
     extra = os.environ.get("BT_NVCC_EXTRA", "").split()
-    cmd = ["nvcc"] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_SO] + srcs
-    subprocess.check_call(cmd)
+    objdir = os.environ.get("BT_OBJ_DIR", os.path.join(os.path.dirname(CSRC), "..", "build", "obj"))
+    os.makedirs(objdir, exist_ok=True)
+    tag = ("_" + "_".join(extra).replace("/", "").replace("=", "")) if extra else ""
+    units = [(os.path.join(CSRC, n), os.path.join(objdir, n.rsplit(".", 1)[0] + tag + ".o"))
+             for n in ("bt_world.cu", "bt_small.cu", "bt_synth.cpp")]
+    compile_flags = [f for f in NVCC_FLAGS if f != "-shared"] + extra + (["-Xptxas", "-v"] if verbose else [])
+    procs = []
+    for src, obj in units:
+        deps = [src] + hdrs
+        if force or not os.path.exists(obj) or any(os.path.getmtime(obj) < os.path.getmtime(d) for d in deps):
+            procs.append((src, subprocess.Popen(["nvcc"] + compile_flags + ["-c", "-o", obj, src])))
+    failed = [src for src, p in procs if p.wait() != 0]
+    if failed:
+        raise subprocess.CalledProcessError(1, "nvcc -c " + " ".join(failed))
+    objs = [obj for _, obj in units]
+    if procs or not os.path.exists(LIB_SO) or any(os.path.getmtime(LIB_SO) < os.path.getmtime(o) for o in objs):
+        subprocess.check_call(["nvcc"] + NVCC_FLAGS + ["-o", LIB_SO] + objs)
     return LIB_SO
 
 

@@ -57,8 +57,6 @@ static __device__ __forceinline__ void stats_flush(const DevWorld &W, const Loca
 #define GS_FOR(i, n) for (i32 i = TID; i < (n); i += (i32)(gridDim.x * blockDim.x))
 #define GS_BLOCK 256
 
-__global__ void __launch_bounds__(BT_BLOCK) k_pre(DevWorld W, u32 phases) { PDL_ENTRY(); t_pre(W, TID, phases); }
-__global__ void __launch_bounds__(BT_BLOCK) k_flush_scan(DevWorld W) { PDL_ENTRY(); t_flush_scan(W, TID); }
 /* flush1's ordered part, one WARP per world.  t_flush_serial (the one-thread restatement the emulator
  * runs) walks the world's entities three times, newest first; almost every visit finds nothing.  Here
  * the 32 lanes look at 32 entities at once and only the hits are handled, one at a time, in the
@@ -134,6 +132,23 @@ static __device__ __forceinline__ void bt_flush_serial_warp(const DevWorld &W, c
 	}
 	st.rk_ordered = 0;
 }
+/* Block-level re-packing: every thread offers up to `per` items; survivors are appended to a
+ * shared-memory queue with one shared atomic per warp (ballot + popc), so that the expensive
+ * second step runs on full warps instead of on the 1-in-4 lanes that had work. */
+static __device__ __forceinline__ void queue_push(u32 *q, u32 *count, int pred, u32 item) {
+	u32 m = __ballot_sync(0xffffffffu, pred);
+	if (!m) return;
+	int lane = threadIdx.x & 31;
+	u32 base = 0;
+	if (lane == 0) base = atomicAdd(count, (u32)__popc(m));
+	base = __shfl_sync(0xffffffffu, base, 0);
+	if (pred) q[base + __popc(m & ((1u << lane) - 1))] = item;
+}
+
+#ifndef BT_KERNEL_HELPERS_ONLY /* bt_small.cu takes the helpers above and defines its own kernel */
+
+__global__ void __launch_bounds__(BT_BLOCK) k_pre(DevWorld W, u32 phases) { PDL_ENTRY(); t_pre(W, TID, phases); }
+__global__ void __launch_bounds__(BT_BLOCK) k_flush_scan(DevWorld W) { PDL_ENTRY(); t_flush_scan(W, TID); }
 __global__ void __launch_bounds__(BT_BLOCK) k_flush_serial(DevWorld W) { PDL_ENTRY();
 	LocalStats st = {0, 0, 0, 0, 0};
 	const i32 g = TID >> 5;
@@ -320,19 +335,6 @@ __global__ void __launch_bounds__(BT_SMALL_WORLD) k_pairs_small(DevWorld W) { PD
 		}
 	}
 	emit.finish();
-}
-
-/* Block-level re-packing: every thread offers up to `per` items; survivors are appended to a
- * shared-memory queue with one shared atomic per warp (ballot + popc), so that the expensive
- * second step runs on full warps instead of on the 1-in-4 lanes that had work. */
-static __device__ __forceinline__ void queue_push(u32 *q, u32 *count, int pred, u32 item) {
-	u32 m = __ballot_sync(0xffffffffu, pred);
-	if (!m) return;
-	int lane = threadIdx.x & 31;
-	u32 base = 0;
-	if (lane == 0) base = atomicAdd(count, (u32)__popc(m));
-	base = __shfl_sync(0xffffffffu, base, 0);
-	if (pred) q[base + __popc(m & ((1u << lane) - 1))] = item;
 }
 
 /* one thread per cached pair, grid-stride so the launch does not need the pair count.
@@ -609,5 +611,7 @@ __global__ void __launch_bounds__(SORT_THREADS) k_sort_scatter(const u64 *keys, 
 		__syncwarp();
 	}
 }
+
+#endif /* BT_KERNEL_HELPERS_ONLY */
 
 #endif

@@ -544,6 +544,7 @@ static BT_HD void bt_check_cover(const DevWorld &W, i32 e, const int4 &o, const 
 	i32 lo[3], hi[3];
 	bt_swept_box(o, c, r, lo, hi);
 	if (lo[0] < ib.lo.x || lo[1] < ib.lo.y || lo[2] < ib.lo.z || hi[0] > ib.hi.x || hi[1] > ib.hi.y || hi[2] > ib.hi.z) {
+		if (W.small_mode) { W.ctr[CT_CACHE_INVALID] = 1; return; } /* brute-force pair search: always a full build, no dirty list */
 		/* once per entity and epoch onto the list the next patch works from */
 		u32 stamp = W.ctr[CT_PATCH_EPOCH] + 1u;
 		if (bt_xchg32(&W.dirtyStamp[e], stamp) != stamp) W.dirtyList[bt_add32(&W.ctr[CT_DIRTY_N], 1u)] = e;
@@ -1500,10 +1501,11 @@ static BT_HD u32 bt_push_key(const DevWorld &W, i32 root) {
  * resolves too (a tie) both go to the serial lane.  ready[] of other roots is only ever
  * rewritten 2 -> 1 by their own thread here, and the test is "non-zero", so the concurrent
  * reads are safe. */
-static BT_HD void t_push(const DevWorld &W, i32 e, LocalStats &st) {
-	if (e >= W.n) return;
+/* 1: root e pushes now, in the parallel lane; 0: it is not ready, or it was handed to the serial lane */
+static BT_HD int bt_push_route(const DevWorld &W, i32 e) {
+	if (e >= W.n) return 0;
 	u8 rd = W.ready[e];
-	if (!rd) return;
+	if (!rd) return 0;
 	Coll pc = bt_unpack_coll(W.pend[e]);
 	/* push handlers that edit somebody else's tree (player_push: pickup into the player's
 	 * holdee list, first come first served) run in the serial lane, canonical order */
@@ -1513,7 +1515,7 @@ static BT_HD void t_push(const DevWorld &W, i32 e, LocalStats &st) {
 		u32 slot = bt_add32(&W.ctr[CT_SERIAL_N], 1u);
 		if ((i32)slot < W.serial_cap) W.serialList[slot] = e;
 		else W.ctr[CT_ERROR] = (u32)(-BT_ERR_OVERFLOW);
-		return;
+		return 0;
 	}
 	if (rd == 2) {
 		i32 r = W.holdRoot[bt_unpack_coll(W.pend[e]).buddy];
@@ -1526,15 +1528,22 @@ static BT_HD void t_push(const DevWorld &W, i32 e, LocalStats &st) {
 			u32 slot = bt_add32(&W.ctr[CT_SERIAL_N], 1u);
 			if ((i32)slot < W.serial_cap) W.serialList[slot] = e;
 			else W.ctr[CT_ERROR] = (u32)(-BT_ERR_OVERFLOW);
-			return;
+			return 0;
 		}
 	}
+	return 1;
+}
+/* the push of ready root e (either lane) */
+static BT_HD void bt_push_root(const DevWorld &W, i32 e, LocalStats &st) {
 	st.rk_ordered = 0; st.rk_local = 0; st.rk_base = bt_push_rootkey(W, e);
 	bt_push(W, bt_unpack_coll(W.pend[e]), bt_push_key(W, e), st);
 }
+static BT_HD void t_push(const DevWorld &W, i32 e, LocalStats &st) {
+	if (bt_push_route(W, e)) bt_push_root(W, e, st);
+}
 
 /* serial lane: one thread, descending root index (DESIGN.md "Canonical order" B3) */
-static BT_HD void t_push_serial(const DevWorld &W, LocalStats &st) {
+static BT_HD i32 bt_serial_sort(const DevWorld &W) {
 	i32 n = (i32)W.ctr[CT_SERIAL_N];
 	if (n > W.serial_cap) n = W.serial_cap;
 	for (i32 i = 1; i < n; i++) { /* insertion sort, descending */
@@ -1543,11 +1552,11 @@ static BT_HD void t_push_serial(const DevWorld &W, LocalStats &st) {
 		while (j >= 0 && W.serialList[j] < v) { W.serialList[j + 1] = W.serialList[j]; j--; }
 		W.serialList[j + 1] = v;
 	}
-	for (i32 i = 0; i < n; i++) {
-		i32 e = W.serialList[i];
-		st.rk_ordered = 0; st.rk_local = 0; st.rk_base = bt_push_rootkey(W, e);
-		bt_push(W, bt_unpack_coll(W.pend[e]), bt_push_key(W, e), st);
-	}
+	return n;
+}
+static BT_HD void t_push_serial(const DevWorld &W, LocalStats &st) {
+	const i32 n = bt_serial_sort(W);
+	for (i32 i = 0; i < n; i++) bt_push_root(W, W.serialList[i], st);
 	W.ctr[CT_SERIAL_N] = 0;
 }
 

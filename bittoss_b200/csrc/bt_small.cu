@@ -1,0 +1,268 @@
+/*
+ * bt_small.cu — whole steps of SMALL worlds in one launch: one thread block per world.
+ *
+ * The batched case (BASELINE.json configs[3]: 8192 x arena.sav, <= 128 entities each) spends the generic schedule's
+ * tick in ~40 launches over all worlds plus one host round trip per resolution batch, although nothing ever crosses
+ * a world boundary.  Here block g runs doWholeStep (main.cpp:1019-1097) for world g from the first flush to
+ * clearDeads with __syncthreads() where the generic schedule has a kernel boundary:
+ *
+ *   thread i          = entity wbegin[g] + i (the per-thread bodies of bt_phys.cuh, unchanged)
+ *   loop control      = the CT_* words in SHARED memory (W.ctr is pointed at them), one set per world: the
+ *                       iteration count, cache invalidation, serial lane and error state of a world are its own
+ *   candidate pairs   = all pairs of the world's inflated boxes, from shared memory, rebuilt when the tick begins and
+ *                       whenever a push leaves its box (bt_check_cover); the list lives in shared memory too
+ *   serial lane, dead list, events, pending-wire pool = shared-memory lists; deaths and events are appended to the
+ *                       world-wide lists (one atomic per block that has any) when the step ends
+ *
+ * Results are those of the generic schedule bit for bit (the proposals are CAS-maxima, pushes of one iteration own
+ * their trees, the serial lane runs in canonical order: none of it depends on which worlds share a launch).
+ * The host sees none of it until it asks (fused_settle in bt_world.cu).
+ *
+ * Its own translation unit: every per-thread body is inlined into this one kernel (W is edited in registers, so
+ * nothing may take its address), which makes it by far the longest compile of the library.
+ */
+#define BT_KERNEL_HELPERS_ONLY
+#include "bt_kernels.cuh"
+#include "bt_small.h"
+
+#define SW_PAIRS_PER_ENT 12 /* shared pair list: entries per thread; beyond it the narrow phase walks the box triangle itself */
+#define SW_EVENTS 64        /* host events (TEAMSELECT / LOADBLOCK pushes, crush handlers) one world can raise per step */
+
+template <int BS> __global__ void __launch_bounds__(BS) k_tick_small(DevWorld W, u32 phases) {
+	PDL_ENTRY();
+	__shared__ int4 blo[BS], bhi[BS];
+	__shared__ u64 spairs[SW_PAIRS_PER_ENT * BS];
+	__shared__ u64 sdead[BS];
+	__shared__ int4 sevents[SW_EVENTS];
+	__shared__ u32 sctr[CT_WORDS];
+	__shared__ i32 sserial[BS];
+	__shared__ i32 swq_next[2 * BS], swq_to[2 * BS];
+	__shared__ u32 sbase_[2];
+
+	const int g = (int)blockIdx.x;
+	const int i = (int)threadIdx.x;
+	/* the world-wide lists and counters, before W is pointed at this world's own */
+	u32 *const gctr = W.ctr;
+	u64 *const gdead = W.deadList;
+	int4 *const gevents = W.events;
+	const i32 gdead_cap = W.dead_cap, gevent_cap = W.event_cap;
+	for (int k = i; k < CT_WORDS; k += BS) sctr[k] = 0;
+	W.ctr = sctr;
+	W.pairs = spairs; W.pair_cap = SW_PAIRS_PER_ENT * BS;
+	W.serialList = sserial; W.serial_cap = BS;
+	W.deadList = sdead; W.dead_cap = BS;
+	W.events = sevents; W.event_cap = SW_EVENTS;
+	W.wq_next = swq_next; W.wq_to = swq_to; W.wq_cap = 2 * BS;
+	const i32 b0 = W.wbegin[g], cnt = W.wend[g] - b0;
+	const i32 e = b0 + i;
+	const bool mine = i < cnt; /* threads past the world's last slot only take part in the barriers */
+	const i32 rp0 = W.root_phase;
+	/* row i of the cyclic balanced triangle of k_pairs_small: j = i + 1 .. i + kmax (mod cnt) sees every unordered pair once */
+	const int kmax = (cnt - 1) / 2 + (((cnt & 1) == 0 && i < cnt / 2) ? 1 : 0);
+	LocalStats st = {0, 0, 0, 0, 0};
+	u32 n_serial = 0, iters = 0;
+	__syncthreads();
+
+	if ((phases & BT_PHASE_WORLD_RULES) && mine) t_world_rules(W, e);
+	if ((phases & BT_PHASE_CTRLS) && mine) t_pre(W, e, phases);
+	if (phases & BT_PHASE_TICKS) { /* doUpdates ent.cpp:826-832: handlers read what flushCtrls just published */
+		__syncthreads();
+		int rnd = 0;
+		if (mine && W.inList[e]) {
+			const u32 ht = W.htick[e];
+			rnd = (W.holder[e] >= 0 ? (ht >> 8) & 0xffu : ht & 0xffu) == TICK_RAND;
+			t_tick(W, e);
+		}
+		if (__syncthreads_or(rnd) && i == 0) t_tick_serial(W, g); /* gs->rand draws in list order */
+	}
+	__syncthreads();
+
+	/* stage 0: prepPhysics, then doPhysics up to invokeOnCrush; stage 1: the flush1 that ends doPhysics (one copy of
+	 * the flush code for both) */
+#pragma unroll 1
+	for (int stage = 0; stage < 2; stage++) {
+		if (phases & (stage ? BT_PHASE_PHYSICS : BT_PHASE_PREP)) {
+			/* flush1 ent.cpp:794-804: requests are looked for by every thread (t_flush_scan), the ordered part is one
+			 * warp (bt_flush_serial_warp), flushMisc one thread per entity */
+			W.flush_stage = stage; /* deaths flushed in stage 1 are past invokeOnCrush (ent.cpp:907-909) */
+			W.root_phase = stage ? rp0 + SW_PHASES - 1 : rp0;
+			if (mine) t_flush_scan(W, e);
+			__syncthreads();
+			if (i < 32) bt_flush_serial_warp(W, g, st);
+			__syncthreads();
+			if (mine) t_flush_misc(W, e);
+			__syncthreads();
+			if (i == 0) sctr[CT_WQ_N] = 0; /* every pending-wire list has been consumed */
+			W.flush_stage = 0;
+			__syncthreads();
+		}
+		if (stage || !(phases & BT_PHASE_PHYSICS)) continue;
+
+		const int gravity = (phases & BT_PHASE_GRAVITY) != 0;
+		/* ---- doGravity, flush2, integrate (ent.cpp:842-858) ---- */
+		if (!(phases & SWF_HOST_DELTAS) && !sctr[CT_ANY_DELTA]) {
+			if (mine) t_begin_fused(W, e, gravity, 0);
+		} else {
+			if (gravity && mine) t_gravity(W, e);
+			__syncthreads();
+			if (mine) t_flush2_apply(W, e);
+			__syncthreads();
+			if (mine) t_integrate(W, e);
+		}
+		__syncthreads();
+		if (i == 0) { sctr[CT_ANY_DELTA] = 0; sctr[CT_CACHE_INVALID] = 1; } /* candidate pairs are found afresh every tick */
+		__syncthreads();
+		/* ---- the resolution loop (ent.cpp:860-905) ---- */
+		W.iter_base = W.iter_id;
+		u32 np = 0;
+		int leaf = 0;
+		Box6 q;
+		q.lo = make_int4(INT32_MAX, INT32_MAX, INT32_MAX, 0); /* empty: touches nothing */
+		q.hi = make_int4(INT32_MIN, INT32_MIN, INT32_MIN, 0);
+#pragma unroll 1
+		while (1) {
+			W.iter_id++;
+			if (sctr[CT_CACHE_INVALID]) { /* block-uniform: last written before the barrier that ended the previous round */
+				leaf = mine && bt_is_leaf_ent(W, e);
+				q.lo = make_int4(INT32_MAX, INT32_MAX, INT32_MAX, 0);
+				q.hi = make_int4(INT32_MIN, INT32_MIN, INT32_MIN, 0);
+				if (leaf) {
+					q = bt_inflated_box(W, e);
+					W.ibox[e] = q;
+				}
+				blo[i] = q.lo; bhi[i] = q.hi;
+				if (i == 0) sctr[CT_PAIR_N] = 0;
+				__syncthreads();
+				if (i == 0) sctr[CT_CACHE_INVALID] = 0;
+				if (leaf) {
+					for (int k = 1; k <= kmax; k++) {
+						int j = i + k;
+						if (j >= cnt) j -= cnt;
+						Box6 o;
+						o.lo = blo[j]; o.hi = bhi[j];
+						if (bt_box_touch(q, o)) {
+							const u32 pos = atomicAdd(&sctr[CT_PAIR_N], 1u);
+							if (pos < (u32)(SW_PAIRS_PER_ENT * BS))
+								spairs[pos] = (u64)(u32)(b0 + (i < j ? i : j)) | ((u64)(u32)(b0 + (i < j ? j : i)) << 32);
+						}
+					}
+				}
+				__syncthreads();
+				np = sctr[CT_PAIR_N];
+			}
+			/* doIteration ent.cpp:437-462: the cached pairs, or -- more touching pairs than the list holds -- straight
+			 * from the boxes of the last build; one copy of the narrow phase either way */
+			u32 any = 0;
+			{
+				const bool listed = np <= (u32)(SW_PAIRS_PER_ENT * BS);
+				u32 p = (u32)i;
+				int k = 1;
+#pragma unroll 1
+				while (1) {
+					u64 pr;
+					if (listed) {
+						if (p >= np) break;
+						pr = spairs[p];
+						p += BS;
+					} else {
+						if (!leaf || k > kmax) break;
+						int j = i + k++;
+						if (j >= cnt) j -= cnt;
+						Box6 o;
+						o.lo = blo[j]; o.hi = bhi[j];
+						if (!bt_box_touch(q, o)) continue;
+						pr = (u64)(u32)(b0 + (i < j ? i : j)) | ((u64)(u32)(b0 + (i < j ? j : i)) << 32);
+					}
+					t_narrow(W, pr, st, any);
+				}
+			}
+			any = (u32)__syncthreads_or((int)any);
+			if (mine) t_decide(W, e); /* clears needsCollision also in the round that proposes nothing (ent.cpp:459) */
+			if (!any) break;          /* doIteration returned 0 (ent.cpp:866) */
+			if (iters >= (u32)(SW_PHASES - 2)) { /* out of root-order phases for this launch */
+				if (i == 0) sctr[CT_ERROR] = (u32)(-BT_ERR_OVERFLOW);
+				break;
+			}
+			iters++;
+			W.root_phase = rp0 + (i32)iters; /* both push lanes of one iteration share it */
+			__syncthreads();
+			/* push loop ent.cpp:879-882, both lanes through ONE copy of the push code: round 0 = every ready root by its own
+			 * thread (roots whose handlers edit other trees, and tied cycles, queue up instead: bt_push_route), round 1 =
+			 * the queue, canonical order, thread 0 */
+			const int now = mine && bt_push_route(W, e);
+#pragma unroll 1
+			for (int round = 0; round < 2; round++) {
+				i32 n = now;
+				if (round) {
+					__syncthreads();
+					n = i == 0 && sctr[CT_SERIAL_N] ? bt_serial_sort(W) : 0;
+					if (n) { n_serial += (u32)n; sctr[CT_SERIAL_N] = 0; }
+				}
+#pragma unroll 1
+				for (i32 k = 0; k < n; k++) bt_push_root(W, round ? sserial[k] : e, st);
+			}
+			__syncthreads();
+			if (mine) t_post(W, e);
+			__syncthreads();
+			if (sctr[CT_ERROR]) break; /* block-uniform */
+		}
+		__syncthreads();
+		/* invokeOnCrush (ent.cpp:907): crush handlers are host events */
+	}
+	if (phases & BT_PHASE_PHYSICS) {
+		/* flush2 (ent.cpp:910): a pickup with HOLD_FREEZE left a d_vel behind (ent.cpp:176-181) */
+		if (sctr[CT_ANY_DELTA]) {
+			if (mine) t_flush2_apply(W, e);
+			__syncthreads();
+			if (mine) t_zero_deltas(W, e);
+		}
+	} else if ((phases & BT_PHASE_GRAVITY) && mine) {
+		t_gravity(W, e);
+	}
+	__syncthreads();
+
+	/* ---- what the rest of the library has to see ---- */
+	u32 live = 0;
+	if (phases & BT_PHASE_FINISH) live = (u32)__syncthreads_count(mine && W.inList[e]); /* clearDeads ent.cpp:471-481 */
+	if (i == 0) {
+		u32 nd = sctr[CT_DEAD_N], ne = sctr[CT_EVENT_N];
+		if (ne > (u32)SW_EVENTS) { sctr[CT_ERROR] = (u32)(-BT_ERR_OVERFLOW); ne = SW_EVENTS; }
+		sbase_[0] = nd ? atomicAdd(&gctr[CT_DEAD_N], nd) : 0u;
+		sbase_[1] = ne ? atomicAdd(&gctr[CT_EVENT_N], ne) : 0u;
+		if (sctr[CT_ERROR]) gctr[CT_ERROR] = sctr[CT_ERROR];
+		if (sctr[CT_UNSUPPORTED]) { atomicAdd(&gctr[CT_UNSUPPORTED], sctr[CT_UNSUPPORTED]); gctr[CT_UNSUP_LAST] = sctr[CT_UNSUP_LAST]; }
+		if (sctr[CT_ORDER_TIES]) atomicAdd(&gctr[CT_ORDER_TIES], sctr[CT_ORDER_TIES]);
+		if (sctr[CT_TREE_EDITS]) atomicAdd(&gctr[CT_TREE_EDITS], sctr[CT_TREE_EDITS]);
+		if (sctr[CT_NEED_REBUILD]) gctr[CT_NEED_REBUILD] = 1;
+		u64 *s = (u64 *)&gctr[CT_STAT0];
+		if (iters) atomicAdd(&s[SK_ITERS], (u64)iters);
+		if (live) atomicAdd(&s[SK_ETICKS], (u64)live);
+		if (n_serial) atomicAdd(&s[SK_SERIAL], (u64)n_serial);
+	}
+	__syncthreads();
+	{
+		const u32 nd = min(sctr[CT_DEAD_N], (u32)BS), ne = min(sctr[CT_EVENT_N], (u32)SW_EVENTS);
+		for (u32 k = (u32)i; k < nd; k += BS)
+			if (sbase_[0] + k < (u32)gdead_cap) gdead[sbase_[0] + k] = sdead[k];
+		for (u32 k = (u32)i; k < ne; k += BS) /* in the order the serial lane raised them */
+			if (sbase_[1] + k < (u32)gevent_cap) gevents[sbase_[1] + k] = sevents[k];
+	}
+	W.ctr = gctr;
+	stats_flush(W, st);
+}
+
+cudaError_t bt_launch_tick_small(const DevWorld &W, unsigned phases, int biggest_world, bool pdl, cudaStream_t stream) {
+	if (W.n_worlds <= 0) return cudaSuccess;
+	const int bs = biggest_world <= 64 ? 64 : BT_SMALL_WORLD;
+	cudaLaunchConfig_t cfg = {};
+	cfg.gridDim = dim3((unsigned)W.n_worlds);
+	cfg.blockDim = dim3((unsigned)bs);
+	cfg.stream = stream;
+	cudaLaunchAttribute at[1];
+	at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+	at[0].val.programmaticStreamSerializationAllowed = 1;
+	cfg.attrs = at;
+	cfg.numAttrs = pdl ? 1 : 0;
+	return bs == 64 ? cudaLaunchKernelEx(&cfg, k_tick_small<64>, W, (u32)phases)
+	                : cudaLaunchKernelEx(&cfg, k_tick_small<BT_SMALL_WORLD>, W, (u32)phases);
+}

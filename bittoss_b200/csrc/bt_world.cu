@@ -22,6 +22,7 @@
 #include <algorithm>
 
 #include "bt_kernels.cuh"
+#include "bt_small.h"
 #include "bt_raycast.cuh"
 
 static thread_local char g_err[512] = "";
@@ -100,7 +101,6 @@ struct bt_world {
 	i64 run_ahead;       /* option: 1 = enqueue the predicted iterations without waiting for the host */
 	bt_tick_stats stats;
 	bool profiling;
-	bool profiling_generic; /* unused knob kept false: per-kernel profiles of small worlds use option fused_small = 0 */
 	cudaEvent_t ev0, ev1;
 	i64 prof_launches[PK_NUM];
 	double prof_ms[PK_NUM];
@@ -125,6 +125,8 @@ struct bt_world {
 	i64 fused_small;            /* option "fused_small": whole ticks of small worlds in one block per world (k_tick_small) */
 	i32 small_biggest;          /* slots of the largest world of the last upload */
 	bool fused_dirty;           /* fused ticks ran since the host last looked: counters, live count, cached pairs are stale */
+	bool wq_host_pending;       /* the host queued uWire / uUnwire requests in the world-wide pending-wire pool (bt_world_poke): the
+	                             * next flush1 must be the generic one, k_tick_small keeps a pool per world in shared memory */
 	DevArrays arrays;
 };
 template <typename T> static int dalloc(bt_world *w, T **p, size_t count) {
@@ -266,10 +268,10 @@ int bt_world_create(bt_world **out, int device, int32_t max_ents, int32_t max_sl
 	w->device = device;
 	w->cap_ents = max_ents; w->cap_sliders = max_sliders; w->cap_wires = max_wires; w->cap_worlds = max_worlds;
 	w->tree_valid = false; w->deltas_pending = true; w->ticks_since_build = 0; w->full_flush_left = 2; w->scan_flushes_left = 2; w->ctrls_fused = false;
-	w->rebuild_every = 16; w->max_iterations = 100000; w->pair_cache = 1; w->pair_rebuilds = 0; w->pair_overflows = 0; w->seen_pair_builds = 0; w->seen_pair_patches = 0; w->pair_builds_at_tree = 0; w->profiling = false; w->profiling_generic = false; w->ray_valid = false; w->uid_map_valid = false; w->ctr_fresh = false; w->margin_opt = -1; w->narrow_blocks = 148 * 8; w->narrow_threads = 256; w->pdl_opt = getenv("BT_NO_PDL") ? 0 : -1; w->pdl = false; w->pdl_long = false; /* decided at upload, together with W.pdl */ w->small_worlds = true; w->d_reqs = NULL; w->d_req_starts = NULL; w->reqs_cap = 0; w->any_ticks = w->any_rand = false; w->bad_tick = 0; w->device_ticks = 1;
+	w->rebuild_every = 16; w->max_iterations = 100000; w->pair_cache = 1; w->pair_rebuilds = 0; w->pair_overflows = 0; w->seen_pair_builds = 0; w->seen_pair_patches = 0; w->pair_builds_at_tree = 0; w->profiling = false; w->ray_valid = false; w->uid_map_valid = false; w->ctr_fresh = false; w->margin_opt = -1; w->narrow_blocks = 148 * 8; w->narrow_threads = 256; w->pdl_opt = getenv("BT_NO_PDL") ? 0 : -1; w->pdl = false; w->pdl_long = false; /* decided at upload, together with W.pdl */ w->small_worlds = true; w->d_reqs = NULL; w->d_req_starts = NULL; w->reqs_cap = 0; w->any_ticks = w->any_rand = false; w->bad_tick = 0; w->device_ticks = 1;
 	w->h_flag = NULL; w->ev0 = w->ev1 = NULL; w->stream = NULL;
 	w->root_phase_ctr = 0; w->sliders_used = 0; w->wires_used = 0; w->d_pokes = NULL; w->pokes_cap = 0; w->poked = false;
-	w->launch_err = cudaSuccess; w->fused_small = 1; w->fused_dirty = false;
+	w->launch_err = cudaSuccess; w->fused_small = 1; w->fused_dirty = false; w->wq_host_pending = false; w->small_biggest = 0;
 	w->d_raykeys = w->d_raykeys_alt = NULL; w->d_rayidx = w->d_rayidx_alt = NULL; w->d_rayhist = NULL; w->rays_cap = 0; w->sort_rays = 0;
 	*out = w;
 #define TRY(x) do { int _r = (x); if (_r) { bt_world_destroy(w); *out = NULL; return _r; } } while (0)
@@ -683,6 +685,7 @@ static int flush1(bt_world *w, bool hint) {
 	LAUNCH(w, PK_FLUSH, k_flush_serial, nblk((i64)W.n_worlds * 32), BT_BLOCK, W); /* one warp per world */
 	LAUNCH(w, PK_FLUSH, k_flush_misc, nblk(W.n), BT_BLOCK, W);
 	CK(cudaMemsetAsync(&W.ctr[CT_WQ_N], 0, sizeof(u32), w->stream)); /* every pending-wire list has been consumed */
+	w->wq_host_pending = false;
 	return 0;
 }
 
@@ -912,10 +915,23 @@ static int step_small_fused(bt_world *w, uint32_t phases) {
 	if (w->root_phase_ctr > (1 << 27) - 2 * SW_PHASES) { snprintf(g_err, sizeof g_err, "root-order phases exhausted: download and upload the world again"); return BT_ERR_OVERFLOW; }
 	W.root_phase = w->root_phase_ctr + 1;
 	w->root_phase_ctr += SW_PHASES;
-	if (w->small_biggest <= 64) LAUNCH(w, PK_FUSED, k_tick_small<64>, W.n_worlds, 64, W, phases);
-	else LAUNCH(w, PK_FUSED, k_tick_small<BT_SMALL_WORLD>, W.n_worlds, BT_SMALL_WORLD, W, phases);
+	const u32 kp = phases | (w->deltas_pending ? SWF_HOST_DELTAS : 0u);
+	if (W.n_worlds > 0) { /* LAUNCH() for a kernel that lives in another translation unit (bt_small.cu) */
+		if (w->profiling) cudaEventRecord(w->ev0, w->stream);
+		cudaError_t le = bt_launch_tick_small(W, kp, w->small_biggest, w->pdl, w->stream);
+		if (le != cudaSuccess) note_launch_error(w, le, "k_tick_small", __LINE__);
+		w->stats.kernel_launches++;
+		w->prof_launches[PK_FUSED]++;
+		if (w->profiling) {
+			cudaEventRecord(w->ev1, w->stream);
+			cudaEventSynchronize(w->ev1);
+			float ms = 0;
+			cudaEventElapsedTime(&ms, w->ev0, w->ev1);
+			w->prof_ms[PK_FUSED] += ms;
+		}
+	}
 	w->fused_dirty = true;
-	w->ctr_fresh = false; w->ray_valid = false; w->uid_map_valid = w->uid_map_valid;
+	w->ctr_fresh = false; w->ray_valid = false;
 	if (phases & BT_PHASE_PHYSICS) { w->deltas_pending = false; w->stats.ticks++; }
 	else if (phases & BT_PHASE_GRAVITY) w->deltas_pending = true;
 	if (phases & BT_PHASE_PREP) { w->full_flush_left = 0; w->scan_flushes_left = 0; }
@@ -931,8 +947,10 @@ int bt_world_step(bt_world *w, uint32_t phases) {
 	DevWorld &W = w->W;
 	const i32 n = W.n;
 	/* small worlds: the whole step in one launch, one block per world, nothing comes back to the host */
-	if (W.small_mode && w->fused_small && w->pair_cache && !w->profiling_generic &&
-	    !(phases & ~(BT_PHASE_ALL | BT_PHASE_WORLD_RULES | BT_PHASE_TICKS)))
+	/* (doPhysics and clearDeads together or not at all: the dead of a fused tick are counted off when the host settles) */
+	if (W.small_mode && w->fused_small && w->pair_cache && !w->wq_host_pending &&
+	    !(phases & ~(BT_PHASE_ALL | BT_PHASE_WORLD_RULES | BT_PHASE_TICKS)) &&
+	    !(phases & BT_PHASE_PHYSICS) == !(phases & BT_PHASE_FINISH))
 		return step_small_fused(w, phases);
 	{ int rr = fused_settle(w, true); if (rr) return rr; }
 	if (phases & BT_PHASE_WORLD_RULES) {
@@ -1313,7 +1331,7 @@ int bt_world_assign(bt_world *dst, bt_world *src) {
 	rebase(&dst->ray, sizeof(dst->ray), src, dst);
 	dst->arrays = src->arrays;
 	rebase(&dst->arrays, sizeof(dst->arrays), src, dst);
-	dst->fused_small = src->fused_small; dst->fused_dirty = src->fused_dirty; dst->small_biggest = src->small_biggest;
+	dst->fused_small = src->fused_small; dst->fused_dirty = src->fused_dirty; dst->small_biggest = src->small_biggest; dst->wq_host_pending = src->wq_host_pending;
 	dst->root_phase_ctr = src->root_phase_ctr; dst->sliders_used = src->sliders_used; dst->wires_used = src->wires_used; dst->poked = src->poked;
 	dst->tree_valid = src->tree_valid; dst->deltas_pending = src->deltas_pending; dst->any_rules = src->any_rules;
 	dst->full_flush_left = src->full_flush_left; dst->scan_flushes_left = src->scan_flushes_left; dst->ctrls_fused = src->ctrls_fused;
@@ -1366,6 +1384,7 @@ int bt_world_profile_read(bt_world *w, bt_profile *out, int reset) {
 int bt_world_count(bt_world *w, int32_t *n_ents, int32_t *n_sliders, int32_t *n_wires) {
 	if (!w) return BT_ERR_ARG;
 	CK(cudaSetDevice(w->device));
+	CK(cudaStreamSynchronize(w->stream)); /* the copies below do not run on the world's (non-blocking) stream */
 	const int n = w->W.n;
 	std::vector<u8> inList(n);
 	std::vector<i32> so(n + 1), wc(n);
@@ -1627,6 +1646,7 @@ int bt_world_poke(bt_world *w, const bt_poke *pokes, int32_t n) {
 			if (p.index < 0 || p.index >= W.n || (p.array != BT_OP_SPAWN && (p.v[0] < 0 || p.v[0] >= W.n))) { snprintf(g_err, sizeof g_err, "poke %d: slot out of range", i); return BT_ERR_ARG; }
 			ops.push_back(p);
 			if (p.array == BT_OP_SPAWN) leafset = true;
+			else w->wq_host_pending = true;
 		} else { snprintf(g_err, sizeof g_err, "poke %d: unknown array / operation %d", i, p.array); return BT_ERR_ARG; }
 	}
 	const i32 total = (i32)(raw.size() + ops.size());
