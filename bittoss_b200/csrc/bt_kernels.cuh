@@ -21,10 +21,14 @@ static __device__ __forceinline__ u32 warp_sum(u32 v) {
 	return __reduce_add_sync(0xffffffffu, v);
 }
 
-/* add a per-thread count into a 64-bit stat with one atomic per warp */
+/* add a per-thread count into a 64-bit stat with one atomic per warp, into this block's row (bt_types.h: BT_STAT_ROWS) */
 static __device__ __forceinline__ void stat_add(const DevWorld &W, int which, u32 v) {
 	u32 s = warp_sum(v);
-	if ((threadIdx.x & 31) == 0 && s) atomicAdd(((u64 *)&W.ctr[CT_STAT0]) + which, (u64)s);
+	if ((threadIdx.x & 31) == 0 && s) atomicAdd(&W.stat[(blockIdx.x & (BT_STAT_ROWS - 1)) * SK_NUM + which], (u64)s);
+}
+/* "this iteration proposed something": one store per block, not one per warp (they all hit the same word) */
+static __device__ __forceinline__ void stamp_any(const DevWorld &W, u32 any, int slot) {
+	if (__syncthreads_or((int)any) && threadIdx.x == 0) W.ctr[slot] = (u32)W.iter_id;
 }
 static __device__ __forceinline__ void stats_flush(const DevWorld &W, const LocalStats &st) {
 	stat_add(W, SK_CAND, st.cand);
@@ -236,7 +240,7 @@ __global__ void __launch_bounds__(BT_BLOCK) k_collide(DevWorld W) { PDL_ENTRY();
 	u32 any = 0;
 	t_collide(W, TID, stacks + threadIdx.x, BT_BLOCK, st, any);
 	stats_flush(W, st);
-	if (__any_sync(0xffffffffu, any) && (threadIdx.x & 31) == 0) W.ctr[ANY_SLOT(W.iter_id)] = (u32)W.iter_id;
+	stamp_any(W, any, ANY_SLOT(W.iter_id));
 }
 /* Pair emitter: hits are buffered per thread and written with ONE atomic per warp flush
  * (warp-ballot/shuffle compaction) instead of one atomic per pair. */
@@ -380,7 +384,7 @@ __global__ void __launch_bounds__(256, BT_NARROW_MINBLOCKS) k_narrow(DevWorld W,
 	if (spec & 2) { /* first iteration of the tick: everybody scans, no flag gathers (see t_narrow_t) */
 		for (; p < np; p += stride) t_narrow_t<1>(W, W.pairs[p], st, any);
 		stats_flush(W, st);
-		if (__any_sync(0xffffffffu, any) && (threadIdx.x & 31) == 0) W.ctr[ANY_SLOT(W.iter_id)] = (u32)W.iter_id;
+		stamp_any(W, any, ANY_SLOT(W.iter_id));
 		return;
 	}
 #endif
@@ -412,7 +416,7 @@ __global__ void __launch_bounds__(256, BT_NARROW_MINBLOCKS) k_narrow(DevWorld W,
 #endif
 	for (; p < np; p += stride) t_narrow(W, W.pairs[p], st, any);
 	stats_flush(W, st);
-	if (__any_sync(0xffffffffu, any) && (threadIdx.x & 31) == 0) W.ctr[ANY_SLOT(W.iter_id)] = (u32)W.iter_id;
+	stamp_any(W, any, ANY_SLOT(W.iter_id));
 }
 
 /* The resolve kernels of an iteration are enqueued right behind its narrow phase, before the
@@ -442,8 +446,8 @@ __global__ void k_push_serial(DevWorld W) { PDL_ENTRY(); PDL_WAIT(); /* launched
 	if (W.ctr[CT_SERIAL_N] == 0 || W.ctr[CT_PAIR_OVERFLOW] || W.ctr[CT_STOP] || W.ctr[CT_ERROR]) return;
 	LocalStats st = {0, 0, 0, 0, 0};
 	t_push_serial(W, st);
-	u64 *s = (u64 *)&W.ctr[CT_STAT0];
-	s[SK_PUSH] += st.push; s[SK_SERIAL] += st.push; s[SK_CRUSH] += st.crush; s[SK_FUMBLE] += st.fumble;
+	u64 *s = W.stat; /* row 0, shared with other kernels' blocks */
+	atomicAdd(&s[SK_PUSH], (u64)st.push); atomicAdd(&s[SK_SERIAL], (u64)st.push); atomicAdd(&s[SK_CRUSH], (u64)st.crush); atomicAdd(&s[SK_FUMBLE], (u64)st.fumble);
 }
 __global__ void __launch_bounds__(BT_BLOCK) k_post(DevWorld W) { PDL_ENTRY();
 	if (W.ctr[CT_PAIR_OVERFLOW] | W.ctr[CT_STOP] | W.ctr[CT_ERROR]) return; /* a raised error (traversal stack, work list) stops the iteration: nobody acts on a partial candidate set */
@@ -502,6 +506,29 @@ __global__ void __launch_bounds__(BT_BLOCK) k_hash(DevWorld W, u64 *sum, u32 *cn
 	} else if (live) {
 		atomicAdd(&sum[g], h);
 		atomicAdd(&cnt[g], 1u);
+	}
+}
+
+/* the same sum for a device world that holds ONE world: per-thread partial sums over a grid-stride loop, then one pair of
+ * atomics per block (k_hash's one per warp all land on the same two words: 31 000 of them at 1 M entities) */
+__global__ void __launch_bounds__(GS_BLOCK) k_hash_one(DevWorld W, u64 *sum, u32 *cnt, int full) { PDL_ENTRY();
+	__shared__ u64 ph[GS_BLOCK / 32];
+	__shared__ u32 pc[GS_BLOCK / 32];
+	u64 h = 0;
+	u32 c = 0;
+	GS_FOR(e, W.n) {
+		if (!W.inList[e]) continue;
+		h += full ? bt_ent_hash_full(W, e) : bt_ent_hash(W, e);
+		c++;
+	}
+#pragma unroll
+	for (int off = 16; off > 0; off >>= 1) h += __shfl_down_sync(0xffffffffu, h, off);
+	c = warp_sum(c);
+	if ((threadIdx.x & 31) == 0) { ph[threadIdx.x >> 5] = h; pc[threadIdx.x >> 5] = c; }
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		for (int k = 1; k < GS_BLOCK / 32; k++) { h += ph[k]; c += pc[k]; }
+		if (c) { atomicAdd(&sum[0], h); atomicAdd(&cnt[0], c); }
 	}
 }
 

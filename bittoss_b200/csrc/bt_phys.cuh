@@ -547,7 +547,20 @@ static BT_HD void bt_check_cover(const DevWorld &W, i32 e, const int4 &o, const 
 		if (W.small_mode) { W.ctr[CT_CACHE_INVALID] = 1; return; } /* brute-force pair search: always a full build, no dirty list */
 		/* once per entity and epoch onto the list the next patch works from */
 		u32 stamp = W.ctr[CT_PATCH_EPOCH] + 1u;
-		if (bt_xchg32(&W.dirtyStamp[e], stamp) != stamp) W.dirtyList[bt_add32(&W.ctr[CT_DIRTY_N], 1u)] = e;
+		if (bt_xchg32(&W.dirtyStamp[e], stamp) != stamp) {
+#ifdef BT_EMU
+			W.dirtyList[bt_add32(&W.ctr[CT_DIRTY_N], 1u)] = e;
+#else
+			/* one atomic per warp for the lanes that are here together (a kicked world appends a quarter of its
+			 * entities in one integrate kernel, all to the same counter) */
+			const u32 m = __activemask();
+			const int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
+			u32 base = 0;
+			if (lane == leader) base = atomicAdd(&W.ctr[CT_DIRTY_N], (u32)__popc(m));
+			base = __shfl_sync(m, base, leader);
+			W.dirtyList[base + __popc(m & ((1u << lane) - 1))] = e;
+#endif
+		}
 		W.ctr[CT_CACHE_INVALID] = 1;
 	}
 }
@@ -1266,31 +1279,40 @@ template <class Emit> static BT_HD void t_pairs(const DevWorld &W, int t, i32 *s
 /* FIRST = the first doIteration of a tick: the integrate kernel has just set needsCollision on every entity that is
  * in gs->ents (ent.cpp:856), so the two byte gathers -- one dependent hop of the chain pair -> flags -> fields ->
  * proposal -- are skipped; entities without a box or out of the list fall to the inList / hasBox test below */
-template <int FIRST> static BT_HD void t_narrow_t(const DevWorld &W, u64 pr, LocalStats &st, u32 &any) {
-	i32 a = (i32)(u32)pr, b = (i32)(pr >> 32);
-	int na = FIRST ? 1 : W.needsCollision[a], nb = FIRST ? 1 : W.needsCollision[b];
-	if (!(na | nb)) return; /* the common case after the first iteration: two byte loads */
-	/* everything else in ONE batch of independent loads (no branch in between, or the compiler
-	 * must wait for each test before it may issue the next gather) */
-	int ia = W.inList[a], ba = W.hasBox[a], ib = W.inList[b], bb = W.hasBox[b];
-	u32 ta = W.type[a], ca = W.collide[a], tb = W.type[b], cb = W.collide[b];
-	i32 ra = W.holdRoot[a], rb = W.holdRoot[b];
-	u32 ha = W.hphys[a], hb = W.hphys[b];
-	EntGeo ga = bt_geo(W, a), gb = bt_geo(W, b);
-	if (!(ia & ba & ib & bb)) return; /* `o->dead` ent.cpp:455 */
-	if (!((tb & ca) | (ta & cb))) { st.cand += (u32)(na + nb); return; }
+/* both ends of one candidate pair in registers */
+struct NarrowEnd {
+	i32 e, root;
+	u32 type, collide, hphys;
+	int needs; /* it scans in this doIteration */
+	EntGeo g;
+};
+/* the narrow phase proper for a pair whose ends are live, boxed and loaded: one copy of checkCollision, run from each
+ * scanning end (ent.cpp:446-449) */
+static BT_HD void bt_narrow_eval(const DevWorld &W, NarrowEnd A, NarrowEnd B, LocalStats &st, u32 &any) {
+	if (!((B.type & A.collide) | (A.type & B.collide))) { st.cand += (u32)(A.needs + B.needs); return; }
 #pragma unroll 1
 	for (int k = 0; k < 2; k++) {
-		if (na) {
+		if (A.needs) {
 			st.cand++;
-			bt_check_loaded(W, a, ga, ta, ca, ra, ha, b, gb, tb, cb, rb, hb, nb, st, any);
+			bt_check_loaded(W, A.e, A.g, A.type, A.collide, A.root, A.hphys, B.e, B.g, B.type, B.collide, B.root, B.hphys, B.needs, st, any);
 		}
-		{ i32 t_ = a; a = b; b = t_; }
-		{ EntGeo t_ = ga; ga = gb; gb = t_; }
-		{ u32 t_ = ta; ta = tb; tb = t_; t_ = ca; ca = cb; cb = t_; t_ = ha; ha = hb; hb = t_; }
-		{ i32 t_ = ra; ra = rb; rb = t_; }
-		{ int t_ = na; na = nb; nb = t_; }
+		{ NarrowEnd t_ = A; A = B; B = t_; }
 	}
+}
+template <int FIRST> static BT_HD void t_narrow_t(const DevWorld &W, u64 pr, LocalStats &st, u32 &any) {
+	NarrowEnd A, B;
+	A.e = (i32)(u32)pr; B.e = (i32)(pr >> 32);
+	A.needs = FIRST ? 1 : W.needsCollision[A.e]; B.needs = FIRST ? 1 : W.needsCollision[B.e];
+	if (!(A.needs | B.needs)) return; /* the common case after the first iteration: two byte loads */
+	/* everything else in ONE batch of independent loads (no branch in between, or the compiler
+	 * must wait for each test before it may issue the next gather) */
+	int ia = W.inList[A.e], ba = W.hasBox[A.e], ib = W.inList[B.e], bb = W.hasBox[B.e];
+	A.type = W.type[A.e]; A.collide = W.collide[A.e]; B.type = W.type[B.e]; B.collide = W.collide[B.e];
+	A.root = W.holdRoot[A.e]; B.root = W.holdRoot[B.e];
+	A.hphys = W.hphys[A.e]; B.hphys = W.hphys[B.e];
+	A.g = bt_geo(W, A.e); B.g = bt_geo(W, B.e);
+	if (!(ia & ba & ib & bb)) return; /* `o->dead` ent.cpp:455 */
+	bt_narrow_eval(W, A, B, st, any);
 }
 
 static BT_HD void t_narrow(const DevWorld &W, u64 pr, LocalStats &st, u32 &any) { t_narrow_t<0>(W, pr, st, any); }

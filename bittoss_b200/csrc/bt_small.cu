@@ -234,7 +234,7 @@ template <int BS> __global__ void __launch_bounds__(BS) k_tick_small(DevWorld W,
 		if (sctr[CT_ORDER_TIES]) atomicAdd(&gctr[CT_ORDER_TIES], sctr[CT_ORDER_TIES]);
 		if (sctr[CT_TREE_EDITS]) atomicAdd(&gctr[CT_TREE_EDITS], sctr[CT_TREE_EDITS]);
 		if (sctr[CT_NEED_REBUILD]) gctr[CT_NEED_REBUILD] = 1;
-		u64 *s = (u64 *)&gctr[CT_STAT0];
+		u64 *s = W.stat + (blockIdx.x & (BT_STAT_ROWS - 1)) * SK_NUM;
 		if (iters) atomicAdd(&s[SK_ITERS], (u64)iters);
 		if (live) atomicAdd(&s[SK_ETICKS], (u64)live);
 		if (n_serial) atomicAdd(&s[SK_SERIAL], (u64)n_serial);
@@ -247,7 +247,6 @@ template <int BS> __global__ void __launch_bounds__(BS) k_tick_small(DevWorld W,
 		for (u32 k = (u32)i; k < ne; k += BS) /* in the order the serial lane raised them */
 			if (sbase_[1] + k < (u32)gevent_cap) gevents[sbase_[1] + k] = sevents[k];
 	}
-	W.ctr = gctr;
 	stats_flush(W, st);
 }
 

@@ -125,6 +125,7 @@ struct bt_world {
 	i64 fused_small;            /* option "fused_small": whole ticks of small worlds in one block per world (k_tick_small) */
 	i32 small_biggest;          /* slots of the largest world of the last upload */
 	bool fused_dirty;           /* fused ticks ran since the host last looked: counters, live count, cached pairs are stale */
+	u64 seen_eticks, seen_iters; /* SK_ETICKS / SK_ITERS already added to `stats` (the device sums keep running) */
 	bool wq_host_pending;       /* the host queued uWire / uUnwire requests in the world-wide pending-wire pool (bt_world_poke): the
 	                             * next flush1 must be the generic one, k_tick_small keeps a pool per world in shared memory */
 	DevArrays arrays;
@@ -150,12 +151,12 @@ template <typename T> static int dalloc(bt_world *w, T **p, size_t count) {
 
 /* every kernel goes through here; pdl: programmatic dependent launch (see PDL_ENTRY in bt_kernels.cuh) */
 template <typename... KArgs, typename... Args>
-static inline cudaError_t launch_k(bool pdl, void (*kern)(KArgs...), int grid, int block, cudaStream_t s, Args &&...args) {
-	if (!pdl) { kern<<<grid, block, 0, s>>>(KArgs(args)...); return cudaPeekAtLastError(); }
+static inline cudaError_t launch_k(bool pdl, void (*kern)(KArgs...), int grid, int block, size_t smem, cudaStream_t s, Args &&...args) {
+	if (!pdl) { kern<<<grid, block, smem, s>>>(KArgs(args)...); return cudaPeekAtLastError(); }
 	cudaLaunchConfig_t cfg = {};
 	cfg.gridDim = dim3((unsigned)grid);
 	cfg.blockDim = dim3((unsigned)block);
-	cfg.dynamicSmemBytes = 0;
+	cfg.dynamicSmemBytes = smem;
 	cfg.stream = s;
 	cudaLaunchAttribute at[1];
 	at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
@@ -172,11 +173,13 @@ static void note_launch_error(struct bt_world *w, cudaError_t e, const char *ker
 #define pdl_for(w, cls) (((cls) == PK_NARROW || (cls) == PK_PUSH) ? (w)->pdl_long : (w)->pdl)
 
 /* launch helper: counts launches and, while profiling, brackets each one with events */
-#define LAUNCH(w, cls, kern, grid, block, ...)                                         \
+#define LAUNCH(w, cls, kern, grid, block, ...) LAUNCH_S(w, cls, kern, grid, block, 0, __VA_ARGS__)
+/* ... with `smem` bytes of dynamic shared memory */
+#define LAUNCH_S(w, cls, kern, grid, block, smem, ...)                                 \
 	do {                                                                               \
 		if ((grid) > 0) {                                                              \
 			if ((w)->profiling) cudaEventRecord((w)->ev0, (w)->stream);                \
-			cudaError_t _le = launch_k(pdl_for((w), cls), kern, (grid), (block), (w)->stream, __VA_ARGS__); \
+			cudaError_t _le = launch_k(pdl_for((w), cls), kern, (grid), (block), (size_t)(smem), (w)->stream, __VA_ARGS__); \
 			if (_le != cudaSuccess) note_launch_error((w), _le, #kern, __LINE__);      \
 			(w)->stats.kernel_launches++;                                              \
 			(w)->prof_launches[cls]++;                                                 \
@@ -271,7 +274,7 @@ int bt_world_create(bt_world **out, int device, int32_t max_ents, int32_t max_sl
 	w->rebuild_every = 16; w->max_iterations = 100000; w->pair_cache = 1; w->pair_rebuilds = 0; w->pair_overflows = 0; w->seen_pair_builds = 0; w->seen_pair_patches = 0; w->pair_builds_at_tree = 0; w->profiling = false; w->ray_valid = false; w->uid_map_valid = false; w->ctr_fresh = false; w->margin_opt = -1; w->narrow_blocks = 148 * 8; w->narrow_threads = 256; w->pdl_opt = getenv("BT_NO_PDL") ? 0 : -1; w->pdl = false; w->pdl_long = false; /* decided at upload, together with W.pdl */ w->small_worlds = true; w->d_reqs = NULL; w->d_req_starts = NULL; w->reqs_cap = 0; w->any_ticks = w->any_rand = false; w->bad_tick = 0; w->device_ticks = 1;
 	w->h_flag = NULL; w->ev0 = w->ev1 = NULL; w->stream = NULL;
 	w->root_phase_ctr = 0; w->sliders_used = 0; w->wires_used = 0; w->d_pokes = NULL; w->pokes_cap = 0; w->poked = false;
-	w->launch_err = cudaSuccess; w->fused_small = 1; w->fused_dirty = false; w->wq_host_pending = false; w->small_biggest = 0;
+	w->launch_err = cudaSuccess; w->fused_small = 1; w->fused_dirty = false; w->seen_eticks = w->seen_iters = 0; w->wq_host_pending = false; w->small_biggest = 0;
 	w->d_raykeys = w->d_raykeys_alt = NULL; w->d_rayidx = w->d_rayidx_alt = NULL; w->d_rayhist = NULL; w->rays_cap = 0; w->sort_rays = 0;
 	*out = w;
 #define TRY(x) do { int _r = (x); if (_r) { bt_world_destroy(w); *out = NULL; return _r; } } while (0)
@@ -318,7 +321,7 @@ int bt_world_create(bt_world **out, int device, int32_t max_ents, int32_t max_sl
 	W.serial_cap = 1 << 16; W.dead_cap = max_ents > 0 ? max_ents : 1; W.event_cap = 1 << 16;
 	TRY(dalloc(w, &W.events, (size_t)W.event_cap));
 	TRY(dalloc(w, &W.serialList, (size_t)W.serial_cap)); TRY(dalloc(w, &W.deadList, (size_t)W.dead_cap));
-	TRY(dalloc(w, &W.hash, nw)); TRY(dalloc(w, &W.ctr, (size_t)CT_WORDS));
+	TRY(dalloc(w, &W.hash, nw)); TRY(dalloc(w, &W.ctr, (size_t)CT_WORDS)); TRY(dalloc(w, &W.stat, (size_t)BT_STAT_ROWS * SK_NUM));
 	TRY(dalloc(w, &w->d_hsum, nw)); TRY(dalloc(w, &w->d_hcnt, nw));
 	w->sorthist_len = 256 * (int)((n + SORT_TILE - 1) / SORT_TILE + 1);
 	TRY(dalloc(w, &w->d_sorthist, (size_t)w->sorthist_len));
@@ -561,6 +564,8 @@ int bt_world_upload(bt_world *w, const bt_world_desc *d) {
 	UP(W.wire_cnt, wire_cnt); UP(W.wireAdd, minus1); UP(W.wireRm, minus1);
 	w->sliders_used = d->n_sliders; w->root_phase_ctr = 0; w->poked = false; w->fused_dirty = false;
 	CK(cudaMemsetAsync(W.ctr, 0, sizeof(u32) * CT_WORDS, w->stream));
+	CK(cudaMemsetAsync(W.stat, 0, sizeof(u64) * BT_STAT_ROWS * SK_NUM, w->stream));
+	w->seen_eticks = w->seen_iters = 0;
 	{ int rr = raise_cache_invalid(w); if (rr) return rr; }
 	CK(cudaMemsetAsync(W.dirtyStamp, 0, sizeof(u32) * (size_t)w->cap_ents, w->stream));
 	w->seen_pair_builds = 0; w->seen_pair_patches = 0; w->pair_builds_at_tree = 0;
@@ -872,6 +877,17 @@ static int do_physics_end(bt_world *w) {
 
 } /* extern "C" */
 
+/* the statistics: BT_STAT_ROWS partial sums per counter (bt_types.h), added up here */
+static int read_stats(bt_world *w, u64 *s) {
+	std::vector<u64> rows((size_t)BT_STAT_ROWS * SK_NUM);
+	CK(cudaMemcpyAsync(rows.data(), w->W.stat, sizeof(u64) * rows.size(), cudaMemcpyDeviceToHost, w->stream));
+	CK(cudaStreamSynchronize(w->stream));
+	for (int k = 0; k < SK_NUM; k++) s[k] = 0;
+	for (int r = 0; r < BT_STAT_ROWS; r++)
+		for (int k = 0; k < SK_NUM; k++) s[k] += rows[(size_t)r * SK_NUM + k];
+	return 0;
+}
+
 /* After ticks of the one-block-per-world kernel the host has not looked at the device: the dead entities of those
  * ticks are still on the dead list, the live count and entity-ticks are in device counters, and the generic schedule's
  * cached pairs / flush hints know nothing of what happened.  Called before anything that needs them. */
@@ -880,11 +896,13 @@ static int fused_settle(bt_world *w, bool leaving) {
 	DevWorld &W = w->W;
 	int r = fetch_ctr(w);
 	if (r) return r;
-	const u64 *s = (const u64 *)&w->h_flag[CT_STAT0];
-	w->stats.entity_ticks += (i64)s[SK_ETICKS];
-	w->stats.iterations += (i64)((s[SK_ITERS] + (u64)W.n_worlds / 2) / (u64)(W.n_worlds ? W.n_worlds : 1)); /* mean over the worlds */
-	CK(cudaMemsetAsync(((u64 *)&W.ctr[CT_STAT0]) + SK_ETICKS, 0, sizeof(u64), w->stream));
-	CK(cudaMemsetAsync(((u64 *)&W.ctr[CT_STAT0]) + SK_ITERS, 0, sizeof(u64), w->stream));
+	u64 s[SK_NUM];
+	r = read_stats(w, s);
+	if (r) return r;
+	w->stats.entity_ticks += (i64)(s[SK_ETICKS] - w->seen_eticks);
+	const u64 di = s[SK_ITERS] - w->seen_iters;
+	w->stats.iterations += (i64)((di + (u64)W.n_worlds / 2) / (u64)(W.n_worlds ? W.n_worlds : 1)); /* mean over the worlds */
+	w->seen_eticks = s[SK_ETICKS]; w->seen_iters = s[SK_ITERS];
 	if (w->h_flag[CT_DEAD_N]) {
 		w->stats.live_ents -= (i64)w->h_flag[CT_DEAD_N];
 		w->ranks_valid = false;
@@ -1023,7 +1041,8 @@ static int hash_into(bt_world *w, uint64_t *out, int full = 0) {
 	DevWorld &W = w->W;
 	CK(cudaMemsetAsync(w->d_hsum, 0, sizeof(u64) * (size_t)W.n_worlds, w->stream));
 	CK(cudaMemsetAsync(w->d_hcnt, 0, sizeof(u32) * (size_t)W.n_worlds, w->stream));
-	LAUNCH(w, PK_HASH, k_hash, nblk(W.n), BT_BLOCK, W, w->d_hsum, w->d_hcnt, full);
+	if (W.n_worlds == 1) LAUNCH(w, PK_HASH, k_hash_one, gsblk(W.n), GS_BLOCK, W, w->d_hsum, w->d_hcnt, full); /* one atomic per block */
+	else LAUNCH(w, PK_HASH, k_hash, nblk(W.n), BT_BLOCK, W, w->d_hsum, w->d_hcnt, full);
 	std::vector<u64> s(W.n_worlds);
 	std::vector<u32> c(W.n_worlds);
 	CK(cudaMemcpyAsync(s.data(), w->d_hsum, sizeof(u64) * s.size(), cudaMemcpyDeviceToHost, w->stream));
@@ -1222,8 +1241,7 @@ int bt_world_stats(bt_world *w, bt_tick_stats *out, int reset) {
 	CK(cudaSetDevice(w->device));
 	{ int rr = fused_settle(w, false); if (rr) return rr; }
 	u64 s[SK_NUM];
-	CK(cudaMemcpyAsync(s, &w->W.ctr[CT_STAT0], sizeof(s), cudaMemcpyDeviceToHost, w->stream));
-	CK(cudaStreamSynchronize(w->stream));
+	{ int rr = read_stats(w, s); if (rr) return rr; }
 	w->stats.candidate_pairs = (i64)s[SK_CAND]; w->stats.positives = (i64)s[SK_POS];
 	w->stats.pushes = (i64)s[SK_PUSH]; w->stats.serial_pushes = (i64)s[SK_SERIAL];
 	w->stats.crushes = (i64)s[SK_CRUSH]; w->stats.fumbles = (i64)s[SK_FUMBLE];
@@ -1239,7 +1257,8 @@ int bt_world_stats(bt_world *w, bt_tick_stats *out, int reset) {
 		i64 live = w->stats.live_ents;
 		memset(&w->stats, 0, sizeof(w->stats));
 		w->stats.live_ents = live;
-		CK(cudaMemsetAsync(&w->W.ctr[CT_STAT0], 0, sizeof(s), w->stream));
+		CK(cudaMemsetAsync(w->W.stat, 0, sizeof(u64) * BT_STAT_ROWS * SK_NUM, w->stream));
+		w->seen_eticks = w->seen_iters = 0;
 		CK(cudaMemsetAsync(&w->W.ctr[CT_UNSUPPORTED], 0, sizeof(u32), w->stream));
 		CK(cudaMemsetAsync(w->W.wunsup, 0, sizeof(u32) * (size_t)w->cap_worlds, w->stream));
 		CK(cudaMemsetAsync(&w->W.ctr[CT_ORDER_TIES], 0, sizeof(u32), w->stream));
@@ -1331,7 +1350,7 @@ int bt_world_assign(bt_world *dst, bt_world *src) {
 	rebase(&dst->ray, sizeof(dst->ray), src, dst);
 	dst->arrays = src->arrays;
 	rebase(&dst->arrays, sizeof(dst->arrays), src, dst);
-	dst->fused_small = src->fused_small; dst->fused_dirty = src->fused_dirty; dst->small_biggest = src->small_biggest; dst->wq_host_pending = src->wq_host_pending;
+	dst->fused_small = src->fused_small; dst->fused_dirty = src->fused_dirty; dst->small_biggest = src->small_biggest; dst->wq_host_pending = src->wq_host_pending; dst->seen_eticks = src->seen_eticks; dst->seen_iters = src->seen_iters;
 	dst->root_phase_ctr = src->root_phase_ctr; dst->sliders_used = src->sliders_used; dst->wires_used = src->wires_used; dst->poked = src->poked;
 	dst->tree_valid = src->tree_valid; dst->deltas_pending = src->deltas_pending; dst->any_rules = src->any_rules;
 	dst->full_flush_left = src->full_flush_left; dst->scan_flushes_left = src->scan_flushes_left; dst->ctrls_fused = src->ctrls_fused;

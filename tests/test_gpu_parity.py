@@ -223,7 +223,7 @@ def test_cuda_schedule_variants_agree_at_scale(bt, oracle_lib):
     streams = []
     patches = []
     for run_ahead, cache, period, patch, pdl in ((1, 1, 16, 1, -1), (0, 1, 16, 1, 0), (1, 1, 3, 1, 1), (0, 0, 5, 1, 3),
-                                                 (1, 1, 16, 0, 1), (1, 1, 1000, 1, 0)):
+                                                 (1, 1, 16, 0, 1), (1, 1, 1000, 1, 0), (0, 1, 4, 1, 2)):
         w = bt.World(wa)
         w.set_option("pdl", pdl)   # dependent launches: auto / off / short kernels only / all kernels
         w.set_option("run_ahead", run_ahead)

@@ -13,6 +13,26 @@ opts = [kv.split("=") for kv in sys.argv[1:]]
 w = bittoss_b200.World(bittoss_b200.synth_boxstack(4096, 4, 1, 64, 60))
 w.tick(3)
 w.close()
+if os.environ.get("AB_DYNAMIC"):   # the broadphase regime: first 12 ticks of the push-all world, per-kernel profile of the same
+    wa = bittoss_b200.synth_boxstack(cubes, 4, 777, 1, 60)
+    w = bittoss_b200.World(wa)
+    for k, v in opts:
+        w.set_option(k, int(v))
+    ms = w.tick_timed(12) / 12
+    h = w.hash()[0]
+    w.close()
+    w = bittoss_b200.World(wa)
+    for k, v in opts:
+        w.set_option(k, int(v))
+    w.profile_enable(True)
+    w.profile(reset=True)
+    w.tick(12)
+    p = w.profile()
+    w.close()
+    per = " ".join("%s %.1f" % (k, 1e3 * t / 12) for k, (n, t) in sorted(p.items(), key=lambda kv: -kv[1][1]) if n and t / 12 > 0.004)
+    print("%-10s dynamic %.4f ms/tick  hash %016x | us/tick: %s" % (
+        os.path.basename(os.environ.get("BT_LIB_SO", "in-tree")).replace("libbt_", "").replace(".so", ""), ms, h, per), flush=True)
+    sys.exit(0)
 w = bittoss_b200.World(bittoss_b200.synth_boxstack(cubes, 4, 777, push_every, 60))
 for k, v in opts:
     w.set_option(k, int(v))
