@@ -338,6 +338,9 @@ def arena_record(bittoss_b200, args, device, rank, world_size):
                "unit": "world-ticks/s", "entity_ticks_per_sec": et / (ms_max * 1e-3), "n_gpus": world_size,
                "worlds": args.arena_worlds, "worlds_per_gpu": e - b, "entities_per_world": n1, "ticks": args.arena_ticks,
                "ms_per_tick": ms_max / args.arena_ticks, "iterations_per_tick": st["iterations"] / max(1, st["ticks"]),
+               "kernel_launches_per_tick": st["kernel_launches"] / max(1, st["ticks"]),
+               "schedule": "one launch per tick, one thread block per world (k_tick_small: loop control, candidate pairs and "
+                           "the serial lane of a world in shared memory)",
                "unsupported_events": st["unsupported_events"], "distinct_hashes": len(set(all_hashes)),
                "hash_gather": "all_gather of 8 B per world (NCCL)" if world_size > 1 else "single process"}
         if world_size > 1:
@@ -357,6 +360,17 @@ def arena_record(bittoss_b200, args, device, rank, world_size):
                 ok = ok and int(w1.hash()[0]) == int(all_hashes[g])
                 w1.close()
             rec["alone_equals_batched"] = {"worlds_checked": k, "equal": bool(ok)}
+        # the generic schedule (~30 launches per tick over all worlds, pair lists cached across ticks) on the first worlds
+        k = min(512, e - b)
+        part, _ = workloads.arena_batch(level, list(range(k)))
+        w1 = workloads.arena_world(part, device)
+        w1.set_option("fused_small", 0)
+        g_ms = w1.tick_timed(args.arena_ticks)
+        g_st = w1.stats()
+        rec["generic_schedule_check"] = {"worlds": k, "equal": bool([int(x) for x in w1.hash()] == [int(x) for x in all_hashes[:k]]),
+                                         "kernel_launches_per_tick": g_st["kernel_launches"] / max(1, g_st["ticks"]),
+                                         "ms_per_tick": g_ms / args.arena_ticks}
+        w1.close()
     return rec
 
 

@@ -56,28 +56,30 @@ class BtProfile(C.Structure):
 
 
 def build(force=False, verbose=False):
-    """Compile the CUDA library for sm_100a with nvcc (cross-compiles without a GPU).  Two translation units, compiled
-    side by side: bt_world.cu (every kernel of the generic schedule + the host side of the C ABI) and bt_small.cu (the
-    one-block-per-world step, by far the longest compile); objects are kept in build/obj and reused while their sources
-    are older."""
+    """Compile the CUDA library for sm_100a with nvcc (cross-compiles without a GPU).  Translation units compiled side by
+    side: bt_world.cu (every kernel of the generic schedule + the host side of the C ABI) and bt_small.cu (the
+    one-block-per-world step, by far the longest compile, in four variants); objects are kept in build/obj and reused
+    while their sources are older."""
     hdrs = [os.path.join(CSRC, f) for f in ("bt_kernels.cuh", "bt_small.h", "bt_phys.cuh", "bt_raycast.cuh", "bt_types.h")]
     hdrs.append(os.path.join(INCLUDE, "bittoss_b200.h"))
     extra = os.environ.get("BT_NVCC_EXTRA", "").split()
     objdir = os.environ.get("BT_OBJ_DIR", os.path.join(os.path.dirname(CSRC), "..", "build", "obj"))
     os.makedirs(objdir, exist_ok=True)
     tag = ("_" + "_".join(extra).replace("/", "").replace("=", "")) if extra else ""
-    units = [(os.path.join(CSRC, n), os.path.join(objdir, n.rsplit(".", 1)[0] + tag + ".o"))
-             for n in ("bt_world.cu", "bt_small.cu", "bt_synth.cpp")]
+    # (source, object, extra flags): bt_small.cu once per (block size, resident warps per SM) variant of its kernel
+    units = [(os.path.join(CSRC, n), os.path.join(objdir, n.rsplit(".", 1)[0] + tag + ".o"), []) for n in ("bt_world.cu", "bt_synth.cpp")]
+    units += [(os.path.join(CSRC, "bt_small.cu"), os.path.join(objdir, "bt_small_%d_%d%s.o" % (bs, mw, tag)),
+               ["-DSW_BS=%d" % bs, "-DSW_MIN_WARPS=%d" % mw]) for bs in (64, 128) for mw in (16, 32)]
     compile_flags = [f for f in NVCC_FLAGS if f != "-shared"] + extra + (["-Xptxas", "-v"] if verbose else [])
     procs = []
-    for src, obj in units:
+    for src, obj, flags in units:
         deps = [src] + hdrs
         if force or not os.path.exists(obj) or any(os.path.getmtime(obj) < os.path.getmtime(d) for d in deps):
-            procs.append((src, subprocess.Popen(["nvcc"] + compile_flags + ["-c", "-o", obj, src])))
+            procs.append((src, subprocess.Popen(["nvcc"] + compile_flags + flags + ["-c", "-o", obj, src])))
     failed = [src for src, p in procs if p.wait() != 0]
     if failed:
         raise subprocess.CalledProcessError(1, "nvcc -c " + " ".join(failed))
-    objs = [obj for _, obj in units]
+    objs = [obj for _, obj, _ in units]
     if procs or not os.path.exists(LIB_SO) or any(os.path.getmtime(LIB_SO) < os.path.getmtime(o) for o in objs):
         subprocess.check_call(["nvcc"] + NVCC_FLAGS + ["-o", LIB_SO] + objs)
     return LIB_SO

@@ -427,7 +427,10 @@ __global__ void __launch_bounds__(BT_BLOCK) k_decide(DevWorld W) { PDL_ENTRY();
 	if (W.ctr[CT_PAIR_OVERFLOW] | W.ctr[CT_STOP] | W.ctr[CT_ERROR]) return; /* a raised error (traversal stack, work list) stops the iteration: nobody acts on a partial candidate set */
 	GS_FOR(e, W.n) t_decide(W, e); /* 148 x 16 blocks, grid-stride: 53 blocks of 128 threads per SM cost more to schedule than to run */
 }
-/* ready roots (typically 1 entity in 4) are re-packed into full warps before the push */
+/* ready roots (typically 1 entity in 4) are re-packed into full warps before the push.  (Letting a block look at 256 /
+ * 512 / 1024 entities so that every one of its warps has roots to push -- at one entity per thread one warp in four
+ * does -- was measured: k_push 228 -> 232 / 237 / 229 us per tick at 1 M entities.  The kernel moves ~150 MB of 32-byte
+ * sectors per launch for ~50 MB it uses, 3.3 TB/s: more chains in flight do not help it.) */
 __global__ void __launch_bounds__(BT_BLOCK) k_push(DevWorld W) { PDL_WAIT();
 	__shared__ u32 queue[BT_BLOCK];
 	__shared__ u32 qn;

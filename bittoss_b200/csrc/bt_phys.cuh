@@ -1108,7 +1108,9 @@ static BT_HD int bt_touch_right(const NodeRegs &n, const i32 *qlo, const i32 *qh
 	       (n.c.x <= qhi[2]) & ((wr & 0xffff) <= w) & (w <= (wr >> 16));
 }
 
+#ifndef BT_STACK
 #define BT_STACK 32 /* deferred right children; observed <= 6 on the benchmark worlds; overflow raises BT_ERR_OVERFLOW */
+#endif
 
 /* doIteration ent.cpp:437-462 for the entity at sorted leaf position t.
  * `stack` is this thread's traversal stack (shared memory on the device). */

@@ -19,7 +19,13 @@
  * The host sees none of it until it asks (fused_settle in bt_world.cu).
  *
  * Its own translation unit: every per-thread body is inlined into this one kernel (W is edited in registers, so
- * nothing may take its address), which makes it by far the longest compile of the library.
+ * nothing may take its address), which makes it by far the longest compile of the library.  It is compiled four times,
+ * side by side (bittoss_b200/capi.py: build): block size SW_BS = 64 or 128 threads (the largest world of the upload)
+ * x SW_MIN_WARPS = 16 or 32 resident warps per SM the registers are held to.  Measured on 8192 / 1024 arena.sav worlds
+ * (64 entities, same box, ms per tick): 16 warps (128 registers) 0.266 / 0.078, 24 warps (80 registers, 216 B of
+ * spills) 0.250 / 0.083, 32 warps (64 registers, 368 B) 0.241 / 0.101, 40 warps (48 registers) 0.288 / 0.110: when
+ * there are enough worlds to fill the SMs the step is bound by latency and more warps pay for their spills, when
+ * there are not only the spills are left.  bt_launch_tick_small picks by the number of worlds.
  */
 #define BT_KERNEL_HELPERS_ONLY
 #include "bt_kernels.cuh"
@@ -28,7 +34,14 @@
 #define SW_PAIRS_PER_ENT 12 /* shared pair list: entries per thread; beyond it the narrow phase walks the box triangle itself */
 #define SW_EVENTS 64        /* host events (TEAMSELECT / LOADBLOCK pushes, crush handlers) one world can raise per step */
 
-template <int BS> __global__ void __launch_bounds__(BS) k_tick_small(DevWorld W, u32 phases) {
+#if !defined(SW_BS) || !defined(SW_MIN_WARPS)
+#error "compile with -DSW_BS=64|128 -DSW_MIN_WARPS=16|32 (bittoss_b200/capi.py: build)"
+#endif
+#define BS SW_BS
+#define SW_CAT3(a, b, c) a##b##_##c
+#define SW_NAME(prefix, bs, w) SW_CAT3(prefix, bs, w)
+#define k_tick_small SW_NAME(k_tick_small_, SW_BS, SW_MIN_WARPS)
+__global__ void __launch_bounds__(BS, SW_MIN_WARPS * 32 / BS) k_tick_small(DevWorld W, u32 phases) {
 	PDL_ENTRY();
 	__shared__ int4 blo[BS], bhi[BS];
 	__shared__ u64 spairs[SW_PAIRS_PER_ENT * BS];
@@ -250,18 +263,16 @@ template <int BS> __global__ void __launch_bounds__(BS) k_tick_small(DevWorld W,
 	stats_flush(W, st);
 }
 
-cudaError_t bt_launch_tick_small(const DevWorld &W, unsigned phases, int biggest_world, bool pdl, cudaStream_t stream) {
+cudaError_t SW_NAME(bt_launch_tick_small_, SW_BS, SW_MIN_WARPS)(const DevWorld &W, unsigned phases, bool pdl, cudaStream_t stream) {
 	if (W.n_worlds <= 0) return cudaSuccess;
-	const int bs = biggest_world <= 64 ? 64 : BT_SMALL_WORLD;
 	cudaLaunchConfig_t cfg = {};
 	cfg.gridDim = dim3((unsigned)W.n_worlds);
-	cfg.blockDim = dim3((unsigned)bs);
+	cfg.blockDim = dim3((unsigned)BS);
 	cfg.stream = stream;
 	cudaLaunchAttribute at[1];
 	at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
 	at[0].val.programmaticStreamSerializationAllowed = 1;
 	cfg.attrs = at;
 	cfg.numAttrs = pdl ? 1 : 0;
-	return bs == 64 ? cudaLaunchKernelEx(&cfg, k_tick_small<64>, W, (u32)phases)
-	                : cudaLaunchKernelEx(&cfg, k_tick_small<BT_SMALL_WORLD>, W, (u32)phases);
+	return cudaLaunchKernelEx(&cfg, k_tick_small, W, (u32)phases);
 }

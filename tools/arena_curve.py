@@ -8,9 +8,10 @@ import bittoss_b200
 from bittoss_b200 import workloads
 
 level = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "host", "_build", "data", "arena.sav")
-opts = [kv.split("=") for kv in sys.argv[1:]]
+opts = [kv.split("=") for kv in sys.argv[1:] if not kv.startswith("only=")]
+sizes = [int(kv[5:]) for kv in sys.argv[1:] if kv.startswith("only=")] or [256, 1024, 4096, 8192]
 tag = os.path.basename(os.environ.get("BT_LIB_SO", "in-tree")).replace("libbt_", "").replace(".so", "")
-for nw in (256, 1024, 4096, 8192):
+for nw in sizes:
     batch, n1 = workloads.arena_batch(level, list(range(nw)))
     w = workloads.arena_world(batch, 0)
     for k, v in opts:

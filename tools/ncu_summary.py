@@ -2,7 +2,9 @@
 `--set full` raw CSV -> per-launch table of the metrics that matter for an HBM-bound path.
     python tools/ncu_summary.py launches <launches.csv>
     python tools/ncu_summary.py full <report.ncu-rep>            (needs ncu on PATH)
-    python tools/ncu_summary.py grep <report.ncu-rep> <kernel regex> <metric regex>   (any raw-page columns, per launch)"""
+    python tools/ncu_summary.py grep <report.ncu-rep> <kernel regex> <metric regex>   (any raw-page columns, per launch)
+A report given as *.csv is read as the raw page already exported (`ncu -i x.ncu-rep --page raw --csv > x.raw.csv`, what
+tools/r2_final.sh brings back from the GPU box: the reports themselves exceed the transfer limit)."""
 import collections
 import csv
 import json
@@ -28,16 +30,26 @@ def launches(path):
           (tot / 1e3, sum(a[0] for a in agg.values())))
 
 
-WANT = [("gpu__time_duration.sum", "us"), ("dram__bytes_read.sum", "dram rd"), ("dram__bytes_write.sum", "dram wr"),
+WANT = [("gpu__time_duration.sum", "us"), ("launch__grid_size", "grid"), ("launch__block_size", "block"), ("dram__bytes_read.sum", "dram rd"), ("dram__bytes_write.sum", "dram wr"),
         ("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "dram %"),
         ("lts__t_bytes.sum", "L2 bytes"), ("l1tex__t_sector_hit_rate.pct", "L1 hit %"),
         ("lts__t_sector_hit_rate.pct", "L2 hit %"), ("sm__warps_active.avg.pct_of_peak_sustained_active", "occupancy %"),
         ("smsp__thread_inst_executed_per_inst_executed.ratio", "active thr/inst"),
-        ("smsp__inst_executed.sum", "warp inst"), ("launch__registers_per_thread", "regs")]
+        ("smsp__inst_executed.sum", "warp inst"), ("launch__registers_per_thread", "regs"),
+        ("smsp__issue_active.avg.pct_of_peak_sustained_active", "issue %"),
+        ("smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio", "long-sb stall/issue"),
+        ("l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum", "L1 ld sectors"),
+        ("l1tex__t_requests_pipe_lsu_mem_global_op_ld.sum", "L1 ld requests")]
+
+
+def raw_page(rep):
+    if rep.endswith(".csv"):
+        return open(rep).read()
+    return subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 
 
 def full(rep):
-    out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    out = raw_page(rep)
     rows = list(csv.reader(out.splitlines()))
     hdr, units = rows[0], rows[1]
     idx = [(hdr.index(m), lab) for m, lab in WANT if m in hdr]
@@ -63,7 +75,7 @@ def grep(rep, kernel_re, metric_re):
     """every raw-page column whose name matches metric_re, for the launches whose kernel matches kernel_re
     (what bounds a latency-looking kernel: l1tex / lts throughput %, warp stall reasons per issue)"""
     import re
-    out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    out = raw_page(rep)
     rows = list(csv.reader(out.splitlines()))
     hdr, units = rows[0], rows[1]
     ki = hdr.index("Kernel Name")
