@@ -169,6 +169,119 @@ __global__ void __launch_bounds__(128) k_raycast(DevWorld W, const i32 *origin, 
 	winner[i] = win >= 0 ? slot2rank[win] : -1;
 }
 
+/* The same sweep with the rays handed out dynamically (option ray_dynamic, the default for batches of >= 4096 rays).
+ * In k_raycast a lane that has found its winner idles until the longest ray of its warp is done: rays that leave the
+ * world traverse an order of magnitude more nodes than rays that hit the next column, 9.2 of 32 threads were active per
+ * issued instruction and the kernel is bound by instruction issue (63 % of the issue slots).  Here a warp keeps pulling
+ * rays: chunks of RAY_CHUNK rays from one global counter, and whenever RAY_REFILL or more of its lanes are idle each of
+ * them takes the next ray of the chunk, so every traversal step runs on (nearly) full warps.  The step is the loop body
+ * of t_raycast, the result the same order-independent minimum. */
+#define RAY_CHUNK 256
+#ifndef RAY_REFILL
+#define RAY_REFILL 8
+#endif
+__global__ void __launch_bounds__(128) k_raycast_dyn(DevWorld W, const i32 *origin, const i32 *look_in, i32 n_rays,
+                                                      i32 *winner_out, const i32 *rank2slot, const i32 *slot2rank, i32 n_live,
+                                                      const i32 *order, u32 *next) { PDL_ENTRY();
+	__shared__ i32 stacks[BT_STACK * 128];
+	i32 *const stack = stacks + threadIdx.x;
+	const int lane = threadIdx.x & 31;
+	const int L = W.n_leaves;
+	u32 pb = 0, pe = 0; /* this warp's chunk of rays (uniform over the warp) */
+	int exhausted = 0;  /* the global counter has run past the batch */
+	int active = 0;
+	i32 ray = -1, root = -1, winner = -1, node = 0;
+	u32 wp = 0;
+	int sp = 0;
+	i32 pos[3] = {0, 0, 0}, look[3] = {0, 0, 1}, flip[3] = {1, 1, 1};
+	Rat best = {INT32_MAX, 1};
+#define RAY_LEAF(t)                                                                              \
+	do {                                                                                         \
+		i32 e_ = W.leafEnt[t];                                                                   \
+		if (W.inList[e_] && W.holdRoot[e_] != root && (u32)W.world[e_] == wp) {                  \
+			Rat lw_;                                                                             \
+			if (ray_hit_ent(pos, look, flip, W.center[e_], W.radius[e_], &lw_)) {                \
+				if (rat_lt(lw_, best) || (winner >= 0 && !rat_lt(best, lw_) && e_ > winner)) { best = lw_; winner = e_; } \
+			}                                                                                    \
+		}                                                                                        \
+	} while (0)
+	while (1) {
+		const u32 idle = __ballot_sync(0xffffffffu, !active);
+		if (idle && (__popc(idle) >= RAY_REFILL || idle == 0xffffffffu || exhausted)) {
+			if (pb == pe && !exhausted) {
+				u32 b = 0;
+				if (lane == 0) b = atomicAdd(next, (u32)RAY_CHUNK);
+				b = __shfl_sync(0xffffffffu, b, 0);
+				if (b >= (u32)n_rays) { exhausted = 1; pb = pe = 0; }
+				else { pb = b; pe = b + RAY_CHUNK < (u32)n_rays ? b + RAY_CHUNK : (u32)n_rays; }
+			}
+			const u32 avail = pe - pb;
+			if (!avail && idle == 0xffffffffu) break; /* nothing left anywhere and nobody is travelling */
+			const u32 rank = (u32)__popc(idle & ((1u << lane) - 1));
+			if (!active && rank < avail) { /* take ray pb + rank */
+				ray = (i32)(pb + rank);
+				if (order) ray = order[ray];
+				const i32 og = origin[ray];
+				winner = -1;
+				if (og < 0 || og >= n_live || L < 1) {
+					winner_out[ray] = -1; /* not a live entity: no caster, no hit */
+				} else {
+					const i32 p = rank2slot[og];
+					const int4 pc = W.center[p];
+					pos[0] = pc.x; pos[1] = pc.y; pos[2] = pc.z;
+#pragma unroll
+					for (int i = 0; i < 3; i++) { /* raycast.cpp:20-28 (on a private copy) */
+						const i32 l = look_in[3 * ray + i];
+						if (l >= 0) { flip[i] = 1; look[i] = l; }
+						else { flip[i] = -1; look[i] = -l; }
+					}
+					root = W.holdRoot[p];
+					wp = (u32)W.world[p];
+					best.n = INT32_MAX; best.d = 1;
+					sp = 0;
+					node = L == 1 ? ~0 : W.wroot[wp];
+					if (node < 0) { /* a single leaf (~node), or none */
+						if (~node < L) RAY_LEAF(~node);
+						winner_out[ray] = winner >= 0 ? slot2rank[winner] : -1;
+					} else {
+						active = 1;
+					}
+				}
+			}
+			pb += __popc(idle) < (int)avail ? (u32)__popc(idle) : avail;
+		}
+		if (active) { /* one node */
+			const NodeRegs N = bt_load_node(W, node);
+			i32 li = N.d.x, ri = N.d.y;
+			u32 wl = (u32)N.d.z, wr = (u32)N.d.w;
+			const i32 llo[3] = {N.a.x, N.a.y, N.a.z}, lhi[3] = {N.a.w, N.b.x, N.b.y};
+			const i32 rlo[3] = {N.b.z, N.b.w, N.c.x}, rhi[3] = {N.c.y, N.c.z, N.c.w};
+			Rat eL = {0, 1}, eR = {0, 1};
+			int ovL = (wl & 0xffff) <= wp && wp <= (wl >> 16) && ray_hit_box(pos, look, flip, llo, lhi, best, &eL);
+			int ovR = (wr & 0xffff) <= wp && wp <= (wr >> 16) && ray_hit_box(pos, look, flip, rlo, rhi, best, &eR);
+			if (ovL && li < 0) RAY_LEAF(~li);
+			if (ovR && ri < 0) RAY_LEAF(~ri);
+			int goL = ovL && li >= 0, goR = ovR && ri >= 0;
+			if (goL && goR) {
+				int rightFirst = rat_lt(eR, eL);
+				node = rightFirst ? ri : li;
+				if (sp < BT_STACK) stack[(sp++) * 128] = rightFirst ? li : ri;
+				else W.ctr[CT_ERROR] = (u32)(-BT_ERR_OVERFLOW);
+			} else if (goL) {
+				node = li;
+			} else if (goR) {
+				node = ri;
+			} else if (sp == 0) {
+				winner_out[ray] = winner >= 0 ? slot2rank[winner] : -1;
+				active = 0;
+			} else {
+				node = stack[(--sp) * 128];
+			}
+		}
+	}
+#undef RAY_LEAF
+}
+
 /* inList -> live rank per slot (rank2slot / slot2rank), three small launches over tiles of RANK_TILE slots:
  * count the live slots of every tile, scan the tile counts (one block), rank inside each tile from its base.
  * (One block looping over the whole world took 0.89 ms at 1 M slots.) */

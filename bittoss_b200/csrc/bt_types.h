@@ -111,6 +111,7 @@ enum {
 	CT_ORDER_TIES = 46,  /* full collisionBetter ties between different collisions (resolved by the canonical key) */
 	CT_WQ_N = 47,        /* nodes handed out from the pending-wire pool (wq_next / wq_to) since the last flushMisc */
 	CT_TREE_EDITS = 48,  /* fumbles + pickups + deaths so far: a host binding re-reads the hold tree only when it moved */
+	CT_RAY_NEXT = 50,    /* k_raycast_dyn: the next unclaimed ray of the batch */
 	CT_WORDS = 64
 };
 enum { SK_ITERS = 0, SK_CAND, SK_POS, SK_PUSH, SK_SERIAL, SK_CRUSH, SK_FUMBLE, SK_ETICKS, SK_NUM };

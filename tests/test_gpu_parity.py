@@ -285,8 +285,9 @@ def test_cuda_small_world_pair_search_agrees_with_tree(bt):
 
 
 def test_cuda_raycast_large_batch_sorted_equals_unsorted_and_oracle(bt, oracle_lib):
-    """option sort_rays: batches of >= 4096 rays traversed in the order of their origin's leaf position (radix-sorted on
-    the device); the winners come back by ray index: identical to the unsorted traversal and to the oracle's brute force"""
+    """batches of >= 4096 rays: handed out dynamically to the warps or one per thread, in the caller's order or in the order of
+    their origin's leaf position (radix-sorted on the device); the winners come back by ray index and equal the oracle's
+    brute force in every mode"""
     wa, _ = load_scenario("stack4k_pushall")
     rng = np.random.RandomState(11)
     n = 20000
@@ -303,12 +304,19 @@ def test_cuda_raycast_large_batch_sorted_equals_unsorted_and_oracle(bt, oracle_l
     origin[::97] = -1                      # not a live entity: no caster, no hit
     want = ow.selectcast(np.where(origin < 0, 0, origin), look)
     want[origin < 0] = -1
-    got_plain = w.raycast(origin, look)
+    got_plain = w.raycast(origin, look)        # rays handed out dynamically to the warps (k_raycast_dyn, the default)
     w.set_option("sort_rays", 1)
     got_sorted = w.raycast(origin, look)
+    w.set_option("ray_dynamic", 0)             # one ray per thread, fixed (k_raycast)
+    got_static_sorted = w.raycast(origin, look)
+    w.set_option("sort_rays", 0)
+    got_static = w.raycast(origin, look)
+    w.set_option("ray_dynamic", 1)
+    w.set_option("ray_blocks", 3)              # far fewer warps than chunks of rays: every warp refills many times
+    got_few = w.raycast(origin, look)
     w.close()
-    assert np.array_equal(got_sorted, got_plain)
-    assert np.array_equal(got_sorted, want)
+    for got in (got_plain, got_sorted, got_static_sorted, got_static, got_few):
+        assert np.array_equal(got, want)
 
 
 def test_cuda_raycast_matches_reference_selectcast(bt, ref_lib):
