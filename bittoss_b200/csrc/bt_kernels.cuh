@@ -557,48 +557,49 @@ __global__ void __launch_bounds__(SORT_THREADS) k_sort_hist(const u64 *keys, i32
 	hist[threadIdx.x * nb + blockIdx.x] = h[threadIdx.x]; /* digit-major */
 }
 
-/* exclusive scan of `len` counters (256 digits x tiles, digit-major) by one block of 1024 threads: every thread owns
- * one contiguous chunk -- sums it, the 1024 chunk sums are scanned once through shared memory, then the chunk is
- * rewritten with running offsets.  Two passes over a table that sits in L2 and three barriers in all (a block-wide
- * scan per 1024 counters needed 4 barriers x 62 rounds: 58 us per radix pass at 1 M keys). */
-__global__ void __launch_bounds__(1024) k_sort_scan(u32 *hist, int len) { PDL_ENTRY_ALWAYS();
-	__shared__ u32 warpTot[32];
-	const int chunk = (len + 1023) / 1024;
-	const int b0 = min(len, (int)threadIdx.x * chunk), b1 = min(len, b0 + chunk);
-	u32 sum = 0;
-#pragma unroll 8
-	for (int i = b0; i < b1; i++) sum += hist[i];
-	u32 x = sum;
-#pragma unroll
-	for (int off = 1; off < 32; off <<= 1) {
-		u32 y = __shfl_up_sync(0xffffffffu, x, off);
-		if ((threadIdx.x & 31) >= off) x += y;
-	}
-	if ((threadIdx.x & 31) == 31) warpTot[threadIdx.x >> 5] = x;
-	__syncthreads();
-	if (threadIdx.x < 32) {
-		u32 w = warpTot[threadIdx.x], t = w;
+/* The counters (256 digits x nb tiles, digit-major) become positions in two steps.  Here one WARP per digit scans its
+ * row of nb tile counts in place (exclusive, inside the digit) and leaves the row total in hist[256 * nb + d]; the
+ * scatter kernel turns the 256 totals into digit bases itself (a 256-element scan per block).  (One block of 1024
+ * threads scanning all 256 * nb counters took 54 us per radix pass at 1 M keys, 4 passes per tree build.) */
+__global__ void __launch_bounds__(1024) k_sort_scan(u32 *hist, int nb) { PDL_ENTRY_ALWAYS();
+	const int d = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+	if (d >= 256) return;
+	u32 *row = hist + (size_t)d * nb;
+	u32 carry = 0;
+	for (int b0 = 0; b0 < nb; b0 += 32) {
+		const int i = b0 + lane;
+		const u32 v = i < nb ? row[i] : 0u;
+		u32 x = v;
 #pragma unroll
 		for (int off = 1; off < 32; off <<= 1) {
-			u32 y = __shfl_up_sync(0xffffffffu, t, off);
-			if (threadIdx.x >= off) t += y;
+			u32 y = __shfl_up_sync(0xffffffffu, x, off);
+			if (lane >= off) x += y;
 		}
-		warpTot[threadIdx.x] = t - w; /* exclusive over warps */
+		if (i < nb) row[i] = carry + x - v;
+		carry += __shfl_sync(0xffffffffu, x, 31);
 	}
-	__syncthreads();
-	u32 run = warpTot[threadIdx.x >> 5] + x - sum;
-#pragma unroll 8
-	for (int i = b0; i < b1; i++) {
-		const u32 v = hist[i];
-		hist[i] = run;
-		run += v;
-	}
+	if (lane == 0) hist[(size_t)256 * nb + d] = carry;
 }
 
 __global__ void __launch_bounds__(SORT_THREADS) k_sort_scatter(const u64 *keys, const i32 *vals, u64 *okeys, i32 *ovals,
                                                              i32 n, int shift, const u32 *hist, int nb) { PDL_ENTRY_ALWAYS();
 	__shared__ u32 warpOff[SORT_THREADS / 32][256];
+	__shared__ u32 dbase[256], wtot[SORT_THREADS / 32];
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	{ /* digit bases = exclusive scan of the 256 row totals k_sort_scan left behind the table (SORT_THREADS == 256) */
+		const u32 v = hist[(size_t)256 * nb + threadIdx.x];
+		u32 x = v;
+#pragma unroll
+		for (int off = 1; off < 32; off <<= 1) {
+			u32 y = __shfl_up_sync(0xffffffffu, x, off);
+			if (lane >= off) x += y;
+		}
+		if (lane == 31) wtot[warp] = x;
+		__syncthreads();
+		u32 before = 0;
+		for (int k = 0; k < warp; k++) before += wtot[k];
+		dbase[threadIdx.x] = before + x - v;
+	}
 	for (int d = lane; d < 256; d += 32) warpOff[warp][d] = 0;
 	__syncwarp();
 	/* each warp owns a contiguous run of 32*SORT_ITEMS keys -> stability */
@@ -616,7 +617,7 @@ __global__ void __launch_bounds__(SORT_THREADS) k_sort_scatter(const u64 *keys, 
 	__syncthreads();
 	{ /* thread d turns the per-warp counts into running offsets */
 		int d = threadIdx.x;
-		u32 run = hist[d * nb + blockIdx.x];
+		u32 run = dbase[d] + hist[d * nb + blockIdx.x];
 #pragma unroll
 		for (int w = 0; w < SORT_THREADS / 32; w++) {
 			u32 c = warpOff[w][d];

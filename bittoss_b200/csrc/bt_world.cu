@@ -611,7 +611,7 @@ static int radix_sort_buf(bt_world *w, int cls, u64 **keys, i32 **vals, u64 **ke
 	const int nb = (n + SORT_TILE - 1) / SORT_TILE;
 	for (int shift = 0; shift < key_bits; shift += 8) {
 		LAUNCH(w, cls, k_sort_hist, nb, SORT_THREADS, (const u64 *)*keys, n, shift, hist, nb);
-		LAUNCH(w, cls, k_sort_scan, 1, 1024, hist, 256 * nb);
+		LAUNCH(w, cls, k_sort_scan, 8, 1024, hist, nb); /* 256 warps: one per digit */
 		LAUNCH(w, cls, k_sort_scatter, nb, SORT_THREADS, (const u64 *)*keys, (const i32 *)*vals, *keys_alt, *vals_alt, n, shift, (const u32 *)hist, nb);
 		std::swap(*keys, *keys_alt);
 		std::swap(*vals, *vals_alt);
