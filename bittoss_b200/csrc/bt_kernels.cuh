@@ -271,6 +271,28 @@ struct PairEmit {
 			n = 0;
 		}
 	}
+	/* called by every thread of the BLOCK, converged: what the threads hold goes out in thread order behind ONE atomic */
+	__device__ __forceinline__ void finish_block(u32 *wsum, u32 *base_sh) {
+		const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+		u32 x = (u32)n;
+#pragma unroll
+		for (int off = 1; off < 32; off <<= 1) {
+			u32 y = __shfl_up_sync(0xffffffffu, x, off);
+			if (lane >= off) x += y;
+		}
+		if (lane == 31) wsum[warp] = x;
+		__syncthreads();
+		u32 before = 0, tot = 0;
+		for (int k = 0; k < (int)(blockDim.x >> 5); k++) { if (k < warp) before += wsum[k]; tot += wsum[k]; }
+		if (threadIdx.x == 0 && tot) *base_sh = atomicAdd(counter, tot);
+		__syncthreads();
+		if (tot) {
+			const u32 base = *base_sh + before + x - (u32)n;
+			for (int k = 0; k < n; k++) store(base + k, buf[k * BT_BLOCK]);
+		}
+		n = 0;
+		__syncthreads(); /* wsum / base_sh are reused by the next round */
+	}
 	/* called once by every thread of the warp, converged */
 	__device__ __forceinline__ void finish() {
 		int lane = threadIdx.x & 31;
@@ -298,12 +320,23 @@ __global__ void __launch_bounds__(BT_BLOCK) k_pairs(DevWorld W) { PDL_ENTRY();
 		emit.finish();
 		return;
 	}
-	/* blocked distribution: each block walks one contiguous run of leaves, so the pair list
-	 * stays in Morton order (k_narrow's gathers depend on that locality) */
-	i32 chunk = (W.n_leaves + (i32)gridDim.x - 1) / (i32)gridDim.x;
-	i32 t0 = (i32)blockIdx.x * chunk, t1 = t0 + chunk < W.n_leaves ? t0 + chunk : W.n_leaves;
-	for (i32 t = t0 + (i32)threadIdx.x; t < t1; t += BT_BLOCK) t_pairs(W, t, stacks + threadIdx.x, BT_BLOCK, emit);
-	emit.finish();
+	/* blocked distribution: each block walks one contiguous run of leaves, 128 consecutive leaves per round, and the
+	 * pairs of a round go out together in leaf order (one atomic per block and round): the list is sorted by the
+	 * position of the emitting leaf down to the grain of a round, and the 32 pairs a warp of k_narrow reads come from
+	 * ~32 neighbouring leaves.  (With every thread flushing its own buffer at the end of its whole run, 8 consecutive
+	 * list entries came from one thread, i.e. from leaves 128 apart: k_narrow, whose gathers live on that locality, went
+	 * 306 -> 270 us per tick on the settled 1 M world and 459 -> 357 in the dynamic phase with the ordered list; handing
+	 * the leaves out dynamically like the rays of k_raycast_dyn made the walk itself no faster, 410 -> 434 us, and the
+	 * list worse.  profiles/r2_ab_experiments.md §10) */
+	__shared__ u32 wsum[BT_BLOCK / 32];
+	__shared__ u32 rbase;
+	const i32 chunk = (W.n_leaves + (i32)gridDim.x - 1) / (i32)gridDim.x;
+	const i32 t0 = (i32)blockIdx.x * chunk, t1 = t0 + chunk < W.n_leaves ? t0 + chunk : W.n_leaves;
+	for (i32 r0 = t0; r0 < t1; r0 += BT_BLOCK) {
+		const i32 t = r0 + (i32)threadIdx.x;
+		if (t < t1) t_pairs(W, t, stacks + threadIdx.x, BT_BLOCK, emit);
+		emit.finish_block(wsum, &rbase);
+	}
 }
 
 /* small-world mode: one block per world, boxes in shared memory, all pairs (see t_pairs_small_world) */

@@ -1358,7 +1358,7 @@ int bt_world_assign(bt_world *dst, bt_world *src) {
 	dst->root_phase_ctr = src->root_phase_ctr; dst->sliders_used = src->sliders_used; dst->wires_used = src->wires_used; dst->poked = src->poked;
 	dst->tree_valid = src->tree_valid; dst->deltas_pending = src->deltas_pending; dst->any_rules = src->any_rules;
 	dst->full_flush_left = src->full_flush_left; dst->scan_flushes_left = src->scan_flushes_left; dst->ctrls_fused = src->ctrls_fused;
-	dst->uid_map_valid = false; dst->ctr_fresh = false; dst->pdl = src->pdl; dst->pdl_long = src->pdl_long; dst->pdl_opt = src->pdl_opt; dst->margin_opt = src->margin_opt; dst->narrow_blocks = src->narrow_blocks; dst->narrow_threads = src->narrow_threads; dst->small_worlds = src->small_worlds;
+	dst->uid_map_valid = false; dst->ctr_fresh = false; dst->pdl = src->pdl; dst->pdl_long = src->pdl_long; dst->pdl_opt = src->pdl_opt; dst->margin_opt = src->margin_opt; dst->narrow_blocks = src->narrow_blocks; dst->ray_dynamic = src->ray_dynamic; dst->ray_blocks = src->ray_blocks; dst->narrow_threads = src->narrow_threads; dst->small_worlds = src->small_worlds;
 	dst->any_ticks = src->any_ticks; dst->any_rand = src->any_rand; dst->bad_tick = src->bad_tick; dst->device_ticks = src->device_ticks;
 	dst->ticks_since_build = src->ticks_since_build; dst->rebuild_every = src->rebuild_every;
 	dst->max_iterations = src->max_iterations; dst->pair_cache = src->pair_cache;
