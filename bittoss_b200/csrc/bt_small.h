@@ -14,9 +14,9 @@ cudaError_t bt_launch_tick_small_128_16(const DevWorld &W, unsigned phases, bool
 cudaError_t bt_launch_tick_small_128_32(const DevWorld &W, unsigned phases, bool pdl, cudaStream_t stream);
 /* block = 64 threads when no world holds more than 64 slots, else BT_SMALL_WORLD; the 32-warp variant (64 registers,
  * spills) once the worlds fill every SM at that occupancy, the 16-warp one (128 registers) below */
-static inline cudaError_t bt_launch_tick_small(const DevWorld &W, unsigned phases, int biggest_world, bool pdl, cudaStream_t stream) {
+static inline cudaError_t bt_launch_tick_small(const DevWorld &W, unsigned phases, int biggest_world, int warps, bool pdl, cudaStream_t stream) {
 	const int bs = biggest_world <= 64 ? 64 : BT_SMALL_WORLD;
-	const bool many = (long long)W.n_worlds * (bs / 32) >= 148LL * 32;
+	const bool many = warps ? warps >= 32 : (long long)W.n_worlds * (bs / 32) >= 148LL * 32; /* warps: option small_warps (0 = by the number of worlds) */
 	if (bs == 64) return many ? bt_launch_tick_small_64_32(W, phases, pdl, stream) : bt_launch_tick_small_64_16(W, phases, pdl, stream);
 	return many ? bt_launch_tick_small_128_32(W, phases, pdl, stream) : bt_launch_tick_small_128_16(W, phases, pdl, stream);
 }

@@ -124,6 +124,7 @@ struct bt_world {
 	                * (9.2 of 32 threads active per instruction), not by where the rays start) */
 	bool poked;                 /* the host wrote into the world since the counters were last fetched */
 	cudaError_t launch_err;     /* first failed kernel launch since the last check (reported at the next sync point) */
+	i64 small_warps;            /* option "small_warps": 0 = pick the k_tick_small variant by the number of worlds, 16 / 32 = force it */
 	i64 fused_small;            /* option "fused_small": whole ticks of small worlds in one block per world (k_tick_small) */
 	i32 small_biggest;          /* slots of the largest world of the last upload */
 	bool fused_dirty;           /* fused ticks ran since the host last looked: counters, live count, cached pairs are stale */
@@ -276,7 +277,7 @@ int bt_world_create(bt_world **out, int device, int32_t max_ents, int32_t max_sl
 	w->rebuild_every = 16; w->max_iterations = 100000; w->pair_cache = 1; w->pair_rebuilds = 0; w->pair_overflows = 0; w->seen_pair_builds = 0; w->seen_pair_patches = 0; w->pair_builds_at_tree = 0; w->profiling = false; w->ray_valid = false; w->uid_map_valid = false; w->ctr_fresh = false; w->margin_opt = -1; w->narrow_blocks = 148 * 8; w->narrow_threads = 256; w->pdl_opt = getenv("BT_NO_PDL") ? 0 : -1; w->pdl = false; w->pdl_long = false; /* decided at upload, together with W.pdl */ w->small_worlds = true; w->d_reqs = NULL; w->d_req_starts = NULL; w->reqs_cap = 0; w->any_ticks = w->any_rand = false; w->bad_tick = 0; w->device_ticks = 1;
 	w->h_flag = NULL; w->ev0 = w->ev1 = NULL; w->stream = NULL;
 	w->root_phase_ctr = 0; w->sliders_used = 0; w->wires_used = 0; w->d_pokes = NULL; w->pokes_cap = 0; w->poked = false;
-	w->launch_err = cudaSuccess; w->fused_small = 1; w->fused_dirty = false; w->seen_eticks = w->seen_iters = 0; w->wq_host_pending = false; w->small_biggest = 0;
+	w->launch_err = cudaSuccess; w->fused_small = 1; w->small_warps = getenv("BT_SMALL_WARPS") ? atoi(getenv("BT_SMALL_WARPS")) : 0; w->fused_dirty = false; w->seen_eticks = w->seen_iters = 0; w->wq_host_pending = false; w->small_biggest = 0;
 	w->d_raykeys = w->d_raykeys_alt = NULL; w->d_rayidx = w->d_rayidx_alt = NULL; w->d_rayhist = NULL; w->rays_cap = 0; w->sort_rays = 0; w->ray_dynamic = 1; w->ray_blocks = 148 * 12; /* measured on 4 M rays: 4.28 ms at 148 x 8 blocks, 4.06 at x 12 and beyond (13 fit an SM) */
 	*out = w;
 #define TRY(x) do { int _r = (x); if (_r) { bt_world_destroy(w); *out = NULL; return _r; } } while (0)
@@ -382,6 +383,7 @@ int bt_world_set_option(bt_world *w, const char *name, int64_t value) {
 	if (!strcmp(name, "ray_dynamic")) { w->ray_dynamic = value != 0; return BT_OK; }
 	if (!strcmp(name, "ray_blocks")) { w->ray_blocks = value < 1 ? 1 : value; return BT_OK; }
 	if (!strcmp(name, "fused_small")) { w->fused_small = value != 0; return BT_OK; }
+	if (!strcmp(name, "small_warps")) { w->small_warps = value; return BT_OK; }
 	if (!strcmp(name, "pair_patch")) { w->W.patch = value != 0; return BT_OK; }
 	if (!strcmp(name, "patch_shift")) { w->W.patch_shift = value < 0 ? 0 : (value > 20 ? 20 : (i32)value); return BT_OK; }
 	if (!strcmp(name, "run_ahead")) { w->run_ahead = value != 0; return BT_OK; }
@@ -940,7 +942,7 @@ static int step_small_fused(bt_world *w, uint32_t phases) {
 	const u32 kp = phases | (w->deltas_pending ? SWF_HOST_DELTAS : 0u);
 	if (W.n_worlds > 0) { /* LAUNCH() for a kernel that lives in another translation unit (bt_small.cu) */
 		if (w->profiling) cudaEventRecord(w->ev0, w->stream);
-		cudaError_t le = bt_launch_tick_small(W, kp, w->small_biggest, w->pdl, w->stream);
+		cudaError_t le = bt_launch_tick_small(W, kp, w->small_biggest, (int)w->small_warps, w->pdl, w->stream);
 		if (le != cudaSuccess) note_launch_error(w, le, "k_tick_small", __LINE__);
 		w->stats.kernel_launches++;
 		w->prof_launches[PK_FUSED]++;
@@ -1354,7 +1356,7 @@ int bt_world_assign(bt_world *dst, bt_world *src) {
 	rebase(&dst->ray, sizeof(dst->ray), src, dst);
 	dst->arrays = src->arrays;
 	rebase(&dst->arrays, sizeof(dst->arrays), src, dst);
-	dst->fused_small = src->fused_small; dst->fused_dirty = src->fused_dirty; dst->small_biggest = src->small_biggest; dst->wq_host_pending = src->wq_host_pending; dst->seen_eticks = src->seen_eticks; dst->seen_iters = src->seen_iters;
+	dst->fused_small = src->fused_small; dst->small_warps = src->small_warps; dst->fused_dirty = src->fused_dirty; dst->small_biggest = src->small_biggest; dst->wq_host_pending = src->wq_host_pending; dst->seen_eticks = src->seen_eticks; dst->seen_iters = src->seen_iters;
 	dst->root_phase_ctr = src->root_phase_ctr; dst->sliders_used = src->sliders_used; dst->wires_used = src->wires_used; dst->poked = src->poked;
 	dst->tree_valid = src->tree_valid; dst->deltas_pending = src->deltas_pending; dst->any_rules = src->any_rules;
 	dst->full_flush_left = src->full_flush_left; dst->scan_flushes_left = src->scan_flushes_left; dst->ctrls_fused = src->ctrls_fused;

@@ -2,8 +2,8 @@
 # Round-2 final measurement on one B200 (run under gpurun): both bench arms, then ncu launch lists and --set full
 # captures of the settled tick, the dynamic phase, the raycast and the one-block-per-world step.  Outputs -> gpurun_out/.
 set -u
-O=gpurun_out; mkdir -p $O; P=r2k
-python bench.py --impl reference --steps 20 --warmup 3 > $O/${P}_reference_arm.json 2> $O/${P}_ref.err || echo "reference arm failed"
+O=gpurun_out; mkdir -p $O; P=${P:-r2k}
+if [ -z "${SKIP_REF:-}" ]; then python bench.py --impl reference --steps 20 --warmup 3 > $O/${P}_reference_arm.json 2> $O/${P}_ref.err || echo "reference arm failed"; fi
 python bench.py --steps 100 --warmup 5 > $O/${P}_bench.json 2> $O/${P}_bench.err || echo "bench failed"
 python tools/arena_curve.py > $O/${P}_arena_curve.txt 2>&1
 python tools/arena_curve.py fused_small=0 >> $O/${P}_arena_curve.txt 2>&1
