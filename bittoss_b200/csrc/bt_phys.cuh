@@ -1600,12 +1600,14 @@ static BT_HD void t_post(const DevWorld &W, i32 e) {
  * TICK_RAND draws from gs->rand and therefore runs per world, in list order (t_tick_serial). */
 enum {
 	TICK_RAND = 6, TICK_LOGIC = 11, TICK_LOGIC_DEBUG = 12, TICK_DOOR = 13, TICK_CURSED = 14, TICK_RESPAWN = 15,
-	TICK_SEAT_OLD = 17, TICK_ADJUST = 19, TICK_SEAT = 23, TICK_TIMER = 28, TICK_DEMOLISH = 29, TICK_SIGN = 34
+	TICK_SEAT_OLD = 17, TICK_ADJUST = 19, TICK_SEAT = 23, TICK_HELD_GUN = 24, TICK_SCOREBOARD = 27, TICK_TIMER = 28,
+	TICK_DEMOLISH = 29, TICK_SIGN = 34
 };
 /* NIL + the ids above */
 #define BT_SUPPORTED_TICK ((1ull << 0) | (1ull << TICK_RAND) | (1ull << TICK_LOGIC) | (1ull << TICK_LOGIC_DEBUG) | \
 	(1ull << TICK_DOOR) | (1ull << TICK_CURSED) | (1ull << TICK_RESPAWN) | (1ull << TICK_SEAT_OLD) |                  \
-	(1ull << TICK_ADJUST) | (1ull << TICK_SEAT) | (1ull << TICK_TIMER) | (1ull << TICK_DEMOLISH) | (1ull << TICK_SIGN))
+	(1ull << TICK_ADJUST) | (1ull << TICK_SEAT) | (1ull << TICK_TIMER) | (1ull << TICK_DEMOLISH) | (1ull << TICK_SIGN) | \
+	(1ull << TICK_HELD_GUN) | (1ull << TICK_SCOREBOARD))
 
 static BT_HD int bt_button(const DevWorld &W, i32 e, int i) { return (int)(int8_t)((W.btn_v[e] >> (8 * i)) & 0xffu); }
 static BT_HD void bt_push_btn(const DevWorld &W, i32 e, int i) { bt_or32(&W.btn_v2[e], 1u << (8 * i)); }
@@ -1688,7 +1690,34 @@ static BT_HD void bt_door_tick(const DevWorld &W, i32 me) {
 	W.ctr[CT_ANY_DELTA] = 1;
 }
 
-/* one entity's tick / tickHeld handler.  Returns without effect for TICK_RAND (serial pass). */
+/* scoreboard_tick scoreboard.cpp:37-90 with gs->players.num == 0 (like TICK_RESPAWN): nobody is alive.  Runs in the
+ * per-world serial pass: at the end of a round it erases every other entity of the world (uErase sets dead_max to 3,
+ * uDead of a handler running at the same time ORs 1 into the same byte: either order gives 3 in the reference). */
+static BT_HD void bt_scoreboard_tick(const DevWorld &W, i32 me) {
+	const i32 alive = 0;
+	i32 timer = bt_getslider(W, me, 1);
+	if (bt_getslider(W, me, 0) != alive) { bt_uslider_shared(W, me, 0, alive); timer = 75; }
+	if (!timer) return;
+	timer--;
+	bt_uslider_shared(W, me, 1, timer);
+	if (timer) return;
+	/* the round is over, a tie: everything but the board is erased (uErase entUpdaters.c:25-27) ... */
+	const int g = W.world[me];
+	for (i32 e = W.wbegin[g]; e < W.wend[g]; e++) {
+		if (e == me || !W.inList[e]) continue;
+		if (W.flip[g]) W.dead_max1[e] = 3; else W.dead_max0[e] = 3;
+	}
+	W.wflush[g] = 1;
+	bt_uslider_shared(W, me, 0, 0);
+	/* ... requestReload + showMessage belong to the host: an event (kind 6 = tick handler, arg = the alive mask) */
+	const u32 slot = bt_add32(&W.ctr[CT_EVENT_N], 1u);
+	if ((i32)slot < W.event_cap) W.events[slot] = make_int4(0x600 | TICK_SCOREBOARD, me, me, alive);
+	W.fullFlush[me] = 1; /* uMyCollideMask(me, T_TERRAIN) entUpdaters.c:80 */
+	W.ncollide[me] = T_TERRAIN;
+	W.ctr[CT_FLUSH_HINT] = 1;
+}
+
+/* one entity's tick / tickHeld handler.  Returns without effect for TICK_RAND and TICK_SCOREBOARD (serial pass). */
 static BT_HD void t_tick(const DevWorld &W, i32 me) {
 	if (me >= W.n || !W.inList[me]) return;
 	u32 ht = W.htick[me];
@@ -1730,6 +1759,14 @@ static BT_HD void t_tick(const DevWorld &W, i32 me) {
 				if (bt_button(W, w, i)) bt_push_btn(W, me, i);
 		}
 		return;
+	case TICK_HELD_GUN: { /* gun_tick_held gun.c:41-88: "doesn't do anything unless held by a person (or similar)".  Held by
+	                       * one, it reads the holder's trigger (host-side control state) and creates bullets: not here */
+		const i32 h = W.holder[me];
+		if (h < 0 || !(W.type[h] & T_INPUTS) || W.holder[h] >= 0) return;
+		bt_unsup(W, me, 6, id);
+		return;
+	}
+	case TICK_SCOREBOARD: return; /* per world, after everybody else (t_tick_serial): it may erase the whole world */
 	default: bt_unsup(W, me, 6, id); return;
 	}
 }
@@ -1740,13 +1777,16 @@ static BT_HD i32 bt_random(const DevWorld &W, int g) {
 	W.rnd[g] = x;
 	return x;
 }
-/* randomazzo_tick logic.c:151-168 for every TICK_RAND entity of world g, newest first (gs->ents order) */
+/* randomazzo_tick logic.c:151-168 for every TICK_RAND entity of world g, newest first (gs->ents order), and the
+ * scoreboards */
 static BT_HD void t_tick_serial(const DevWorld &W, int g) {
 	if (g >= W.n_worlds) return;
 	for (i32 me = W.wend[g] - 1; me >= W.wbegin[g]; me--) {
 		if (!W.inList[me]) continue;
 		u32 ht = W.htick[me];
-		if ((W.holder[me] >= 0 ? (ht >> 8) & 0xffu : ht & 0xffu) != TICK_RAND) continue;
+		const u32 id = W.holder[me] >= 0 ? (ht >> 8) & 0xffu : ht & 0xffu;
+		if (id == TICK_SCOREBOARD) { bt_scoreboard_tick(W, me); continue; }
+		if (id != TICK_RAND) continue;
 		if (!bt_logic_input(W, me, bt_getslider(W, me, 0))) continue;
 		int options = 0;
 		for (i32 k = 0; k < W.wire_cnt[me]; k++) options += !bt_button(W, W.wire_to[W.wire_off[me] + k], 0);

@@ -70,12 +70,15 @@ def arena_kicks(n_ents, world, max_v):
 
 def arena_batch(level_path, world_ids, kick_max=150):
     """one batched bt_world_desc holding a copy of the level per world id, each with its own seeded velocity kick
-    (the device has no player / gun tick handlers yet: without them a shipped level is at rest)"""
+    (the device has no player table: without players a shipped level is at rest)"""
     from . import concat_worlds
     from .savfile import load_sav
     base, _ = load_sav(level_path)
-    base.a["handlers"][1::10] = 0   # tick / tickHeld ids: not run on the device in this workload
-    base.a["handlers"][2::10] = 0
+    # every handler of the level stays, tick handlers included (respawners, guns nobody holds: they have device bodies, so
+    # bt_world_tick runs the whole doWholeStep of a world without players) -- except the scoreboard's: without players
+    # it calls every round a tie after 70 ticks, erases the world and asks the HOST to reload the level
+    h = base.a["handlers"].reshape(-1, 10)
+    h[:, 1][h[:, 1] == 27] = 0   # TICK_SCOREBOARD
     n1 = base.n
     batch = concat_worlds([base] * len(world_ids))
     for k, g in enumerate(world_ids):

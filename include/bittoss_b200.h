@@ -165,8 +165,9 @@ typedef struct bt_profile {
  * after every step: push events come in the canonical push order, then the crush events in the
  * order invokeOnCrush (ent.cpp:464-469) calls the handlers, most recent death first. */
 typedef struct bt_event {
-	int32_t kind;     /* 0 = push handler, 3 = crush handler */
-	int32_t handler;  /* catalog id (PUSH_TEAMSELECT = 4, PUSH_LOADBLOCK = 7; CRUSH_FLAG = 1, CRUSH_PLATFORM = 2) */
+	int32_t kind;     /* 0 = push handler, 3 = crush handler, 6 = tick handler (BT_PHASE_TICKS only) */
+	int32_t handler;  /* catalog id (PUSH_TEAMSELECT = 4, PUSH_LOADBLOCK = 7; CRUSH_FLAG = 1, CRUSH_PLATFORM = 2;
+	                   * TICK_SCOREBOARD = 27: the round ended, the host owes requestReload + showMessage, scoreboard.cpp:81-86) */
 	int32_t world;
 	int32_t me_uid;   /* the entity owning the handler */
 	int32_t him_uid;  /* push: the entity that pushed it; crush: me_uid again */

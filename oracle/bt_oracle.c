@@ -1349,7 +1349,7 @@ static void worldRules(World *w, int g) {
  * Run one entity after the other in gs->ents order (newest first), like the reference. ---- */
 enum {
 	TICK_RAND = 6, TICK_LOGIC = 11, TICK_LOGIC_DEBUG = 12, TICK_DOOR = 13, TICK_CURSED = 14, TICK_RESPAWN = 15,
-	TICK_SEAT_OLD = 17, TICK_ADJUST = 19, TICK_SEAT = 23, TICK_TIMER = 28, TICK_DEMOLISH = 29, TICK_SIGN = 34
+	TICK_SEAT_OLD = 17, TICK_ADJUST = 19, TICK_SEAT = 23, TICK_SCOREBOARD = 27, TICK_TIMER = 28, TICK_DEMOLISH = 29, TICK_SIGN = 34
 };
 static int getButton(const World *w, i32 e, int i) { return (int)(signed char)w->btn[e][i]; }
 static void pushBtn(World *w, i32 e, int i) { w->btn[e][4 + i] = 1; }
@@ -1462,7 +1462,22 @@ static void tickOne(World *w, int g, i32 me) {
 				if (getButton(w, x, i)) pushBtn(w, me, i);
 		}
 		break;
-	default: break; /* NIL, SIGN; other ids belong to the host */
+	case TICK_SCOREBOARD: { /* scoreboard.cpp:37-90 with gs->players.num == 0: alive == 0 */
+		i32 timer = getSlider(w, me, 1);
+		if (getSlider(w, me, 0) != 0) { uSlider(w, me, 0, 0); timer = 75; }
+		if (!timer) break;
+		timer--;
+		uSlider(w, me, 1, timer);
+		if (timer) break;
+		for (i32 e = w->wbegin[g]; e < w->wend[g]; e++) /* uErase entUpdaters.c:25-27 for everything but the board */
+			if (e != me && w->inList[e]) w->dead_max[e][w->flip[g]] = 3;
+		uSlider(w, me, 0, 0);
+		w->n_events++; /* requestReload + showMessage: the host's */
+		w->fullFlush[me] = 1; /* uMyCollideMask(me, T_TERRAIN) */
+		w->ncollide[me] = T_TERRAIN;
+		break;
+	}
+	default: break; /* NIL, SIGN, HELD_GUN without a holder that has inputs (gun.c:43-44); other ids belong to the host */
 	}
 }
 

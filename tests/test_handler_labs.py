@@ -165,7 +165,7 @@ def test_cuda_every_shipped_level_full_catalog(ref_lib, bt, level):
 
 
 # ---- shipped levels whose tick handlers all have device bodies: the FULL game tick on the device ----
-TICK_LEVELS = ["tower", "forest", "speed", "blank", "lights"]
+TICK_LEVELS = ["tower", "forest", "speed", "blank", "lights", "arena"]   # arena: + HELD_GUN (never held here), SCOREBOARD
 EFFECT_BLOCKS = 4   # createDebris (effects.cpp:99-150) spawns platforms from gs->rand: host side, switched off here
 
 
@@ -179,13 +179,22 @@ def _device_tick_level(R, level, seed, maxv):
     return wid
 
 
-def _run_tick_level(R, level, make, step_hash, maxv, ticks):
+def _run_tick_level(R, level, make, step_hash, maxv, ticks, reload=None):
     wid = _device_tick_level(R, level, 5, maxv)
     w = make(R.export())
     n0 = R.count()[0]
+    reloads = 0
     for t in range(ticks):
         R.step(0)                                  # the reference's whole doWholeStep (main.cpp:1019-1097)
+        if reload is not None and reload(w):
+            # the scoreboard ended the round in the tick before (arena.sav without players: a tie after 70 ticks, everything
+            # erased, scoreboard.cpp:81-86); requestReload is the host's: the reference has just reloaded the level
+            w.upload(R.export())
+            reloads += 1
+            continue
         assert step_hash(w) == R.hash(), (level, t)
+    if reload is not None and level == "arena":
+        assert reloads >= 1
     n1 = R.count()[0]
     R.free_world(wid)
     return w, n0, n1
@@ -209,8 +218,12 @@ def test_emu_levels_with_device_tick_handlers(ref_lib, emu, level, maxv):
 @pytest.mark.parametrize("level,maxv", TICK_CASES)
 def test_cuda_levels_with_device_tick_handlers(ref_lib, bt, level, maxv):
     """bt_world_tick alone = doWholeStep of the unmodified reference, tick handlers and world rules included"""
-    w, n0, n1 = _run_tick_level(ref_lib, level, lambda wa: bt.World(wa), lambda w: int(w.tick(1, hashes=True)[0, 0]),
-                                maxv, 150)
+    def round_over(w):   # the device reports the tick handler whose effect is the host's: kind 6, TICK_SCOREBOARD
+        return any(ev["kind"] == 6 and ev["handler"] == 27 for ev in w.drain_events())
+    def make(wa):   # room for what a reloaded level may hold beyond the kicked one's survivors
+        return bt.World(wa, max_ents=wa.n + 64, max_sliders=int(wa.desc.n_sliders) + 512, max_wires=int(wa.desc.n_wires) + 256)
+    w, n0, n1 = _run_tick_level(ref_lib, level, make, lambda w: int(w.tick(1, hashes=True)[0, 0]),
+                                maxv, 150, reload=round_over)
     st = w.stats()
     assert st["unsupported_events"] == 0 and st["live_ents"] == n1
     w.close()
