@@ -55,7 +55,11 @@ static BT_HD int bt_clz32(u32 x) { return __clz((int)x); }
 static BT_HD int bt_clz64(u64 x) { return __clzll((long long)x); }
 static BT_HD int bt_abs(int x) { return x < 0 ? -x : x; }
 /* start a line on its way to L1 without waiting for it */
+#ifdef BT_NO_PREFETCH /* bt_small.cu: the arrays it would touch are staged in shared memory there */
+static BT_HD void bt_prefetch(const void *) {}
+#else
 static BT_HD void bt_prefetch(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+#endif
 #endif
 
 struct LocalStats {

@@ -13,6 +13,11 @@
  *                       whenever a push leaves its box (bt_check_cover); the list lives in shared memory too
  *   serial lane, dead list, events, pending-wire pool = shared-memory lists; deaths and events are appended to the
  *                       world-wide lists (one atomic per block that has any) when the step ends
+ *   entity state      = the arrays the resolution loop lives on (SW_STAGED below: geometry, masks, hold tree, pending
+ *                       collision, flags; 165 B per entity) are copied into shared memory when the step begins and
+ *                       back when it ends; in between W.center etc. point INTO shared memory, offset by -wbegin[g] so
+ *                       that the bodies keep indexing them by slot: a world's gathers cost a shared-memory access
+ *                       instead of an L2 / HBM round trip per hop
  *
  * Results are those of the generic schedule bit for bit (the proposals are CAS-maxima, pushes of one iteration own
  * their trees, the serial lane runs in canonical order: none of it depends on which worlds share a launch).
@@ -28,6 +33,7 @@
  * there are not only the spills are left.  bt_launch_tick_small picks by the number of worlds.
  */
 #define BT_KERNEL_HELPERS_ONLY
+#define BT_NO_PREFETCH
 #include "bt_kernels.cuh"
 #include "bt_small.h"
 
@@ -38,6 +44,12 @@
 #error "compile with -DSW_BS=64|128 -DSW_MIN_WARPS=16|32 (bittoss_b200/capi.py: build)"
 #endif
 #define BS SW_BS
+/* Two regimes (measured on arena.sav worlds, ms per tick once the kicks have died down, unstaged at 32 warps / staged
+ * at 16): 8192 worlds 0.234 / 0.286, 1024 worlds 0.081 / 0.062.  With enough worlds to fill every SM the other
+ * blocks hide a world's memory latency and what counts is how many fit (the staged arrays take 10 KB per 64 entities,
+ * the copies in and out triple the traffic); with fewer, a world's chain of dependent gathers is the step time and
+ * shared memory cuts every hop.  So the 16-warp variant stages, the 32-warp variant does not. */
+#define SW_STAGE (SW_MIN_WARPS == 16)
 #define SW_CAT3(a, b, c) a##b##_##c
 #define SW_NAME(prefix, bs, w) SW_CAT3(prefix, bs, w)
 #define k_tick_small SW_NAME(k_tick_small_, SW_BS, SW_MIN_WARPS)
@@ -69,6 +81,23 @@ __global__ void __launch_bounds__(BS, SW_MIN_WARPS * 32 / BS) k_tick_small(DevWo
 	const i32 b0 = W.wbegin[g], cnt = W.wend[g] - b0;
 	const i32 e = b0 + i;
 	const bool mine = i < cnt; /* threads past the world's last slot only take part in the barriers */
+	/* the staged arrays: in, and W pointed at the copies (slot e of the world = element e - b0) */
+#define SW_STAGED(X)                                                                                        \
+	X(int4, center) X(int4, old) X(int4, vel) X(int4, radius) X(int4, forcedHoldees) X(Box6, ibox) X(u64, pend) \
+	X(u32, type) X(u32, collide) X(u32, hphys) X(u32, forced)                                               \
+	X(i32, holdRoot) X(i32, holder) X(i32, holdee) X(i32, LLn) X(i32, LLp) X(i32, holdFlags) X(i32, friction) \
+	X(u8, inList) X(u8, needsCollision) X(u8, hasBox) X(u8, ready) X(u8, dead)
+#if SW_STAGE
+#define SW_DECL(T, name) __shared__ T s_##name[BS]; T *const g_##name = W.name;
+#define SW_IN(T, name) if (mine) s_##name[i] = g_##name[e]; W.name = s_##name - b0;
+#define SW_OUT(T, name) if (mine) g_##name[e] = s_##name[i];
+#else
+#define SW_DECL(T, name)
+#define SW_IN(T, name)
+#define SW_OUT(T, name)
+#endif
+	SW_STAGED(SW_DECL)
+	SW_STAGED(SW_IN)
 	const i32 rp0 = W.root_phase;
 	/* row i of the cyclic balanced triangle of k_pairs_small: j = i + 1 .. i + kmax (mod cnt) sees every unordered pair once */
 	const int kmax = (cnt - 1) / 2 + (((cnt & 1) == 0 && i < cnt / 2) ? 1 : 0);
@@ -236,6 +265,7 @@ __global__ void __launch_bounds__(BS, SW_MIN_WARPS * 32 / BS) k_tick_small(DevWo
 	__syncthreads();
 
 	/* ---- what the rest of the library has to see ---- */
+	SW_STAGED(SW_OUT)
 	u32 live = 0;
 	if (phases & BT_PHASE_FINISH) live = (u32)__syncthreads_count(mine && W.inList[e]); /* clearDeads ent.cpp:471-481 */
 	if (i == 0) {
