@@ -189,7 +189,9 @@ def _run_tick_level(R, level, make, step_hash, maxv, ticks, reload=None):
         if reload is not None and reload(w):
             # the scoreboard ended the round in the tick before (arena.sav without players: a tie after 70 ticks, everything
             # erased, scoreboard.cpp:81-86); requestReload is the host's: the reference has just reloaded the level
-            w.upload(R.export())
+            if hasattr(w, "close"):
+                w.close()
+            w = make(R.export())
             reloads += 1
             continue
         assert step_hash(w) == R.hash(), (level, t)
@@ -209,8 +211,10 @@ def test_emu_levels_with_device_tick_handlers(ref_lib, emu, level, maxv):
     def step_hash(w):
         w.step(31 | TICKS | 32)
         return w.hash()[0]
+    def round_over(w):   # kind 6 = a tick handler whose effect is the host's: TICK_SCOREBOARD asks for the level to be reloaded
+        return any(ev["kind"] == 6 and ev["handler"] == 27 for ev in w.drain_events())
     w, n0, n1 = _run_tick_level(ref_lib, level, lambda wa: emu.EmuWorld(wa, rebuild_every=4, shuffle_seed=9),
-                                step_hash, maxv, 60)
+                                step_hash, maxv, 60 if level != "arena" else 80, reload=round_over)
     assert w.unsupported() == 0
 
 
@@ -220,9 +224,7 @@ def test_cuda_levels_with_device_tick_handlers(ref_lib, bt, level, maxv):
     """bt_world_tick alone = doWholeStep of the unmodified reference, tick handlers and world rules included"""
     def round_over(w):   # the device reports the tick handler whose effect is the host's: kind 6, TICK_SCOREBOARD
         return any(ev["kind"] == 6 and ev["handler"] == 27 for ev in w.drain_events())
-    def make(wa):   # room for what a reloaded level may hold beyond the kicked one's survivors
-        return bt.World(wa, max_ents=wa.n + 64, max_sliders=int(wa.desc.n_sliders) + 512, max_wires=int(wa.desc.n_wires) + 256)
-    w, n0, n1 = _run_tick_level(ref_lib, level, make, lambda w: int(w.tick(1, hashes=True)[0, 0]),
+    w, n0, n1 = _run_tick_level(ref_lib, level, lambda wa: bt.World(wa), lambda w: int(w.tick(1, hashes=True)[0, 0]),
                                 maxv, 150, reload=round_over)
     st = w.stats()
     assert st["unsupported_events"] == 0 and st["live_ents"] == n1
