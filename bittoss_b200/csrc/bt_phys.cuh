@@ -1605,13 +1605,14 @@ static BT_HD void t_post(const DevWorld &W, i32 e) {
 enum {
 	TICK_RAND = 6, TICK_LOGIC = 11, TICK_LOGIC_DEBUG = 12, TICK_DOOR = 13, TICK_CURSED = 14, TICK_RESPAWN = 15,
 	TICK_SEAT_OLD = 17, TICK_ADJUST = 19, TICK_SEAT = 23, TICK_HELD_GUN = 24, TICK_SCOREBOARD = 27, TICK_TIMER = 28,
-	TICK_DEMOLISH = 29, TICK_SIGN = 34
+	TICK_DEMOLISH = 29, TICK_HELD_BLINK = 30, TICK_HELD_JUMPER = 31, TICK_SPIDER = 33, TICK_SIGN = 34, TICK_LOADBLOCK = 35, TICK_PUDDLEJUMP = 36
 };
 /* NIL + the ids above */
 #define BT_SUPPORTED_TICK ((1ull << 0) | (1ull << TICK_RAND) | (1ull << TICK_LOGIC) | (1ull << TICK_LOGIC_DEBUG) | \
 	(1ull << TICK_DOOR) | (1ull << TICK_CURSED) | (1ull << TICK_RESPAWN) | (1ull << TICK_SEAT_OLD) |                  \
 	(1ull << TICK_ADJUST) | (1ull << TICK_SEAT) | (1ull << TICK_TIMER) | (1ull << TICK_DEMOLISH) | (1ull << TICK_SIGN) | \
-	(1ull << TICK_HELD_GUN) | (1ull << TICK_SCOREBOARD))
+	(1ull << TICK_HELD_GUN) | (1ull << TICK_SCOREBOARD) | (1ull << TICK_HELD_BLINK) | (1ull << TICK_HELD_JUMPER) |        \
+	(1ull << TICK_LOADBLOCK) | (1ull << TICK_PUDDLEJUMP) | (1ull << TICK_SPIDER))
 
 static BT_HD int bt_button(const DevWorld &W, i32 e, int i) { return (int)(int8_t)((W.btn_v[e] >> (8 * i)) & 0xffu); }
 static BT_HD void bt_push_btn(const DevWorld &W, i32 e, int i) { bt_or32(&W.btn_v2[e], 1u << (8 * i)); }
@@ -1763,8 +1764,97 @@ static BT_HD void t_tick(const DevWorld &W, i32 me) {
 				if (bt_button(W, w, i)) bt_push_btn(W, me, i);
 		}
 		return;
-	case TICK_HELD_GUN: { /* gun_tick_held gun.c:41-88: "doesn't do anything unless held by a person (or similar)".  Held by
-	                       * one, it reads the holder's trigger (host-side control state) and creates bullets: not here */
+	case TICK_SPIDER: { /* spider_tick spider.cpp:58-122 (a leg: tickHeld): a spring towards where the gait wants the foot,
+	                     * the reaction on the body; several legs add to one body, so uVel is an atomic add here */
+		const i32 h = W.holder[me];
+		if (h < 0) return;
+		const i32 height_top = bt_getslider(W, me, 0), height_bottom = bt_getslider(W, me, 1), width = bt_getslider(W, me, 2);
+		const i32 t_top = bt_getslider(W, me, 3), t_bottom = bt_getslider(W, me, 4);
+		i32 counter = bt_getslider(W, me, 5), spring = bt_getslider(W, me, 6), ratio_legs = bt_getslider(W, me, 9);
+		const i32 drag = bt_getslider(W, me, 7), a_max = bt_getslider(W, me, 8);
+		if (spring <= 0) spring = 1;
+		if (ratio_legs <= 0) ratio_legs = 1;
+		i32 v1[3] = {0, 0, 0}, vel[3] = {0, 0, 0};
+		for (i32 k = 0; k < W.wire_cnt[me]; k++) { /* getInput :30-39 */
+			const i32 w = W.wire_to[W.wire_off[me] + k];
+			v1[0] += bt_getslider(W, w, 0) * width / 64;
+			v1[1] += bt_getslider(W, w, 1) * width / 64;
+		}
+		const int hasInput = v1[0] || v1[1];
+		v1[2] = height_bottom;
+		const i32 t_cycle = t_top + t_bottom;
+		if (hasInput && t_cycle) {
+			counter++;
+			while (counter >= t_cycle) counter -= t_cycle;
+			bt_uslider_shared(W, me, 5, counter);
+			i32 numer, denom;
+			if (counter >= t_bottom) { v1[2] = height_top; denom = t_top; numer = counter - t_bottom; }
+			else { v1[0] *= -1; v1[1] *= -1; denom = t_bottom; numer = counter; }
+			for (int i = 0; i < 2; i++) vel[i] = v1[i] / denom;
+			for (int i = 0; i < 2; i++) v1[i] = (2 * numer - denom) * v1[i] / denom;
+		}
+		{ /* computeAccel :41-56 */
+			const int4 mc = W.center[me], hc = W.center[h], mv = W.vel[me], hv = W.vel[h];
+			const i32 cp[3] = {mc.x - hc.x, mc.y - hc.y, mc.z - hc.z}, cv[3] = {mv.x - hv.x, mv.y - hv.y, mv.z - hv.z};
+			for (int i = 0; i < 3; i++) v1[i] = (v1[i] - cp[i]) * 64 / spring;
+			bt_bound_vec(v1, a_max, 3);
+			for (int i = 0; i < 3; i++) vel[i] -= cv[i];
+			bt_bound_vec(vel, drag, 3);
+		}
+		i32 a[3];
+		for (int i = 0; i < 3; i++) a[i] = (v1[i] + vel[i]) / -ratio_legs;
+		const i32 r = W.holdRoot[me];
+		i32 *dr = (i32 *)&W.d_vel[r], *dm = (i32 *)&W.d_vel[me];
+		for (int i = 0; i < 3; i++) bt_add32((u32 *)&dr[i], (u32)a[i]);              /* uVel(me->holdRoot, a) */
+		for (int i = 0; i < 3; i++) bt_add32((u32 *)&dm[i], (u32)(a[i] * -ratio_legs)); /* uVel(me, a) */
+		W.ctr[CT_ANY_DELTA] = 1;
+		return;
+	}
+	case TICK_LOADBLOCK: { /* loadblock_tick loadblock.cpp:33-36 */
+		i32 cooldown = bt_getslider(W, me, 1);
+		if (cooldown > 0) bt_uslider_shared(W, me, 1, cooldown - 1);
+		return;
+	}
+	case TICK_PUDDLEJUMP: { /* pj_tick puddlejumper.cpp:94-162.  The pilot's controls arrive through the wired seat as
+	                         * sliders (getAxis = sliders 0 / 1, player.c:48-51) and buttons (getTrigger(e, i) = button i + 2,
+	                         * entGetters.c:27-29).  Vertical thrust makes dust (mkDust creates entities): host side */
+		i32 dvel[3] = {0, 0, 16};
+		const int flying = !bt_getslider(W, me, 4);
+		bt_uslider_shared(W, me, 4, 0);
+		const i32 fuel = bt_getslider(W, me, 0);
+		if (fuel && flying) bt_uslider_shared(W, me, 0, fuel - 1);
+		if (W.wire_cnt[me] == 1) {
+			const i32 input = W.wire_to[W.wire_off[me]];
+			if (fuel && bt_button(W, input, 2)) { bt_unsup(W, me, 6, id); dvel[2] = -8; }
+			const i32 axis[2] = {bt_getslider(W, input, 0), bt_getslider(W, input, 1)};
+			if (axis[0] || axis[1]) {
+				const i32 sl[2] = {bt_getslider(W, me, 2), bt_getslider(W, me, 3)};
+				const int signX = 2 * (axis[0] >= 0) - 1, signY = 2 * (axis[1] >= 0) - 1;
+				i32 denomX = signX * axis[0], numerX = 200 - signX * sl[0]; /* PJ_SPD */
+				i32 denomY = signY * axis[1], numerY = 200 - signY * sl[1];
+				if (numerX > 20) numerX = 20; else if (numerX < 0) numerX = 0; /* PJ_ACCEL */
+				if (numerY > 20) numerY = 20; else if (numerY < 0) numerY = 0;
+				if (denomY && numerY * denomX <= numerX * denomY) { numerX = numerY; denomX = denomY; }
+				for (int k = 0; k < 2; k++) {
+					dvel[k] = numerX * axis[k] / denomX;
+					bt_uslider_shared(W, me, 2 + k, sl[k] + dvel[k]);
+					dvel[k] += axis[k] / 16;
+				}
+				bt_uslider_shared(W, me, 5, numerX ? 2 : 1);
+			} else {
+				bt_uslider_shared(W, me, 5, 0);
+			}
+		}
+		int4 dv = W.d_vel[me]; /* uVel(me, dvel) */
+		dv.x += dvel[0]; dv.y += dvel[1]; dv.z += dvel[2];
+		W.d_vel[me] = dv;
+		W.ctr[CT_ANY_DELTA] = 1;
+		return;
+	}
+	case TICK_HELD_GUN: case TICK_HELD_BLINK: case TICK_HELD_JUMPER: {
+		/* gun_tick_held gun.c:41-88, blink_tick_held blink.c:33-60, jumper_tick_held jumper.c:39-70: "doesn't do anything
+		 * unless held by a person (or similar)".  Held by one, they read the holder's trigger (host-side control state)
+		 * and create bullets / dust: not here */
 		const i32 h = W.holder[me];
 		if (h < 0 || !(W.type[h] & T_INPUTS) || W.holder[h] >= 0) return;
 		bt_unsup(W, me, 6, id);

@@ -1349,7 +1349,8 @@ static void worldRules(World *w, int g) {
  * Run one entity after the other in gs->ents order (newest first), like the reference. ---- */
 enum {
 	TICK_RAND = 6, TICK_LOGIC = 11, TICK_LOGIC_DEBUG = 12, TICK_DOOR = 13, TICK_CURSED = 14, TICK_RESPAWN = 15,
-	TICK_SEAT_OLD = 17, TICK_ADJUST = 19, TICK_SEAT = 23, TICK_SCOREBOARD = 27, TICK_TIMER = 28, TICK_DEMOLISH = 29, TICK_SIGN = 34
+	TICK_SEAT_OLD = 17, TICK_ADJUST = 19, TICK_SEAT = 23, TICK_SCOREBOARD = 27, TICK_TIMER = 28, TICK_DEMOLISH = 29, TICK_SIGN = 34,
+	TICK_LOADBLOCK = 35, TICK_PUDDLEJUMP = 36, TICK_SPIDER = 33
 };
 static int getButton(const World *w, i32 e, int i) { return (int)(signed char)w->btn[e][i]; }
 static void pushBtn(World *w, i32 e, int i) { w->btn[e][4 + i] = 1; }
@@ -1462,6 +1463,75 @@ static void tickOne(World *w, int g, i32 me) {
 				if (getButton(w, x, i)) pushBtn(w, me, i);
 		}
 		break;
+	case TICK_SPIDER: { /* spider.cpp:58-122 */
+		i32 h = w->holder[me];
+		if (h < 0) break;
+		i32 height_top = getSlider(w, me, 0), height_bottom = getSlider(w, me, 1), width = getSlider(w, me, 2);
+		i32 t_top = getSlider(w, me, 3), t_bottom = getSlider(w, me, 4), counter = getSlider(w, me, 5);
+		i32 spring = getSlider(w, me, 6), drag = getSlider(w, me, 7), a_max = getSlider(w, me, 8), ratio_legs = getSlider(w, me, 9);
+		if (spring <= 0) spring = 1;
+		if (ratio_legs <= 0) ratio_legs = 1;
+		i32 v1[3] = {0, 0, 0}, vel[3] = {0, 0, 0}, a[3];
+		for (int k = 0; k < w->wires[me].num; k++)
+			for (int i = 0; i < 2; i++) v1[i] += getSlider(w, w->wires[me].items[k], i) * width / 64;
+		int hasInput = v1[0] || v1[1];
+		v1[2] = height_bottom;
+		i32 t_cycle = t_top + t_bottom;
+		if (hasInput && t_cycle) {
+			counter++;
+			while (counter >= t_cycle) counter -= t_cycle;
+			uSlider(w, me, 5, counter);
+			i32 numer, denom;
+			if (counter >= t_bottom) { v1[2] = height_top; denom = t_top; numer = counter - t_bottom; }
+			else { v1[0] *= -1; v1[1] *= -1; denom = t_bottom; numer = counter; }
+			for (int i = 0; i < 2; i++) vel[i] = v1[i] / denom;
+			for (int i = 0; i < 2; i++) v1[i] = (2 * numer - denom) * v1[i] / denom;
+		}
+		for (int i = 0; i < 3; i++) v1[i] = (v1[i] - (w->center[me][i] - w->center[h][i])) * 64 / spring;
+		boundVec(v1, a_max, 3);
+		for (int i = 0; i < 3; i++) vel[i] -= w->vel[me][i] - w->vel[h][i];
+		boundVec(vel, drag, 3);
+		for (int i = 0; i < 3; i++) a[i] = (v1[i] + vel[i]) / -ratio_legs;
+		for (int i = 0; i < 3; i++) w->d_vel[w->holdRoot[me]][i] += a[i];
+		for (int i = 0; i < 3; i++) w->d_vel[me][i] += a[i] * -ratio_legs;
+		break;
+	}
+	case TICK_LOADBLOCK: { /* loadblock.cpp:33-36 */
+		i32 cooldown = getSlider(w, me, 1);
+		if (cooldown > 0) uSlider(w, me, 1, cooldown - 1);
+		break;
+	}
+	case TICK_PUDDLEJUMP: { /* puddlejumper.cpp:94-162; vertical thrust (dust: entity creation) is the host's */
+		i32 dvel[3] = {0, 0, 16};
+		int flying = !getSlider(w, me, 4);
+		uSlider(w, me, 4, 0);
+		i32 fuel = getSlider(w, me, 0);
+		if (fuel && flying) uSlider(w, me, 0, fuel - 1);
+		if (w->wires[me].num == 1) {
+			i32 input = w->wires[me].items[0];
+			if (fuel && getButton(w, input, 2)) dvel[2] = -8; /* getTrigger(input, 0) entGetters.c:27-29 */
+			i32 axis[2] = {getSlider(w, input, 0), getSlider(w, input, 1)}; /* getAxis player.c:48-51 */
+			if (axis[0] || axis[1]) {
+				i32 sl[2] = {getSlider(w, me, 2), getSlider(w, me, 3)};
+				int signX = 2 * (axis[0] >= 0) - 1, signY = 2 * (axis[1] >= 0) - 1;
+				i32 denomX = signX * axis[0], numerX = 200 - signX * sl[0];
+				i32 denomY = signY * axis[1], numerY = 200 - signY * sl[1];
+				if (numerX > 20) numerX = 20; else if (numerX < 0) numerX = 0;
+				if (numerY > 20) numerY = 20; else if (numerY < 0) numerY = 0;
+				if (denomY && numerY * denomX <= numerX * denomY) { numerX = numerY; denomX = denomY; }
+				for (int k = 0; k < 2; k++) {
+					dvel[k] = numerX * axis[k] / denomX;
+					uSlider(w, me, 2 + k, sl[k] + dvel[k]);
+					dvel[k] += axis[k] / 16;
+				}
+				uSlider(w, me, 5, numerX ? 2 : 1);
+			} else {
+				uSlider(w, me, 5, 0);
+			}
+		}
+		for (int k = 0; k < 3; k++) w->d_vel[me][k] += dvel[k]; /* uVel */
+		break;
+	}
 	case TICK_SCOREBOARD: { /* scoreboard.cpp:37-90 with gs->players.num == 0: alive == 0 */
 		i32 timer = getSlider(w, me, 1);
 		if (getSlider(w, me, 0) != 0) { uSlider(w, me, 0, 0); timer = 75; }

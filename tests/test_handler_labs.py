@@ -165,7 +165,7 @@ def test_cuda_every_shipped_level_full_catalog(ref_lib, bt, level):
 
 
 # ---- shipped levels whose tick handlers all have device bodies: the FULL game tick on the device ----
-TICK_LEVELS = ["tower", "forest", "speed", "blank", "lights", "arena"]   # arena: + HELD_GUN (never held here), SCOREBOARD
+TICK_LEVELS = ["tower", "forest", "speed", "blank", "lights", "arena", "lobby", "spider"]   # arena: + HELD_GUN (never held here), SCOREBOARD; lobby: + blink, jumper, loadblock, puddlejumper; spider: + its legs
 EFFECT_BLOCKS = 4   # createDebris (effects.cpp:99-150) spawns platforms from gs->rand: host side, switched off here
 
 
@@ -216,6 +216,15 @@ def test_emu_levels_with_device_tick_handlers(ref_lib, emu, level, maxv):
     w, n0, n1 = _run_tick_level(ref_lib, level, lambda wa: emu.EmuWorld(wa, rebuild_every=4, shuffle_seed=9),
                                 step_hash, maxv, 60 if level != "arena" else 80, reload=round_over)
     assert w.unsupported() == 0
+
+
+@pytest.mark.parametrize("level,maxv", TICK_CASES)
+def test_oracle_levels_with_device_tick_handlers(ref_lib, oracle_lib, level, maxv):
+    """the plain-C restatement of the same tick handlers against the reference's whole doWholeStep"""
+    def step_hash(w):
+        w.step(31 | TICKS | 32)
+        return w.hash()[0]
+    _run_tick_level(ref_lib, level, lambda wa: oracle_lib.create(wa), step_hash, maxv, 60)
 
 
 @pytest.mark.gpu
