@@ -244,7 +244,60 @@ def lab_rootorder(R):
 
 # builders return ticks, or (ticks, script[, btref step mode]) with script rows (tick, kind, uid, other, a0[, a1, a2])
 # applied before that tick's step; kind = BT_REQ_* (0 uDrop, 1 uDead, 2 uPickup(uid, other, a0), 3 pushBtn(uid, a0), ...)
+TICK_SPIDER, TICK_LOADBLOCK, TICK_PUDDLEJUMP, TICK_HELD_GUN, TICK_HELD_BLINK, TICK_HELD_JUMPER = 33, 35, 36, 24, 30, 31
+PUSHED_PUDDLEJUMP = 1
+REQ_PICKUP, REQ_SLIDER = 2, 6
+
+
+def lab_pilots(R):
+    """FULL ticks: the tick handlers that read a pilot's controls (sliders and buttons of a wired entity: getAxis =
+    sliders 0 / 1, player.c:48-51): a puddlejumper steered around over a pad by a scripted input block (its fuel runs
+    out on the way), a two-legged spider walking its body across a floor, a loadblock cooling down, and a gun / blink
+    / jumper held by a cube WITHOUT inputs (their tickHeld handlers do nothing then).  Scripted uSlider calls on the
+    input blocks play the pilot."""
+    script = []
+    # puddlejumper: falls 16 per tick per tick unless grounded; pushed handler tracks grounded / slide velocity
+    pad(R, 0, 0, r=(6000, 6000, 300), z=400)
+    pj = R.add_ent((0, 0, -700), (0, 0, 0), (400, 400, 300), CUBE, CUBE_COLLIDE, WM_WOOD)
+    R.lab_set_handlers(pj, push=PUSH_PUDDLEJUMP, pushed=PUSHED_PUDDLEJUMP, tick=TICK_PUDDLEJUMP)
+    R.lab_set_sliders(pj, [30, 4000, 0, 0, 1, 0])
+    stick = gate(R, 0, 0, -5000, 0, [0, 0, 0, 0, 0, 0])
+    R.lab_add_wire(pj, stick)
+    for t, (ax, ay) in ((3, (64, 0)), (12, (64, -40)), (25, (-10, 64)), (40, (0, 0)), (55, (-64, -64)), (70, (5, 0))):
+        script += [(t, REQ_SLIDER, stick, -1, 0, ax, 0), (t, REQ_SLIDER, stick, -1, 1, ay, 0)]
+    # a second one without a pilot, airborne: burns its fuel, sinks
+    pj2 = R.add_ent((3000, 3000, -4000), (0, 0, 0), (400, 400, 300), CUBE, CUBE_COLLIDE, WM_WOOD)
+    R.lab_set_handlers(pj2, push=PUSH_PUDDLEJUMP, pushed=PUSHED_PUDDLEJUMP, tick=TICK_PUDDLEJUMP)
+    R.lab_set_sliders(pj2, [12, 4000, 0, 0, 0, 0])
+    # spider: a body on a floor holds two legs (tickHeld) wired to one input block
+    pad(R, 20000, 0, r=(8000, 8000, 300), z=400)
+    body = cube(R, 20000, 0, -1100, r=500)
+    walk = gate(R, 20000, 0, -6000, 0, [0, 0])
+    legs = []
+    for k, dx in enumerate((-700, 700)):
+        leg = R.add_ent((20000 + dx, 0, -500), (0, 0, 0), (150, 150, 150), CUBE, CUBE_COLLIDE, WM_WOOD)
+        R.lab_set_handlers(leg, tick_held=TICK_SPIDER)
+        # d1, d2, scale, t1, t2, t, spring, drag, max accel, ratio
+        R.lab_set_sliders(leg, [300, 600, 400, 6, 10, 3 * k, 8, 30, 60, 2])
+        R.lab_add_wire(leg, walk)
+        legs.append(leg)
+        script.append((0, REQ_PICKUP, body, leg, HOLD_MOVE, 0, 0))
+    for t, (ax, ay) in ((5, (64, 0)), (30, (30, 50)), (50, (0, 0)), (60, (-64, 20))):
+        script += [(t, REQ_SLIDER, walk, -1, 0, ax, 0), (t, REQ_SLIDER, walk, -1, 1, ay, 0)]
+    # loadblock cooling down; equipment held by a cube that has no inputs
+    lb = gate(R, -8000, 0, -3000, TICK_LOADBLOCK, [3, 9])
+    pad(R, -8000, 4000)
+    holder = cube(R, -8000, 4000, -800)
+    for k, th in enumerate((TICK_HELD_GUN, TICK_HELD_BLINK, TICK_HELD_JUMPER)):
+        it = R.add_ent((-8000 + 300 * k, 4000, -1500), (0, 0, 0), (100, 100, 100), CUBE | T_EQUIP_SM, CUBE_COLLIDE, WM_WOOD)
+        R.lab_set_handlers(it, tick_held=th)
+        R.lab_set_sliders(it, [0, 5, 1, 0, 10, 3, 45, 14000])
+        script.append((1, REQ_PICKUP, holder, it, HOLD_MOVE, 0, 0))
+    return 90, script, 0
+
+
 LABS = {
+    "lab_pilots": lab_pilots,
     "lab_teleport": lab_teleport,
     "lab_bottles": lab_bottles,
     "lab_seats": lab_seats,
