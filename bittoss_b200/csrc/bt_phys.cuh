@@ -1603,7 +1603,7 @@ static BT_HD void t_post(const DevWorld &W, i32 e) {
  * min/max, uVel = add, uDead = OR, uDrop), so every entity can run its handler at the same time.
  * TICK_RAND draws from gs->rand and therefore runs per world, in list order (t_tick_serial). */
 enum {
-	TICK_RAND = 6, TICK_LOGIC = 11, TICK_LOGIC_DEBUG = 12, TICK_DOOR = 13, TICK_CURSED = 14, TICK_RESPAWN = 15,
+	TICK_RAND = 6, TICK_EYE = 8, TICK_HELD_EYE = 9, TICK_HELD_VEH_EYE = 18, TICK_LOGIC = 11, TICK_LOGIC_DEBUG = 12, TICK_DOOR = 13, TICK_CURSED = 14, TICK_RESPAWN = 15,
 	TICK_SEAT_OLD = 17, TICK_ADJUST = 19, TICK_SEAT = 23, TICK_HELD_GUN = 24, TICK_SCOREBOARD = 27, TICK_TIMER = 28,
 	TICK_DEMOLISH = 29, TICK_HELD_BLINK = 30, TICK_HELD_JUMPER = 31, TICK_SPIDER = 33, TICK_SIGN = 34, TICK_LOADBLOCK = 35, TICK_PUDDLEJUMP = 36
 };
@@ -1612,7 +1612,8 @@ enum {
 	(1ull << TICK_DOOR) | (1ull << TICK_CURSED) | (1ull << TICK_RESPAWN) | (1ull << TICK_SEAT_OLD) |                  \
 	(1ull << TICK_ADJUST) | (1ull << TICK_SEAT) | (1ull << TICK_TIMER) | (1ull << TICK_DEMOLISH) | (1ull << TICK_SIGN) | \
 	(1ull << TICK_HELD_GUN) | (1ull << TICK_SCOREBOARD) | (1ull << TICK_HELD_BLINK) | (1ull << TICK_HELD_JUMPER) |        \
-	(1ull << TICK_LOADBLOCK) | (1ull << TICK_PUDDLEJUMP) | (1ull << TICK_SPIDER))
+	(1ull << TICK_LOADBLOCK) | (1ull << TICK_PUDDLEJUMP) | (1ull << TICK_SPIDER) | (1ull << TICK_EYE) |                  \
+	(1ull << TICK_HELD_EYE) | (1ull << TICK_HELD_VEH_EYE))
 
 static BT_HD int bt_button(const DevWorld &W, i32 e, int i) { return (int)(int8_t)((W.btn_v[e] >> (8 * i)) & 0xffu); }
 static BT_HD void bt_push_btn(const DevWorld &W, i32 e, int i) { bt_or32(&W.btn_v2[e], 1u << (8 * i)); }
@@ -1764,6 +1765,56 @@ static BT_HD void t_tick(const DevWorld &W, i32 me) {
 				if (bt_button(W, w, i)) bt_push_btn(W, me, i);
 		}
 		return;
+	case TICK_EYE: /* eye_tick eyes.cpp:14-22: the first tick an eye is NOT held it becomes debris and retires its handler
+	                * ("it's fine to set this directly in a tick handler": a direct write, visible to this tick's hash) */
+		W.fullFlush[me] = 1;
+		W.ntype[me] = W.type[me] | T_DEBRIS;
+		W.ncollide[me] = W.collide[me] | T_TERRAIN | T_OBSTACLE | T_DEBRIS;
+		W.htick[me] = ht & ~0xffu;
+		W.ctr[CT_FLUSH_HINT] = 1;
+		return;
+	case TICK_HELD_EYE: { /* eye_tick_held eyes.cpp:24-47: sits on the holder's surface where the holder looks (getLook =
+	                       * sliders 2..4, player.c:53-57) */
+		const i32 p = W.holder[me];
+		if (p < 0) return;
+		i32 vec[3] = {bt_getslider(W, p, 2), bt_getslider(W, p, 3), bt_getslider(W, p, 4)};
+		const int4 pr = W.radius[p], pc = W.center[p], pv = W.vel[p], mc = W.center[me], mv = W.vel[me];
+		const i32 rad[3] = {pr.x, pr.y, pr.z};
+		i32 component = bt_abs(vec[2]), r = rad[2] - 50; /* eyeInset */
+		for (int i = 0; i < 2; i++) {
+			const i32 i_comp = bt_abs(vec[i]), i_r = rad[i] - 50;
+			if (i_comp * r > component * i_r) { r = i_r; component = i_comp; }
+		}
+		if (!component) return;
+		const i32 pos[3] = {mc.x - pc.x, mc.y - pc.y, mc.z - pc.z}, vel[3] = {mv.x - pv.x, mv.y - pv.y, mv.z - pv.z};
+		int4 dv = W.d_vel[me]; /* uVel(me, vec) */
+		dv.x += r * vec[0] / component - pos[0] - vel[0];
+		dv.y += r * vec[1] / component - pos[1] - vel[1];
+		dv.z += r * vec[2] / component - pos[2] - vel[2];
+		W.d_vel[me] = dv;
+		W.ctr[CT_ANY_DELTA] = 1;
+		return;
+	}
+	case TICK_HELD_VEH_EYE: { /* vehicle_eye_tick_held eyes.cpp:49-66: wired to a seat that is wired to (at most) a pilot */
+		const i32 p = W.holder[me];
+		if (p < 0) return;
+		i32 vec[3] = {0, 0, 0};
+		for (i32 k = 0; k < W.wire_cnt[me]; k++) {
+			const i32 w = W.wire_to[W.wire_off[me] + k];
+			for (i32 j = 0; j < W.wire_cnt[w]; j++) {
+				const i32 e2 = W.wire_to[W.wire_off[w] + j];
+				vec[0] += bt_getslider(W, e2, 0); vec[1] += bt_getslider(W, e2, 1); /* getAxis */
+			}
+		}
+		const int4 pr = W.radius[p], pc = W.center[p], mc = W.center[me];
+		int4 dc = W.d_center[me]; /* uCenter(me, vec) */
+		dc.x += vec[0] * pr.x / 64 - (mc.x - pc.x);
+		dc.y += vec[1] * pr.y / 64 - (mc.y - pc.y);
+		dc.z += vec[2] * pr.z / 64 - (mc.z - pc.z);
+		W.d_center[me] = dc;
+		W.ctr[CT_ANY_DELTA] = 1;
+		return;
+	}
 	case TICK_SPIDER: { /* spider_tick spider.cpp:58-122 (a leg: tickHeld): a spring towards where the gait wants the foot,
 	                     * the reaction on the body; several legs add to one body, so uVel is an atomic add here */
 		const i32 h = W.holder[me];

@@ -1350,7 +1350,7 @@ static void worldRules(World *w, int g) {
 enum {
 	TICK_RAND = 6, TICK_LOGIC = 11, TICK_LOGIC_DEBUG = 12, TICK_DOOR = 13, TICK_CURSED = 14, TICK_RESPAWN = 15,
 	TICK_SEAT_OLD = 17, TICK_ADJUST = 19, TICK_SEAT = 23, TICK_SCOREBOARD = 27, TICK_TIMER = 28, TICK_DEMOLISH = 29, TICK_SIGN = 34,
-	TICK_LOADBLOCK = 35, TICK_PUDDLEJUMP = 36, TICK_SPIDER = 33
+	TICK_LOADBLOCK = 35, TICK_PUDDLEJUMP = 36, TICK_SPIDER = 33, TICK_EYE = 8, TICK_HELD_EYE = 9, TICK_HELD_VEH_EYE = 18
 };
 static int getButton(const World *w, i32 e, int i) { return (int)(signed char)w->btn[e][i]; }
 static void pushBtn(World *w, i32 e, int i) { w->btn[e][4 + i] = 1; }
@@ -1463,6 +1463,38 @@ static void tickOne(World *w, int g, i32 me) {
 				if (getButton(w, x, i)) pushBtn(w, me, i);
 		}
 		break;
+	case TICK_EYE: /* eyes.cpp:14-22 */
+		w->fullFlush[me] = 1;
+		w->ntype[me] = w->type[me] | T_DEBRIS;
+		w->ncollide[me] = w->collide[me] | T_TERRAIN | T_OBSTACLE | T_DEBRIS;
+		w->h[me][BT_H_TICK] = 0;
+		break;
+	case TICK_HELD_EYE: { /* eyes.cpp:24-47 */
+		i32 p = w->holder[me];
+		if (p < 0) break;
+		i32 vec[3] = {getSlider(w, p, 2), getSlider(w, p, 3), getSlider(w, p, 4)};
+		i32 component = abs(vec[2]), r = w->radius[p][2] - 50;
+		for (int i = 0; i < 2; i++) {
+			i32 i_comp = abs(vec[i]), i_r = w->radius[p][i] - 50;
+			if (i_comp * r > component * i_r) { r = i_r; component = i_comp; }
+		}
+		if (!component) break;
+		for (int i = 0; i < 3; i++)
+			w->d_vel[me][i] += r * vec[i] / component - (w->center[me][i] - w->center[p][i]) - (w->vel[me][i] - w->vel[p][i]);
+		break;
+	}
+	case TICK_HELD_VEH_EYE: { /* eyes.cpp:49-66 */
+		i32 p = w->holder[me];
+		if (p < 0) break;
+		i32 vec[3] = {0, 0, 0};
+		for (int k = 0; k < w->wires[me].num; k++) {
+			i32 x = w->wires[me].items[k];
+			for (int j = 0; j < w->wires[x].num; j++)
+				for (int i = 0; i < 2; i++) vec[i] += getSlider(w, w->wires[x].items[j], i);
+		}
+		for (int i = 0; i < 3; i++) w->d_center[me][i] += vec[i] * w->radius[p][i] / 64 - (w->center[me][i] - w->center[p][i]);
+		break;
+	}
 	case TICK_SPIDER: { /* spider.cpp:58-122 */
 		i32 h = w->holder[me];
 		if (h < 0) break;

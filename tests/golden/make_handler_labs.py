@@ -293,8 +293,28 @@ def lab_pilots(R):
         R.lab_set_handlers(it, tick_held=th)
         R.lab_set_sliders(it, [0, 5, 1, 0, 10, 3, 45, 14000])
         script.append((1, REQ_PICKUP, holder, it, HOLD_MOVE, 0, 0))
+    # eyes (eyes.cpp): a head with look sliders holds an eye that tracks where it looks and is dropped later (the eye's own
+    # tick handler then makes it debris and retires itself); a vehicle eye follows the pilot's axis through seat wires
+    pad(R, -20000, 0, r=(5000, 5000, 300), z=400)
+    head = cube(R, -20000, 0, -900, r=500, extra_type=T_INPUTS)
+    R.lab_set_sliders(head, [0, 0, 64, 0, 0, 0])
+    eye = R.add_ent((-20000, 0, -900), (0, 0, 0), (100, 100, 100), T_DECOR | 128, 0, WM_ME)
+    R.lab_set_handlers(eye, pair=(-1, 3, -1, -1), tick=TICK_EYE, tick_held=TICK_HELD_EYE)   # onFumbled = FUMBLED_DECOR
+    script.append((0, REQ_PICKUP, head, eye, HOLD_DROP, 0, 0))
+    for t, look in ((6, (0, 64, 0)), (15, (40, -40, 20)), (28, (0, 0, -64)), (36, (-64, 10, 3))):
+        script += [(t, REQ_SLIDER, head, -1, 2 + k, look[k], 0) for k in range(3)]
+    script.append((45, 0, eye, -1, 0, 0, 0))                       # uDrop(eye)
+    car = cube(R, -20000, 3000, -900, r=600)
+    veye = R.add_ent((-20000, 3000, -900), (0, 0, 0), (100, 100, 100), T_DECOR | 128, 0, WM_ME)
+    R.lab_set_handlers(veye, tick_held=TICK_HELD_VEH_EYE)
+    vseat = gate(R, -20000, 3000, -7000, 0, [0, 0])
+    R.lab_add_wire(veye, vseat)
+    R.lab_add_wire(vseat, stick)                                   # the puddlejumper's pilot drives this one too
+    script.append((0, REQ_PICKUP, car, veye, HOLD_DROP, 0, 0))
     return 90, script, 0
 
+
+TICK_EYE, TICK_HELD_EYE, TICK_HELD_VEH_EYE = 8, 9, 18
 
 LABS = {
     "lab_pilots": lab_pilots,
