@@ -1603,6 +1603,8 @@ static BT_HD void t_post(const DevWorld &W, i32 e) {
  * min/max, uVel = add, uDead = OR, uDrop), so every entity can run its handler at the same time.
  * TICK_RAND draws from gs->rand and therefore runs per world, in list order (t_tick_serial). */
 enum {
+	TICK_EXPLOSION = 1, TICK_PLATFORM = 3, TICK_THRUST = 10, TICK_BULLET = 25, TICK_HELD_BULLET = 26, TICK_DUST = 32,
+	TICK_INCINERATE = 40, TICK_BOTTLE_HELD = 41,
 	TICK_RAND = 6, TICK_EYE = 8, TICK_HELD_EYE = 9, TICK_HELD_VEH_EYE = 18, TICK_LOGIC = 11, TICK_LOGIC_DEBUG = 12, TICK_DOOR = 13, TICK_CURSED = 14, TICK_RESPAWN = 15,
 	TICK_SEAT_OLD = 17, TICK_ADJUST = 19, TICK_SEAT = 23, TICK_HELD_GUN = 24, TICK_SCOREBOARD = 27, TICK_TIMER = 28,
 	TICK_DEMOLISH = 29, TICK_HELD_BLINK = 30, TICK_HELD_JUMPER = 31, TICK_SPIDER = 33, TICK_SIGN = 34, TICK_LOADBLOCK = 35, TICK_PUDDLEJUMP = 36
@@ -1613,7 +1615,13 @@ enum {
 	(1ull << TICK_ADJUST) | (1ull << TICK_SEAT) | (1ull << TICK_TIMER) | (1ull << TICK_DEMOLISH) | (1ull << TICK_SIGN) | \
 	(1ull << TICK_HELD_GUN) | (1ull << TICK_SCOREBOARD) | (1ull << TICK_HELD_BLINK) | (1ull << TICK_HELD_JUMPER) |        \
 	(1ull << TICK_LOADBLOCK) | (1ull << TICK_PUDDLEJUMP) | (1ull << TICK_SPIDER) | (1ull << TICK_EYE) |                  \
-	(1ull << TICK_HELD_EYE) | (1ull << TICK_HELD_VEH_EYE))
+	(1ull << TICK_HELD_EYE) | (1ull << TICK_HELD_VEH_EYE) | (1ull << TICK_EXPLOSION) | (1ull << TICK_PLATFORM) |           \
+	(1ull << TICK_THRUST) | (1ull << TICK_BULLET) | (1ull << TICK_HELD_BULLET) | (1ull << TICK_DUST) |                   \
+	(1ull << TICK_BOTTLE) | (1ull << TICK_INCINERATE) | (1ull << TICK_BOTTLE_HELD))
+/* the ones that run per world, in list order, after everybody else (t_tick_serial): they draw from gs->rand or mark many
+ * other entities at once.  (TICK_DEPLETE, logic.c:110-121, writes a slider of its HOLDER directly, which the holder's own
+ * handler may read in the same tick before or after, by list order: not reproducible from a parallel pass, left to the host.) */
+#define BT_SERIAL_TICK ((1ull << TICK_RAND) | (1ull << TICK_SCOREBOARD) | (1ull << TICK_INCINERATE))
 
 static BT_HD int bt_button(const DevWorld &W, i32 e, int i) { return (int)(int8_t)((W.btn_v[e] >> (8 * i)) & 0xffu); }
 static BT_HD void bt_push_btn(const DevWorld &W, i32 e, int i) { bt_or32(&W.btn_v2[e], 1u << (8 * i)); }
@@ -1911,7 +1919,76 @@ static BT_HD void t_tick(const DevWorld &W, i32 me) {
 		bt_unsup(W, me, 6, id);
 		return;
 	}
-	case TICK_SCOREBOARD: return; /* per world, after everybody else (t_tick_serial): it may erase the whole world */
+	case TICK_SCOREBOARD: case TICK_INCINERATE: return; /* per world, in list order (t_tick_serial) */
+	case TICK_BOTTLE: return; /* bottle_tick bottle.cpp:42-43 is empty */
+	case TICK_EXPLOSION: { /* explosion_tick explosion.cpp:12-19 */
+		const i32 timer = bt_getslider(W, me, 0);
+		if (timer < 3) bt_uslider_shared(W, me, 0, timer + 1);
+		else bt_udead(W, me);
+		return;
+	}
+	case TICK_PLATFORM: /* platform_tick platform.c:15-23: surviving its first tick clears the special behaviour (direct writes) */
+		W.htick[me] = ht & ~0xffu;
+		W.hphys[me] &= ~(0xffu << 24);
+		for (i32 k = 0; k < W.wire_cnt[me]; k++) bt_uunwire(W, me, W.wire_to[W.wire_off[me] + k]);
+		return;
+	case TICK_THRUST: { /* thrust_tick thrust.c:19-37: pushed away from its lit wires; several thrusters share a body */
+		if (!W.wire_cnt[me] || bt_button(W, me, 0)) return;
+		const i32 divisor = bt_getslider(W, me, 0);
+		if (!divisor) return;
+		i32 off[3] = {0, 0, 0};
+		const int4 mc = W.center[me];
+		for (i32 k = 0; k < W.wire_cnt[me]; k++) {
+			const i32 w = W.wire_to[W.wire_off[me] + k];
+			if (!bt_button(W, w, 2)) continue;
+			const int4 wc = W.center[w];
+			off[0] += mc.x - wc.x; off[1] += mc.y - wc.y; off[2] += mc.z - wc.z;
+		}
+		i32 *dr = (i32 *)&W.d_vel[W.holdRoot[me]];
+		for (int i = 0; i < 3; i++) bt_add32((u32 *)&dr[i], (u32)(off[i] * 64 / divisor)); /* uVel(me->holdRoot, offset) */
+		W.ctr[CT_ANY_DELTA] = 1;
+		return;
+	}
+	case TICK_BULLET: { /* bullet_tick gun.c:116-123 */
+		const i32 ttl = bt_getslider(W, me, 0);
+		if (ttl <= 0) bt_udead(W, me);
+		else bt_uslider_shared(W, me, 0, ttl - 1);
+		return;
+	}
+	case TICK_HELD_BULLET: { /* bullet_tick_held gun.c:125-152: stuck in something; enough of them kill it */
+		const i32 ttl = bt_getslider(W, me, 0);
+		if (ttl <= -15 || ttl > 0) {
+			const i32 h = W.holder[me];
+			const u32 t = W.type[h];
+			int hits = (t & T_DEBRIS) ? 1 : ((t & T_TERRAIN) ? ((t & T_HEAVY) ? 15 : 5) : 3);
+			for (i32 c = W.holdee[h]; c >= 0; c = W.LLn[c]) {
+				if (((W.htick[c] >> 8) & 0xffu) != TICK_HELD_BULLET) continue;
+				if (!--hits) { bt_udead(W, h); break; }
+			}
+			bt_udead(W, me);
+		} else {
+			bt_uslider_shared(W, me, 0, ttl - 1); /* (+ a colour: not simulation state) */
+		}
+		return;
+	}
+	case TICK_DUST: { /* dust_tick dust.c:9-21 */
+		const i32 time = bt_getslider(W, me, 3);
+		if (time <= -8) { bt_udead(W, me); return; }
+		if (time > 0) {
+			int4 dv = W.d_vel[me]; /* uVel(me, sliders 0..2) */
+			dv.x += bt_getslider(W, me, 0); dv.y += bt_getslider(W, me, 1); dv.z += bt_getslider(W, me, 2);
+			W.d_vel[me] = dv;
+			W.ctr[CT_ANY_DELTA] = 1;
+		}
+		bt_uslider_shared(W, me, 3, time - 1);
+		return;
+	}
+	case TICK_BOTTLE_HELD: { /* bottle_tick_held bottle.cpp:47-90: "doesn't do anything unless held by a person (or similar)" */
+		const i32 h = W.holder[me];
+		if (h < 0 || !(W.type[h] & T_INPUTS)) return;
+		bt_unsup(W, me, 6, id);
+		return;
+	}
 	default: bt_unsup(W, me, 6, id); return;
 	}
 }
@@ -1931,6 +2008,18 @@ static BT_HD void t_tick_serial(const DevWorld &W, int g) {
 		u32 ht = W.htick[me];
 		const u32 id = W.holder[me] >= 0 ? (ht >> 8) & 0xffu : ht & 0xffu;
 		if (id == TICK_SCOREBOARD) { bt_scoreboard_tick(W, me); continue; }
+		if (id == TICK_INCINERATE) { /* incin_tick incinerate.cpp:15-32: everything fully beyond `range` dies */
+			if (bt_button(W, me, 0) ^ bt_button(W, me, 1)) continue;
+			const i32 range = bt_getslider(W, me, 0);
+			if (range <= 0) continue;
+			const int4 mc = W.center[me];
+			for (i32 e = W.wbegin[g]; e < W.wend[g]; e++) {
+				if (!W.inList[e]) continue;
+				const int4 c = W.center[e], r = W.radius[e];
+				if (bt_abs(c.x - mc.x) - r.x >= range || bt_abs(c.y - mc.y) - r.y >= range || bt_abs(c.z - mc.z) - r.z >= range) bt_udead(W, e);
+			}
+			continue;
+		}
 		if (id != TICK_RAND) continue;
 		if (!bt_logic_input(W, me, bt_getslider(W, me, 0))) continue;
 		int options = 0;

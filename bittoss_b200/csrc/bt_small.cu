@@ -113,7 +113,7 @@ __global__ void __launch_bounds__(BS, SW_MIN_WARPS * 32 / BS) k_tick_small(DevWo
 		if (mine && W.inList[e]) {
 			const u32 ht = W.htick[e];
 			const u32 id = W.holder[e] >= 0 ? (ht >> 8) & 0xffu : ht & 0xffu;
-			rnd = id == TICK_RAND || id == TICK_SCOREBOARD; /* the serial pass has work */
+			rnd = id < 64 && ((BT_SERIAL_TICK >> id) & 1ull); /* the serial pass has work */
 			t_tick(W, e);
 		}
 		if (__syncthreads_or(rnd) && i == 0) t_tick_serial(W, g); /* gs->rand draws in list order */

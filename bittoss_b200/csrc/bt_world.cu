@@ -509,7 +509,7 @@ int bt_world_upload(bt_world *w, const bt_world_desc *d) {
 			int id = h[k ? BT_H_TICKHELD : BT_H_TICK];
 			if (id) any_ticks = true;
 			if (id >= 64 || !((BT_SUPPORTED_TICK >> id) & 1ull)) { if (!bad_tick) bad_tick = id; }
-			if (id == TICK_RAND || id == TICK_SCOREBOARD) any_rand = true; /* the per-world serial pass has work */
+			if (id < 64 && ((BT_SERIAL_TICK >> id) & 1ull)) any_rand = true; /* the per-world serial pass has work */
 		}
 		const uint8_t *b = d->btn + 8 * (size_t)i;
 		bv[i] = b[0] | (b[1] << 8) | (b[2] << 16) | ((u32)b[3] << 24);

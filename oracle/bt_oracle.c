@@ -1350,7 +1350,8 @@ static void worldRules(World *w, int g) {
 enum {
 	TICK_RAND = 6, TICK_LOGIC = 11, TICK_LOGIC_DEBUG = 12, TICK_DOOR = 13, TICK_CURSED = 14, TICK_RESPAWN = 15,
 	TICK_SEAT_OLD = 17, TICK_ADJUST = 19, TICK_SEAT = 23, TICK_SCOREBOARD = 27, TICK_TIMER = 28, TICK_DEMOLISH = 29, TICK_SIGN = 34,
-	TICK_LOADBLOCK = 35, TICK_PUDDLEJUMP = 36, TICK_SPIDER = 33, TICK_EYE = 8, TICK_HELD_EYE = 9, TICK_HELD_VEH_EYE = 18
+	TICK_LOADBLOCK = 35, TICK_PUDDLEJUMP = 36, TICK_SPIDER = 33, TICK_EYE = 8, TICK_HELD_EYE = 9, TICK_HELD_VEH_EYE = 18,
+	TICK_EXPLOSION = 1, TICK_PLATFORM = 3, TICK_THRUST = 10, TICK_BULLET = 25, TICK_HELD_BULLET = 26, TICK_DUST = 32, TICK_INCINERATE = 40
 };
 static int getButton(const World *w, i32 e, int i) { return (int)(signed char)w->btn[e][i]; }
 static void pushBtn(World *w, i32 e, int i) { w->btn[e][4 + i] = 1; }
@@ -1463,6 +1464,68 @@ static void tickOne(World *w, int g, i32 me) {
 				if (getButton(w, x, i)) pushBtn(w, me, i);
 		}
 		break;
+	case TICK_EXPLOSION: { /* explosion.cpp:12-19 */
+		i32 timer = getSlider(w, me, 0);
+		if (timer < 3) uSlider(w, me, 0, timer + 1); else uDead(w, me);
+		break;
+	}
+	case TICK_PLATFORM: /* platform.c:15-23 */
+		w->h[me][BT_H_TICK] = 0;
+		w->h[me][BT_H_CRUSH] = 0;
+		for (int k = 0; k < w->wires[me].num; k++) il_add(&w->wiresRm[me], w->wires[me].items[k]); /* uUnwire */
+		break;
+	case TICK_THRUST: { /* thrust.c:19-37 */
+		if (!w->wires[me].num || getButton(w, me, 0)) break;
+		i32 divisor = getSlider(w, me, 0);
+		if (!divisor) break;
+		i32 off[3] = {0, 0, 0};
+		for (int k = 0; k < w->wires[me].num; k++) {
+			i32 x = w->wires[me].items[k];
+			if (!getButton(w, x, 2)) continue;
+			for (int i = 0; i < 3; i++) off[i] += w->center[me][i] - w->center[x][i];
+		}
+		for (int i = 0; i < 3; i++) w->d_vel[w->holdRoot[me]][i] += off[i] * 64 / divisor;
+		break;
+	}
+	case TICK_BULLET: { /* gun.c:116-123 */
+		i32 ttl = getSlider(w, me, 0);
+		if (ttl <= 0) uDead(w, me); else uSlider(w, me, 0, ttl - 1);
+		break;
+	}
+	case TICK_HELD_BULLET: { /* gun.c:125-152 */
+		i32 ttl = getSlider(w, me, 0);
+		if (ttl <= -15 || ttl > 0) {
+			i32 h = w->holder[me];
+			uint32_t t = w->type[h];
+			int hits = (t & T_DEBRIS) ? 1 : ((t & T_TERRAIN) ? ((t & T_HEAVY) ? 15 : 5) : 3);
+			for (i32 c = w->holdee[h]; c >= 0; c = w->LLn[c]) {
+				if (w->h[c][BT_H_TICKHELD] != TICK_HELD_BULLET) continue;
+				if (!--hits) { uDead(w, h); break; }
+			}
+			uDead(w, me);
+		} else {
+			uSlider(w, me, 0, ttl - 1);
+		}
+		break;
+	}
+	case TICK_DUST: { /* dust.c:9-21 */
+		i32 time = getSlider(w, me, 3);
+		if (time <= -8) { uDead(w, me); break; }
+		if (time > 0) for (int i = 0; i < 3; i++) w->d_vel[me][i] += getSlider(w, me, i);
+		uSlider(w, me, 3, time - 1);
+		break;
+	}
+	case TICK_INCINERATE: { /* incinerate.cpp:15-32 */
+		if (getButton(w, me, 0) ^ getButton(w, me, 1)) break;
+		i32 range = getSlider(w, me, 0);
+		if (range <= 0) break;
+		for (i32 e = w->wbegin[g]; e < w->wend[g]; e++) {
+			if (!w->inList[e]) continue;
+			for (int i = 0; i < 3; i++)
+				if (abs(w->center[e][i] - w->center[me][i]) - w->radius[e][i] >= range) { uDead(w, e); break; }
+		}
+		break;
+	}
 	case TICK_EYE: /* eyes.cpp:14-22 */
 		w->fullFlush[me] = 1;
 		w->ntype[me] = w->type[me] | T_DEBRIS;

@@ -315,9 +315,58 @@ def lab_pilots(R):
 
 
 TICK_EYE, TICK_HELD_EYE, TICK_HELD_VEH_EYE = 8, 9, 18
+TICK_EXPLOSION, TICK_PLATFORM, TICK_THRUST, TICK_BULLET, TICK_HELD_BULLET, TICK_DUST, TICK_INCINERATE = 1, 3, 10, 25, 26, 32, 40
+REQ_BUTTON = 3
+
+
+def lab_ticks2(R):
+    """FULL ticks: the short-lived things other handlers leave behind, built by hand (nothing here creates entities): an
+    explosion fragment and a dust mote running out, a platform clearing its special behaviour on its first tick, bullets
+    in flight timing out and bullets stuck in a block killing it, thrusters pushing a floating body away from their lit
+    wires, an incinerator switched on late that kills whatever lies fully beyond its range."""
+    script = []
+    pad(R, 0, 0, r=(6000, 6000, 300), z=400)
+    ex = cube(R, -2000, 0, -800, r=100)
+    R.lab_set_handlers(ex, tick=TICK_EXPLOSION); R.lab_set_sliders(ex, [0])
+    du = R.add_ent((-1000, 0, -2000), (5, 0, 0), (60, 60, 60), T_WEIGHTLESS, 0, WM_ME)
+    R.lab_set_handlers(du, tick=TICK_DUST); R.lab_set_sliders(du, [3, -2, 1, 5])
+    pf = R.add_ent((3000, 3000, -1500), (0, 0, 0), (1600, 1600, 250), GROUND, 0, WM_ME)
+    R.lab_set_handlers(pf, crush=2, tick=TICK_PLATFORM)
+    m = gate(R, 3000, 3000, -4000, 0, [0, 0])
+    R.lab_add_wire(pf, m); R.lab_add_wire(pf, ex)
+    # bullets in flight
+    for k in range(3):
+        b = R.add_ent((-3000, 1000 * k, -3000), (40, 0, 0), (100, 100, 100), T_WEIGHTLESS, 0, WM_ME)
+        R.lab_set_handlers(b, tick=TICK_BULLET, tick_held=TICK_HELD_BULLET); R.lab_set_sliders(b, [4 + 3 * k])
+    # bullets stuck in a plain block (3 kill it), in a debris block (1 kills it) and two in a third block (not enough); they
+    # are picked up by the first prepPhysics (ttl 1 -> 0 in the tick before), then ttl runs 0 .. -15
+    victim = cube(R, 1500, -1500, -800)
+    deb = cube(R, 1500, 1500, -800, extra_type=T_DEBRIS)
+    tough = cube(R, 3000, -3000, -800)
+    for k, host in enumerate((victim, victim, victim, deb, tough, tough)):
+        b = R.add_ent((1500, -1500 + 100 * k, -800), (0, 0, 0), (100, 100, 100), 0, 0, WM_ME)
+        R.lab_set_handlers(b, tick=TICK_BULLET, tick_held=TICK_HELD_BULLET); R.lab_set_sliders(b, [1])
+        script.append((0, REQ_PICKUP, host, b, HOLD_DROP | HOLD_FREEZE, 0, 0))
+    # a floating body with two thrusters wired to lamps; the lamps are lit by script (button 2 = "active")
+    body = R.add_ent((-4000, -4000, -3000), (0, 0, 0), (500, 500, 500), CUBE | T_WEIGHTLESS, CUBE_COLLIDE, WM_WOOD)
+    lamps = [gate(R, -4000 + 800 * d, -4000, -3000, 0, [0, 0]) for d in (-1, 1)]
+    for k in range(2):
+        th = R.add_ent((-4000, -4000 + 300 * k, -3600), (0, 0, 0), (100, 100, 100), T_WEIGHTLESS, 0, WM_ME)
+        R.lab_set_handlers(th, tick=TICK_THRUST, tick_held=TICK_THRUST); R.lab_set_sliders(th, [640])
+        R.lab_add_wire(th, lamps[k])
+        script.append((0, REQ_PICKUP, body, th, HOLD_MOVE, 0, 0))
+    script += [(t, REQ_BUTTON, lamps[0], -1, 2, 0, 0) for t in range(5, 30)] + [(t, REQ_BUTTON, lamps[1], -1, 2, 0, 0) for t in range(20, 45)]
+    # incinerator: off while its two inputs differ (button 0 held by script), then on
+    inc = gate(R, 0, 0, -1000, TICK_INCINERATE, [7000])
+    script += [(t, REQ_BUTTON, inc, -1, 0, 0, 0) for t in range(0, 40)]
+    far = cube(R, 9000, 0, -3000)            # fully beyond 7000 on x: dies when the incinerator comes on
+    near = cube(R, 6000, 0, -3000)           # 6000 - 400 < 7000: stays
+    return 60, script, 0
+
 
 LABS = {
     "lab_pilots": lab_pilots,
+    "lab_ticks2": lab_ticks2,
     "lab_teleport": lab_teleport,
     "lab_bottles": lab_bottles,
     "lab_seats": lab_seats,

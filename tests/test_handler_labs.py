@@ -8,7 +8,7 @@ import pytest
 
 from util import golden_path, load_world
 
-LABS = ["lab_teleport", "lab_bottles", "lab_seats", "lab_crush", "lab_logic", "lab_requests", "lab_rootorder", "lab_pilots"]
+LABS = ["lab_teleport", "lab_bottles", "lab_seats", "lab_crush", "lab_logic", "lab_requests", "lab_rootorder", "lab_pilots", "lab_ticks2"]
 TICKS = 64  # BT_PHASE_TICKS
 
 

@@ -11,7 +11,7 @@ from util import SCENARIOS, golden_path, load_scenario, load_world
 
 SMALL = [n for n in SCENARIOS if n in ("arena_kick", "diner_kick", "tower_kick", "forest_kick", "leggs_kick", "spider_kick",
                                        "spider_static")]
-LABS = ["lab_teleport", "lab_bottles", "lab_seats", "lab_crush", "lab_logic", "lab_requests", "lab_rootorder", "lab_pilots"]
+LABS = ["lab_teleport", "lab_bottles", "lab_seats", "lab_crush", "lab_logic", "lab_requests", "lab_rootorder", "lab_pilots", "lab_ticks2"]
 SAME_STATS = ("ticks", "positives", "pushes", "serial_pushes", "crushes", "fumbles", "live_ents", "entity_ticks",
               "unsupported_events")
 
