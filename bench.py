@@ -489,31 +489,79 @@ def run_cuda(args):
     value = et_sum / (ms_max * 1e-3)
 
     # ---- (2) end to end through the C ABI with HOST buffers: `e2e` ----
-    # per step: H2D of the host-side deltas (uCenter/uVel of the tick handlers, 24 B/entity),
-    # the tick, D2H of centre+velocity (24 B/entity) and of the state hash
+    # per step: H2D of the host-side deltas (uCenter/uVel of the tick handlers, 24 B/entity), the tick, D2H of centre +
+    # velocity (24 B/entity) and of the state hash.  Two forms of the same exchange, both timed:
+    #   serial     apply_host_deltas -> step -> read_state -> hash, everything on the world's stream, one after the other
+    #              (a host whose next deltas need the state it has just read: round 1's `e2e`)
+    #   pipelined  the *_async calls: the copies on their own streams, double-buffered, so that H2D of step t+1 and D2H of
+    #              step t-1 overlap the tick of step t (a host whose handlers are input-driven, a renderer one tick behind);
+    #              every step still copies its own 24 + 24 B/entity inside the timed region and reads its own hash
     live = w.count()[0]
-    dc = torch.zeros((live, 3), dtype=torch.int32).pin_memory().numpy()
-    dv = torch.zeros((live, 3), dtype=torch.int32).pin_memory().numpy()
-    oc = torch.zeros((live, 3), dtype=torch.int32).pin_memory().numpy()
-    ov = torch.zeros((live, 3), dtype=torch.int32).pin_memory().numpy()
+    bufs = [[torch.zeros((live, 3), dtype=torch.int32).pin_memory().numpy() for _ in range(4)] for _ in range(2)]
     e2e_steps = max(1, min(args.steps, 20))
+
+    def e2e_serial(n_steps):
+        nonlocal live
+        dc, dv, oc, ov = bufs[0]
+        et = 0
+        for _ in range(n_steps):
+            w.apply_host_deltas(dc[:live], dv[:live])
+            w.step(31)
+            live = w.live_ents()   # host-side bookkeeping of the step that just finished: no extra round trip
+            w.read_state(oc[:live], ov[:live])
+            _ = w.hash()
+            et += live
+        return et
+
+    def e2e_pipelined(n_steps):
+        nonlocal live
+        et = 0
+        tickets = [None, None]
+        w.apply_host_deltas_async(bufs[0][0][:live], bufs[0][1][:live])
+        for t in range(n_steps):
+            k = t & 1
+            if t + 1 < n_steps:   # the next step's deltas start travelling now: bt_world_step waits for its own tick
+                w.send_host_deltas(bufs[k ^ 1][0][:live], bufs[k ^ 1][1][:live])
+            w.step(31)
+            live_now = w.live_ents()
+            _ = w.hash()          # this step's result (12 bytes, through mapped host memory: not behind the state copies)
+            tickets[k] = w.read_state_async(bufs[k][2][:live_now], bufs[k][3][:live_now])   # travels during the next tick
+            if t + 1 < n_steps:
+                if live_now == live:
+                    w.commit_host_deltas()   # ... and are added in front of the next step
+                else:   # an entity died: the rows sent no longer line up with the ranks; send this step's again, serially
+                    try:
+                        w.commit_host_deltas()
+                    except Exception:
+                        pass
+                    w.apply_host_deltas_async(bufs[k ^ 1][0][:live_now], bufs[k ^ 1][1][:live_now])
+            if tickets[k ^ 1] is not None:
+                w.read_state_wait(tickets[k ^ 1])   # the state of the step before is on the host by now
+                tickets[k ^ 1] = None
+            live = live_now
+            et += live
+        for tk in tickets:
+            if tk is not None:
+                w.read_state_wait(tk)
+        w.sync()
+        return et
+
+    e2e_serial(2)
+    e2e_pipelined(2)   # both paths warm (buffers, streams)
     barrier()
     t0 = time.perf_counter()
-    et_e2e = 0
-    for _ in range(e2e_steps):
-        w.apply_host_deltas(dc, dv)
-        w.step(31)
-        live_now = w.live_ents()   # host-side bookkeeping of the step that just finished: no extra round trip
-        if live_now != live:  # an entity died: the host arrays shrink with the world
-            live = live_now
-            dc, dv, oc, ov = dc[:live], dv[:live], oc[:live], ov[:live]
-        w.read_state(oc, ov)
-        _ = w.hash()
-        et_e2e += live
+    et_ser = e2e_serial(e2e_steps)
+    barrier()
+    ser_s = time.perf_counter() - t0
+    ser_max, ser_work = reduce_time_and_work(ser_s, float(et_ser), device="cuda")
+    barrier()
+    t0 = time.perf_counter()
+    et_e2e = e2e_pipelined(e2e_steps)
     barrier()
     e2e_s = time.perf_counter() - t0
     e2e_max, e2e_work = reduce_time_and_work(e2e_s, float(et_e2e), device="cuda")
     e2e_value = e2e_work / e2e_max
+    e2e_serial_value = ser_work / ser_max
 
     # ---- (3) per-kernel device times (separate pass, CUDA events around every launch) ----
     w.profile_enable(True)
@@ -577,7 +625,12 @@ def run_cuda(args):
                 "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 24 * live,
                         "d2h_bytes_per_step": 24 * live + 8, "steps": e2e_steps,
-                        "exchange": "serial per step: H2D deltas -> tick -> D2H centre + velocity -> D2H hash",
+                        "exchange": "pipelined (bt_world_*_async): every step copies its deltas in (pinned, H2D) and its centre + "
+                                    "velocity and hash out (D2H) inside the timed region; the copies of neighbouring steps run on their "
+                                    "own streams and overlap the tick in between",
+                        "serial_value": e2e_serial_value,
+                        "serial_exchange": "H2D deltas -> tick -> D2H centre + velocity -> D2H hash, one after the other on one stream "
+                                           "(round 1's e2e)",
                         "rank0_numa": numa},
                 "gpu_launches": st["kernel_launches"],
                 "roofline": roofline,

@@ -113,6 +113,11 @@ def lib():
     L.bt_world_tick_timed.argtypes = [C.c_void_p, C.c_int32, C.POINTER(C.c_float)]
     L.bt_world_apply_host_deltas.argtypes = [C.c_void_p, _i32p, _i32p, C.c_int32]
     L.bt_world_read_state.argtypes = [C.c_void_p, _i32p, _i32p, C.c_int32]
+    L.bt_world_apply_host_deltas_async.argtypes = [C.c_void_p, _i32p, _i32p, C.c_int32]
+    L.bt_world_send_host_deltas.argtypes = [C.c_void_p, _i32p, _i32p, C.c_int32]
+    L.bt_world_commit_host_deltas.argtypes = [C.c_void_p]
+    L.bt_world_read_state_async.argtypes = [C.c_void_p, _i32p, _i32p, C.c_int32, _i32p]
+    L.bt_world_read_state_wait.argtypes = [C.c_void_p, C.c_int32]
     L.bt_world_stream.argtypes = [C.c_void_p]
     L.bt_world_stream.restype = C.c_void_p
     L.bt_world_hash.argtypes = [C.c_void_p, _u64p]
@@ -267,6 +272,33 @@ class World:
         n = center.size // 3
         _ck(self.L.bt_world_read_state(self.h, C.cast(center.ctypes.data, _i32p), C.cast(vel.ctypes.data, _i32p), n),
             "bt_world_read_state")
+
+    def apply_host_deltas_async(self, d_center, d_vel):
+        """pipelined: the copy starts now on its own stream, the deltas are added in front of the next step (pinned arrays)"""
+        n = d_center.size // 3
+        _ck(self.L.bt_world_apply_host_deltas_async(self.h, C.cast(d_center.ctypes.data, _i32p),
+                                                    C.cast(d_vel.ctypes.data, _i32p), n), "bt_world_apply_host_deltas_async")
+
+    def send_host_deltas(self, d_center, d_vel):
+        """pipelined, first half: only the copy starts (call it before the step the deltas must not reach)"""
+        n = d_center.size // 3
+        _ck(self.L.bt_world_send_host_deltas(self.h, C.cast(d_center.ctypes.data, _i32p), C.cast(d_vel.ctypes.data, _i32p), n),
+            "bt_world_send_host_deltas")
+
+    def commit_host_deltas(self):
+        """pipelined, second half: the oldest batch sent is added in front of the next step"""
+        _ck(self.L.bt_world_commit_host_deltas(self.h), "bt_world_commit_host_deltas")
+
+    def read_state_async(self, center, vel):
+        """pipelined: packs the state behind everything enqueued and starts the copy; returns the ticket for read_state_wait"""
+        n = center.size // 3
+        t = C.c_int32()
+        _ck(self.L.bt_world_read_state_async(self.h, C.cast(center.ctypes.data, _i32p), C.cast(vel.ctypes.data, _i32p), n,
+                                             C.byref(t)), "bt_world_read_state_async")
+        return int(t.value)
+
+    def read_state_wait(self, ticket):
+        _ck(self.L.bt_world_read_state_wait(self.h, int(ticket)), "bt_world_read_state_wait")
 
     def sync(self):
         _ck(self.L.bt_world_sync(self.h), "bt_world_sync")

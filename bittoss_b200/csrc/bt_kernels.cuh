@@ -568,6 +568,24 @@ __global__ void __launch_bounds__(GS_BLOCK) k_hash_one(DevWorld W, u64 *sum, u32
 	}
 }
 
+/* A few words for the host, written straight into mapped pinned host memory (zero copy).  The counters the host reads
+ * once per tick used to come back with cudaMemcpyAsync: that is a job for the device-to-host COPY ENGINE, which a host
+ * streaming a 24 MB state read-back on another stream (bt_world_read_state_async) keeps busy for 0.5 ms at a time: the
+ * 256 bytes queued behind it and the tick with them. */
+__global__ void __launch_bounds__(64) k_publish(const u32 *src, u32 *host_mapped, int n) { PDL_ENTRY_ALWAYS();
+	for (int i = threadIdx.x; i < n; i += 64) host_mapped[i] = src[i];
+	__threadfence_system();
+}
+
+/* a single world's hash sum and entity count, the same way */
+__global__ void k_publish_hash(const u64 *sum, const u32 *cnt, u32 *host_mapped) { PDL_ENTRY_ALWAYS();
+	if (threadIdx.x == 0) {
+		const u64 s = sum[0];
+		host_mapped[0] = (u32)s; host_mapped[1] = (u32)(s >> 32); host_mapped[2] = cnt[0];
+		__threadfence_system();
+	}
+}
+
 /* --------------------------------------------------------------------------
  * LSD radix sort, 8 bits per pass, keys u64 + payload i32, stable.
  * pass = histogram -> scan -> scatter.  Tile = 256 threads x 16 keys.

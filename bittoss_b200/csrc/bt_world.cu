@@ -69,7 +69,8 @@ struct bt_world {
 	DevWorld W;
 	std::vector<void *> allocs;
 	std::vector<size_t> alloc_bytes;
-	u32 *h_flag; /* pinned, CT_WORDS words */
+	u32 *h_flag; /* pinned + mapped, CT_WORDS words (+ 4 for a single world's hash sum and count): kernels write it (k_publish) */
+	u32 *d_hflag; /* the same memory as the device sees it */
 	u64 *d_hsum; u32 *d_hcnt;
 	u32 *d_sorthist; int sorthist_len;
 	bool any_rules; /* some world's gamerules contain a scan rule (crush / lava / bounce) */
@@ -109,6 +110,13 @@ struct bt_world {
 	RayTree ray;
 	bool ray_valid;
 	i32 *d_stage_a, *d_stage_b; /* 3*cap ints each, staging for the per-tick host exchange */
+	/* the pipelined exchange (bt_world_apply_host_deltas_async / bt_world_read_state_async): copy streams, double buffers */
+	cudaStream_t s_h2d, s_d2h;
+	i32 *px_in[2][2], *px_out[2][2];                  /* [buffer][centre / velocity] */
+	cudaEvent_t px_arrived[2], px_added[2], px_packed[2], px_read[2];
+	int px_in_k, px_out_k, px_commit_k;
+	bool px_ready, px_sent[2]; /* sent[k]: buffer k was sent and not yet committed (FIFO: commit_k is the older one) */
+	i32 px_sent_n[2];
 	bool ranks_valid;           /* ray.slot2rank reflects the current live set */
 	/* incremental host binding */
 	i32 root_phase_ctr;         /* last value handed to a launch / the host as W.root_phase */
@@ -253,6 +261,13 @@ void bt_world_destroy(bt_world *w) {
 	if (w->d_rayhist) cudaFree(w->d_rayhist);
 	if (w->ev0) cudaEventDestroy(w->ev0);
 	if (w->ev1) cudaEventDestroy(w->ev1);
+	if (w->px_ready) {
+		for (int k = 0; k < 2; k++) {
+			cudaEventDestroy(w->px_arrived[k]); cudaEventDestroy(w->px_added[k]); cudaEventDestroy(w->px_packed[k]); cudaEventDestroy(w->px_read[k]);
+			for (int j = 0; j < 2; j++) { cudaFree(w->px_in[k][j]); cudaFree(w->px_out[k][j]); }
+		}
+		cudaStreamDestroy(w->s_h2d); cudaStreamDestroy(w->s_d2h);
+	}
 	if (w->stream) cudaStreamDestroy(w->stream);
 	delete w;
 }
@@ -276,6 +291,7 @@ int bt_world_create(bt_world **out, int device, int32_t max_ents, int32_t max_sl
 	w->tree_valid = false; w->deltas_pending = true; w->ticks_since_build = 0; w->full_flush_left = 2; w->scan_flushes_left = 2; w->ctrls_fused = false;
 	w->rebuild_every = 16; w->max_iterations = 100000; w->pair_cache = 1; w->pair_rebuilds = 0; w->pair_overflows = 0; w->seen_pair_builds = 0; w->seen_pair_patches = 0; w->pair_builds_at_tree = 0; w->profiling = false; w->ray_valid = false; w->uid_map_valid = false; w->ctr_fresh = false; w->margin_opt = -1; w->narrow_blocks = 148 * 8; w->narrow_threads = 256; w->pdl_opt = getenv("BT_NO_PDL") ? 0 : -1; w->pdl = false; w->pdl_long = false; /* decided at upload, together with W.pdl */ w->small_worlds = true; w->d_reqs = NULL; w->d_req_starts = NULL; w->reqs_cap = 0; w->any_ticks = w->any_rand = false; w->bad_tick = 0; w->device_ticks = 1;
 	w->h_flag = NULL; w->ev0 = w->ev1 = NULL; w->stream = NULL;
+	w->px_ready = false; w->s_h2d = w->s_d2h = NULL; w->px_in_k = w->px_out_k = w->px_commit_k = 0; w->px_sent[0] = w->px_sent[1] = false;
 	w->root_phase_ctr = 0; w->sliders_used = 0; w->wires_used = 0; w->d_pokes = NULL; w->pokes_cap = 0; w->poked = false;
 	w->launch_err = cudaSuccess; w->fused_small = 1; w->small_warps = getenv("BT_SMALL_WARPS") ? atoi(getenv("BT_SMALL_WARPS")) : 0; w->fused_dirty = false; w->seen_eticks = w->seen_iters = 0; w->wq_host_pending = false; w->small_biggest = 0;
 	w->d_raykeys = w->d_raykeys_alt = NULL; w->d_rayidx = w->d_rayidx_alt = NULL; w->d_rayhist = NULL; w->rays_cap = 0; w->sort_rays = 0; w->ray_dynamic = 1; w->ray_blocks = 148 * 12; /* measured on 4 M rays: 4.28 ms at 148 x 8 blocks, 4.06 at x 12 and beyond (13 fit an SM) */
@@ -285,7 +301,8 @@ int bt_world_create(bt_world **out, int device, int32_t max_ents, int32_t max_sl
 	TRYCU(cudaStreamCreateWithFlags(&w->stream, cudaStreamNonBlocking));
 	TRYCU(cudaEventCreate(&w->ev0));
 	TRYCU(cudaEventCreate(&w->ev1));
-	TRYCU(cudaHostAlloc((void **)&w->h_flag, sizeof(u32) * CT_WORDS, cudaHostAllocDefault));
+	TRYCU(cudaHostAlloc((void **)&w->h_flag, sizeof(u32) * (CT_WORDS + 4), cudaHostAllocMapped));
+	TRYCU(cudaHostGetDevicePointer((void **)&w->d_hflag, w->h_flag, 0));
 	DevWorld &W = w->W;
 	size_t n = (size_t)max_ents, nw = (size_t)max_worlds;
 	TRY(dalloc(w, &W.wbegin, nw)); TRY(dalloc(w, &W.wend, nw)); TRY(dalloc(w, &W.flip, nw));
@@ -635,7 +652,7 @@ static int build_tree(bt_world *w) {
 	i32 init[8] = {0, INT32_MAX, INT32_MAX, INT32_MAX, INT32_MIN, INT32_MIN, INT32_MIN, 0};
 	CK(cudaMemcpyAsync(&W.ctr[CT_N_LEAVES], init, sizeof(i32) * 7, cudaMemcpyHostToDevice, w->stream));
 	LAUNCH(w, PK_BUILD_KEYS, k_bounds, gsblk(n), GS_BLOCK, W);
-	CK(cudaMemcpyAsync(w->h_flag, W.ctr, sizeof(u32) * CT_WORDS, cudaMemcpyDeviceToHost, w->stream));
+	LAUNCH(w, PK_BUILD_KEYS, k_publish, 1, 64, (const u32 *)W.ctr, w->d_hflag, (int)CT_WORDS);
 	CK(cudaStreamSynchronize(w->stream));
 	W.n_leaves = (i32)w->h_flag[CT_N_LEAVES];
 	const i32 *b = (const i32 *)&w->h_flag[CT_BOUNDS];
@@ -702,7 +719,7 @@ static int flush1(bt_world *w, bool hint) {
 
 static int fetch_ctr(bt_world *w) {
 	CHECK_LAUNCHES(w);
-	CK(cudaMemcpyAsync(w->h_flag, w->W.ctr, sizeof(u32) * CT_WORDS, cudaMemcpyDeviceToHost, w->stream));
+	LAUNCH(w, PK_EXCHANGE, k_publish, 1, 64, (const u32 *)w->W.ctr, w->d_hflag, (int)CT_WORDS); /* not a copy: see k_publish */
 	CK(cudaStreamSynchronize(w->stream));
 	w->poked = false;
 	if (w->h_flag[CT_ERROR]) {
@@ -1051,9 +1068,16 @@ static int hash_into(bt_world *w, uint64_t *out, int full = 0) {
 	else LAUNCH(w, PK_HASH, k_hash, nblk(W.n), BT_BLOCK, W, w->d_hsum, w->d_hcnt, full);
 	std::vector<u64> s(W.n_worlds);
 	std::vector<u32> c(W.n_worlds);
-	CK(cudaMemcpyAsync(s.data(), w->d_hsum, sizeof(u64) * s.size(), cudaMemcpyDeviceToHost, w->stream));
-	CK(cudaMemcpyAsync(c.data(), w->d_hcnt, sizeof(u32) * c.size(), cudaMemcpyDeviceToHost, w->stream));
-	CK(cudaStreamSynchronize(w->stream));
+	if (W.n_worlds == 1) { /* 12 bytes: through the mapped words behind the counters, not through the copy engine */
+		LAUNCH(w, PK_HASH, k_publish_hash, 1, 32, (const u64 *)w->d_hsum, (const u32 *)w->d_hcnt, w->d_hflag + CT_WORDS);
+		CK(cudaStreamSynchronize(w->stream));
+		memcpy(&s[0], &w->h_flag[CT_WORDS], sizeof(u64));
+		c[0] = w->h_flag[CT_WORDS + 2];
+	} else {
+		CK(cudaMemcpyAsync(s.data(), w->d_hsum, sizeof(u64) * s.size(), cudaMemcpyDeviceToHost, w->stream));
+		CK(cudaMemcpyAsync(c.data(), w->d_hcnt, sizeof(u32) * c.size(), cudaMemcpyDeviceToHost, w->stream));
+		CK(cudaStreamSynchronize(w->stream));
+	}
 	std::vector<i32> flip, rules, rnd;
 	if (full) {
 		flip.resize(W.n_worlds); rules.resize(W.n_worlds); rnd.resize(W.n_worlds);
@@ -1225,10 +1249,101 @@ int bt_world_read_state(bt_world *w, int32_t *center, int32_t *vel, int32_t n_en
 	return BT_OK;
 }
 
+/* ---- the pipelined exchange ---- */
+static int px_init(bt_world *w) {
+	if (w->px_ready) return 0;
+	CK(cudaStreamCreateWithFlags(&w->s_h2d, cudaStreamNonBlocking));
+	CK(cudaStreamCreateWithFlags(&w->s_d2h, cudaStreamNonBlocking));
+	const size_t bytes = sizeof(i32) * 3 * (size_t)(w->cap_ents > 0 ? w->cap_ents : 1);
+	for (int k = 0; k < 2; k++) {
+		for (int j = 0; j < 2; j++) { CK(cudaMalloc(&w->px_in[k][j], bytes)); CK(cudaMalloc(&w->px_out[k][j], bytes)); }
+		CK(cudaEventCreateWithFlags(&w->px_arrived[k], cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&w->px_added[k], cudaEventDisableTiming));
+		CK(cudaEventCreateWithFlags(&w->px_packed[k], cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&w->px_read[k], cudaEventDisableTiming));
+	}
+	w->px_ready = true;
+	return 0;
+}
+
+int bt_world_send_host_deltas(bt_world *w, const int32_t *d_center, const int32_t *d_vel, int32_t n_ents) {
+	if (!w || !d_center || !d_vel || n_ents < 0) return BT_ERR_ARG;
+	CK(cudaSetDevice(w->device));
+	{ int rr = px_init(w); if (rr) return rr; }
+	if (w->px_sent[0] && w->px_sent[1]) { snprintf(g_err, sizeof g_err, "bt_world_send_host_deltas: two batches are already on their way, commit one first"); return BT_ERR_ARG; }
+	const int k = w->px_in_k;
+	w->px_in_k ^= 1;
+	const size_t bytes = sizeof(i32) * 3 * (size_t)n_ents;
+	CK(cudaStreamWaitEvent(w->s_h2d, w->px_added[k], 0)); /* the kernel that last consumed this buffer is done */
+	CK(cudaMemcpyAsync(w->px_in[k][0], d_center, bytes, cudaMemcpyHostToDevice, w->s_h2d));
+	CK(cudaMemcpyAsync(w->px_in[k][1], d_vel, bytes, cudaMemcpyHostToDevice, w->s_h2d));
+	CK(cudaEventRecord(w->px_arrived[k], w->s_h2d));
+	w->px_sent[k] = true;
+	w->px_sent_n[k] = n_ents;
+	return BT_OK;
+}
+
+int bt_world_commit_host_deltas(bt_world *w) {
+	if (!w || !w->px_ready) return BT_ERR_ARG;
+	CK(cudaSetDevice(w->device));
+	const int k = w->px_commit_k;
+	if (!w->px_sent[k]) { snprintf(g_err, sizeof g_err, "bt_world_commit_host_deltas: nothing was sent"); return BT_ERR_ARG; }
+	{ int rr = fused_settle(w, false); if (rr) return rr; }
+	w->px_sent[k] = false;
+	w->px_commit_k ^= 1;
+	if ((i64)w->px_sent_n[k] != w->stats.live_ents) { /* an entity died since the batch was sent: its rows no longer line up */
+		snprintf(g_err, sizeof g_err, "bt_world_commit_host_deltas: %d rows were sent, the world holds %lld entities now", w->px_sent_n[k], (long long)w->stats.live_ents);
+		return BT_ERR_ARG;
+	}
+	bool dense = (i64)w->W.n == w->stats.live_ents;
+	if (!dense) { int r = ensure_ranks(w); if (r) return r; }
+	CK(cudaStreamWaitEvent(w->stream, w->px_arrived[k], 0));
+	LAUNCH(w, PK_EXCHANGE, k_add_deltas, nblk(w->W.n), BT_BLOCK, w->W, (const i32 *)w->px_in[k][0], (const i32 *)w->px_in[k][1],
+	       dense ? (const i32 *)NULL : (const i32 *)w->ray.slot2rank);
+	CK(cudaEventRecord(w->px_added[k], w->stream));
+	w->deltas_pending = true;
+	return BT_OK;
+}
+
+int bt_world_apply_host_deltas_async(bt_world *w, const int32_t *d_center, const int32_t *d_vel, int32_t n_ents) {
+	int r = bt_world_send_host_deltas(w, d_center, d_vel, n_ents);
+	return r ? r : bt_world_commit_host_deltas(w);
+}
+
+int bt_world_read_state_async(bt_world *w, int32_t *center, int32_t *vel, int32_t n_ents, int32_t *ticket) {
+	if (!w || !center || !vel || n_ents < 0 || !ticket) return BT_ERR_ARG;
+	CK(cudaSetDevice(w->device));
+	{ int rr = fused_settle(w, false); if (rr) return rr; }
+	if ((i64)n_ents != w->stats.live_ents) return BT_ERR_ARG;
+	{ int rr = px_init(w); if (rr) return rr; }
+	const int k = w->px_out_k;
+	w->px_out_k ^= 1;
+	const size_t bytes = sizeof(i32) * 3 * (size_t)n_ents;
+	bool dense = (i64)w->W.n == w->stats.live_ents;
+	if (!dense) { int r = ensure_ranks(w); if (r) return r; }
+	CK(cudaStreamWaitEvent(w->stream, w->px_read[k], 0)); /* the copy that last read this buffer is done */
+	LAUNCH(w, PK_EXCHANGE, k_pack_state, nblk(w->W.n), BT_BLOCK, w->W, w->px_out[k][0], w->px_out[k][1],
+	       dense ? (const i32 *)NULL : (const i32 *)w->ray.slot2rank);
+	CK(cudaEventRecord(w->px_packed[k], w->stream));
+	CK(cudaStreamWaitEvent(w->s_d2h, w->px_packed[k], 0));
+	CK(cudaMemcpyAsync(center, w->px_out[k][0], bytes, cudaMemcpyDeviceToHost, w->s_d2h));
+	CK(cudaMemcpyAsync(vel, w->px_out[k][1], bytes, cudaMemcpyDeviceToHost, w->s_d2h));
+	CK(cudaEventRecord(w->px_read[k], w->s_d2h));
+	*ticket = k;
+	CHECK_LAUNCHES(w);
+	return BT_OK;
+}
+
+int bt_world_read_state_wait(bt_world *w, int32_t ticket) {
+	if (!w || ticket < 0 || ticket > 1 || !w->px_ready) return BT_ERR_ARG;
+	CK(cudaSetDevice(w->device));
+	CK(cudaEventSynchronize(w->px_read[ticket]));
+	return BT_OK;
+}
+
 int bt_world_sync(bt_world *w) {
 	if (!w) return BT_ERR_ARG;
 	CK(cudaSetDevice(w->device));
 	CK(cudaStreamSynchronize(w->stream));
+	if (w->px_ready) { CK(cudaStreamSynchronize(w->s_h2d)); CK(cudaStreamSynchronize(w->s_d2h)); }
 	return BT_OK;
 }
 

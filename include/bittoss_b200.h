@@ -248,6 +248,24 @@ int bt_world_apply_host_deltas(bt_world *w, const int32_t *d_center, const int32
  * made this tick, applied in the order given before the next step.  Unknown (world, uid): BT_ERR_ARG. */
 int bt_world_apply_requests(bt_world *w, const bt_request *reqs, int32_t n);
 int bt_world_read_state(bt_world *w, int32_t *center, int32_t *vel, int32_t n_ents);
+/* The same exchange, PIPELINED (for a host whose next deltas do not wait for the state it reads back -- input-driven
+ * handlers, a renderer or recorder one tick behind): the copies run on two streams of their own, host -> device and
+ * device -> host, so that the transfers of neighbouring ticks overlap each other and the tick in between (PCIe is
+ * full duplex; a 1 M-entity world moves 24 MB each way per tick, about the time of the tick itself).
+ *   bt_world_send_host_deltas: the copy starts at once and nothing else happens -- call it BEFORE the step the deltas
+ *     must not reach (bt_world_step waits for its own tick, so a copy started after it cannot overlap it).
+ *     bt_world_commit_host_deltas: the oldest batch sent is added on the world's stream as soon as it has arrived, in front
+ *     of the next step enqueued; BT_ERR_ARG if an entity died since it was sent (its rows no longer line up: send
+ *     again).  bt_world_apply_host_deltas_async = send + commit.  The host arrays (PINNED memory, or the copy is not
+ *     asynchronous) must stay untouched until two more batches have been sent or bt_world_sync returned.
+ *   bt_world_read_state_async: packs the state behind everything enqueued so far and starts the copy; *ticket (0 / 1)
+ *     names it.  bt_world_read_state_wait(ticket) returns once `center` / `vel` hold it.  At most two reads in flight.
+ * Both use double buffers on the device (4 x 12 B per entity more, allocated at the first call). */
+int bt_world_send_host_deltas(bt_world *w, const int32_t *d_center, const int32_t *d_vel, int32_t n_ents);
+int bt_world_commit_host_deltas(bt_world *w);
+int bt_world_apply_host_deltas_async(bt_world *w, const int32_t *d_center, const int32_t *d_vel, int32_t n_ents);
+int bt_world_read_state_async(bt_world *w, int32_t *center, int32_t *vel, int32_t n_ents, int32_t *ticket);
+int bt_world_read_state_wait(bt_world *w, int32_t ticket);
 void *bt_world_stream(bt_world *w); /* the cudaStream_t every kernel of w runs on */
 
 /* Commutative 64-bit state hash per world over (uid, center, vel, typeMask,
