@@ -140,3 +140,29 @@ def test_cuda_fused_small_partial_phases_and_host_deltas(bt):
     assert f.stats()["kernel_launches"] < g.stats()["kernel_launches"] // 2
     f.close()
     g.close()
+
+
+@pytest.mark.gpu
+def test_cuda_fused_small_pair_list_overflow_walks_the_boxes(bt):
+    """a pile: every entity of the world within touching distance of most others, far more touching pairs than the
+    shared-memory pair list holds (12 per entity) -- the narrow phase then walks the box triangle itself; the generic
+    schedule (global list, no overflow) must see the same collisions, crushes included"""
+    wa, _ = load_scenario("arena_kick")
+    rng = np.random.RandomState(17)
+    n = wa.n
+    wa.a["center"][:] = rng.randint(-900, 901, size=3 * n).astype(np.int32)
+    wa.a["old"][:] = wa.a["center"]
+    wa.a["vel"][:] = rng.randint(-40, 41, size=3 * n).astype(np.int32)
+    batch = bt.concat_worlds([wa] * 5)
+    f, g = _pair(bt, batch)
+    for t in range(25):
+        f.step(31)
+        g.step(31)
+        assert np.array_equal(f.hash(), g.hash()), t
+    sf, sg = f.stats(), g.stats()
+    assert sf["positives"] == sg["positives"] and sf["positives"] > 20 * n   # a real pile
+    for k in ("pushes", "crushes", "fumbles", "live_ents"):
+        assert sf[k] == sg[k], (k, sf[k], sg[k])
+    _same_arrays(f.download(), g.download())
+    f.close()
+    g.close()
