@@ -1265,7 +1265,7 @@ static int px_init(bt_world *w) {
 }
 
 int bt_world_send_host_deltas(bt_world *w, const int32_t *d_center, const int32_t *d_vel, int32_t n_ents) {
-	if (!w || !d_center || !d_vel || n_ents < 0) return BT_ERR_ARG;
+	if (!w || !d_center || !d_vel || n_ents < 0 || n_ents > w->cap_ents) return BT_ERR_ARG;
 	CK(cudaSetDevice(w->device));
 	{ int rr = px_init(w); if (rr) return rr; }
 	if (w->px_sent[0] && w->px_sent[1]) { snprintf(g_err, sizeof g_err, "bt_world_send_host_deltas: two batches are already on their way, commit one first"); return BT_ERR_ARG; }
