@@ -1484,8 +1484,10 @@ static BT_HD void bt_push(const DevWorld &W, const Coll &c, u32 key, LocalStats 
 	/* the push is a chain of dependent gathers through handler code the compiler cannot
 	 * reorder; start everything it is going to touch on its way to L1 now */
 	bt_prefetch(&W.forced[e]); bt_prefetch(&W.friction[e]); bt_prefetch(&W.holder[e]); bt_prefetch(&W.hphys[e]);
-	bt_prefetch(&W.hphys[o]); bt_prefetch(&W.type[o]); bt_prefetch(&W.ibox[e]); bt_prefetch(&W.old[e]);
-	bt_prefetch(&W.forcedHoldees[e]); bt_prefetch(&W.holdee[e]); bt_prefetch(&W.hasBox[e]); bt_prefetch(&W.LLn[e]);
+	bt_prefetch(&W.hphys[o]); bt_prefetch(&W.ibox[e]); bt_prefetch(&W.old[e]);
+	bt_prefetch(&W.forcedHoldees[e]); bt_prefetch(&W.holdee[e]); bt_prefetch(&W.hasBox[e]);
+	/* (not type[o] and LLn[e]: a plain push -- handler NIL, nothing held -- never reads them, and the kernel is bound by
+	 * the sectors it moves) */
 	i32 displacement = (bt_get3(W.center[o], axis) - bt_get3(W.center[e], axis)) * dir + bt_get3(W.radius[e], axis) +
 	                   bt_get3(W.radius[o], axis);
 	i32 accel = (bt_get3(W.vel[o], axis) - bt_get3(W.vel[e], axis)) * dir;
