@@ -574,7 +574,7 @@ __global__ void __launch_bounds__(GS_BLOCK) k_hash_one(DevWorld W, u64 *sum, u32
  * 256 bytes queued behind it and the tick with them. */
 __global__ void __launch_bounds__(64) k_publish(const u32 *src, u32 *host_mapped, int n) { PDL_ENTRY_ALWAYS();
 	for (int i = threadIdx.x; i < n; i += 64) host_mapped[i] = src[i];
-	__threadfence_system();
+	/* no fence: the host reads after cudaStreamSynchronize, i.e. after the kernel has completed and its writes with it */
 }
 
 /* a single world's hash sum and entity count, the same way */
@@ -582,7 +582,6 @@ __global__ void k_publish_hash(const u64 *sum, const u32 *cnt, u32 *host_mapped)
 	if (threadIdx.x == 0) {
 		const u64 s = sum[0];
 		host_mapped[0] = (u32)s; host_mapped[1] = (u32)(s >> 32); host_mapped[2] = cnt[0];
-		__threadfence_system();
 	}
 }
 
