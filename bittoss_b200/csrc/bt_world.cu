@@ -155,6 +155,11 @@ template <typename T> static int dalloc(bt_world *w, T **p, size_t count) {
 	return 0;
 }
 
+/* Inflation of the boxes candidate pairs are cached with (worlds with a tree).  Measured on the 1 M-cube worlds, ms per
+ * tick settled / first 12 ticks of the push-all world: 32: 0.584 / 1.32, 48: 0.583 / 1.25, 56: 0.585 / -, 64: - / 1.15
+ * (but +14 % settled in round 1: neighbouring columns start to pair up), 96: - / 1.57.  Results never depend on it. */
+#define BT_TREE_MARGIN 48
+
 /* "pdl" auto: measured on single box-stack worlds, dependent launches gain 34 % at 20 k entities, 15 % at
  * 200 k, 8 % at 400 k, 2 % at 700 k and lose 3 % at 1 M */
 #define BT_PDL_MAX_ENTS (3 << 18)
@@ -336,7 +341,7 @@ int bt_world_create(bt_world **out, int device, int32_t max_ents, int32_t max_sl
 	TRY(dalloc(w, &W.iboxOld, n)); TRY(dalloc(w, &W.leafOf, n)); TRY(dalloc(w, &W.dirtyList, n)); TRY(dalloc(w, &W.dirtyStamp, n));
 	W.patch = 1; W.patch_shift = 4;
 	W.pair_cap = (i32)std::min<size_t>((size_t)1 << 30, 12 * n + 4096);
-	W.margin = 32;
+	W.margin = BT_TREE_MARGIN;
 	TRY(dalloc(w, &W.pairs, (size_t)W.pair_cap));
 	W.serial_cap = 1 << 16; W.dead_cap = max_ents > 0 ? max_ents : 1; W.event_cap = 1 << 16;
 	TRY(dalloc(w, &W.events, (size_t)W.event_cap));
@@ -391,7 +396,7 @@ int bt_world_set_option(bt_world *w, const char *name, int64_t value) {
 		w->small_worlds = value != 0;
 		if (!w->small_worlds && w->W.small_mode) {
 			w->W.small_mode = 0; w->tree_valid = false;
-			if (w->margin_opt < 0) w->W.margin = 32;
+			if (w->margin_opt < 0) w->W.margin = BT_TREE_MARGIN;
 		}
 		return BT_OK;
 	}
@@ -406,7 +411,7 @@ int bt_world_set_option(bt_world *w, const char *name, int64_t value) {
 	if (!strcmp(name, "run_ahead")) { w->run_ahead = value != 0; return BT_OK; }
 	if (!strcmp(name, "cache_margin")) { /* < 0: auto (32; 128 in small-world mode, where a rebuild is cheap but every one is global) */
 		w->margin_opt = value < 0 ? -1 : (i32)value;
-		w->W.margin = value < 0 ? (w->W.small_mode ? 128 : 32) : (i32)value;
+		w->W.margin = value < 0 ? (w->W.small_mode ? 128 : BT_TREE_MARGIN) : (i32)value;
 		return BT_OK;
 	}
 	return BT_ERR_ARG;
@@ -610,7 +615,7 @@ int bt_world_upload(bt_world *w, const bt_world_desc *d) {
 		for (int g = 0; g < nw; g++) biggest = std::max(biggest, wend[g] - wbegin[g]);
 		W.small_mode = (w->small_worlds && biggest <= BT_SMALL_WORLD) ? 1 : 0;
 		w->small_biggest = biggest;
-		if (w->margin_opt < 0) W.margin = W.small_mode ? 128 : 32;
+		if (w->margin_opt < 0) W.margin = W.small_mode ? 128 : BT_TREE_MARGIN;
 		/* Dependent launches pay when a tick is many short kernels (batched or small worlds: +5-7 %).
 		 * One big world spends its tick in two long kernels; there the resident waiting blocks cost
 		 * 0.1-0.4 % instead (measured A/B on the 1 M-entity world), so "auto" leaves them off. */
@@ -1751,7 +1756,7 @@ int bt_world_grow(bt_world *w, int32_t n_new, const int32_t *n_sliders, const in
 	w->sliders_used = s; w->wires_used = q;
 	if (W.small_mode && W.n > BT_SMALL_WORLD) { /* the brute-force pair search holds one world per block */
 		W.small_mode = 0;
-		if (w->margin_opt < 0) W.margin = 32;
+		if (w->margin_opt < 0) W.margin = BT_TREE_MARGIN;
 	}
 	w->tree_valid = false; /* the leaf set is about to change */
 	{ int rr = raise_cache_invalid(w); if (rr) return rr; }
