@@ -1606,7 +1606,7 @@ static BT_HD void t_post(const DevWorld &W, i32 e) {
  * TICK_RAND draws from gs->rand and therefore runs per world, in list order (t_tick_serial). */
 enum {
 	TICK_EXPLOSION = 1, TICK_PLATFORM = 3, TICK_THRUST = 10, TICK_BULLET = 25, TICK_HELD_BULLET = 26, TICK_DUST = 32,
-	TICK_INCINERATE = 40, TICK_BOTTLE_HELD = 41,
+	TICK_INCINERATE = 40, TICK_BOTTLE_HELD = 41, TICK_LEGG_OLD = 16, TICK_LEGG = 22, TICK_FACTORY = 20, TICK_FACTORY_WIRES = 21,
 	TICK_RAND = 6, TICK_EYE = 8, TICK_HELD_EYE = 9, TICK_HELD_VEH_EYE = 18, TICK_LOGIC = 11, TICK_LOGIC_DEBUG = 12, TICK_DOOR = 13, TICK_CURSED = 14, TICK_RESPAWN = 15,
 	TICK_SEAT_OLD = 17, TICK_ADJUST = 19, TICK_SEAT = 23, TICK_HELD_GUN = 24, TICK_SCOREBOARD = 27, TICK_TIMER = 28,
 	TICK_DEMOLISH = 29, TICK_HELD_BLINK = 30, TICK_HELD_JUMPER = 31, TICK_SPIDER = 33, TICK_SIGN = 34, TICK_LOADBLOCK = 35, TICK_PUDDLEJUMP = 36
@@ -1619,11 +1619,13 @@ enum {
 	(1ull << TICK_LOADBLOCK) | (1ull << TICK_PUDDLEJUMP) | (1ull << TICK_SPIDER) | (1ull << TICK_EYE) |                  \
 	(1ull << TICK_HELD_EYE) | (1ull << TICK_HELD_VEH_EYE) | (1ull << TICK_EXPLOSION) | (1ull << TICK_PLATFORM) |           \
 	(1ull << TICK_THRUST) | (1ull << TICK_BULLET) | (1ull << TICK_HELD_BULLET) | (1ull << TICK_DUST) |                   \
-	(1ull << TICK_BOTTLE) | (1ull << TICK_INCINERATE) | (1ull << TICK_BOTTLE_HELD))
+	(1ull << TICK_BOTTLE) | (1ull << TICK_INCINERATE) | (1ull << TICK_BOTTLE_HELD) | (1ull << TICK_LEGG_OLD) |          \
+	(1ull << TICK_LEGG) | (1ull << TICK_FACTORY) | (1ull << TICK_FACTORY_WIRES))
 /* the ones that run per world, in list order, after everybody else (t_tick_serial): they draw from gs->rand or mark many
  * other entities at once.  (TICK_DEPLETE, logic.c:110-121, writes a slider of its HOLDER directly, which the holder's own
  * handler may read in the same tick before or after, by list order: not reproducible from a parallel pass, left to the host.) */
-#define BT_SERIAL_TICK ((1ull << TICK_RAND) | (1ull << TICK_SCOREBOARD) | (1ull << TICK_INCINERATE))
+#define BT_SERIAL_TICK ((1ull << TICK_RAND) | (1ull << TICK_SCOREBOARD) | (1ull << TICK_INCINERATE) | (1ull << TICK_FACTORY) | \
+	(1ull << TICK_FACTORY_WIRES))
 
 static BT_HD int bt_button(const DevWorld &W, i32 e, int i) { return (int)(int8_t)((W.btn_v[e] >> (8 * i)) & 0xffu); }
 static BT_HD void bt_push_btn(const DevWorld &W, i32 e, int i) { bt_or32(&W.btn_v2[e], 1u << (8 * i)); }
@@ -1733,6 +1735,71 @@ static BT_HD void bt_scoreboard_tick(const DevWorld &W, i32 me) {
 	W.ctr[CT_FLUSH_HINT] = 1;
 }
 
+/* legg_tick / legg_tick_old legg.cpp:101-164 (a leg: tickHeld).  o = 2 / 1: where the gait sliders start.  The "fancy"
+ * max / min of legg.cpp:30-39 are kept as written (they wrap like the reference's on huge values). */
+static BT_HD i32 bt_legg_max(i32 a, i32 b) { return (a + b + bt_abs(a - b)) / 2; }
+static BT_HD i32 bt_legg_min(i32 a, i32 b) { return (a + b - bt_abs(a - b)) / 2; }
+static BT_HD i32 bt_bound1(i32 x, i32 b) { return x > b ? b : (x < -b ? -b : x); } /* bound entGetters.c:7-11 */
+static BT_HD void bt_legg_tick(const DevWorld &W, i32 me, int old_style) {
+	const i32 h = W.holder[me];
+	if (h < 0) return;
+	i32 v1[3] = {0, 0, 0};
+	if (old_style) { /* getInputOld :42-52: the wired entity's offset from ITS holder */
+		for (i32 k = 0; k < W.wire_cnt[me]; k++) {
+			const i32 w = W.wire_to[W.wire_off[me] + k], wh = W.holder[w];
+			if (wh < 0) continue;
+			const int4 a = W.center[wh], b = W.center[w];
+			v1[0] += b.x - a.x; v1[1] += b.y - a.y;
+		}
+	} else { /* getInput :55-63 */
+		const i32 width = bt_getslider(W, me, 1);
+		for (i32 k = 0; k < W.wire_cnt[me]; k++) {
+			const i32 w = W.wire_to[W.wire_off[me] + k];
+			v1[0] += bt_getslider(W, w, 0) * width / 64; v1[1] += bt_getslider(W, w, 1) * width / 64;
+		}
+	}
+	int o = old_style ? 1 : 2;
+	i32 counter = bt_getslider(W, me, 0);
+	i32 height = bt_getslider(W, me, o), stepHeight = bt_getslider(W, me, o + 1), tread = bt_getslider(W, me, o + 2);
+	i32 s = bt_getslider(W, me, o + 3);
+	const i32 a = bt_getslider(W, me, o + 4), time = bt_getslider(W, me, o + 5), v_time = bt_getslider(W, me, o + 6);
+	const int hasInput = v1[0] || v1[1];
+	const i32 half = time + v_time;
+	if (hasInput && half) {
+		counter++;
+		while (counter >= 2 * half) counter -= 2 * half;
+		bt_uslider_shared(W, me, 0, counter);
+		if (counter >= time) {
+			tread = 0;
+			if (counter < half + time) height -= stepHeight;
+		}
+		if (counter < half) { v1[0] *= -1; v1[1] *= -1; }
+	} else {
+		tread = 0;
+	}
+	v1[2] = height;
+	/* move :65-99 */
+	const int4 mc = W.center[me], hc = W.center[h], mv = W.vel[me], hv = W.vel[h];
+	i32 vel[3] = {hc.x - mc.x, hc.y - mc.y, hc.z - mc.z}, acc[3];
+	for (int i = 0; i < 3; i++) v1[i] += vel[i];
+	vel[0] = mv.x - hv.x; vel[1] = mv.y - hv.y; vel[2] = mv.z - hv.z;
+	i32 v_s = s;
+	const i32 dist = bt_legg_max(bt_abs(v1[0]), bt_abs(v1[1]));
+	if (dist) s = bt_legg_min(s, bt_approach_speed(W, me, dist, a));
+	bt_bound_vec(v1, s, 2);
+	for (int i = 0; i < 2; i++) acc[i] = v1[i] - vel[i];
+	bt_bound_vec(acc, a, 2);
+	const i32 new_speed = bt_legg_max(bt_abs(vel[0] + acc[0]), bt_abs(vel[1] + acc[1]));
+	if (s) v1[2] += tread * new_speed / s;
+	if (v1[2]) v_s = bt_legg_min(v_s, bt_approach_speed(W, me, bt_abs(v1[2]), a));
+	v1[2] = bt_bound1(v1[2], v_s);
+	acc[2] = bt_bound1(v1[2] - vel[2], a);
+	int4 dv = W.d_vel[me]; /* uVel(me, acc) */
+	dv.x += acc[0]; dv.y += acc[1]; dv.z += acc[2];
+	W.d_vel[me] = dv;
+	W.ctr[CT_ANY_DELTA] = 1;
+}
+
 /* one entity's tick / tickHeld handler.  Returns without effect for TICK_RAND and TICK_SCOREBOARD (serial pass). */
 static BT_HD void t_tick(const DevWorld &W, i32 me) {
 	if (me >= W.n || !W.inList[me]) return;
@@ -1825,6 +1892,8 @@ static BT_HD void t_tick(const DevWorld &W, i32 me) {
 		W.ctr[CT_ANY_DELTA] = 1;
 		return;
 	}
+	case TICK_LEGG: bt_legg_tick(W, me, 0); return;
+	case TICK_LEGG_OLD: bt_legg_tick(W, me, 1); return;
 	case TICK_SPIDER: { /* spider_tick spider.cpp:58-122 (a leg: tickHeld): a spring towards where the gait wants the foot,
 	                     * the reaction on the body; several legs add to one body, so uVel is an atomic add here */
 		const i32 h = W.holder[me];
@@ -1921,7 +1990,7 @@ static BT_HD void t_tick(const DevWorld &W, i32 me) {
 		bt_unsup(W, me, 6, id);
 		return;
 	}
-	case TICK_SCOREBOARD: case TICK_INCINERATE: return; /* per world, in list order (t_tick_serial) */
+	case TICK_SCOREBOARD: case TICK_INCINERATE: case TICK_FACTORY: case TICK_FACTORY_WIRES: return; /* per world, in list order (t_tick_serial) */
 	case TICK_BOTTLE: return; /* bottle_tick bottle.cpp:42-43 is empty */
 	case TICK_EXPLOSION: { /* explosion_tick explosion.cpp:12-19 */
 		const i32 timer = bt_getslider(W, me, 0);
@@ -2010,6 +2079,53 @@ static BT_HD void t_tick_serial(const DevWorld &W, int g) {
 		u32 ht = W.htick[me];
 		const u32 id = W.holder[me] >= 0 ? (ht >> 8) & 0xffu : ht & 0xffu;
 		if (id == TICK_SCOREBOARD) { bt_scoreboard_tick(W, me); continue; }
+		if (id == TICK_FACTORY) { /* factory_tick factory.cpp:63-73.  spawn() creates an entity: host side, counted.  What
+		                           * follows a spawn -- finalize (:30-61) of the wired product -- is all deferred updaters and
+		                           * writes to the product's own handler slots */
+			if (bt_button(W, me, 0) || bt_button(W, me, 1)) { bt_unsup(W, me, 6, (int)id); continue; }
+			if (!bt_button(W, me, 2) || !W.wire_cnt[me]) continue;
+			if (W.wire_cnt[me] == 1) {
+				const i32 e = W.wire_to[W.wire_off[me]];
+				/* a product is newer than its factory (spawn() prepends it to gs->ents), so in the reference's newest-first loop
+				 * it has had this tick's turn with its old handler when the factory rewrites the slot -- what the serial pass
+				 * behind the parallel one amounts to.  An OLDER entity wired in by hand would tick again with the new one */
+				if (e < me) bt_unsup(W, me, 6, (int)id);
+				int4 dv = W.d_vel[e]; /* uVel(e, sliders FACT_VEL..) */
+				dv.x += bt_getslider(W, me, 1); dv.y += bt_getslider(W, me, 2); dv.z += bt_getslider(W, me, 3);
+				W.d_vel[e] = dv;
+				W.ctr[CT_ANY_DELTA] = 1;
+				const u32 misc = (u32)bt_getslider(W, me, 7);
+				if (misc & 0x80000000u) { /* FACT_MISC_HOLD: whoever the factory's holder is wired to picks the product up */
+					const i32 h = W.holder[me];
+					if (h >= 0 && W.wire_cnt[h] == 1) bt_upickup(W, W.wire_to[W.wire_off[h]], e, W.holdFlags[me]);
+				}
+				for (int i = 0; i < 4; i++)
+					if (misc & (1u << i)) bt_push_btn(W, e, i);
+				W.fullFlush[e] = 1; /* uMyTypeMask / uMyCollideMask */
+				W.ntype[e] = (u32)bt_getslider(W, me, 4);
+				W.ncollide[e] = (u32)bt_getslider(W, me, 5);
+				W.ctr[CT_FLUSH_HINT] = 1;
+				W.htick[e] = ((u32)bt_getslider(W, me, 9) & 0xffu) | (((u32)bt_getslider(W, me, 10) & 0xffu) << 8);
+				W.hphys[e] = (W.hphys[e] & 0xffu) | (((u32)bt_getslider(W, me, 12) & 0xffu) << 8) | (((u32)bt_getslider(W, me, 13) & 0xffu) << 16) |
+				             (((u32)bt_getslider(W, me, 11) & 0xffu) << 24);
+				W.hpair[e] = ((u32)bt_getslider(W, me, 14) & 0xffu) | (((u32)bt_getslider(W, me, 15) & 0xffu) << 8) |
+				             (((u32)bt_getslider(W, me, 16) & 0xffu) << 16) | (((u32)bt_getslider(W, me, 17) & 0xffu) << 24);
+			}
+			for (i32 k = 0; k < W.wire_cnt[me]; k++) bt_uunwire(W, me, W.wire_to[W.wire_off[me] + k]);
+			continue;
+		}
+		if (id == TICK_FACTORY_WIRES) { /* factory_wires_tick factory.cpp:75-91 */
+			if (bt_button(W, me, 0) || bt_button(W, me, 1)) bt_push_btn(W, me, 2);
+			if (!bt_button(W, me, 2)) continue;
+			const i32 h = W.holder[me];
+			if (h < 0 || W.wire_cnt[h] != 1) continue;
+			const i32 e = W.wire_to[W.wire_off[h]];
+			for (i32 k = 0; k < W.wire_cnt[me]; k++) {
+				const i32 w = W.wire_to[W.wire_off[me] + k];
+				for (i32 j = 0; j < W.wire_cnt[w]; j++) bt_uwire(W, e, W.wire_to[W.wire_off[w] + j]);
+			}
+			continue;
+		}
 		if (id == TICK_INCINERATE) { /* incin_tick incinerate.cpp:15-32: everything fully beyond `range` dies */
 			if (bt_button(W, me, 0) ^ bt_button(W, me, 1)) continue;
 			const i32 range = bt_getslider(W, me, 0);

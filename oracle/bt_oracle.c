@@ -1351,7 +1351,7 @@ enum {
 	TICK_RAND = 6, TICK_LOGIC = 11, TICK_LOGIC_DEBUG = 12, TICK_DOOR = 13, TICK_CURSED = 14, TICK_RESPAWN = 15,
 	TICK_SEAT_OLD = 17, TICK_ADJUST = 19, TICK_SEAT = 23, TICK_SCOREBOARD = 27, TICK_TIMER = 28, TICK_DEMOLISH = 29, TICK_SIGN = 34,
 	TICK_LOADBLOCK = 35, TICK_PUDDLEJUMP = 36, TICK_SPIDER = 33, TICK_EYE = 8, TICK_HELD_EYE = 9, TICK_HELD_VEH_EYE = 18,
-	TICK_EXPLOSION = 1, TICK_PLATFORM = 3, TICK_THRUST = 10, TICK_BULLET = 25, TICK_HELD_BULLET = 26, TICK_DUST = 32, TICK_INCINERATE = 40
+	TICK_EXPLOSION = 1, TICK_PLATFORM = 3, TICK_THRUST = 10, TICK_BULLET = 25, TICK_HELD_BULLET = 26, TICK_DUST = 32, TICK_INCINERATE = 40, TICK_LEGG_OLD = 16, TICK_LEGG = 22, TICK_FACTORY = 20, TICK_FACTORY_WIRES = 21
 };
 static int getButton(const World *w, i32 e, int i) { return (int)(signed char)w->btn[e][i]; }
 static void pushBtn(World *w, i32 e, int i) { w->btn[e][4 + i] = 1; }
@@ -1408,6 +1408,61 @@ static void door_tick(World *w, i32 me) { /* door.c:14-62 */
 	boundVec(vel, accel, 3);
 	for (int i = 0; i < 3; i++) w->d_vel[me][i] += vel[i]; /* uVel */
 }
+/* legg.cpp:30-164 */
+static i32 leggMax(i32 a, i32 b) { return (a + b + abs(a - b)) / 2; }
+static i32 leggMin(i32 a, i32 b) { return (a + b - abs(a - b)) / 2; }
+static i32 bound1(i32 x, i32 b) { return x > b ? b : (x < -b ? -b : x); }
+static void legg_tick(World *w, i32 me, int old_style) {
+	i32 h = w->holder[me];
+	if (h < 0) return;
+	i32 v1[3] = {0, 0, 0};
+	if (old_style) {
+		for (int k = 0; k < w->wires[me].num; k++) {
+			i32 x = w->wires[me].items[k], xh = w->holder[x];
+			if (xh < 0) continue;
+			for (int i = 0; i < 2; i++) v1[i] += w->center[x][i] - w->center[xh][i];
+		}
+	} else {
+		i32 width = getSlider(w, me, 1);
+		for (int k = 0; k < w->wires[me].num; k++)
+			for (int i = 0; i < 2; i++) v1[i] += getSlider(w, w->wires[me].items[k], i) * width / 64;
+	}
+	int o = old_style ? 1 : 2;
+	i32 counter = getSlider(w, me, 0);
+	i32 height = getSlider(w, me, o), stepHeight = getSlider(w, me, o + 1), tread = getSlider(w, me, o + 2);
+	i32 s = getSlider(w, me, o + 3), a = getSlider(w, me, o + 4), time = getSlider(w, me, o + 5), v_time = getSlider(w, me, o + 6);
+	int hasInput = v1[0] || v1[1];
+	i32 half = time + v_time;
+	if (hasInput && half) {
+		counter++;
+		while (counter >= 2 * half) counter -= 2 * half;
+		uSlider(w, me, 0, counter);
+		if (counter >= time) {
+			tread = 0;
+			if (counter < half + time) height -= stepHeight;
+		}
+		if (counter < half) { v1[0] *= -1; v1[1] *= -1; }
+	} else {
+		tread = 0;
+	}
+	v1[2] = height;
+	i32 vel[3], acc[3];
+	for (int i = 0; i < 3; i++) v1[i] += w->center[h][i] - w->center[me][i];
+	for (int i = 0; i < 3; i++) vel[i] = w->vel[me][i] - w->vel[h][i];
+	i32 v_s = s;
+	i32 dist = leggMax(abs(v1[0]), abs(v1[1]));
+	if (dist) s = leggMin(s, getApproachSpeed(dist, a));
+	boundVec(v1, s, 2);
+	for (int i = 0; i < 2; i++) acc[i] = v1[i] - vel[i];
+	boundVec(acc, a, 2);
+	i32 new_speed = leggMax(abs(vel[0] + acc[0]), abs(vel[1] + acc[1]));
+	if (s) v1[2] += tread * new_speed / s;
+	if (v1[2]) v_s = leggMin(v_s, getApproachSpeed(abs(v1[2]), a));
+	v1[2] = bound1(v1[2], v_s);
+	acc[2] = bound1(v1[2] - vel[2], a);
+	for (int i = 0; i < 3; i++) w->d_vel[me][i] += acc[i];
+}
+
 static void tickOne(World *w, int g, i32 me) {
 	int id = w->h[me][w->holder[me] >= 0 ? BT_H_TICKHELD : BT_H_TICK];
 	switch (id) {
@@ -1558,6 +1613,45 @@ static void tickOne(World *w, int g, i32 me) {
 		for (int i = 0; i < 3; i++) w->d_center[me][i] += vec[i] * w->radius[p][i] / 64 - (w->center[me][i] - w->center[p][i]);
 		break;
 	}
+	case TICK_FACTORY: { /* factory.cpp:63-73; spawn() (entity creation) is the host's */
+		if (getButton(w, me, 0) || getButton(w, me, 1)) break;
+		if (!getButton(w, me, 2) || !w->wires[me].num) break;
+		if (w->wires[me].num == 1) { /* finalize :30-61 */
+			i32 e = w->wires[me].items[0];
+			for (int i = 0; i < 3; i++) w->d_vel[e][i] += getSlider(w, me, 1 + i);
+			uint32_t misc = (uint32_t)getSlider(w, me, 7);
+			if (misc & 0x80000000u) {
+				i32 h = w->holder[me];
+				if (h >= 0 && w->wires[h].num == 1) uPickup(w, w->wires[h].items[0], e, w->holdFlags[me]);
+			}
+			for (int i = 0; i < 4; i++)
+				if (misc & (1u << i)) pushBtn(w, e, i);
+			w->fullFlush[e] = 1;
+			w->ntype[e] = (uint32_t)getSlider(w, me, 4);
+			w->ncollide[e] = (uint32_t)getSlider(w, me, 5);
+			w->h[e][BT_H_TICK] = getSlider(w, me, 9) & 0xff; w->h[e][BT_H_TICKHELD] = getSlider(w, me, 10) & 0xff;
+			w->h[e][BT_H_CRUSH] = getSlider(w, me, 11) & 0xff; w->h[e][BT_H_PUSH] = getSlider(w, me, 12) & 0xff;
+			w->h[e][BT_H_PUSHED] = getSlider(w, me, 13) & 0xff; w->h[e][BT_H_ONFUMBLE] = getSlider(w, me, 14) & 0xff;
+			w->h[e][BT_H_ONFUMBLED] = getSlider(w, me, 15) & 0xff; w->h[e][BT_H_ONPICKUP] = getSlider(w, me, 16) & 0xff;
+			w->h[e][BT_H_ONPICKEDUP] = getSlider(w, me, 17) & 0xff;
+		}
+		for (int k = 0; k < w->wires[me].num; k++) il_add(&w->wiresRm[me], w->wires[me].items[k]);
+		break;
+	}
+	case TICK_FACTORY_WIRES: { /* factory.cpp:75-91 */
+		if (getButton(w, me, 0) || getButton(w, me, 1)) pushBtn(w, me, 2);
+		if (!getButton(w, me, 2)) break;
+		i32 h = w->holder[me];
+		if (h < 0 || w->wires[h].num != 1) break;
+		i32 e = w->wires[h].items[0];
+		for (int k = 0; k < w->wires[me].num; k++) {
+			i32 x = w->wires[me].items[k];
+			for (int j = 0; j < w->wires[x].num; j++) { w->fullFlush[e] = 1; il_add(&w->wiresAdd[e], w->wires[x].items[j]); }
+		}
+		break;
+	}
+	case TICK_LEGG: legg_tick(w, me, 0); break;
+	case TICK_LEGG_OLD: legg_tick(w, me, 1); break;
 	case TICK_SPIDER: { /* spider.cpp:58-122 */
 		i32 h = w->holder[me];
 		if (h < 0) break;

@@ -311,9 +311,26 @@ def lab_pilots(R):
     R.lab_add_wire(veye, vseat)
     R.lab_add_wire(vseat, stick)                                   # the puddlejumper's pilot drives this one too
     script.append((0, REQ_PICKUP, car, veye, HOLD_DROP, 0, 0))
+    # leggs (legg.cpp): a walker body on a floor holds two new-style leggs wired to the spider's input block, and one old-style
+    # legg wired to the vehicle eye (its input = the eye's offset from the car that holds it)
+    pad(R, 20000, 20000, r=(8000, 8000, 300), z=400)
+    wbody = cube(R, 20000, 20000, -1100, r=500)
+    for k, dx in enumerate((-700, 700)):
+        lg = R.add_ent((20000 + dx, 20000, -500), (0, 0, 0), (150, 150, 150), CUBE, CUBE_COLLIDE, WM_WOOD)
+        R.lab_set_handlers(lg, tick_held=TICK_LEGG)
+        # counter, width, height, stepHeight, tread, speed, accel, time, v_time
+        R.lab_set_sliders(lg, [4 * k, 500, 600, 250, 40, 60, 12, 8, 3])
+        R.lab_add_wire(lg, walk)
+        script.append((0, REQ_PICKUP, wbody, lg, HOLD_MOVE, 0, 0))
+    lo = R.add_ent((20000, 20700, -500), (0, 0, 0), (150, 150, 150), CUBE, CUBE_COLLIDE, WM_WOOD)
+    R.lab_set_handlers(lo, tick_held=TICK_LEGG_OLD)
+    R.lab_set_sliders(lo, [0, 600, 250, 40, 60, 12, 8, 3])   # counter, height, stepHeight, tread, speed, accel, time, v_time
+    R.lab_add_wire(lo, veye)
+    script.append((0, REQ_PICKUP, wbody, lo, HOLD_MOVE, 0, 0))
     return 90, script, 0
 
 
+TICK_LEGG_OLD, TICK_LEGG = 16, 22
 TICK_EYE, TICK_HELD_EYE, TICK_HELD_VEH_EYE = 8, 9, 18
 TICK_EXPLOSION, TICK_PLATFORM, TICK_THRUST, TICK_BULLET, TICK_HELD_BULLET, TICK_DUST, TICK_INCINERATE = 1, 3, 10, 25, 26, 32, 40
 REQ_BUTTON = 3
@@ -361,6 +378,28 @@ def lab_ticks2(R):
     script += [(t, REQ_BUTTON, inc, -1, 0, 0, 0) for t in range(0, 40)]
     far = cube(R, 9000, 0, -3000)            # fully beyond 7000 on x: dies when the incinerator comes on
     near = cube(R, 6000, 0, -3000)           # 6000 - 400 < 7000: stays
+    # factory.cpp without the spawn (entity creation is the host's): a factory told to finalize its wired product (velocity,
+    # masks, buttons, handler slots, then it unwires), and a factory-wires block copying the wires of its inputs to the
+    # entity its holder is wired to
+    fac = gate(R, -2000, 3000, -3500, 20, [0, 6, -4, 2, CUBE, CUBE_COLLIDE, 0xff00, 2 | 8, WM_WOOD, TICK_BULLET, 0, 0, 0, 2, 0, 3, 0, 0, 25])
+    # the product is NEWER than its factory, as after a real spawn() (initEnt prepends to gs->ents): it has had its tick by
+    # the time the factory, later in the list, gives it its handlers
+    prod = R.add_ent((-2000, 3000, -2500), (0, 0, 0), (200, 200, 200), T_WEIGHTLESS, 0, WM_ME)
+    R.lab_set_sliders(prod, [0, 0, 0])
+    R.lab_add_wire(fac, prod)
+    script.append((5, REQ_BUTTON, fac, -1, 2, 0, 0))
+    target = gate(R, -2000, 4000, -3500, 0, [0])
+    R.lab_set_handlers(target, pair=(-1, -1, PICKUP_SEAT, -1))   # a seat: its wire block has one spare slot on the device
+    hh = cube(R, -2000, 5000, -800)
+    R.lab_add_wire(hh, target)
+    fw = R.add_ent((-2000, 5000, -1500), (0, 0, 0), (100, 100, 100), T_WEIGHTLESS, 0, WM_ME)
+    R.lab_set_handlers(fw, tick=21, tick_held=21)
+    srcs = [gate(R, -2500 + 200 * k, 5500, -3500, 0, [0]) for k in range(2)]
+    for sgate in srcs:
+        R.lab_add_wire(fw, sgate)
+    R.lab_add_wire(srcs[0], m); R.lab_add_wire(srcs[1], m)       # the same target twice: one new wire
+    script.append((0, REQ_PICKUP, hh, fw, HOLD_MOVE, 0, 0))
+    script.append((8, REQ_BUTTON, fw, -1, 0, 0, 0))
     return 60, script, 0
 
 
