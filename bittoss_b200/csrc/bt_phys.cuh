@@ -1606,7 +1606,7 @@ static BT_HD void t_post(const DevWorld &W, i32 e) {
  * TICK_RAND draws from gs->rand and therefore runs per world, in list order (t_tick_serial). */
 enum {
 	TICK_EXPLOSION = 1, TICK_PLATFORM = 3, TICK_THRUST = 10, TICK_BULLET = 25, TICK_HELD_BULLET = 26, TICK_DUST = 32,
-	TICK_INCINERATE = 40, TICK_BOTTLE_HELD = 41, TICK_LEGG_OLD = 16, TICK_LEGG = 22, TICK_FACTORY = 20, TICK_FACTORY_WIRES = 21,
+	TICK_INCINERATE = 40, TICK_BOTTLE_HELD = 41, TICK_LEGG_OLD = 16, TICK_LEGG = 22, TICK_FACTORY = 20, TICK_FACTORY_WIRES = 21, TICK_FLAG_SPAWNER = 2,
 	TICK_RAND = 6, TICK_EYE = 8, TICK_HELD_EYE = 9, TICK_HELD_VEH_EYE = 18, TICK_LOGIC = 11, TICK_LOGIC_DEBUG = 12, TICK_DOOR = 13, TICK_CURSED = 14, TICK_RESPAWN = 15,
 	TICK_SEAT_OLD = 17, TICK_ADJUST = 19, TICK_SEAT = 23, TICK_HELD_GUN = 24, TICK_SCOREBOARD = 27, TICK_TIMER = 28,
 	TICK_DEMOLISH = 29, TICK_HELD_BLINK = 30, TICK_HELD_JUMPER = 31, TICK_SPIDER = 33, TICK_SIGN = 34, TICK_LOADBLOCK = 35, TICK_PUDDLEJUMP = 36
@@ -1620,7 +1620,7 @@ enum {
 	(1ull << TICK_HELD_EYE) | (1ull << TICK_HELD_VEH_EYE) | (1ull << TICK_EXPLOSION) | (1ull << TICK_PLATFORM) |           \
 	(1ull << TICK_THRUST) | (1ull << TICK_BULLET) | (1ull << TICK_HELD_BULLET) | (1ull << TICK_DUST) |                   \
 	(1ull << TICK_BOTTLE) | (1ull << TICK_INCINERATE) | (1ull << TICK_BOTTLE_HELD) | (1ull << TICK_LEGG_OLD) |          \
-	(1ull << TICK_LEGG) | (1ull << TICK_FACTORY) | (1ull << TICK_FACTORY_WIRES))
+	(1ull << TICK_LEGG) | (1ull << TICK_FACTORY) | (1ull << TICK_FACTORY_WIRES) | (1ull << TICK_FLAG_SPAWNER))
 /* the ones that run per world, in list order, after everybody else (t_tick_serial): they draw from gs->rand or mark many
  * other entities at once.  (TICK_DEPLETE, logic.c:110-121, writes a slider of its HOLDER directly, which the holder's own
  * handler may read in the same tick before or after, by list order: not reproducible from a parallel pass, left to the host.) */
@@ -1890,6 +1890,16 @@ static BT_HD void t_tick(const DevWorld &W, i32 me) {
 		dc.z += vec[2] * pr.z / 64 - (mc.z - pc.z);
 		W.d_center[me] = dc;
 		W.ctr[CT_ANY_DELTA] = 1;
+		return;
+	}
+	case TICK_FLAG_SPAWNER: { /* flagSpawner_tick flag.c:36-45: idle while its flag (its one wire) exists; making a new one is
+	                           * entity creation: host side, counted */
+		const i32 cooldown = bt_getslider(W, me, 0);
+		if (cooldown == 0) {
+			if (!W.wire_cnt[me]) bt_unsup(W, me, 6, id);
+			return;
+		}
+		bt_uslider_shared(W, me, 0, cooldown - 1);
 		return;
 	}
 	case TICK_LEGG: bt_legg_tick(W, me, 0); return;

@@ -1351,7 +1351,7 @@ enum {
 	TICK_RAND = 6, TICK_LOGIC = 11, TICK_LOGIC_DEBUG = 12, TICK_DOOR = 13, TICK_CURSED = 14, TICK_RESPAWN = 15,
 	TICK_SEAT_OLD = 17, TICK_ADJUST = 19, TICK_SEAT = 23, TICK_SCOREBOARD = 27, TICK_TIMER = 28, TICK_DEMOLISH = 29, TICK_SIGN = 34,
 	TICK_LOADBLOCK = 35, TICK_PUDDLEJUMP = 36, TICK_SPIDER = 33, TICK_EYE = 8, TICK_HELD_EYE = 9, TICK_HELD_VEH_EYE = 18,
-	TICK_EXPLOSION = 1, TICK_PLATFORM = 3, TICK_THRUST = 10, TICK_BULLET = 25, TICK_HELD_BULLET = 26, TICK_DUST = 32, TICK_INCINERATE = 40, TICK_LEGG_OLD = 16, TICK_LEGG = 22, TICK_FACTORY = 20, TICK_FACTORY_WIRES = 21
+	TICK_EXPLOSION = 1, TICK_PLATFORM = 3, TICK_THRUST = 10, TICK_BULLET = 25, TICK_HELD_BULLET = 26, TICK_DUST = 32, TICK_INCINERATE = 40, TICK_LEGG_OLD = 16, TICK_LEGG = 22, TICK_FACTORY = 20, TICK_FACTORY_WIRES = 21, TICK_FLAG_SPAWNER = 2
 };
 static int getButton(const World *w, i32 e, int i) { return (int)(signed char)w->btn[e][i]; }
 static void pushBtn(World *w, i32 e, int i) { w->btn[e][4 + i] = 1; }
@@ -1648,6 +1648,12 @@ static void tickOne(World *w, int g, i32 me) {
 			i32 x = w->wires[me].items[k];
 			for (int j = 0; j < w->wires[x].num; j++) { w->fullFlush[e] = 1; il_add(&w->wiresAdd[e], w->wires[x].items[j]); }
 		}
+		break;
+	}
+	case TICK_FLAG_SPAWNER: { /* flag.c:36-45; mkFlag (entity creation) is the host's */
+		i32 cooldown = getSlider(w, me, 0);
+		if (cooldown == 0) break;
+		uSlider(w, me, 0, cooldown - 1);
 		break;
 	}
 	case TICK_LEGG: legg_tick(w, me, 0); break;
