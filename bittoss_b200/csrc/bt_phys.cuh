@@ -1620,7 +1620,8 @@ enum {
 	(1ull << TICK_HELD_EYE) | (1ull << TICK_HELD_VEH_EYE) | (1ull << TICK_EXPLOSION) | (1ull << TICK_PLATFORM) |           \
 	(1ull << TICK_THRUST) | (1ull << TICK_BULLET) | (1ull << TICK_HELD_BULLET) | (1ull << TICK_DUST) |                   \
 	(1ull << TICK_BOTTLE) | (1ull << TICK_INCINERATE) | (1ull << TICK_BOTTLE_HELD) | (1ull << TICK_LEGG_OLD) |          \
-	(1ull << TICK_LEGG) | (1ull << TICK_FACTORY) | (1ull << TICK_FACTORY_WIRES) | (1ull << TICK_FLAG_SPAWNER))
+	(1ull << TICK_LEGG) | (1ull << TICK_FACTORY) | (1ull << TICK_FACTORY_WIRES) | (1ull << TICK_FLAG_SPAWNER) |          \
+	(1ull << TICK_PLAYER))
 /* the ones that run per world, in list order, after everybody else (t_tick_serial): they draw from gs->rand or mark many
  * other entities at once.  (TICK_DEPLETE, logic.c:110-121, writes a slider of its HOLDER directly, which the holder's own
  * handler may read in the same tick before or after, by list order: not reproducible from a parallel pass, left to the host.) */
@@ -1800,6 +1801,111 @@ static BT_HD void bt_legg_tick(const DevWorld &W, i32 me, int old_style) {
 	W.ctr[CT_ANY_DELTA] = 1;
 }
 
+/* player_tick player.c:229-443.  The controls are sliders and buttons the host's doInputs writes (axis 0 / 1, look 2..4,
+ * the extra buttons in slider 12; jump = button 0, shift = 1, triggers = 2 / 3), so walking, jumping, dropping and
+ * swapping equipment, charge and cooldown all run here.  What creates entities does not: a stackem block or a platform
+ * fired (mkStackem / mkPlatform, the second draws from gs->rand) and the edit tool's baubles are counted as unsupported,
+ * with the sliders advanced as the reference would have. */
+static BT_HD int bt_equip_hands(const DevWorld &W, i32 e) { /* getEquipHands :217-227 */
+	const u32 f = W.type[e] & EQUIP_MASK;
+	if (!f) return 0;
+	if (f == EQUIP_MASK) return 3;
+	return 1 + (bt_getslider(W, e, 0) != 0);
+}
+static BT_HD void bt_uvel_other(const DevWorld &W, i32 e, const i32 *v, int center_too) {
+	i32 *dv = (i32 *)&W.d_vel[e], *dc = (i32 *)&W.d_center[e];
+	for (int i = 0; i < 3; i++) {
+		bt_add32((u32 *)&dv[i], (u32)v[i]);
+		if (center_too) bt_add32((u32 *)&dc[i], (u32)v[i]);
+	}
+	W.ctr[CT_ANY_DELTA] = 1;
+}
+static BT_HD void bt_player_tick(const DevWorld &W, i32 me, int id) {
+	const int grounded = bt_getslider(W, me, 7) > 0;
+	bt_uslider_shared(W, me, 7, 0);
+	{
+		const i32 axis[2] = {bt_getslider(W, me, 0), bt_getslider(W, me, 1)};
+		i32 sl[2] = {bt_getslider(W, me, 5), bt_getslider(W, me, 6)};
+		i32 speed;
+		if (!grounded) { bt_bound_vec(sl, 256, 2); speed = 256; } /* PLAYER_SPD */
+		else {
+			speed = bt_abs(sl[0]) > bt_abs(sl[1]) ? bt_abs(sl[0]) : bt_abs(sl[1]); /* getMagnitude common.c:39-46 */
+			if (speed < 256) speed = 256;
+		}
+		i32 vel[3];
+		vel[2] = bt_button(W, me, 0) && grounded ? -384 : 0;
+		for (int i = 0; i < 2; i++) vel[i] = speed * axis[i] / 64 - sl[i];
+		bt_bound_vec(vel, grounded ? 56 : 16, 2);
+		for (int i = 0; i < 2; i++) bt_uslider_shared(W, me, 5 + i, sl[i] + vel[i]);
+		int4 dv = W.d_vel[me]; /* uVel(me, vel) */
+		dv.x += vel[0]; dv.y += vel[1]; dv.z += vel[2];
+		W.d_vel[me] = dv;
+		W.ctr[CT_ANY_DELTA] = 1;
+	}
+	i32 charge = bt_getslider(W, me, 8), cooldown = bt_getslider(W, me, 9);
+	const int fire = bt_button(W, me, 2), fire2 = bt_button(W, me, 3), utility = bt_button(W, me, 1);
+	const i32 other = bt_getslider(W, me, 12);
+	const int altfire = (other & 1) != 0, altfire2 = (other & 2) != 0;
+	if (bt_getslider(W, me, 11)) { /* edit mode */
+		for (int mode = 0; mode < 2; mode++) { /* player_clearBaubles :198-204 */
+			if (!(mode ? altfire2 : altfire)) continue;
+			for (i32 h = W.holdee[me]; h >= 0; h = W.LLn[h])
+				if ((W.type[h] & 64u) && W.wire_cnt[h] == 1 && mode == bt_getslider(W, h, 0)) { W.newDrop[h] = 1; W.wflush[W.world[h]] = 1; W.ctr[CT_FLUSH_HINT] = 1; }
+		}
+		if (cooldown >= 3) {
+			if (utility && bt_button(W, me, 0)) { /* player_flipBaubles :206-215 */
+				for (i32 h = W.holdee[me]; h >= 0; h = W.LLn[h])
+					if ((W.type[h] & 64u) && W.wire_cnt[h] == 1) bt_push_btn(W, h, 2);
+				cooldown = 0;
+			} else if (fire || fire2) { /* edittool_select makes baubles */
+				bt_unsup(W, me, 6, id);
+				cooldown = 0;
+			}
+		}
+	} else {
+		int hands = 0, drops = 0;
+		for (i32 h = W.holdee[me]; h >= 0; h = W.LLn[h]) {
+			const int eh = bt_equip_hands(W, h);
+			drops |= hands & eh;
+			hands |= eh;
+		}
+		i32 ep = bt_getslider(W, me, 10);
+		ep &= ~1;
+		if (altfire) { if (!(ep & 2)) { ep |= 2; drops |= 1; } } else ep &= ~2;
+		if (altfire2) { if (!(ep & 4)) { ep |= 4; drops |= 2; } } else ep &= ~4;
+		if (fire) { if (hands & 1) ep |= 8; } else ep &= ~8;
+		if (fire2) { if (hands & 2) ep |= 16; } else ep &= ~16;
+		bt_uslider_shared(W, me, 10, ep);
+		const i32 look[3] = {bt_getslider(W, me, 2), bt_getslider(W, me, 3), bt_getslider(W, me, 4)};
+		if (drops) {
+			if (drops & hands) {
+				const i32 v[3] = {200 * look[0] / 64, 200 * look[1] / 64, 200 * look[2] / 64};
+				for (i32 h = W.holdee[me]; h >= 0; h = W.LLn[h])
+					if (drops & bt_equip_hands(W, h)) {
+						bt_uvel_other(W, h, v, 1);
+						W.newDrop[h] = 1; W.wflush[W.world[h]] = 1; W.ctr[CT_FLUSH_HINT] = 1; /* uDrop */
+					}
+			} else { /* nothing in that hand: move the off-hand item over */
+				for (i32 h = W.holdee[me]; h >= 0; h = W.LLn[h])
+					if (W.type[h] & EQUIP_MASK) bt_uslider_shared(W, h, 0, drops - 1);
+			}
+		}
+		if (hands == 3) return;
+		if (cooldown >= 5 && charge >= 60) {
+			const i32 rules = W.gamerules[W.world[me]];
+			if (fire && !(hands & 1) && !(ep & 8) && !(rules & (1 << 7))) { /* mkStackem */
+				bt_unsup(W, me, 6, id);
+				charge -= 60; cooldown = 0;
+			} else if (charge >= 180 && fire2 && !(hands & 2) && !(ep & 16) && !(rules & (1 << 8))) { /* mkPlatform, random() */
+				bt_unsup(W, me, 6, id);
+				charge -= 180; cooldown = 0;
+			}
+		}
+	}
+	if (charge < 180) bt_uslider_shared(W, me, 8, charge + 2);
+	if (cooldown < 5) bt_uslider_shared(W, me, 9, cooldown + 1);
+}
+
 /* one entity's tick / tickHeld handler.  Returns without effect for TICK_RAND and TICK_SCOREBOARD (serial pass). */
 static BT_HD void t_tick(const DevWorld &W, i32 me) {
 	if (me >= W.n || !W.inList[me]) return;
@@ -1902,6 +2008,7 @@ static BT_HD void t_tick(const DevWorld &W, i32 me) {
 		bt_uslider_shared(W, me, 0, cooldown - 1);
 		return;
 	}
+	case TICK_PLAYER: bt_player_tick(W, me, id); return;
 	case TICK_LEGG: bt_legg_tick(W, me, 0); return;
 	case TICK_LEGG_OLD: bt_legg_tick(W, me, 1); return;
 	case TICK_SPIDER: { /* spider_tick spider.cpp:58-122 (a leg: tickHeld): a spring towards where the gait wants the foot,
@@ -1993,11 +2100,37 @@ static BT_HD void t_tick(const DevWorld &W, i32 me) {
 	}
 	case TICK_HELD_GUN: case TICK_HELD_BLINK: case TICK_HELD_JUMPER: {
 		/* gun_tick_held gun.c:41-88, blink_tick_held blink.c:33-60, jumper_tick_held jumper.c:39-70: "doesn't do anything
-		 * unless held by a person (or similar)".  Held by one, they read the holder's trigger (host-side control state)
-		 * and create bullets / dust: not here */
+		 * unless held by a person (or similar)".  Held by one they count their cooldown down and reload; pulling the
+		 * holder's trigger (getTrigger entGetters.c:27-29 = button 2 + hand) creates a bullet / a dust cloud: the host's */
 		const i32 h = W.holder[me];
 		if (h < 0 || !(W.type[h] & T_INPUTS) || W.holder[h] >= 0) return;
-		bt_unsup(W, me, 6, id);
+		const int trigger = bt_button(W, h, 2 + (bt_getslider(W, me, 0) != 0));
+		if (id == TICK_HELD_GUN) { /* sliders: hand, ammo, cooldown, reload, ammo max, cooldown max, reload max, speed */
+			const i32 cooldown = bt_getslider(W, me, 2), ammo = bt_getslider(W, me, 1);
+			if (cooldown > 1) bt_uslider(W, me, 2, cooldown - 1);
+			else if (trigger && ammo) { bt_unsup(W, me, 6, id); return; }
+			const i32 ammo_max = bt_getslider(W, me, 4);
+			if (ammo != ammo_max) {
+				const i32 reload = bt_getslider(W, me, 3) + 1;
+				if (reload >= bt_getslider(W, me, 6)) { bt_uslider(W, me, 3, 0); bt_uslider(W, me, 1, ammo_max); }
+				else bt_uslider(W, me, 3, reload);
+			}
+		} else if (id == TICK_HELD_BLINK) { /* hand, cooldown, cooldown max, range */
+			const i32 cooldown = bt_getslider(W, me, 1);
+			if (cooldown > 0) bt_uslider(W, me, 1, cooldown - 1);
+			else if (trigger) bt_unsup(W, me, 6, id);
+		} else { /* jumper: hand, ammo, reload, cooldown, ammo max, reload max, cooldown max, speed */
+			i32 ammo = bt_getslider(W, me, 1);
+			if (ammo < bt_getslider(W, me, 4)) {
+				i32 reload = 1 + bt_getslider(W, me, 2);
+				if (reload >= bt_getslider(W, me, 5)) { reload = 0; ammo++; }
+				bt_uslider(W, me, 2, reload);
+			}
+			const i32 cooldown = bt_getslider(W, me, 3);
+			if (cooldown > 0) bt_uslider(W, me, 3, cooldown - 1);
+			else if (ammo && trigger) { bt_unsup(W, me, 6, id); return; }
+			bt_uslider(W, me, 1, ammo);
+		}
 		return;
 	}
 	case TICK_SCOREBOARD: case TICK_INCINERATE: case TICK_FACTORY: case TICK_FACTORY_WIRES: return; /* per world, in list order (t_tick_serial) */

@@ -108,13 +108,14 @@ typedef struct bt_world_desc {
  * bt_world_tick adds it when a world's gamerules ask for one of them.  createDebris
  * (EFFECT_BLOCKS) creates entities and stays on the host. */
 #define BT_PHASE_WORLD_RULES 32u
-/* The tick handlers of doUpdates (ent.cpp:826-832) that have a device implementation (37 of the catalog's 42): the logic
+/* The tick handlers of doUpdates (ent.cpp:826-832) that have a device implementation (38 of the catalog's 42): the logic
  * family (logic.c: LOGIC, LOGIC_DEBUG, TIMER, ADJUST, DEMOLISH, RAND), DOOR (door.c), CURSED, SEAT / SEAT_OLD
  * (seat.cpp), SIGN, LOADBLOCK, INCINERATE, THRUST, SPIDER, PUDDLEJUMP (a pilot's controls are sliders and buttons of the
  * wired seat), the eyes (eyes.cpp), EXPLOSION, DUST, BULLET, HELD_BULLET, PLATFORM, BOTTLE; and for a world without
- * players RESPAWN and SCOREBOARD (the end of a round is handed to the host as an event of kind 6), HELD_GUN / HELD_BLINK
- * / HELD_JUMPER / BOTTLE_HELD (nothing unless the holder has inputs; counted as unsupported if it has), LEGG / LEGG_OLD,
- * FACTORY / FACTORY_WIRES / FLAG_SPAWNER (all but the creation of an entity, which is counted as unsupported).  PLAYER,
+ * players RESPAWN and SCOREBOARD (the end of a round is handed to the host as an event of kind 6), PLAYER (player.c:229-443:
+ * walking, jumping, looking, the equipment hands and drops), HELD_GUN / HELD_BLINK / HELD_JUMPER (cooldown and reload in
+ * a player's hand), BOTTLE_HELD, LEGG / LEGG_OLD, FACTORY / FACTORY_WIRES / FLAG_SPAWNER -- each of them up to the moment
+ * it would CREATE an entity (a shot, a stackem block, a platform, a product), which is counted as unsupported.
  * SPACETRASH, the editor's baubles and DEPLETE stay on the host.
  * Runs right after BT_PHASE_CTRLS.  Not part of BT_PHASE_ALL: a host that runs its own tick handlers must not get
  * them twice.  Fails with BT_ERR_UNSUPPORTED if the world holds any other tick handler (unless

@@ -1350,8 +1350,8 @@ static void worldRules(World *w, int g) {
 enum {
 	TICK_RAND = 6, TICK_LOGIC = 11, TICK_LOGIC_DEBUG = 12, TICK_DOOR = 13, TICK_CURSED = 14, TICK_RESPAWN = 15,
 	TICK_SEAT_OLD = 17, TICK_ADJUST = 19, TICK_SEAT = 23, TICK_SCOREBOARD = 27, TICK_TIMER = 28, TICK_DEMOLISH = 29, TICK_SIGN = 34,
-	TICK_LOADBLOCK = 35, TICK_PUDDLEJUMP = 36, TICK_SPIDER = 33, TICK_EYE = 8, TICK_HELD_EYE = 9, TICK_HELD_VEH_EYE = 18,
-	TICK_EXPLOSION = 1, TICK_PLATFORM = 3, TICK_THRUST = 10, TICK_BULLET = 25, TICK_HELD_BULLET = 26, TICK_DUST = 32, TICK_INCINERATE = 40, TICK_LEGG_OLD = 16, TICK_LEGG = 22, TICK_FACTORY = 20, TICK_FACTORY_WIRES = 21, TICK_FLAG_SPAWNER = 2
+	TICK_HELD_GUN = 24, TICK_HELD_BLINK = 30, TICK_HELD_JUMPER = 31, TICK_LOADBLOCK = 35, TICK_PUDDLEJUMP = 36, TICK_SPIDER = 33, TICK_EYE = 8, TICK_HELD_EYE = 9, TICK_HELD_VEH_EYE = 18,
+	TICK_EXPLOSION = 1, TICK_PLATFORM = 3, TICK_THRUST = 10, TICK_BULLET = 25, TICK_HELD_BULLET = 26, TICK_DUST = 32, TICK_INCINERATE = 40, TICK_LEGG_OLD = 16, TICK_LEGG = 22, TICK_FACTORY = 20, TICK_FACTORY_WIRES = 21, TICK_FLAG_SPAWNER = 2, TICK_PLAYER = 7
 };
 static int getButton(const World *w, i32 e, int i) { return (int)(signed char)w->btn[e][i]; }
 static void pushBtn(World *w, i32 e, int i) { w->btn[e][4 + i] = 1; }
@@ -1461,6 +1461,74 @@ static void legg_tick(World *w, i32 me, int old_style) {
 	v1[2] = bound1(v1[2], v_s);
 	acc[2] = bound1(v1[2] - vel[2], a);
 	for (int i = 0; i < 3; i++) w->d_vel[me][i] += acc[i];
+}
+
+/* player.c:229-443 without what creates entities (stackem blocks, platforms, baubles: the host's) */
+static int equipHands(World *w, i32 e) {
+	uint32_t f = w->type[e] & (T_EQUIP | T_EQUIP_SM);
+	if (!f) return 0;
+	if (f == (T_EQUIP | T_EQUIP_SM)) return 3;
+	return 1 + (getSlider(w, e, 0) != 0);
+}
+static void player_tick(World *w, int g, i32 me) {
+	int grounded = getSlider(w, me, 7) > 0;
+	uSlider(w, me, 7, 0);
+	i32 axis[2] = {getSlider(w, me, 0), getSlider(w, me, 1)}, sl[2] = {getSlider(w, me, 5), getSlider(w, me, 6)}, speed, vel[3];
+	if (!grounded) { boundVec(sl, 256, 2); speed = 256; }
+	else { speed = abs(sl[0]) > abs(sl[1]) ? abs(sl[0]) : abs(sl[1]); if (speed < 256) speed = 256; }
+	vel[2] = getButton(w, me, 0) && grounded ? -384 : 0;
+	for (int i = 0; i < 2; i++) vel[i] = speed * axis[i] / 64 - sl[i];
+	boundVec(vel, grounded ? 56 : 16, 2);
+	for (int i = 0; i < 2; i++) uSlider(w, me, 5 + i, sl[i] + vel[i]);
+	for (int i = 0; i < 3; i++) w->d_vel[me][i] += vel[i];
+	i32 charge = getSlider(w, me, 8), cooldown = getSlider(w, me, 9);
+	int fire = getButton(w, me, 2), fire2 = getButton(w, me, 3), utility = getButton(w, me, 1);
+	i32 other = getSlider(w, me, 12);
+	int altfire = (other & 1) != 0, altfire2 = (other & 2) != 0;
+	if (getSlider(w, me, 11)) {
+		for (int mode = 0; mode < 2; mode++) {
+			if (!(mode ? altfire2 : altfire)) continue;
+			for (i32 h = w->holdee[me]; h >= 0; h = w->LLn[h])
+				if ((w->type[h] & 64u) && w->wires[h].num == 1 && mode == getSlider(w, h, 0)) w->newDrop[h] = 1;
+		}
+		if (cooldown >= 3) {
+			if (utility && getButton(w, me, 0)) {
+				for (i32 h = w->holdee[me]; h >= 0; h = w->LLn[h])
+					if ((w->type[h] & 64u) && w->wires[h].num == 1) pushBtn(w, h, 2);
+				cooldown = 0;
+			} else if (fire || fire2) cooldown = 0;
+		}
+	} else {
+		int hands = 0, drops = 0;
+		for (i32 h = w->holdee[me]; h >= 0; h = w->LLn[h]) { int eh = equipHands(w, h); drops |= hands & eh; hands |= eh; }
+		i32 ep = getSlider(w, me, 10);
+		ep &= ~1;
+		if (altfire) { if (!(ep & 2)) { ep |= 2; drops |= 1; } } else ep &= ~2;
+		if (altfire2) { if (!(ep & 4)) { ep |= 4; drops |= 2; } } else ep &= ~4;
+		if (fire) { if (hands & 1) ep |= 8; } else ep &= ~8;
+		if (fire2) { if (hands & 2) ep |= 16; } else ep &= ~16;
+		uSlider(w, me, 10, ep);
+		i32 look[3] = {getSlider(w, me, 2), getSlider(w, me, 3), getSlider(w, me, 4)};
+		if (drops) {
+			if (drops & hands) {
+				for (i32 h = w->holdee[me]; h >= 0; h = w->LLn[h])
+					if (drops & equipHands(w, h)) {
+						for (int i = 0; i < 3; i++) { w->d_vel[h][i] += 200 * look[i] / 64; w->d_center[h][i] += 200 * look[i] / 64; }
+						w->newDrop[h] = 1;
+					}
+			} else {
+				for (i32 h = w->holdee[me]; h >= 0; h = w->LLn[h])
+					if (w->type[h] & (T_EQUIP | T_EQUIP_SM)) uSlider(w, h, 0, drops - 1);
+			}
+		}
+		if (hands == 3) return;
+		if (cooldown >= 5 && charge >= 60) {
+			if (fire && !(hands & 1) && !(ep & 8) && !(w->gamerules[g] & (1 << 7))) { charge -= 60; cooldown = 0; }
+			else if (charge >= 180 && fire2 && !(hands & 2) && !(ep & 16) && !(w->gamerules[g] & (1 << 8))) { charge -= 180; cooldown = 0; }
+		}
+	}
+	if (charge < 180) uSlider(w, me, 8, charge + 2);
+	if (cooldown < 5) uSlider(w, me, 9, cooldown + 1);
 }
 
 static void tickOne(World *w, int g, i32 me) {
@@ -1656,6 +1724,7 @@ static void tickOne(World *w, int g, i32 me) {
 		uSlider(w, me, 0, cooldown - 1);
 		break;
 	}
+	case TICK_PLAYER: player_tick(w, g, me); break;
 	case TICK_LEGG: legg_tick(w, me, 0); break;
 	case TICK_LEGG_OLD: legg_tick(w, me, 1); break;
 	case TICK_SPIDER: { /* spider.cpp:58-122 */
@@ -1742,7 +1811,39 @@ static void tickOne(World *w, int g, i32 me) {
 		w->ncollide[me] = T_TERRAIN;
 		break;
 	}
-	default: break; /* NIL, SIGN, HELD_GUN without a holder that has inputs (gun.c:43-44); other ids belong to the host */
+	case TICK_HELD_GUN: case TICK_HELD_BLINK: case TICK_HELD_JUMPER: {
+		/* gun.c:41-88, blink.c:33-60, jumper.c:39-70 up to where the trigger fires (entity creation: the host's) */
+		i32 h = w->holder[me];
+		if (h < 0 || !(w->type[h] & T_INPUTS) || w->holder[h] >= 0) break;
+		int trigger = getButton(w, h, 2 + (getSlider(w, me, 0) != 0)); /* getTrigger entGetters.c:27-29 */
+		if (id == TICK_HELD_GUN) {
+			i32 cooldown = getSlider(w, me, 2), ammo = getSlider(w, me, 1);
+			if (cooldown > 1) uSlider(w, me, 2, cooldown - 1);
+			else if (trigger && ammo) break;
+			i32 ammoMax = getSlider(w, me, 4);
+			if (ammo != ammoMax) {
+				i32 reload = getSlider(w, me, 3) + 1;
+				if (reload >= getSlider(w, me, 6)) { uSlider(w, me, 3, 0); uSlider(w, me, 1, ammoMax); }
+				else uSlider(w, me, 3, reload);
+			}
+		} else if (id == TICK_HELD_BLINK) {
+			i32 cooldown = getSlider(w, me, 1);
+			if (cooldown > 0) uSlider(w, me, 1, cooldown - 1);
+		} else {
+			i32 ammo = getSlider(w, me, 1);
+			if (ammo < getSlider(w, me, 4)) {
+				i32 reload = 1 + getSlider(w, me, 2);
+				if (reload >= getSlider(w, me, 5)) { reload = 0; ammo++; }
+				uSlider(w, me, 2, reload);
+			}
+			i32 cooldown = getSlider(w, me, 3);
+			if (cooldown > 0) uSlider(w, me, 3, cooldown - 1);
+			else if (ammo && trigger) break;
+			uSlider(w, me, 1, ammo);
+		}
+		break;
+	}
+	default: break; /* NIL, SIGN; other ids belong to the host */
 	}
 }
 

@@ -327,6 +327,25 @@ def lab_pilots(R):
     R.lab_set_sliders(lo, [0, 600, 250, 40, 60, 12, 8, 3])   # counter, height, stepHeight, tread, speed, accel, time, v_time
     R.lab_add_wire(lo, veye)
     script.append((0, REQ_PICKUP, wbody, lo, HOLD_MOVE, 0, 0))
+    # a player body (player.c) walked, jumped and made to drop / swap its equipment by scripted controls: sliders 0 / 1 = axis,
+    # 2..4 = look, 12 = the extra buttons (alt-fire 1 / 2), button 0 = jump.  It never fires: stackem blocks and platforms
+    # are entities somebody has to create
+    pad(R, -20000, -20000, r=(9000, 9000, 300), z=400)
+    pl = R.add_ent((-20000, -20000, -900), (0, 0, 0), (500, 500, 500), T_OBSTACLE | 256 | T_INPUTS, T_OBSTACLE | T_TERRAIN, 5)
+    R.lab_set_handlers(pl, push=1, pushed=5, pair=(-1, -1, 5, -1), tick=7)
+    R.lab_set_sliders(pl, [0, 0, 0, 64, 0, 0, 0, 0, 0, 0, 0, 0, 0])
+    gun = R.add_ent((-20000, -20000, -1500), (0, 0, 0), (120, 120, 120), CUBE | T_EQUIP, CUBE_COLLIDE, WM_WOOD)
+    R.lab_set_handlers(gun, tick_held=TICK_HELD_GUN)
+    R.lab_set_sliders(gun, [0, 5, 1, 0, 10, 3, 45, 14000])
+    charm = R.add_ent((-20300, -20000, -1500), (0, 0, 0), (80, 80, 80), CUBE | T_EQUIP_SM, CUBE_COLLIDE, WM_WOOD)
+    R.lab_set_handlers(charm, tick_held=31)      # a jumper (jumper.c): reloads and cools down in the hand, never triggered
+    R.lab_set_sliders(charm, [1, 0, 0, 5, 2, 20, 10, 300])
+    script += [(0, REQ_PICKUP, pl, gun, HOLD_DROP, 0, 0), (0, REQ_PICKUP, pl, charm, HOLD_DROP, 0, 0)]
+    for t, (ax, ay) in ((3, (64, 0)), (20, (0, -64)), (35, (0, 0)), (60, (-40, 40))):
+        script += [(t, REQ_SLIDER, pl, -1, 0, ax, 0), (t, REQ_SLIDER, pl, -1, 1, ay, 0)]
+    script += [(t, REQ_BUTTON, pl, -1, 0, 0, 0) for t in (10, 11, 12, 50, 51)]          # jump
+    script += [(40, REQ_SLIDER, pl, -1, 12, 1, 0), (44, REQ_SLIDER, pl, -1, 12, 0, 0)]      # alt-fire 1: the gun is thrown where it looks
+    script += [(55, REQ_SLIDER, pl, -1, 12, 1, 0), (58, REQ_SLIDER, pl, -1, 12, 0, 0)]      # again, hand 1 empty: the charm changes hands
     return 90, script, 0
 
 

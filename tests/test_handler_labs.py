@@ -165,7 +165,7 @@ def test_cuda_every_shipped_level_full_catalog(ref_lib, bt, level):
 
 
 # ---- shipped levels whose tick handlers all have device bodies: the FULL game tick on the device ----
-TICK_LEVELS = ["tower", "forest", "speed", "blank", "lights", "arena", "lobby", "spider", "run", "soccer", "forts", "ctf"]   # arena: + HELD_GUN (never held here), SCOREBOARD; lobby: + blink, jumper, loadblock, puddlejumper; spider: + its legs
+TICK_LEVELS = ["tower", "forest", "speed", "blank", "lights", "arena", "lobby", "spider", "run", "soccer", "forts", "ctf", "diner", "leggs"]   # arena: + HELD_GUN (never held here), SCOREBOARD; lobby: + blink, jumper, loadblock, puddlejumper; spider: + its legs
 EFFECT_BLOCKS = 4   # createDebris (effects.cpp:99-150) spawns platforms from gs->rand: host side, switched off here
 
 
