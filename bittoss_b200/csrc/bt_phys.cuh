@@ -1907,10 +1907,15 @@ static BT_HD void bt_player_tick(const DevWorld &W, i32 me, int id) {
 }
 
 /* one entity's tick / tickHeld handler.  Returns without effect for TICK_RAND and TICK_SCOREBOARD (serial pass). */
+static BT_HD void t_tick_id(const DevWorld &W, i32 me, u32 ht, int id);
 static BT_HD void t_tick(const DevWorld &W, i32 me) {
 	if (me >= W.n || !W.inList[me]) return;
 	u32 ht = W.htick[me];
 	int id = (int)(W.holder[me] >= 0 ? (ht >> 8) & 0xffu : ht & 0xffu);
+	if (id) t_tick_id(W, me, ht, id);
+}
+/* ... with the handler word and the id (tick or tickHeld, by whether it is held) already read by the caller */
+static BT_HD void t_tick_id(const DevWorld &W, i32 me, u32 ht, int id) {
 	switch (id) {
 	case 0: case TICK_SIGN: case TICK_RAND: return;
 	case TICK_LOGIC: case TICK_LOGIC_DEBUG: /* logic_tick logic.c:131-149 (the debug colour is not simulation state) */

@@ -96,6 +96,13 @@ __global__ void __launch_bounds__(BS, SW_MIN_WARPS * 32 / BS) k_tick_small(DevWo
 #define SW_IN(T, name)
 #define SW_OUT(T, name)
 #endif
+	/* whose tick handler runs (read up here so that the loads are under way while the state is staged; nothing before
+	 * the handlers themselves changes the word, the hold tree or the list) */
+	u32 tick_ht = 0, tick_id = 0;
+	if ((phases & BT_PHASE_TICKS) && mine && W.inList[e]) {
+		tick_ht = W.htick[e];
+		tick_id = W.holder[e] >= 0 ? (tick_ht >> 8) & 0xffu : tick_ht & 0xffu;
+	}
 	SW_STAGED(SW_DECL)
 	SW_STAGED(SW_IN)
 	const i32 rp0 = W.root_phase;
@@ -110,11 +117,9 @@ __global__ void __launch_bounds__(BS, SW_MIN_WARPS * 32 / BS) k_tick_small(DevWo
 	if (phases & BT_PHASE_TICKS) { /* doUpdates ent.cpp:826-832: handlers read what flushCtrls just published */
 		__syncthreads();
 		int rnd = 0;
-		if (mine && W.inList[e]) {
-			const u32 ht = W.htick[e];
-			const u32 id = W.holder[e] >= 0 ? (ht >> 8) & 0xffu : ht & 0xffu;
-			rnd = id < 64 && ((BT_SERIAL_TICK >> id) & 1ull); /* the serial pass has work */
-			t_tick(W, e);
+		if (tick_id) {
+			rnd = tick_id < 64 && ((BT_SERIAL_TICK >> tick_id) & 1ull); /* the serial pass has work */
+			t_tick_id(W, e, tick_ht, (int)tick_id);
 		}
 		if (__syncthreads_or(rnd) && i == 0) t_tick_serial(W, g); /* gs->rand draws in list order */
 	}
