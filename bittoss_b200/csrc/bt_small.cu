@@ -105,6 +105,16 @@ __global__ void __launch_bounds__(BS, SW_MIN_WARPS * 32 / BS) k_tick_small(DevWo
 	}
 	SW_STAGED(SW_DECL)
 	SW_STAGED(SW_IN)
+	/* the world's own words (death flip-flop, "flush1 has ordered work", roots keyed by the ordered lane): read once, up
+	 * here; the serial warp of every flush1 looks at them right behind a barrier, with the whole block waiting */
+	__shared__ i32 s_flip;
+	__shared__ u32 s_wrootseq;
+	__shared__ u8 s_wflush;
+	i32 *const g_flip = W.flip;
+	u32 *const g_wrootseq = W.wrootseq;
+	u8 *const g_wflush = W.wflush;
+	if (i == 0) { s_flip = g_flip[g]; s_wrootseq = g_wrootseq[g]; s_wflush = g_wflush[g]; }
+	W.flip = &s_flip - g; W.wrootseq = &s_wrootseq - g; W.wflush = &s_wflush - g;
 	const i32 rp0 = W.root_phase;
 	/* row i of the cyclic balanced triangle of k_pairs_small: j = i + 1 .. i + kmax (mod cnt) sees every unordered pair once */
 	const int kmax = (cnt - 1) / 2 + (((cnt & 1) == 0 && i < cnt / 2) ? 1 : 0);
@@ -283,6 +293,7 @@ __global__ void __launch_bounds__(BS, SW_MIN_WARPS * 32 / BS) k_tick_small(DevWo
 		if (sctr[CT_ORDER_TIES]) atomicAdd(&gctr[CT_ORDER_TIES], sctr[CT_ORDER_TIES]);
 		if (sctr[CT_TREE_EDITS]) atomicAdd(&gctr[CT_TREE_EDITS], sctr[CT_TREE_EDITS]);
 		if (sctr[CT_NEED_REBUILD]) gctr[CT_NEED_REBUILD] = 1;
+		g_flip[g] = s_flip; g_wrootseq[g] = s_wrootseq; g_wflush[g] = s_wflush;
 		u64 *s = W.stat + (blockIdx.x & (BT_STAT_ROWS - 1)) * SK_NUM;
 		if (iters) atomicAdd(&s[SK_ITERS], (u64)iters);
 		if (live) atomicAdd(&s[SK_ETICKS], (u64)live);
