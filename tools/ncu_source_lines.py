@@ -1,6 +1,7 @@
 """Samples and instructions of one kernel by source line, from `ncu --page source --csv` (SASS rows) and the line table of
 the same object (`cuobjdump -xelf all obj; nvdisasm -gi -c x.cubin > x.sass`): by call site in the kernel's own file
-(outermost inlined-at) and by innermost line.  python tools/ncu_source_lines.py source.csv x.sass kernel_file.cu [top]"""
+(outermost inlined-at) and by innermost line.
+python tools/ncu_source_lines.py source.csv x.sass kernel_file.cu [top [mangled kernel name, when x.sass holds several]]"""
 import collections
 import csv
 import re
@@ -9,12 +10,20 @@ import sys
 csv.field_size_limit(10 ** 9)
 src, sass, own = sys.argv[1:4]
 top = int(sys.argv[4]) if len(sys.argv) > 4 else 25
+only = sys.argv[5] if len(sys.argv) > 5 else None
 rows = list(csv.reader(open(src)))
 hdr, data = rows[1], rows[2:]
 base = int(data[0][0], 16)
 col = {k: hdr.index(k) for k in ("# Samples", "Instructions Executed", "Thread Instructions Executed", "stall_long_sb", "stall_barrier")}
 loc, cur, fresh = {}, [], True
+section = None
 for line in open(sass):
+    m = re.match(r"\s*\.section\s+\.text\.(\S+?),", line)
+    if m:
+        section = m.group(1)
+        continue
+    if only and section != only:
+        continue
     m = re.match(r'\s*//## File "([^"]+)", line (\d+)(?: inlined at "([^"]+)", line (\d+))?', line)
     if m:
         if fresh:
