@@ -26,9 +26,11 @@ static __device__ __forceinline__ void stat_add(const DevWorld &W, int which, u3
 	u32 s = warp_sum(v);
 	if ((threadIdx.x & 31) == 0 && s) atomicAdd(&W.stat[(blockIdx.x & (BT_STAT_ROWS - 1)) * SK_NUM + which], (u64)s);
 }
-/* "this iteration proposed something": one store per block, not one per warp (they all hit the same word) */
+/* "this iteration proposed something": a warp stores only while the word is not stamped yet (read at L2: every warp of
+ * the first iteration has something to say, and they all hit the same word).  No block-wide vote: warps that are done
+ * leave instead of holding their slots until the block's slowest is (k_narrow -6.6 %, tick 0.586 -> 0.567 ms at 1 M). */
 static __device__ __forceinline__ void stamp_any(const DevWorld &W, u32 any, int slot) {
-	if (__syncthreads_or((int)any) && threadIdx.x == 0) W.ctr[slot] = (u32)W.iter_id;
+	if (__any_sync(0xffffffffu, any) && (threadIdx.x & 31) == 0 && __ldcg(&W.ctr[slot]) != (u32)W.iter_id) W.ctr[slot] = (u32)W.iter_id;
 }
 static __device__ __forceinline__ void stats_flush(const DevWorld &W, const LocalStats &st) {
 	stat_add(W, SK_CAND, st.cand);
