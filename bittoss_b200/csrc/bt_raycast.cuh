@@ -259,8 +259,18 @@ __global__ void __launch_bounds__(128) k_raycast_dyn(DevWorld W, const i32 *orig
 			Rat eL = {0, 1}, eR = {0, 1};
 			int ovL = (wl & 0xffff) <= wp && wp <= (wl >> 16) && ray_hit_box(pos, look, flip, llo, lhi, best, &eL);
 			int ovR = (wr & 0xffff) <= wp && wp <= (wr >> 16) && ray_hit_box(pos, look, flip, rlo, rhi, best, &eR);
-			if (ovL && li < 0) RAY_LEAF(~li);
-			if (ovR && ri < 0) RAY_LEAF(~ri);
+			/* leaf children: ONE copy of the entity test for both sides, so that lanes with a left leaf and lanes with a
+			 * right one go through it together (a few lanes of a warp have one at any time, and the test is three
+			 * dependent gathers) */
+			i32 lf0 = -1, lf1 = -1;
+			if (ovL && li < 0) lf0 = ~li;
+			if (ovR && ri < 0) { if (lf0 < 0) lf0 = ~ri; else lf1 = ~ri; }
+#pragma unroll 1
+			while (lf0 >= 0) {
+				RAY_LEAF(lf0);
+				lf0 = lf1;
+				lf1 = -1;
+			}
 			int goL = ovL && li >= 0, goR = ovR && ri >= 0;
 			if (goL && goR) {
 				int rightFirst = rat_lt(eR, eL);
